@@ -1,0 +1,446 @@
+"""
+CPU ORACLE (test infrastructure, NOT product code) -- numpy/ctypes front end of judi_oracle.c.
+
+PARITY UNPINNED: see the header of judi_oracle.c.  Nothing under judi.jl_b200/ may import this.
+
+The classes/functions below restate, with the same names and argument meaning, the part of
+/root/reference/src/pysource that sits above the Devito operators:
+
+  Model                models.py:123-527  (padded grid :157-180, damp :54-120, params :301-326,
+                                           critical_dt :466-482, _cfl_coeff :440-456)
+  forward / born / gradient   propagators.py:15-230 (what they allocate, bind and return)
+  forward_rec / born_rec / J_adjoint / J_adjoint_standard / J_adjoint_checkpointing
+                              interface.py:17-47, 208-241, 279-345, 411-470, 473-562
+  Loss                 sensitivity.py:236-276
+  remove_padding / pad_array  src/TimeModeling/Utils/auxiliaryFunctions.jl:52-89
+  ricker_wavelet       src/TimeModeling/Utils/auxiliaryFunctions.jl:205-213
+
+Array conventions are pysource's: model arrays have shape (nx[,ny],nz); coordinates are
+(npoint, ndim) in metres; wavelets / shot records are (nt, ntrace).
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    """Compile the two oracle libraries with the committed Makefile."""
+    need = force or not all(os.path.exists(os.path.join(_HERE, "libjudi_oracle_%s.so" % p))
+                            for p in ("f32", "f64"))
+    src_m = os.path.getmtime(os.path.join(_HERE, "judi_oracle.c"))
+    for p in ("f32", "f64"):
+        f = os.path.join(_HERE, "libjudi_oracle_%s.so" % p)
+        if os.path.exists(f) and os.path.getmtime(f) < src_m:
+            need = True
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
+
+
+def _lib(precision):
+    if precision in _LIBS:
+        return _LIBS[precision]
+    path = os.path.join(_HERE, "libjudi_oracle_%s.so" % precision)
+    if not os.path.exists(path):
+        build()
+    lib = ctypes.CDLL(path)
+    real = ctypes.c_float if precision == "f32" else ctypes.c_double
+    P = ctypes.c_void_p
+    lib.oracle_create.restype = P
+    lib.oracle_create.argtypes = [ctypes.c_int, P, ctypes.c_int, P, P, real, P, P, P, real,
+                                  ctypes.c_int, P, real, P, real, P, real, P, real, P]
+    lib.oracle_destroy.argtypes = [P]
+    lib.oracle_sparse_create.restype = P
+    lib.oracle_sparse_create.argtypes = [P, ctypes.c_int, P]
+    lib.oracle_sparse_destroy.argtypes = [P]
+    lib.oracle_sparse_export.argtypes = [P, P, P, P]
+    lib.oracle_weights.argtypes = [P, P, P]
+    lib.oracle_forward.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P, P, P, ctypes.c_int,
+                                   ctypes.c_int, P, P]
+    lib.oracle_born.argtypes = [P, ctypes.c_int, P, P, P, P, P, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_int, P, P]
+    lib.oracle_gradient.argtypes = [P, ctypes.c_int, P, P, ctypes.c_int, ctypes.c_int, P, P, P]
+    lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
+    lib._real = real
+    lib._dtype = np.float32 if precision == "f32" else np.float64
+    _LIBS[precision] = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+IC = {"as": 0, "isic": 1, "fwi": 2}
+
+
+# --------------------------------------------------------------------------------------------
+# Host helpers (Julia side of the boundary)
+def ricker_wavelet(tmax, dt, f0, t0=None):
+    """auxiliaryFunctions.jl:205-213 (f0 in kHz, times in ms) -> (nt, 1) float32."""
+    tmax, dt, f0 = np.float32(tmax), np.float32(dt), np.float32(f0)
+    if t0 is None:
+        t0 = np.float32(0)
+    else:
+        tmax = np.float32(tmax - t0)
+    nt = int(np.floor(tmax / dt)) + 1
+    t = np.linspace(t0, tmax, nt, dtype=np.float32)
+    r = (np.float32(np.pi) * f0 * (t - np.float32(1) / f0)).astype(np.float32)
+    q = ((1 - 2 * r ** 2) * np.exp(-r ** 2)).astype(np.float32)
+    return q.reshape(nt, 1)
+
+
+def pad_array(m, nb, mode="border"):
+    """auxiliaryFunctions.jl:52-62."""
+    return np.pad(m, nb, mode="edge" if mode == "border" else "constant")
+
+
+def remove_padding(g, nb, true_adjoint=False):
+    """auxiliaryFunctions.jl:79-89: crop; true_adjoint first folds the pad into the edge."""
+    g = np.array(g, copy=True)
+    if true_adjoint:
+        for dim, (nbl, nbr) in enumerate(nb):
+            N = g.shape[dim]
+            sl = [slice(None)] * g.ndim
+
+            def sel(i):
+                s = list(sl)
+                s[dim] = i
+                return tuple(s)
+            g[sel(nbl)] += g[sel(slice(0, nbl))].sum(axis=dim)
+            g[sel(N - nbr - 1)] += g[sel(slice(N - nbr, N))].sum(axis=dim)
+    crop = tuple(slice(nbl, n - nbr) for (nbl, nbr), n in zip(nb, g.shape))
+    return g[crop]
+
+
+# --------------------------------------------------------------------------------------------
+def _damp_profile(npad, h):
+    """One side of models.py:74-94: values for the outer (npad-3) cells, outermost first."""
+    nb = npad - 3
+    if nb <= 0:
+        return np.zeros(0, dtype=np.float32)
+    coeff = np.float32(1.5 * np.log(1.0 / 0.001) / nb)
+    i = np.arange(nb, dtype=np.float32)
+    pos = np.abs((np.float32(nb) - i + np.float32(1)) / np.float32(nb)).astype(np.float32)
+    val = coeff * (pos - np.sin(np.float32(2 * np.pi) * pos) / np.float32(2 * np.pi))
+    return (val.astype(np.float32) / np.float32(h)).astype(np.float32)
+
+
+def damp_field(shape_pml, padsizes, spacing, fs=False):
+    """initialize_damp (models.py:99-120) with abc_type='damp': separable sum of 1-D profiles,
+    accumulated dimension by dimension in fp32 (left then right, like the Inc sequence)."""
+    damp = np.zeros(shape_pml, dtype=np.float32)
+    nd = len(shape_pml)
+    for d, ((nbl, nbr), h) in enumerate(zip(padsizes, spacing)):
+        shp = [1] * nd
+        if not fs or d != nd - 1:
+            prof = _damp_profile(nbl, h)
+            n = prof.size
+            if n:
+                shp[d] = n
+                sl = [slice(None)] * nd
+                sl[d] = slice(0, n)
+                damp[tuple(sl)] += prof.reshape(shp)
+        prof = _damp_profile(nbr, h)
+        n = prof.size
+        if n:
+            shp = [1] * nd
+            shp[d] = n
+            sl = [slice(None)] * nd
+            sl[d] = slice(shape_pml[d] - n, shape_pml[d])
+            damp[tuple(sl)] += prof[::-1].reshape(shp)
+    return damp
+
+
+def cfl_coeff(space_order, ndim):
+    """models.py:440-456 (acoustic / TTI branch), literally, with sympy."""
+    from sympy import finite_diff_weights as fd_w
+    so = max(space_order // 2, 4)
+    coeffs = fd_w(2, range(-so, so), 0)[-1][-1]
+    return .9 * np.sqrt(4 / float(ndim * sum(np.abs(np.array(coeffs, dtype=np.float64)))))
+
+
+class Model(object):
+    """Restatement of pysource models.Model for the acoustic / TTI families."""
+
+    def __init__(self, origin, spacing, shape, space_order=8, nbl=40, m=None, epsilon=None,
+                 delta=None, theta=None, phi=None, rho=None, b=None, dm=None, fs=False,
+                 dt=None, precision="f32"):
+        if fs:
+            raise NotImplementedError("free surface is a 'next' row (SURVEY 8f rank 3)")
+        self.shape = tuple(int(s) for s in shape)
+        self.dim = len(self.shape)
+        self.nbl = int(nbl)
+        self.fs = fs
+        self.space_order = int(space_order)
+        self.spacing = tuple(np.float32(s) for s in spacing)
+        self.origin = tuple(np.float32(o) for o in origin)
+        # models.py:172-177
+        self.origin_pml = tuple(np.float32(float(o) - float(s) * nbl)
+                                for o, s in zip(origin, spacing))
+        self.shape_pml = tuple(int(s + 2 * self.nbl) for s in self.shape)
+        self.precision = precision
+        self._dt = dt
+        self.damp = damp_field(self.shape_pml, self.padsizes, self.spacing, fs)
+        self.m = self._param(m)
+        # density (models.py:250-266): scalar -> Constant irho; array -> field irho = 1/rho
+        self.irho_field = None
+        self.irho_const = 1.0
+        if rho is not None:
+            if np.ndim(rho) == 0:
+                self.irho_const = float(np.reciprocal(np.float32(rho)))
+            else:
+                self.irho_field = self._param(np.reciprocal(np.asarray(rho, dtype=np.float32)))
+        elif b is not None:
+            if np.ndim(b) == 0:
+                self.irho_const = float(np.float32(b))
+            else:
+                self.irho_field = self._param(b)
+        self.dm = None if dm is None or (np.ndim(dm) == 0 and dm == 0) else self._param(dm)
+        self.is_tti = any(p is not None for p in (epsilon, delta, theta, phi))
+        self.tti = {}
+        self.scale = 1.0
+        if self.is_tti:
+            # models.py:216-225
+            eps = 1 if epsilon is None else 1 + 2 * np.asarray(epsilon, dtype=np.float32)
+            dlt = 1 if delta is None else 1 + 2 * np.asarray(delta, dtype=np.float32)
+            self._eps_max = float(np.max(eps))
+            for name, val, default in (("epsilon", eps, 1.0), ("delta", dlt, 1.0),
+                                       ("theta", theta, 0.0), ("phi", phi, 0.0)):
+                if name == "phi" and self.dim == 2:
+                    val = None
+                if val is None:
+                    self.tti[name] = (None, default)
+                elif np.ndim(val) == 0:
+                    self.tti[name] = (None, float(np.float32(val)))
+                else:
+                    self.tti[name] = (self._param(val), 0.0)
+        self._handle = None
+
+    def _param(self, field):
+        if field is None:
+            return None
+        field = np.asarray(field, dtype=np.float32)
+        if field.shape == self.shape_pml:
+            return np.ascontiguousarray(field)
+        assert field.shape == self.shape, (field.shape, self.shape)
+        return np.ascontiguousarray(np.pad(field, self.padsizes, mode="edge"))
+
+    @property
+    def padsizes(self):
+        p = [(self.nbl, self.nbl) for _ in range(self.dim - 1)]
+        p.append((0 if self.fs else self.nbl, self.nbl))
+        return tuple(p)
+
+    @property
+    def critical_dt(self):
+        """models.py:466-482."""
+        vmax = np.sqrt(1. / np.min(self.m))
+        scale = np.sqrt(1 + 2 * self._eps_max) if self.is_tti else 1
+        dt = cfl_coeff(self.space_order, self.dim) * np.min(self.spacing) / (scale * vmax)
+        dt = np.float32("%.3e" % dt)
+        if self._dt:
+            if self._dt <= dt:
+                return np.float32("%.3e" % self._dt)
+        return dt
+
+    # ---- C handle -------------------------------------------------------------------------
+    def handle(self):
+        if self._handle is not None:
+            return self._handle
+        lib = _lib(self.precision)
+        dt_ = lib._dtype
+        self._keep = []
+
+        def conv(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt_)
+            self._keep.append(a)
+            return a
+        N = np.array(self.shape_pml, dtype=np.int32)
+        h = np.array(self.spacing, dtype=dt_)
+        o = np.array(self.origin_pml, dtype=np.float32)
+        t = self.tti
+        g = lambda k, d: t.get(k, (None, d))
+        self._handle = lib.oracle_create(
+            self.dim, _ptr(N), self.space_order, _ptr(h), _ptr(o), lib._real(self.critical_dt),
+            _ptr(conv(self.m)), _ptr(conv(self.damp)), _ptr(conv(self.irho_field)),
+            lib._real(self.irho_const), int(self.is_tti),
+            _ptr(conv(g("epsilon", 1.0)[0])), lib._real(g("epsilon", 1.0)[1]),
+            _ptr(conv(g("delta", 1.0)[0])), lib._real(g("delta", 1.0)[1]),
+            _ptr(conv(g("theta", 0.0)[0])), lib._real(g("theta", 0.0)[1]),
+            _ptr(conv(g("phi", 0.0)[0])), lib._real(g("phi", 0.0)[1]),
+            _ptr(conv(self.dm)))
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib(self.precision).oracle_destroy(self._handle)
+        except Exception:
+            pass
+
+    @property
+    def lib(self):
+        return _lib(self.precision)
+
+    @property
+    def nfields(self):
+        return 2 if self.is_tti else 1
+
+
+class _Sparse(object):
+    def __init__(self, model, coords):
+        self.model = model
+        c = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, model.dim)
+        self.np = c.shape[0]
+        self.h = model.lib.oracle_sparse_create(model.handle(), self.np, _ptr(c))
+
+    def export(self):
+        nc = 2 ** self.model.dim
+        ijk = np.zeros((self.np, nc, 3), dtype=np.int32)
+        w = np.zeros((self.np, nc), dtype=np.float32)
+        valid = np.zeros((self.np, nc), dtype=np.int32)
+        self.model.lib.oracle_sparse_export(self.h, _ptr(ijk), _ptr(w), _ptr(valid))
+        return ijk, w, valid
+
+    def __del__(self):
+        try:
+            self.model.lib.oracle_sparse_destroy(self.h)
+        except Exception:
+            pass
+
+
+def sparse_locate(model, coords):
+    """(ijk, weights, valid) of every interpolation corner: the bit-exact indexing contract."""
+    return _Sparse(model, coords).export()
+
+
+def nsave(nt, t_sub):
+    """fields.py:141-144."""
+    return nt if t_sub == 1 else int(np.ceil((nt + t_sub) / t_sub))
+
+
+# --------------------------------------------------------------------------------------------
+# propagators.py
+def forward(model, src_coords, rcv_coords, wavelet, save=False, t_sub=1, illum=False, fw=True):
+    """propagators.py:15-89 -> (rec, usave, I)."""
+    lib, dt_ = model.lib, model.lib._dtype
+    nt = wavelet.shape[0]
+    src = _Sparse(model, src_coords) if src_coords is not None else None
+    rec = _Sparse(model, rcv_coords) if rcv_coords is not None else None
+    wav = np.ascontiguousarray(wavelet, dtype=dt_)
+    rec_out = np.zeros((nt, rec.np), dtype=dt_) if rec is not None else None
+    usave = None
+    if save:
+        usave = np.zeros((nsave(nt, t_sub), model.nfields) + model.shape_pml, dtype=dt_)
+    I = np.zeros(model.shape_pml, dtype=dt_) if illum else None
+    lib.oracle_forward(model.handle(), int(fw), nt, src.h if src else None, _ptr(wav),
+                       rec.h if rec else None, _ptr(rec_out), int(bool(save)), int(t_sub),
+                       _ptr(usave), _ptr(I))
+    return rec_out, usave, I
+
+
+def born(model, src_coords, rcv_coords, wavelet, save=False, ic="as", t_sub=1, nlind=False,
+         illum=False):
+    """propagators.py:155-230 -> ((recl, recnl) if nlind else recl, usave, I)."""
+    lib, dt_ = model.lib, model.lib._dtype
+    nt = wavelet.shape[0]
+    if model.dm is None:
+        # propagators.py:181-194: zero perturbation -> plain forward, linearised data stay zero
+        rnl, usave, I = forward(model, src_coords, rcv_coords, wavelet, save=save, t_sub=t_sub,
+                                illum=illum)
+        recl = np.zeros_like(rnl)
+        return ((recl, rnl) if nlind else recl), usave, I
+    src = _Sparse(model, src_coords)
+    rec = _Sparse(model, rcv_coords)
+    wav = np.ascontiguousarray(wavelet, dtype=dt_)
+    recl = np.zeros((nt, rec.np), dtype=dt_)
+    recnl = np.zeros((nt, rec.np), dtype=dt_) if nlind else None
+    usave = None
+    if save:
+        usave = np.zeros((nsave(nt, t_sub), model.nfields) + model.shape_pml, dtype=dt_)
+    I = np.zeros(model.shape_pml, dtype=dt_) if illum else None
+    rc = lib.oracle_born(model.handle(), nt, src.h, _ptr(wav), rec.h, _ptr(recl), _ptr(recnl),
+                         IC[ic], int(bool(save)), int(t_sub), _ptr(usave), _ptr(I))
+    assert rc == 0
+    return ((recl, recnl) if nlind else recl), usave, I
+
+
+def gradient(model, residual, rcv_coords, usave, t_sub=1, ic="as", illum=False):
+    """propagators.py:98-152 -> (gradm on the padded grid, Iv)."""
+    lib, dt_ = model.lib, model.lib._dtype
+    nt = residual.shape[0]
+    rec = _Sparse(model, rcv_coords)
+    res = np.ascontiguousarray(residual, dtype=dt_)
+    g = np.zeros(model.shape_pml, dtype=dt_)
+    I = np.zeros(model.shape_pml, dtype=dt_) if illum else None
+    us = np.ascontiguousarray(usave, dtype=dt_)
+    lib.oracle_gradient(model.handle(), nt, rec.h, _ptr(res), IC[ic], int(t_sub), _ptr(us),
+                        _ptr(g), _ptr(I))
+    return g, I
+
+
+# --------------------------------------------------------------------------------------------
+# sensitivity.py:236-276
+def Loss(dsyn, dobs, dt, is_residual=False, misfit=None):
+    if misfit is not None:
+        if isinstance(dsyn, tuple):
+            f, r = misfit(dsyn[0], dobs - dsyn[1])
+            return dt * f, r
+        f, r = misfit(dsyn, dobs)
+        return dt * f, r
+    if not is_residual:
+        if isinstance(dsyn, tuple):
+            r = dsyn[0] - (dobs - dsyn[1])
+            return .5 * dt * np.linalg.norm(r) ** 2, r
+        r = dsyn - dobs
+    else:
+        r = np.array(dobs, dtype=dsyn[0].dtype if isinstance(dsyn, tuple) else dsyn.dtype)
+    return .5 * dt * np.linalg.norm(r) ** 2, r
+
+
+# --------------------------------------------------------------------------------------------
+# interface.py
+def forward_rec(model, src_coords, wavelet, rec_coords, illum=False, fw=True):
+    rec, _, I = forward(model, src_coords, rec_coords, wavelet, save=False, illum=illum, fw=fw)
+    return rec, I
+
+
+def born_rec(model, src_coords, wavelet, rec_coords, ic="as", illum=False):
+    rec, _, I = born(model, src_coords, rec_coords, wavelet, save=False, ic=ic, illum=illum)
+    return rec, I
+
+
+def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
+              checkpointing=False, n_checkpoints=None, t_sub=1, return_obj=False, ic="as",
+              illum=False, born_fwd=False, nlind=False, misfit=None):
+    """interface.py:279-345 + :411-470.  Checkpointing (interface.py:473-562) recomputes the
+    forward wavefield instead of storing it, so its result equals the t_sub=1 standard path;
+    the oracle evaluates it that way."""
+    if checkpointing:
+        t_sub = 1
+    if born_fwd:
+        rec, u, Iu = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind,
+                          illum=illum, ic=ic, t_sub=t_sub)
+    else:
+        rec, u, Iu = forward(model, src_coords, rec_coords, wavelet, save=True, illum=illum,
+                             t_sub=t_sub)
+    f, residual = Loss(rec, recin, float(model.critical_dt), is_residual=is_residual,
+                       misfit=misfit)
+    g, Iv = gradient(model, residual, rec_coords, u, t_sub=t_sub, ic=ic, illum=illum)
+    if return_obj:
+        return f, g, Iu, Iv
+    return g, Iu, Iv
+
+
+def time_steps(model, nsteps, with_gradient=True, t_sub=1):
+    """Bounded CPU-baseline sample (bench.py only): seconds for nsteps fwd (+ nsteps adj+IC)."""
+    s = ctypes.c_double(0)
+    model.lib.oracle_time_steps(model.handle(), int(nsteps), int(with_gradient), int(t_sub),
+                                ctypes.byref(s))
+    return s.value
