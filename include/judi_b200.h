@@ -1,0 +1,168 @@
+/*
+ * judi_b200.h -- C-ABI of libjudi_b200.so: B200-native (sm_100a) finite-difference wave
+ * propagators that replace JUDI's `src/pysource` + Devito hot path.
+ *
+ * Every entry point below replaces one reference interface (paths relative to the reference
+ * repository slimgroup/JUDI.jl v4.1.7).  The Julia driver reaches the reference through
+ * `wrapcall_data(ac.<fn>, modelPy, ...)` (src/TimeModeling/Modeling/python_interface.jl:9-27);
+ * the binding a maintainer adds instead is a `ccall` per function -- see INTEGRATION.md.
+ *
+ * Conventions (chosen so Julia arrays are passed as they are, without copies):
+ *   - grids (m, rho, dm, gradients, illumination): fp32, x fastest (Julia column-major
+ *     Array{Float32,N} of size n / padded size), i.e. element (ix,iy,iz) at ix + nx*(iy + ny*iz);
+ *   - coordinates: `hcat(x[,y],z)` column-major (auxiliaryFunctions.jl:319-321), i.e. SoA
+ *     coords[d*npoint + p], absolute metres, fp32;
+ *   - traces (wavelets, shot records, residuals): (nt x ntrace) column-major, i.e. time fastest:
+ *     data[p*nt + t];
+ *   - all functions return 0 on success, non-zero on failure with the message available from
+ *     judi_last_error() (thread local).  The Julia wrapper turns non-zero into `error(...)`, so the
+ *     reference's `retry` wrapper (time_modeling_serial.jl:95, misfit_fg.jl:91) keeps working.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef JUDI_B200_H
+#define JUDI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JUDI_B200_ABI_VERSION 1
+
+typedef struct judi_ctx judi_ctx;     /* one per (process, GPU): stream, memory pool          */
+typedef struct judi_model judi_model; /* padded physical model resident in HBM                */
+
+/* how a physical parameter is given (pysource Model accepts array | scalar | None,
+ * src/pysource/models.py:301-326) */
+enum { JUDI_PARAM_NONE = 0, JUDI_PARAM_SCALAR = 1, JUDI_PARAM_ARRAY = 2 };
+typedef struct {
+    int kind;          /* JUDI_PARAM_* */
+    float value;       /* used when kind == JUDI_PARAM_SCALAR */
+    const float *data; /* used when kind == JUDI_PARAM_ARRAY: prod(shape) floats, x fastest */
+} judi_param;
+
+/* replaces `pm.Model(origin, spacing, shape; nbl, space_order, dt, fs, dm, m=, rho=, ...)`
+ * (src/TimeModeling/Utils/auxiliaryFunctions.jl:26-37 -> src/pysource/models.py:157-248) */
+typedef struct {
+    int ndim;         /* 2 or 3 */
+    int shape[3];     /* n: (nx, nz) or (nx, ny, nz) */
+    float spacing[3]; /* d, metres */
+    float origin[3];  /* o, metres */
+    int nbl;          /* absorbing layer width in cells */
+    int space_order;  /* 4, 8 or 16 */
+    int fs;           /* free surface (not supported yet: returns an error) */
+    float dt;         /* user dt_comp (ms); <= 0 means "use the CFL value" */
+    judi_param m;     /* squared slowness s^2/km^2 (required) */
+    judi_param rho;   /* density; scalar -> constant-density Laplacian, array -> div(1/rho grad) */
+    judi_param b;     /* buoyancy 1/rho (alternative to rho) */
+    judi_param epsilon, delta, theta, phi; /* Thomsen / tilt / azimuth: any present => TTI */
+    judi_param dm;    /* squared-slowness perturbation for Born modelling */
+    int params_on_device; /* 1: the `data` pointers are device pointers (inputs resident in HBM) */
+} judi_model_desc;
+
+/* imaging condition, src/pysource/sensitivity.py:231-233 */
+enum { JUDI_IC_AS = 0, JUDI_IC_ISIC = 1, JUDI_IC_FWI = 2 };
+
+/* flags of the propagation calls */
+enum {
+    JUDI_DATA_ON_DEVICE = 1, /* wavelet / recin / rec_out / grad_out / illum pointers are device
+                                pointers (same layouts); coordinates are always host pointers */
+    JUDI_GRAD_ACCUMULATE = 2 /* grad_out += g and *f_out += f instead of overwriting: the local
+                                reduction of src/TimeModeling/Modeling/distributed.jl:6-22 */
+};
+
+/* where forward-wavefield snapshots are kept for the imaging condition */
+enum {
+    JUDI_SNAP_PADDED = 0,  /* whole padded grid: reference semantics, gradient defined in the
+                              absorbing layer too (needed by Options(sum_padding=true)) */
+    JUDI_SNAP_PHYSICAL = 1 /* physical domain only: the returned gradient is zero in the layer,
+                              which `remove_padding` crops anyway (auxiliaryFunctions.jl:79-89) */
+};
+
+/* options of J_adjoint: the keyword arguments of src/pysource/interface.py:279-282 that this
+ * path supports (freq_list/dft_sub/ws are out of scope) */
+typedef struct {
+    int is_residual;   /* recin is already the residual (J' as an operator, python_interface.jl:119) */
+    int checkpointing; /* Options(optimal_checkpointing): recompute segments from HBM checkpoints */
+    int n_checkpoints; /* <= 0: choose from free HBM */
+    int t_sub;         /* Options(subsampling_factor) */
+    int ic;            /* JUDI_IC_* */
+    int born_fwd;      /* lsrtm_objective: linearised forward (interface.py:565) */
+    int nlind;         /* remove the non-linear data (only with born_fwd) */
+    int illum;         /* also return illumination of u and v */
+    int snapshot_region; /* JUDI_SNAP_* */
+} judi_jopts;
+
+/* optional host misfit callback, replaces `misfit=pyjl(runtime_misfit)`
+ * (src/TimeModeling/Modeling/misfit_fg.jl:55-64, src/pysource/sensitivity.py:255-263):
+ * given synthetic and observed data (nt x nrec, time fastest) it writes the adjoint source into
+ * `residual` and returns the objective value (the library multiplies it by dt like the reference).
+ * NULL selects the on-device L2 misfit of src/TimeModeling/Modeling/losses.jl:15-19. */
+typedef float (*judi_misfit_fn)(const float *dsyn, const float *dobs, float *residual, int nt,
+                                int nrec, void *user);
+
+/* ---- context --------------------------------------------------------------------------- */
+int judi_abi_version(void);
+const char *judi_last_error(void);
+judi_ctx *judi_ctx_create(int device);
+void judi_ctx_destroy(judi_ctx *ctx);
+int judi_ctx_synchronize(judi_ctx *ctx);
+void *judi_ctx_stream(judi_ctx *ctx); /* the cudaStream_t all work of this context runs on */
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long long judi_ctx_launch_count(judi_ctx *ctx);
+/* accumulated device time (ms, CUDA events on the context stream) of the stencil kernels, and
+ * the number of stencil launches and grid-point updates they covered; reset clears them */
+int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, double *points);
+int judi_ctx_reset_stats(judi_ctx *ctx);
+/* tuning knobs: "acoustic3d_kernel" (0 generic, 1 TMA z-marching), "zchunks", ... */
+int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value);
+
+/* ---- model ----------------------------------------------------------------------------- */
+judi_model *judi_model_create(judi_ctx *ctx, const judi_model_desc *desc);
+void judi_model_destroy(judi_model *model);
+/* modelPy.critical_dt (models.py:466-482; read at python_interface.jl:33, misfit_fg.jl:40) */
+float judi_model_critical_dt(const judi_model *model);
+/* modelPy.padsizes (models.py:269-272): out[2*d] = left, out[2*d+1] = right */
+int judi_model_padsizes(const judi_model *model, int *out);
+/* padded grid shape (Devito grid.shape, models.py:173) */
+int judi_model_padded_shape(const judi_model *model, int *out);
+/* replace the perturbation dm of an existing model (born / lsrtm with a new dm) */
+int judi_model_set_dm(judi_model *model, const judi_param *dm, int on_device);
+/* the padded damping field (models.py:54-120) and padded m, for tests: out is padded-grid sized */
+int judi_model_get_field(const judi_model *model, const char *name, float *out);
+
+/* ---- sparse geometry: bit-exact indexing contract ---------------------------------------- */
+/* corner cells and weights of Devito's linear SparseTimeFunction for `npoint` coordinates
+ * (src/pysource/geom_utils.py:74-94).  ijk: [npoint][2^ndim][3] ints (x,y,z; y = 0 in 2-D),
+ * w: [npoint][2^ndim] floats, valid: [npoint][2^ndim] ints (0 = corner outside the padded grid) */
+int judi_sparse_locate(const judi_model *model, int npoint, const float *coords, int *ijk,
+                       float *w, int *valid);
+
+/* ---- propagators (src/pysource/interface.py) --------------------------------------------- */
+/* forward_rec (interface.py:17-47; called at python_interface.jl:42): rec = Pr*F*Ps'*q, or the
+ * adjoint F' with fw = 0.  illum_out (padded grid) may be NULL. */
+int judi_forward_rec(judi_model *model, int fw, int nsrc, const float *src_coords,
+                     const float *wavelet, int nt, int nrec, const float *rec_coords,
+                     float *rec_out, float *illum_out, int flags);
+
+/* born_rec (interface.py:208-241; python_interface.jl:97): d_lin = J*dm with the model's dm */
+int judi_born_rec(judi_model *model, int nsrc, const float *src_coords, const float *wavelet,
+                  int nt, int nrec, const float *rec_coords, int ic, float *rec_out,
+                  float *illum_out, int flags);
+
+/* J_adjoint (interface.py:279-345 -> :411-470 standard, :473-562 checkpointing; called at
+ * python_interface.jl:116-120 and misfit_fg.jl:69-73).  f_out may be NULL (return_obj=false).
+ * grad_out / illum_u / illum_v are padded-grid sized (the caller crops with remove_padding). */
+int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const float *wavelet,
+                   int nt, int nrec, const float *rec_coords, const float *recin,
+                   const judi_jopts *opts, judi_misfit_fn misfit, void *user, float *f_out,
+                   float *grad_out, float *illum_u, float *illum_v, int flags);
+
+/* forward_no_rec (interface.py:83-111; python_interface.jl:56): the full wavefield history,
+ * u_out is nt x padded grid (time slowest).  TTI returns the first field like the reference. */
+int judi_forward_no_rec(judi_model *model, int fw, int nsrc, const float *src_coords,
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUDI_B200_H */

@@ -1,0 +1,293 @@
+// capi.cu -- the extern "C" boundary declared in include/judi_b200.h.
+// Every function converts C++ exceptions into a non-zero return code + judi_last_error().
+#include "common.cuh"
+#include "propagate.h"
+
+static thread_local std::string g_last_error;
+
+#define API_BEGIN try {
+#define API_END(ret_fail)                                   \
+    }                                                       \
+    catch (const std::exception &e) {                       \
+        g_last_error = e.what();                            \
+        return ret_fail;                                    \
+    }                                                       \
+    catch (...) {                                           \
+        g_last_error = "unknown C++ exception";             \
+        return ret_fail;                                    \
+    }
+
+extern "C" {
+
+int judi_abi_version(void) { return JUDI_B200_ABI_VERSION; }
+
+const char *judi_last_error(void) { return g_last_error.c_str(); }
+
+judi_ctx *judi_ctx_create(int device)
+{
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw JudiError("no CUDA device available: libjudi_b200 has no CPU fallback");
+    JUDI_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        throw JudiError(std::string("libjudi_b200 is built for sm_100a (B200) only; found ") +
+                        prop.name);
+    judi_ctx *ctx = new judi_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&ctx->pool, device));
+    unsigned long long thresh = ~0ull;  // keep freed blocks: shots reuse the same buffers
+    CUDA_CHECK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    cudaDriverEntryPointQueryResult qres;
+    void *fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) ctx->encode_tiled = fn;
+    else cudaGetLastError();
+    return ctx;
+    API_END(nullptr)
+}
+
+void judi_ctx_destroy(judi_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto e : ctx->free_events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int judi_ctx_synchronize(judi_ctx *ctx)
+{
+    API_BEGIN
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+    API_END(1)
+}
+
+void *judi_ctx_stream(judi_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+long long judi_ctx_launch_count(judi_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, double *points)
+{
+    API_BEGIN
+    ctx->flush_timing();
+    if (ms) *ms = ctx->stencil_ms;
+    if (launches) *launches = ctx->stencil_launches;
+    if (points) *points = ctx->stencil_points;
+    return 0;
+    API_END(1)
+}
+
+int judi_ctx_reset_stats(judi_ctx *ctx)
+{
+    API_BEGIN
+    ctx->flush_timing();
+    ctx->stencil_ms = 0;
+    ctx->stencil_launches = 0;
+    ctx->stencil_points = 0;
+    ctx->launches = 0;
+    return 0;
+    API_END(1)
+}
+
+int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value)
+{
+    API_BEGIN
+    std::string k(key);
+    if (k == "acoustic3d_kernel") ctx->opt_kernel3d = value;
+    else if (k == "zchunks") ctx->opt_zchunks = value;
+    else if (k == "tile") ctx->opt_tile = value;
+    else if (k == "atomic_inject") ctx->opt_atomic_inject = value;
+    else if (k == "timing") ctx->timing = value;
+    else throw JudiError("unknown option " + k);
+    return 0;
+    API_END(1)
+}
+
+judi_model *judi_model_create(judi_ctx *ctx, const judi_model_desc *desc)
+{
+    judi_model *M = nullptr;
+    try {
+        JUDI_REQUIRE(ctx != nullptr && desc != nullptr, "null argument");
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        M = new judi_model();
+        model_build(M, ctx, desc);
+        return M;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        delete M;
+        return nullptr;
+    }
+}
+
+void judi_model_destroy(judi_model *model)
+{
+    if (!model) return;
+    cudaStreamSynchronize(model->ctx->stream);
+    delete model;
+}
+
+float judi_model_critical_dt(const judi_model *model) { return model ? model->dt : 0.f; }
+
+int judi_model_padsizes(const judi_model *model, int *out)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && out, "null argument");
+    const int dm2[2] = {0, 2};
+    for (int k = 0; k < model->ndim; k++) {
+        int gd = model->ndim == 3 ? k : dm2[k];
+        out[2 * k] = model->padl[gd];
+        out[2 * k + 1] = model->padr[gd];
+    }
+    return 0;
+    API_END(1)
+}
+
+int judi_model_padded_shape(const judi_model *model, int *out)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && out, "null argument");
+    const int dm2[2] = {0, 2};
+    for (int k = 0; k < model->ndim; k++) out[k] = model->N[model->ndim == 3 ? k : dm2[k]];
+    return 0;
+    API_END(1)
+}
+
+int judi_model_set_dm(judi_model *model, const judi_param *dm, int on_device)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && dm, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    if (dm->kind == JUDI_PARAM_NONE || (dm->kind == JUDI_PARAM_SCALAR && dm->value == 0.f)) {
+        model->has_dm = false;
+        return 0;
+    }
+    model_set_param(model, model->dm, *dm, on_device, 0.f, true);
+    model->has_dm = true;
+    CUDA_CHECK(cudaStreamSynchronize(model->ctx->stream));
+    return 0;
+    API_END(1)
+}
+
+__global__ void damp_field_kernel(Grid g, const float *dx, const float *dy, const float *dz,
+                                  float *out)
+{
+    long long n = (long long)g.n[0] * g.n[1] * g.n[2];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = (int)(i % g.n[0]);
+    long long t = i / g.n[0];
+    int y = (int)(t % g.n[1]), z = (int)(t / g.n[1]);
+    out[i] = (dx[x] + dy[y]) + dz[z];
+}
+
+int judi_model_get_field(const judi_model *model, const char *name, float *out)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && name && out, "null argument");
+    judi_ctx *ctx = model->ctx;
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::string k(name);
+    const float *f = nullptr;
+    if (k == "m") f = model->m.p;
+    else if (k == "irho") f = model->irho.p;
+    else if (k == "epsilon") f = model->eps.p;
+    else if (k == "delta") f = model->delta.p;
+    else if (k == "theta") f = model->theta.p;
+    else if (k == "phi") f = model->phi.p;
+    else if (k == "dm") f = model->dm.p;
+    else if (k == "damp") {
+        long long n = (long long)model->N[0] * model->N[1] * model->N[2];
+        DevBuf tmp(ctx, (size_t)n, false);
+        damp_field_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            model->g, model->damp[0].p, model->damp[1].p, model->damp[2].p, tmp.p);
+        launch_count(ctx, "damp_field");
+        CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    } else throw JudiError("unknown field " + k);
+    JUDI_REQUIRE(f != nullptr, "field not present in this model");
+    grid_output(model, f, out, false);
+    return 0;
+    API_END(1)
+}
+
+int judi_sparse_locate(const judi_model *model, int npoint, const float *coords, int *ijk, float *w,
+                       int *valid)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && coords && ijk && w && valid, "null argument");
+    std::vector<int> vi, vv;
+    std::vector<float> vw;
+    sparse_locate_host(model, npoint, coords, vi, vw, vv);
+    memcpy(ijk, vi.data(), vi.size() * sizeof(int));
+    memcpy(w, vw.data(), vw.size() * sizeof(float));
+    memcpy(valid, vv.data(), vv.size() * sizeof(int));
+    return 0;
+    API_END(1)
+}
+
+int judi_forward_rec(judi_model *model, int fw, int nsrc, const float *src_coords,
+                     const float *wavelet, int nt, int nrec, const float *rec_coords,
+                     float *rec_out, float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && src_coords && wavelet, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    run_forward_rec(model, fw, nsrc, src_coords, wavelet, nt, nrec, rec_coords, rec_out, illum_out,
+                    flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_forward_no_rec(judi_model *model, int fw, int nsrc, const float *src_coords,
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && src_coords && wavelet && u_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    run_forward_no_rec(model, fw, nsrc, src_coords, wavelet, nt, u_out, illum_out, flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_born_rec(judi_model *model, int nsrc, const float *src_coords, const float *wavelet,
+                  int nt, int nrec, const float *rec_coords, int ic, float *rec_out,
+                  float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && src_coords && wavelet && rec_coords && rec_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    run_born_rec(model, nsrc, src_coords, wavelet, nt, nrec, rec_coords, ic, rec_out, illum_out,
+                 flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const float *wavelet,
+                   int nt, int nrec, const float *rec_coords, const float *recin,
+                   const judi_jopts *opts, judi_misfit_fn misfit, void *user, float *f_out,
+                   float *grad_out, float *illum_u, float *illum_v, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && src_coords && wavelet && rec_coords && recin && opts && grad_out,
+                 "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    judi_jopts o = *opts;
+    if (!o.illum) { illum_u = nullptr; illum_v = nullptr; }
+    run_J_adjoint(model, nsrc, src_coords, wavelet, nt, nrec, rec_coords, recin, &o, misfit, user,
+                  f_out, grad_out, illum_u, illum_v, flags);
+    return 0;
+    API_END(1)
+}
+
+}  // extern "C"

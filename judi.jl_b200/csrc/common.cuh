@@ -1,0 +1,245 @@
+// common.cuh -- shared host/device declarations of libjudi_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/judi_b200.h"
+
+#define JUDI_MAXR 8       // space_order <= 16
+#define JUDI_HALO 8       // zero halo (cells) kept around every padded-grid field in y and z
+#define JUDI_HALO_XL 32   // left x halo: keeps domain point x=0 128-byte aligned
+#define JUDI_HALO_XR 8
+
+// ------------------------------------------------------------------------------------------
+// Device layout of one padded-grid scalar field: x fastest (Julia's native order), zero halo.
+struct Grid {
+    int ndim;
+    int n[3];          // padded-domain points along x, y, z (n[1] == 1 in 2-D)
+    int hx, hy, hz;    // index of the first domain point inside the allocation
+    int px, py, pz;    // allocated extents
+    long long sy, sz;  // strides (elements) of y and z
+    long long off0;    // element offset of domain point (0,0,0)
+    long long nalloc;  // elements allocated
+    __host__ __device__ inline long long at(int x, int y, int z) const {
+        return off0 + x + (long long)y * sy + (long long)z * sz;
+    }
+};
+
+// Box of the padded grid over which snapshots / gradient / illumination are produced, with the
+// compact layout they are stored in (x fastest, pitch multiple of 4, no halo).
+struct Region {
+    int lo[3], hi[3];  // [lo, hi) in padded-domain coordinates
+    int ext[3];        // hi - lo
+    int pitch;         // x pitch of the compact layout
+    long long slot;    // elements per field per snapshot slot
+    __host__ __device__ inline long long at(int x, int y, int z) const {
+        return (x - lo[0]) + (long long)pitch * ((y - lo[1]) + (long long)ext[1] * (z - lo[2]));
+    }
+    __host__ __device__ inline bool has(int x, int y, int z) const {
+        return x >= lo[0] && x < hi[0] && y >= lo[1] && y < hi[1] && z >= lo[2] && z < hi[2];
+    }
+};
+
+// Coefficients shared by every stencil kernel (passed by value: kernel parameters live in the
+// constant bank, so these are uniform loads).
+struct Coefs {
+    int r;                      // space_order / 2
+    float c0;                   // sum over dims of dt^2 * c2[0] / h_d^2
+    float cx[JUDI_MAXR + 1];    // dt^2 * c2[k] / hx^2   (centred 2nd derivative, k = 1..r)
+    float cy[JUDI_MAXR + 1];
+    float cz[JUDI_MAXR + 1];
+    float wx[JUDI_MAXR + 1];    // w1[k] / hx            (staggered 1st derivative, k = 1..r)
+    float wy[JUDI_MAXR + 1];
+    float wz[JUDI_MAXR + 1];
+    float dt, dt2, idt, idt2;
+};
+
+// What the update epilogue fuses besides the leapfrog step (all optional).
+struct Fuse {
+    float *snap[2];         // SAVE: snapshot slot(s) to write level t into (forward)
+    const float *usnap[2];  // IC:   snapshot slot(s) of the forward field(s) (adjoint)
+    float *grad;            // IC:   gradient accumulator (region layout)
+    float *illum;           // ILLUM: illumination accumulator (region layout)
+    float gcoef;            // IC:   t_sub / dt  (multiplied by irho in the kernel)
+    int ic;                 // JUDI_IC_*
+    Region reg;
+};
+
+// ------------------------------------------------------------------------------------------
+// error handling: C++ exceptions inside the library, converted to return codes at the C-ABI
+struct JudiError : public std::runtime_error {
+    explicit JudiError(const std::string &s) : std::runtime_error(s) {}
+};
+
+#define CUDA_CHECK(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            char _b[512];                                                                    \
+            snprintf(_b, sizeof(_b), "CUDA error %s (%s) at %s:%d", cudaGetErrorName(_e),    \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                            \
+            throw JudiError(_b);                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define JUDI_REQUIRE(cond, msg)                                                              \
+    do {                                                                                     \
+        if (!(cond)) throw JudiError(std::string(msg) + " [" #cond "]");                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+struct judi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    long long launches = 0;
+    // stencil timing (CUDA events on `stream`)
+    int timing = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> free_events;
+    double stencil_ms = 0;
+    long long stencil_launches = 0;
+    double stencil_points = 0;
+    // options
+    int opt_kernel3d = 1;       // 0 generic, 1 TMA z-marching
+    int opt_zchunks = 0;        // 0 = auto
+    int opt_tile = 0;           // TMA kernel tile variant
+    int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
+    int num_sms = 148;
+    void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
+
+    void *alloc_bytes(size_t nbytes, bool zero = true);
+    float *alloc(size_t nfloat, bool zero = true) {
+        return (float *)alloc_bytes(nfloat * sizeof(float), zero);
+    }
+    void free(void *p);
+    void flush_timing();
+};
+
+// RAII device buffer on the context's stream-ordered pool
+template <typename T>
+struct DevArr {
+    judi_ctx *ctx = nullptr;
+    T *p = nullptr;
+    size_t n = 0;
+    DevArr() {}
+    DevArr(judi_ctx *c, size_t count, bool zero = true) : ctx(c), n(count) {
+        p = (T *)c->alloc_bytes(count * sizeof(T), zero);
+    }
+    DevArr(const DevArr &) = delete;
+    DevArr &operator=(const DevArr &) = delete;
+    DevArr(DevArr &&o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; }
+    DevArr &operator=(DevArr &&o) noexcept {
+        if (this != &o) { reset(); ctx = o.ctx; p = o.p; n = o.n; o.p = nullptr; }
+        return *this;
+    }
+    void reset() { if (p && ctx) ctx->free(p); p = nullptr; n = 0; }
+    void upload(const std::vector<T> &h) {
+        CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h may be a temporary
+    }
+    ~DevArr() { reset(); }
+};
+typedef DevArr<float> DevBuf;
+
+// ------------------------------------------------------------------------------------------
+struct judi_model {
+    judi_ctx *ctx = nullptr;
+    int ndim = 0, so = 0, r = 0, nbl = 0, fs = 0;
+    int n[3] = {1, 1, 1};        // physical shape (x,y,z), y == 1 in 2-D
+    int N[3] = {1, 1, 1};        // padded shape
+    int padl[3] = {0, 0, 0}, padr[3] = {0, 0, 0};
+    float d[3] = {1, 1, 1};      // spacing
+    float o[3] = {0, 0, 0};      // physical origin
+    float opml[3] = {0, 0, 0};   // origin of the padded grid (fp32, models.py:172)
+    float dt_user = 0, dt = 0;   // dt = critical_dt actually used
+    Grid g;
+    Coefs cf;
+    bool tti = false, irho_field = false, has_dm = false;
+    float irho_c = 1.f;
+    DevBuf m, irho, eps, delta, theta, phi, dm;  // fields on `g` (edge-replicated into halo)
+    DevBuf damp[3];              // 1-D damping profiles per dimension (value of `damp`)
+    std::vector<float> damp_h[3];
+    Region phys, full;
+};
+
+// sparse points of one geometry (sources or receivers) prepared for injection/interpolation
+struct SparseSet {
+    int np = 0, nc = 0;           // traces, corners per trace
+    int ncell = 0, nent = 0;      // unique injected cells, valid (trace, corner) entries
+    DevArr<long long> corner_off; // [np*nc] element offsets on Grid, -1 if outside
+    DevBuf corner_w;              // [np*nc]
+    DevArr<long long> cell_off;   // [ncell] element offset of each unique cell (sorted)
+    DevArr<int> cell_start;       // [ncell+1] CSR row pointers into the entries
+    DevArr<int> cell_ijk;         // [ncell*3]
+    DevArr<int> ent_trace;        // [nent] sorted by (cell, trace, corner)
+    DevBuf ent_w;                 // [nent]
+    DevBuf cell_scale;            // [ncell] dt^2 / (m*irho)
+    DevBuf cell_born;             // [ncell] -dm*irho / (m*irho + dt*damp)   (if model has dm)
+};
+
+// optional post-injection corrections applied by the sparse kernel
+struct SparseCorr {
+    float *ul_next = nullptr;     // Born: ul_next[cell] += cell_born * inj
+    int born_scale_m = 0;         // isic/fwi Born source: also multiply by m[cell]
+    float *grad = nullptr;        // IC:   grad[reg(cell)] -= gcoef*irho * usnap[reg(cell)] * inj
+    const float *usnap = nullptr;
+    float gcoef = 0;
+    int scale_m = 0;              // isic/fwi: also multiply by m[cell]
+    Region reg;
+};
+
+// ---- model.cu
+Grid make_grid(int ndim, const int *N, int halo);
+void fornberg_weights(double z, const double *x, int n, int m, double *c);
+void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc);
+void model_set_param(judi_model *M, DevBuf &dst, const judi_param &p, int on_device,
+                     float default_value, bool force_field);
+void launch_count(judi_ctx *ctx, const char *what);
+
+// ---- sparse.cu
+void sparse_locate_host(const judi_model *M, int np, const float *coords, std::vector<int> &ijk,
+                        std::vector<float> &w, std::vector<int> &valid);
+void sparse_build(const judi_model *M, int np, const float *coords, SparseSet &S);
+// One launch: inject row `src_row` ([np_src], device) of S_src into field `dst` (+ corrections),
+// and interpolate field `cur` at S_rec into rec_row (and `cur2` at S_rec2 into rec_row2).
+void sparse_step(const judi_model *M, const SparseSet *S_src, const float *src_row, float *dst,
+                 const SparseCorr *corr, const SparseSet *S_rec, const float *cur, float *rec_row,
+                 const SparseSet *S_rec2, const float *cur2, float *rec_row2);
+
+// ---- kernels.cu (generic kernels) / tma3d.cu (z-marching TMA kernel)
+struct StepArgs {
+    const float *u[2];   // level t of field(s)
+    float *up[2];        // level t-+1 in, level t+-1 out (in place)
+    const float *ul[2];  // Born: linearised field(s), level t
+    float *ulp[2];
+    int born;            // 1: also step the linearised field(s) with the Born source
+    int born_ic;         // imaging condition of the Born source
+    Fuse f;
+    const CUtensorMap *tmap;   // tensor map of u[0] (TMA kernel), or nullptr
+    struct Wavefield *scratch; // owner of the flux-form scratch buffers
+};
+void stencil_step(const judi_model *M, const StepArgs &a);
+
+// Working set of one propagation: wavefield buffers + scratch for the flux form + tensor maps
+struct Wavefield {
+    judi_ctx *ctx = nullptr;
+    int nf = 1;
+    DevBuf b[2][2];            // [field][slot]
+    int cur = 0;
+    DevBuf flux[6];            // P_x,P_y,P_z,M_x,M_y,M_z (flux form only)
+    DevBuf dd[2];              // u+ - 2u + u- of the background field (flux-form Born)
+    CUtensorMap tmap[2][2];    // [field][slot]
+    bool has_tmap = false;
+    void init(const judi_model *M, bool born_scratch);
+    void swap() { cur = 1 - cur; }
+    float *level(int f) { return b[f][cur].p; }
+    float *other(int f) { return b[f][1 - cur].p; }
+};

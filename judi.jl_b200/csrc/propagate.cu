@@ -1,0 +1,580 @@
+// propagate.cu -- per-shot time loops: the schedule of the reference's three Devito operators.
+//
+//   forward  (operators.py:81-135):  pde ; inject src[t] -> level t+1 ; rec[t] = interp(level t) ;
+//                                    save level t ; illumination.     t = 1 .. nt-2
+//   adjoint  (same operator, fw=False): mirror image, t = nt-2 .. 1, writes level t-1
+//   born     (operators.py:138-192): pde(u) ; inject ; interp(u) [nlind] ; interp(ul) ;
+//                                    pde(ul ; q = lin_src(u)) ; save ; illumination
+//   gradient (operators.py:195-240): pde(v, backward) ; inject residual[t] -> v[t-1] ;
+//                                    gradm -= w * IC(u[t], v) ; illumination
+// Loop bounds and ordering follow SURVEY.md Appendix A.2 / A.6; J_adjoint composition follows
+// src/pysource/interface.py:411-470 (standard) and :473-562 (checkpointing, here as fixed-stride
+// HBM checkpoints + segment recompute instead of pyrevolve).
+#include "common.cuh"
+#include "propagate.h"
+#include <algorithm>
+#include <cmath>
+
+// ---- small data-movement kernels -------------------------------------------------------------
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int rows,
+                                 int cols)
+{
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int cc = c0 + j;
+        if (r < rows && cc < cols) out[(size_t)cc * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+static void transpose(judi_ctx *ctx, const float *in, float *out, int rows, int cols)
+{
+    if (rows == 0 || cols == 0) return;
+    dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grd, blk, 0, ctx->stream>>>(in, out, rows, cols);
+    launch_count(ctx, "transpose");
+}
+
+void Traces::alloc(judi_ctx *ctx, int nt_, int np_)
+{
+    nt = nt_; np = np_;
+    buf = DevBuf(ctx, (size_t)nt * std::max(np, 1), true);
+}
+
+// user layout is time fastest (data[p*nt + t]); device rows are trace fastest
+void Traces::load(judi_ctx *ctx, const float *user, int nt_, int np_, bool on_device)
+{
+    alloc(ctx, nt_, np_);
+    size_t n = (size_t)nt * np;
+    if (n == 0) return;
+    if (on_device) {
+        transpose(ctx, user, buf.p, np, nt);
+    } else {
+        DevBuf tmp(ctx, n, false);
+        CUDA_CHECK(cudaMemcpyAsync(tmp.p, user, n * sizeof(float), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+        transpose(ctx, tmp.p, buf.p, np, nt);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+void Traces::store(judi_ctx *ctx, float *user, bool on_device) const
+{
+    size_t n = (size_t)nt * np;
+    if (n == 0) return;
+    if (on_device) {
+        transpose(ctx, buf.p, user, nt, np);
+    } else {
+        DevBuf tmp(ctx, n, false);
+        transpose(ctx, buf.p, tmp.p, nt, np);
+        CUDA_CHECK(cudaMemcpyAsync(user, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+// region layout -> padded-grid compact array (x fastest), zero outside the region
+__global__ void region_to_padded_kernel(Region reg, const float *__restrict__ src, int nx, int ny,
+                                        int nz, float *__restrict__ dst, int accumulate)
+{
+    long long n = (long long)nx * ny * nz;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = (int)(i % nx);
+    long long t = i / nx;
+    int y = (int)(t % ny), z = (int)(t / ny);
+    float v = reg.has(x, y, z) ? src[reg.at(x, y, z)] : 0.f;
+    if (accumulate) dst[i] += v;
+    else dst[i] = v;
+}
+
+void region_output(const judi_model *M, const Region &reg, const float *src, float *user,
+                   bool on_device, bool accumulate)
+{
+    judi_ctx *ctx = M->ctx;
+    long long n = (long long)M->N[0] * M->N[1] * M->N[2];
+    int nb = (int)((n + 255) / 256);
+    if (on_device) {
+        region_to_padded_kernel<<<nb, 256, 0, ctx->stream>>>(reg, src, M->N[0], M->N[1], M->N[2],
+                                                             user, accumulate ? 1 : 0);
+        launch_count(ctx, "region_to_padded");
+        return;
+    }
+    DevBuf tmp(ctx, (size_t)n, false);
+    if (accumulate)
+        CUDA_CHECK(cudaMemcpyAsync(tmp.p, user, n * sizeof(float), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    region_to_padded_kernel<<<nb, 256, 0, ctx->stream>>>(reg, src, M->N[0], M->N[1], M->N[2],
+                                                         tmp.p, accumulate ? 1 : 0);
+    launch_count(ctx, "region_to_padded");
+    CUDA_CHECK(cudaMemcpyAsync(user, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// Grid-layout field -> padded-grid compact array
+__global__ void grid_to_padded_kernel(Grid g, const float *__restrict__ src,
+                                      float *__restrict__ dst)
+{
+    long long n = (long long)g.n[0] * g.n[1] * g.n[2];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = (int)(i % g.n[0]);
+    long long t = i / g.n[0];
+    int y = (int)(t % g.n[1]), z = (int)(t / g.n[1]);
+    dst[i] = src[g.at(x, y, z)];
+}
+
+void grid_output(const judi_model *M, const float *field, float *user, bool on_device)
+{
+    judi_ctx *ctx = M->ctx;
+    long long n = (long long)M->N[0] * M->N[1] * M->N[2];
+    int nb = (int)((n + 255) / 256);
+    if (on_device) {
+        grid_to_padded_kernel<<<nb, 256, 0, ctx->stream>>>(M->g, field, user);
+        launch_count(ctx, "grid_to_padded");
+        return;
+    }
+    DevBuf tmp(ctx, (size_t)n, false);
+    grid_to_padded_kernel<<<nb, 256, 0, ctx->stream>>>(M->g, field, tmp.p);
+    launch_count(ctx, "grid_to_padded");
+    CUDA_CHECK(cudaMemcpyAsync(user, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// residual = a + b - obs (b optional), f += 0.5 * dt * sum(residual^2)    (sensitivity.py:264-276)
+__global__ void loss_kernel(long long n, float *__restrict__ a, const float *__restrict__ b,
+                            const float *__restrict__ obs, int is_residual, double *fout,
+                            float half_dt)
+{
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float r;
+        if (is_residual) r = obs[i];
+        else r = b ? a[i] - (obs[i] - b[i]) : a[i] - obs[i];
+        a[i] = r;
+        acc += (double)r * (double)r;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
+        atomicAdd(fout, s * (double)half_dt);
+    }
+}
+
+// ---- Shot ------------------------------------------------------------------------------------
+Shot::Shot(judi_model *M_) : M(M_), ctx(M_->ctx) {}
+
+void Shot::make_args(StepArgs &s, Wavefield &W)
+{
+    memset(&s, 0, sizeof(s));
+    for (int f = 0; f < W.nf; f++) { s.u[f] = W.level(f); s.up[f] = W.other(f); }
+    s.tmap = W.has_tmap ? &W.tmap[0][W.cur] : nullptr;
+    s.scratch = &W;
+}
+
+// One forward (dir=+1) or backward (dir=-1) step of the background field at time index t.
+void Shot::step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_in,
+                      const Traces *in, const SparseCorr *corr, const SparseSet *S_out,
+                      Traces *out)
+{
+    StepArgs s;
+    make_args(s, W);
+    if (fuse) s.f = *fuse;
+    stencil_step(M, s);
+    sparse_step(M, S_in, in ? in->row(t) : nullptr, W.other(0), corr, S_out, W.level(0),
+                out ? out->row(t) : nullptr, nullptr, nullptr, nullptr);
+    W.swap();
+}
+
+void Shot::step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fuse,
+                     const SparseSet *S_src, const Traces *q, const SparseSet *S_rec,
+                     Traces *recl, Traces *recnl)
+{
+    StepArgs s;
+    make_args(s, W);
+    s.born = 1;
+    s.born_ic = ic;
+    for (int f = 0; f < WL.nf; f++) { s.ul[f] = WL.level(f); s.ulp[f] = WL.other(f); }
+    if (fuse) s.f = *fuse;
+    stencil_step(M, s);
+    SparseCorr corr;
+    corr.ul_next = WL.other(0);
+    corr.born_scale_m = ic != JUDI_IC_AS;
+    sparse_step(M, S_src, q->row(t), W.other(0), &corr, S_rec, WL.level(0),
+                recl ? recl->row(t) : nullptr, recnl ? S_rec : nullptr, W.level(0),
+                recnl ? recnl->row(t) : nullptr);
+    W.swap();
+    WL.swap();
+}
+
+static Fuse no_fuse()
+{
+    Fuse f;
+    memset(&f, 0, sizeof(f));
+    return f;
+}
+
+// ---- forward_rec / adjoint --------------------------------------------------------------------
+void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
+                     const float *wavelet, int nt, int nrec, const float *rec_coords,
+                     float *rec_out, float *illum_out, int flags)
+{
+    judi_ctx *ctx = M->ctx;
+    bool dev = flags & JUDI_DATA_ON_DEVICE;
+    JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
+    Shot sh(M);
+    SparseSet S_src, S_rec;
+    sparse_build(M, nsrc, src_coords, S_src);
+    if (nrec > 0) sparse_build(M, nrec, rec_coords, S_rec);
+    Traces q, rec;
+    q.load(ctx, wavelet, nt, nsrc, dev);
+    rec.alloc(ctx, nt, nrec);
+    Wavefield W;
+    W.init(M, false);
+    DevBuf illum;
+    Fuse fz = no_fuse();
+    fz.reg = M->full;
+    if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
+    if (fw) {
+        for (int t = 1; t <= nt - 2; t++)
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr,
+                          nrec > 0 ? &S_rec : nullptr, &rec);
+    } else {
+        for (int t = nt - 2; t >= 1; t--)
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr,
+                          nrec > 0 ? &S_rec : nullptr, &rec);
+    }
+    if (rec_out && nrec > 0) rec.store(ctx, rec_out, dev);
+    if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
+    ctx->flush_timing();
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- forward_no_rec: full wavefield history -----------------------------------------------------
+void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags)
+{
+    judi_ctx *ctx = M->ctx;
+    bool dev = flags & JUDI_DATA_ON_DEVICE;
+    JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
+    Shot sh(M);
+    SparseSet S_src;
+    sparse_build(M, nsrc, src_coords, S_src);
+    Traces q;
+    q.load(ctx, wavelet, nt, nsrc, dev);
+    Wavefield W;
+    W.init(M, false);
+    DevBuf illum;
+    Fuse fz = no_fuse();
+    fz.reg = M->full;
+    if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
+    size_t ng = (size_t)M->N[0] * M->N[1] * M->N[2];
+    // u.data[t] for t = 0..nt-1 (fields.py:41-42, save=nt): levels 0,1 (fw) / nt-1,nt-2 (adjoint)
+    // are never written and stay zero.
+    auto emit = [&](int t, const float *field) {
+        grid_output(M, field, u_out + (size_t)t * ng, dev);
+    };
+    if (dev) CUDA_CHECK(cudaMemsetAsync(u_out, 0, (size_t)nt * ng * sizeof(float), ctx->stream));
+    else memset(u_out, 0, (size_t)nt * ng * sizeof(float));
+    if (fw) {
+        for (int t = 1; t <= nt - 2; t++) {
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr, nullptr, nullptr);
+            emit(t + 1, W.level(0));
+        }
+    } else {
+        for (int t = nt - 2; t >= 1; t--) {
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr, nullptr, nullptr);
+            emit(t - 1, W.level(0));
+        }
+    }
+    if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
+    ctx->flush_timing();
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- born_rec ------------------------------------------------------------------------------------
+void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
+                  int nrec, const float *rec_coords, int ic, float *rec_out, float *illum_out,
+                  int flags)
+{
+    judi_ctx *ctx = M->ctx;
+    bool dev = flags & JUDI_DATA_ON_DEVICE;
+    JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
+    size_t nr = (size_t)nt * nrec;
+    if (!M->has_dm) {
+        // propagators.py:181-194 / time_modeling_serial.jl:22-24: J*0 is exactly zero
+        if (rec_out) {
+            if (dev) CUDA_CHECK(cudaMemsetAsync(rec_out, 0, nr * sizeof(float), ctx->stream));
+            else memset(rec_out, 0, nr * sizeof(float));
+        }
+        if (illum_out)
+            run_forward_rec(M, 1, nsrc, src_coords, wavelet, nt, 0, nullptr, nullptr, illum_out,
+                            flags);
+        return;
+    }
+    Shot sh(M);
+    SparseSet S_src, S_rec;
+    sparse_build(M, nsrc, src_coords, S_src);
+    sparse_build(M, nrec, rec_coords, S_rec);
+    Traces q, rec;
+    q.load(ctx, wavelet, nt, nsrc, dev);
+    rec.alloc(ctx, nt, nrec);
+    Wavefield W, WL;
+    W.init(M, true);
+    WL.init(M, false);
+    DevBuf illum;
+    Fuse fz = no_fuse();
+    fz.reg = M->full;
+    if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
+    for (int t = 1; t <= nt - 2; t++)
+        sh.step_born(W, WL, t, ic, illum_out ? &fz : nullptr, &S_src, &q, &S_rec, &rec, nullptr);
+    rec.store(ctx, rec_out, dev);
+    if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
+    ctx->flush_timing();
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- J_adjoint -----------------------------------------------------------------------------------
+static int num_slots(int nt, int t_sub)
+{
+    // fields.py:141-144
+    return t_sub == 1 ? nt : (int)std::ceil((double)(nt + t_sub) / (double)t_sub);
+}
+
+void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
+                   int nrec, const float *rec_coords, const float *recin, const judi_jopts *o,
+                   judi_misfit_fn misfit, void *user, float *f_out, float *grad_out,
+                   float *illum_u, float *illum_v, int flags)
+{
+    judi_ctx *ctx = M->ctx;
+    bool dev = flags & JUDI_DATA_ON_DEVICE;
+    bool accumulate = flags & JUDI_GRAD_ACCUMULATE;
+    JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
+    JUDI_REQUIRE(o->t_sub >= 1, "t_sub must be >= 1");
+    JUDI_REQUIRE(!(o->nlind && !o->born_fwd), "nlind requires born_fwd");
+    JUDI_REQUIRE(o->ic >= JUDI_IC_AS && o->ic <= JUDI_IC_FWI, "unknown imaging condition");
+    bool flux = M->tti || M->irho_field;
+    JUDI_REQUIRE(o->ic == JUDI_IC_AS || !flux,
+                 "isic/fwi imaging conditions are only implemented for constant-density acoustics");
+    bool born = o->born_fwd && M->has_dm;
+    const int nf = M->tti ? 2 : 1;
+    const int k = o->checkpointing ? 1 : o->t_sub;
+    // ISIC/FWI differentiate the snapshot: it must cover the whole padded grid
+    const Region reg = (o->snapshot_region == JUDI_SNAP_PHYSICAL && o->ic == JUDI_IC_AS)
+                           ? M->phys : M->full;
+
+    Shot sh(M);
+    SparseSet S_src, S_rec;
+    sparse_build(M, nsrc, src_coords, S_src);
+    sparse_build(M, nrec, rec_coords, S_rec);
+    Traces q, obs, rec, recnl;
+    q.load(ctx, wavelet, nt, nsrc, dev);
+    obs.load(ctx, recin, nt, nrec, dev);
+    rec.alloc(ctx, nt, nrec);
+    if (born && o->nlind) recnl.alloc(ctx, nt, nrec);
+
+    Wavefield W, WL;
+    W.init(M, born);
+    if (born) WL.init(M, false);
+    DevBuf Iu, Iv, grad(ctx, (size_t)reg.slot, true);
+    if (illum_u) Iu = DevBuf(ctx, (size_t)reg.slot, true);
+    if (illum_v) Iv = DevBuf(ctx, (size_t)reg.slot, true);
+
+    // ---- snapshot storage ------------------------------------------------------------------
+    const size_t slot_floats = (size_t)reg.slot * nf;
+    int seg = 0, nseg = 0;          // checkpointing: segment length / count
+    int nslots;
+    std::vector<DevBuf> ckpt;       // per segment: level t and level t-1 of every field
+    if (!o->checkpointing) {
+        nslots = num_slots(nt, k);
+    } else {
+        // fixed-stride checkpoints + segment recompute: memory ~ seg snapshots + (nt/seg) states;
+        // seg ~ sqrt(nt * state/snapshot) balances the two, bounded by n_checkpoints if given.
+        double state = 2.0 * nf * (double)M->g.nalloc, snapf = (double)slot_floats;
+        seg = (int)std::ceil(std::sqrt((double)nt * state / snapf));
+        if (o->n_checkpoints > 0) seg = std::max(1, (nt + o->n_checkpoints - 1) / o->n_checkpoints);
+        seg = std::max(1, std::min(seg, nt));
+        nseg = (nt - 2 + seg - 1) / seg;
+        nslots = seg;
+    }
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        unsigned long long reserved = 0, used = 0;
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        double avail = (double)free_b + (double)(reserved - used);
+        double need = (double)nslots * slot_floats * 4.0 +
+                      (double)nseg * 2.0 * nf * (double)M->g.nalloc * 4.0;
+        if (need > 0.97 * avail) {
+            char b[256];
+            snprintf(b, sizeof(b),
+                     "wavefield snapshots need %.1f GB but only %.1f GB of HBM are free: raise "
+                     "subsampling_factor, use snapshot_region=physical or optimal_checkpointing",
+                     need / 1e9, avail / 1e9);
+            throw JudiError(b);
+        }
+    }
+    DevBuf snaps(ctx, (size_t)nslots * slot_floats, false);
+    auto slot_ptr = [&](int s, int f) { return snaps.p + ((size_t)s * nf + f) * reg.slot; };
+
+    Fuse fsave = no_fuse();
+    fsave.reg = reg;
+    fsave.illum = illum_u ? Iu.p : nullptr;
+
+    // ---- forward sweep ---------------------------------------------------------------------
+    auto fwd_step = [&](int t, int save_slot) {
+        Fuse f = fsave;
+        if (save_slot >= 0)
+            for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot_ptr(save_slot, ff);
+        bool any = f.snap[0] || f.illum;
+        if (born)
+            sh.step_born(W, WL, t, o->ic, any ? &f : nullptr, &S_src, &q, &S_rec, &rec,
+                         o->nlind ? &recnl : nullptr);
+        else
+            sh.step_plain(W, t, any ? &f : nullptr, &S_src, &q, nullptr, &S_rec, &rec);
+    };
+    if (!o->checkpointing) {
+        for (int t = 1; t <= nt - 2; t++) fwd_step(t, (t % k) == 0 ? t / k : -1);
+    } else {
+        JUDI_REQUIRE(!born, "optimal_checkpointing with born_fwd is not supported yet");
+        ckpt.resize((size_t)nseg * 2 * nf);
+        for (int t = 1; t <= nt - 2; t++) {
+            if ((t - 1) % seg == 0) {
+                int s = (t - 1) / seg;
+                for (int ff = 0; ff < nf; ff++) {
+                    for (int lv = 0; lv < 2; lv++) {
+                        DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];
+                        c = DevBuf(ctx, (size_t)M->g.nalloc, false);
+                        CUDA_CHECK(cudaMemcpyAsync(c.p, lv == 0 ? W.level(ff) : W.other(ff),
+                                                   (size_t)M->g.nalloc * sizeof(float),
+                                                   cudaMemcpyDeviceToDevice, ctx->stream));
+                    }
+                }
+            }
+            fwd_step(t, -1);
+        }
+        fsave.illum = nullptr;  // the recomputation must not add to the illumination again
+    }
+
+    // ---- misfit (sensitivity.py:236-276) ---------------------------------------------------
+    double fval = 0.0;
+    if (misfit) {
+        size_t n = (size_t)nt * nrec;
+        std::vector<float> hsyn(n), hobs(n), hres(n);
+        if (born && o->nlind) {
+            // misfit(dsyn[0], dobs - dsyn[1]) with dsyn = (rcvl, rnl)
+            std::vector<float> hnl(n);
+            rec.store(ctx, hsyn.data(), false);
+            recnl.store(ctx, hnl.data(), false);
+            obs.store(ctx, hobs.data(), false);
+            for (size_t i = 0; i < n; i++) hobs[i] -= hnl[i];
+        } else {
+            rec.store(ctx, hsyn.data(), false);
+            obs.store(ctx, hobs.data(), false);
+        }
+        float fv = misfit(hsyn.data(), hobs.data(), hres.data(), nt, nrec, user);
+        fval = (double)M->dt * (double)fv;
+        rec.load(ctx, hres.data(), nt, nrec, false);
+    } else {
+        DevArr<double> fd(ctx, 1, true);
+        long long n = (long long)nt * nrec;
+        int nb = (int)std::min<long long>((n + 255) / 256, 1024);
+        if (nb < 1) nb = 1;
+        loss_kernel<<<nb, 256, 0, ctx->stream>>>(n, rec.buf.p,
+                                                 (born && o->nlind) ? recnl.buf.p : nullptr,
+                                                 obs.buf.p, o->is_residual ? 1 : 0, fd.p,
+                                                 0.5f * M->dt);
+        launch_count(ctx, "loss");
+        CUDA_CHECK(cudaMemcpyAsync(&fval, fd.p, sizeof(double), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    // rec now holds the adjoint source (residual)
+
+    // ---- adjoint sweep with the imaging condition ---------------------------------------------
+    Wavefield V;
+    V.init(M, false);
+    Fuse fadj = no_fuse();
+    fadj.reg = reg;
+    fadj.illum = illum_v ? Iv.p : nullptr;
+    fadj.ic = o->ic;
+    fadj.gcoef = (float)((double)k / (double)M->dt);
+    auto adj_step = [&](int t, int slot) {
+        Fuse f = fadj;
+        SparseCorr corr;
+        if (slot >= 0) {
+            f.grad = grad.p;
+            for (int ff = 0; ff < nf; ff++) f.usnap[ff] = slot_ptr(slot, ff);
+            corr.grad = grad.p;
+            corr.usnap = slot_ptr(slot, 0);
+            corr.gcoef = fadj.gcoef;
+            corr.scale_m = o->ic != JUDI_IC_AS;
+            corr.reg = reg;
+        }
+        bool any = f.grad || f.illum;
+        sh.step_plain(V, t, any ? &f : nullptr, &S_rec, &rec, slot >= 0 ? &corr : nullptr, nullptr,
+                      nullptr);
+    };
+    if (!o->checkpointing) {
+        for (int t = nt - 2; t >= 1; t--) adj_step(t, (t % k) == 0 ? t / k : -1);
+    } else {
+        for (int s = nseg - 1; s >= 0; s--) {
+            int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
+            // restore the state at the start of the segment and recompute its snapshots
+            W.cur = 0;
+            for (int ff = 0; ff < nf; ff++)
+                for (int lv = 0; lv < 2; lv++) {
+                    DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];
+                    CUDA_CHECK(cudaMemcpyAsync(lv == 0 ? W.level(ff) : W.other(ff), c.p,
+                                               (size_t)M->g.nalloc * sizeof(float),
+                                               cudaMemcpyDeviceToDevice, ctx->stream));
+                    c.reset();
+                }
+            Fuse f = fsave;
+            for (int t = ts; t <= te; t++) {
+                for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot_ptr(t - ts, ff);
+                sh.step_plain(W, t, &f, &S_src, &q, nullptr, nullptr, nullptr);
+            }
+            for (int t = te; t >= ts; t--) adj_step(t, t - ts);
+        }
+    }
+
+    // ---- outputs -----------------------------------------------------------------------------
+    region_output(M, reg, grad.p, grad_out, dev, accumulate);
+    if (illum_u) region_output(M, reg, Iu.p, illum_u, dev, false);
+    if (illum_v) region_output(M, reg, Iv.p, illum_v, dev, false);
+    if (f_out) {
+        if (dev) {
+            // device scalar: keep the reduction on the GPU side of the boundary
+            float fv = (float)fval, prev = 0.f;
+            if (accumulate) {
+                CUDA_CHECK(cudaMemcpyAsync(&prev, f_out, sizeof(float), cudaMemcpyDeviceToHost,
+                                           ctx->stream));
+                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            }
+            fv += prev;
+            CUDA_CHECK(cudaMemcpyAsync(f_out, &fv, sizeof(float), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+        } else {
+            if (accumulate) *f_out += (float)fval;
+            else *f_out = (float)fval;
+        }
+    }
+    ctx->flush_timing();
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}

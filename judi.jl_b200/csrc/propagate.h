@@ -1,0 +1,42 @@
+// propagate.h -- per-shot drivers (see propagate.cu)
+#pragma once
+#include "common.cuh"
+
+// device-resident traces, one row per time sample (trace fastest)
+struct Traces {
+    DevBuf buf;
+    int nt = 0, np = 0;
+    float *row(int t) const { return buf.p + (size_t)t * np; }
+    void alloc(judi_ctx *ctx, int nt, int np);
+    void load(judi_ctx *ctx, const float *user, int nt, int np, bool on_device);
+    void store(judi_ctx *ctx, float *user, bool on_device) const;
+};
+
+struct Shot {
+    judi_model *M;
+    judi_ctx *ctx;
+    explicit Shot(judi_model *M);
+    void make_args(StepArgs &s, Wavefield &W);
+    void step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_in, const Traces *in,
+                    const SparseCorr *corr, const SparseSet *S_out, Traces *out);
+    void step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fuse,
+                   const SparseSet *S_src, const Traces *q, const SparseSet *S_rec, Traces *recl,
+                   Traces *recnl);
+};
+
+void region_output(const judi_model *M, const Region &reg, const float *src, float *user,
+                   bool on_device, bool accumulate);
+void grid_output(const judi_model *M, const float *field, float *user, bool on_device);
+
+void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
+                     const float *wavelet, int nt, int nrec, const float *rec_coords,
+                     float *rec_out, float *illum_out, int flags);
+void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags);
+void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
+                  int nrec, const float *rec_coords, int ic, float *rec_out, float *illum_out,
+                  int flags);
+void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
+                   int nrec, const float *rec_coords, const float *recin, const judi_jopts *o,
+                   judi_misfit_fn misfit, void *user, float *f_out, float *grad_out,
+                   float *illum_u, float *illum_v, int flags);

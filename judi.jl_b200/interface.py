@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's `pysource.interface` (src/pysource/interface.py): the
+functions the Julia driver calls through `wrapcall_data(ac.<fn>, modelPy, ...)`
+(src/TimeModeling/Modeling/python_interface.jl:30-198, misfit_fg.jl:69-73), with the same names,
+argument meaning, defaults and return tuples -- but executed by libjudi_b200 on a B200.
+
+Conventions: coordinates (npoint, ndim) in metres; wavelets / shot records (nt, ntrace);
+grids (nx[,ny],nz).  Outputs are F-ordered numpy arrays, i.e. exactly the memory layout Julia
+uses, so the `ccall` twin of these wrappers needs no copies.  When the wavelet / data are torch
+CUDA tensors (given time-fastest: contiguous (ntrace, nt)) everything stays in HBM and the
+results are written into the caller's `*_out` device tensors.
+
+Out of this backend's scope (raise NotImplementedError): on-the-fly DFT (`freq_list`), extended
+sources (`ws`, `forward_rec_w`, `adjoint_w`, `born_rec_w`), wavefield sources
+(`forward_wf_src*`), `wri_func`, free surface.
+"""
+import ctypes
+import numpy as np
+
+from . import _lib as L
+from .models import is_device_tensor
+
+
+def _coords(c, ndim):
+    """(npoint, ndim) -> SoA float32 (Julia's hcat(x[,y],z) column-major memory)."""
+    c = np.asarray(c, dtype=np.float32)
+    if c.ndim == 1:
+        c = c.reshape(1, -1)
+    assert c.shape[1] == ndim, "coordinates must be (npoint, %d)" % ndim
+    return np.asfortranarray(c)
+
+
+def _traces(a):
+    """(nt, ntrace) host array -> time-fastest float32 memory; returns (array, nt, ntrace)."""
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    a = np.asfortranarray(a)
+    return a, a.shape[0], a.shape[1]
+
+
+def _dev_traces(t):
+    assert t.is_contiguous() and t.dim() == 2, "device traces must be contiguous (ntrace, nt)"
+    return t, int(t.shape[1]), int(t.shape[0])
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if is_device_tensor(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _grid_out(model, out):
+    if out is not None:
+        return out
+    return np.zeros(model.shape_pml, dtype=np.float32, order="F")
+
+
+# Forward wrappers Pr*F*Ps'*q
+def forward_rec(model, src_coords, wavelet, rec_coords, f0=0.015, illum=False, fw=True,
+                rec_out=None, illum_out=None):
+    """Modeling of a point source with receivers Pr*F*Ps^T*q (interface.py:17-47).
+
+    Returns (shot record (nt, nrec), illumination or None).  With fw=False the adjoint
+    propagator is run (time reversed), as the reference does for F'.
+    """
+    dev = is_device_tensor(wavelet)
+    sc = _coords(src_coords, model.dim)
+    rc = _coords(rec_coords, model.dim)
+    if dev:
+        q, nt, nsrc = _dev_traces(wavelet)
+        assert rec_out is not None and is_device_tensor(rec_out)
+        rec = rec_out
+        I = illum_out if illum else None
+    else:
+        q, nt, nsrc = _traces(wavelet)
+        rec = np.zeros((nt, rc.shape[0]), dtype=np.float32, order="F")
+        I = _grid_out(model, illum_out) if illum else None
+    assert nsrc == sc.shape[0], "one wavelet column per source point"
+    L.check(L.lib().judi_forward_rec(model.h, int(bool(fw)), nsrc, sc.ctypes.data, _ptr(q), nt,
+                                     rc.shape[0], rc.ctypes.data, _ptr(rec), _ptr(I),
+                                     L.DATA_ON_DEVICE if dev else 0))
+    return rec, I
+
+
+# F*Ps'*q
+def forward_no_rec(model, src_coords, wavelet, f0=0.015, illum=False, fw=True):
+    """Forward modeling of a point source without receiver (interface.py:83-111): returns the
+    wavefield history (nt, nx[,ny],nz) on the padded grid and the illumination."""
+    sc = _coords(src_coords, model.dim)
+    q, nt, nsrc = _traces(wavelet)
+    u = np.zeros(model.shape_pml + (nt,), dtype=np.float32, order="F")  # memory: time slowest
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_forward_no_rec(model.h, int(bool(fw)), nsrc, sc.ctypes.data, _ptr(q), nt,
+                                        _ptr(u), _ptr(I), 0))
+    return np.moveaxis(u, -1, 0), I
+
+
+# Linearized modeling d/dm (Pr*F*Ps'*q)
+def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=0.015, illum=False, fw=True,
+             rec_out=None, illum_out=None):
+    """Linearized (Born) modeling of a point source for the model's dm (interface.py:208-241)."""
+    if not fw:
+        raise NotImplementedError("born_rec with fw=False")
+    dev = is_device_tensor(wavelet)
+    sc = _coords(src_coords, model.dim)
+    rc = _coords(rec_coords, model.dim)
+    if dev:
+        q, nt, nsrc = _dev_traces(wavelet)
+        assert rec_out is not None and is_device_tensor(rec_out)
+        rec = rec_out
+        I = illum_out if illum else None
+    else:
+        q, nt, nsrc = _traces(wavelet)
+        rec = np.zeros((nt, rc.shape[0]), dtype=np.float32, order="F")
+        I = _grid_out(model, illum_out) if illum else None
+    L.check(L.lib().judi_born_rec(model.h, nsrc, sc.ctypes.data, _ptr(q), nt, rc.shape[0],
+                                  rc.ctypes.data, L.IC_CODES[ic], _ptr(rec), _ptr(I),
+                                  L.DATA_ON_DEVICE if dev else 0))
+    return rec, I
+
+
+def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
+              checkpointing=False, n_checkpoints=None, t_sub=1, return_obj=False, freq_list=None,
+              dft_sub=None, ic="as", illum=False, ws=None, f0=0.015, born_fwd=False, nlind=False,
+              misfit=None, fw=True, snapshot_region="padded", grad_out=None, f_out=None,
+              illum_out=None, accumulate=False):
+    """Adjoint Jacobian on a shot record (interface.py:279-345): standard zero-lag
+    cross-correlation (:411-470) or checkpointed (:473-562).
+
+    Returns `(f, g, Iu, Iv)` if return_obj else `(g, Iu, Iv)`, g on the padded grid (the caller
+    crops it with remove_padding, misfit_fg.jl:77).  `misfit(dsyn, dobs) -> (f, residual)` is
+    the optional user misfit (misfit_fg.jl:55-64).  Extra keywords of this backend:
+    `snapshot_region` ('padded' = reference semantics | 'physical'), and for device-resident
+    runs `grad_out`, `f_out`, `illum_out=(Iu, Iv)`, `accumulate`.
+    """
+    if freq_list is not None and len(freq_list) > 0:
+        raise NotImplementedError("on-the-fly DFT gradients are out of the B200 backend's scope")
+    if ws is not None:
+        raise NotImplementedError("extended sources are a 'next' row of the B200 backend")
+    if not fw:
+        raise NotImplementedError("J_adjoint with fw=False")
+    dev = is_device_tensor(wavelet)
+    sc = _coords(src_coords, model.dim)
+    rc = _coords(rec_coords, model.dim)
+    o = L.JudiJopts()
+    o.is_residual = int(bool(is_residual))
+    o.checkpointing = int(bool(checkpointing))
+    o.n_checkpoints = int(n_checkpoints) if n_checkpoints else 0
+    o.t_sub = int(t_sub)
+    o.ic = L.IC_CODES[ic]
+    o.born_fwd = int(bool(born_fwd))
+    o.nlind = int(bool(nlind))
+    o.illum = int(bool(illum))
+    o.snapshot_region = L.SNAP_PHYSICAL if snapshot_region == "physical" else L.SNAP_PADDED
+    flags = (L.DATA_ON_DEVICE if dev else 0) | (L.GRAD_ACCUMULATE if accumulate else 0)
+    Iu = Iv = None
+    if dev:
+        q, nt, nsrc = _dev_traces(wavelet)
+        d, ntd, nrec = _dev_traces(recin)
+        assert grad_out is not None and is_device_tensor(grad_out)
+        g = grad_out
+        fbuf = f_out
+        if illum:
+            Iu, Iv = illum_out
+    else:
+        q, nt, nsrc = _traces(wavelet)
+        d, ntd, nrec = _traces(recin)
+        g = grad_out if grad_out is not None else _grid_out(model, None)
+        fbuf = ctypes.c_float(0.0 if not accumulate or f_out is None else float(f_out))
+        if illum:
+            Iu, Iv = _grid_out(model, None), _grid_out(model, None)
+    assert ntd == nt and nrec == rc.shape[0], "data shape does not match geometry / wavelet"
+
+    cb = ctypes.cast(None, L.MISFIT_FN)
+    if misfit is not None:
+        def _cb(psyn, pobs, pres, nt_, nrec_, _user):
+            shp = (nt_, nrec_)
+            dsyn = np.ctypeslib.as_array(psyn, shape=(nrec_, nt_)).T
+            dobs = np.ctypeslib.as_array(pobs, shape=(nrec_, nt_)).T
+            res = np.ctypeslib.as_array(pres, shape=(nrec_, nt_)).T
+            fval, r = misfit(dsyn, dobs)
+            res[...] = np.asarray(r, dtype=np.float32).reshape(shp)
+            return float(fval)
+        cb = L.MISFIT_FN(_cb)
+
+    fptr = None
+    if return_obj or fbuf is not None:
+        fptr = _ptr(fbuf) if dev else ctypes.addressof(fbuf)
+    L.check(L.lib().judi_J_adjoint(model.h, nsrc, sc.ctypes.data, _ptr(q), nt, nrec,
+                                   rc.ctypes.data, _ptr(d), ctypes.byref(o),
+                                   ctypes.cast(cb, ctypes.c_void_p), None, fptr, _ptr(g),
+                                   _ptr(Iu), _ptr(Iv), flags))
+    if return_obj:
+        f = fbuf if dev else np.float32(fbuf.value)
+        return f, g, Iu, Iv
+    return g, Iu, Iv
+
+
+# ---- out of scope: keep the reference names so callers fail loudly, not silently ---------------
+def _out_of_scope(name):
+    def fn(*a, **k):
+        raise NotImplementedError("%s is outside the B200 backend's hot path (see DESIGN.md)" % name)
+    fn.__name__ = name
+    return fn
+
+
+forward_rec_w = _out_of_scope("forward_rec_w")
+forward_wf_src = _out_of_scope("forward_wf_src")
+forward_wf_src_norec = _out_of_scope("forward_wf_src_norec")
+adjoint_w = _out_of_scope("adjoint_w")
+born_rec_w = _out_of_scope("born_rec_w")
+wri_func = _out_of_scope("wri_func")

@@ -1,0 +1,104 @@
+"""Mirror of the Julia drivers above the boundary: the shot scheduler and reduction
+(src/TimeModeling/Modeling/propagation.jl:23-107, distributed.jl:6-95) and the objective
+wrappers (misfit_fg.jl:143-198), with the reference's process-per-worker Julia `Distributed`
+pool replaced by one process per GPU and a single all-reduce of (gradient, objective).
+
+Shots are independent until the final sum, so they are partitioned round-robin over the ranks
+(shot i -> rank i mod world_size); every rank accumulates its shots locally (in HBM when the
+inputs are device resident) and one `torch.distributed.all_reduce(SUM)` -- NCCL over NVLink on
+GPUs, gloo in the CPU tests -- replaces `reduce!`'s binary tree over Futures.
+"""
+import numpy as np
+
+
+def remove_padding(g, nb, true_adjoint=False):
+    """src/TimeModeling/Utils/auxiliaryFunctions.jl:79-89 (crop; true_adjoint folds the pad)."""
+    g = np.array(g, copy=True)
+    if true_adjoint:
+        for dim, (nbl, nbr) in enumerate(nb):
+            N = g.shape[dim]
+
+            def sel(i):
+                s = [slice(None)] * g.ndim
+                s[dim] = i
+                return tuple(s)
+            g[sel(nbl)] += g[sel(slice(0, nbl))].sum(axis=dim)
+            g[sel(N - nbr - 1)] += g[sel(slice(N - nbr, N))].sum(axis=dim)
+    crop = tuple(slice(nbl, n - nbr) for (nbl, nbr), n in zip(nb, g.shape))
+    return g[crop]
+
+
+def shot_partition(nsrc, world_size, rank):
+    """Static round-robin: the shots rank `rank` propagates."""
+    return list(range(rank, nsrc, world_size))
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def reduce_fg(f, g):
+    """Sum (objective, gradient) over all ranks: distributed.jl:60-95 as one all-reduce.
+
+    `g` is a numpy array (host path) or a torch tensor (device path, reduced in place over
+    NCCL); the objective scalar rides along as one extra element, as in SURVEY 8(e)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return f, g
+    import torch
+    if hasattr(g, "is_cuda"):
+        buf = torch.cat([g.reshape(-1), torch.as_tensor([float(f)], dtype=g.dtype, device=g.device)])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        g.copy_(buf[:-1].reshape(g.shape))
+        return float(buf[-1].item()), g
+    g = np.asarray(g, dtype=np.float32)
+    flat = np.concatenate([g.ravel(order="F"), np.array([f], dtype=np.float32)])
+    t = torch.from_numpy(flat)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    t = t.cpu().numpy()
+    return float(t[-1]), t[:-1].reshape(g.shape, order="F")
+
+
+def multi_src_fg(model, shots, dm=None, lin=False, nlind=False, misfit=None, reduce=True,
+                 sum_padding=False, **options):
+    """multi_src_fg! (propagation.jl:93-107) over this rank's share of `shots`.
+
+    `shots`: sequence of (src_coords, wavelet, rec_coords, dobs) per source experiment.
+    Returns (f, gradient on the physical grid), summed over all shots of all ranks."""
+    from . import interface
+    dist = _dist()
+    ws = dist.get_world_size() if dist else 1
+    rk = dist.get_rank() if dist else 0
+    if dm is not None:
+        model.set_dm(dm)
+    f, g = 0.0, None
+    for i in shot_partition(len(shots), ws, rk):
+        sc, q, rc, dobs = shots[i]
+        fi, gi, _, _ = interface.J_adjoint(model, sc, q, rc, dobs, return_obj=True,
+                                           born_fwd=lin, nlind=nlind, misfit=misfit, **options)
+        f += float(fi)
+        g = gi if g is None else g + gi
+    if g is None:
+        g = np.zeros(model.shape_pml, dtype=np.float32, order="F")
+    if reduce:
+        f, g = reduce_fg(f, g)
+    return np.float32(f), remove_padding(g, model.padsizes, true_adjoint=sum_padding)
+
+
+def fwi_objective(model, shots, **options):
+    """fwi_objective (misfit_fg.jl:143-148): f = sum_i 1/2 dt ||F(m) q_i - d_i||^2 and its
+    gradient w.r.t. the squared slowness."""
+    return multi_src_fg(model, shots, dm=None, lin=False, **options)
+
+
+def lsrtm_objective(model, shots, dm, nlind=False, **options):
+    """lsrtm_objective (misfit_fg.jl:161-166): f = sum_i 1/2 dt ||J dm - (d_i - nlind*F q_i)||^2."""
+    return multi_src_fg(model, shots, dm=dm, lin=True, nlind=nlind, **options)
