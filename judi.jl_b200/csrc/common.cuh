@@ -109,7 +109,7 @@ struct judi_ctx {
     // options
     int opt_kernel3d = 1;       // 0 generic, 1 TMA z-marching
     int opt_zchunks = 0;        // 0 = auto
-    int opt_tile = 0;           // TMA kernel tile variant
+    int opt_tile = 6;           // TMA kernel variant (6: 64x16 tile, 2 producer warps)
     int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
@@ -223,7 +223,9 @@ struct StepArgs {
     int born;            // 1: also step the linearised field(s) with the Born source
     int born_ic;         // imaging condition of the Born source
     Fuse f;
-    const CUtensorMap *tmap;   // tensor map of u[0] (TMA kernel), or nullptr
+    const CUtensorMap *tmap;       // halo-box tensor map of u[0] (TMA kernel), or nullptr
+    const CUtensorMap *tmap_prev;  // tile-box tensor map of up[0]
+    const CUtensorMap *tmap_m;     // tile-box tensor map of m
     struct Wavefield *scratch; // owner of the flux-form scratch buffers
 };
 void stencil_step(const judi_model *M, const StepArgs &a);
@@ -236,7 +238,9 @@ struct Wavefield {
     int cur = 0;
     DevBuf flux[6];            // P_x,P_y,P_z,M_x,M_y,M_z (flux form only)
     DevBuf dd[2];              // u+ - 2u + u- of the background field (flux-form Born)
-    CUtensorMap tmap[2][2];    // [field][slot]
+    CUtensorMap tmap_halo[2][2];  // [field][slot]: haloed plane box
+    CUtensorMap tmap_tile[2][2];  // [field][slot]: tile box
+    CUtensorMap tmap_m;           // tile box over the model's m
     bool has_tmap = false;
     void init(const judi_model *M, bool born_scratch);
     void swap() { cur = 1 - cur; }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
-void tma3d_encode(const judi_model *M, float *base, CUtensorMap *out);
+void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
 
@@ -314,7 +314,8 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
     has_tmap = false;
     if (tma3d_supported(M)) {
         for (int f = 0; f < nf; f++)
-            for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap[f][s]);
+            for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
+        tma3d_encode(M, M->m.p, nullptr, &tmap_m);
         has_tmap = true;
     }
 }

@@ -182,7 +182,9 @@ void Shot::make_args(StepArgs &s, Wavefield &W)
 {
     memset(&s, 0, sizeof(s));
     for (int f = 0; f < W.nf; f++) { s.u[f] = W.level(f); s.up[f] = W.other(f); }
-    s.tmap = W.has_tmap ? &W.tmap[0][W.cur] : nullptr;
+    s.tmap = W.has_tmap ? &W.tmap_halo[0][W.cur] : nullptr;
+    s.tmap_prev = W.has_tmap ? &W.tmap_tile[0][1 - W.cur] : nullptr;
+    s.tmap_m = W.has_tmap ? &W.tmap_m : nullptr;
     s.scratch = &W;
 }
 

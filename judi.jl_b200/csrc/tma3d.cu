@@ -7,14 +7,19 @@
 // Design:
 //  * 2.5-D blocking: a CTA owns a (TX x TY) tile of the (x,y) plane and marches along z (the
 //    slowest axis) over one z-chunk.  x is the fastest axis = Julia's native order.
-//  * Each (TX+2HR) x (TY+2R) haloed plane is fetched ONCE per CTA by a single
-//    cp.async.bulk.tensor.3d (TMA) into a ring of NS shared-memory slots, completion signalled on
-//    an mbarrier; out-of-range box parts are zero-filled by the TMA unit, which is exactly the
-//    Dirichlet halo.  NS - R - 1 planes are always in flight ahead of the compute.
+//  * Warp-specialised TMA pipeline.  One producer warp issues every global->shared transfer as
+//    cp.async.bulk.tensor.3d: the haloed (TX+2HR) x (TY+2R) plane of u(t) into a ring of NS
+//    slots, and the (TX x TY) tiles of u(t-1) and m of the output plane into a ring of NP slots.
+//    Completion is signalled on "full" mbarriers; the 8 consumer warps hand slots back through
+//    "empty" mbarriers (one elected arrive per warp).  There is no CTA-wide barrier in the main
+//    loop, so warps drift apart and hide each other's latency.  Out-of-range box parts are
+//    zero-filled by the TMA unit, which is exactly the Dirichlet halo of the reference.
 //  * The z-neighbours live in a per-thread register queue of 2R+1 float4 (4 consecutive x per
-//    thread); x and y neighbours are read from the shared plane with 128-bit loads.
-//  * u(t-1) is read and u(t+1) written in place with 128-bit global accesses; damping is
-//    separable, three 1-D profiles, so it costs no HBM traffic.
+//    thread) that is rotated at compile time (main loop unrolled by 2R+1); x and y neighbours
+//    are read from the shared plane with 128-bit loads.
+//  * u(t+1) overwrites u(t-1) in place with 128-bit stores; damping is separable (three 1-D
+//    profiles) so it costs no HBM traffic, and tiles/planes outside the absorbing layer take a
+//    branch-free fast path.
 //  Algorithmic HBM traffic: 16 B per grid-point update (u(t), u(t-1), m read; u(t+1) written).
 #include "common.cuh"
 
@@ -36,6 +41,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -60,233 +69,297 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, in
         "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // ---- kernel ------------------------------------------------------------------------------
 struct TmaArgs {
     Grid g;
     Coefs cf;
     float *up;
-    const float *m;
     const float *dx, *dy, *dz;
-    float sdamp;   // dt / irho
+    float sdamp;     // dt / irho
     float irho_c;
-    int zchunk;    // planes per z-chunk
+    int zchunk;      // planes per z-chunk
+    int dlo[3], dhi[3];  // [dlo, dhi): indices where the damping profile of each axis is zero
     Fuse f;
 };
 
-template <int R, int TXT, int TYT, int RY, int NS>
+template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1>
 struct TmaCfg {
     static constexpr int HR = ((R + 3) / 4) * 4;  // x halo in shared memory (float4 aligned)
-    static constexpr int TX = 4 * TXT, TY = TYT * RY;
+    static constexpr int TX = 4 * TXT, TY = TYT;
     static constexpr int PX = TX + 2 * HR, PY = TY + 2 * R;
-    static constexpr int SLOT = ((PX * PY * 4 + 127) / 128) * 128 / 4;  // floats per ring slot
+    static constexpr int SLOT = ((PX * PY * 4 + 127) / 128) * 128 / 4;  // floats per u slot
+    static constexpr int PSLOT = TX * TY;                               // floats per tile
     static constexpr int NQ = 2 * R + 1;
-    static constexpr int NTHREADS = TXT * TYT;
-    static constexpr size_t SMEM = (size_t)NS * SLOT * 4 + NS * 8 + 128;
+    static constexpr int NCONS = TXT * TYT;       // consumer threads
+    static constexpr int NTHREADS = NCONS + 32 * NPW;   // + producer warp(s)
+    static constexpr size_t SMEM =
+        (size_t)NS * SLOT * 4 + (size_t)NP * 2 * PSLOT * 4 + (2 * NS + 2 * NP) * 8 + 128;
 };
 
-__device__ __forceinline__ float f4get(const float4 &v, int e)
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, bool FUSE, int NPW>
+__global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
+    acoustic3d_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP,
+                   const __grid_constant__ CUtensorMap tmM, const TmaArgs a)
 {
-    return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
-}
-
-template <int R, int TXT, int TYT, int RY, int NS, int MINB>
-__global__ void __launch_bounds__(TXT *TYT, MINB)
-    acoustic3d_tma(const __grid_constant__ CUtensorMap tm, const TmaArgs a)
-{
-    typedef TmaCfg<R, TXT, TYT, RY, NS> C;
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
     constexpr int HR = C::HR, TX = C::TX, TY = C::TY, PX = C::PX, PY = C::PY, SLOT = C::SLOT;
-    constexpr int NQ = C::NQ;
+    constexpr int PSLOT = C::PSLOT, NQ = C::NQ, NCW = C::NCONS / 32;
+    // STATIC: ring length == queue length, so ring slots are compile-time constants inside the
+    // unrolled main loop and every shared-memory address is an immediate offset
+    constexpr bool STATIC = (NS == NQ) && (NQ % NP == 0);
+    static_assert(STATIC || ((NS & (NS - 1)) == 0 && (NP & (NP - 1)) == 0),
+                  "dynamic ring sizes must be powers of 2");
     extern __shared__ unsigned char smem_raw[];
-    // 128-byte aligned ring (TMA destination alignment)
-    float *ring = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    uint64_t *bars = (uint64_t *)(ring + NS * SLOT);
+    float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    float *ringP = ringU + NS * SLOT;                 // [NP][2][PSLOT]: u(t-1) tile, m tile
+    uint64_t *fullU = (uint64_t *)(ringP + NP * 2 * PSLOT);
+    uint64_t *emptyU = fullU + NS;
+    uint64_t *fullP = emptyU + NS;
+    uint64_t *emptyP = fullP + NP;
 
     const Grid &g = a.g;
     const Coefs &cf = a.cf;
-    const int tx = threadIdx.x % TXT, ty = threadIdx.x / TXT;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int z0 = blockIdx.z * a.zchunk;
     const int z1 = min(z0 + a.zchunk, g.n[2]);
-    const int total = (z1 - z0) + 2 * R;  // planes this CTA consumes: z0-R .. z1-1+R
-    const int bx = g.hx + x0 - HR, by = g.hy + y0 - R, bz = g.hz + z0 - R;
-    constexpr uint32_t BOX_BYTES = PX * PY * 4;
+    const int nzc = z1 - z0;
+    const int total = nzc + 2 * R;  // u planes this CTA consumes: z0-R .. z1-1+R
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NCW); }
+        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], NCW); }
         fence_barrier_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int npre = total < NS ? total : NS;
-        for (int j = 0; j < npre; j++) {
-            mbar_arrive_expect_tx(&bars[j], BOX_BYTES);
-            tma_load_3d(ring + j * SLOT, &tm, bx, by, bz + j, &bars[j]);
+
+    if (threadIdx.x >= C::NCONS) {
+        // ===== producer warp(s): one lane issues the TMA loads of this CTA =====================
+        // NPW == 1: a single lane issues both streams; NPW == 2: warp 0 streams the haloed u(t)
+        // planes, warp 1 the u(t-1)/m tiles, so neither ring can stall the other.
+        const int pw = (threadIdx.x - C::NCONS) >> 5;
+        if ((threadIdx.x & 31) == 0) {
+            const int bx = g.hx + x0 - HR, by = g.hy + y0 - R, bz = g.hz + z0 - R;
+            const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
+            constexpr uint32_t UBYTES = PX * PY * 4, PBYTES = 2 * PSLOT * 4;
+            if (NPW == 1) {
+                for (int j = 0; j < total; j++) {
+                    const int s = j % NS;
+                    if (j >= NS) mbar_wait(&emptyU[s], (uint32_t)(((j / NS) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullU[s], UBYTES);
+                    tma_load_3d(ringU + s * SLOT, &tmU, bx, by, bz + j, &fullU[s]);
+                    // tiles of output plane z0+i are consumed at iteration i+2R: issue them one
+                    // iteration early (the ring depth NP then allows NP-2 planes of run-ahead)
+                    const int i = j - 2 * R + 1;
+                    if (i >= 0 && i < nzc) {
+                        const int sp = i % NP;
+                        if (i >= NP) mbar_wait(&emptyP[sp], (uint32_t)(((i / NP) - 1) & 1));
+                        mbar_arrive_expect_tx(&fullP[sp], PBYTES);
+                        tma_load_3d(ringP + sp * 2 * PSLOT, &tmP, tx0, ty0, tz0 + i, &fullP[sp]);
+                        tma_load_3d(ringP + sp * 2 * PSLOT + PSLOT, &tmM, tx0, ty0, tz0 + i, &fullP[sp]);
+                    }
+                }
+            } else if (pw == 0) {
+                for (int j = 0; j < total; j++) {
+                    const int s = j % NS;
+                    if (j >= NS) mbar_wait(&emptyU[s], (uint32_t)(((j / NS) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullU[s], UBYTES);
+                    tma_load_3d(ringU + s * SLOT, &tmU, bx, by, bz + j, &fullU[s]);
+                }
+            } else {
+                for (int i = 0; i < nzc; i++) {
+                    const int sp = i % NP;
+                    if (i >= NP) mbar_wait(&emptyP[sp], (uint32_t)(((i / NP) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullP[sp], PBYTES);
+                    tma_load_3d(ringP + sp * 2 * PSLOT, &tmP, tx0, ty0, tz0 + i, &fullP[sp]);
+                    tma_load_3d(ringP + sp * 2 * PSLOT + PSLOT, &tmM, tx0, ty0, tz0 + i, &fullP[sp]);
+                }
+            }
         }
+        return;
     }
 
-    const int x = x0 + 4 * tx;
-    const bool xact = x < g.n[0];
+    // ===== consumer warps ===================================================================
+    const int tx = threadIdx.x % TXT, ty = threadIdx.x / TXT;
+    const int lane = threadIdx.x & 31;
+    const int x = x0 + 4 * tx, y = y0 + ty;
+    const bool act = x < g.n[0] && y < g.n[1];
     const bool xfull = x + 3 < g.n[0];
-    float4 q[RY][NQ];
+    float4 q[NQ];
 #pragma unroll
-    for (int j = 0; j < RY; j++)
-#pragma unroll
-        for (int k = 0; k < NQ; k++) q[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < NQ; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // damping profile along x for this thread's 4 points
-    float sx[4], sy[RY];
-    {
-        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xact) d4 = *(const float4 *)(a.dx + x);  // profile arrays are padded 8 past n[0]
-        sx[0] = d4.x; sx[1] = d4.y; sx[2] = d4.z; sx[3] = d4.w;
-#pragma unroll
-        for (int j = 0; j < RY; j++) {
-            int y = y0 + ty * RY + j;
-            sy[j] = y < g.n[1] ? a.dy[y] : 0.f;
-        }
+    // damping along x and y for this thread's points: (dx + dy), z added per plane
+    float sxy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        const float4 d4 = *(const float4 *)(a.dx + x);  // profile arrays are padded 8 past n[0]
+        const float dyv = a.dy[y];
+        sxy[0] = d4.x + dyv; sxy[1] = d4.y + dyv; sxy[2] = d4.z + dyv; sxy[3] = d4.w + dyv;
     }
-    const Fuse &fz = a.f;
-    const bool fuse_any = fz.snap[0] || fz.grad || fz.illum;
-    const bool reg_vec = (fz.reg.lo[0] & 3) == 0;
+    const bool tile_interior = x0 >= a.dlo[0] && x0 + TX <= a.dhi[0] && y0 >= a.dlo[1] &&
+                               y0 + TY <= a.dhi[1];
+    const int sm_own = (ty + R) * PX + HR + 4 * tx;  // this thread's first point in a u slot
+    const int sm_tile = ty * TX + 4 * tx;            // ... and in a tile slot
+    float *gout = a.up + g.at(x, y, z0);             // advanced by sz per output plane
+    [[maybe_unused]] const Fuse &fz = a.f;
+    [[maybe_unused]] const bool reg_vec = FUSE && (fz.reg.lo[0] & 3) == 0;
 
-    for (int jt = 0; jt < total; ++jt) {
-        const int z = z0 + jt - 2 * R;  // output plane of this iteration (if jt >= 2R)
-        const bool out = jt >= 2 * R;
-        // ---- issue the point-wise global loads of the output plane early --------------------
-        float4 upv[RY], mv[RY];
-        long long gi[RY];
-        bool act[RY];
+    for (int jt0 = 0; jt0 < total; jt0 += NQ) {
 #pragma unroll
-        for (int j = 0; j < RY; j++) {
-            int y = y0 + ty * RY + j;
-            act[j] = out && xact && y < g.n[1];
-            gi[j] = g.at(x, y, z);
-            if (act[j]) {
-                upv[j] = *(const float4 *)(a.up + gi[j]);
-                mv[j] = __ldg((const float4 *)(a.m + gi[j]));
-            }
-        }
-        // ---- wait for the incoming plane (z + R) and append it to the z-queue --------------
-        mbar_wait(&bars[jt % NS], (uint32_t)((jt / NS) & 1));
-        const float *tail = ring + (jt % NS) * SLOT;
-#pragma unroll
-        for (int j = 0; j < RY; j++) {
-#pragma unroll
-            for (int k = 0; k < NQ - 1; k++) q[j][k] = q[j][k + 1];
-            q[j][NQ - 1] = *(const float4 *)(tail + (ty * RY + j + R) * PX + HR + 4 * tx);
-        }
-        if (out) {
-            const float *cen = ring + ((jt - R) % NS) * SLOT;
-            float lap[RY][4];
-            // z part (register queue)
-#pragma unroll
-            for (int j = 0; j < RY; j++)
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    float acc = cf.c0 * f4get(q[j][R], e);
-#pragma unroll
-                    for (int k = 1; k <= R; k++)
-                        acc += cf.cz[k] * (f4get(q[j][R + k], e) + f4get(q[j][R - k], e));
-                    lap[j][e] = acc;
-                }
-            // x part (shared plane, row of the point)
-#pragma unroll
-            for (int j = 0; j < RY; j++) {
-                const float *crow = cen + (ty * RY + j + R) * PX + 4 * tx;
-                float w[4 + 2 * HR];
-#pragma unroll
-                for (int v = 0; v < 1 + 2 * (HR / 4); v++) {
-                    float4 t = *(const float4 *)(crow + 4 * v);
-                    w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+        for (int ph = 0; ph < NQ; ph++) {
+            const int jt = jt0 + ph;
+            if (jt >= total) break;
+            // queue element of z-offset k (k = R is the centre, k = 2R the incoming plane)
+#define Q(k) q[((ph) + 1 + (k)) % NQ]
+            // ---- incoming plane z + R ------------------------------------------------------
+            const int st = STATIC ? ph : (jt % NS);                     // slot of the incoming plane
+            const int sc = STATIC ? (ph + NQ - R) % NQ : ((jt + NS - R) % NS);  // slot of the centre
+            mbar_wait(&fullU[st], (uint32_t)((jt / NS) & 1));
+            Q(2 * R) = *(const float4 *)(ringU + st * SLOT + sm_own);
+            if (jt >= 2 * R) {
+                const int i = jt - 2 * R;  // output plane index inside the chunk
+                const int z = z0 + i;
+                const float *cen = ringU + sc * SLOT;
+                // z part (register queue), x part (row), y part (column): three accumulators
+                float lz[4], lx[4], ly[4];
+                {
+                    const float4 c = Q(R);
+                    lz[0] = cf.c0 * c.x; lz[1] = cf.c0 * c.y; lz[2] = cf.c0 * c.z; lz[3] = cf.c0 * c.w;
                 }
 #pragma unroll
-                for (int e = 0; e < 4; e++)
-#pragma unroll
-                    for (int k = 1; k <= R; k++)
-                        lap[j][e] += cf.cx[k] * (w[HR + e + k] + w[HR + e - k]);
-            }
-            // y part (shared plane, column of the points; rows shared by the RY outputs)
-#pragma unroll
-            for (int rr = 0; rr < RY + 2 * R; rr++) {
-                float4 t = *(const float4 *)(cen + (ty * RY + rr) * PX + HR + 4 * tx);
-#pragma unroll
-                for (int j = 0; j < RY; j++) {
-                    const int k = rr - R - j;
-                    if (k != 0 && k >= -R && k <= R) {
-                        const float c = cf.cy[k < 0 ? -k : k];
-                        lap[j][0] += c * t.x; lap[j][1] += c * t.y;
-                        lap[j][2] += c * t.z; lap[j][3] += c * t.w;
-                    }
+                for (int k = 1; k <= R; k++) {
+                    const float4 p = Q(R + k), m_ = Q(R - k);
+                    lz[0] += cf.cz[k] * (p.x + m_.x); lz[1] += cf.cz[k] * (p.y + m_.y);
+                    lz[2] += cf.cz[k] * (p.z + m_.z); lz[3] += cf.cz[k] * (p.w + m_.w);
                 }
-            }
-            // ---- time update + fused extras ------------------------------------------------
-            const float sz = a.dz[z];
+                {
+                    const float *crow = cen + sm_own - HR;
+                    float w[4 + 2 * HR];
 #pragma unroll
-            for (int j = 0; j < RY; j++) {
-                if (!act[j]) continue;
-                const int y = y0 + ty * RY + j;
-                float uc[4] = {q[j][R].x, q[j][R].y, q[j][R].z, q[j][R].w};
-                float up4[4] = {upv[j].x, upv[j].y, upv[j].z, upv[j].w};
-                float m4[4] = {mv[j].x, mv[j].y, mv[j].z, mv[j].w};
-                float un[4], delta[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    float s = ((sx[e] + sy[j]) + sz) * a.sdamp;
-                    float rden = __frcp_rn(m4[e] + s);
-                    float d1 = uc[e] - up4[e];
-                    delta[e] = (lap[j][e] - s * d1) * rden;
-                    un[e] = (uc[e] + d1) + delta[e];
-                }
-                if (xfull) *(float4 *)(a.up + gi[j]) = make_float4(un[0], un[1], un[2], un[3]);
-                else {
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (x + e < g.n[0]) a.up[gi[j] + e] = un[e];
-                }
-                if (fuse_any && y >= fz.reg.lo[1] && y < fz.reg.hi[1] && z >= fz.reg.lo[2] &&
-                    z < fz.reg.hi[2] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0]) {
-                    const long long ri = fz.reg.at(x, y, z);
-                    const bool vec = reg_vec && x >= fz.reg.lo[0] && x + 3 < fz.reg.hi[0];
-                    if (vec) {
-                        if (fz.snap[0])
-                            *(float4 *)(fz.snap[0] + ri) = make_float4(uc[0], uc[1], uc[2], uc[3]);
-                        if (fz.illum) {
-                            float4 I = *(float4 *)(fz.illum + ri);
-                            I.x += cf.dt * uc[0] * uc[0]; I.y += cf.dt * uc[1] * uc[1];
-                            I.z += cf.dt * uc[2] * uc[2]; I.w += cf.dt * uc[3] * uc[3];
-                            *(float4 *)(fz.illum + ri) = I;
-                        }
-                        if (fz.grad) {
-                            const float gc = fz.gcoef * a.irho_c;
-                            float4 us = __ldg((const float4 *)(fz.usnap[0] + ri));
-                            float4 G = *(float4 *)(fz.grad + ri);
-                            G.x -= gc * us.x * delta[0]; G.y -= gc * us.y * delta[1];
-                            G.z -= gc * us.z * delta[2]; G.w -= gc * us.w * delta[3];
-                            *(float4 *)(fz.grad + ri) = G;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
-                            if (fz.snap[0]) fz.snap[0][ri + e] = uc[e];
-                            if (fz.illum) fz.illum[ri + e] += cf.dt * uc[e] * uc[e];
-                            if (fz.grad)
-                                fz.grad[ri + e] -= fz.gcoef * a.irho_c * fz.usnap[0][ri + e] * delta[e];
+                    for (int v = 0; v < 1 + 2 * (HR / 4); v++) {
+                        if (v == HR / 4) {  // the centre vector is already in the queue
+                            const float4 c = Q(R);
+                            w[4 * v] = c.x; w[4 * v + 1] = c.y; w[4 * v + 2] = c.z; w[4 * v + 3] = c.w;
+                        } else {
+                            const float4 t = *(const float4 *)(crow + 4 * v);
+                            w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
                         }
                     }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        lx[e] = cf.cx[1] * (w[HR + e + 1] + w[HR + e - 1]);
+#pragma unroll
+                        for (int k = 2; k <= R; k++) lx[e] += cf.cx[k] * (w[HR + e + k] + w[HR + e - k]);
+                    }
                 }
+                {
+                    const float *ccol = cen + sm_own;
+                    {
+                        const float4 p = *(const float4 *)(ccol + PX), m_ = *(const float4 *)(ccol - PX);
+                        ly[0] = cf.cy[1] * (p.x + m_.x); ly[1] = cf.cy[1] * (p.y + m_.y);
+                        ly[2] = cf.cy[1] * (p.z + m_.z); ly[3] = cf.cy[1] * (p.w + m_.w);
+                    }
+#pragma unroll
+                    for (int k = 2; k <= R; k++) {
+                        const float4 p = *(const float4 *)(ccol + k * PX);
+                        const float4 m_ = *(const float4 *)(ccol - k * PX);
+                        ly[0] += cf.cy[k] * (p.x + m_.x); ly[1] += cf.cy[k] * (p.y + m_.y);
+                        ly[2] += cf.cy[k] * (p.z + m_.z); ly[3] += cf.cy[k] * (p.w + m_.w);
+                    }
+                }
+                // the centre plane is dead for this warp: hand its slot back to the producer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyU[sc]);
+                // ---- u(t-1) and m tiles of the output plane ----------------------------------
+                const int sp = STATIC ? (ph + 4 * NQ - 2 * R) % NP : (i % NP);
+                mbar_wait(&fullP[sp], (uint32_t)((i / NP) & 1));
+                const float *pt = ringP + sp * 2 * PSLOT + sm_tile;
+                const float4 up4 = *(const float4 *)pt;
+                const float4 m4 = *(const float4 *)(pt + PSLOT);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyP[sp]);
+                const float4 c4 = Q(R);
+                const float uc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float upv[4] = {up4.x, up4.y, up4.z, up4.w};
+                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                float un[4];
+                [[maybe_unused]] float delta[4];
+                if (tile_interior && z >= a.dlo[2] && z < a.dhi[2]) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float lap = (lz[e] + lx[e]) + ly[e];
+                        const float d1 = uc[e] - upv[e];
+                        delta[e] = lap * rcp_approx(mv[e]);
+                        un[e] = (uc[e] + d1) + delta[e];
+                    }
+                } else {
+                    const float szv = a.dz[z];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float lap = (lz[e] + lx[e]) + ly[e];
+                        const float s = (sxy[e] + szv) * a.sdamp;
+                        const float d1 = uc[e] - upv[e];
+                        delta[e] = (lap - s * d1) * rcp_approx(mv[e] + s);
+                        un[e] = (uc[e] + d1) + delta[e];
+                    }
+                }
+                if (act) {
+                    if (xfull) *(float4 *)gout = make_float4(un[0], un[1], un[2], un[3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (x + e < g.n[0]) gout[e] = un[e];
+                    }
+                }
+                if (FUSE) {
+                    if (act && y >= fz.reg.lo[1] && y < fz.reg.hi[1] && z >= fz.reg.lo[2] &&
+                        z < fz.reg.hi[2] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0]) {
+                        const long long ri = fz.reg.at(x, y, z);
+                        const bool vec = reg_vec && x >= fz.reg.lo[0] && x + 3 < fz.reg.hi[0];
+                        if (vec) {
+                            if (fz.snap[0])
+                                *(float4 *)(fz.snap[0] + ri) = make_float4(uc[0], uc[1], uc[2], uc[3]);
+                            if (fz.illum) {
+                                float4 I = *(float4 *)(fz.illum + ri);
+                                I.x += cf.dt * uc[0] * uc[0]; I.y += cf.dt * uc[1] * uc[1];
+                                I.z += cf.dt * uc[2] * uc[2]; I.w += cf.dt * uc[3] * uc[3];
+                                *(float4 *)(fz.illum + ri) = I;
+                            }
+                            if (fz.grad) {
+                                const float gc = fz.gcoef * a.irho_c;
+                                const float4 us = __ldg((const float4 *)(fz.usnap[0] + ri));
+                                float4 G = *(float4 *)(fz.grad + ri);
+                                G.x -= gc * us.x * delta[0]; G.y -= gc * us.y * delta[1];
+                                G.z -= gc * us.z * delta[2]; G.w -= gc * us.w * delta[3];
+                                *(float4 *)(fz.grad + ri) = G;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
+                                if (fz.snap[0]) fz.snap[0][ri + e] = uc[e];
+                                if (fz.illum) fz.illum[ri + e] += cf.dt * uc[e] * uc[e];
+                                if (fz.grad)
+                                    fz.grad[ri + e] -=
+                                        fz.gcoef * a.irho_c * fz.usnap[0][ri + e] * delta[e];
+                            }
+                        }
+                    }
+                }
+                gout += g.sz;
+            } else if (jt >= R) {
+                // planes below the chunk are never centres: release them as soon as R newer
+                // planes have arrived (keeps the producer's slot accounting uniform)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyU[sc]);
             }
-        }
-        // ---- the centre plane is now dead: refill its slot NS planes ahead ------------------
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int jc = jt - R;
-            if (jc >= 0 && jc + NS < total) {
-                const int s = jc % NS;
-                mbar_arrive_expect_tx(&bars[s], BOX_BYTES);
-                tma_load_3d(ring + s * SLOT, &tm, bx, by, bz + jc + NS, &bars[s]);
-            }
+#undef Q
         }
     }
 }
@@ -297,16 +370,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct TileVariant { int txt, tyt, ry; };
-static const TileVariant kVariants[] = {{16, 16, 1}, {32, 8, 2}, {16, 16, 2}, {32, 8, 1}};
+struct TileVariant { int txt, tyt; };
+static const TileVariant kVariants[] = {{16, 16}, {32, 8}, {16, 8}, {32, 4},
+                                        {16, 16}, {32, 8}, {16, 16}, {16, 8}};
+static const int kNumVariants = 8;
 
-static void variant_box(const judi_model *M, int &px, int &py)
+static int variant_of(const judi_model *M)
 {
     int v = M->ctx->opt_tile;
-    if (v < 0 || v > 3 || M->r != 4) v = 0;
-    int R = M->r, HR = ((R + 3) / 4) * 4;
-    px = 4 * kVariants[v].txt + 2 * HR;
-    py = kVariants[v].tyt * kVariants[v].ry + 2 * R;
+    if (v < 0 || v >= kNumVariants || M->r != 4) v = 6;
+    return v;
 }
 
 bool tma3d_supported(const judi_model *M)
@@ -315,17 +388,15 @@ bool tma3d_supported(const judi_model *M)
            M->ctx->encode_tiled != nullptr;
 }
 
-void tma3d_encode(const judi_model *M, float *base, CUtensorMap *out)
+static void encode_box(const judi_model *M, const float *base, int bx, int by, CUtensorMap *out)
 {
     const Grid &g = M->g;
-    int px, py;
-    variant_box(M, px, py);
     cuuint64_t dims[3] = {(cuuint64_t)g.px, (cuuint64_t)g.py, (cuuint64_t)g.pz};
     cuuint64_t strides[2] = {(cuuint64_t)g.sy * 4, (cuuint64_t)g.sz * 4};
-    cuuint32_t box[3] = {(cuuint32_t)px, (cuuint32_t)py, 1};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = ((EncodeTiledFn)M->ctx->encode_tiled)(
-        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+        out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
@@ -335,15 +406,29 @@ void tma3d_encode(const judi_model *M, float *base, CUtensorMap *out)
     }
 }
 
-template <int R, int TXT, int TYT, int RY, int NS, int MINB>
-static void launch_variant(const judi_model *M, const StepArgs &s, const CUtensorMap *tm)
+// halo-box map (whole haloed plane of u(t)) and tile-box map (u(t-1), m) of one buffer
+void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map)
 {
-    typedef TmaCfg<R, TXT, TYT, RY, NS> C;
+    int v = variant_of(M);
+    int R = M->r, HR = ((R + 3) / 4) * 4;
+    int tx = 4 * kVariants[v].txt, ty = kVariants[v].tyt;
+    if (halo_map) encode_box(M, base, tx + 2 * HR, ty + 2 * R, halo_map);
+    if (tile_map) encode_box(M, base, tx, ty, tile_map);
+}
+
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1>
+static void launch_variant(const judi_model *M, const StepArgs &s)
+{
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
     judi_ctx *ctx = M->ctx;
-    auto kern = acoustic3d_tma<R, TXT, TYT, RY, NS, MINB>;
+    const bool fuse = s.f.snap[0] || s.f.grad || s.f.illum;
+    auto kplain = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, false, NPW>;
+    auto kfuse = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, true, NPW>;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(kplain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)C::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(kfuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)C::SMEM));
         configured = true;
     }
@@ -352,10 +437,13 @@ static void launch_variant(const judi_model *M, const StepArgs &s, const CUtenso
     a.g = M->g;
     a.cf = M->cf;
     a.up = s.up[0];
-    a.m = M->m.p;
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.sdamp = M->dt / M->irho_c;
     a.irho_c = M->irho_c;
+    for (int d = 0; d < 3; d++) {
+        a.dlo[d] = M->padl[d] > 3 ? M->padl[d] - 3 : 0;
+        a.dhi[d] = M->N[d] - (M->padr[d] > 3 ? M->padr[d] - 3 : 0);
+    }
     a.f = s.f;
     int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
     int nzc = ctx->opt_zchunks;
@@ -371,21 +459,25 @@ static void launch_variant(const judi_model *M, const StepArgs &s, const CUtenso
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     dim3 grd(ntx, nty, nzc);
-    kern<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*tm, a);
+    if (fuse) kfuse<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
+    else kplain<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
     launch_count(ctx, "acoustic3d_tma");
 }
 
 void tma3d_step(const judi_model *M, const StepArgs &s)
 {
-    const CUtensorMap *tm = s.tmap;
-    JUDI_REQUIRE(tm != nullptr, "tensor map missing");
-    int v = M->ctx->opt_tile;
-    if (M->r == 2) { launch_variant<2, 16, 16, 1, 6, 2>(M, s, tm); return; }
-    if (M->r == 8) { launch_variant<8, 16, 16, 1, 12, 1>(M, s, tm); return; }
+    JUDI_REQUIRE(s.tmap && s.tmap_prev && s.tmap_m, "tensor maps missing");
+    int v = variant_of(M);
+    if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2>(M, s); return; }
+    if (M->r == 8) { launch_variant<8, 16, 16, 16, 4, 1>(M, s); return; }
     switch (v) {
-    case 1: launch_variant<4, 32, 8, 2, 8, 1>(M, s, tm); break;
-    case 2: launch_variant<4, 16, 16, 2, 8, 1>(M, s, tm); break;
-    case 3: launch_variant<4, 32, 8, 1, 8, 2>(M, s, tm); break;
-    default: launch_variant<4, 16, 16, 1, 8, 2>(M, s, tm); break;
+    case 1: launch_variant<4, 32, 8, 8, 4, 2>(M, s); break;
+    case 2: launch_variant<4, 16, 8, 8, 4, 3>(M, s); break;
+    case 3: launch_variant<4, 32, 4, 8, 4, 3>(M, s); break;
+    case 4: launch_variant<4, 16, 16, 9, 3, 2, 2>(M, s); break;   // static ring, 2 producer warps
+    case 5: launch_variant<4, 32, 8, 9, 3, 2, 2>(M, s); break;
+    case 6: launch_variant<4, 16, 16, 8, 4, 2, 2>(M, s); break;   // dynamic ring, 2 producer warps
+    case 7: launch_variant<4, 16, 8, 9, 3, 3, 2>(M, s); break;
+    default: launch_variant<4, 16, 16, 8, 4, 2>(M, s); break;
     }
 }
