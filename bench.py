@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- FWI-gradient throughput of the B200 backend on BASELINE.json's headline workload.
+
+Workload (config.workload): 3-D isotropic acoustic, space order 8, FWI gradient
+(`J_adjoint(..., return_obj=True)` = forward with snapshots + adjoint with the fused imaging
+condition), SURVEY.md 8(d) config C3's grid: n = 401x401x201 @ 25 m (padded 481x481x281 =
+65.0 M points), 101x101 receivers, T = 2 s (nt = 1042), subsampling_factor 4.
+A "step" is ONE shot per GPU (weak scaling: N GPUs -> N shots per step) followed by the
+all-reduce of (gradient, objective) over the ranks -- the only collective of the path.
+
+  value  : shots/s with model, wavelet and observed data resident in HBM before the timed region
+  e2e    : the same through the host-buffer call a JUDI worker makes per shot
+           (Model(...) from host arrays -> J_adjoint with host arrays -> gradient back on host)
+  roofline: the stencil kernel (acoustic3d_tma), algorithmic bytes / CUDA-event time per launch
+  cpu_baseline / --impl reference: the CPU oracle (a port of the reference's Devito schedule --
+           Devito itself cannot be installed here) on the host cores, bounded sample.
+
+Launch: `python bench.py --gpus 1 --steps K --warmup W`, or for N > 1
+`python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (401, 401, 201)
+SPACING = (25., 25., 25.)
+NBL = 40
+SO = 8
+T_MS = 2000.
+F0 = 0.008
+DT = 1.921          # critical dt of the true model (vmax 5.5 km/s), passed as dt_comp
+T_SUB = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--t-sub", type=int, default=T_SUB)
+    ap.add_argument("--shape", type=int, nargs=3, default=list(SHAPE))
+    ap.add_argument("--tn", type=float, default=T_MS)
+    ap.add_argument("--snapshot-region", default="physical", choices=["physical", "padded"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ---- synthetic "overthrust-shaped" model --------------------------------------------
+def velocity(shape):
+    nx, ny, nz = shape
+    x = (np.arange(nx, dtype=np.float32) * SPACING[0]).reshape(nx, 1, 1)
+    y = (np.arange(ny, dtype=np.float32) * SPACING[1]).reshape(1, ny, 1)
+    z = (np.arange(nz, dtype=np.float32) * SPACING[2]).reshape(1, 1, nz)
+    zr = z / np.float32((SHAPE[2] - 1) * SPACING[2])
+    v = 1.5 + 4.0 * zr + 0.4 * np.sin(2 * np.pi * x / 5000.) * np.sin(2 * np.pi * y / 7000.) * zr
+    v = np.clip(v, 1.5, 5.5).astype(np.float32)
+    v[:, :, :21] = 1.5          # water layer
+    v[0, 0, -1] = 5.5           # pins vmax so that dt = 1.921 ms for every sub-shape
+    return v
+
+
+def smooth_model(v):
+    from scipy.ndimage import gaussian_filter1d
+    v0 = gaussian_filter1d(v, sigma=10, axis=2, mode="nearest").astype(np.float32)
+    v0[:, :, :21] = 1.5
+    return v0
+
+
+def geometry(shape, shot):
+    ex = (shape[0] - 1) * SPACING[0]
+    ey = (shape[1] - 1) * SPACING[1]
+    gx = np.linspace(0.15 * ex, 0.85 * ex, 8)
+    gy = np.linspace(0.15 * ey, 0.85 * ey, 8)
+    i, j = shot % 8, (shot // 8) % 8
+    src = np.array([[gx[i], gy[j], 50.]], dtype=np.float32)
+    xr, yr = np.meshgrid(np.linspace(0., ex, 101), np.linspace(0., ey, 101), indexing="ij")
+    rec = np.stack([xr.ravel(), yr.ravel(), np.full(xr.size, 50.)], axis=1).astype(np.float32)
+    return src, rec
+
+
+def ricker(nt, dt, f0):
+    t = np.arange(nt, dtype=np.float32) * np.float32(dt)
+    r = np.pi * f0 * (t - 1 / f0)
+    return ((1 - 2 * r ** 2) * np.exp(-r ** 2)).astype(np.float32).reshape(nt, 1)
+
+
+def workload_name(shape, nt, t_sub, region):
+    return ("3D acoustic so=8 FWI gradient (fwd+snapshots, adj+IC), n=%dx%dx%d d=25m nbl=40, "
+            "10201 receivers, nt=%d, t_sub=%d, %s-domain snapshots, 1 shot/GPU/step"
+            % (shape[0], shape[1], shape[2], nt, t_sub, region))
+
+
+# ---- clocks -------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [s.strip() for s in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ---- CPU arm: the oracle on the host cores -------------------------------------------------------
+def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0):
+    """Times a bounded sample of the workload with the CPU oracle (all host threads):
+    `ns` forward steps + `ns` adjoint+IC steps on the full grid, extrapolated to one shot."""
+    from oracle import oracle as O
+    O.build()
+    v0 = smooth_model(velocity(shape))
+    model = O.Model((0., 0., 0.), SPACING, shape, space_order=SO, nbl=NBL,
+                    m=(1 / v0 ** 2).astype(np.float32), dt=DT, precision="f32")
+    t1 = O.time_steps(model, 2, True, t_sub)          # calibration (also first-touch of memory)
+    per_pair = max(t1 / 2, 1e-6)
+    ns = int(max(4, min(nt - 2, seconds / per_pair)))
+    ns -= ns % t_sub
+    ns = max(ns, t_sub)
+    times = []
+    for _ in range(warmup + steps):
+        times.append(O.time_steps(model, ns, True, t_sub))
+    times = times[warmup:]
+    sec_per_shot = float(np.mean(times)) / ns * (nt - 2)
+    npts = float(np.prod(model.shape_pml))
+    return {"value": 1.0 / sec_per_shot, "unit": "shots/s", "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": "%d of %d forward + %d of %d adjoint+IC time steps on the full %dx%dx%d "
+                      "padded grid (t_sub=%d), extrapolated linearly to one shot; OpenMP, all %d "
+                      "host threads; oracle = C port of the reference's Devito schedule (Devito "
+                      "itself is not installable offline)"
+                      % (ns, nt - 2, ns, nt - 2, model.shape_pml[0], model.shape_pml[1],
+                         model.shape_pml[2], t_sub, os.cpu_count()),
+            "gpts_per_s": 2 * ns * npts / float(np.mean(times)) / 1e9,
+            "ms_per_step": 1e3 * sec_per_shot}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = tuple(args.shape)
+    nt = int(np.floor(args.tn / DT)) + 1
+    r = cpu_sample(shape, nt, args.t_sub, args.cpu_seconds / 2, steps=args.steps,
+                   warmup=args.warmup)
+    line = {"impl": "reference", "metric": "fwi_gradient_shots_per_s", "value": r["value"],
+            "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region),
+                       "note": "CPU arm: one process, all host threads, no GPU"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "gpts_per_s": r["gpts_per_s"],
+            "e2e": {"value": r["value"], "unit": "shots/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ---------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import judi_jl_b200 as J
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = J.get_context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    shape = tuple(args.shape)
+    nt = int(np.floor(args.tn / DT)) + 1
+    v = velocity(shape)
+    v0 = smooth_model(v)
+    m_true = np.asfortranarray((1 / v ** 2).astype(np.float32))
+    m0 = np.asfortranarray((1 / v0 ** 2).astype(np.float32))
+    src, rec = geometry(shape, rank)
+    q = ricker(nt, DT, F0)
+    nrec = rec.shape[0]
+    kw = dict(space_order=SO, nbl=NBL, dt=DT)
+
+    # ---- untimed setup: observed data of this rank's shot from the true model ---------------
+    mt = J.Model((0., 0., 0.), SPACING, shape, m=m_true, **kw)
+    dobs, _ = J.forward_rec(mt, src, q, rec)
+    del mt
+    npad = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # device-resident inputs (x fastest == reversed shape, contiguous)
+        m0_d = torch.from_numpy(np.ascontiguousarray(m0.transpose(2, 1, 0))).to(dev)
+        q_d = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev)
+        dobs_d = torch.from_numpy(np.ascontiguousarray(dobs.T)).to(dev)
+        model = J.Model((0., 0., 0.), SPACING, shape, m=m0_d, **kw)
+        npad = model.shape_pml
+        ngrid = int(np.prod(npad))
+        red = torch.zeros(ngrid + 1, dtype=torch.float32, device=dev)   # gradient + objective
+        grad_d, f_d = red[:ngrid], red[ngrid:]
+        opts = dict(return_obj=True, t_sub=args.t_sub, snapshot_region=args.snapshot_region,
+                    grad_out=grad_d, f_out=f_d)
+
+        def step_device():
+            red.zero_()
+            J.J_adjoint(model, src, q_d, rec, dobs_d, accumulate=True, **opts)
+            if world > 1:
+                dist.all_reduce(red, op=dist.ReduceOp.SUM)
+
+        ctx.set_option("timing", 1)
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        ctx.reset_stats()
+        clocks = ClockSampler(local)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        clk = clocks.stop()
+        ms = e0.elapsed_time(e1)
+        stats = ctx.stencil_stats()
+        launches = ctx.launch_count
+        fval = float(f_d.item())
+        gnorm = float(torch.linalg.vector_norm(grad_d).item())
+        ctx.set_option("timing", 0)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+        # ---- e2e: host buffers in, host gradient out, every step --------------------------------
+        e2e = None
+        if not args.no_e2e:
+            def pinned(a):
+                tt = torch.empty(a.shape[::-1], dtype=torch.float32).pin_memory()
+                h = tt.numpy().T           # F-ordered view of pinned memory
+                h[...] = a
+                return tt, h
+            keep_m, m0_h = pinned(m0)
+            keep_q, q_h = pinned(q)
+            keep_d, d_h = pinned(dobs)
+            keep_g, g_h = pinned(np.zeros(npad, dtype=np.float32))
+
+            def step_host():
+                mh = J.Model((0., 0., 0.), SPACING, shape, m=m0_h, **kw)
+                f, g, _, _ = J.J_adjoint(mh, src, q_h, rec, d_h, return_obj=True, t_sub=args.t_sub,
+                                         snapshot_region=args.snapshot_region, grad_out=g_h)
+                if world > 1:
+                    f, g = J.objectives.reduce_fg(f, g)
+                return f, g
+            for _ in range(min(args.warmup, 2)):
+                step_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fh, gh = step_host()
+            barrier()
+            wall = time.perf_counter() - t0
+            t = torch.tensor([wall], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+            h2d = m0.nbytes + q.nbytes + dobs.nbytes + (4 * (ngrid + 1) if world > 1 else 0)
+            d2h = 4 * ngrid + 4 + (4 * (ngrid + 1) if world > 1 else 0)
+            e2e = {"value": world * args.steps / wall, "unit": "shots/s",
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": 1e3 * wall / args.steps,
+                   "f_matches_device_path": bool(abs(float(fh) * (1 if world == 1 else 1.0) - fval)
+                                                 <= 1e-3 * abs(fval)) if world == 1 else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the stencil kernel over the timed region --------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    npts = float(ngrid)
+    nphys = float(np.prod(shape)) if args.snapshot_region == "physical" else npts
+    k = args.t_sub
+    nsteps_t = nt - 2
+    nsave = len([t_ for t_ in range(1, nt - 1) if t_ % k == 0])
+    # per shot: fwd launches 16 B/pt (+4 B per snapshot point when saving), adjoint launches
+    # 16 B/pt (+12 B per snapshot point with the imaging condition: read u_s, RMW gradient)
+    bytes_shot = 2 * nsteps_t * 16.0 * npts + nsave * (4.0 + 12.0) * nphys
+    alg_bytes_per_launch = bytes_shot / (2 * nsteps_t)
+    ms_launch = stats["ms"] / max(stats["launches"], 1)
+    achieved = alg_bytes_per_launch / (ms_launch * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            "acoustic3d_tma_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "acoustic3d_tma (fwd / fwd+save / adj / adj+IC launches averaged)",
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "avg_launch_ms": ms_launch, "launches_timed": stats["launches"],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
+                               "fallback 6650 GB/s (of fallback)"}
+
+    shots = world * args.steps
+    line = {"metric": "fwi_gradient_shots_per_s", "value": shots / (ms * 1e-3), "unit": "shots/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region),
+                       "padded_grid": list(npad), "nt": nt, "dt_ms": DT,
+                       "l2_policy": "inputs_larger_than_L2 (each field 260 MB vs 126 MB L2)",
+                       "parallelism": "shots partitioned over %d GPU(s), one all-reduce per step"
+                                      % world},
+            "gpts_per_s": shots * 2 * nsteps_t * npts / (ms * 1e-3) / 1e9,
+            "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
+            "objective": fval, "gradient_l2": gnorm}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = {kk: vv for kk, vv in
+                                cpu_sample(shape, nt, args.t_sub, args.cpu_seconds).items()
+                                if kk in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -292,21 +292,23 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 [[maybe_unused]] float delta[4];
                 if (tile_interior && z >= a.dlo[2] && z < a.dhi[2]) {
 #pragma unroll
+                    // explicit rounding intrinsics: the plain and the fused instantiation must
+                    // produce bit-identical wavefields (checkpoint recomputation relies on it)
                     for (int e = 0; e < 4; e++) {
-                        const float lap = (lz[e] + lx[e]) + ly[e];
-                        const float d1 = uc[e] - upv[e];
-                        delta[e] = lap * rcp_approx(mv[e]);
-                        un[e] = (uc[e] + d1) + delta[e];
+                        const float lap = __fadd_rn(__fadd_rn(lz[e], lx[e]), ly[e]);
+                        const float d1 = __fsub_rn(uc[e], upv[e]);
+                        delta[e] = __fmul_rn(lap, rcp_approx(mv[e]));
+                        un[e] = __fadd_rn(__fadd_rn(uc[e], d1), delta[e]);
                     }
                 } else {
                     const float szv = a.dz[z];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
-                        const float lap = (lz[e] + lx[e]) + ly[e];
-                        const float s = (sxy[e] + szv) * a.sdamp;
-                        const float d1 = uc[e] - upv[e];
-                        delta[e] = (lap - s * d1) * rcp_approx(mv[e] + s);
-                        un[e] = (uc[e] + d1) + delta[e];
+                        const float lap = __fadd_rn(__fadd_rn(lz[e], lx[e]), ly[e]);
+                        const float s = __fmul_rn(__fadd_rn(sxy[e], szv), a.sdamp);
+                        const float d1 = __fsub_rn(uc[e], upv[e]);
+                        delta[e] = __fmul_rn(__fmaf_rn(-s, d1, lap), rcp_approx(__fadd_rn(mv[e], s)));
+                        un[e] = __fadd_rn(__fadd_rn(uc[e], d1), delta[e]);
                     }
                 }
                 if (act) {

@@ -1,0 +1,121 @@
+# B200Backend.jl -- the reference-side binding of libjudi_b200.so.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI (the build image has no Julia).  It is the `ccall` twin of
+# JUDI's ten `devito_interface` methods (src/TimeModeling/Modeling/python_interface.jl:30-198) and of
+# the `ac.J_adjoint` call in `_multi_src_fg` (src/TimeModeling/Modeling/misfit_fg.jl:69-73).
+# Include it from src/JUDI.jl after python_interface.jl and select it with JUDI.set_backend(:b200)
+# (or ENV["JUDI_BACKEND"]="b200"); everything above `devito_interface` stays untouched.
+module B200Backend
+
+using ..JUDI: Geometry, JUDIOptions, PhysicalParameter, AbstractModel, time_resample,
+              _maybe_pad_t0, setup_grid, origin, spacing, nbl, _params
+
+const LIB = get(ENV, "JUDI_B200_LIB", "libjudi_b200.so")
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+struct JudiParam           # judi_param
+    kind::Cint; value::Cfloat; data::Ptr{Cfloat}
+end
+none() = JudiParam(0, 0f0, C_NULL)
+param(::Nothing) = none()
+param(x::Number) = JudiParam(1, Float32(x), C_NULL)
+param(x::Array{Float32}) = JudiParam(2, 0f0, pointer(x))        # Julia arrays are x-fastest: no copy
+param(x::PhysicalParameter) = param(x.data)
+
+struct JudiModelDesc       # judi_model_desc
+    ndim::Cint; shape::NTuple{3,Cint}; spacing::NTuple{3,Cfloat}; origin::NTuple{3,Cfloat}
+    nbl::Cint; space_order::Cint; fs::Cint; dt::Cfloat
+    m::JudiParam; rho::JudiParam; b::JudiParam; epsilon::JudiParam; delta::JudiParam
+    theta::JudiParam; phi::JudiParam; dm::JudiParam; params_on_device::Cint
+end
+
+struct JudiJopts           # judi_jopts
+    is_residual::Cint; checkpointing::Cint; n_checkpoints::Cint; t_sub::Cint; ic::Cint
+    born_fwd::Cint; nlind::Cint; illum::Cint; snapshot_region::Cint
+end
+
+lasterr() = unsafe_string(ccall((:judi_last_error, LIB), Cstring, ()))
+check(rc) = rc == 0 || error("judi_b200: " * lasterr())      # `retry` in time_modeling_serial.jl:95 still applies
+
+function ctx()
+    if CTX[] == C_NULL
+        dev = parse(Int, get(ENV, "JUDI_B200_DEVICE", "0"))   # one Julia worker per GPU
+        CTX[] = ccall((:judi_ctx_create, LIB), Ptr{Cvoid}, (Cint,), dev)
+        CTX[] == C_NULL && error("judi_b200: " * lasterr())
+    end
+    CTX[]
+end
+
+pad3(t, fill) = ntuple(i -> i <= length(t) ? t[i] : fill, 3)
+const IC = Dict("as" => 0, "isic" => 1, "fwi" => 2)
+
+# replaces devito_model (src/TimeModeling/Utils/auxiliaryFunctions.jl:26-37)
+function b200_model(model::AbstractModel, options::JUDIOptions, dm)
+    p = Dict(_params(model))
+    get_p(k) = haskey(p, k) ? param(p[k]) : none()
+    n = size(model)
+    desc = JudiModelDesc(length(n), Cint.(pad3(n, 1)), Cfloat.(pad3(spacing(model), 1)),
+                         Cfloat.(pad3(origin(model), 0)), nbl(model), options.space_order,
+                         options.free_surface, something(options.dt_comp, 0f0),
+                         get_p(:m), get_p(:rho), none(), get_p(:epsilon), get_p(:delta),
+                         get_p(:theta), get_p(:phi), param(dm), 0)
+    h = GC.@preserve p dm ccall((:judi_model_create, LIB), Ptr{Cvoid},
+                                (Ptr{Cvoid}, Ref{JudiModelDesc}), ctx(), desc)
+    h == C_NULL && error("judi_b200: " * lasterr())
+    return h
+end
+critical_dt(h) = ccall((:judi_model_critical_dt, LIB), Cfloat, (Ptr{Cvoid},), h)
+function padded_shape(h, ndim)
+    out = zeros(Cint, ndim); check(ccall((:judi_model_padded_shape, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), h, out)); Tuple(out)
+end
+destroy(h) = ccall((:judi_model_destroy, LIB), Cvoid, (Ptr{Cvoid},), h)
+
+# d_obs = Pr*F*Ps'*q   (python_interface.jl:30-43 -> interface.py:17)
+function b200_interface(h, srcGeometry::Geometry, srcData::Array, recGeometry::Geometry, ::Nothing,
+                        ::Nothing, options::JUDIOptions, illum::Bool, fw::Bool, n)
+    dtComp = critical_dt(h)
+    qIn = _maybe_pad_t0(time_resample(srcData, srcGeometry, dtComp), srcGeometry, recGeometry, dtComp)
+    sc = Float32.(setup_grid(srcGeometry, n)); rc = Float32.(setup_grid(recGeometry, n))   # hcat(x[,y],z)
+    nt = size(qIn, 1); rec = zeros(Float32, nt, size(rc, 1))
+    I = illum ? zeros(Float32, padded_shape(h, length(n))) : nothing
+    check(ccall((:judi_forward_rec, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, fw, size(sc, 1), sc, qIn, nt, size(rc, 1), rc, rec, illum ? I : C_NULL, 0))
+    return illum ? (rec, I) : rec
+end
+
+# d_lin = J*dm         (python_interface.jl:83-99 -> interface.py:208)
+function b200_born(h, srcGeometry, srcData, recGeometry, options::JUDIOptions, illum::Bool, n)
+    dtComp = critical_dt(h)
+    qIn = _maybe_pad_t0(time_resample(srcData, srcGeometry, dtComp), srcGeometry, recGeometry, dtComp)
+    sc = Float32.(setup_grid(srcGeometry, n)); rc = Float32.(setup_grid(recGeometry, n))
+    nt = size(qIn, 1); rec = zeros(Float32, nt, size(rc, 1))
+    check(ccall((:judi_born_rec, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, size(sc, 1), sc, qIn, nt, size(rc, 1), rc, IC[options.IC], rec, C_NULL, 0))
+    return rec
+end
+
+# (f, g) of one shot   (misfit_fg.jl:69-73 / python_interface.jl:102-121 -> interface.py:279)
+function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOptions, n;
+                        is_residual=false, born_fwd=false, nlind=false, illum=false, misfit=nothing)
+    nt = size(qIn, 1)
+    g = zeros(Float32, padded_shape(h, length(n))); f = Ref{Cfloat}(0)
+    Iu = illum ? similar(g) : nothing; Iv = illum ? similar(g) : nothing
+    o = JudiJopts(is_residual, options.optimal_checkpointing, 0, options.subsampling_factor,
+                  IC[options.IC], born_fwd, nlind, illum, options.sum_padding ? 0 : 1)
+    # custom misfit: judi_misfit_fn; the default mse (losses.jl:15-19) stays on the device (C_NULL)
+    cb = misfit === nothing ? C_NULL :
+        @cfunction($((ps, po, pr, nt_, nr_, _) -> begin
+            dsyn = unsafe_wrap(Array, ps, (Int(nt_), Int(nr_))); dobs = unsafe_wrap(Array, po, (Int(nt_), Int(nr_)))
+            fv, r = misfit(dsyn, dobs); copyto!(unsafe_wrap(Array, pr, (Int(nt_), Int(nr_))), r); Cfloat(fv)
+        end), Cfloat, (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cvoid}))
+    check(ccall((:judi_J_adjoint, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ref{JudiJopts},
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, size(src_coords, 1), src_coords, qIn, nt, size(rec_coords, 1), rec_coords, dIn, o,
+                cb, C_NULL, f, g, illum ? Iu : C_NULL, illum ? Iv : C_NULL, 0))
+    return illum ? (f[], g, Iu, Iv) : (f[], g)
+end
+
+end # module

@@ -481,6 +481,72 @@ static void step_fields(const ogrid *g, oscratch *sc, int nf, real *const *u, re
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Vectorised fast path of step_fields for the constant-density isotropic case (compile-time      */
+/* radius, z-contiguous inner loop).  Same operations in the same order as the generic path, so   */
+/* results are bit-identical (tests/test_oracle_properties.py checks this); it exists so that the */
+/* CPU baseline bench.py reports is a fair multi-threaded SIMD implementation.  Optionally fuses  */
+/* the "as" imaging condition G -= w * us * (un - 2u + up)/dt^2 (sensitivity.py:55-69).           */
+static int g_use_fast = 1;
+void oracle_set_fast(int on) { g_use_fast = on; }
+
+#define DEFINE_FAST_STEP(RR)                                                                     \
+    static void fast_step_r##RR(const ogrid *g, const real *restrict u, real *restrict up,      \
+                                const real *restrict us, real *restrict G, real wdt)            \
+    {                                                                                            \
+        const int X = g->N[0], Y = g->N[1], Z = g->N[2], nd = g->ndim;                           \
+        const size_t SX = g->SX, SY = g->SY;                                                     \
+        const real r1 = 1 / (g->dt * g->dt), r2 = 1 / g->dt;                                     \
+        const real ix = 1 / (g->h[0] * g->h[0]), iy = 1 / (g->h[1] * g->h[1]),                   \
+                   iz = 1 / (g->h[2] * g->h[2]);                                                 \
+        const real irho = g->irho_c;                                                             \
+        real c[RR + 1];                                                                          \
+        for (int k = 0; k <= RR; k++) c[k] = g->c2[k];                                           \
+        const real *restrict m = g->m, *restrict damp = g->damp;                                 \
+        _Pragma("omp parallel for collapse(2) schedule(static)")                                 \
+        for (int x = 0; x < X; x++)                                                              \
+            for (int y = 0; y < Y; y++) {                                                        \
+                const size_t i0 = IDX(g, x, y, 0);                                               \
+                _Pragma("omp simd")                                                              \
+                for (int z = 0; z < Z; z++) {                                                    \
+                    const size_t i = i0 + z;                                                     \
+                    real ax = c[0] * u[i], az = c[0] * u[i], ay = c[0] * u[i];                   \
+                    for (int k = 1; k <= RR; k++) {                                              \
+                        ax += c[k] * (u[i + k * SX] + u[i - k * SX]);                            \
+                        az += c[k] * (u[i + k] + u[i - k]);                                      \
+                    }                                                                            \
+                    real L = ax * ix + az * iz;                                                  \
+                    if (nd == 3) {                                                               \
+                        for (int k = 1; k <= RR; k++) ay += c[k] * (u[i + k * SY] + u[i - k * SY]); \
+                        L += ay * iy;                                                            \
+                    }                                                                            \
+                    L = irho * L;                                                                \
+                    const real a = m[i] * irho * r1;                                             \
+                    const real b = damp[i] * r2;                                                 \
+                    const real inv = 1 / (a + b);                                                \
+                    const real uc = u[i], upo = up[i];                                           \
+                    const real un = (a * (2 * uc - upo) + b * uc + L + 0) * inv;                 \
+                    up[i] = un;                                                                  \
+                    if (G) G[i] -= (wdt * irho) * (((un - 2 * uc + upo) * r1) * us[i]);          \
+                }                                                                                \
+            }                                                                                    \
+    }
+DEFINE_FAST_STEP(2)
+DEFINE_FAST_STEP(4)
+DEFINE_FAST_STEP(8)
+
+static int fast_ok(const ogrid *g)
+{
+    return g_use_fast && !flux_form(g) && (g->r == 2 || g->r == 4 || g->r == 8);
+}
+
+static void fast_step(const ogrid *g, const real *u, real *up, const real *us, real *G, real wdt)
+{
+    if (g->r == 2) fast_step_r2(g, u, up, us, G, wdt);
+    else if (g->r == 4) fast_step_r4(g, u, up, us, G, wdt);
+    else fast_step_r8(g, u, up, us, G, wdt);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* forward / adjoint propagation:  operators.py:81-135 schedule                                 */
 /*   pde ; inject src[t] into the new level ; rec[t] = interp(level t) ; save ; illum           */
 /* fw=1: t = 1..nt-2 computing level t+1.  fw=0: t = nt-2..1 computing level t-1.    */
@@ -505,7 +571,8 @@ int oracle_forward(const ogrid *g, int fw, int nt, const osparse *src, const rea
     for (int t = t0; t != t1; t += dtt) {
         real *u[2], *up[2];
         for (int f = 0; f < nf; f++) { u[f] = bufs[f][cur]; up[f] = bufs[f][1 - cur]; }
-        step_fields(g, &sc, nf, u, up, up, NULL);
+        if (fast_ok(g)) fast_step(g, u[0], up[0], NULL, NULL, 0);
+        else step_fields(g, &sc, nf, u, up, up, NULL);
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
         if (rec && rec_out) interpolate(rec, u[0], rec_out + (size_t)t * rec->np);
         if (save_mode && (t % t_sub) == 0)
@@ -755,10 +822,12 @@ int oracle_time_steps(const ogrid *g, int nsteps, int with_gradient, int t_sub, 
     real r1 = 1 / (g->dt * g->dt);
     double t0 = now_s();
     int cur = 0;
+    const int fast = fast_ok(g);
     for (int s = 0; s < nsteps; s++) { /* forward leg (+ snapshot copy every t_sub) */
         real *u[2], *up[2];
         for (int f = 0; f < nf; f++) { u[f] = b[f][cur]; up[f] = b[f][1 - cur]; }
-        step_fields(g, &sc, nf, u, up, up, NULL);
+        if (fast) fast_step(g, u[0], up[0], NULL, NULL, 0);
+        else step_fields(g, &sc, nf, u, up, up, NULL);
         if (with_gradient && (s % t_sub) == 0) memcpy(us, u[0], g->ntot * sizeof(real));
         cur = 1 - cur;
     }
@@ -766,6 +835,12 @@ int oracle_time_steps(const ogrid *g, int nsteps, int with_gradient, int t_sub, 
         for (int s = 0; s < nsteps; s++) { /* adjoint + imaging-condition leg */
             real *v[2], *vp[2];
             for (int f = 0; f < nf; f++) { v[f] = b[f][cur]; vp[f] = b[f][1 - cur]; }
+            if (fast) { /* adjoint step with the imaging condition fused into the same sweep */
+                int ic_on = (s % t_sub) == 0;
+                fast_step(g, v[0], vp[0], ic_on ? us : NULL, ic_on ? G : NULL, (real)t_sub * g->dt);
+                cur = 1 - cur;
+                continue;
+            }
             memcpy(vn, vp[0], g->ntot * sizeof(real));
             step_fields(g, &sc, nf, v, vp, vp, NULL);
             if ((s % t_sub) == 0) {

@@ -64,6 +64,7 @@ def _lib(precision):
                                 ctypes.c_int, P, P]
     lib.oracle_gradient.argtypes = [P, ctypes.c_int, P, P, ctypes.c_int, ctypes.c_int, P, P, P]
     lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
+    lib.oracle_set_fast.argtypes = [ctypes.c_int]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
     _LIBS[precision] = lib
@@ -436,6 +437,11 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     if return_obj:
         return f, g, Iu, Iv
     return g, Iu, Iv
+
+
+def set_fast(on, precision="f32"):
+    """Toggle the vectorised constant-density fast path (bit-identical to the generic one)."""
+    _lib(precision).oracle_set_fast(int(bool(on)))
 
 
 def time_steps(model, nsteps, with_gradient=True, t_sub=1):

@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes -> libjudi_b200.so), against
+the CPU oracle on the same seeded inputs.
+
+Tolerances are the north-star ones (BASELINE.json): shot records <= 1e-4 relative L2, gradients
+<= 1e-3 relative L2, source/receiver indexing bit-exact; adjoint dot tests are held to the
+reference's own single-precision bound of test/test_adjoint.jl:21 (5e-4) and, tighter, 1e-4
+(fp32 accumulation of ~1e3 time steps does not reach 1e-5 in any fp32 implementation -- the fp64
+oracle, which is the same algorithm, passes at 1e-11; see tests/test_oracle_properties.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import model_args, geometry, rel_l2
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NT = 260
+TOL_SHOT = 1e-4
+TOL_GRAD = 1e-3
+TOL_DOT = 1e-4
+
+
+def both(kind, ndim, so, nt=NT, **kw):
+    import judi_jl_b200 as J
+    args = model_args(kind, ndim, so, **kw)
+    gm = J.Model(**args)
+    om = O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dt = float(gm.critical_dt)
+    q = O.ricker_wavelet((nt - 1) * dt, dt, 0.02)[:nt]
+    return J, args, gm, om, src, rec, q, dt
+
+
+CASES = [("iso", 2, 8), ("iso", 2, 4), ("iso", 2, 16), ("rho", 2, 8), ("tti", 2, 8),
+         ("iso", 3, 8), ("iso", 3, 4), ("iso", 3, 16), ("rho", 3, 8), ("tti", 3, 8)]
+
+
+@pytest.mark.parametrize("kind,ndim,so", CASES)
+def test_host_logic_matches_oracle(kind, ndim, so):
+    """critical_dt, padsizes, damping field and padded m are identical; receiver corner indices
+    and weights are bit-exact (geom_utils.py:74-94 / SURVEY A.5)."""
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, so)
+    assert gm.critical_dt == om.critical_dt
+    assert gm.padsizes == om.padsizes
+    assert gm.shape_pml == om.shape_pml
+    assert rel_l2(gm.get_field("damp"), om.damp) < 1e-6
+    assert np.array_equal(gm.get_field("m"), om.m)
+    rng = np.random.default_rng(1)
+    ext = np.array([(s - 1) * h for s, h in zip(args["shape"], args["spacing"])], dtype=np.float32)
+    pts = (rng.random((500, ndim)).astype(np.float32) * (ext + 60) - 30).astype(np.float32)
+    pts = np.concatenate([pts, rec, src, np.zeros((1, ndim), np.float32), ext.reshape(1, -1)])
+    ijk, w, valid = gm.sparse_locate(pts)
+    oijk, ow, ovalid = O.sparse_locate(om, pts)
+    assert np.array_equal(ijk, oijk)
+    assert np.array_equal(valid, ovalid)
+    assert np.array_equal(w.view(np.int32), ow.view(np.int32))
+
+
+@pytest.mark.parametrize("kind,ndim,so", CASES)
+def test_forward_adjoint_parity_and_dot(kind, ndim, so):
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, so)
+    d, I = J.forward_rec(gm, src, q, rec, illum=True)
+    do, Io = O.forward_rec(om, src, q, rec, illum=True)
+    assert np.linalg.norm(do) > 0
+    assert rel_l2(d, do) < TOL_SHOT
+    assert rel_l2(I, Io) < TOL_SHOT
+    assert np.all(d[0] == 0) and np.all(d[-1] == 0)        # rec[0], rec[nt-1] never written (A.2)
+    y = np.random.default_rng(0).standard_normal(d.shape).astype(np.float32)
+    qa, _ = J.forward_rec(gm, rec, y, src, fw=False)
+    qao, _ = O.forward_rec(om, rec, y, src, fw=False)
+    assert rel_l2(qa, qao) < TOL_SHOT
+    a, b = np.vdot(d.astype(np.float64), y), np.vdot(q.astype(np.float64), qa)
+    assert abs((a - b) / (a + b)) < TOL_DOT
+
+
+@pytest.mark.parametrize("kind,ndim,so", CASES)
+def test_born_and_gradient_parity_and_dot(kind, ndim, so):
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, so)
+    dl, _ = J.born_rec(gm, src, q, rec)
+    dlo, _ = O.born_rec(om, src, q, rec)
+    assert np.linalg.norm(dlo) > 0
+    assert rel_l2(dl, dlo) < TOL_SHOT
+    y = np.random.default_rng(0).standard_normal(dl.shape).astype(np.float32)
+    g, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True)
+    go, _, _ = O.J_adjoint(om, src, q, rec, y, is_residual=True)
+    assert rel_l2(g, go) < TOL_GRAD
+    dmp = np.pad(args["dm"], gm.padsizes, mode="edge").astype(np.float64)
+    c, e = dt * np.vdot(dl.astype(np.float64), y), np.vdot(g.astype(np.float64), dmp)
+    assert abs((c - e) / (c + e)) < TOL_DOT
+
+
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3)])
+def test_fwi_objective_and_options(kind, ndim):
+    """fwi objective value + gradient, t_sub, checkpointing, physical-domain snapshots,
+    lsrtm (born_fwd, nlind), illumination (test_gradients.jl, test_all_options.jl)."""
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, 8)
+    do, _ = O.forward_rec(om, src, q, rec)
+    dobs = (0.9 * do).astype(np.float32)
+    f, g, Iu, Iv = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, illum=True)
+    fo, go, Iuo, Ivo = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, illum=True)
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, go) < TOL_GRAD
+    assert rel_l2(Iu, Iuo) < TOL_SHOT and rel_l2(Iv, Ivo) < TOL_GRAD
+    # objective equals 1/2 dt ||F q - dobs||^2 (test_gradients.jl:36)
+    d, _ = J.forward_rec(gm, src, q, rec)
+    assert abs(float(f) - 0.5 * dt * np.linalg.norm(d - dobs) ** 2) <= 1e-4 * abs(float(f))
+    # t_sub
+    f4, g4, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=4)
+    _, g4o, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, t_sub=4)
+    assert rel_l2(g4, g4o) < TOL_GRAD
+    # checkpointing recomputes the same arithmetic: bitwise equal to the stored-wavefield path
+    fc, gc, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, checkpointing=True)
+    assert fc == f and np.array_equal(gc, g)
+    fc2, gc2, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, checkpointing=True,
+                                 n_checkpoints=7)
+    assert np.array_equal(gc2, g)
+    # physical-domain snapshots: same gradient inside, zero in the absorbing layer
+    _, gp, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, snapshot_region="physical")
+    crop = tuple(slice(l, n - r) for (l, r), n in zip(gm.padsizes, g.shape))
+    assert np.array_equal(gp[crop], g[crop])
+    outside = gp.copy()
+    outside[crop] = 0
+    assert not outside.any()
+    # lsrtm_objective with nlind (interface.py:565, sensitivity.py:264-270)
+    fl, gl, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True)
+    flo, glo, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True)
+    assert abs(float(fl) - float(flo)) <= 1e-4 * abs(float(flo))
+    assert rel_l2(gl, glo) < TOL_GRAD
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("ic", ["isic", "fwi"])
+def test_isic_fwi_imaging_conditions(ndim, ic):
+    J, args, gm, om, src, rec, q, dt = both("iso", ndim, 8)
+    dl, _ = J.born_rec(gm, src, q, rec, ic=ic)
+    dlo, _ = O.born_rec(om, src, q, rec, ic=ic)
+    assert rel_l2(dl, dlo) < TOL_SHOT
+    y = np.random.default_rng(0).standard_normal(dl.shape).astype(np.float32)
+    g, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True, ic=ic)
+    go, _, _ = O.J_adjoint(om, src, q, rec, y, is_residual=True, ic=ic)
+    assert rel_l2(g, go) < TOL_GRAD
+    dmp = np.pad(args["dm"], gm.padsizes, mode="edge").astype(np.float64)
+    c, e = dt * np.vdot(dl.astype(np.float64), y), np.vdot(g.astype(np.float64), dmp)
+    assert abs((c - e) / (c + e)) < TOL_DOT
+
+
+def test_born_of_zero_is_exactly_zero_and_lsrtm_equals_fwi_bitwise():
+    """test_jacobian.jl:32 (J*0 == 0) and test_gradients.jl:92-97 (atol = 0)."""
+    J, args, gm, om, src, rec, q, dt = both("iso", 2, 8, with_dm=False)
+    dl, _ = J.born_rec(gm, src, q, rec)
+    assert not dl.any()
+    dobs = np.random.default_rng(3).standard_normal((NT, rec.shape[0])).astype(np.float32)
+    f1, g1, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    f2, g2, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True)
+    assert f1 == f2 and np.array_equal(g1, g2)
+
+
+def test_linearity_and_determinism():
+    """test_linearity.jl:17 (5e-5) and bit-reproducibility of repeated runs."""
+    J, args, gm, om, src, rec, q, dt = both("iso", 3, 8)
+    q2 = (np.roll(q, 9, axis=0) * np.float32(0.5)).astype(np.float32)
+    d1, _ = J.forward_rec(gm, src, q, rec)
+    d1b, _ = J.forward_rec(gm, src, q, rec)
+    assert np.array_equal(d1, d1b)
+    d2, _ = J.forward_rec(gm, src, q2, rec)
+    d12, _ = J.forward_rec(gm, src, q + q2, rec)
+    assert rel_l2(d12, d1 + d2) < 5e-5
+    y = np.random.default_rng(5).standard_normal(d1.shape).astype(np.float32)
+    ga, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True)
+    gb, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True)
+    assert np.array_equal(ga, gb)
+    g2, _, _ = J.J_adjoint(gm, src, q, rec, 2 * y, is_residual=True)
+    assert rel_l2(g2, 2 * ga) < 5e-5
+
+
+def test_tma_kernel_matches_generic_kernel():
+    """The z-marching TMA kernel against the one-thread-per-point kernel on a grid that spans
+    several tiles and z-chunks, partial tiles included."""
+    import judi_jl_b200 as J
+    n = (150, 70, 90)
+    rng = np.random.default_rng(7)
+    v = (1.5 + rng.random(n) * 2.0).astype(np.float32)
+    args = dict(origin=(0., 0., 0.), spacing=(10., 12., 8.), shape=n, space_order=8, nbl=14,
+                m=(1 / v ** 2).astype(np.float32))
+    ctx = J.get_context()
+    gm = J.Model(**args)
+    dt = float(gm.critical_dt)
+    nt = 60
+    q = O.ricker_wavelet((nt - 1) * dt, dt, 0.03)[:nt]
+    src = np.array([[700., 400., 300.]], dtype=np.float32)
+    rec = (rng.random((300, 3)) * np.array([1490., 828., 712.])).astype(np.float32)
+    out = {}
+    try:
+        for kern in (0, 1):
+            ctx.set_option("acoustic3d_kernel", kern)
+            d, _ = J.forward_rec(gm, src, q, rec)
+            dobs = np.zeros_like(d)
+            f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=2)
+            out[kern] = (d, g, f)
+    finally:
+        ctx.set_option("acoustic3d_kernel", 1)
+    assert np.linalg.norm(out[0][0]) > 0
+    assert rel_l2(out[1][0], out[0][0]) < 1e-5
+    assert rel_l2(out[1][1], out[0][1]) < 1e-5
+    for zc in (1, 2, 5):
+        ctx.set_option("zchunks", zc)
+        d, _ = J.forward_rec(gm, src, q, rec)
+        ctx.set_option("zchunks", 0)
+        assert np.array_equal(d, out[1][0])      # chunking does not change a single bit
+
+
+def test_misfit_callback_and_forward_no_rec():
+    J, args, gm, om, src, rec, q, dt = both("iso", 2, 8)
+    do, _ = O.forward_rec(om, src, q, rec)
+    dobs = (0.9 * do).astype(np.float32)
+
+    def mse(dsyn, dob):   # src/TimeModeling/Modeling/losses.jl:15-19
+        r = dsyn - dob
+        return 0.5 * float(np.linalg.norm(r)) ** 2, r
+
+    f0, g0, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    f1, g1, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, misfit=mse)
+    assert abs(float(f1) - float(f0)) <= 1e-5 * abs(float(f0))
+    assert rel_l2(g1, g0) < 1e-6
+    # wavefield history: u[t] sampled at the receivers reproduces the shot record
+    u, _ = J.forward_no_rec(gm, src, q[:80])
+    _, usave, _ = O.forward(om, src, None, q[:80], save=True)
+    assert u.shape == (80,) + gm.shape_pml
+    assert rel_l2(u[2:79], usave[2:79, 0]) < TOL_SHOT
+
+
+def test_device_resident_path_matches_host_path():
+    import torch
+    J, args, gm, om, src, rec, q, dt = both("iso", 3, 8)
+    d, _ = J.forward_rec(gm, src, q, rec)
+    dobs = (0.9 * d).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    dev = torch.device("cuda", gm.ctx.device)
+    m_d = torch.from_numpy(np.ascontiguousarray(args["m"].transpose(2, 1, 0))).to(dev)
+    a2 = dict(args)
+    a2["m"] = m_d
+    a2["dm"] = torch.from_numpy(np.ascontiguousarray(args["dm"].transpose(2, 1, 0))).to(dev)
+    gm2 = J.Model(**a2)
+    q_d = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev)
+    dobs_d = torch.from_numpy(np.ascontiguousarray(dobs.T)).to(dev)
+    rec_d = torch.zeros((rec.shape[0], q.shape[0]), dtype=torch.float32, device=dev)
+    J.forward_rec(gm2, src, q_d, rec, rec_out=rec_d)
+    torch.cuda.synchronize()
+    assert np.array_equal(rec_d.cpu().numpy().T, d)
+    red = torch.zeros(int(np.prod(gm2.shape_pml)) + 1, dtype=torch.float32, device=dev)
+    for _ in range(2):   # accumulate twice: the local reduction of distributed.jl:6-22
+        J.J_adjoint(gm2, src, q_d, rec, dobs_d, return_obj=True, grad_out=red[:-1], f_out=red[-1:],
+                    accumulate=True)
+    torch.cuda.synchronize()
+    gd = red[:-1].cpu().numpy().reshape(gm2.shape_pml[::-1]).transpose(2, 1, 0)
+    assert rel_l2(gd, 2 * g) < 1e-6
+    assert abs(float(red[-1].item()) - 2 * float(f)) <= 1e-5 * abs(2 * float(f))

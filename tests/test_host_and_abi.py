@@ -1,0 +1,147 @@
+"""CPU tests: host logic of the oracle against the reference's formulas, the C-ABI library
+(loads without a GPU, exports every symbol the header declares, fails loudly instead of falling
+back), and the Julia-side helpers restated in the package."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, model_args
+from oracle import oracle as O
+
+
+def test_cfl_coefficients_match_survey_values():
+    """models.py:440-456: cfl(2-D)=0.5177 (so 4/8), 0.4721 (so16); cfl(3-D)=0.4227, 0.3855."""
+    assert abs(O.cfl_coeff(8, 2) - 0.5177) < 1e-4
+    assert abs(O.cfl_coeff(4, 2) - 0.5177) < 1e-4
+    assert abs(O.cfl_coeff(16, 2) - 0.4721) < 1e-4
+    assert abs(O.cfl_coeff(8, 3) - 0.4227) < 1e-4
+    assert abs(O.cfl_coeff(16, 3) - 0.3855) < 1e-4
+
+
+def test_critical_dt_rounding_and_user_dt():
+    """models.py:466-482: '%.3e' rounding; a smaller user dt wins, a larger one is ignored."""
+    n = (401, 401, 201)
+    m = np.full((5, 5, 5), 1 / 5.5 ** 2, dtype=np.float32)
+    mod = O.Model((0, 0, 0), (25., 25., 25.), (5, 5, 5), space_order=8, nbl=4, m=m)
+    assert mod.critical_dt == np.float32(1.921)      # C3 dt
+    assert O.Model((0, 0, 0), (25., 25., 25.), (5, 5, 5), nbl=4, m=m, dt=1.5).critical_dt == np.float32(1.5)
+    assert O.Model((0, 0, 0), (25., 25., 25.), (5, 5, 5), nbl=4, m=m, dt=3.0).critical_dt == np.float32(1.921)
+    del n
+
+
+def test_damping_profile_properties():
+    """models.py:54-96: zero inside the domain and in the 3 innermost layer cells, separable sum,
+    symmetric, increasing outwards, coefficient 1.5 ln(1000)/(nbl-3) / h."""
+    mod = O.Model((0, 0), (10., 20.), (31, 21), nbl=15, m=np.ones((31, 21), np.float32))
+    d = mod.damp
+    assert d.shape == (61, 51)
+    assert not d[12:-12, 12:-12].any()
+    assert d[11, 25] > 0 and d[12, 25] == 0
+    assert np.allclose(d[:, 25], d[::-1, 25])
+    px, pz = d[:, 25], d[30, :]
+    assert np.allclose(d, px[:, None] + pz[None, :], rtol=1e-6)
+    assert np.all(np.diff(px[:12]) < 0)
+    nb = 12
+    pos = (nb + 1) / nb
+    expect = 1.5 * np.log(1000.) / nb * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / 10.
+    assert abs(px[0] - expect) < 1e-6 * expect
+    assert abs(pz[0] / px[0] - 0.5) < 1e-6          # divided by the spacing of its own axis
+
+
+def test_padding_is_edge_replication_and_its_adjoint():
+    """auxiliaryFunctions.jl:52-89: remove_padding(true_adjoint) is the adjoint of pad_array."""
+    rng = np.random.default_rng(0)
+    nb = ((3, 4), (2, 5))
+    x = rng.standard_normal((6, 7))
+    y = rng.standard_normal((13, 14))
+    px = O.pad_array(x, nb)
+    assert np.array_equal(px[:3, 2:-5], np.broadcast_to(x[0], (3, 7)))
+    a = np.vdot(px, y)
+    b = np.vdot(x, O.remove_padding(y, nb, true_adjoint=True))
+    assert abs(a - b) < 1e-12 * abs(a)
+    assert np.array_equal(O.remove_padding(y, nb), y[3:-4, 2:-5])
+    import judi_jl_b200 as J
+    assert np.array_equal(J.objectives.remove_padding(y, nb, True), O.remove_padding(y, nb, True))
+
+
+def test_model_parameters_edge_padded_and_tti_scaling():
+    args = model_args("tti", 2, 8)
+    mod = O.Model(**args)
+    assert mod.m.shape == mod.shape_pml
+    assert np.array_equal(mod.m[:20, 30], np.full(20, mod.m[20, 30]))
+    eps, _ = mod.tti["epsilon"]
+    assert np.allclose(eps[20:-20, 20:-20], 1 + 2 * args["epsilon"])   # models.py:218
+    assert mod.padsizes == ((20, 20), (20, 20))
+    assert mod.origin_pml == (np.float32(-200.), np.float32(-200.))
+
+
+def test_ricker_wavelet_matches_julia_formula():
+    q = O.ricker_wavelet(1000., 2., 0.01)
+    assert q.shape == (501, 1)
+    t = np.arange(501) * 2.0
+    r = np.pi * 0.01 * (t - 100.0)
+    assert np.allclose(q[:, 0], (1 - 2 * r ** 2) * np.exp(-r ** 2), atol=1e-5)
+
+
+def test_sparse_weights_partition_unity_and_skip_outside():
+    args = model_args("iso", 3, 8)
+    mod = O.Model(**args)
+    pts = np.array([[13.7, 25.2, 31.9], [-150., 0., 0.], [0., 0., 0.], [400., 360., 320.]],
+                   dtype=np.float32)
+    ijk, w, valid = O.sparse_locate(mod, pts)
+    assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+    assert valid[0].all() and not valid[1].any()           # second point is outside the padded grid
+    assert tuple(ijk[0, 0]) == (11, 12, 13)                # floor((13.7+100)/10) etc.
+    assert w[2, 0] == 1.0 and not w[2, 1:].any()           # on a node: all weight on one corner
+
+
+# ---- C-ABI ----------------------------------------------------------------------------------
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "judi_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(judi_[a-zA-Z0-9_]+)\s*\(", txt)) - {"judi_misfit_fn"})
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import judi_jl_b200 as J
+    from judi_jl_b200 import _lib
+    assert os.path.exists(J.LIB_PATH), "run python judi.jl_b200/build.py"
+    L = ctypes.CDLL(J.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), "symbol %s declared in include/judi_b200.h is not exported" % name
+    assert sorted(_lib.SIGNATURES) == declared          # the ctypes binding covers the header
+    assert _lib.lib().judi_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly (no oracle / CPU path behind it)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import judi_jl_b200 as J
+    with pytest.raises(J.JudiB200Error, match="no CPU fallback"):
+        J.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "judi.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_out_of_scope_entry_points_fail_loudly():
+    import judi_jl_b200 as J
+    for name in ("forward_rec_w", "adjoint_w", "born_rec_w", "forward_wf_src", "wri_func"):
+        with pytest.raises(NotImplementedError):
+            getattr(J.interface, name)()
