@@ -109,7 +109,7 @@ struct judi_ctx {
     // options
     int opt_kernel3d = 1;       // 0 generic, 1 TMA z-marching
     int opt_zchunks = 0;        // 0 = auto
-    int opt_tile = 6;           // TMA kernel variant (6: 64x16 tile, 2 producer warps)
+    int opt_tile = 8;           // TMA kernel variant (8: 64x16 tile, 2 producer warps, shifted queue)
     int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
@@ -226,7 +226,10 @@ struct StepArgs {
     const CUtensorMap *tmap;       // halo-box tensor map of u[0] (TMA kernel), or nullptr
     const CUtensorMap *tmap_prev;  // tile-box tensor map of up[0]
     const CUtensorMap *tmap_m;     // tile-box tensor map of m
-    struct Wavefield *scratch; // owner of the flux-form scratch buffers
+    struct Wavefield *scratch; // owner of the flux-form / Born scratch buffers
+    struct Wavefield *lin;     // Born: the linearised wavefield (tensor maps of ul)
+    float *dd_out;             // TMA kernel, Born background pass: write delta
+    const float *qsrc;         // TMA kernel, Born linearised pass: read delta of the background
 };
 void stencil_step(const judi_model *M, const StepArgs &a);
 

@@ -310,6 +310,8 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         for (int k = 0; k < nflux; k++) flux[k] = DevBuf(ctx, (size_t)M->g.nalloc, true);
         if (born_scratch)
             for (int f = 0; f < nf; f++) dd[f] = DevBuf(ctx, (size_t)M->g.nalloc, true);
+    } else if (born_scratch && tma3d_supported(M)) {
+        dd[0] = DevBuf(ctx, (size_t)M->g.nalloc, true);  // two-launch Born of the TMA kernel
     }
     has_tmap = false;
     if (tma3d_supported(M)) {
@@ -440,8 +442,25 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     }
     bool ff = M->tti || M->irho_field;
     bool use_tma = M->ndim == 3 && !ff && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
-                   !s.born && (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr;
-    if (use_tma) tma3d_step(M, s);
+                   (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr &&
+                   (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
+    if (use_tma && s.born) {
+        // Born as two launches of the TMA kernel (44 B/pt): the background step also writes
+        // delta = u+ - 2u + u-, the linearised step reads it as the source -dm * delta
+        StepArgs a1 = s;
+        a1.born = 0;
+        a1.dd_out = s.scratch->dd[0].p;
+        tma3d_step(M, a1);
+        StepArgs a2 = s;
+        memset(&a2.f, 0, sizeof(a2.f));
+        a2.born = 0;
+        a2.u[0] = s.ul[0];
+        a2.up[0] = s.ulp[0];
+        a2.tmap = &s.lin->tmap_halo[0][s.lin->cur];
+        a2.tmap_prev = &s.lin->tmap_tile[0][1 - s.lin->cur];
+        a2.qsrc = s.scratch->dd[0].p;
+        tma3d_step(M, a2);
+    } else if (use_tma) tma3d_step(M, s);
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);
     if (ctx->timing) {

@@ -247,7 +247,6 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
     JUDI_REQUIRE(desc->space_order == 4 || desc->space_order == 8 || desc->space_order == 16 ||
                      desc->space_order == 2 || desc->space_order == 12,
                  "space_order must be one of 2, 4, 8, 12, 16");
-    JUDI_REQUIRE(!desc->fs, "free surface is not supported by the B200 backend yet");
     JUDI_REQUIRE(desc->m.kind != JUDI_PARAM_NONE, "squared slowness m is required");
     JUDI_REQUIRE(desc->nbl >= 0, "nbl must be >= 0");
     M->ctx = ctx;
@@ -267,6 +266,11 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
         M->padl[gd] = M->padr[gd] = desc->nbl;
         // models.py:172: origin_pml = dtype(o - s*nbl), evaluated in double from the fp32 inputs
         M->opml[gd] = (float)((double)desc->origin[k] - (double)desc->spacing[k] * desc->nbl);
+        if (desc->fs && gd == 2) {
+            // free surface (models.py:174-176, 269-272): no layer above z = 0, origin unshifted
+            M->padl[gd] = 0;
+            M->opml[gd] = desc->origin[k];
+        }
     }
     for (int d = 0; d < 3; d++) M->N[d] = M->n[d] + M->padl[d] + M->padr[d];
     // the two-pass flux form (TTI / variable density) differentiates twice: halo of 2R

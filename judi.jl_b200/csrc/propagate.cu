@@ -175,6 +175,25 @@ __global__ void loss_kernel(long long n, float *__restrict__ a, const float *__r
     }
 }
 
+// Free surface (fields_exprs.py:106-137, applied to the new level after the injection, see the
+// `extra` position in operators.py:131,188,231): u(-k) = -u(k-1) for k = 1..so/2, then u(0) = 0.
+__global__ void free_surface_kernel(Grid g, float *__restrict__ u, int r)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= g.n[0] || y >= g.n[1]) return;
+    long long i0 = g.at(x, y, 0);
+    for (int k = 1; k <= r; k++) u[i0 - k * g.sz] = -u[i0 + (k - 1) * g.sz];
+    u[i0] = 0.f;
+}
+
+static void free_surface(const judi_model *M, float *u)
+{
+    dim3 blk(128, 1), grd((M->N[0] + 127) / 128, M->N[1]);
+    free_surface_kernel<<<grd, blk, 0, M->ctx->stream>>>(M->g, u, M->r);
+    launch_count(M->ctx, "free_surface");
+}
+
 // ---- Shot ------------------------------------------------------------------------------------
 Shot::Shot(judi_model *M_) : M(M_), ctx(M_->ctx) {}
 
@@ -199,6 +218,8 @@ void Shot::step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_
     stencil_step(M, s);
     sparse_step(M, S_in, in ? in->row(t) : nullptr, W.other(0), corr, S_out, W.level(0),
                 out ? out->row(t) : nullptr, nullptr, nullptr, nullptr);
+    if (M->fs)
+        for (int f = 0; f < W.nf; f++) free_surface(M, W.other(f));
     W.swap();
 }
 
@@ -211,6 +232,7 @@ void Shot::step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fus
     s.born = 1;
     s.born_ic = ic;
     for (int f = 0; f < WL.nf; f++) { s.ul[f] = WL.level(f); s.ulp[f] = WL.other(f); }
+    s.lin = &WL;
     if (fuse) s.f = *fuse;
     stencil_step(M, s);
     SparseCorr corr;
@@ -219,6 +241,8 @@ void Shot::step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fus
     sparse_step(M, S_src, q->row(t), W.other(0), &corr, S_rec, WL.level(0),
                 recl ? recl->row(t) : nullptr, recnl ? S_rec : nullptr, W.level(0),
                 recnl ? recnl->row(t) : nullptr);
+    if (M->fs)
+        for (int f = 0; f < W.nf; f++) { free_surface(M, W.other(f)); free_surface(M, WL.other(f)); }
     W.swap();
     WL.swap();
 }

@@ -87,6 +87,9 @@ struct TmaArgs {
     int zchunk;      // planes per z-chunk
     int dlo[3], dhi[3];  // [dlo, dhi): indices where the damping profile of each axis is zero
     Fuse f;
+    float *dd_out;       // Born, background pass: write delta = u+ - 2u + u-   (Grid layout)
+    const float *qsrc;   // Born, linearised pass: delta of the background field ...
+    const float *dm;     // ... and the perturbation: source term -dm * qsrc
 };
 
 template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1>
@@ -103,7 +106,7 @@ struct TmaCfg {
         (size_t)NS * SLOT * 4 + (size_t)NP * 2 * PSLOT * 4 + (2 * NS + 2 * NP) * 8 + 128;
 };
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, bool FUSE, int NPW>
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, bool FUSE, int NPW, bool ROT>
 __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     acoustic3d_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP,
                    const __grid_constant__ CUtensorMap tmM, const TmaArgs a)
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     constexpr int PSLOT = C::PSLOT, NQ = C::NQ, NCW = C::NCONS / 32;
     // STATIC: ring length == queue length, so ring slots are compile-time constants inside the
     // unrolled main loop and every shared-memory address is an immediate offset
-    constexpr bool STATIC = (NS == NQ) && (NQ % NP == 0);
+    constexpr bool STATIC = ROT && (NS == NQ) && (NQ % NP == 0);
     static_assert(STATIC || ((NS & (NS - 1)) == 0 && (NP & (NP - 1)) == 0),
                   "dynamic ring sizes must be powers of 2");
     extern __shared__ unsigned char smem_raw[];
@@ -206,20 +209,61 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                                y0 + TY <= a.dhi[1];
     const int sm_own = (ty + R) * PX + HR + 4 * tx;  // this thread's first point in a u slot
     const int sm_tile = ty * TX + 4 * tx;            // ... and in a tile slot
-    float *gout = a.up + g.at(x, y, z0);             // advanced by sz per output plane
+    long long goff = g.at(x, y, z0);                 // advanced by sz per output plane
+    // fused extras: everything that does not depend on z is decided once per thread; the region
+    // offset advances by one region plane per output plane (no 64-bit index math in the loop)
     [[maybe_unused]] const Fuse &fz = a.f;
-    [[maybe_unused]] const bool reg_vec = FUSE && (fz.reg.lo[0] & 3) == 0;
+    [[maybe_unused]] const bool f_snap = FUSE && fz.snap[0] != nullptr;
+    [[maybe_unused]] const bool f_grad = FUSE && fz.grad != nullptr;
+    [[maybe_unused]] const bool f_il = FUSE && fz.illum != nullptr;
+    [[maybe_unused]] const bool f_born = FUSE && a.qsrc != nullptr && act;
+    [[maybe_unused]] const bool f_xy = FUSE && act && (f_snap || f_grad || f_il) && y >= fz.reg.lo[1] &&
+                                       y < fz.reg.hi[1] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0];
+    [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && x >= fz.reg.lo[0] &&
+                                        x + 3 < fz.reg.hi[0];
+    [[maybe_unused]] long long ri = FUSE ? fz.reg.at(x, y, z0) : 0;
+    [[maybe_unused]] const long long rstride = FUSE ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
+    [[maybe_unused]] const float gc = FUSE ? fz.gcoef * a.irho_c : 0.f;
+    [[maybe_unused]] const int rz0 = FUSE ? fz.reg.lo[2] : 0, rz1 = FUSE ? fz.reg.hi[2] : 0;
 
-    for (int jt0 = 0; jt0 < total; jt0 += NQ) {
+    // ROT: the z-queue is rotated at compile time (main loop unrolled by NQ, no register moves,
+    // ~9x the code); !ROT: the queue is shifted by NQ-1 register moves per plane (compact code).
+    constexpr int UNR = ROT ? NQ : 1;
+    for (int jt0 = 0; jt0 < total; jt0 += UNR) {
 #pragma unroll
-        for (int ph = 0; ph < NQ; ph++) {
+        for (int ph = 0; ph < UNR; ph++) {
             const int jt = jt0 + ph;
             if (jt >= total) break;
             // queue element of z-offset k (k = R is the centre, k = 2R the incoming plane)
-#define Q(k) q[((ph) + 1 + (k)) % NQ]
+#define Q(k) q[ROT ? (((ph) + 1 + (k)) % NQ) : (k)]
+            if (!ROT) {
+#pragma unroll
+                for (int k = 0; k < NQ - 1; k++) q[k] = q[k + 1];
+            }
             // ---- incoming plane z + R ------------------------------------------------------
             const int st = STATIC ? ph : (jt % NS);                     // slot of the incoming plane
             const int sc = STATIC ? (ph + NQ - R) % NQ : ((jt + NS - R) % NS);  // slot of the centre
+            // fused extras: issue their point-wise global loads before waiting on the pipeline so
+            // that their latency hides behind the stencil arithmetic of this plane
+            [[maybe_unused]] bool fin = false, fvec = false;
+            [[maybe_unused]] float4 us4, g4, il4, qs4, dm4;
+            if (FUSE && jt >= 2 * R) {
+                const int z = z0 + jt - 2 * R;
+                const bool zin = z >= rz0 && z < rz1;
+                fin = f_xy && zin;
+                fvec = f_vec && zin;
+                if (fvec) {
+                    if (f_grad) {
+                        us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
+                        g4 = *(const float4 *)(fz.grad + ri);
+                    }
+                    if (f_il) il4 = *(const float4 *)(fz.illum + ri);
+                }
+                if (f_born) {
+                    qs4 = *(const float4 *)(a.qsrc + goff);
+                    dm4 = __ldg((const float4 *)(a.dm + goff));
+                }
+            }
             mbar_wait(&fullU[st], (uint32_t)((jt / NS) & 1));
             Q(2 * R) = *(const float4 *)(ringU + st * SLOT + sm_own);
             if (jt >= 2 * R) {
@@ -290,6 +334,10 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
                 float un[4];
                 [[maybe_unused]] float delta[4];
+                if (FUSE && f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
+                    lz[0] = __fmaf_rn(-dm4.x, qs4.x, lz[0]); lz[1] = __fmaf_rn(-dm4.y, qs4.y, lz[1]);
+                    lz[2] = __fmaf_rn(-dm4.z, qs4.z, lz[2]); lz[3] = __fmaf_rn(-dm4.w, qs4.w, lz[3]);
+                }
                 if (tile_interior && z >= a.dlo[2] && z < a.dhi[2]) {
 #pragma unroll
                     // explicit rounding intrinsics: the plain and the fused instantiation must
@@ -312,49 +360,53 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                     }
                 }
                 if (act) {
+                    float *gout = a.up + goff;
                     if (xfull) *(float4 *)gout = make_float4(un[0], un[1], un[2], un[3]);
                     else {
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             if (x + e < g.n[0]) gout[e] = un[e];
                     }
+                    if (FUSE && a.dd_out) {
+                        float *dout = a.dd_out + goff;
+                        if (xfull) *(float4 *)dout = make_float4(delta[0], delta[1], delta[2], delta[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                if (x + e < g.n[0]) dout[e] = delta[e];
+                        }
+                    }
                 }
                 if (FUSE) {
-                    if (act && y >= fz.reg.lo[1] && y < fz.reg.hi[1] && z >= fz.reg.lo[2] &&
-                        z < fz.reg.hi[2] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0]) {
-                        const long long ri = fz.reg.at(x, y, z);
-                        const bool vec = reg_vec && x >= fz.reg.lo[0] && x + 3 < fz.reg.hi[0];
-                        if (vec) {
-                            if (fz.snap[0])
+                    if (fin) {
+                        if (fvec) {
+                            if (f_snap)
                                 *(float4 *)(fz.snap[0] + ri) = make_float4(uc[0], uc[1], uc[2], uc[3]);
-                            if (fz.illum) {
-                                float4 I = *(float4 *)(fz.illum + ri);
+                            if (f_il) {
+                                float4 I = il4;
                                 I.x += cf.dt * uc[0] * uc[0]; I.y += cf.dt * uc[1] * uc[1];
                                 I.z += cf.dt * uc[2] * uc[2]; I.w += cf.dt * uc[3] * uc[3];
                                 *(float4 *)(fz.illum + ri) = I;
                             }
-                            if (fz.grad) {
-                                const float gc = fz.gcoef * a.irho_c;
-                                const float4 us = __ldg((const float4 *)(fz.usnap[0] + ri));
-                                float4 G = *(float4 *)(fz.grad + ri);
-                                G.x -= gc * us.x * delta[0]; G.y -= gc * us.y * delta[1];
-                                G.z -= gc * us.z * delta[2]; G.w -= gc * us.w * delta[3];
+                            if (f_grad) {
+                                float4 G = g4;
+                                G.x -= gc * us4.x * delta[0]; G.y -= gc * us4.y * delta[1];
+                                G.z -= gc * us4.z * delta[2]; G.w -= gc * us4.w * delta[3];
                                 *(float4 *)(fz.grad + ri) = G;
                             }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
                                 if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
-                                if (fz.snap[0]) fz.snap[0][ri + e] = uc[e];
-                                if (fz.illum) fz.illum[ri + e] += cf.dt * uc[e] * uc[e];
-                                if (fz.grad)
-                                    fz.grad[ri + e] -=
-                                        fz.gcoef * a.irho_c * fz.usnap[0][ri + e] * delta[e];
+                                if (f_snap) fz.snap[0][ri + e] = uc[e];
+                                if (f_il) fz.illum[ri + e] += cf.dt * uc[e] * uc[e];
+                                if (f_grad) fz.grad[ri + e] -= gc * fz.usnap[0][ri + e] * delta[e];
                             }
                         }
                     }
                 }
-                gout += g.sz;
+                goff += g.sz;
+                if (FUSE) ri += rstride;
             } else if (jt >= R) {
                 // planes below the chunk are never centres: release them as soon as R newer
                 // planes have arrived (keeps the producer's slot accounting uniform)
@@ -374,13 +426,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 struct TileVariant { int txt, tyt; };
 static const TileVariant kVariants[] = {{16, 16}, {32, 8}, {16, 8}, {32, 4},
-                                        {16, 16}, {32, 8}, {16, 16}, {16, 8}};
-static const int kNumVariants = 8;
+                                        {16, 16}, {32, 8}, {16, 16}, {16, 8},
+                                        {16, 16}, {32, 8}};
+static const int kNumVariants = 10;
 
 static int variant_of(const judi_model *M)
 {
     int v = M->ctx->opt_tile;
-    if (v < 0 || v >= kNumVariants || M->r != 4) v = 6;
+    if (v < 0 || v >= kNumVariants || M->r != 4) v = 8;
     return v;
 }
 
@@ -418,14 +471,14 @@ void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map,
     if (tile_map) encode_box(M, base, tx, ty, tile_map);
 }
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1>
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
 static void launch_variant(const judi_model *M, const StepArgs &s)
 {
     typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
     judi_ctx *ctx = M->ctx;
-    const bool fuse = s.f.snap[0] || s.f.grad || s.f.illum;
-    auto kplain = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, false, NPW>;
-    auto kfuse = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, true, NPW>;
+    const bool fuse = s.f.snap[0] || s.f.grad || s.f.illum || s.dd_out || s.qsrc;
+    auto kplain = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, false, NPW, ROT>;
+    auto kfuse = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, true, NPW, ROT>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kplain, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -447,6 +500,9 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
         a.dhi[d] = M->N[d] - (M->padr[d] > 3 ? M->padr[d] - 3 : 0);
     }
     a.f = s.f;
+    a.dd_out = s.dd_out;
+    a.qsrc = s.qsrc;
+    a.dm = s.qsrc ? M->dm.p : nullptr;
     int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
@@ -480,6 +536,8 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
     case 5: launch_variant<4, 32, 8, 9, 3, 2, 2>(M, s); break;
     case 6: launch_variant<4, 16, 16, 8, 4, 2, 2>(M, s); break;   // dynamic ring, 2 producer warps
     case 7: launch_variant<4, 16, 8, 9, 3, 3, 2>(M, s); break;
+    case 8: launch_variant<4, 16, 16, 8, 4, 2, 2, false>(M, s); break;  // shifted queue, compact code
+    case 9: launch_variant<4, 32, 8, 8, 4, 2, 2, false>(M, s); break;
     default: launch_variant<4, 16, 16, 8, 4, 2>(M, s); break;
     }
 }

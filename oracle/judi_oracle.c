@@ -58,6 +58,7 @@ typedef struct {
     float hf[3];    /* fp32 spacing for the sparse position arithmetic */
     real dt;
     int tti;
+    int fs;         /* free surface at z = 0 (fields_exprs.py:106-137) */
     int irho_is_field;
     real irho_c;
     real *m, *damp, *irho, *eps, *delta, *theta, *phi, *dm;
@@ -207,6 +208,21 @@ void oracle_destroy(ogrid *g)
 }
 
 int oracle_real_size(void) { return (int)sizeof(real); }
+
+void oracle_set_fs(ogrid *g, int fs) { g->fs = fs; }
+
+/* freesurface(model, u_n): u(-k) = -u(k-1), k = 1..so/2 (loop over zfs), then u(0) = 0;
+ * placed after the injection (`extra` in operators.py:131,188,231). */
+static void apply_fs(const ogrid *g, real *u)
+{
+    if (!g->fs) return;
+    for (int x = 0; x < g->N[0]; x++)
+        for (int y = 0; y < g->N[1]; y++) {
+            size_t i0 = IDX(g, x, y, 0);
+            for (int k = 1; k <= g->r; k++) u[i0 - k] = -u[i0 + (k - 1)];
+            u[i0] = 0;
+        }
+}
 
 void oracle_weights(const ogrid *g, real *c2, real *w1)
 {
@@ -574,6 +590,7 @@ int oracle_forward(const ogrid *g, int fw, int nt, const osparse *src, const rea
         if (fast_ok(g)) fast_step(g, u[0], up[0], NULL, NULL, 0);
         else step_fields(g, &sc, nf, u, up, up, NULL);
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
+        for (int f = 0; f < nf; f++) apply_fs(g, up[f]);
         if (rec && rec_out) interpolate(rec, u[0], rec_out + (size_t)t * rec->np);
         if (save_mode && (t % t_sub) == 0)
             for (int f = 0; f < nf; f++)
@@ -668,6 +685,7 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
         }
         step_fields(g, &sc, nf, u, up, up, NULL);
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
+        for (int f = 0; f < nf; f++) apply_fs(g, up[f]);
         if (recnl_out) interpolate(rec, u[0], recnl_out + (size_t)t * rec->np);
         if (recl_out) interpolate(rec, ul[0], recl_out + (size_t)t * rec->np);
         /* linearised source from the post-injection u[t+1] */
@@ -686,6 +704,7 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
                     }
                 }
         step_fields(g, &sc, nf, ul, ulp, ulp, (const real *const *)q);
+        for (int f = 0; f < nf; f++) apply_fs(g, ulp[f]);
         if (save_mode && (t % t_sub) == 0)
             for (int f = 0; f < nf; f++)
                 extract(g, u[f], usave + ((size_t)(t / t_sub) * nf + f) * ng);
@@ -742,6 +761,7 @@ int oracle_gradient(const ogrid *g, int nt, const osparse *rec, const real *resi
         }
         step_fields(g, &sc, nf, v, vp, vp, NULL);
         inject(g, rec, residual + (size_t)t * rec->np, vp[0]);
+        for (int f = 0; f < nf; f++) apply_fs(g, vp[f]);
         if ((t % t_sub) == 0) {
             for (int f = 0; f < nf; f++) {
                 const real *slot = usave + ((size_t)(t / t_sub) * nf + f) * ng;

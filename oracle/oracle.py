@@ -65,6 +65,7 @@ def _lib(precision):
     lib.oracle_gradient.argtypes = [P, ctypes.c_int, P, P, ctypes.c_int, ctypes.c_int, P, P, P]
     lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
     lib.oracle_set_fast.argtypes = [ctypes.c_int]
+    lib.oracle_set_fs.argtypes = [P, ctypes.c_int]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
     _LIBS[precision] = lib
@@ -170,8 +171,6 @@ class Model(object):
     def __init__(self, origin, spacing, shape, space_order=8, nbl=40, m=None, epsilon=None,
                  delta=None, theta=None, phi=None, rho=None, b=None, dm=None, fs=False,
                  dt=None, precision="f32"):
-        if fs:
-            raise NotImplementedError("free surface is a 'next' row (SURVEY 8f rank 3)")
         self.shape = tuple(int(s) for s in shape)
         self.dim = len(self.shape)
         self.nbl = int(nbl)
@@ -180,9 +179,13 @@ class Model(object):
         self.spacing = tuple(np.float32(s) for s in spacing)
         self.origin = tuple(np.float32(o) for o in origin)
         # models.py:172-177
-        self.origin_pml = tuple(np.float32(float(o) - float(s) * nbl)
-                                for o, s in zip(origin, spacing))
-        self.shape_pml = tuple(int(s + 2 * self.nbl) for s in self.shape)
+        op = [np.float32(float(o) - float(s) * nbl) for o, s in zip(origin, spacing)]
+        sp = [int(s + 2 * self.nbl) for s in self.shape]
+        if fs:   # models.py:174-176
+            op[-1] = np.float32(origin[-1])
+            sp[-1] -= self.nbl
+        self.origin_pml = tuple(op)
+        self.shape_pml = tuple(sp)
         self.precision = precision
         self._dt = dt
         self.damp = damp_field(self.shape_pml, self.padsizes, self.spacing, fs)
@@ -276,6 +279,7 @@ class Model(object):
             _ptr(conv(g("theta", 0.0)[0])), lib._real(g("theta", 0.0)[1]),
             _ptr(conv(g("phi", 0.0)[0])), lib._real(g("phi", 0.0)[1]),
             _ptr(conv(self.dm)))
+        lib.oracle_set_fs(self._handle, int(bool(self.fs)))
         return self._handle
 
     def __del__(self):

@@ -35,7 +35,7 @@ def _build_oracle():
 
 # ---- shared model / geometry recipes (value ranges follow the reference tests:
 # test/seismic_utils.jl:23-63, src/pysource/adjoint_test_F.py:28-54) ---------------------------
-def model_args(kind="iso", ndim=2, so=8, with_dm=True, n=None, nbl=None):
+def model_args(kind="iso", ndim=2, so=8, with_dm=True, n=None, nbl=None, fs=False):
     if ndim == 2:
         n = n or (101, 81)
         nbl = 20 if nbl is None else nbl
@@ -68,6 +68,8 @@ def model_args(kind="iso", ndim=2, so=8, with_dm=True, n=None, nbl=None):
         else:
             dm[10:30, 8:28, 12:25] = 0.03
         kw["dm"] = dm
+    if fs:
+        kw["fs"] = True
     return dict(origin=(0.,) * ndim, spacing=d, shape=n, space_order=so, nbl=nbl, m=m, **kw)
 
 

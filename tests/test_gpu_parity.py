@@ -256,3 +256,24 @@ def test_device_resident_path_matches_host_path():
     gd = red[:-1].cpu().numpy().reshape(gm2.shape_pml[::-1]).transpose(2, 1, 0)
     assert rel_l2(gd, 2 * g) < 1e-6
     assert abs(float(red[-1].item()) - 2 * float(f)) <= 1e-5 * abs(2 * float(f))
+
+
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3)])
+def test_free_surface_parity(kind, ndim):
+    """Options(free_surface=true): no layer above z=0 (models.py:174-176,269-272) and the mirror
+    u(-k) = -u(k-1), u(0) = 0 after every update (fields_exprs.py:106-137)."""
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, 8, fs=True)
+    assert gm.padsizes == om.padsizes and gm.padsizes[-1][0] == 0
+    assert gm.shape_pml == om.shape_pml
+    assert rel_l2(gm.get_field("damp"), om.damp) < 1e-6
+    d, _ = J.forward_rec(gm, src, q, rec)
+    do, _ = O.forward_rec(om, src, q, rec)
+    assert rel_l2(d, do) < TOL_SHOT
+    dl, _ = J.born_rec(gm, src, q, rec)
+    dlo, _ = O.born_rec(om, src, q, rec)
+    assert rel_l2(dl, dlo) < TOL_SHOT
+    dobs = (0.9 * do).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    fo, go, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True)
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, go) < TOL_GRAD
