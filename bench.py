@@ -300,14 +300,14 @@ def run_b200(args):
             keep_m, m0_h = pinned(m0)
             keep_q, q_h = pinned(q)
             keep_d, d_h = pinned(dobs)
-            keep_g, g_h = pinned(np.zeros(npad, dtype=np.float32))
+            g_h, g_pin = J.objectives.pinned_gradient_buffer(npad)
 
             def step_host():
                 mh = J.Model((0., 0., 0.), SPACING, shape, m=m0_h, **kw)
                 f, g, _, _ = J.J_adjoint(mh, src, q_h, rec, d_h, return_obj=True, t_sub=args.t_sub,
                                          snapshot_region=args.snapshot_region, grad_out=g_h)
                 if world > 1:
-                    f, g = J.objectives.reduce_fg(f, g)
+                    f, g = J.objectives.reduce_fg(f, g, pinned=g_pin)
                 return f, g
             for _ in range(min(args.warmup, 2)):
                 step_host()

@@ -43,11 +43,27 @@ def _dist():
     return None
 
 
-def reduce_fg(f, g):
+_staging = {}
+
+
+def pinned_gradient_buffer(shape_pml):
+    """Host buffer for one padded gradient + objective in page-locked memory: returns
+    (F-ordered numpy view of the gradient part, torch tensor of prod(shape)+1 floats).  Passing
+    the view as `grad_out` to J_adjoint and the tensor as `pinned` to reduce_fg makes the
+    reduction copy-free on the host side."""
+    import torch
+    n = int(np.prod(shape_pml))
+    t = torch.zeros(n + 1, dtype=torch.float32).pin_memory()
+    g = t[:n].numpy().reshape(tuple(shape_pml)[::-1]).T
+    return g, t
+
+
+def reduce_fg(f, g, pinned=None):
     """Sum (objective, gradient) over all ranks: distributed.jl:60-95 as one all-reduce.
 
     `g` is a numpy array (host path) or a torch tensor (device path, reduced in place over
-    NCCL); the objective scalar rides along as one extra element, as in SURVEY 8(e)."""
+    NCCL); the objective scalar rides along as one extra element, as in SURVEY 8(e).  `pinned`
+    (see pinned_gradient_buffer) must alias `g` in its first prod(shape) elements."""
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return f, g
@@ -57,10 +73,25 @@ def reduce_fg(f, g):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         g.copy_(buf[:-1].reshape(g.shape))
         return float(buf[-1].item()), g
+    nccl = dist.get_backend() == "nccl"
+    if pinned is not None:
+        pinned[-1] = float(f)
+        if nccl:
+            key = ("dev", pinned.numel())
+            if key not in _staging:
+                _staging[key] = torch.empty(pinned.numel(), dtype=torch.float32, device="cuda")
+            d = _staging[key]
+            d.copy_(pinned, non_blocking=True)
+            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+            pinned.copy_(d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            dist.all_reduce(pinned, op=dist.ReduceOp.SUM)
+        return float(pinned[-1]), g
     g = np.asarray(g, dtype=np.float32)
     flat = np.concatenate([g.ravel(order="F"), np.array([f], dtype=np.float32)])
     t = torch.from_numpy(flat)
-    if dist.get_backend() == "nccl":
+    if nccl:
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     t = t.cpu().numpy()
