@@ -107,6 +107,7 @@ int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value)
     else if (k == "tile") ctx->opt_tile = value;
     else if (k == "atomic_inject") ctx->opt_atomic_inject = value;
     else if (k == "timing") ctx->timing = value;
+    else if (k == "persist2d") ctx->opt_persist2d = value;
     else throw JudiError("unknown option " + k);
     return 0;
     API_END(1)

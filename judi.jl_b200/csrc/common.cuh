@@ -111,6 +111,7 @@ struct judi_ctx {
     int opt_zchunks = 0;        // 0 = auto
     int opt_tile = 8;           // TMA kernel variant (8: 64x16 tile, 2 producer warps, shifted queue)
     int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
+    int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
 
@@ -183,6 +184,7 @@ struct SparseSet {
     DevBuf ent_w;                 // [nent]
     DevBuf cell_scale;            // [ncell] dt^2 / (m*irho)
     DevBuf cell_born;             // [ncell] -dm*irho / (m*irho + dt*damp)   (if model has dm)
+    DevArr<int> cellmap;          // 2-D only: [nalloc] row of the cell in the CSR, or -1
 };
 
 // optional post-injection corrections applied by the sparse kernel

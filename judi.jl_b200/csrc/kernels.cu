@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
 void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
+bool flux3d_step(const judi_model *M, const StepArgs &s);
 
 void Wavefield::init(const judi_model *M, bool born_scratch)
 {
@@ -461,6 +462,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.qsrc = s.scratch->dd[0].p;
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
+    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && flux3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);
     if (ctx->timing) {

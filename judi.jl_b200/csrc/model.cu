@@ -62,7 +62,7 @@ Grid make_grid(int ndim, const int *N, int halo)
     g.sy = g.px;
     g.sz = (long long)g.px * g.py;
     g.off0 = g.hx + (long long)g.hy * g.sy + (long long)g.hz * g.sz;
-    g.nalloc = g.sz * g.pz;
+    g.nalloc = g.sz * g.pz + 64;  // slack: vector loads of the last row may run a few floats over
     return g;
 }
 

@@ -275,7 +275,13 @@ void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    if (fw) {
+    if (persist2d_supported(M, JUDI_IC_AS)) {
+        P2Fuse pf;
+        pf.reg = M->full;
+        pf.illum = fz.illum;
+        persist2d_run(M, W, nullptr, fw ? 1 : nt - 2, fw ? nt - 2 : 1, fw ? 1 : -1, &S_src, &q,
+                      nrec > 0 ? &S_rec : nullptr, &rec, nullptr, pf);
+    } else if (fw) {
         for (int t = 1; t <= nt - 2; t++)
             sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr,
                           nrec > 0 ? &S_rec : nullptr, &rec);
@@ -366,8 +372,15 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    for (int t = 1; t <= nt - 2; t++)
-        sh.step_born(W, WL, t, ic, illum_out ? &fz : nullptr, &S_src, &q, &S_rec, &rec, nullptr);
+    if (persist2d_supported(M, ic)) {
+        P2Fuse pf;
+        pf.reg = M->full;
+        pf.illum = fz.illum;
+        persist2d_run(M, W, &WL, 1, nt - 2, 1, &S_src, &q, &S_rec, &rec, nullptr, pf);
+    } else {
+        for (int t = 1; t <= nt - 2; t++)
+            sh.step_born(W, WL, t, ic, illum_out ? &fz : nullptr, &S_src, &q, &S_rec, &rec, nullptr);
+    }
     rec.store(ctx, rec_out, dev);
     if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
     ctx->flush_timing();
@@ -474,25 +487,54 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         else
             sh.step_plain(W, t, any ? &f : nullptr, &S_src, &q, nullptr, &S_rec, &rec);
     };
+    // A range of forward steps.  mode 0: no snapshots; 1: slot t/k when t % k == 0; 2: slot t-base
+    // (segment recomputation).  2-D constant-density models run the whole range inside one
+    // persistent kernel (persist2d.cu), everything else steps kernel by kernel.
+    const bool p2 = persist2d_supported(M, o->ic);
+    auto fwd_range = [&](int ta, int tb, int mode, int base, bool record) {
+        if (tb < ta) return;
+        if (p2) {
+            P2Fuse pf;
+            pf.reg = reg;
+            pf.illum = fsave.illum;
+            if (mode) {
+                pf.snap = snaps.p;
+                pf.slot = (long long)slot_floats;
+                pf.t_sub = mode == 1 ? k : 1;
+                pf.t_base = mode == 1 ? 0 : base;
+            }
+            persist2d_run(M, W, born ? &WL : nullptr, ta, tb, 1, &S_src, &q,
+                          record ? &S_rec : nullptr, &rec,
+                          (record && born && o->nlind) ? &recnl : nullptr, pf);
+            return;
+        }
+        for (int t = ta; t <= tb; t++) {
+            int slot = mode == 1 ? ((t % k) == 0 ? t / k : -1) : (mode == 2 ? t - base : -1);
+            if (record) fwd_step(t, slot);
+            else {
+                Fuse f = fsave;
+                for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot >= 0 ? slot_ptr(slot, ff) : nullptr;
+                sh.step_plain(W, t, &f, &S_src, &q, nullptr, nullptr, nullptr);
+            }
+        }
+    };
     if (!o->checkpointing) {
-        for (int t = 1; t <= nt - 2; t++) fwd_step(t, (t % k) == 0 ? t / k : -1);
+        fwd_range(1, nt - 2, 1, 0, true);
     } else {
         JUDI_REQUIRE(!born, "optimal_checkpointing with born_fwd is not supported yet");
         ckpt.resize((size_t)nseg * 2 * nf);
-        for (int t = 1; t <= nt - 2; t++) {
-            if ((t - 1) % seg == 0) {
-                int s = (t - 1) / seg;
-                for (int ff = 0; ff < nf; ff++) {
-                    for (int lv = 0; lv < 2; lv++) {
-                        DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];
-                        c = DevBuf(ctx, (size_t)M->g.nalloc, false);
-                        CUDA_CHECK(cudaMemcpyAsync(c.p, lv == 0 ? W.level(ff) : W.other(ff),
-                                                   (size_t)M->g.nalloc * sizeof(float),
-                                                   cudaMemcpyDeviceToDevice, ctx->stream));
-                    }
+        for (int s = 0; s < nseg; s++) {
+            int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
+            for (int ff = 0; ff < nf; ff++) {
+                for (int lv = 0; lv < 2; lv++) {
+                    DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];
+                    c = DevBuf(ctx, (size_t)M->g.nalloc, false);
+                    CUDA_CHECK(cudaMemcpyAsync(c.p, lv == 0 ? W.level(ff) : W.other(ff),
+                                               (size_t)M->g.nalloc * sizeof(float),
+                                               cudaMemcpyDeviceToDevice, ctx->stream));
                 }
             }
-            fwd_step(t, -1);
+            fwd_range(ts, te, 0, 0, true);
         }
         fsave.illum = nullptr;  // the recomputation must not add to the illumination again
     }
@@ -556,8 +598,26 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         sh.step_plain(V, t, any ? &f : nullptr, &S_rec, &rec, slot >= 0 ? &corr : nullptr, nullptr,
                       nullptr);
     };
+    auto adj_range = [&](int ta, int tb, int mode, int base) {  // ta >= tb, descending
+        if (ta < tb) return;
+        if (p2) {
+            P2Fuse pf;
+            pf.reg = reg;
+            pf.illum = fadj.illum;
+            pf.grad = grad.p;
+            pf.usnap = snaps.p;
+            pf.slot = (long long)slot_floats;
+            pf.t_sub = mode == 1 ? k : 1;
+            pf.t_base = mode == 1 ? 0 : base;
+            pf.gcoef = fadj.gcoef;
+            persist2d_run(M, V, nullptr, ta, tb, -1, &S_rec, &rec, nullptr, nullptr, nullptr, pf);
+            return;
+        }
+        for (int t = ta; t >= tb; t--)
+            adj_step(t, mode == 1 ? ((t % k) == 0 ? t / k : -1) : t - base);
+    };
     if (!o->checkpointing) {
-        for (int t = nt - 2; t >= 1; t--) adj_step(t, (t % k) == 0 ? t / k : -1);
+        adj_range(nt - 2, 1, 1, 0);
     } else {
         for (int s = nseg - 1; s >= 0; s--) {
             int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
@@ -571,12 +631,8 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                                                cudaMemcpyDeviceToDevice, ctx->stream));
                     c.reset();
                 }
-            Fuse f = fsave;
-            for (int t = ts; t <= te; t++) {
-                for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot_ptr(t - ts, ff);
-                sh.step_plain(W, t, &f, &S_src, &q, nullptr, nullptr, nullptr);
-            }
-            for (int t = te; t >= ts; t--) adj_step(t, t - ts);
+            fwd_range(ts, te, 2, ts, false);
+            adj_range(te, ts, 2, ts);
         }
     }
 

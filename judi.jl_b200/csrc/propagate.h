@@ -24,6 +24,21 @@ struct Shot {
                    Traces *recnl);
 };
 
+// fused extras of the persistent 2-D kernel (persist2d.cu)
+struct P2Fuse {
+    float *snap = nullptr;        // snapshot pool base (save) ...
+    const float *usnap = nullptr; // ... or (imaging condition) the pool to read
+    float *grad = nullptr, *illum = nullptr;
+    long long slot = 0;           // floats per snapshot slot
+    int t_sub = 1, t_base = 0;    // slot of time index t is (t - t_base) / t_sub
+    float gcoef = 0;
+    Region reg;
+};
+bool persist2d_supported(const judi_model *M, int ic);
+void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int t1, int dir,
+                   const SparseSet *S_in, const Traces *in, const SparseSet *S_out, Traces *out,
+                   Traces *out_bg, const P2Fuse &fz);
+
 void region_output(const judi_model *M, const Region &reg, const float *src, float *user,
                    bool on_device, bool accumulate);
 void grid_output(const judi_model *M, const float *field, float *user, bool on_device);

@@ -84,6 +84,12 @@ __global__ void sparse_cell_setup(int ncell, const long long *__restrict__ off,
     }
 }
 
+__global__ void cellmap_kernel(int ncell, const long long *__restrict__ off, int *map)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncell) map[off[i]] = i;
+}
+
 void sparse_build(const judi_model *M, int np, const float *coords, SparseSet &S)
 {
     judi_ctx *ctx = M->ctx;
@@ -149,6 +155,16 @@ void sparse_build(const judi_model *M, int np, const float *coords, SparseSet &S
             M->has_dm ? M->dm.p : nullptr, M->damp[0].p, M->damp[1].p, M->damp[2].p, M->dt,
             S.cell_scale.p, S.cell_born.p);
         launch_count(ctx, "sparse_cell_setup");
+    }
+    if (M->ndim == 2 && ctx->opt_persist2d) {
+        // point -> CSR row map for the owner-computes injection of the persistent 2-D kernel
+        S.cellmap = DevArr<int>(ctx, (size_t)M->g.nalloc, false);
+        CUDA_CHECK(cudaMemsetAsync(S.cellmap.p, 0xFF, (size_t)M->g.nalloc * sizeof(int), ctx->stream));
+        if (S.ncell > 0) {
+            cellmap_kernel<<<(S.ncell + 127) / 128, 128, 0, ctx->stream>>>(S.ncell, S.cell_off.p,
+                                                                            S.cellmap.p);
+            launch_count(ctx, "cellmap");
+        }
     }
 }
 
