@@ -49,7 +49,7 @@ typedef struct {
     float origin[3];  /* o, metres */
     int nbl;          /* absorbing layer width in cells */
     int space_order;  /* 4, 8 or 16 */
-    int fs;           /* free surface (not supported yet: returns an error) */
+    int fs;           /* Options(free_surface): no layer above z=0 + mirror (fields_exprs.py:106) */
     float dt;         /* user dt_comp (ms); <= 0 means "use the CFL value" */
     judi_param m;     /* squared slowness s^2/km^2 (required) */
     judi_param rho;   /* density; scalar -> constant-density Laplacian, array -> div(1/rho grad) */
@@ -79,7 +79,7 @@ enum {
 };
 
 /* options of J_adjoint: the keyword arguments of src/pysource/interface.py:279-282 that this
- * path supports (freq_list/dft_sub/ws are out of scope) */
+ * path supports (freq_list/dft_sub are out of scope) */
 typedef struct {
     int is_residual;   /* recin is already the residual (J' as an operator, python_interface.jl:119) */
     int checkpointing; /* Options(optimal_checkpointing): recompute segments from HBM checkpoints */
@@ -90,6 +90,8 @@ typedef struct {
     int nlind;         /* remove the non-linear data (only with born_fwd) */
     int illum;         /* also return illumination of u and v */
     int snapshot_region; /* JUDI_SNAP_* */
+    const float *ws;   /* extended source weights (padded grid) instead of point sources, or NULL:
+                          J_adjoint(ws=...) of python_interface.jl:179-198 */
 } judi_jopts;
 
 /* optional host misfit callback, replaces `misfit=pyjl(runtime_misfit)`
@@ -161,6 +163,33 @@ int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const f
  * u_out is nt x padded grid (time slowest).  TTI returns the first field like the reference. */
 int judi_forward_no_rec(judi_model *model, int fw, int nsrc, const float *src_coords,
                         const float *wavelet, int nt, float *u_out, float *illum_out, int flags);
+
+/* ---- extended and wavefield sources -------------------------------------- */
+/* forward_rec_w (interface.py:50-80; python_interface.jl:139): rec = Pr*F*Pw'*w.  `weight` is the
+ * spatial source distribution on the PADDED grid (Julia zero-pads it, python_interface.jl:129),
+ * `wavelet` its (nt x 1) time signature. */
+int judi_forward_rec_w(judi_model *model, int fw, const float *weight, const float *wavelet, int nt,
+                       int nrec, const float *rec_coords, float *rec_out, float *illum_out,
+                       int flags);
+
+/* adjoint_w (interface.py:174-204; python_interface.jl:156): w = Pw*F'*Pr'*d.  The data are
+ * injected at the receivers, the wavefield is correlated with `wavelet`; w_out is padded-grid
+ * sized. */
+int judi_adjoint_w(judi_model *model, int fw, int nrec, const float *rec_coords, const float *data,
+                   const float *wavelet, int nt, float *w_out, float *illum_out, int flags);
+
+/* born_rec_w (interface.py:244-276; python_interface.jl:174) */
+int judi_born_rec_w(judi_model *model, const float *weight, const float *wavelet, int nt, int nrec,
+                    const float *rec_coords, int ic, float *rec_out, float *illum_out, int flags);
+
+/* forward_wf_src (interface.py:114-142; python_interface.jl:69): rec = Pr*F*u with a full
+ * space-time source u_src (nt x padded grid, time slowest) */
+int judi_forward_wf_src(judi_model *model, int fw, const float *u_src, int nt, int nrec,
+                        const float *rec_coords, float *rec_out, float *illum_out, int flags);
+
+/* forward_wf_src_norec (interface.py:145-171; python_interface.jl:79): u_out = F*u_src */
+int judi_forward_wf_src_norec(judi_model *model, int fw, const float *u_src, int nt, float *u_out,
+                              float *illum_out, int flags);
 
 #ifdef __cplusplus
 }

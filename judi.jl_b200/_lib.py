@@ -37,7 +37,7 @@ class JudiJopts(ctypes.Structure):
     _fields_ = [("is_residual", ctypes.c_int), ("checkpointing", ctypes.c_int),
                 ("n_checkpoints", ctypes.c_int), ("t_sub", ctypes.c_int), ("ic", ctypes.c_int),
                 ("born_fwd", ctypes.c_int), ("nlind", ctypes.c_int), ("illum", ctypes.c_int),
-                ("snapshot_region", ctypes.c_int)]
+                ("snapshot_region", ctypes.c_int), ("ws", ctypes.c_void_p)]
 
 
 MISFIT_FN = ctypes.CFUNCTYPE(ctypes.c_float, c_float_p, c_float_p, c_float_p, ctypes.c_int,
@@ -81,6 +81,22 @@ SIGNATURES = {
     "judi_forward_no_rec": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_forward_rec_w": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int]),
+    "judi_adjoint_w": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_born_rec_w": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_forward_wf_src": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_forward_wf_src_norec": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_int]),
 }
 
 _lib = None

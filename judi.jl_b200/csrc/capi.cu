@@ -280,13 +280,84 @@ int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const f
                    float *grad_out, float *illum_u, float *illum_v, int flags)
 {
     API_BEGIN
-    JUDI_REQUIRE(model && src_coords && wavelet && rec_coords && recin && opts && grad_out,
-                 "null argument");
+    JUDI_REQUIRE(model && wavelet && rec_coords && recin && opts && grad_out, "null argument");
+    JUDI_REQUIRE((src_coords && nsrc > 0) || opts->ws, "need point sources or extended-source weights");
     CUDA_CHECK(cudaSetDevice(model->ctx->device));
     judi_jopts o = *opts;
     if (!o.illum) { illum_u = nullptr; illum_v = nullptr; }
     run_J_adjoint(model, nsrc, src_coords, wavelet, nt, nrec, rec_coords, recin, &o, misfit, user,
                   f_out, grad_out, illum_u, illum_v, flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_forward_rec_w(judi_model *model, int fw, const float *weight, const float *wavelet, int nt,
+                       int nrec, const float *rec_coords, float *rec_out, float *illum_out,
+                       int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && weight && wavelet && rec_coords && rec_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    ExtSpec ext;
+    ext.ws = weight;
+    run_forward_rec(model, fw, 0, nullptr, wavelet, nt, nrec, rec_coords, rec_out, illum_out, flags,
+                    &ext);
+    return 0;
+    API_END(1)
+}
+
+int judi_adjoint_w(judi_model *model, int fw, int nrec, const float *rec_coords, const float *data,
+                   const float *wavelet, int nt, float *w_out, float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && rec_coords && data && wavelet && w_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    ExtSpec ext;
+    ext.wr_wavelet = wavelet;
+    ext.w_out = w_out;
+    run_forward_rec(model, fw, nrec, rec_coords, data, nt, 0, nullptr, nullptr, illum_out, flags,
+                    &ext);
+    return 0;
+    API_END(1)
+}
+
+int judi_born_rec_w(judi_model *model, const float *weight, const float *wavelet, int nt, int nrec,
+                    const float *rec_coords, int ic, float *rec_out, float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && weight && wavelet && rec_coords && rec_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    ExtSpec ext;
+    ext.ws = weight;
+    run_born_rec(model, 0, nullptr, wavelet, nt, nrec, rec_coords, ic, rec_out, illum_out, flags,
+                 &ext);
+    return 0;
+    API_END(1)
+}
+
+int judi_forward_wf_src(judi_model *model, int fw, const float *u_src, int nt, int nrec,
+                        const float *rec_coords, float *rec_out, float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && u_src && rec_coords && rec_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    ExtSpec ext;
+    ext.qwf = u_src;
+    run_forward_rec(model, fw, 0, nullptr, nullptr, nt, nrec, rec_coords, rec_out, illum_out, flags,
+                    &ext);
+    return 0;
+    API_END(1)
+}
+
+int judi_forward_wf_src_norec(judi_model *model, int fw, const float *u_src, int nt, float *u_out,
+                              float *illum_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && u_src && u_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    ExtSpec ext;
+    ext.qwf = u_src;
+    run_forward_no_rec(model, fw, 0, nullptr, nullptr, nt, u_out, illum_out, flags, &ext);
     return 0;
     API_END(1)
 }

@@ -67,6 +67,8 @@ struct Fuse {
     float *grad;            // IC:   gradient accumulator (region layout)
     float *illum;           // ILLUM: illumination accumulator (region layout)
     float gcoef;            // IC:   t_sub / dt  (multiplied by irho in the kernel)
+    float *wrec;            // extended receiver accumulator (region layout): += wrec_scale * sum(u)
+    float wrec_scale;       //   dt * wavelet[t]   (fields_exprs.py:85-103)
     int ic;                 // JUDI_IC_*
     Region reg;
 };
@@ -230,6 +232,8 @@ struct StepArgs {
     const CUtensorMap *tmap_m;     // tile-box tensor map of m
     struct Wavefield *scratch; // owner of the flux-form / Born scratch buffers
     struct Wavefield *lin;     // Born: the linearised wavefield (tensor maps of ul)
+    const float *qext;         // space-time source field of this step (Grid layout) or nullptr:
+    float qext_scale;          //   q = qext_scale * qext  (already multiplied by dt^2 [/ irho])
     float *dd_out;             // TMA kernel, Born background pass: write delta
     const float *qsrc;         // TMA kernel, Born linearised pass: read delta of the background
 };

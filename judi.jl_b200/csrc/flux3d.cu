@@ -135,6 +135,8 @@ struct FluxDiv3Args {
     const float *dx, *dy, *dz;
     float *dd_out[2];
     const float *dd_in[2];
+    const float *qext;
+    float qext_scale;
     Fuse f;
 };
 
@@ -202,10 +204,12 @@ __global__ void __launch_bounds__(128) fluxdiv3d_vec(FluxDiv3Args a)
         ld4(a.up[f] + i, upv);
         const bool born = a.dd_in[f] != nullptr;
         if (born) { ld4(a.dm + i, dmv); ld4(a.dd_in[f] + i, ddv); }
+        float qe[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.qext) ld4(a.qext + i, qe);
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const float d1 = uc[f][e] - upv[e];
-            const float q = born ? -dmv[e] * ir[e] * ddv[e] : 0.f;
+            const float q = (born ? -dmv[e] * ir[e] * ddv[e] : 0.f) + a.qext_scale * qe[e];
             delta[f][e] = (cf.dt2 * L[e] + q - sd[e] * d1) * rden[e];
             un[e] = (uc[f][e] + d1) + delta[f][e];
         }
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(128) fluxdiv3d_vec(FluxDiv3Args a)
         }
     }
     const Fuse &fz = a.f;
-    if ((fz.snap[0] || fz.grad || fz.illum) && y >= fz.reg.lo[1] && y < fz.reg.hi[1] &&
+    if ((fz.snap[0] || fz.grad || fz.illum || fz.wrec) && y >= fz.reg.lo[1] && y < fz.reg.hi[1] &&
         z >= fz.reg.lo[2] && z < fz.reg.hi[2]) {
         const long long ri = fz.reg.at(x, y, z);
 #pragma unroll
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(128) fluxdiv3d_vec(FluxDiv3Args a)
                 if (fz.grad) ic += fz.usnap[f][ri + e] * delta[f][e];
             }
             if (fz.illum) fz.illum[ri + e] += cf.dt * e2;
+            if (fz.wrec) fz.wrec[ri + e] += fz.wrec_scale * (NF == 2 ? uc[0][e] + uc[1][e] : uc[0][e]);
             if (fz.grad) fz.grad[ri + e] -= fz.gcoef * ir[e] * ic;
         }
     }
@@ -244,7 +249,8 @@ __global__ void __launch_bounds__(128) fluxdiv3d_vec(FluxDiv3Args a)
 // ------------------------------------------------------------------------------------------
 template <int R>
 static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u, float *const *up,
-                       float *const *dd_out, const float *const *dd_in, const Fuse &fuse)
+                       float *const *dd_out, const float *const *dd_in, const Fuse &fuse,
+                       const float *qext = nullptr, float qext_scale = 0.f)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
     judi_ctx *ctx = M->ctx;
@@ -273,6 +279,8 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
     ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p;
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;
+    ua.qext = qext;
+    ua.qext_scale = qext_scale;
     ua.f = fuse;
     dim3 grd2(((M->N[0] + 3) / 4 + 31) / 32, (M->N[1] + 3) / 4, M->N[2]);
     if (nf == 2) fluxdiv3d_vec<R, 2><<<grd2, blk, 0, ctx->stream>>>(ua);
@@ -289,14 +297,14 @@ bool flux3d_step(const judi_model *M, const StepArgs &s)
     auto run = [&](auto rtag) {
         constexpr int R = decltype(rtag)::value;
         if (!s.born) {
-            flux3d_one<R>(M, W, s.u, s.up, nullptr, nullptr, s.f);
+            flux3d_one<R>(M, W, s.u, s.up, nullptr, nullptr, s.f, s.qext, s.qext_scale);
             return;
         }
         JUDI_REQUIRE(s.born_ic == JUDI_IC_AS,
                      "isic/fwi Born sources are only implemented for constant-density acoustics");
         float *dd[2] = {W->dd[0].p, W->dd[1].p};
         const float *ddc[2] = {W->dd[0].p, W->dd[1].p};
-        flux3d_one<R>(M, W, s.u, s.up, dd, nullptr, s.f);
+        flux3d_one<R>(M, W, s.u, s.up, dd, nullptr, s.f, s.qext, s.qext_scale);
         Fuse none;
         memset(&none, 0, sizeof(none));
         flux3d_one<R>(M, W, s.ul, s.ulp, nullptr, ddc, none);

@@ -27,6 +27,8 @@ struct AcArgs {
     float *ulp;
     const float *dm;
     int born_ic;
+    const float *qext;          // extended / wavefield source (nullptr: off)
+    float qext_scale;
     Fuse f;
 };
 
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) acoustic_generic(AcArgs a)
     long long i = g.at(x, y, z);
     float uc = a.u[i];
     float lap = lap_at<NDIM, R>(g, a.cf, a.u, i);
+    if (a.qext) lap += a.qext_scale * a.qext[i];
     float s = ((a.dx[x] + a.dy[y]) + a.dz[z]) * a.sdamp;
     float mm = a.m[i];
     float rden = 1.0f / (mm + s);
@@ -148,8 +151,9 @@ __global__ void __launch_bounds__(256) acoustic_generic(AcArgs a)
         a.ulp[i] = (ulc + d1l) + deltal;
     }
     const Fuse &f = a.f;
-    if ((f.snap[0] || f.grad || f.illum) && f.reg.has(x, y, z)) {
+    if ((f.snap[0] || f.grad || f.illum || f.wrec) && f.reg.has(x, y, z)) {
         long long ri = f.reg.at(x, y, z);
+        if (f.wrec) f.wrec[ri] += f.wrec_scale * uc;
         if (f.snap[0]) f.snap[0][ri] = uc;
         if (f.illum) f.illum[ri] += a.cf.dt * uc * uc;
         if (f.grad) {
@@ -244,6 +248,8 @@ struct FluxUpdArgs {
     const float *dx, *dy, *dz;
     float *dd_out[2];        // write delta of each field (background pass of Born)
     const float *dd_in[2];   // read delta of the background field (linearised pass of Born)
+    const float *qext;       // extended / wavefield source, fed to every field
+    float qext_scale;
     Fuse f;
 };
 
@@ -273,14 +279,16 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
         float d1 = uc[f] - upv;
         float q = 0.f;
         if (a.dd_in[f]) q = -a.dm[i] * ir * a.dd_in[f][i];  // dt^2 * lin_src ("as")
+        if (a.qext) q += a.qext_scale * a.qext[i];
         delta[f] = (cf.dt2 * L + q - sd * d1) * rden;
         a.up[f][i] = (uc[f] + d1) + delta[f];
         if (a.dd_out[f]) a.dd_out[f][i] = delta[f];
     }
     const Fuse &fz = a.f;
-    if ((fz.snap[0] || fz.grad || fz.illum) && fz.reg.has(x, y, z)) {
+    if ((fz.snap[0] || fz.grad || fz.illum || fz.wrec) && fz.reg.has(x, y, z)) {
         long long ri = fz.reg.at(x, y, z);
         float e2 = 0.f, ic = 0.f;
+        if (fz.wrec) fz.wrec[ri] += fz.wrec_scale * (NF == 2 ? uc[0] + uc[1] : uc[0]);
 #pragma unroll
         for (int f = 0; f < NF; f++) {
             if (fz.snap[f]) fz.snap[f][ri] = uc[f];
@@ -338,6 +346,8 @@ static void launch_acoustic_generic(const judi_model *M, const StepArgs &s)
     a.sdamp = M->dt / M->irho_c;
     a.irho_c = M->irho_c;
     if (s.born) { a.ul = s.ul[0]; a.ulp = s.ulp[0]; a.dm = M->dm.p; a.born_ic = s.born_ic; }
+    a.qext = s.qext;
+    a.qext_scale = s.qext_scale;
     a.f = s.f;
     dim3 blk(64, 4, 1), grd;
     if (NDIM == 3) grd = dim3((M->N[0] + 63) / 64, (M->N[1] + 3) / 4, M->N[2]);
@@ -348,7 +358,8 @@ static void launch_acoustic_generic(const judi_model *M, const StepArgs &s)
 
 template <int NDIM, int R>
 static void flux_one(const judi_model *M, Wavefield *W, const float *const *u, float *const *up,
-                     float *const *dd_out, const float *const *dd_in, const Fuse &fuse)
+                     float *const *dd_out, const float *const *dd_in, const Fuse &fuse,
+                     const float *qext = nullptr, float qext_scale = 0.f)
 {
     judi_ctx *ctx = M->ctx;
     int nf = M->tti ? 2 : 1;
@@ -377,6 +388,8 @@ static void flux_one(const judi_model *M, Wavefield *W, const float *const *u, f
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
     ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p;
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;
+    ua.qext = qext;
+    ua.qext_scale = qext_scale;
     ua.f = fuse;
     if (NDIM == 3) grd = dim3((M->N[0] + 63) / 64, (M->N[1] + 3) / 4, M->N[2]);
     else grd = dim3((M->N[0] + 63) / 64, (M->N[2] + 3) / 4, 1);
@@ -391,14 +404,14 @@ static void step_flux(const judi_model *M, const StepArgs &s)
     Wavefield *W = s.scratch;
     JUDI_REQUIRE(W != nullptr, "flux scratch not bound");
     if (!s.born) {
-        flux_one<NDIM, R>(M, W, s.u, s.up, nullptr, nullptr, s.f);
+        flux_one<NDIM, R>(M, W, s.u, s.up, nullptr, nullptr, s.f, s.qext, s.qext_scale);
         return;
     }
     JUDI_REQUIRE(s.born_ic == JUDI_IC_AS,
                  "isic/fwi Born sources are only implemented for constant-density acoustics");
     float *dd[2] = {W->dd[0].p, W->dd[1].p};
     const float *ddc[2] = {W->dd[0].p, W->dd[1].p};
-    flux_one<NDIM, R>(M, W, s.u, s.up, dd, nullptr, s.f);
+    flux_one<NDIM, R>(M, W, s.u, s.up, dd, nullptr, s.f, s.qext, s.qext_scale);
     Fuse none;
     memset(&none, 0, sizeof(none));
     flux_one<NDIM, R>(M, W, s.ul, s.ulp, nullptr, ddc, none);
@@ -443,7 +456,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     }
     bool ff = M->tti || M->irho_field;
     bool use_tma = M->ndim == 3 && !ff && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
-                   (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr &&
+                   (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && !s.qext && !s.f.wrec &&
                    (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
     if (use_tma && s.born) {
         // Born as two launches of the TMA kernel (44 B/pt): the background step also writes

@@ -194,8 +194,95 @@ static void free_surface(const judi_model *M, float *u)
     launch_count(M->ctx, "free_surface");
 }
 
+// padded-grid compact array -> Grid-layout field (halo untouched, must be zero already)
+__global__ void padded_to_grid_kernel(Grid g, const float *__restrict__ src, float *__restrict__ dst)
+{
+    long long n = (long long)g.n[0] * g.n[1] * g.n[2];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x = (int)(i % g.n[0]);
+    long long t = i / g.n[0];
+    int y = (int)(t % g.n[1]), z = (int)(t / g.n[1]);
+    dst[g.at(x, y, z)] = src[i];
+}
+
+static void padded_to_grid(const judi_model *M, const float *src_dev, float *dst)
+{
+    long long n = (long long)M->N[0] * M->N[1] * M->N[2];
+    padded_to_grid_kernel<<<(int)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, src_dev, dst);
+    launch_count(M->ctx, "padded_to_grid");
+}
+
 // ---- Shot ------------------------------------------------------------------------------------
 Shot::Shot(judi_model *M_) : M(M_), ctx(M_->ctx) {}
+
+static std::vector<float> first_column(judi_ctx *ctx, const float *user, int nt, bool on_device)
+{
+    std::vector<float> h(nt);
+    if (on_device) {
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), user, nt * sizeof(float), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } else memcpy(h.data(), user, nt * sizeof(float));
+    return h;
+}
+
+// Upload the space-time source / extended receiver description of this call.
+void Shot::bind_ext(const ExtSpec *ext, const float *wavelet, int nt, bool on_device)
+{
+    if (!ext) return;
+    size_t ng = (size_t)M->N[0] * M->N[1] * M->N[2];
+    auto to_dev = [&](const float *user, size_t n, DevBuf &owned) -> const float * {
+        if (on_device) return user;
+        owned = DevBuf(ctx, n, false);
+        CUDA_CHECK(cudaMemcpyAsync(owned.p, user, n * sizeof(float), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+        return owned.p;
+    };
+    if (ext->ws) {
+        JUDI_REQUIRE(wavelet != nullptr, "extended source needs a wavelet");
+        DevBuf tmp;
+        const float *d = to_dev(ext->ws, ng, tmp);
+        ws_grid = DevBuf(ctx, (size_t)M->g.nalloc, true);
+        padded_to_grid(M, d, ws_grid.p);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        wt_host = first_column(ctx, wavelet, nt, on_device);
+    }
+    if (ext->wr_wavelet) {
+        JUDI_REQUIRE(ext->w_out != nullptr, "extended receiver needs an output array");
+        wrec = DevBuf(ctx, (size_t)M->full.slot, true);
+        wrt_host = first_column(ctx, ext->wr_wavelet, nt, on_device);
+    }
+    if (ext->qwf) {
+        qwf_dev = to_dev(ext->qwf, ng * (size_t)nt, qwf_owned);
+        qgrid = DevBuf(ctx, (size_t)M->g.nalloc, true);
+    }
+}
+
+void Shot::apply_ext(StepArgs &s, int t)
+{
+    const bool flux = M->tti || M->irho_field;
+    const float base = flux ? M->cf.dt2 : M->cf.dt2 / M->irho_c;  // see the update formula
+    if (ws_grid.p) {
+        s.qext = ws_grid.p;
+        s.qext_scale = base * wt_host[t];
+    } else if (qwf_dev) {
+        size_t ng = (size_t)M->N[0] * M->N[1] * M->N[2];
+        padded_to_grid(M, qwf_dev + (size_t)t * ng, qgrid.p);
+        s.qext = qgrid.p;
+        s.qext_scale = base;
+    }
+    if (wrec.p) {
+        if (!(s.f.snap[0] || s.f.grad || s.f.illum)) s.f.reg = M->full;
+        s.f.wrec = wrec.p;
+        s.f.wrec_scale = M->dt * wrt_host[t];
+    }
+}
+
+void Shot::finish_ext(const ExtSpec *ext, bool on_device)
+{
+    if (ext && ext->w_out && wrec.p) region_output(M, M->full, wrec.p, ext->w_out, on_device, false);
+}
 
 void Shot::make_args(StepArgs &s, Wavefield &W)
 {
@@ -215,6 +302,7 @@ void Shot::step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_
     StepArgs s;
     make_args(s, W);
     if (fuse) s.f = *fuse;
+    if (ext_active()) apply_ext(s, t);
     stencil_step(M, s);
     sparse_step(M, S_in, in ? in->row(t) : nullptr, W.other(0), corr, S_out, W.level(0),
                 out ? out->row(t) : nullptr, nullptr, nullptr, nullptr);
@@ -234,11 +322,12 @@ void Shot::step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fus
     for (int f = 0; f < WL.nf; f++) { s.ul[f] = WL.level(f); s.ulp[f] = WL.other(f); }
     s.lin = &WL;
     if (fuse) s.f = *fuse;
+    if (ext_active()) apply_ext(s, t);
     stencil_step(M, s);
     SparseCorr corr;
     corr.ul_next = WL.other(0);
     corr.born_scale_m = ic != JUDI_IC_AS;
-    sparse_step(M, S_src, q->row(t), W.other(0), &corr, S_rec, WL.level(0),
+    sparse_step(M, S_src, S_src ? q->row(t) : nullptr, W.other(0), &corr, S_rec, WL.level(0),
                 recl ? recl->row(t) : nullptr, recnl ? S_rec : nullptr, W.level(0),
                 recnl ? recnl->row(t) : nullptr);
     if (M->fs)
@@ -257,17 +346,18 @@ static Fuse no_fuse()
 // ---- forward_rec / adjoint --------------------------------------------------------------------
 void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
                      const float *wavelet, int nt, int nrec, const float *rec_coords,
-                     float *rec_out, float *illum_out, int flags)
+                     float *rec_out, float *illum_out, int flags, const ExtSpec *ext)
 {
     judi_ctx *ctx = M->ctx;
     bool dev = flags & JUDI_DATA_ON_DEVICE;
     JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
     Shot sh(M);
+    sh.bind_ext(ext, wavelet, nt, dev);
     SparseSet S_src, S_rec;
-    sparse_build(M, nsrc, src_coords, S_src);
+    if (nsrc > 0) sparse_build(M, nsrc, src_coords, S_src);
     if (nrec > 0) sparse_build(M, nrec, rec_coords, S_rec);
     Traces q, rec;
-    q.load(ctx, wavelet, nt, nsrc, dev);
+    if (nsrc > 0) q.load(ctx, wavelet, nt, nsrc, dev);
     rec.alloc(ctx, nt, nrec);
     Wavefield W;
     W.init(M, false);
@@ -275,21 +365,23 @@ void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    if (persist2d_supported(M, JUDI_IC_AS)) {
+    const SparseSet *pS = nsrc > 0 ? &S_src : nullptr;
+    if (persist2d_supported(M, JUDI_IC_AS) && !sh.ext_active()) {
         P2Fuse pf;
         pf.reg = M->full;
         pf.illum = fz.illum;
-        persist2d_run(M, W, nullptr, fw ? 1 : nt - 2, fw ? nt - 2 : 1, fw ? 1 : -1, &S_src, &q,
+        persist2d_run(M, W, nullptr, fw ? 1 : nt - 2, fw ? nt - 2 : 1, fw ? 1 : -1, pS, &q,
                       nrec > 0 ? &S_rec : nullptr, &rec, nullptr, pf);
     } else if (fw) {
         for (int t = 1; t <= nt - 2; t++)
-            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr,
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, pS, &q, nullptr,
                           nrec > 0 ? &S_rec : nullptr, &rec);
     } else {
         for (int t = nt - 2; t >= 1; t--)
-            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr,
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, pS, &q, nullptr,
                           nrec > 0 ? &S_rec : nullptr, &rec);
     }
+    sh.finish_ext(ext, dev);
     if (rec_out && nrec > 0) rec.store(ctx, rec_out, dev);
     if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
     ctx->flush_timing();
@@ -298,16 +390,19 @@ void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
 
 // ---- forward_no_rec: full wavefield history -----------------------------------------------------
 void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
-                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags)
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags,
+                        const ExtSpec *ext)
 {
     judi_ctx *ctx = M->ctx;
     bool dev = flags & JUDI_DATA_ON_DEVICE;
     JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
     Shot sh(M);
+    sh.bind_ext(ext, wavelet, nt, dev);
     SparseSet S_src;
-    sparse_build(M, nsrc, src_coords, S_src);
+    if (nsrc > 0) sparse_build(M, nsrc, src_coords, S_src);
+    const SparseSet *pS = nsrc > 0 ? &S_src : nullptr;
     Traces q;
-    q.load(ctx, wavelet, nt, nsrc, dev);
+    if (nsrc > 0) q.load(ctx, wavelet, nt, nsrc, dev);
     Wavefield W;
     W.init(M, false);
     DevBuf illum;
@@ -324,12 +419,12 @@ void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords
     else memset(u_out, 0, (size_t)nt * ng * sizeof(float));
     if (fw) {
         for (int t = 1; t <= nt - 2; t++) {
-            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr, nullptr, nullptr);
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, pS, &q, nullptr, nullptr, nullptr);
             emit(t + 1, W.level(0));
         }
     } else {
         for (int t = nt - 2; t >= 1; t--) {
-            sh.step_plain(W, t, illum_out ? &fz : nullptr, &S_src, &q, nullptr, nullptr, nullptr);
+            sh.step_plain(W, t, illum_out ? &fz : nullptr, pS, &q, nullptr, nullptr, nullptr);
             emit(t - 1, W.level(0));
         }
     }
@@ -341,7 +436,7 @@ void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords
 // ---- born_rec ------------------------------------------------------------------------------------
 void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
                   int nrec, const float *rec_coords, int ic, float *rec_out, float *illum_out,
-                  int flags)
+                  int flags, const ExtSpec *ext)
 {
     judi_ctx *ctx = M->ctx;
     bool dev = flags & JUDI_DATA_ON_DEVICE;
@@ -355,15 +450,17 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
         }
         if (illum_out)
             run_forward_rec(M, 1, nsrc, src_coords, wavelet, nt, 0, nullptr, nullptr, illum_out,
-                            flags);
+                            flags, ext);
         return;
     }
     Shot sh(M);
+    sh.bind_ext(ext, wavelet, nt, dev);
     SparseSet S_src, S_rec;
-    sparse_build(M, nsrc, src_coords, S_src);
+    if (nsrc > 0) sparse_build(M, nsrc, src_coords, S_src);
     sparse_build(M, nrec, rec_coords, S_rec);
+    const SparseSet *pS = nsrc > 0 ? &S_src : nullptr;
     Traces q, rec;
-    q.load(ctx, wavelet, nt, nsrc, dev);
+    if (nsrc > 0) q.load(ctx, wavelet, nt, nsrc, dev);
     rec.alloc(ctx, nt, nrec);
     Wavefield W, WL;
     W.init(M, true);
@@ -372,14 +469,14 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    if (persist2d_supported(M, ic)) {
+    if (persist2d_supported(M, ic) && !sh.ext_active()) {
         P2Fuse pf;
         pf.reg = M->full;
         pf.illum = fz.illum;
-        persist2d_run(M, W, &WL, 1, nt - 2, 1, &S_src, &q, &S_rec, &rec, nullptr, pf);
+        persist2d_run(M, W, &WL, 1, nt - 2, 1, pS, &q, &S_rec, &rec, nullptr, pf);
     } else {
         for (int t = 1; t <= nt - 2; t++)
-            sh.step_born(W, WL, t, ic, illum_out ? &fz : nullptr, &S_src, &q, &S_rec, &rec, nullptr);
+            sh.step_born(W, WL, t, ic, illum_out ? &fz : nullptr, pS, &q, &S_rec, &rec, nullptr);
     }
     rec.store(ctx, rec_out, dev);
     if (illum_out) region_output(M, M->full, illum.p, illum_out, dev, false);
@@ -417,11 +514,15 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                            ? M->phys : M->full;
 
     Shot sh(M);
-    SparseSet S_src, S_rec;
-    sparse_build(M, nsrc, src_coords, S_src);
+    ExtSpec jext;
+    jext.ws = o->ws;
+    sh.bind_ext(o->ws ? &jext : nullptr, wavelet, nt, dev);
+    SparseSet S_src0, S_rec;
+    if (nsrc > 0) sparse_build(M, nsrc, src_coords, S_src0);
     sparse_build(M, nrec, rec_coords, S_rec);
+    const SparseSet *pSrc = nsrc > 0 ? &S_src0 : nullptr;
     Traces q, obs, rec, recnl;
-    q.load(ctx, wavelet, nt, nsrc, dev);
+    if (nsrc > 0) q.load(ctx, wavelet, nt, nsrc, dev);
     obs.load(ctx, recin, nt, nrec, dev);
     rec.alloc(ctx, nt, nrec);
     if (born && o->nlind) recnl.alloc(ctx, nt, nrec);
@@ -482,15 +583,15 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot_ptr(save_slot, ff);
         bool any = f.snap[0] || f.illum;
         if (born)
-            sh.step_born(W, WL, t, o->ic, any ? &f : nullptr, &S_src, &q, &S_rec, &rec,
+            sh.step_born(W, WL, t, o->ic, any ? &f : nullptr, pSrc, &q, &S_rec, &rec,
                          o->nlind ? &recnl : nullptr);
         else
-            sh.step_plain(W, t, any ? &f : nullptr, &S_src, &q, nullptr, &S_rec, &rec);
+            sh.step_plain(W, t, any ? &f : nullptr, pSrc, &q, nullptr, &S_rec, &rec);
     };
     // A range of forward steps.  mode 0: no snapshots; 1: slot t/k when t % k == 0; 2: slot t-base
     // (segment recomputation).  2-D constant-density models run the whole range inside one
     // persistent kernel (persist2d.cu), everything else steps kernel by kernel.
-    const bool p2 = persist2d_supported(M, o->ic);
+    const bool p2 = persist2d_supported(M, o->ic) && !sh.ext_active();
     auto fwd_range = [&](int ta, int tb, int mode, int base, bool record) {
         if (tb < ta) return;
         if (p2) {
@@ -503,7 +604,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                 pf.t_sub = mode == 1 ? k : 1;
                 pf.t_base = mode == 1 ? 0 : base;
             }
-            persist2d_run(M, W, born ? &WL : nullptr, ta, tb, 1, &S_src, &q,
+            persist2d_run(M, W, born ? &WL : nullptr, ta, tb, 1, pSrc, &q,
                           record ? &S_rec : nullptr, &rec,
                           (record && born && o->nlind) ? &recnl : nullptr, pf);
             return;
@@ -514,7 +615,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             else {
                 Fuse f = fsave;
                 for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot >= 0 ? slot_ptr(slot, ff) : nullptr;
-                sh.step_plain(W, t, &f, &S_src, &q, nullptr, nullptr, nullptr);
+                sh.step_plain(W, t, &f, pSrc, &q, nullptr, nullptr, nullptr);
             }
         }
     };
@@ -595,8 +696,10 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             corr.reg = reg;
         }
         bool any = f.grad || f.illum;
+        sh.ext_on = false;  // the extended source drives the forward sweep only
         sh.step_plain(V, t, any ? &f : nullptr, &S_rec, &rec, slot >= 0 ? &corr : nullptr, nullptr,
                       nullptr);
+        sh.ext_on = true;
     };
     auto adj_range = [&](int ta, int tb, int mode, int base) {  // ta >= tb, descending
         if (ta < tb) return;

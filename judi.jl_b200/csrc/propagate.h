@@ -12,9 +12,27 @@ struct Traces {
     void store(judi_ctx *ctx, float *user, bool on_device) const;
 };
 
+// optional space-time sources / extended receiver of one call (user pointers, see judi_b200.h)
+struct ExtSpec {
+    const float *ws = nullptr;          // extended source weights, padded grid   (interface.py:50)
+    const float *wr_wavelet = nullptr;  // extended receiver: wavelet to correlate with ...
+    float *w_out = nullptr;             // ... and the padded-grid output           (interface.py:174)
+    const float *qwf = nullptr;         // full wavefield source, nt x padded grid  (interface.py:114)
+};
+
 struct Shot {
     judi_model *M;
     judi_ctx *ctx;
+    // device-side state of the ExtSpec of the current call
+    DevBuf ws_grid, qgrid, wrec;
+    std::vector<float> wt_host, wrt_host;
+    const float *qwf_dev = nullptr;
+    DevBuf qwf_owned;
+    bool ext_on = true;
+    bool ext_active() const { return ext_on && (ws_grid.p || qwf_dev || wrec.p); }
+    void bind_ext(const ExtSpec *ext, const float *wavelet, int nt, bool on_device);
+    void apply_ext(StepArgs &s, int t);
+    void finish_ext(const ExtSpec *ext, bool on_device);
     explicit Shot(judi_model *M);
     void make_args(StepArgs &s, Wavefield &W);
     void step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_in, const Traces *in,
@@ -45,12 +63,13 @@ void grid_output(const judi_model *M, const float *field, float *user, bool on_d
 
 void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
                      const float *wavelet, int nt, int nrec, const float *rec_coords,
-                     float *rec_out, float *illum_out, int flags);
+                     float *rec_out, float *illum_out, int flags, const ExtSpec *ext = nullptr);
 void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
-                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags);
+                        const float *wavelet, int nt, float *u_out, float *illum_out, int flags,
+                        const ExtSpec *ext = nullptr);
 void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
                   int nrec, const float *rec_coords, int ic, float *rec_out, float *illum_out,
-                  int flags);
+                  int flags, const ExtSpec *ext = nullptr);
 void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
                    int nrec, const float *rec_coords, const float *recin, const judi_jopts *o,
                    judi_misfit_fn misfit, void *user, float *f_out, float *grad_out,

@@ -9,9 +9,8 @@ uses, so the `ccall` twin of these wrappers needs no copies.  When the wavelet /
 CUDA tensors (given time-fastest: contiguous (ntrace, nt)) everything stays in HBM and the
 results are written into the caller's `*_out` device tensors.
 
-Out of this backend's scope (raise NotImplementedError): on-the-fly DFT (`freq_list`), extended
-sources (`ws`, `forward_rec_w`, `adjoint_w`, `born_rec_w`), wavefield sources
-(`forward_wf_src*`), `wri_func`, free surface.
+Out of this backend's scope (raise NotImplementedError): on-the-fly DFT (`freq_list`) and
+`wri_func`.
 """
 import ctypes
 import numpy as np
@@ -137,13 +136,12 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     """
     if freq_list is not None and len(freq_list) > 0:
         raise NotImplementedError("on-the-fly DFT gradients are out of the B200 backend's scope")
-    if ws is not None:
-        raise NotImplementedError("extended sources are a 'next' row of the B200 backend")
     if not fw:
         raise NotImplementedError("J_adjoint with fw=False")
     dev = is_device_tensor(wavelet)
-    sc = _coords(src_coords, model.dim)
+    sc = _coords(src_coords, model.dim) if src_coords is not None else None
     rc = _coords(rec_coords, model.dim)
+    wsp = _weights(model, ws) if ws is not None else None
     o = L.JudiJopts()
     o.is_residual = int(bool(is_residual))
     o.checkpointing = int(bool(checkpointing))
@@ -154,6 +152,7 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     o.nlind = int(bool(nlind))
     o.illum = int(bool(illum))
     o.snapshot_region = L.SNAP_PHYSICAL if snapshot_region == "physical" else L.SNAP_PADDED
+    o.ws = _ptr(wsp)
     flags = (L.DATA_ON_DEVICE if dev else 0) | (L.GRAD_ACCUMULATE if accumulate else 0)
     Iu = Iv = None
     if dev:
@@ -188,7 +187,10 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     fptr = None
     if return_obj or fbuf is not None:
         fptr = _ptr(fbuf) if dev else ctypes.addressof(fbuf)
-    L.check(L.lib().judi_J_adjoint(model.h, nsrc, sc.ctypes.data, _ptr(q), nt, nrec,
+    if sc is None:
+        nsrc = 0
+    L.check(L.lib().judi_J_adjoint(model.h, nsrc, sc.ctypes.data if sc is not None else None,
+                                   _ptr(q), nt, nrec,
                                    rc.ctypes.data, _ptr(d), ctypes.byref(o),
                                    ctypes.cast(cb, ctypes.c_void_p), None, fptr, _ptr(g),
                                    _ptr(Iu), _ptr(Iv), flags))
@@ -198,17 +200,88 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     return g, Iu, Iv
 
 
-# ---- out of scope: keep the reference names so callers fail loudly, not silently ---------------
-def _out_of_scope(name):
-    def fn(*a, **k):
-        raise NotImplementedError("%s is outside the B200 backend's hot path (see DESIGN.md)" % name)
-    fn.__name__ = name
-    return fn
+def _weights(model, w):
+    """Extended-source weights on the padded grid (python_interface.jl:129 zero-pads them)."""
+    if is_device_tensor(w):
+        return w
+    w = np.asarray(w, dtype=np.float32)
+    if w.shape == model.shape:
+        w = np.pad(w, model.padsizes, mode="constant")
+    assert w.shape == model.shape_pml, "weights must have the (padded) model shape"
+    return np.asfortranarray(w)
 
 
-forward_rec_w = _out_of_scope("forward_rec_w")
-forward_wf_src = _out_of_scope("forward_wf_src")
-forward_wf_src_norec = _out_of_scope("forward_wf_src_norec")
-adjoint_w = _out_of_scope("adjoint_w")
-born_rec_w = _out_of_scope("born_rec_w")
-wri_func = _out_of_scope("wri_func")
+# Pr*F*Pw'*w
+def forward_rec_w(model, weight, wavelet, rec_coords, f0=0.015, illum=False, fw=True):
+    """Forward modeling of an extended source with receivers Pr*F*Pw^T*w (interface.py:50-80)."""
+    rc = _coords(rec_coords, model.dim)
+    q, nt, _ = _traces(wavelet)
+    w = _weights(model, weight)
+    rec = np.zeros((nt, rc.shape[0]), dtype=np.float32, order="F")
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_forward_rec_w(model.h, int(bool(fw)), _ptr(w), _ptr(q), nt, rc.shape[0],
+                                       rc.ctypes.data, _ptr(rec), _ptr(I), 0))
+    return rec, I
+
+
+# Pw*F'*Pr'*d_obs
+def adjoint_w(model, rec_coords, data, wavelet, f0=0.015, illum=False, fw=True):
+    """Adjoint modeling of a shot record for an extended source Pw*F^T*Pr^T*d (interface.py:174-204):
+    returns the spatial distribution on the padded grid."""
+    rc = _coords(rec_coords, model.dim)
+    d, nt, nrec = _traces(data)
+    q, ntq, _ = _traces(wavelet)
+    assert ntq == nt and nrec == rc.shape[0]
+    w = _grid_out(model, None)
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_adjoint_w(model.h, int(bool(fw)), nrec, rc.ctypes.data, _ptr(d), _ptr(q),
+                                   nt, _ptr(w), _ptr(I), 0))
+    return w, I
+
+
+# d/dm (Pr*F*Pw'*w)
+def born_rec_w(model, weight, wavelet, rec_coords, ic="as", f0=0.015, illum=False, fw=True):
+    """Linearized modeling of an extended source (interface.py:244-276)."""
+    rc = _coords(rec_coords, model.dim)
+    q, nt, _ = _traces(wavelet)
+    w = _weights(model, weight)
+    rec = np.zeros((nt, rc.shape[0]), dtype=np.float32, order="F")
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_born_rec_w(model.h, _ptr(w), _ptr(q), nt, rc.shape[0], rc.ctypes.data,
+                                    L.IC_CODES[ic], _ptr(rec), _ptr(I), 0))
+    return rec, I
+
+
+def _wf_src(model, u):
+    u = np.asarray(u, dtype=np.float32)
+    assert u.shape[1:] == model.shape_pml, "wavefield source must be (nt, padded grid)"
+    # memory: time slowest, x fastest
+    return np.asfortranarray(np.moveaxis(u, 0, -1)), u.shape[0]
+
+
+# Pr*F*u
+def forward_wf_src(model, u, rec_coords, f0=0.015, illum=False, fw=True):
+    """Forward modeling of a full wavefield source Pr*F*u (interface.py:114-142)."""
+    rc = _coords(rec_coords, model.dim)
+    us, nt = _wf_src(model, u)
+    rec = np.zeros((nt, rc.shape[0]), dtype=np.float32, order="F")
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_forward_wf_src(model.h, int(bool(fw)), _ptr(us), nt, rc.shape[0],
+                                        rc.ctypes.data, _ptr(rec), _ptr(I), 0))
+    return rec, I
+
+
+# F*u
+def forward_wf_src_norec(model, u, f0=0.015, illum=False, fw=True):
+    """Forward modeling of a full wavefield source without receivers F*u (interface.py:145-171)."""
+    us, nt = _wf_src(model, u)
+    out = np.zeros(model.shape_pml + (nt,), dtype=np.float32, order="F")
+    I = _grid_out(model, None) if illum else None
+    L.check(L.lib().judi_forward_wf_src_norec(model.h, int(bool(fw)), _ptr(us), nt, _ptr(out),
+                                              _ptr(I), 0))
+    return np.moveaxis(out, -1, 0), I
+
+
+def wri_func(*a, **k):
+    """Wavefield-reconstruction inversion (interface.py:568) is outside this backend's hot path."""
+    raise NotImplementedError("wri_func is outside the B200 backend's hot path (see DESIGN.md)")

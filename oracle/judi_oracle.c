@@ -62,6 +62,10 @@ typedef struct {
     int irho_is_field;
     real irho_c;
     real *m, *damp, *irho, *eps, *delta, *theta, *phi, *dm;
+    /* extended / wavefield sources and extended receiver of the current call (oracle_set_ext) */
+    const real *ext_ws, *ext_wt;   /* q(x,t) = ws(x) * wt[t]        (fields_exprs.py:58-82) */
+    real *ext_wr; const real *ext_wrt; /* wr(x) += dt * u[t](x) * wrt[t]  (fields_exprs.py:85-103) */
+    const real *ext_qwf;           /* q(x,t) = qwf[t](x), full wavefield source (fields.py:103-120) */
     real c2[MAXR + 1]; /* centred 2nd-derivative weights, offset k */
     real w1[MAXR + 1]; /* staggered 1st-derivative weights, offset k-1/2 (k>=1) */
 } ogrid;
@@ -210,6 +214,13 @@ void oracle_destroy(ogrid *g)
 int oracle_real_size(void) { return (int)sizeof(real); }
 
 void oracle_set_fs(ogrid *g, int fs) { g->fs = fs; }
+
+/* All arrays padded-grid sized, C order, no halo (ws, wr, qwf slices); wt / wrt have nt entries. */
+void oracle_set_ext(ogrid *g, const real *ws, const real *wt, real *wr, const real *wrt,
+                    const real *qwf)
+{
+    g->ext_ws = ws; g->ext_wt = wt; g->ext_wr = wr; g->ext_wrt = wrt; g->ext_qwf = qwf;
+}
 
 /* freesurface(model, u_n): u(-k) = -u(k-1), k = 1..so/2 (loop over zfs), then u(0) = 0;
  * placed after the injection (`extra` in operators.py:131,188,231). */
@@ -562,6 +573,40 @@ static void fast_step(const ogrid *g, const real *u, real *up, const real *us, r
     else fast_step_r8(g, u, up, us, G, wdt);
 }
 
+/* q[f] = ws*wt[t] + qwf[t] on the halo'd grid for every field (extented_src feeds both TTI
+ * fields, fields_exprs.py:79-81); returns 0 when no space-time source is active. */
+static int ext_source(const ogrid *g, int t, int nf, real **q)
+{
+    if (!g->ext_ws && !g->ext_qwf) return 0;
+    int X = g->N[0], Y = g->N[1], Z = g->N[2];
+    size_t ng = (size_t)X * Y * Z;
+    for (int x = 0; x < X; x++)
+        for (int y = 0; y < Y; y++)
+            for (int z = 0; z < Z; z++) {
+                size_t c = ((size_t)x * Y + y) * Z + z, i = IDX(g, x, y, z);
+                real v = 0;
+                if (g->ext_ws) v += g->ext_ws[c] * g->ext_wt[t];
+                if (g->ext_qwf) v += g->ext_qwf[(size_t)t * ng + c];
+                for (int f = 0; f < nf; f++) q[f][i] = v;
+            }
+    return 1;
+}
+
+/* extended receiver: wr += dt * (sum of fields at level t) * wrt[t] */
+static void ext_receiver(const ogrid *g, int t, int nf, real *const *u)
+{
+    if (!g->ext_wr) return;
+    int X = g->N[0], Y = g->N[1], Z = g->N[2];
+    for (int x = 0; x < X; x++)
+        for (int y = 0; y < Y; y++)
+            for (int z = 0; z < Z; z++) {
+                size_t c = ((size_t)x * Y + y) * Z + z, i = IDX(g, x, y, z);
+                real wf = u[0][i];
+                if (nf == 2) wf += u[1][i];
+                g->ext_wr[c] += g->dt * wf * g->ext_wrt[t];
+            }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* forward / adjoint propagation:  operators.py:81-135 schedule                                 */
 /*   pde ; inject src[t] into the new level ; rec[t] = interp(level t) ; save ; illum           */
@@ -584,11 +629,16 @@ int oracle_forward(const ogrid *g, int fw, int nt, const osparse *src, const rea
     if (rec && rec_out) memset(rec_out, 0, sizeof(real) * (size_t)nt * rec->np);
     int cur = 0; /* bufs[f][cur] = level t, bufs[f][1-cur] = level t-/+1 -> overwritten */
     int t0 = fw ? 1 : nt - 2, t1 = fw ? nt - 1 : 0, dtt = fw ? 1 : -1;
+    real *qe[2] = {NULL, NULL};
+    if (g->ext_ws || g->ext_qwf)
+        for (int f = 0; f < nf; f++) qe[f] = (real *)calloc(g->ntot, sizeof(real));
     for (int t = t0; t != t1; t += dtt) {
         real *u[2], *up[2];
         for (int f = 0; f < nf; f++) { u[f] = bufs[f][cur]; up[f] = bufs[f][1 - cur]; }
-        if (fast_ok(g)) fast_step(g, u[0], up[0], NULL, NULL, 0);
-        else step_fields(g, &sc, nf, u, up, up, NULL);
+        int has_q = ext_source(g, t, nf, qe);
+        ext_receiver(g, t, nf, u);
+        if (fast_ok(g) && !has_q) fast_step(g, u[0], up[0], NULL, NULL, 0);
+        else step_fields(g, &sc, nf, u, up, up, has_q ? (const real *const *)qe : NULL);
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
         for (int f = 0; f < nf; f++) apply_fs(g, up[f]);
         if (rec && rec_out) interpolate(rec, u[0], rec_out + (size_t)t * rec->np);
@@ -607,8 +657,10 @@ int oracle_forward(const ogrid *g, int fw, int nt, const osparse *src, const rea
     }
     if (I) { extract(g, I, illum); free(I); }
     scratch_free(&sc);
-    for (int f = 0; f < nf; f++)
+    for (int f = 0; f < nf; f++) {
         for (int b = 0; b < 2; b++) free(bufs[f][b]);
+        free(qe[f]);
+    }
     return 0;
 }
 
@@ -683,7 +735,10 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
             ul[f] = bl[f][cur]; ulp[f] = bl[f][1 - cur];
             memcpy(uprev_copy[f], up[f], g->ntot * sizeof(real)); /* keep u[t-1] for u.dt2 */
         }
-        step_fields(g, &sc, nf, u, up, up, NULL);
+        {
+            int has_q = ext_source(g, t, nf, q); /* q[] is rebuilt below for the linearised field */
+            step_fields(g, &sc, nf, u, up, up, has_q ? (const real *const *)q : NULL);
+        }
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
         for (int f = 0; f < nf; f++) apply_fs(g, up[f]);
         if (recnl_out) interpolate(rec, u[0], recnl_out + (size_t)t * rec->np);

@@ -66,6 +66,7 @@ def _lib(precision):
     lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
     lib.oracle_set_fast.argtypes = [ctypes.c_int]
     lib.oracle_set_fs.argtypes = [P, ctypes.c_int]
+    lib.oracle_set_ext.argtypes = [P, P, P, P, P, P]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
     _LIBS[precision] = lib
@@ -332,8 +333,39 @@ def nsave(nt, t_sub):
 
 # --------------------------------------------------------------------------------------------
 # propagators.py
-def forward(model, src_coords, rcv_coords, wavelet, save=False, t_sub=1, illum=False, fw=True):
-    """propagators.py:15-89 -> (rec, usave, I)."""
+class _Ext(object):
+    """Binds extended source (ws, wavelet), extended receiver (wr wavelet) or a full wavefield
+    source for the duration of one propagation (fields_exprs.py:58-103, fields.py:103-120)."""
+
+    def __init__(self, model, ws=None, wavelet=None, wr=None, qwf=None):
+        self.model, dt_ = model, model.lib._dtype
+        self.ws = None if ws is None else np.ascontiguousarray(ws, dtype=dt_)
+        self.wt = None if ws is None else np.ascontiguousarray(np.asarray(wavelet)[:, 0], dtype=dt_)
+        self.wrt = None if wr is None else np.ascontiguousarray(np.asarray(wr)[:, 0], dtype=dt_)
+        self.wr = None if wr is None else np.zeros(model.shape_pml, dtype=dt_)
+        self.qwf = None if qwf is None else np.ascontiguousarray(qwf, dtype=dt_)
+        if self.ws is not None:
+            assert self.ws.shape == model.shape_pml, "weights must be padded-grid sized"
+
+    def __enter__(self):
+        self.model.lib.oracle_set_ext(self.model.handle(), _ptr(self.ws), _ptr(self.wt),
+                                      _ptr(self.wr), _ptr(self.wrt), _ptr(self.qwf))
+        return self
+
+    def __exit__(self, *a):
+        self.model.lib.oracle_set_ext(self.model.handle(), None, None, None, None, None)
+
+
+def forward(model, src_coords, rcv_coords, wavelet, save=False, t_sub=1, illum=False, fw=True,
+            ws=None, wr=None, qwf=None):
+    """propagators.py:15-89 -> (rec, usave, I), or (wr, usave, I) with an extended receiver."""
+    if ws is not None or wr is not None or qwf is not None:
+        nt = wavelet.shape[0] if wavelet is not None else qwf.shape[0]
+        with _Ext(model, ws=ws, wavelet=wavelet, wr=wr, qwf=qwf) as ext:
+            wav = wavelet if wavelet is not None else np.zeros((nt, 1), dtype=np.float32)
+            rec, usave, I = forward(model, src_coords, rcv_coords, wav, save=save, t_sub=t_sub,
+                                    illum=illum, fw=fw)
+        return (ext.wr if wr is not None else rec), usave, I
     lib, dt_ = model.lib, model.lib._dtype
     nt = wavelet.shape[0]
     src = _Sparse(model, src_coords) if src_coords is not None else None
@@ -351,8 +383,12 @@ def forward(model, src_coords, rcv_coords, wavelet, save=False, t_sub=1, illum=F
 
 
 def born(model, src_coords, rcv_coords, wavelet, save=False, ic="as", t_sub=1, nlind=False,
-         illum=False):
+         illum=False, ws=None):
     """propagators.py:155-230 -> ((recl, recnl) if nlind else recl, usave, I)."""
+    if ws is not None:
+        with _Ext(model, ws=ws, wavelet=wavelet):
+            return born(model, src_coords, rcv_coords, wavelet, save=save, ic=ic, t_sub=t_sub,
+                        nlind=nlind, illum=illum)
     lib, dt_ = model.lib, model.lib._dtype
     nt = wavelet.shape[0]
     if model.dm is None:
@@ -361,7 +397,7 @@ def born(model, src_coords, rcv_coords, wavelet, save=False, ic="as", t_sub=1, n
                                 illum=illum)
         recl = np.zeros_like(rnl)
         return ((recl, rnl) if nlind else recl), usave, I
-    src = _Sparse(model, src_coords)
+    src = _Sparse(model, src_coords) if src_coords is not None else None
     rec = _Sparse(model, rcv_coords)
     wav = np.ascontiguousarray(wavelet, dtype=dt_)
     recl = np.zeros((nt, rec.np), dtype=dt_)
@@ -370,7 +406,7 @@ def born(model, src_coords, rcv_coords, wavelet, save=False, ic="as", t_sub=1, n
     if save:
         usave = np.zeros((nsave(nt, t_sub), model.nfields) + model.shape_pml, dtype=dt_)
     I = np.zeros(model.shape_pml, dtype=dt_) if illum else None
-    rc = lib.oracle_born(model.handle(), nt, src.h, _ptr(wav), rec.h, _ptr(recl), _ptr(recnl),
+    rc = lib.oracle_born(model.handle(), nt, src.h if src else None, _ptr(wav), rec.h, _ptr(recl), _ptr(recnl),
                          IC[ic], int(bool(save)), int(t_sub), _ptr(usave), _ptr(I))
     assert rc == 0
     return ((recl, recnl) if nlind else recl), usave, I
@@ -421,9 +457,39 @@ def born_rec(model, src_coords, wavelet, rec_coords, ic="as", illum=False):
     return rec, I
 
 
+def forward_rec_w(model, weight, wavelet, rec_coords, illum=False, fw=True):
+    """interface.py:50-80."""
+    rec, _, I = forward(model, None, rec_coords, wavelet, ws=weight, illum=illum, fw=fw)
+    return rec, I
+
+
+def adjoint_w(model, rec_coords, data, wavelet, illum=False, fw=True):
+    """interface.py:174-204: data injected at the receivers, wavefield correlated with the wavelet."""
+    w, _, I = forward(model, rec_coords, None, data, wr=wavelet, illum=illum, fw=fw)
+    return w, I
+
+
+def born_rec_w(model, weight, wavelet, rec_coords, ic="as", illum=False):
+    """interface.py:244-276."""
+    rec, _, I = born(model, None, rec_coords, wavelet, ws=weight, ic=ic, illum=illum)
+    return rec, I
+
+
+def forward_wf_src(model, u, rec_coords, illum=False, fw=True):
+    """interface.py:114-142: u is (nt, padded grid)."""
+    rec, _, I = forward(model, None, rec_coords, None, qwf=u, illum=illum, fw=fw)
+    return rec, I
+
+
+def forward_wf_src_norec(model, u, illum=False, fw=True):
+    """interface.py:145-171: returns the wavefield history (nt, padded grid)."""
+    _, usave, I = forward(model, None, None, None, qwf=u, save=True, illum=illum, fw=fw)
+    return usave[:, 0], I
+
+
 def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
               checkpointing=False, n_checkpoints=None, t_sub=1, return_obj=False, ic="as",
-              illum=False, born_fwd=False, nlind=False, misfit=None):
+              illum=False, born_fwd=False, nlind=False, misfit=None, ws=None):
     """interface.py:279-345 + :411-470.  Checkpointing (interface.py:473-562) recomputes the
     forward wavefield instead of storing it, so its result equals the t_sub=1 standard path;
     the oracle evaluates it that way."""
@@ -431,10 +497,10 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
         t_sub = 1
     if born_fwd:
         rec, u, Iu = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind,
-                          illum=illum, ic=ic, t_sub=t_sub)
+                          illum=illum, ic=ic, t_sub=t_sub, ws=ws)
     else:
         rec, u, Iu = forward(model, src_coords, rec_coords, wavelet, save=True, illum=illum,
-                             t_sub=t_sub)
+                             t_sub=t_sub, ws=ws)
     f, residual = Loss(rec, recin, float(model.critical_dt), is_residual=is_residual,
                        misfit=misfit)
     g, Iv = gradient(model, residual, rec_coords, u, t_sub=t_sub, ic=ic, illum=illum)

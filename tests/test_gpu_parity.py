@@ -277,3 +277,40 @@ def test_free_surface_parity(kind, ndim):
     fo, go, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True)
     assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
     assert rel_l2(g, go) < TOL_GRAD
+
+
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2)])
+def test_extended_and_wavefield_sources(kind, ndim):
+    """The remaining entry points of src/pysource/interface.py: forward_rec_w (:50), adjoint_w
+    (:174), born_rec_w (:244), J_adjoint(ws=...) and forward_wf_src / _norec (:114, :145);
+    adjointness as in test/test_adjoint.jl:85-115."""
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, 8, nt=200)
+    rng = np.random.default_rng(11)
+    w = np.zeros(gm.shape_pml, dtype=np.float32)
+    box = tuple(slice(s // 2 - 6, s // 2 + 6) for s in gm.shape_pml)
+    w[box] = rng.standard_normal(w[box].shape).astype(np.float32)
+    d, _ = J.forward_rec_w(gm, w, q, rec)
+    do, _ = O.forward_rec_w(om, w, q, rec)
+    assert np.linalg.norm(do) > 0 and rel_l2(d, do) < TOL_SHOT
+    y = rng.standard_normal(d.shape).astype(np.float32)
+    wa, _ = J.adjoint_w(gm, rec, y, q, fw=False)
+    wao, _ = O.adjoint_w(om, rec, y, q, fw=False)
+    assert rel_l2(wa, wao) < TOL_SHOT
+    a, b = dt * np.vdot(d.astype(np.float64), y), np.vdot(w.astype(np.float64), wa)
+    assert abs((a - b) / (a + b)) < TOL_DOT
+    dl, _ = J.born_rec_w(gm, w, q, rec)
+    dlo, _ = O.born_rec_w(om, w, q, rec)
+    assert np.linalg.norm(dlo) > 0 and rel_l2(dl, dlo) < TOL_SHOT
+    g, _, _ = J.J_adjoint(gm, None, q, rec, y, is_residual=True, ws=w)
+    go, _, _ = O.J_adjoint(om, None, q, rec, y, is_residual=True, ws=w)
+    assert rel_l2(g, go) < TOL_GRAD
+    # full wavefield source (short, the array is nt x grid)
+    nts = 40
+    usrc = np.zeros((nts,) + gm.shape_pml, dtype=np.float32)
+    usrc[(slice(2, 30),) + box] = rng.standard_normal((28,) + w[box].shape).astype(np.float32)
+    r1, _ = J.forward_wf_src(gm, usrc, rec)
+    r1o, _ = O.forward_wf_src(om, usrc, rec)
+    assert np.linalg.norm(r1o) > 0 and rel_l2(r1, r1o) < TOL_SHOT
+    u1, _ = J.forward_wf_src_norec(gm, usrc)
+    u1o, _ = O.forward_wf_src_norec(om, usrc)
+    assert rel_l2(u1[2:nts - 1], u1o[2:nts - 1]) < TOL_SHOT
