@@ -161,6 +161,7 @@ def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0):
     `ns` forward steps + `ns` adjoint+IC steps on the full grid, extrapolated to one shot."""
     from oracle import oracle as O
     O.build()
+    ncores = O.set_threads(os.cpu_count() or 1)   # torchrun sets OMP_NUM_THREADS=1: override
     v0 = smooth_model(velocity(shape))
     model = O.Model((0., 0., 0.), SPACING, shape, space_order=SO, nbl=NBL,
                     m=(1 / v0 ** 2).astype(np.float32), dt=DT, precision="f32")
@@ -175,14 +176,14 @@ def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0):
     times = times[warmup:]
     sec_per_shot = float(np.mean(times)) / ns * (nt - 2)
     npts = float(np.prod(model.shape_pml))
-    return {"value": 1.0 / sec_per_shot, "unit": "shots/s", "cores": os.cpu_count(),
+    return {"value": 1.0 / sec_per_shot, "unit": "shots/s", "cores": ncores,
             "kind": "port",
             "sample": "%d of %d forward + %d of %d adjoint+IC time steps on the full %dx%dx%d "
                       "padded grid (t_sub=%d), extrapolated linearly to one shot; OpenMP, all %d "
                       "host threads; oracle = C port of the reference's Devito schedule (Devito "
                       "itself is not installable offline)"
                       % (ns, nt - 2, ns, nt - 2, model.shape_pml[0], model.shape_pml[1],
-                         model.shape_pml[2], t_sub, os.cpu_count()),
+                         model.shape_pml[2], t_sub, ncores),
             "gpts_per_s": 2 * ns * npts / float(np.mean(times)) / 1e9,
             "ms_per_step": 1e3 * sec_per_shot}
 

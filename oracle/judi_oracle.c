@@ -213,6 +213,21 @@ void oracle_destroy(ogrid *g)
 
 int oracle_real_size(void) { return (int)sizeof(real); }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py asks for all host threads */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 void oracle_set_fs(ogrid *g, int fs) { g->fs = fs; }
 
 /* All arrays padded-grid sized, C order, no halo (ws, wr, qwf slices); wt / wrt have nt entries. */

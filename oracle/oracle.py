@@ -66,6 +66,8 @@ def _lib(precision):
     lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
     lib.oracle_set_fast.argtypes = [ctypes.c_int]
     lib.oracle_set_fs.argtypes = [P, ctypes.c_int]
+    lib.oracle_set_threads.argtypes = [ctypes.c_int]
+    lib.oracle_set_threads.restype = ctypes.c_int
     lib.oracle_set_ext.argtypes = [P, P, P, P, P, P]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
@@ -512,6 +514,11 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
 def set_fast(on, precision="f32"):
     """Toggle the vectorised constant-density fast path (bit-identical to the generic one)."""
     _lib(precision).oracle_set_fast(int(bool(on)))
+
+
+def set_threads(n, precision="f32"):
+    """Number of OpenMP threads of the oracle loops (returns the value in effect)."""
+    return int(_lib(precision).oracle_set_threads(int(n)))
 
 
 def time_steps(model, nsteps, with_gradient=True, t_sub=1):
