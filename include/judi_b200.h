@@ -66,8 +66,11 @@ enum { JUDI_IC_AS = 0, JUDI_IC_ISIC = 1, JUDI_IC_FWI = 2 };
 enum {
     JUDI_DATA_ON_DEVICE = 1, /* wavelet / recin / rec_out / grad_out / illum pointers are device
                                 pointers (same layouts); coordinates are always host pointers */
-    JUDI_GRAD_ACCUMULATE = 2 /* grad_out += g and *f_out += f instead of overwriting: the local
+    JUDI_GRAD_ACCUMULATE = 2, /* grad_out += g and *f_out += f instead of overwriting: the local
                                 reduction of src/TimeModeling/Modeling/distributed.jl:6-22 */
+    JUDI_OUT_ON_DEVICE = 4   /* J_adjoint: f_out / grad_out / illum are device pointers although the
+                                traces are host arrays: a worker sums its shots in HBM and copies
+                                the gradient back once, after the all-reduce */
 };
 
 /* where forward-wavefield snapshots are kept for the imaging condition */
@@ -114,6 +117,13 @@ long long judi_ctx_launch_count(judi_ctx *ctx);
 /* accumulated device time (ms, CUDA events on the context stream) of the stencil kernels, and
  * the number of stencil launches and grid-point updates they covered; reset clears them */
 int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, double *points);
+/* the same split by the flavour of the time step (what was fused into the stencil launch) */
+#define JUDI_KIND_PLAIN 0 /* leapfrog step only (+ illumination) */
+#define JUDI_KIND_SAVE 1  /* + snapshot save (forward sweep of a gradient) */
+#define JUDI_KIND_IC 2    /* + imaging condition (adjoint sweep of a gradient) */
+#define JUDI_KIND_BORN 3  /* background + linearised field */
+#define JUDI_NUM_KINDS 4
+int judi_ctx_stencil_stats_kind(judi_ctx *ctx, int kind, double *ms, long long *launches);
 int judi_ctx_reset_stats(judi_ctx *ctx);
 /* tuning knobs: "acoustic3d_kernel" (0 generic, 1 TMA z-marching), "zchunks", ... */
 int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value);
@@ -190,6 +200,23 @@ int judi_forward_wf_src(judi_model *model, int fw, const float *u_src, int nt, i
 /* forward_wf_src_norec (interface.py:145-171; python_interface.jl:79): u_out = F*u_src */
 int judi_forward_wf_src_norec(judi_model *model, int fw, const float *u_src, int nt, float *u_out,
                               float *illum_out, int flags);
+
+/* ---- the steps around every propagator call ----------------------------- */
+/* remove_padding (src/TimeModeling/Utils/auxiliaryFunctions.jl:79-89; called at
+ * time_modeling_serial.jl:70-71, misfit_fg.jl:77): crop a padded-grid array to the physical
+ * grid; true_adjoint != 0 first sums every pad cell into the nearest edge cell (the adjoint of
+ * edge-replication padding, `sum_padding=true`).  flags: JUDI_DATA_ON_DEVICE = `padded` is a
+ * device pointer, JUDI_OUT_ON_DEVICE = `out` is a device pointer. */
+int judi_remove_padding(const judi_model *model, const float *padded, int true_adjoint, float *out,
+                        int flags);
+
+/* time_resample (src/TimeModeling/Utils/time_utilities.jl:32-48, SincInterpolation :84; called
+ * at python_interface.jl:33-39 on the wavelet / data and time_modeling_serial.jl:78-79 on the
+ * shot record): traces are time fastest, in = [ntrace][nt_in] sampled at t0_in + i*dt_in,
+ * out = [ntrace][nt_out] at t0_out + j*dt_out.  Equal steps copy, integer ratios decimate,
+ * everything else is sinc interpolation.  Flags as for judi_remove_padding. */
+int judi_time_resample(judi_ctx *ctx, const float *in, int nt_in, int ntrace, float t0_in,
+                       float dt_in, float *out, int nt_out, float t0_out, float dt_out, int flags);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,8 @@ slimgroup/JUDI.jl: the part of `src/pysource` that Devito-generated code execute
   interface.py   mirror of pysource.interface (forward_rec, born_rec, J_adjoint, ...)
   objectives.py  mirror of the Julia L2/L5 drivers (multi_src_fg!, fwi_objective,
                  lsrtm_objective): shot partition over GPUs + one all-reduce
+  time_modeling.py  mirror of the per-shot driver (_time_modeling / devito_interface):
+                 limit_m, device time_resample, device remove_padding
 
 The directory name contains a dot, so the package is imported through the top-level shim
 `judi_jl_b200` (see /judi_jl_b200.py).
@@ -16,3 +18,5 @@ from . import interface  # noqa: F401
 from .interface import (forward_rec, forward_no_rec, born_rec, J_adjoint, forward_rec_w,  # noqa: F401
                         adjoint_w, born_rec_w, forward_wf_src, forward_wf_src_norec)
 from . import objectives  # noqa: F401
+from . import time_modeling  # noqa: F401
+from .time_modeling import Geometry, Options, time_resample  # noqa: F401

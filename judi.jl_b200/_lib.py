@@ -14,7 +14,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 
 PARAM_NONE, PARAM_SCALAR, PARAM_ARRAY = 0, 1, 2
 IC_CODES = {"as": 0, "isic": 1, "fwi": 2}
-DATA_ON_DEVICE, GRAD_ACCUMULATE = 1, 2
+DATA_ON_DEVICE, GRAD_ACCUMULATE, OUT_ON_DEVICE = 1, 2, 4
 SNAP_PADDED, SNAP_PHYSICAL = 0, 1
 
 
@@ -55,6 +55,9 @@ SIGNATURES = {
     "judi_ctx_stencil_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                               ctypes.POINTER(ctypes.c_longlong),
                                               ctypes.POINTER(ctypes.c_double)]),
+    "judi_ctx_stencil_stats_kind": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_double),
+                                                   ctypes.POINTER(ctypes.c_longlong)]),
     "judi_ctx_reset_stats": (ctypes.c_int, [ctypes.c_void_p]),
     "judi_ctx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "judi_model_create": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.POINTER(JudiModelDesc)]),
@@ -97,6 +100,12 @@ SIGNATURES = {
     "judi_forward_wf_src_norec": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_int]),
+    "judi_remove_padding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int]),
+    "judi_time_resample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_int]),
 }
 
 _lib = None

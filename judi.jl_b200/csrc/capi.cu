@@ -57,7 +57,7 @@ void judi_ctx_destroy(judi_ctx *ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -86,10 +86,22 @@ int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, doubl
     API_END(1)
 }
 
+int judi_ctx_stencil_stats_kind(judi_ctx *ctx, int kind, double *ms, long long *launches)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx && kind >= 0 && kind < JUDI_NUM_KINDS, "unknown launch kind");
+    ctx->flush_timing();
+    if (ms) *ms = ctx->kind_ms[kind];
+    if (launches) *launches = ctx->kind_launches[kind];
+    return 0;
+    API_END(1)
+}
+
 int judi_ctx_reset_stats(judi_ctx *ctx)
 {
     API_BEGIN
     ctx->flush_timing();
+    for (int k = 0; k < JUDI_NUM_KINDS; k++) { ctx->kind_ms[k] = 0; ctx->kind_launches[k] = 0; }
     ctx->stencil_ms = 0;
     ctx->stencil_launches = 0;
     ctx->stencil_points = 0;
@@ -358,6 +370,28 @@ int judi_forward_wf_src_norec(judi_model *model, int fw, const float *u_src, int
     ExtSpec ext;
     ext.qwf = u_src;
     run_forward_no_rec(model, fw, 0, nullptr, nullptr, nt, u_out, illum_out, flags, &ext);
+    return 0;
+    API_END(1)
+}
+
+int judi_remove_padding(const judi_model *model, const float *padded, int true_adjoint, float *out,
+                        int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && padded && out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    run_remove_padding(model, padded, true_adjoint, out, flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_time_resample(judi_ctx *ctx, const float *in, int nt_in, int ntrace, float t0_in,
+                       float dt_in, float *out, int nt_out, float t0_out, float dt_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx && in && out, "null argument");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    run_time_resample(ctx, in, nt_in, ntrace, t0_in, dt_in, out, nt_out, t0_out, dt_out, flags);
     return 0;
     API_END(1)
 }

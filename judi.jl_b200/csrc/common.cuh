@@ -103,11 +103,15 @@ struct judi_ctx {
     long long launches = 0;
     // stencil timing (CUDA events on `stream`)
     int timing = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    struct Timed { cudaEvent_t e0, e1; int kind; };
+    std::vector<Timed> pending;
     std::vector<cudaEvent_t> free_events;
     double stencil_ms = 0;
     long long stencil_launches = 0;
     double stencil_points = 0;
+    // the same, split by launch flavour (JUDI_KIND_*)
+    double kind_ms[JUDI_NUM_KINDS] = {0};
+    long long kind_launches[JUDI_NUM_KINDS] = {0};
     // options
     int opt_kernel3d = 1;       // 0 generic, 1 TMA z-marching
     int opt_zchunks = 0;        // 0 = auto

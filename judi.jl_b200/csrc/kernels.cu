@@ -480,7 +480,9 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     else step_ndim<2>(M, s);
     if (ctx->timing) {
         CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
-        ctx->pending.emplace_back(e0, e1);
+        int kind = s.born ? JUDI_KIND_BORN : s.f.grad ? JUDI_KIND_IC : s.f.snap[0] ? JUDI_KIND_SAVE
+                                                     : JUDI_KIND_PLAIN;
+        ctx->pending.push_back({e0, e1, kind});
         ctx->stencil_launches++;
         ctx->stencil_points += (double)M->N[0] * M->N[1] * M->N[2] * (s.born ? 2 : 1);
         if (ctx->pending.size() >= 4096) ctx->flush_timing();

@@ -39,10 +39,12 @@ void judi_ctx::flush_timing()
     CUDA_CHECK(cudaStreamSynchronize(stream));
     for (auto &pr : pending) {
         float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
         stencil_ms += ms;
-        free_events.push_back(pr.first);
-        free_events.push_back(pr.second);
+        kind_ms[pr.kind] += ms;
+        kind_launches[pr.kind]++;
+        free_events.push_back(pr.e0);
+        free_events.push_back(pr.e1);
     }
     pending.clear();
 }

@@ -499,6 +499,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     judi_ctx *ctx = M->ctx;
     bool dev = flags & JUDI_DATA_ON_DEVICE;
     bool accumulate = flags & JUDI_GRAD_ACCUMULATE;
+    bool dev_out = dev || (flags & JUDI_OUT_ON_DEVICE);
     JUDI_REQUIRE(nt >= 3, "need at least 3 time samples");
     JUDI_REQUIRE(o->t_sub >= 1, "t_sub must be >= 1");
     JUDI_REQUIRE(!(o->nlind && !o->born_fwd), "nlind requires born_fwd");
@@ -740,11 +741,11 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     }
 
     // ---- outputs -----------------------------------------------------------------------------
-    region_output(M, reg, grad.p, grad_out, dev, accumulate);
-    if (illum_u) region_output(M, reg, Iu.p, illum_u, dev, false);
-    if (illum_v) region_output(M, reg, Iv.p, illum_v, dev, false);
+    region_output(M, reg, grad.p, grad_out, dev_out, accumulate);
+    if (illum_u) region_output(M, reg, Iu.p, illum_u, dev_out, false);
+    if (illum_v) region_output(M, reg, Iv.p, illum_v, dev_out, false);
     if (f_out) {
-        if (dev) {
+        if (dev_out) {
             // device scalar: keep the reduction on the GPU side of the boundary
             float fv = (float)fval, prev = 0.f;
             if (accumulate) {

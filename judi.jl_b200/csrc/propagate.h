@@ -74,3 +74,9 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                    int nrec, const float *rec_coords, const float *recin, const judi_jopts *o,
                    judi_misfit_fn misfit, void *user, float *f_out, float *grad_out,
                    float *illum_u, float *illum_v, int flags);
+
+// hostops.cu
+void run_remove_padding(const judi_model *M, const float *padded, int true_adjoint, float *out,
+                        int flags);
+void run_time_resample(judi_ctx *ctx, const float *in, int nt_in, int np, float t0_in, float dt_in,
+                       float *out, int nt_out, float t0_out, float dt_out, int flags);

@@ -163,6 +163,16 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
         fbuf = f_out
         if illum:
             Iu, Iv = illum_out
+    elif is_device_tensor(grad_out):
+        # host traces, outputs summed in HBM (one copy back after the reduction over shots/ranks)
+        q, nt, nsrc = _traces(wavelet)
+        d, ntd, nrec = _traces(recin)
+        g, fbuf = grad_out, f_out
+        assert fbuf is None or is_device_tensor(fbuf)
+        dev = True
+        flags |= L.OUT_ON_DEVICE
+        if illum:
+            Iu, Iv = illum_out
     else:
         q, nt, nsrc = _traces(wavelet)
         d, ntd, nrec = _traces(recin)

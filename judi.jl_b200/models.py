@@ -40,7 +40,13 @@ class Context(object):
         ms, n, pts = ctypes.c_double(0), ctypes.c_longlong(0), ctypes.c_double(0)
         L.check(L.lib().judi_ctx_stencil_stats(self.h, ctypes.byref(ms), ctypes.byref(n),
                                                ctypes.byref(pts)))
-        return {"ms": ms.value, "launches": n.value, "points": pts.value}
+        out = {"ms": ms.value, "launches": n.value, "points": pts.value, "kinds": {}}
+        for kind, name in enumerate(("plain", "save", "ic", "born")):
+            L.check(L.lib().judi_ctx_stencil_stats_kind(self.h, kind, ctypes.byref(ms),
+                                                        ctypes.byref(n)))
+            if n.value:
+                out["kinds"][name] = {"ms": ms.value, "launches": n.value}
+        return out
 
     def reset_stats(self):
         L.check(L.lib().judi_ctx_reset_stats(self.h))

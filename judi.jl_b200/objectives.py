@@ -110,6 +110,9 @@ def multi_src_fg(model, shots, dm=None, lin=False, nlind=False, misfit=None, red
     rk = dist.get_rank() if dist else 0
     if dm is not None:
         model.set_dm(dm)
+    if getattr(model, "h", None) is not None and "grad_out" not in options:
+        return _multi_src_fg_hbm(model, shots, shot_partition(len(shots), ws, rk), lin, nlind,
+                                 misfit, reduce, sum_padding, options)
     f, g = 0.0, None
     for i in shot_partition(len(shots), ws, rk):
         sc, q, rc, dobs = shots[i]
@@ -122,6 +125,52 @@ def multi_src_fg(model, shots, dm=None, lin=False, nlind=False, misfit=None, red
     if reduce:
         f, g = reduce_fg(f, g)
     return np.float32(f), remove_padding(g, model.padsizes, true_adjoint=sum_padding)
+
+
+_hbm_acc = {}
+
+
+def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_padding, options):
+    """The production path: every shot of this rank adds its gradient and objective
+    to one accumulator in HBM (`JUDI_OUT_ON_DEVICE | JUDI_GRAD_ACCUMULATE`), the ranks are summed
+    by ONE all-reduce of prod(n)+1 floats over NCCL, and the result crosses PCIe once, already
+    cropped to the physical grid.  The returned gradient is a view of a reused page-locked
+    staging buffer: it is valid until the next call (copy it to keep it)."""
+    import torch
+    from . import interface
+    dist = _dist()
+    n = int(np.prod(model.shape_pml))
+    dev = torch.device("cuda", model.ctx.device)
+    key = (model.ctx.device, n)
+    if key not in _hbm_acc:
+        _hbm_acc.clear()
+        _hbm_acc[key] = (torch.zeros(n + 1, dtype=torch.float32, device=dev),
+                         torch.zeros(n + 1, dtype=torch.float32).pin_memory())
+    red, host = _hbm_acc[key]
+    stream = torch.cuda.ExternalStream(model.ctx.stream, device=dev)
+    nccl = reduce and dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+    with torch.cuda.stream(stream):
+        red.zero_()
+        for i in mine:
+            sc, q, rc, dobs = shots[i]
+            interface.J_adjoint(model, sc, q, rc, dobs, return_obj=True, born_fwd=lin, nlind=nlind,
+                                misfit=misfit, grad_out=red[:n], f_out=red[n:], accumulate=True,
+                                **options)
+        if nccl:
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        if nccl or not (reduce and dist is not None and dist.get_world_size() > 1):
+            # crop (or fold the pad) on the device: only prod(n_physical)+1 floats cross PCIe
+            from .time_modeling import remove_padding as remove_padding_device
+            nphys = int(np.prod(model.shape))
+            g = host[:nphys].numpy().reshape(tuple(model.shape)[::-1]).T
+            stream.synchronize()
+            remove_padding_device(red[:n], model, true_adjoint=sum_padding, out=g)
+            return np.float32(red[n].item()), g
+        host.copy_(red, non_blocking=True)      # non-NCCL process group: reduce on the host
+        stream.synchronize()
+        dist.all_reduce(host, op=dist.ReduceOp.SUM)
+    g = host[:n].numpy().reshape(tuple(model.shape_pml)[::-1]).T
+    return np.float32(host[n].item()), remove_padding(g, model.padsizes, true_adjoint=sum_padding)
 
 
 def fwi_objective(model, shots, **options):

@@ -1,0 +1,225 @@
+"""Mirror of JUDI's per-shot driver above the propagator calls
+(src/TimeModeling/Modeling/time_modeling_serial.jl:9-51 `_time_modeling`,
+src/TimeModeling/Modeling/python_interface.jl:30-198 `devito_interface`) with the steps that
+bracket every call executed by libjudi_b200 on the device:
+
+  time_resample                    src/TimeModeling/Utils/time_utilities.jl:32-48, 84
+  remove_padding                   src/TimeModeling/Utils/auxiliaryFunctions.jl:79-89
+  limit_model_to_receiver_area     src/TimeModeling/Utils/auxiliaryFunctions.jl:129-173
+
+`Geometry` / `Options` carry only the fields this path reads (Geometry: xloc/yloc/zloc, dt, nt,
+t0 -- GeometryStructure.jl; Options: JUDIOptions fields of OptionsStructure.jl that reach the
+propagators).
+"""
+import ctypes
+import numpy as np
+
+from . import _lib as L
+from . import interface
+from .models import Model, get_context, is_device_tensor
+
+
+class Geometry(object):
+    """One source or receiver geometry (one shot): coordinates in metres and the time axis
+    `t0:dt:t` in ms (GeometryStructure.jl `GeometryIC`, single-source view)."""
+
+    def __init__(self, xloc, yloc, zloc, dt, t, t0=0.0):
+        self.xloc = np.atleast_1d(np.asarray(xloc, dtype=np.float32))
+        self.zloc = np.atleast_1d(np.asarray(zloc, dtype=np.float32))
+        self.yloc = None if yloc is None else np.atleast_1d(np.asarray(yloc, dtype=np.float32))
+        self.dt, self.t, self.t0 = np.float32(dt), np.float32(t), np.float32(t0)
+        self.nt = int(np.floor((self.t - self.t0) / self.dt)) + 1
+
+    @property
+    def taxis(self):
+        return (self.t0, self.dt, self.nt)
+
+    def coords(self, ndim):
+        """setup_grid (auxiliaryFunctions.jl:316-326): hcat(x[,y],z); 2-D models drop y."""
+        if ndim == 3:
+            return np.stack([self.xloc, self.yloc, self.zloc], axis=1).astype(np.float32)
+        return np.stack([self.xloc, self.zloc], axis=1).astype(np.float32)
+
+
+class Options(object):
+    """The JUDIOptions fields that reach this path (OptionsStructure.jl:7-60), same defaults."""
+
+    def __init__(self, space_order=8, free_surface=False, limit_m=False, buffer_size=1000.0,
+                 optimal_checkpointing=False, subsampling_factor=1, sum_padding=False,
+                 dt_comp=None, IC="as", f0=0.015, snapshot_region="padded", nbl=40):
+        self.space_order = space_order
+        self.free_surface = free_surface
+        self.limit_m = limit_m
+        self.buffer_size = buffer_size
+        self.optimal_checkpointing = optimal_checkpointing
+        self.subsampling_factor = subsampling_factor
+        self.sum_padding = sum_padding
+        self.dt_comp = dt_comp
+        self.IC = IC
+        self.f0 = f0
+        self.snapshot_region = snapshot_region
+        self.nbl = nbl
+
+
+# ---- time_resample ---------------------------------------------------------------------------
+def _resampled_length(t_in, t_new):
+    t0i, dti, nti = np.float32(t_in[0]), np.float32(t_in[1]), int(t_in[2])
+    t0n, dtn, ntn = np.float32(t_new[0]), np.float32(t_new[1]), int(t_new[2])
+    if dtn == dti:
+        return nti - int(np.trunc(np.float32(t0n - t0i) / dtn))
+    if np.fmod(dtn, dti) == 0:
+        rate = int(np.trunc(dtn / dti))
+        return (nti + rate - 1) // rate - int(np.trunc(np.float32(t0n - t0i) / dtn))
+    return ntn
+
+
+def time_resample(data, t_in, t_new, out=None, context=None):
+    """time_resample(data, t_in::StepRangeLen, t_new::StepRangeLen) (time_utilities.jl:32-48).
+
+    `data`: (nt_in, ntrace) host array, or a torch CUDA tensor given time fastest
+    (contiguous (ntrace, nt_in)); `t_in` / `t_new`: (first, step, length).  Returns the
+    resampled traces in the same convention (device in -> device out)."""
+    ctx = context or get_context()
+    nt_out = _resampled_length(t_in, t_new)
+    if is_device_tensor(data):
+        import torch
+        assert data.is_contiguous() and data.dim() == 2
+        ntr, nt_in = int(data.shape[0]), int(data.shape[1])
+        res = out if out is not None else torch.empty((ntr, nt_out), dtype=torch.float32,
+                                                      device=data.device)
+        flags = L.DATA_ON_DEVICE | L.OUT_ON_DEVICE
+        pin, pout = data.data_ptr(), res.data_ptr()
+    else:
+        a = np.asarray(data, dtype=np.float32)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        a = np.asfortranarray(a)
+        nt_in, ntr = a.shape
+        res = np.zeros((nt_out, ntr), dtype=np.float32, order="F")
+        flags = 0
+        pin, pout = a.ctypes.data, res.ctypes.data
+    assert nt_in == int(t_in[2]), "data length does not match its time axis"
+    L.check(L.lib().judi_time_resample(ctx.h, pin, nt_in, ntr, float(t_in[0]), float(t_in[1]),
+                                       pout, nt_out, float(t_new[0]), float(t_new[1]), flags))
+    return res
+
+
+def time_resample_to_dt(data, geometry, dt_new, context=None):
+    """time_resample(data, G_in, dt_new) (time_utilities.jl:15-18): same start and end time."""
+    t0, t = geometry.t0, np.float32(geometry.t0 + geometry.dt * (geometry.nt - 1))
+    n_new = int(np.floor(np.float32(t - t0) / np.float32(dt_new))) + 1
+    return time_resample(data, geometry.taxis, (t0, np.float32(dt_new), n_new), context=context)
+
+
+def time_resample_to_geometry(data, dt_in, geometry, context=None):
+    """time_resample(data, dt_in, G_out) (time_utilities.jl:66-69)."""
+    nt_in = data.shape[1] if is_device_tensor(data) else np.asarray(data).shape[0]
+    return time_resample(data, (np.float32(0), np.float32(dt_in), nt_in), geometry.taxis,
+                         context=context)
+
+
+# ---- remove_padding --------------------------------------------------------------------------
+def remove_padding(g, model, true_adjoint=False, out=None):
+    """remove_padding(gradient, modelPy.padsizes; true_adjoint) on the device.  `g` is a padded
+    grid array (F-ordered numpy (nx[,ny],nz)) or a torch CUDA tensor (x fastest); returns the
+    physical-grid array as F-ordered numpy, or fills the CUDA tensor `out`."""
+    flags = 0
+    if is_device_tensor(g):
+        flags |= L.DATA_ON_DEVICE
+        pin = g.data_ptr()
+    else:
+        g = np.asfortranarray(np.asarray(g, dtype=np.float32))
+        assert g.shape == model.shape_pml
+        pin = g.ctypes.data
+    if out is not None and is_device_tensor(out):
+        flags |= L.OUT_ON_DEVICE
+        res, pout = out, out.data_ptr()
+    else:
+        res = out if out is not None else np.zeros(model.shape, dtype=np.float32, order="F")
+        assert res.flags.f_contiguous and res.shape == model.shape
+        pout = res.ctypes.data
+    L.check(L.lib().judi_remove_padding(model.h, pin, int(bool(true_adjoint)), pout, flags))
+    return res
+
+
+# ---- limit_model_to_receiver_area ----------------------------------------------------------------
+def limit_model_to_receiver_area(src_geom, rec_geom, origin, spacing, shape, buffer, params,
+                                 pert=None):
+    """auxiliaryFunctions.jl:129-173: crop the model arrays to the x[,y] range of the sources and
+    receivers plus `buffer`; returns (origin, shape, params, pert)."""
+    ndim = len(shape)
+    axes = [("xloc",), ("yloc",)] if ndim == 3 else [("xloc",)]
+    inds = []
+    for d, (name,) in enumerate(axes):
+        o, h, n = np.float32(origin[d]), np.float32(spacing[d]), shape[d]
+        loc_r, loc_s = getattr(rec_geom, name), getattr(src_geom, name)
+        lo = min(loc_r.min(), loc_s.min())
+        hi = max(loc_r.max(), loc_s.max())
+        lo = max(o, np.float32(lo - np.float32(buffer)))
+        hi = min(np.float32(o + h * np.float32(n - 1)), np.float32(hi + np.float32(buffer)))
+        i0 = int(np.floor(np.float32(lo - o) / h)) + 1
+        i1 = int(np.floor(np.float32(hi - o) / h)) + 1
+        inds.append(slice(max(1, i0) - 1, i1))
+    inds.append(slice(0, shape[-1]))
+    inds = tuple(inds)
+    newp = {k: (np.asarray(v)[inds] if isinstance(v, np.ndarray) and v.ndim == ndim else v)
+            for k, v in params.items()}
+    new_shape = tuple(s.stop - s.start for s in inds)
+    new_origin = tuple(np.float32(origin[d]) + np.float32(spacing[d]) * np.float32(inds[d].start)
+                       for d in range(ndim))
+    newpert = None if pert is None else np.asarray(pert).reshape(shape)[inds]
+    return new_origin, new_shape, newp, newpert
+
+
+# ---- the per-shot driver ---------------------------------------------------------------------
+def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, rec_data, dm, op,
+                  options=None, fw=True, illum=False, context=None):
+    """_time_modeling (time_modeling_serial.jl:9-51) for one source experiment.
+
+    `params`: dict of model arrays / scalars (m, rho, epsilon, delta, theta, phi);
+    `op` in {"forward", "adjoint", "born", "adjoint_born"} as in the reference.
+    Returns the shot record resampled to the receiver geometry (nt_rec, nrec), or the gradient
+    on the (full, un-limited) physical grid.
+    """
+    o = options or Options()
+    ndim = len(shape)
+    if op == "born" and (dm is None or not np.any(np.asarray(dm))):
+        # time_modeling_serial.jl:22-24: J*0 returns zeros without propagating
+        return np.zeros((rec_geom.nt, rec_geom.xloc.size), dtype=np.float32, order="F")
+    full_shape, full_origin = tuple(shape), tuple(origin)
+    if o.limit_m:
+        origin, shape, params, dm = limit_model_to_receiver_area(
+            src_geom, rec_geom, origin, spacing, shape, o.buffer_size, params, pert=dm)
+    kw = dict(params)
+    if dm is not None:
+        kw["dm"] = np.asarray(dm, dtype=np.float32).reshape(shape)
+    model = Model(origin, spacing, shape, space_order=o.space_order, nbl=o.nbl,
+                  fs=o.free_surface, dt=o.dt_comp, context=context, **kw)
+    dt_comp = np.float32(model.critical_dt)
+    q_in = time_resample_to_dt(src_data, src_geom, dt_comp, context=model.ctx)
+    sc, rc = src_geom.coords(ndim), rec_geom.coords(ndim)
+    if op in ("forward", "adjoint") and rec_data is None:
+        rec, _ = interface.forward_rec(model, sc, q_in, rc, f0=o.f0, illum=illum,
+                                       fw=(op == "forward") == fw)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+    if op == "born":
+        rec, _ = interface.born_rec(model, sc, q_in, rc, ic=o.IC, f0=o.f0, illum=illum)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+    if op == "adjoint_born":
+        d_in = time_resample_to_dt(rec_data, rec_geom, dt_comp, context=model.ctx)
+        nt = min(q_in.shape[0], d_in.shape[0])
+        g, _, _ = interface.J_adjoint(model, sc, q_in[:nt], rc, d_in[:nt], is_residual=True,
+                                      t_sub=o.subsampling_factor,
+                                      checkpointing=o.optimal_checkpointing, ic=o.IC, f0=o.f0,
+                                      snapshot_region=o.snapshot_region)
+        g = remove_padding(g, model, true_adjoint=o.sum_padding)
+        if o.limit_m and tuple(shape) != full_shape:
+            # the gradient of a limited model is embedded in the full grid (PhysicalParameter
+            # arithmetic with origins, ModelStructure.jl:186-240)
+            full = np.zeros(full_shape, dtype=np.float32, order="F")
+            start = [int(round(float((origin[d] - full_origin[d]) / spacing[d])))
+                     for d in range(ndim)]
+            full[tuple(slice(s, s + n) for s, n in zip(start, shape))] = g
+            return full
+        return g
+    raise ValueError("unknown operator %r" % (op,))

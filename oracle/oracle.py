@@ -14,6 +14,8 @@ The classes/functions below restate, with the same names and argument meaning, t
   Loss                 sensitivity.py:236-276
   remove_padding / pad_array  src/TimeModeling/Utils/auxiliaryFunctions.jl:52-89
   ricker_wavelet       src/TimeModeling/Utils/auxiliaryFunctions.jl:205-213
+  time_resample        src/TimeModeling/Utils/time_utilities.jl:32-48, 84
+  limit_model_to_receiver_area  src/TimeModeling/Utils/auxiliaryFunctions.jl:129-173
 
 Array conventions are pysource's: model arrays have shape (nx[,ny],nz); coordinates are
 (npoint, ndim) in metres; wavelets / shot records are (nt, ntrace).
@@ -119,6 +121,75 @@ def remove_padding(g, nb, true_adjoint=False):
             g[sel(N - nbr - 1)] += g[sel(slice(N - nbr, N))].sum(axis=dim)
     crop = tuple(slice(nbl, n - nbr) for (nbl, nbr), n in zip(nb, g.shape))
     return g[crop]
+
+
+def _steprange(t0, dt, n):
+    """Elements of a Julia Float32 StepRangeLen (computed in double, rounded once)."""
+    return (np.float64(np.float32(t0)) + np.arange(n, dtype=np.float64) *
+            np.float64(np.float32(dt))).astype(np.float32)
+
+
+def time_axis(dt, t):
+    """`0:dt:(dt*ceil(t/dt))` (time_utilities.jl:50-51) as (t0, dt, nt)."""
+    dt = np.float32(dt)
+    return (np.float32(0), dt, int(np.ceil(np.float32(t) / dt)) + 1)
+
+
+def time_resample(data, t_in, t_new):
+    """time_utilities.jl:32-48: `data` (nt_in, ntrace) sampled on the range t_in = (t0, dt, nt)
+    -> samples on t_new.  Equal steps: shifted view; integer ratio: decimation; else
+    `sinc.((Up .- S') ./ dt) * Y` in Float32 (:84)."""
+    data = np.asarray(data, dtype=np.float32)
+    if data.ndim == 1:
+        data = data.reshape(-1, 1)
+    t0i, dti, nti = np.float32(t_in[0]), np.float32(t_in[1]), int(t_in[2])
+    t0n, dtn, ntn = np.float32(t_new[0]), np.float32(t_new[1]), int(t_new[2])
+    assert data.shape[0] == nti
+    if dtn == dti:
+        idx0 = int(np.trunc(np.float32(t0n - t0i) / dtn))
+        return data[idx0:, :]
+    if np.fmod(dtn, dti) == 0:
+        rate = int(np.trunc(dtn / dti))
+        idx0 = int(np.trunc(np.float32(t0n - t0i) / dtn))
+        return data[::rate, :][idx0:, :]
+    S = _steprange(t0i, dti, nti)
+    Up = _steprange(t0n, dtn, ntn)
+    x = ((Up[:, None] - S[None, :]) / dti).astype(np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        # Julia: sinc(x) = sinpi(x) / (pi * x); sinpi is exact in the argument reduction
+        red = (x.astype(np.float64) - 2.0 * np.round(x.astype(np.float64) / 2.0))
+        sp = np.sin(np.pi * red).astype(np.float32)
+        k = np.where(x == 0, np.float32(1), sp / (np.float32(np.pi) * x)).astype(np.float32)
+    return (k @ data).astype(np.float32)
+
+
+def limit_model_to_receiver_area(src_coords, rec_coords, origin, spacing, shape, buffer, params,
+                                 pert=None):
+    """auxiliaryFunctions.jl:129-173: restrict the model arrays in `params` (dict of arrays or
+    scalars, shape `shape`) to the x[,y] range covered by sources and receivers plus `buffer`
+    metres.  Returns (new_origin, new_shape, new_params, new_pert, index slices)."""
+    ndim = len(shape)
+    src = np.asarray(src_coords, dtype=np.float32).reshape(-1, ndim)
+    rec = np.asarray(rec_coords, dtype=np.float32).reshape(-1, ndim)
+    inds = []
+    for d in range(ndim - 1):
+        o, h, n = np.float32(origin[d]), np.float32(spacing[d]), shape[d]
+        lo = min(rec[:, d].min(), src[:, d].min())
+        hi = max(rec[:, d].max(), src[:, d].max())
+        lo = max(o, np.float32(lo - np.float32(buffer)))
+        hi = min(np.float32(o + h * np.float32(n - 1)), np.float32(hi + np.float32(buffer)))
+        i0 = int(np.floor(np.float32(lo - o) / h)) + 1       # Julia 1-based, `÷` on floats
+        i1 = int(np.floor(np.float32(hi - o) / h)) + 1
+        inds.append(slice(max(1, i0) - 1, i1))
+    inds.append(slice(0, shape[-1]))
+    inds = tuple(inds)
+    newp = {k: (np.asarray(v)[inds] if isinstance(v, np.ndarray) and v.ndim == ndim else v)
+            for k, v in params.items()}
+    new_shape = tuple(s.stop - s.start for s in inds)
+    new_origin = tuple(np.float32(origin[d]) + np.float32(spacing[d]) * np.float32(inds[d].start)
+                       for d in range(ndim))
+    newpert = None if pert is None else np.asarray(pert).reshape(shape)[inds]
+    return new_origin, new_shape, newp, newpert, inds
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,215 @@
+"""The steps around every propagator call: time_resample
+(time_utilities.jl:32-48,84), remove_padding (auxiliaryFunctions.jl:79-89),
+limit_model_to_receiver_area (auxiliaryFunctions.jl:129-173) and the per-shot driver
+(time_modeling_serial.jl:9-51).  CPU tests pin the oracle restatements on known answers; GPU tests
+compare the device implementations (through the C-ABI) with them."""
+import numpy as np
+import pytest
+
+from conftest import model_args, geometry, rel_l2
+from oracle import oracle as O
+
+
+# ---- oracle restatements (CPU) -------------------------------------------------------------------
+def test_time_axis_and_resample_cases():
+    """time_utilities.jl:34-41: equal dt -> shifted view; integer ratio -> decimation."""
+    assert O.time_axis(4.0, 1000.0) == (np.float32(0), np.float32(4), 251)
+    assert O.time_axis(1.5, 10.0)[2] == 8                      # 0:1.5:(1.5*ceil(10/1.5))
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal((101, 4)).astype(np.float32)
+    assert np.array_equal(O.time_resample(d, (0., 2., 101), (0., 2., 101)), d)
+    assert np.array_equal(O.time_resample(d, (0., 2., 101), (8., 2., 97)), d[4:])
+    assert np.array_equal(O.time_resample(d, (0., 2., 101), (0., 4., 51)), d[::2])
+    assert np.array_equal(O.time_resample(d, (0., 2., 101), (8., 4., 49)), d[::2][2:])
+
+
+def test_sinc_resample_reproduces_band_limited_signal_and_nodes():
+    """time_utilities.jl:84: the sinc matrix is the identity on coinciding samples and
+    interpolates a band-limited signal (well below Nyquist) to ~1e-3 away from the ends."""
+    dt_in, nt_in = np.float32(4.0), 501
+    t_in = np.arange(nt_in) * 4.0
+    f = 0.008                                                   # kHz, Nyquist is 0.125
+    sig = (np.exp(-((t_in - 1000.) / 300.) ** 2) * np.sin(2 * np.pi * f * t_in)).astype(np.float32)
+    dt_new, nt_new = np.float32(1.733), int(np.floor(2000. / 1.733)) + 1
+    out = O.time_resample(sig, (0., dt_in, nt_in), (0., dt_new, nt_new))
+    t_new = np.arange(nt_new) * np.float64(dt_new)
+    ref = np.exp(-((t_new - 1000.) / 300.) ** 2) * np.sin(2 * np.pi * f * t_new)
+    assert out.shape == (nt_new, 1)
+    assert np.abs(out[:, 0] - ref).max() < 2e-3
+    # down then up returns the original samples where the axes coincide (dt ratio 3/2)
+    back = O.time_resample(sig, (0., 4., nt_in), (0., 6., 334))
+    assert np.allclose(back[::2, 0], sig[::3][:167], atol=2e-6)
+
+
+def test_limit_model_matches_julia_index_arithmetic():
+    """auxiliaryFunctions.jl:143-157 on a 2-D and a 3-D model (1-based `÷` arithmetic)."""
+    shape, spacing, origin = (101, 51), (10., 10.), (0., 0.)
+    m = np.arange(101 * 51, dtype=np.float32).reshape(shape)
+    src = np.array([[400., 20.]], dtype=np.float32)
+    rec = np.stack([np.linspace(250., 655., 30), np.full(30, 20.)], axis=1).astype(np.float32)
+    o, n, p, pert, inds = O.limit_model_to_receiver_area(src, rec, origin, spacing, shape, 100.,
+                                                         {"m": m, "rho": 1.0}, pert=m.ravel())
+    assert inds[0] == slice(15, 76) and inds[1] == slice(0, 51)   # (250-100)/10 .. (655+100)÷10
+    assert n == (61, 51) and o == (np.float32(150.), np.float32(0.))
+    assert np.array_equal(p["m"], m[15:76]) and p["rho"] == 1.0
+    assert np.array_equal(pert, m[15:76])
+    # the buffer is clipped at the model edges
+    o, n, p, _, inds = O.limit_model_to_receiver_area(src, rec, origin, spacing, shape, 5000.,
+                                                      {"m": m})
+    assert n == shape and o == (np.float32(0.), np.float32(0.))
+    shape3 = (41, 31, 21)
+    m3 = np.zeros(shape3, np.float32)
+    src3 = np.array([[200., 100., 10.]], dtype=np.float32)
+    rec3 = np.array([[120., 60., 10.], [260., 180., 10.]], dtype=np.float32)
+    o, n, p, _, inds = O.limit_model_to_receiver_area(src3, rec3, (0., 0., 0.), (10.,) * 3, shape3,
+                                                      30., {"m": m3})
+    assert inds == (slice(9, 30), slice(3, 22), slice(0, 21))
+    assert o == (np.float32(90.), np.float32(30.), np.float32(0.))
+
+
+# ---- device implementations (GPU) ----------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["equal", "shift", "decimate", "sinc_up", "sinc_down", "long"])
+def test_time_resample_device_matches_oracle(case):
+    import judi_jl_b200 as J
+    rng = np.random.default_rng(7)
+    cfg = {"equal": ((0., 2., 301), (0., 2., 301), 5),
+           "shift": ((0., 2., 301), (10., 2., 296), 5),
+           "decimate": ((0., 1., 1201), (4., 4., 300), 3),
+           "sinc_up": ((0., 4., 251), (0., 1.733, 578), 17),
+           "sinc_down": ((0., 1.921, 1042), (0., 4., 501), 9),
+           "long": ((0., 0.75, 2700), (0., 2., 1013), 2)}[case]
+    t_in, t_new, ntr = cfg
+    d = rng.standard_normal((t_in[2], ntr)).astype(np.float32)
+    ref = O.time_resample(d, t_in, t_new)
+    out = J.time_resample(d, t_in, t_new)
+    assert out.shape == ref.shape
+    if case in ("equal", "shift", "decimate"):
+        assert np.array_equal(out, ref)                       # pure data movement: bit-exact
+    else:
+        assert rel_l2(out, ref) < 1e-5                        # fp32 sums in a different order
+
+
+@pytest.mark.gpu
+def test_time_resample_device_tensor_path():
+    import torch
+    import judi_jl_b200 as J
+    rng = np.random.default_rng(8)
+    d = rng.standard_normal((400, 33)).astype(np.float32)
+    t_in, t_new = (0., 3., 400), (0., 1.3, 921)
+    ref = J.time_resample(d, t_in, t_new)
+    dd = torch.from_numpy(np.ascontiguousarray(d.T)).cuda()
+    out = J.time_resample(dd, t_in, t_new)
+    assert out.is_cuda and tuple(out.shape) == (33, 921)
+    assert np.array_equal(out.cpu().numpy().T, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("fold", [False, True])
+def test_remove_padding_device_matches_oracle(ndim, fold):
+    import torch
+    import judi_jl_b200 as J
+    args = model_args("iso", ndim, 8, with_dm=False, fs=(ndim == 2 and fold))
+    gm = J.Model(**args)
+    rng = np.random.default_rng(5)
+    g = np.asfortranarray(rng.standard_normal(gm.shape_pml).astype(np.float32))
+    ref = O.remove_padding(g.astype(np.float64), gm.padsizes, true_adjoint=fold)
+    out = J.time_modeling.remove_padding(g, gm, true_adjoint=fold)
+    assert out.shape == args["shape"]
+    if not fold:
+        assert np.array_equal(out, ref.astype(np.float32))    # crop: bit-exact
+    else:
+        assert rel_l2(out, ref) < 1e-6
+        # adjoint of edge padding: <pad(x), g> == <x, remove_padding(g, true_adjoint)>
+        x = rng.standard_normal(args["shape"])
+        a = np.vdot(np.pad(x, gm.padsizes, mode="edge"), g.astype(np.float64))
+        assert abs(a - np.vdot(x, out.astype(np.float64))) < 1e-5 * abs(a)
+    gd = torch.from_numpy(np.ascontiguousarray(g.transpose(*range(ndim - 1, -1, -1)))).cuda()
+    od = torch.empty(args["shape"][::-1], dtype=torch.float32, device="cuda")
+    J.time_modeling.remove_padding(gd, gm, true_adjoint=fold, out=od)
+    assert np.array_equal(od.cpu().numpy().transpose(*range(ndim - 1, -1, -1)), out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_time_modeling_driver_with_resampling_and_limit_m(ndim):
+    """_time_modeling (time_modeling_serial.jl:9-51): limit_m crop, wavelet resampled to dt_comp,
+    shot record resampled to the receiver sampling, gradient cropped and embedded."""
+    import judi_jl_b200 as J
+    n = (81, 61) if ndim == 2 else (41, 37, 29)
+    args = model_args("iso", ndim, 8, with_dm=True, n=n, nbl=10)
+    spacing, shape = args["spacing"], args["shape"]
+    ex = (shape[0] - 1) * spacing[0]
+    if ndim == 2:
+        sg = J.Geometry([0.5 * ex + 3.], None, [22.], dt=2.0, t=600.)
+        rg = J.Geometry(np.linspace(0.3 * ex, 0.7 * ex, 21), None, np.full(21, 31.7), dt=3.0, t=600.)
+    else:
+        ey = (shape[1] - 1) * spacing[1]
+        sg = J.Geometry([0.5 * ex + 3.], [0.5 * ey], [22.], dt=2.0, t=300.)
+        xr, yr = np.meshgrid(np.linspace(0.3 * ex, 0.7 * ex, 5), np.linspace(0.4 * ey, 0.6 * ey, 3),
+                             indexing="ij")
+        rg = J.Geometry(xr.ravel(), yr.ravel(), np.full(xr.size, 31.7), dt=3.0, t=300.)
+    q = O.ricker_wavelet(sg.t, sg.dt, 0.02)
+    opt = J.Options(space_order=8, nbl=10, limit_m=True, buffer_size=60.)
+    params = {"m": args["m"]}
+    d = J.time_modeling.time_modeling(args["origin"], spacing, shape, params, sg, q, rg, None, None,
+                                      "forward", opt)
+    # the same composition with the oracle pieces
+    sc, rc = sg.coords(ndim), rg.coords(ndim)
+    o2, n2, p2, dm2, inds = O.limit_model_to_receiver_area(sc, rc, args["origin"], spacing, shape, 60.,
+                                                           params, pert=args["dm"])
+    assert n2[0] < shape[0]
+    om = O.Model(o2, spacing, n2, space_order=8, nbl=10, m=p2["m"], dm=dm2, precision="f32")
+    dtc = om.critical_dt
+    nq = int(np.floor(np.float32(sg.t) / dtc)) + 1
+    qi = O.time_resample(q, sg.taxis, (0., dtc, nq))
+    do, _ = O.forward_rec(om, sc, qi, rc)
+    dref = O.time_resample(do, (0., dtc, do.shape[0]), rg.taxis)
+    assert d.shape == (rg.nt, rc.shape[0]) == dref.shape
+    assert rel_l2(d, dref) < 1e-4
+    # Born through the driver
+    dl = J.time_modeling.time_modeling(args["origin"], spacing, shape, params, sg, q, rg, None,
+                                       args["dm"], "born", opt)
+    dlo, _ = O.born_rec(om, sc, qi, rc)
+    assert rel_l2(dl, O.time_resample(dlo, (0., dtc, dlo.shape[0]), rg.taxis)) < 1e-4
+    assert not J.time_modeling.time_modeling(args["origin"], spacing, shape, params, sg, q, rg, None,
+                                             np.zeros(shape, np.float32), "born", opt).any()
+    # adjoint Jacobian: gradient on the full grid, zero outside the limited area
+    g = J.time_modeling.time_modeling(args["origin"], spacing, shape, params, sg, q, rg, dref, None,
+                                      "adjoint_born", opt)
+    di = O.time_resample(dref, rg.taxis, (0., dtc, nq))
+    nt = min(qi.shape[0], di.shape[0])
+    go, _, _ = O.J_adjoint(om, sc, qi[:nt], rc, di[:nt], is_residual=True)
+    gref = np.zeros(shape, np.float32)
+    gref[inds] = O.remove_padding(go, om.padsizes)
+    assert g.shape == shape
+    assert rel_l2(g, gref) < 1e-3
+
+
+@pytest.mark.gpu
+def test_fwi_objective_hbm_accumulation_matches_oracle_sum():
+    """multi_src_fg! (propagation.jl:93-107): shots summed in HBM, cropped on the device."""
+    import judi_jl_b200 as J
+    args = model_args("iso", 2, 8, with_dm=False, n=(61, 51), nbl=12)
+    gm = J.Model(**args)
+    om = O.Model(precision="f32", **args)
+    src0, rec = geometry(args)
+    dt = float(om.critical_dt)
+    q = O.ricker_wavelet(119 * dt, dt, 0.02)[:120]
+    shots, fs, gs = [], 0.0, 0.0
+    for i in range(3):
+        src = src0.copy()
+        src[0, 0] += 40.0 * (i - 1)
+        d, _ = O.forward_rec(om, src, q, rec)
+        dobs = (0.9 * d).astype(np.float32)
+        shots.append((src, q, rec, dobs))
+        f, g, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True)
+        fs += float(f)
+        gs = gs + g
+    for fold in (False, True):
+        f, g = J.objectives.fwi_objective(gm, shots, sum_padding=fold)
+        gref = O.remove_padding(gs, om.padsizes, true_adjoint=fold)
+        assert g.shape == args["shape"]
+        assert abs(float(f) - fs) <= 1e-4 * abs(fs)
+        assert rel_l2(g, gref) < 1e-3
