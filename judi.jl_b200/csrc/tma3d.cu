@@ -69,6 +69,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, in
         "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ float rcp_approx(float x)
 {
     float r;
@@ -106,7 +110,12 @@ struct TmaCfg {
         (size_t)NS * SLOT * 4 + (size_t)NP * 2 * PSLOT * 4 + (2 * NS + 2 * NP) * 8 + 128;
 };
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, bool FUSE, int NPW, bool ROT>
+// FUSE is a compile-time mask of what rides on the step, so that each flavour of launch carries
+// only its own instructions (the all-in-one fused instantiation executed 33% more instructions
+// than the plain one for a single extra store):
+enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16 };
+
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT>
 __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     acoustic3d_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP,
                    const __grid_constant__ CUtensorMap tmM, const TmaArgs a)
@@ -199,11 +208,12 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     for (int k = 0; k < NQ; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // damping along x and y for this thread's points: (dx + dy), z added per plane
-    float sxy[4] = {0.f, 0.f, 0.f, 0.f};
+    f2 sxy0 = pk1(0.f), sxy1 = pk1(0.f);
     if (act) {
         const float4 d4 = *(const float4 *)(a.dx + x);  // profile arrays are padded 8 past n[0]
         const float dyv = a.dy[y];
-        sxy[0] = d4.x + dyv; sxy[1] = d4.y + dyv; sxy[2] = d4.z + dyv; sxy[3] = d4.w + dyv;
+        sxy0 = add2(lo2(d4), pk1(dyv));
+        sxy1 = add2(hi2(d4), pk1(dyv));
     }
     const bool tile_interior = x0 >= a.dlo[0] && x0 + TX <= a.dhi[0] && y0 >= a.dlo[1] &&
                                y0 + TY <= a.dhi[1];
@@ -213,18 +223,18 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     // fused extras: everything that does not depend on z is decided once per thread; the region
     // offset advances by one region plane per output plane (no 64-bit index math in the loop)
     [[maybe_unused]] const Fuse &fz = a.f;
-    [[maybe_unused]] const bool f_snap = FUSE && fz.snap[0] != nullptr;
-    [[maybe_unused]] const bool f_grad = FUSE && fz.grad != nullptr;
-    [[maybe_unused]] const bool f_il = FUSE && fz.illum != nullptr;
-    [[maybe_unused]] const bool f_born = FUSE && a.qsrc != nullptr && act;
-    [[maybe_unused]] const bool f_xy = FUSE && act && (f_snap || f_grad || f_il) && y >= fz.reg.lo[1] &&
+    constexpr bool f_snap = (FUSE & F_SNAP) != 0, f_grad = (FUSE & F_GRAD) != 0;
+    constexpr bool f_il = (FUSE & F_ILLUM) != 0, f_dd = (FUSE & F_DDOUT) != 0;
+    constexpr bool f_reg = f_snap || f_grad || f_il;   // anything stored in the region layout
+    [[maybe_unused]] const bool f_born = (FUSE & F_QSRC) != 0 && act;
+    [[maybe_unused]] const bool f_xy = f_reg && act && y >= fz.reg.lo[1] &&
                                        y < fz.reg.hi[1] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0];
     [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && x >= fz.reg.lo[0] &&
                                         x + 3 < fz.reg.hi[0];
-    [[maybe_unused]] long long ri = FUSE ? fz.reg.at(x, y, z0) : 0;
-    [[maybe_unused]] const long long rstride = FUSE ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
-    [[maybe_unused]] const float gc = FUSE ? fz.gcoef * a.irho_c : 0.f;
-    [[maybe_unused]] const int rz0 = FUSE ? fz.reg.lo[2] : 0, rz1 = FUSE ? fz.reg.hi[2] : 0;
+    [[maybe_unused]] long long ri = f_reg ? fz.reg.at(x, y, z0) : 0;
+    [[maybe_unused]] const long long rstride = f_reg ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
+    [[maybe_unused]] const float gc = f_grad ? fz.gcoef * a.irho_c : 0.f;
+    [[maybe_unused]] const int rz0 = f_reg ? fz.reg.lo[2] : 0, rz1 = f_reg ? fz.reg.hi[2] : 0;
 
     // ROT: the z-queue is rotated at compile time (main loop unrolled by NQ, no register moves,
     // ~9x the code); !ROT: the queue is shifted by NQ-1 register moves per plane (compact code).
@@ -247,12 +257,19 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
             // that their latency hides behind the stencil arithmetic of this plane
             [[maybe_unused]] bool fin = false, fvec = false;
             [[maybe_unused]] float4 us4, g4, il4, qs4, dm4;
-            if (FUSE && jt >= 2 * R) {
+            if (FUSE != 0 && jt >= 2 * R) {
                 const int z = z0 + jt - 2 * R;
                 const bool zin = z >= rz0 && z < rz1;
                 fin = f_xy && zin;
                 fvec = f_vec && zin;
-                if (fvec) {
+                // the imaging condition streams the snapshot and the gradient through the consumer
+                // threads: pull the lines of plane z + 3 into L2 now so the loads below cost an
+                // L2 hit, not a DRAM round trip, when that plane comes up
+                if (f_grad && f_vec && z + 3 >= rz0 && z + 3 < rz1) {
+                    prefetch_l2(fz.usnap[0] + ri + 3 * rstride);
+                    prefetch_l2(fz.grad + ri + 3 * rstride);
+                }
+                if ((f_grad || f_il) && fvec) {
                     if (f_grad) {
                         us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
                         g4 = *(const float4 *)(fz.grad + ri);
@@ -270,51 +287,63 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 const int i = jt - 2 * R;  // output plane index inside the chunk
                 const int z = z0 + i;
                 const float *cen = ringU + sc * SLOT;
+                // All point-wise arithmetic is packed fp32x2 on the pairs (x, x+1), (x+2, x+3):
                 // z part (register queue), x part (row), y part (column): three accumulators
-                float lz[4], lx[4], ly[4];
-                {
-                    const float4 c = Q(R);
-                    lz[0] = cf.c0 * c.x; lz[1] = cf.c0 * c.y; lz[2] = cf.c0 * c.z; lz[3] = cf.c0 * c.w;
-                }
+                const float4 cq = Q(R);
+                const f2 uc0 = lo2(cq), uc1 = hi2(cq);
+                f2 lz0 = mul2s(cf.c0, uc0), lz1 = mul2s(cf.c0, uc1);
 #pragma unroll
                 for (int k = 1; k <= R; k++) {
                     const float4 p = Q(R + k), m_ = Q(R - k);
-                    lz[0] += cf.cz[k] * (p.x + m_.x); lz[1] += cf.cz[k] * (p.y + m_.y);
-                    lz[2] += cf.cz[k] * (p.z + m_.z); lz[3] += cf.cz[k] * (p.w + m_.w);
+                    lz0 = fma2s(cf.cz[k], add2(lo2(p), lo2(m_)), lz0);
+                    lz1 = fma2s(cf.cz[k], add2(hi2(p), hi2(m_)), lz1);
                 }
+                f2 lxp[2];
                 {
                     const float *crow = cen + sm_own - HR;
                     float w[4 + 2 * HR];
 #pragma unroll
                     for (int v = 0; v < 1 + 2 * (HR / 4); v++) {
                         if (v == HR / 4) {  // the centre vector is already in the queue
-                            const float4 c = Q(R);
-                            w[4 * v] = c.x; w[4 * v + 1] = c.y; w[4 * v + 2] = c.z; w[4 * v + 3] = c.w;
+                            w[4 * v] = cq.x; w[4 * v + 1] = cq.y; w[4 * v + 2] = cq.z; w[4 * v + 3] = cq.w;
                         } else {
                             const float4 t = *(const float4 *)(crow + 4 * v);
                             w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
                         }
                     }
+                    // even offsets keep the register pairs aligned (packed); odd ones straddle
+                    // two pairs and stay scalar
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        lx[e] = cf.cx[1] * (w[HR + e + 1] + w[HR + e - 1]);
+                    for (int h = 0; h < 2; h++) {
+                        const int b = HR + 2 * h;
+                        lxp[h].x = __fmul_rn(cf.cx[1], __fadd_rn(w[b + 1], w[b - 1]));
+                        lxp[h].y = __fmul_rn(cf.cx[1], __fadd_rn(w[b + 2], w[b]));
 #pragma unroll
-                        for (int k = 2; k <= R; k++) lx[e] += cf.cx[k] * (w[HR + e + k] + w[HR + e - k]);
+                        for (int k = 2; k <= R; k++) {
+                            if (k & 1) {
+                                lxp[h].x = __fmaf_rn(cf.cx[k], __fadd_rn(w[b + k], w[b - k]), lxp[h].x);
+                                lxp[h].y = __fmaf_rn(cf.cx[k], __fadd_rn(w[b + 1 + k], w[b + 1 - k]), lxp[h].y);
+                            } else {
+                                lxp[h] = fma2s(cf.cx[k], add2(pk(w[b + k], w[b + k + 1]),
+                                                             pk(w[b - k], w[b - k + 1])), lxp[h]);
+                            }
+                        }
                     }
                 }
+                f2 ly0, ly1;
                 {
                     const float *ccol = cen + sm_own;
                     {
                         const float4 p = *(const float4 *)(ccol + PX), m_ = *(const float4 *)(ccol - PX);
-                        ly[0] = cf.cy[1] * (p.x + m_.x); ly[1] = cf.cy[1] * (p.y + m_.y);
-                        ly[2] = cf.cy[1] * (p.z + m_.z); ly[3] = cf.cy[1] * (p.w + m_.w);
+                        ly0 = mul2s(cf.cy[1], add2(lo2(p), lo2(m_)));
+                        ly1 = mul2s(cf.cy[1], add2(hi2(p), hi2(m_)));
                     }
 #pragma unroll
                     for (int k = 2; k <= R; k++) {
                         const float4 p = *(const float4 *)(ccol + k * PX);
                         const float4 m_ = *(const float4 *)(ccol - k * PX);
-                        ly[0] += cf.cy[k] * (p.x + m_.x); ly[1] += cf.cy[k] * (p.y + m_.y);
-                        ly[2] += cf.cy[k] * (p.z + m_.z); ly[3] += cf.cy[k] * (p.w + m_.w);
+                        ly0 = fma2s(cf.cy[k], add2(lo2(p), lo2(m_)), ly0);
+                        ly1 = fma2s(cf.cy[k], add2(hi2(p), hi2(m_)), ly1);
                     }
                 }
                 // the centre plane is dead for this warp: hand its slot back to the producer
@@ -328,85 +357,89 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 const float4 m4 = *(const float4 *)(pt + PSLOT);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyP[sp]);
-                const float4 c4 = Q(R);
-                const float uc[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float upv[4] = {up4.x, up4.y, up4.z, up4.w};
-                const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-                float un[4];
-                [[maybe_unused]] float delta[4];
-                if (FUSE && f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
-                    lz[0] = __fmaf_rn(-dm4.x, qs4.x, lz[0]); lz[1] = __fmaf_rn(-dm4.y, qs4.y, lz[1]);
-                    lz[2] = __fmaf_rn(-dm4.z, qs4.z, lz[2]); lz[3] = __fmaf_rn(-dm4.w, qs4.w, lz[3]);
+                if (f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
+                    lz0.x = __fmaf_rn(-dm4.x, qs4.x, lz0.x); lz0.y = __fmaf_rn(-dm4.y, qs4.y, lz0.y);
+                    lz1.x = __fmaf_rn(-dm4.z, qs4.z, lz1.x); lz1.y = __fmaf_rn(-dm4.w, qs4.w, lz1.y);
                 }
+                // explicit rn operations: the plain and the fused instantiation must produce
+                // bit-identical wavefields (checkpoint recomputation relies on it)
+                const f2 lap0 = add2(add2(lz0, lxp[0]), ly0), lap1 = add2(add2(lz1, lxp[1]), ly1);
+                const f2 d10 = sub2(uc0, lo2(up4)), d11 = sub2(uc1, hi2(up4));
+                // u+ = (u + (u - u-)) + t * r with t the numerator and r the reciprocal of the
+                // denominator of the increment; written as ONE explicit fma so that ptxas cannot
+                // contract it in one instantiation and not in the other (it fuses mul.rn.f32x2 +
+                // add.rn.f32x2 when the product has no other use)
+                f2 t0, t1, r0, r1;
                 if (tile_interior && z >= a.dlo[2] && z < a.dhi[2]) {
-#pragma unroll
-                    // explicit rounding intrinsics: the plain and the fused instantiation must
-                    // produce bit-identical wavefields (checkpoint recomputation relies on it)
-                    for (int e = 0; e < 4; e++) {
-                        const float lap = __fadd_rn(__fadd_rn(lz[e], lx[e]), ly[e]);
-                        const float d1 = __fsub_rn(uc[e], upv[e]);
-                        delta[e] = __fmul_rn(lap, rcp_approx(mv[e]));
-                        un[e] = __fadd_rn(__fadd_rn(uc[e], d1), delta[e]);
-                    }
+                    t0 = lap0; t1 = lap1;
+                    r0 = pk(rcp_approx(m4.x), rcp_approx(m4.y));
+                    r1 = pk(rcp_approx(m4.z), rcp_approx(m4.w));
                 } else {
-                    const float szv = a.dz[z];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float lap = __fadd_rn(__fadd_rn(lz[e], lx[e]), ly[e]);
-                        const float s = __fmul_rn(__fadd_rn(sxy[e], szv), a.sdamp);
-                        const float d1 = __fsub_rn(uc[e], upv[e]);
-                        delta[e] = __fmul_rn(__fmaf_rn(-s, d1, lap), rcp_approx(__fadd_rn(mv[e], s)));
-                        un[e] = __fadd_rn(__fadd_rn(uc[e], d1), delta[e]);
-                    }
+                    // ns = -(dx + dy + dz) * dt / irho: the sign rides on the scalar (exact)
+                    const f2 szv = pk1(a.dz[z]);
+                    const f2 ns0 = mul2s(-a.sdamp, add2(sxy0, szv)), ns1 = mul2s(-a.sdamp, add2(sxy1, szv));
+                    const f2 den0 = sub2(lo2(m4), ns0), den1 = sub2(hi2(m4), ns1);
+                    t0 = fma2(ns0, d10, lap0); t1 = fma2(ns1, d11, lap1);
+                    r0 = pk(rcp_approx(den0.x), rcp_approx(den0.y));
+                    r1 = pk(rcp_approx(den1.x), rcp_approx(den1.y));
                 }
+                const f2 un0 = fma2(t0, r0, add2(uc0, d10)), un1 = fma2(t1, r1, add2(uc1, d11));
+                // delta = u+ - 2u + u- (imaging condition, Born source): fused variants only
+                [[maybe_unused]] f2 dl0, dl1;
+                if (f_grad || f_dd) { dl0 = mul2(t0, r0); dl1 = mul2(t1, r1); }
                 if (act) {
                     float *gout = a.up + goff;
-                    if (xfull) *(float4 *)gout = make_float4(un[0], un[1], un[2], un[3]);
+                    if (xfull) *(float4 *)gout = cat4(un0, un1);
                     else {
+                        const float un[4] = {un0.x, un0.y, un1.x, un1.y};
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                             if (x + e < g.n[0]) gout[e] = un[e];
                     }
-                    if (FUSE && a.dd_out) {
+                    if (f_dd) {
                         float *dout = a.dd_out + goff;
-                        if (xfull) *(float4 *)dout = make_float4(delta[0], delta[1], delta[2], delta[3]);
+                        if (xfull) *(float4 *)dout = cat4(dl0, dl1);
                         else {
+                            const float delta[4] = {dl0.x, dl0.y, dl1.x, dl1.y};
 #pragma unroll
                             for (int e = 0; e < 4; e++)
                                 if (x + e < g.n[0]) dout[e] = delta[e];
                         }
                     }
                 }
-                if (FUSE) {
+                if (f_reg) {
                     if (fin) {
                         if (fvec) {
-                            if (f_snap)
-                                *(float4 *)(fz.snap[0] + ri) = make_float4(uc[0], uc[1], uc[2], uc[3]);
+                            // written once, read a whole sweep later: streaming store
+                            if (f_snap) __stcs((float4 *)(fz.snap[0] + ri), cq);
                             if (f_il) {
-                                float4 I = il4;
-                                I.x += cf.dt * uc[0] * uc[0]; I.y += cf.dt * uc[1] * uc[1];
-                                I.z += cf.dt * uc[2] * uc[2]; I.w += cf.dt * uc[3] * uc[3];
-                                *(float4 *)(fz.illum + ri) = I;
+                                const f2 I0 = fma2(mul2s(cf.dt, uc0), uc0, lo2(il4));
+                                const f2 I1 = fma2(mul2s(cf.dt, uc1), uc1, hi2(il4));
+                                *(float4 *)(fz.illum + ri) = cat4(I0, I1);
                             }
                             if (f_grad) {
-                                float4 G = g4;
-                                G.x -= gc * us4.x * delta[0]; G.y -= gc * us4.y * delta[1];
-                                G.z -= gc * us4.z * delta[2]; G.w -= gc * us4.w * delta[3];
-                                *(float4 *)(fz.grad + ri) = G;
+                                const f2 G0 = fma2(mul2s(-gc, lo2(us4)), dl0, lo2(g4));
+                                const f2 G1 = fma2(mul2s(-gc, hi2(us4)), dl1, hi2(g4));
+                                *(float4 *)(fz.grad + ri) = cat4(G0, G1);
                             }
                         } else {
+                            const float uc[4] = {cq.x, cq.y, cq.z, cq.w};
+                            const float delta[4] = {dl0.x, dl0.y, dl1.x, dl1.y};
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
                                 if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
                                 if (f_snap) fz.snap[0][ri + e] = uc[e];
-                                if (f_il) fz.illum[ri + e] += cf.dt * uc[e] * uc[e];
-                                if (f_grad) fz.grad[ri + e] -= gc * fz.usnap[0][ri + e] * delta[e];
+                                if (f_il)
+                                    fz.illum[ri + e] = __fmaf_rn(__fmul_rn(cf.dt, uc[e]), uc[e], fz.illum[ri + e]);
+                                if (f_grad)
+                                    fz.grad[ri + e] = __fmaf_rn(__fmul_rn(-gc, fz.usnap[0][ri + e]), delta[e],
+                                                                fz.grad[ri + e]);
                             }
                         }
                     }
                 }
                 goff += g.sz;
-                if (FUSE) ri += rstride;
+                if (f_reg) ri += rstride;
             } else if (jt >= R) {
                 // planes below the chunk are never centres: release them as soon as R newer
                 // planes have arrived (keeps the producer's slot accounting uniform)
@@ -433,7 +466,7 @@ static const int kNumVariants = 10;
 static int variant_of(const judi_model *M)
 {
     int v = M->ctx->opt_tile;
-    if (v < 0 || v >= kNumVariants || M->r != 4) v = 8;
+    if ((v != 6 && v != 9) || M->r != 4) v = 8;
     return v;
 }
 
@@ -471,19 +504,15 @@ void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map,
     if (tile_map) encode_box(M, base, tx, ty, tile_map);
 }
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
-static void launch_variant(const judi_model *M, const StepArgs &s)
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW, bool ROT, int FUSE>
+static void launch_fused(const judi_model *M, const StepArgs &s)
 {
     typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
     judi_ctx *ctx = M->ctx;
-    const bool fuse = s.f.snap[0] || s.f.grad || s.f.illum || s.dd_out || s.qsrc;
-    auto kplain = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, false, NPW, ROT>;
-    auto kfuse = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, true, NPW, ROT>;
+    auto kern = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, FUSE, NPW, ROT>;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kplain, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)C::SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(kfuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)C::SMEM));
         configured = true;
     }
@@ -517,9 +546,37 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     dim3 grd(ntx, nty, nzc);
-    if (fuse) kfuse<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
-    else kplain<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
+    kern<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
     launch_count(ctx, "acoustic3d_tma");
+}
+
+// what the step carries -> the instantiation compiled for exactly that
+static int fuse_mask(const StepArgs &s)
+{
+    return (s.f.snap[0] ? F_SNAP : 0) | (s.f.grad ? F_GRAD : 0) | (s.f.illum ? F_ILLUM : 0) |
+           (s.dd_out ? F_DDOUT : 0) | (s.qsrc ? F_QSRC : 0);
+}
+
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
+static void launch_variant(const judi_model *M, const StepArgs &s)
+{
+#define FUSE_CASE(F) case F: launch_fused<R, TXT, TYT, NS, NP, MINB, NPW, ROT, F>(M, s); return;
+    switch (fuse_mask(s)) {
+        FUSE_CASE(0)
+        FUSE_CASE(F_SNAP)
+        FUSE_CASE(F_GRAD)
+        FUSE_CASE(F_ILLUM)
+        FUSE_CASE(F_SNAP | F_ILLUM)
+        FUSE_CASE(F_GRAD | F_ILLUM)
+        FUSE_CASE(F_DDOUT)
+        FUSE_CASE(F_DDOUT | F_SNAP)
+        FUSE_CASE(F_DDOUT | F_ILLUM)
+        FUSE_CASE(F_DDOUT | F_SNAP | F_ILLUM)
+        FUSE_CASE(F_QSRC)
+    default:
+        throw JudiError("acoustic3d_tma: unsupported combination of fused extras");
+    }
+#undef FUSE_CASE
 }
 
 void tma3d_step(const judi_model *M, const StepArgs &s)
@@ -529,15 +586,8 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
     if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2>(M, s); return; }
     if (M->r == 8) { launch_variant<8, 16, 16, 16, 4, 1>(M, s); return; }
     switch (v) {
-    case 1: launch_variant<4, 32, 8, 8, 4, 2>(M, s); break;
-    case 2: launch_variant<4, 16, 8, 8, 4, 3>(M, s); break;
-    case 3: launch_variant<4, 32, 4, 8, 4, 3>(M, s); break;
-    case 4: launch_variant<4, 16, 16, 9, 3, 2, 2>(M, s); break;   // static ring, 2 producer warps
-    case 5: launch_variant<4, 32, 8, 9, 3, 2, 2>(M, s); break;
-    case 6: launch_variant<4, 16, 16, 8, 4, 2, 2>(M, s); break;   // dynamic ring, 2 producer warps
-    case 7: launch_variant<4, 16, 8, 9, 3, 3, 2>(M, s); break;
-    case 8: launch_variant<4, 16, 16, 8, 4, 2, 2, false>(M, s); break;  // shifted queue, compact code
-    case 9: launch_variant<4, 32, 8, 8, 4, 2, 2, false>(M, s); break;
-    default: launch_variant<4, 16, 16, 8, 4, 2>(M, s); break;
+    case 6: launch_variant<4, 16, 16, 8, 4, 2, 2>(M, s); break;          // rotated queue (x9 code)
+    case 9: launch_variant<4, 32, 8, 8, 4, 2, 2, false>(M, s); break;   // 128 x 8 tile
+    default: launch_variant<4, 16, 16, 8, 4, 2, 2, false>(M, s); break; // 8: shifted queue
     }
 }
