@@ -266,7 +266,10 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(red, op=dist.ReduceOp.SUM)
 
-        ctx.set_option("timing", 1)
+        # CUDA events around every 7th stencil launch (7 is coprime with t_sub, so the sample holds
+        # the plain / save / imaging-condition flavours in their true proportions); bracketing
+        # every launch costs ~4 us of stream time per event and would slow the timed region
+        ctx.set_option("timing", 7)
         for _ in range(args.warmup):
             step_device()
         barrier()
@@ -366,6 +369,9 @@ def run_b200(args):
                 "kernel": "acoustic3d_tma (fwd / fwd+save / adj / adj+IC launches averaged)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": ms_launch, "launches_timed": stats["launches"],
+                "launches_in_region": 2 * nsteps_t * args.steps,
+                "avg_launch_ms_by_flavour": {k_: v_["ms"] / v_["launches"]
+                                             for k_, v_ in stats["kinds"].items()},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
                                "fallback 6650 GB/s (of fallback)"}
 

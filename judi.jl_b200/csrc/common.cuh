@@ -123,7 +123,8 @@ struct judi_ctx {
     cudaMemPool_t pool = nullptr;
     long long launches = 0;
     // stencil timing (CUDA events on `stream`)
-    int timing = 0;
+    int timing = 0;             // 0 off, k: time every k-th stencil launch
+    long long timing_seq = 0;
     struct Timed { cudaEvent_t e0, e1; int kind; };
     std::vector<Timed> pending;
     std::vector<cudaEvent_t> free_events;
@@ -138,6 +139,8 @@ struct judi_ctx {
     int opt_zchunks = 0;        // 0 = auto
     int opt_tile = 8;           // TMA kernel variant (8: 64x16 tile, 2 producer warps, shifted queue)
     int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
+    int opt_flux_block = 32 | (4 << 8) | (1 << 16);  // thread block of the 3-D flux kernels
+    int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
@@ -193,6 +196,7 @@ struct judi_model {
     bool tti = false, irho_field = false, has_dm = false;
     float irho_c = 1.f;
     DevBuf m, irho, eps, delta, theta, phi, dm;  // fields on `g` (edge-replicated into halo)
+    DevBuf r3[3];                // 3-D TTI: symmetry axis (sin th cos ph, sin th sin ph, cos th)
     DevBuf damp[3];              // 1-D damping profiles per dimension (value of `damp`)
     std::vector<float> damp_h[3];
     Region phys, full;

@@ -5,15 +5,27 @@
 //                          (or P = irho * G u) on the grid extended by R nodes
 //   pass 2  fluxdiv3d_vec: H = sum_d D-_d P_d, time update of 1 or 2 fields + fused extras
 // Every thread owns 4 consecutive x points; all global accesses are 128-bit and aligned (x is a
-// multiple of 4 relative to the 128-byte aligned grid origin).  The same arithmetic as the
-// one-point-per-thread kernels in kernels.cu (which remain the 2-D path).
+// multiple of 4 relative to the 128-byte aligned grid origin).
+//
+// The rotation is applied in closed form.  With r = third row of R = rot_y(theta) rot_z(phi)
+// = (sin(theta) cos(phi), sin(theta) sin(phi), cos(theta)) (the symmetry axis),
+//     R^T diag(1,1,0) R = I - r r^T,   R^T diag(0,0,1) R = r r^T,
+// hence (A = b diag(d,d,1), B = b sqrt((e-d) d) diag(1,1,0), C = b (e-d) diag(1,1,0)):
+//     P = A0 g1 + B0 g2 + [(b - A0)(r.g1) - B0 (r.g2)] r
+//     M = B0 g1 + C0 g2 - [ B0 (r.g1)     + C0 (r.g2)] r
+// which needs the unit vector r (precomputed once per model, model.cu) instead of two sincos and
+// two 3x3 rotations per point and step (same operator as the one-point-per-thread kernels in
+// kernels.cu, which remain the 2-D path, up to rounding).  The algebra is packed fp32x2.
+// (A z-marching variant with the z-lines in register queues was measured slower, 1.42 vs
+// 1.15 ms/step: 237 registers -> 8 warps/SM cannot hide the latency of synchronous loads.)
 #include "common.cuh"
 
 struct Flux3Args {
     Grid g;
     Coefs cf;
     const float *u1, *u2;
-    const float *irho, *eps, *delta, *theta, *phi;
+    const float *irho, *eps, *delta, *r3[3];
+    float irho_c;
     float *P[3], *M[3];
 };
 
@@ -60,20 +72,21 @@ __device__ __forceinline__ void grad4(const Grid &g, const Coefs &cf, const floa
     }
 }
 
-template <int R, bool TTI>
-__global__ void __launch_bounds__(128) flux3d_vec(Flux3Args a)
+template <int R, bool TTI, bool IRHOF>
+__global__ void __launch_bounds__(512) flux3d_vec(Flux3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
     const Grid &g = a.g;
     const int x = -XE + 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y) - R;
-    const int z = (int)blockIdx.z - R;
-    if (x >= g.n[0] + R || y >= g.n[1] + R) return;
+    const int z = (int)(blockIdx.z * blockDim.z + threadIdx.z) - R;
+    if (x >= g.n[0] + R || y >= g.n[1] + R || z >= g.n[2] + R) return;
     const long long i = g.at(x, y, z);
     const Coefs &cf = a.cf;
     float gx[4], gy[4], gz[4], b[4];
     grad4<R, XE>(g, cf, a.u1, i, gx, gy, gz);
-    ld4(a.irho + i, b);
+    if (IRHOF) ld4(a.irho + i, b);
+    else b[0] = b[1] = b[2] = b[3] = a.irho_c;
     if (!TTI) {
         float o[4];
 #pragma unroll
@@ -87,38 +100,39 @@ __global__ void __launch_bounds__(128) flux3d_vec(Flux3Args a)
         st4(a.P[2] + i, o);
         return;
     }
-    float hx[4], hy[4], hz[4], ep[4], dl[4], th[4], ph[4];
+    float hx[4], hy[4], hz[4], ep[4], dl[4], rx[4], ry[4], rz[4];
     grad4<R, XE>(g, cf, a.u2, i, hx, hy, hz);
     ld4(a.eps + i, ep);
     ld4(a.delta + i, dl);
-    ld4(a.theta + i, th);
-    ld4(a.phi + i, ph);
+    ld4(a.r3[0] + i, rx);
+    ld4(a.r3[1] + i, ry);
+    ld4(a.r3[2] + i, rz);
     float Px[4], Py[4], Pz[4], Mx[4], My[4], Mz[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        float st, ct, sp, cp;
-        sincosf(th[e], &st, &ct);
-        sincosf(ph[e], &sp, &cp);
-        // R = rot_axis2(theta) * rot_axis3(phi)  (FD_utils.py:24-47, sympy conventions)
-        const float R00 = ct * cp, R01 = ct * sp, R02 = -st;
-        const float R10 = -sp, R11 = cp;
-        const float R20 = st * cp, R21 = st * sp, R22 = ct;
-        const float A0 = b[e] * dl[e], A2 = b[e];
-        const float B0 = b[e] * sqrtf((ep[e] - dl[e]) * dl[e]);
-        const float C0 = b[e] * (ep[e] - dl[e]);
-        const float r1x = R00 * gx[e] + R01 * gy[e] + R02 * gz[e];
-        const float r1y = R10 * gx[e] + R11 * gy[e];
-        const float r1z = R20 * gx[e] + R21 * gy[e] + R22 * gz[e];
-        const float r2x = R00 * hx[e] + R01 * hy[e] + R02 * hz[e];
-        const float r2y = R10 * hx[e] + R11 * hy[e];
-        const float px = A0 * r1x + B0 * r2x, py = A0 * r1y + B0 * r2y, pz = A2 * r1z;
-        const float mx = B0 * r1x + C0 * r2x, my = B0 * r1y + C0 * r2y;
-        Px[e] = R00 * px + R10 * py + R20 * pz;
-        Py[e] = R01 * px + R11 * py + R21 * pz;
-        Pz[e] = R02 * px + R22 * pz;
-        Mx[e] = R00 * mx + R10 * my;
-        My[e] = R01 * mx + R11 * my;
-        Mz[e] = R02 * mx;
+    for (int h = 0; h < 4; h += 2) {
+#define P2(v) pk(v[h], v[h + 1])
+        const f2 bb = P2(b), e2 = P2(ep), d2_ = P2(dl), r_x = P2(rx), r_y = P2(ry), r_z = P2(rz);
+        const f2 g1x = P2(gx), g1y = P2(gy), g1z = P2(gz), g2x = P2(hx), g2y = P2(hy), g2z = P2(hz);
+#undef P2
+        const f2 emd = sub2(e2, d2_);
+        const f2 A0 = mul2(bb, d2_);
+        const f2 pr = mul2(emd, d2_);
+        const f2 B0 = mul2(bb, pk(sqrtf(pr.x), sqrtf(pr.y)));
+        const f2 C0 = mul2(bb, emd);
+        const f2 d1 = fma2(r_z, g1z, fma2(r_y, g1y, mul2(r_x, g1x)));
+        const f2 d2 = fma2(r_z, g2z, fma2(r_y, g2y, mul2(r_x, g2x)));
+        // sP = (b - A0) d1 - B0 d2,   sM = -(B0 d1 + C0 d2)
+        const f2 nB0 = mul2s(-1.f, B0);
+        const f2 sP = fma2(nB0, d2, mul2(sub2(bb, A0), d1));
+        const f2 sM = fma2(nB0, d1, mul2(mul2s(-1.f, C0), d2));
+        const f2 px = fma2(sP, r_x, fma2(B0, g2x, mul2(A0, g1x)));
+        const f2 py = fma2(sP, r_y, fma2(B0, g2y, mul2(A0, g1y)));
+        const f2 pz = fma2(sP, r_z, fma2(B0, g2z, mul2(A0, g1z)));
+        const f2 mx = fma2(sM, r_x, fma2(C0, g2x, mul2(B0, g1x)));
+        const f2 my = fma2(sM, r_y, fma2(C0, g2y, mul2(B0, g1y)));
+        const f2 mz = fma2(sM, r_z, fma2(C0, g2z, mul2(B0, g1z)));
+        Px[h] = px.x; Px[h + 1] = px.y; Py[h] = py.x; Py[h + 1] = py.y; Pz[h] = pz.x; Pz[h + 1] = pz.y;
+        Mx[h] = mx.x; Mx[h + 1] = mx.y; My[h] = my.x; My[h + 1] = my.y; Mz[h] = mz.x; Mz[h + 1] = mz.y;
     }
     st4(a.P[0] + i, Px); st4(a.P[1] + i, Py); st4(a.P[2] + i, Pz);
     st4(a.M[0] + i, Mx); st4(a.M[1] + i, My); st4(a.M[2] + i, Mz);
@@ -132,6 +146,7 @@ struct FluxDiv3Args {
     float *up[2];
     const float *P[3], *M[3];
     const float *m, *irho, *dm;
+    float irho_c;
     const float *dx, *dy, *dz;
     float *dd_out[2];
     const float *dd_in[2];
@@ -172,19 +187,20 @@ __device__ __forceinline__ void div4(const Grid &g, const Coefs &cf, const float
     for (int e = 0; e < 4; e++) L[e] = (L[e] + az[e]) + ay[e];
 }
 
-template <int R, int NF>
-__global__ void __launch_bounds__(128) fluxdiv3d_vec(FluxDiv3Args a)
+template <int R, int NF, bool IRHOF>
+__global__ void __launch_bounds__(512) fluxdiv3d_vec(FluxDiv3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
     const Grid &g = a.g;
     const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z;
-    if (x >= g.n[0] || y >= g.n[1]) return;
+    const int z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
     const long long i = g.at(x, y, z);
     const Coefs &cf = a.cf;
     float ir[4], mm[4], dxv[4], rden[4], sd[4];
-    ld4(a.irho + i, ir);
+    if (IRHOF) ld4(a.irho + i, ir);
+    else ir[0] = ir[1] = ir[2] = ir[3] = a.irho_c;
     ld4(a.m + i, mm);
     ld4(a.dx + x, dxv);
     const float dyz = a.dy[y];
@@ -259,14 +275,24 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
     memset(&fa, 0, sizeof(fa));
     fa.g = M->g; fa.cf = M->cf;
     fa.u1 = u[0]; fa.u2 = nf == 2 ? u[1] : nullptr;
-    fa.irho = M->irho.p; fa.eps = M->eps.p; fa.delta = M->delta.p;
-    fa.theta = M->theta.p; fa.phi = M->phi.p;
-    for (int d = 0; d < 3; d++) { fa.P[d] = W->flux[d].p; fa.M[d] = W->flux[3 + d].p; }
-    dim3 blk(32, 4, 1);
+    fa.irho = M->irho_field ? M->irho.p : nullptr;
+    fa.irho_c = M->irho_c;
+    fa.eps = M->eps.p; fa.delta = M->delta.p;
+    for (int d = 0; d < 3; d++) {
+        fa.r3[d] = M->r3[d].p;
+        fa.P[d] = W->flux[d].p; fa.M[d] = W->flux[3 + d].p;
+    }
+    // 3-D thread blocks: the 2R-wide y- and z-lines of neighbouring threads overlap inside the CTA
+    // and are served by the L1 instead of L2 (tunable: option "flux_block" = bx | by<<8 | bz<<16)
+    int fb = ctx->opt_flux_block;
+    dim3 blk(fb & 255, (fb >> 8) & 255, (fb >> 16) & 255);
     int nxt = (M->N[0] + R + XE + 3) / 4;  // threads along x covering [-XE, nx + R)
-    dim3 grd((nxt + 31) / 32, (M->N[1] + 2 * R + 3) / 4, M->N[2] + 2 * R);
-    if (M->tti) flux3d_vec<R, true><<<grd, blk, 0, ctx->stream>>>(fa);
-    else flux3d_vec<R, false><<<grd, blk, 0, ctx->stream>>>(fa);
+    dim3 grd((nxt + blk.x - 1) / blk.x, (M->N[1] + 2 * R + blk.y - 1) / blk.y,
+             (M->N[2] + 2 * R + blk.z - 1) / blk.z);
+    if (M->tti) {
+        if (M->irho_field) flux3d_vec<R, true, true><<<grd, blk, 0, ctx->stream>>>(fa);
+        else flux3d_vec<R, true, false><<<grd, blk, 0, ctx->stream>>>(fa);
+    } else flux3d_vec<R, false, true><<<grd, blk, 0, ctx->stream>>>(fa);
     launch_count(ctx, "flux3d_vec");
     FluxDiv3Args ua;
     memset(&ua, 0, sizeof(ua));
@@ -277,14 +303,19 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
         ua.dd_in[f] = dd_in ? dd_in[f] : nullptr;
     }
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
-    ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p;
+    ua.m = M->m.p; ua.dm = M->dm.p;
+    ua.irho = M->irho_field ? M->irho.p : nullptr;
+    ua.irho_c = M->irho_c;
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;
     ua.qext = qext;
     ua.qext_scale = qext_scale;
     ua.f = fuse;
-    dim3 grd2(((M->N[0] + 3) / 4 + 31) / 32, (M->N[1] + 3) / 4, M->N[2]);
-    if (nf == 2) fluxdiv3d_vec<R, 2><<<grd2, blk, 0, ctx->stream>>>(ua);
-    else fluxdiv3d_vec<R, 1><<<grd2, blk, 0, ctx->stream>>>(ua);
+    dim3 grd2(((M->N[0] + 3) / 4 + blk.x - 1) / blk.x, (M->N[1] + blk.y - 1) / blk.y,
+              (M->N[2] + blk.z - 1) / blk.z);
+    if (nf == 2) {
+        if (M->irho_field) fluxdiv3d_vec<R, 2, true><<<grd2, blk, 0, ctx->stream>>>(ua);
+        else fluxdiv3d_vec<R, 2, false><<<grd2, blk, 0, ctx->stream>>>(ua);
+    } else fluxdiv3d_vec<R, 1, true><<<grd2, blk, 0, ctx->stream>>>(ua);
     launch_count(ctx, "fluxdiv3d_vec");
 }
 

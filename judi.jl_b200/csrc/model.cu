@@ -243,6 +243,21 @@ static Region make_region(const int lo[3], const int hi[3])
     return r;
 }
 
+// symmetry axis of the TTI medium = third row of rot_y(theta) rot_z(phi) (FD_utils.py:24-47)
+__global__ void tti_axis_kernel(const float *__restrict__ theta, const float *__restrict__ phi,
+                                long long n, float *__restrict__ rx, float *__restrict__ ry,
+                                float *__restrict__ rz)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float st, ct, sp, cp;
+    sincosf(theta[i], &st, &ct);
+    sincosf(phi[i], &sp, &cp);
+    rx[i] = st * cp;
+    ry[i] = st * sp;
+    rz[i] = ct;
+}
+
 void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
 {
     JUDI_REQUIRE(desc->ndim == 2 || desc->ndim == 3, "ndim must be 2 or 3");
@@ -321,7 +336,13 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
         affine_kernel<<<nb, 256, 0, ctx->stream>>>(M->delta.p, M->g.nalloc, 2.0f, 1.0f);
         launch_count(ctx, "affine");
         model_set_param(M, M->theta, desc->theta, dev, 0.0f, true);
-        if (M->ndim == 3) model_set_param(M, M->phi, desc->phi, dev, 0.0f, true);
+        if (M->ndim == 3) {
+            model_set_param(M, M->phi, desc->phi, dev, 0.0f, true);
+            for (int d = 0; d < 3; d++) M->r3[d] = DevBuf(ctx, (size_t)M->g.nalloc, true);
+            tti_axis_kernel<<<nb, 256, 0, ctx->stream>>>(M->theta.p, M->phi.p, M->g.nalloc,
+                                                         M->r3[0].p, M->r3[1].p, M->r3[2].p);
+            launch_count(ctx, "tti_axis");
+        }
         if (M->tti && !M->irho_field) {
             // the flux-form kernels read irho as a field
             M->irho = DevBuf(ctx, (size_t)M->g.nalloc, false);

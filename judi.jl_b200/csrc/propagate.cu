@@ -13,7 +13,25 @@
 #include "common.cuh"
 #include "propagate.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+
+// phase timing of one call (option "profile"): host clock after a stream synchronize
+struct PhaseClock {
+    judi_ctx *ctx;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseClock(judi_ctx *c) : ctx(c) { if (ctx->opt_profile) mark(nullptr); }
+    void mark(const char *what)
+    {
+        if (!ctx->opt_profile) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        if (what)
+            fprintf(stderr, "[judi_b200] %-28s %9.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // ---- small data-movement kernels -------------------------------------------------------------
 // out[c][r] = in[r][c]
@@ -514,6 +532,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     const Region reg = (o->snapshot_region == JUDI_SNAP_PHYSICAL && o->ic == JUDI_IC_AS)
                            ? M->phys : M->full;
 
+    PhaseClock pc(ctx);
     Shot sh(M);
     ExtSpec jext;
     jext.ws = o->ws;
@@ -573,6 +592,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     DevBuf snaps(ctx, (size_t)nslots * slot_floats, false);
     auto slot_ptr = [&](int s, int f) { return snaps.p + ((size_t)s * nf + f) * reg.slot; };
 
+    pc.mark("setup (sparse, traces, alloc)");
     Fuse fsave = no_fuse();
     fsave.reg = reg;
     fsave.illum = illum_u ? Iu.p : nullptr;
@@ -641,6 +661,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         fsave.illum = nullptr;  // the recomputation must not add to the illumination again
     }
 
+    pc.mark("forward sweep");
     // ---- misfit (sensitivity.py:236-276) ---------------------------------------------------
     double fval = 0.0;
     if (misfit) {
@@ -676,6 +697,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     }
     // rec now holds the adjoint source (residual)
 
+    pc.mark("misfit");
     // ---- adjoint sweep with the imaging condition ---------------------------------------------
     Wavefield V;
     V.init(M, false);
@@ -740,6 +762,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         }
     }
 
+    pc.mark("adjoint sweep");
     // ---- outputs -----------------------------------------------------------------------------
     region_output(M, reg, grad.p, grad_out, dev_out, accumulate);
     if (illum_u) region_output(M, reg, Iu.p, illum_u, dev_out, false);
@@ -763,4 +786,5 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     }
     ctx->flush_timing();
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    pc.mark("outputs");
 }
