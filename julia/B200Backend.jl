@@ -32,6 +32,7 @@ end
 struct JudiJopts           # judi_jopts
     is_residual::Cint; checkpointing::Cint; n_checkpoints::Cint; t_sub::Cint; ic::Cint
     born_fwd::Cint; nlind::Cint; illum::Cint; snapshot_region::Cint
+    ws::Ptr{Cfloat}        # extended-source weights on the padded grid, or C_NULL
 end
 
 lasterr() = unsafe_string(ccall((:judi_last_error, LIB), Cstring, ()))
@@ -98,12 +99,14 @@ end
 
 # (f, g) of one shot   (misfit_fg.jl:69-73 / python_interface.jl:102-121 -> interface.py:279)
 function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOptions, n;
-                        is_residual=false, born_fwd=false, nlind=false, illum=false, misfit=nothing)
+                        is_residual=false, born_fwd=false, nlind=false, illum=false, misfit=nothing,
+                        ws=nothing)
     nt = size(qIn, 1)
     g = zeros(Float32, padded_shape(h, length(n))); f = Ref{Cfloat}(0)
     Iu = illum ? similar(g) : nothing; Iv = illum ? similar(g) : nothing
     o = JudiJopts(is_residual, options.optimal_checkpointing, 0, options.subsampling_factor,
-                  IC[options.IC], born_fwd, nlind, illum, options.sum_padding ? 0 : 1)
+                  IC[options.IC], born_fwd, nlind, illum, options.sum_padding ? 0 : 1,
+                  ws === nothing ? Ptr{Cfloat}(C_NULL) : pointer(ws))
     # custom misfit: judi_misfit_fn; the default mse (losses.jl:15-19) stays on the device (C_NULL)
     cb = misfit === nothing ? C_NULL :
         @cfunction($((ps, po, pr, nt_, nr_, _) -> begin
@@ -116,6 +119,63 @@ function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOption
                 h, size(src_coords, 1), src_coords, qIn, nt, size(rec_coords, 1), rec_coords, dIn, o,
                 cb, C_NULL, f, g, illum ? Iu : C_NULL, illum ? Iv : C_NULL, 0))
     return illum ? (f[], g, Iu, Iv) : (f[], g)
+end
+
+# ---- extended and wavefield sources (python_interface.jl:58-81, 124-198 -> interface.py:50-204, 244-276)
+# `weights` arrive on the physical grid; JUDI zero-pads them (python_interface.jl:129)
+function b200_forward_rec_w(h, wpad::Array{Float32}, qIn, rec_coords, fw::Bool)
+    nt = size(qIn, 1); rec = zeros(Float32, nt, size(rec_coords, 1))
+    check(ccall((:judi_forward_rec_w, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, fw, wpad, qIn, nt, size(rec_coords, 1), rec_coords, rec, C_NULL, 0))
+    return rec
+end
+function b200_adjoint_w(h, rec_coords, dIn, qIn, fw::Bool, n)
+    w = zeros(Float32, padded_shape(h, length(n)))
+    check(ccall((:judi_adjoint_w, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, fw, size(rec_coords, 1), rec_coords, dIn, qIn, size(qIn, 1), w, C_NULL, 0))
+    return w
+end
+function b200_born_rec_w(h, wpad::Array{Float32}, qIn, rec_coords, ic::String)
+    nt = size(qIn, 1); rec = zeros(Float32, nt, size(rec_coords, 1))
+    check(ccall((:judi_born_rec_w, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, wpad, qIn, nt, size(rec_coords, 1), rec_coords, IC[ic], rec, C_NULL, 0))
+    return rec
+end
+# u_src: (padded grid..., nt) column-major = time slowest, as JUDI's judiWavefield data permuted
+function b200_forward_wf_src(h, u_src::Array{Float32}, rec_coords, fw::Bool)
+    nt = size(u_src)[end]; rec = zeros(Float32, nt, size(rec_coords, 1))
+    check(ccall((:judi_forward_wf_src, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, fw, u_src, nt, size(rec_coords, 1), rec_coords, rec, C_NULL, 0))
+    return rec
+end
+function b200_forward_wf_src_norec(h, u_src::Array{Float32}, fw::Bool)
+    u = similar(u_src)
+    check(ccall((:judi_forward_wf_src_norec, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
+                h, fw, u_src, size(u_src)[end], u, C_NULL, 0))
+    return u
+end
+
+# ---- the steps around the propagators, on the device (SURVEY 8f rank 2) ------------------------
+# remove_padding(gradient, modelPy.padsizes; true_adjoint) (auxiliaryFunctions.jl:79-89)
+function b200_remove_padding(h, g::Array{Float32}, n; true_adjoint::Bool=false)
+    out = zeros(Float32, n)
+    check(ccall((:judi_remove_padding, LIB), Cint, (Ptr{Cvoid}, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Cint),
+                h, g, true_adjoint, out, 0))
+    return out
+end
+# time_resample(data, t_in, t_new) (time_utilities.jl:32-48)
+function b200_time_resample(data::Matrix{Float32}, t_in::StepRangeLen, t_new::StepRangeLen, nt_out::Int)
+    out = zeros(Float32, nt_out, size(data, 2))
+    check(ccall((:judi_time_resample, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cfloat}, Cint, Cint, Cfloat, Cfloat, Ptr{Cfloat}, Cint, Cfloat, Cfloat, Cint),
+                ctx(), data, size(data, 1), size(data, 2), first(t_in), step(t_in), out, nt_out,
+                first(t_new), step(t_new), 0))
+    return out
 end
 
 end # module
