@@ -140,6 +140,7 @@ struct judi_ctx {
     int opt_tile = 8;           // TMA kernel variant (8: 64x16 tile, 2 producer warps, shifted queue)
     int opt_atomic_inject = 0;  // 1: atomicAdd injection instead of the sorted segmented path
     int opt_flux_block = 32 | (4 << 8) | (1 << 16);  // thread block of the 3-D flux kernels
+    int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
     int num_sms = 148;
@@ -259,6 +260,9 @@ struct StepArgs {
     const CUtensorMap *tmap;       // halo-box tensor map of u[0] (TMA kernel), or nullptr
     const CUtensorMap *tmap_prev;  // tile-box tensor map of up[0]
     const CUtensorMap *tmap_m;     // tile-box tensor map of m
+    const CUtensorMap *tmap2;      // fused Born: halo-box map of ul[0], tile-box map of ulp[0] ...
+    const CUtensorMap *tmap_prev2;
+    const CUtensorMap *tmap_dm;    // ... and tile-box map of dm
     struct Wavefield *scratch; // owner of the flux-form / Born scratch buffers
     struct Wavefield *lin;     // Born: the linearised wavefield (tensor maps of ul)
     const float *qext;         // space-time source field of this step (Grid layout) or nullptr:
@@ -279,6 +283,7 @@ struct Wavefield {
     CUtensorMap tmap_halo[2][2];  // [field][slot]: haloed plane box
     CUtensorMap tmap_tile[2][2];  // [field][slot]: tile box
     CUtensorMap tmap_m;           // tile box over the model's m
+    CUtensorMap tmap_dm;          // tile box over the model's dm (Born)
     bool has_tmap = false;
     void init(const judi_model *M, bool born_scratch);
     void swap() { cur = 1 - cur; }

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
 void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
+bool tma3d_step_born(const judi_model *M, const StepArgs &a);
 bool flux3d_step(const judi_model *M, const StepArgs &s);
 
 void Wavefield::init(const judi_model *M, bool born_scratch)
@@ -327,6 +328,7 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         for (int f = 0; f < nf; f++)
             for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
         tma3d_encode(M, M->m.p, nullptr, &tmap_m);
+        if (M->dm.p) tma3d_encode(M, M->dm.p, nullptr, &tmap_dm);
         has_tmap = true;
     }
 }
@@ -462,7 +464,18 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     bool use_tma = M->ndim == 3 && !ff && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
                    (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && !s.qext && !s.f.wrec &&
                    (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
-    if (use_tma && s.born) {
+    bool born_done = false;
+    if (use_tma && s.born && ctx->opt_born_fused) {
+        // fused Born (32 B/pt): both fields in one launch, delta handed over in shared memory
+        StepArgs a = s;
+        a.born = 0;
+        a.tmap2 = &s.lin->tmap_halo[0][s.lin->cur];
+        a.tmap_prev2 = &s.lin->tmap_tile[0][1 - s.lin->cur];
+        a.tmap_dm = &s.lin->tmap_dm;
+        born_done = tma3d_step_born(M, a);
+    }
+    if (born_done) { /* one launch */ }
+    else if (use_tma && s.born) {
         // Born as two launches of the TMA kernel (44 B/pt): the background step also writes
         // delta = u+ - 2u + u-, the linearised step reads it as the source -dm * delta
         StepArgs a1 = s;

@@ -94,9 +94,15 @@ struct TmaArgs {
     float *dd_out;       // Born, background pass: write delta = u+ - 2u + u-   (Grid layout)
     const float *qsrc;   // Born, linearised pass: delta of the background field ...
     const float *dm;     // ... and the perturbation: source term -dm * qsrc
+    float *ulp;          // fused Born (DUAL): output of the linearised field, in place
 };
 
-template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1>
+// DUAL: fused Born step.  Two groups of consumer warps share one CTA: group 0 steps the background
+// field u, group 1 the linearised field ul; both planes travel in one ring slot, the tiles
+// (u-, m, ul-, dm) in one tile slot, and the Born source -dm (u+ - 2u + u-) goes from group 0 to
+// group 1 through a shared-memory tile ring guarded by per-warp mbarriers.  32 B per grid point
+// of HBM traffic instead of the 44 B of two launches that exchange delta through HBM.
+template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1, bool DUAL = false>
 struct TmaCfg {
     static constexpr int HR = ((R + 3) / 4) * 4;  // x halo in shared memory (float4 aligned)
     static constexpr int TX = 4 * TXT, TY = TYT;
@@ -104,10 +110,15 @@ struct TmaCfg {
     static constexpr int SLOT = ((PX * PY * 4 + 127) / 128) * 128 / 4;  // floats per u slot
     static constexpr int PSLOT = TX * TY;                               // floats per tile
     static constexpr int NQ = 2 * R + 1;
-    static constexpr int NCONS = TXT * TYT;       // consumer threads
-    static constexpr int NTHREADS = NCONS + 32 * NPW;   // + producer warp(s)
-    static constexpr size_t SMEM =
-        (size_t)NS * SLOT * 4 + (size_t)NP * 2 * PSLOT * 4 + (2 * NS + 2 * NP) * 8 + 128;
+    static constexpr int NCONS = TXT * TYT;       // consumer threads per group
+    static constexpr int NG = DUAL ? 2 : 1;       // consumer groups
+    static constexpr int ND = 2;                  // delta-exchange slots (DUAL)
+    static constexpr int USTRIDE = NG * SLOT;     // floats per ring slot (u [, ul] plane)
+    static constexpr int PSTRIDE = 2 * NG * PSLOT;  // floats per tile slot (u-, m [, ul-, dm])
+    static constexpr int NTHREADS = NG * NCONS + 32 * NPW;   // + producer warp(s)
+    static constexpr int NBAR = 2 * NS + 2 * NP + (DUAL ? 2 * ND * (NCONS / 32) : 0);
+    static constexpr size_t SMEM = (size_t)NS * USTRIDE * 4 + (size_t)NP * PSTRIDE * 4 +
+                                   (DUAL ? (size_t)ND * PSLOT * 4 : 0) + NBAR * 8 + 128;
 };
 
 // FUSE is a compile-time mask of what rides on the step, so that each flavour of launch carries
@@ -115,14 +126,20 @@ struct TmaCfg {
 // than the plain one for a single extra store):
 enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16 };
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT>
-__global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
-    acoustic3d_tma(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP,
-                   const __grid_constant__ CUtensorMap tmM, const TmaArgs a)
+struct TmaMaps {   // tensor maps of one launch (kernel parameter, __grid_constant__)
+    CUtensorMap U, P, M;      // haloed u(t), tile u(t-1), tile m
+    CUtensorMap U2, P2, D;    // DUAL: haloed ul(t), tile ul(t-1), tile dm
+};
+
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT, bool DUAL>
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
+    acoustic3d_tma(const __grid_constant__ TmaMaps tm, const TmaArgs a)
 {
-    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL> C;
     constexpr int HR = C::HR, TX = C::TX, TY = C::TY, PX = C::PX, PY = C::PY, SLOT = C::SLOT;
     constexpr int PSLOT = C::PSLOT, NQ = C::NQ, NCW = C::NCONS / 32;
+    constexpr int NG = C::NG, ND = C::ND, USTRIDE = C::USTRIDE, PSTRIDE = C::PSTRIDE;
+    static_assert(!DUAL || NPW == 2, "the fused Born variant uses two producer warps");
     // STATIC: ring length == queue length, so ring slots are compile-time constants inside the
     // unrolled main loop and every shared-memory address is an immediate offset
     constexpr bool STATIC = ROT && (NS == NQ) && (NQ % NP == 0);
@@ -130,11 +147,14 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                   "dynamic ring sizes must be powers of 2");
     extern __shared__ unsigned char smem_raw[];
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    float *ringP = ringU + NS * SLOT;                 // [NP][2][PSLOT]: u(t-1) tile, m tile
-    uint64_t *fullU = (uint64_t *)(ringP + NP * 2 * PSLOT);
+    float *ringP = ringU + NS * USTRIDE;              // [NP][2 NG][PSLOT]: u(t-1), m [, ul(t-1), dm]
+    float *ringD = ringP + NP * PSTRIDE;              // DUAL: [ND][PSLOT] delta of the background
+    uint64_t *fullU = (uint64_t *)(ringD + (DUAL ? ND * PSLOT : 0));
     uint64_t *emptyU = fullU + NS;
     uint64_t *fullP = emptyU + NS;
     uint64_t *emptyP = fullP + NP;
+    [[maybe_unused]] uint64_t *fullD = emptyP + NP;   // DUAL: [ND][NCW], one per consumer warp
+    [[maybe_unused]] uint64_t *emptyD = fullD + ND * NCW;
 
     const Grid &g = a.g;
     const Coefs &cf = a.cf;
@@ -145,27 +165,30 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     const int total = nzc + 2 * R;  // u planes this CTA consumes: z0-R .. z1-1+R
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NCW); }
-        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], NCW); }
+        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NG * NCW); }
+        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], NG * NCW); }
+        if (DUAL)
+            for (int s = 0; s < ND * NCW; s++) { mbar_init(&fullD[s], 1); mbar_init(&emptyD[s], 1); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (threadIdx.x >= C::NCONS) {
+    if (threadIdx.x >= NG * C::NCONS) {
         // ===== producer warp(s): one lane issues the TMA loads of this CTA =====================
         // NPW == 1: a single lane issues both streams; NPW == 2: warp 0 streams the haloed u(t)
         // planes, warp 1 the u(t-1)/m tiles, so neither ring can stall the other.
-        const int pw = (threadIdx.x - C::NCONS) >> 5;
+        const int pw = (threadIdx.x - NG * C::NCONS) >> 5;
         if ((threadIdx.x & 31) == 0) {
             const int bx = g.hx + x0 - HR, by = g.hy + y0 - R, bz = g.hz + z0 - R;
             const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
-            constexpr uint32_t UBYTES = PX * PY * 4, PBYTES = 2 * PSLOT * 4;
+            constexpr uint32_t UBYTES = NG * PX * PY * 4, PBYTES = 2 * NG * PSLOT * 4;
+            const CUtensorMap *tmU = &tm.U, *tmP = &tm.P, *tmM = &tm.M;
             if (NPW == 1) {
                 for (int j = 0; j < total; j++) {
                     const int s = j % NS;
                     if (j >= NS) mbar_wait(&emptyU[s], (uint32_t)(((j / NS) - 1) & 1));
                     mbar_arrive_expect_tx(&fullU[s], UBYTES);
-                    tma_load_3d(ringU + s * SLOT, &tmU, bx, by, bz + j, &fullU[s]);
+                    tma_load_3d(ringU + s * USTRIDE, tmU, bx, by, bz + j, &fullU[s]);
                     // tiles of output plane z0+i are consumed at iteration i+2R: issue them one
                     // iteration early (the ring depth NP then allows NP-2 planes of run-ahead)
                     const int i = j - 2 * R + 1;
@@ -173,8 +196,8 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                         const int sp = i % NP;
                         if (i >= NP) mbar_wait(&emptyP[sp], (uint32_t)(((i / NP) - 1) & 1));
                         mbar_arrive_expect_tx(&fullP[sp], PBYTES);
-                        tma_load_3d(ringP + sp * 2 * PSLOT, &tmP, tx0, ty0, tz0 + i, &fullP[sp]);
-                        tma_load_3d(ringP + sp * 2 * PSLOT + PSLOT, &tmM, tx0, ty0, tz0 + i, &fullP[sp]);
+                        tma_load_3d(ringP + sp * PSTRIDE, tmP, tx0, ty0, tz0 + i, &fullP[sp]);
+                        tma_load_3d(ringP + sp * PSTRIDE + PSLOT, tmM, tx0, ty0, tz0 + i, &fullP[sp]);
                     }
                 }
             } else if (pw == 0) {
@@ -182,15 +205,20 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                     const int s = j % NS;
                     if (j >= NS) mbar_wait(&emptyU[s], (uint32_t)(((j / NS) - 1) & 1));
                     mbar_arrive_expect_tx(&fullU[s], UBYTES);
-                    tma_load_3d(ringU + s * SLOT, &tmU, bx, by, bz + j, &fullU[s]);
+                    tma_load_3d(ringU + s * USTRIDE, tmU, bx, by, bz + j, &fullU[s]);
+                    if (DUAL) tma_load_3d(ringU + s * USTRIDE + SLOT, &tm.U2, bx, by, bz + j, &fullU[s]);
                 }
             } else {
                 for (int i = 0; i < nzc; i++) {
                     const int sp = i % NP;
                     if (i >= NP) mbar_wait(&emptyP[sp], (uint32_t)(((i / NP) - 1) & 1));
                     mbar_arrive_expect_tx(&fullP[sp], PBYTES);
-                    tma_load_3d(ringP + sp * 2 * PSLOT, &tmP, tx0, ty0, tz0 + i, &fullP[sp]);
-                    tma_load_3d(ringP + sp * 2 * PSLOT + PSLOT, &tmM, tx0, ty0, tz0 + i, &fullP[sp]);
+                    tma_load_3d(ringP + sp * PSTRIDE, tmP, tx0, ty0, tz0 + i, &fullP[sp]);
+                    tma_load_3d(ringP + sp * PSTRIDE + PSLOT, tmM, tx0, ty0, tz0 + i, &fullP[sp]);
+                    if (DUAL) {
+                        tma_load_3d(ringP + sp * PSTRIDE + 2 * PSLOT, &tm.P2, tx0, ty0, tz0 + i, &fullP[sp]);
+                        tma_load_3d(ringP + sp * PSTRIDE + 3 * PSLOT, &tm.D, tx0, ty0, tz0 + i, &fullP[sp]);
+                    }
                 }
             }
         }
@@ -198,8 +226,14 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     }
 
     // ===== consumer warps ===================================================================
-    const int tx = threadIdx.x % TXT, ty = threadIdx.x / TXT;
+    // grp 0 steps the background field (and is the only group when !DUAL), grp 1 the linearised one
+    const int grp = DUAL ? (int)threadIdx.x / C::NCONS : 0;
+    const int ctid = (int)threadIdx.x - grp * C::NCONS;
+    const int tx = ctid % TXT, ty = ctid / TXT;
     const int lane = threadIdx.x & 31;
+    [[maybe_unused]] const int wg = ctid >> 5;          // warp index inside the group
+    const float *ringUg = ringU + grp * SLOT;           // this group's plane inside a ring slot
+    float *const outp = (DUAL && grp == 1) ? a.ulp : a.up;
     const int x = x0 + 4 * tx, y = y0 + ty;
     const bool act = x < g.n[0] && y < g.n[1];
     const bool xfull = x + 3 < g.n[0];
@@ -227,7 +261,7 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
     constexpr bool f_il = (FUSE & F_ILLUM) != 0, f_dd = (FUSE & F_DDOUT) != 0;
     constexpr bool f_reg = f_snap || f_grad || f_il;   // anything stored in the region layout
     [[maybe_unused]] const bool f_born = (FUSE & F_QSRC) != 0 && act;
-    [[maybe_unused]] const bool f_xy = f_reg && act && y >= fz.reg.lo[1] &&
+    [[maybe_unused]] const bool f_xy = f_reg && act && grp == 0 && y >= fz.reg.lo[1] &&
                                        y < fz.reg.hi[1] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0];
     [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && x >= fz.reg.lo[0] &&
                                         x + 3 < fz.reg.hi[0];
@@ -282,11 +316,11 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 }
             }
             mbar_wait(&fullU[st], (uint32_t)((jt / NS) & 1));
-            Q(2 * R) = *(const float4 *)(ringU + st * SLOT + sm_own);
+            Q(2 * R) = *(const float4 *)(ringUg + st * USTRIDE + sm_own);
             if (jt >= 2 * R) {
                 const int i = jt - 2 * R;  // output plane index inside the chunk
                 const int z = z0 + i;
-                const float *cen = ringU + sc * SLOT;
+                const float *cen = ringUg + sc * USTRIDE;
                 // All point-wise arithmetic is packed fp32x2 on the pairs (x, x+1), (x+2, x+3):
                 // z part (register queue), x part (row), y part (column): three accumulators
                 const float4 cq = Q(R);
@@ -352,11 +386,24 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 // ---- u(t-1) and m tiles of the output plane ----------------------------------
                 const int sp = STATIC ? (ph + 4 * NQ - 2 * R) % NP : (i % NP);
                 mbar_wait(&fullP[sp], (uint32_t)((i / NP) & 1));
-                const float *pt = ringP + sp * 2 * PSLOT + sm_tile;
-                const float4 up4 = *(const float4 *)pt;
+                const float *pt = ringP + sp * PSTRIDE + sm_tile;
+                const float4 up4 = *(const float4 *)(pt + (DUAL ? 2 * grp * PSLOT : 0));
                 const float4 m4 = *(const float4 *)(pt + PSLOT);
+                [[maybe_unused]] float4 dmt4;
+                if (DUAL && grp == 1) dmt4 = *(const float4 *)(pt + 3 * PSLOT);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyP[sp]);
+                if (DUAL && grp == 1) {
+                    // Born source of the linearised field: -dm * delta of the background, handed
+                    // over by the same warp of group 0 through shared memory
+                    const int sd = i % ND;
+                    mbar_wait(&fullD[sd * NCW + wg], (uint32_t)((i / ND) & 1));
+                    const float4 dd4 = *(const float4 *)(ringD + sd * PSLOT + sm_tile);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&emptyD[sd * NCW + wg]);
+                    lz0.x = __fmaf_rn(-dmt4.x, dd4.x, lz0.x); lz0.y = __fmaf_rn(-dmt4.y, dd4.y, lz0.y);
+                    lz1.x = __fmaf_rn(-dmt4.z, dd4.z, lz1.x); lz1.y = __fmaf_rn(-dmt4.w, dd4.w, lz1.y);
+                }
                 if (f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
                     lz0.x = __fmaf_rn(-dm4.x, qs4.x, lz0.x); lz0.y = __fmaf_rn(-dm4.y, qs4.y, lz0.y);
                     lz1.x = __fmaf_rn(-dm4.z, qs4.z, lz1.x); lz1.y = __fmaf_rn(-dm4.w, qs4.w, lz1.y);
@@ -386,9 +433,16 @@ __global__ void __launch_bounds__(TXT *TYT + 32 * NPW, MINB)
                 const f2 un0 = fma2(t0, r0, add2(uc0, d10)), un1 = fma2(t1, r1, add2(uc1, d11));
                 // delta = u+ - 2u + u- (imaging condition, Born source): fused variants only
                 [[maybe_unused]] f2 dl0, dl1;
-                if (f_grad || f_dd) { dl0 = mul2(t0, r0); dl1 = mul2(t1, r1); }
+                if (f_grad || f_dd || DUAL) { dl0 = mul2(t0, r0); dl1 = mul2(t1, r1); }
+                if (DUAL && grp == 0) {
+                    const int sd = i % ND;
+                    if (i >= ND) mbar_wait(&emptyD[sd * NCW + wg], (uint32_t)(((i / ND) - 1) & 1));
+                    *(float4 *)(ringD + sd * PSLOT + sm_tile) = cat4(dl0, dl1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fullD[sd * NCW + wg]);
+                }
                 if (act) {
-                    float *gout = a.up + goff;
+                    float *gout = outp + goff;
                     if (xfull) *(float4 *)gout = cat4(un0, un1);
                     else {
                         const float un[4] = {un0.x, un0.y, un1.x, un1.y};
@@ -504,12 +558,13 @@ void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map,
     if (tile_map) encode_box(M, base, tx, ty, tile_map);
 }
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW, bool ROT, int FUSE>
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW, bool ROT, int FUSE,
+          bool DUAL = false>
 static void launch_fused(const judi_model *M, const StepArgs &s)
 {
-    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW> C;
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL> C;
     judi_ctx *ctx = M->ctx;
-    auto kern = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, FUSE, NPW, ROT>;
+    auto kern = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, FUSE, NPW, ROT, DUAL>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -532,6 +587,15 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
     a.dd_out = s.dd_out;
     a.qsrc = s.qsrc;
     a.dm = s.qsrc ? M->dm.p : nullptr;
+    TmaMaps tm;
+    tm.U = *s.tmap; tm.P = *s.tmap_prev; tm.M = *s.tmap_m;
+    if (DUAL) {
+        JUDI_REQUIRE(s.tmap2 && s.tmap_prev2 && s.tmap_dm && s.ulp[0], "fused Born: maps missing");
+        tm.U2 = *s.tmap2; tm.P2 = *s.tmap_prev2; tm.D = *s.tmap_dm;
+        a.ulp = s.ulp[0];
+    } else {
+        tm.U2 = tm.U; tm.P2 = tm.P; tm.D = tm.M;
+    }
     int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
@@ -546,7 +610,7 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     dim3 grd(ntx, nty, nzc);
-    kern<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(*s.tmap, *s.tmap_prev, *s.tmap_m, a);
+    kern<<<grd, C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
     launch_count(ctx, "acoustic3d_tma");
 }
 
@@ -577,6 +641,23 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
         throw JudiError("acoustic3d_tma: unsupported combination of fused extras");
     }
 #undef FUSE_CASE
+}
+
+// Fused Born step (background + linearised field in one launch); false if this radius / tile
+// has no fused instantiation (the caller then runs the two-launch form).
+bool tma3d_step_born(const judi_model *M, const StepArgs &s)
+{
+    if (variant_of(M) != 8 || s.f.grad || s.dd_out || s.qsrc) return false;
+    const int mask = (s.f.snap[0] ? F_SNAP : 0) | (s.f.illum ? F_ILLUM : 0);
+#define BORN_CASE(RR, F) \
+    case F: launch_fused<RR, 16, 16, 8, 4, 1, 2, false, F, true>(M, s); return true;
+    if (M->r == 4) {
+        switch (mask) { BORN_CASE(4, 0) BORN_CASE(4, F_SNAP) BORN_CASE(4, F_ILLUM) BORN_CASE(4, F_SNAP | F_ILLUM) }
+    } else if (M->r == 2) {
+        switch (mask) { BORN_CASE(2, 0) BORN_CASE(2, F_SNAP) BORN_CASE(2, F_ILLUM) BORN_CASE(2, F_SNAP | F_ILLUM) }
+    }
+#undef BORN_CASE
+    return false;
 }
 
 void tma3d_step(const judi_model *M, const StepArgs &s)
