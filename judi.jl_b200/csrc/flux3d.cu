@@ -27,6 +27,7 @@ struct Flux3Args {
     const float *irho, *eps, *delta, *r3[3];
     float irho_c;
     float *P[3], *M[3];
+    int z0, z1;   // flux planes [z0, z1) of this launch
 };
 
 __device__ __forceinline__ void ld4(const float *p, float *w)
@@ -72,15 +73,15 @@ __device__ __forceinline__ void grad4(const Grid &g, const Coefs &cf, const floa
     }
 }
 
-template <int R, bool TTI, bool IRHOF>
-__global__ void __launch_bounds__(512) flux3d_vec(Flux3Args a)
+template <int R, bool TTI, bool IRHOF, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) flux3d_vec(Flux3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
     const Grid &g = a.g;
     const int x = -XE + 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = (int)(blockIdx.y * blockDim.y + threadIdx.y) - R;
-    const int z = (int)(blockIdx.z * blockDim.z + threadIdx.z) - R;
-    if (x >= g.n[0] + R || y >= g.n[1] + R || z >= g.n[2] + R) return;
+    const int z = a.z0 + (int)(blockIdx.z * blockDim.z + threadIdx.z);
+    if (x >= g.n[0] + R || y >= g.n[1] + R || z >= a.z1) return;
     const long long i = g.at(x, y, z);
     const Coefs &cf = a.cf;
     float gx[4], gy[4], gz[4], b[4];
@@ -153,6 +154,7 @@ struct FluxDiv3Args {
     const float *qext;
     float qext_scale;
     Fuse f;
+    int z0, z1;   // output planes [z0, z1) of this launch
 };
 
 template <int R, int XE>
@@ -187,15 +189,15 @@ __device__ __forceinline__ void div4(const Grid &g, const Coefs &cf, const float
     for (int e = 0; e < 4; e++) L[e] = (L[e] + az[e]) + ay[e];
 }
 
-template <int R, int NF, bool IRHOF>
-__global__ void __launch_bounds__(512) fluxdiv3d_vec(FluxDiv3Args a)
+template <int R, int NF, bool IRHOF, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) fluxdiv3d_vec(FluxDiv3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
     const Grid &g = a.g;
     const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z * blockDim.z + threadIdx.z;
-    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
+    const int z = a.z0 + (int)(blockIdx.z * blockDim.z + threadIdx.z);
+    if (x >= g.n[0] || y >= g.n[1] || z >= a.z1) return;
     const long long i = g.at(x, y, z);
     const Coefs &cf = a.cf;
     float ir[4], mm[4], dxv[4], rden[4], sd[4];
@@ -287,13 +289,7 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
     int fb = ctx->opt_flux_block;
     dim3 blk(fb & 255, (fb >> 8) & 255, (fb >> 16) & 255);
     int nxt = (M->N[0] + R + XE + 3) / 4;  // threads along x covering [-XE, nx + R)
-    dim3 grd((nxt + blk.x - 1) / blk.x, (M->N[1] + 2 * R + blk.y - 1) / blk.y,
-             (M->N[2] + 2 * R + blk.z - 1) / blk.z);
-    if (M->tti) {
-        if (M->irho_field) flux3d_vec<R, true, true><<<grd, blk, 0, ctx->stream>>>(fa);
-        else flux3d_vec<R, true, false><<<grd, blk, 0, ctx->stream>>>(fa);
-    } else flux3d_vec<R, false, true><<<grd, blk, 0, ctx->stream>>>(fa);
-    launch_count(ctx, "flux3d_vec");
+    dim3 grd((nxt + blk.x - 1) / blk.x, (M->N[1] + 2 * R + blk.y - 1) / blk.y, 1);
     FluxDiv3Args ua;
     memset(&ua, 0, sizeof(ua));
     ua.g = M->g; ua.cf = M->cf;
@@ -310,13 +306,39 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
     ua.qext = qext;
     ua.qext_scale = qext_scale;
     ua.f = fuse;
-    dim3 grd2(((M->N[0] + 3) / 4 + blk.x - 1) / blk.x, (M->N[1] + blk.y - 1) / blk.y,
-              (M->N[2] + blk.z - 1) / blk.z);
-    if (nf == 2) {
-        if (M->irho_field) fluxdiv3d_vec<R, 2, true><<<grd2, blk, 0, ctx->stream>>>(ua);
-        else fluxdiv3d_vec<R, 2, false><<<grd2, blk, 0, ctx->stream>>>(ua);
-    } else fluxdiv3d_vec<R, 1, true><<<grd2, blk, 0, ctx->stream>>>(ua);
-    launch_count(ctx, "fluxdiv3d_vec");
+    dim3 grd2(((M->N[0] + 3) / 4 + blk.x - 1) / blk.x, (M->N[1] + blk.y - 1) / blk.y, 1);
+    // The two passes alternate over slabs of z planes so that the flux fields written by pass 1
+    // are still in L2 (126 MB) when pass 2 reads them: pass 2 of slab k needs the flux planes
+    // [kS - R, (k+1)S + R - 1]; pass 1 never reads what pass 2 writes (u(t-1) -> u(t+1) in place),
+    // so the interleaving is free of hazards.
+    const int S = ctx->opt_flux_slab > 0 ? ctx->opt_flux_slab : M->N[2];
+    int fdone = -R;   // flux planes [-R, fdone) are computed
+    for (int zs = 0; zs < M->N[2]; zs += S) {
+        const int ze = std::min(zs + S, M->N[2]);
+        fa.z0 = fdone;
+        fa.z1 = ze == M->N[2] ? M->N[2] + R : ze + R;
+        fdone = fa.z1;
+        grd.z = (fa.z1 - fa.z0 + blk.z - 1) / blk.z;
+        if (M->tti) {
+            if (M->irho_field) flux3d_vec<R, true, true><<<grd, blk, 0, ctx->stream>>>(fa);
+            else if (ctx->opt_flux_minb == 8) flux3d_vec<R, true, false, 8><<<grd, blk, 0, ctx->stream>>>(fa);
+            else if (ctx->opt_flux_minb == 10) flux3d_vec<R, true, false, 10><<<grd, blk, 0, ctx->stream>>>(fa);
+            else if (ctx->opt_flux_minb == 12) flux3d_vec<R, true, false, 12><<<grd, blk, 0, ctx->stream>>>(fa);
+            else flux3d_vec<R, true, false><<<grd, blk, 0, ctx->stream>>>(fa);
+        } else flux3d_vec<R, false, true><<<grd, blk, 0, ctx->stream>>>(fa);
+        launch_count(ctx, "flux3d_vec");
+        ua.z0 = zs;
+        ua.z1 = ze;
+        grd2.z = (ze - zs + blk.z - 1) / blk.z;
+        if (nf == 2) {
+            if (M->irho_field) fluxdiv3d_vec<R, 2, true><<<grd2, blk, 0, ctx->stream>>>(ua);
+            else if (ctx->opt_flux_minb == 8) fluxdiv3d_vec<R, 2, false, 8><<<grd2, blk, 0, ctx->stream>>>(ua);
+            else if (ctx->opt_flux_minb == 10) fluxdiv3d_vec<R, 2, false, 10><<<grd2, blk, 0, ctx->stream>>>(ua);
+            else if (ctx->opt_flux_minb == 12) fluxdiv3d_vec<R, 2, false, 12><<<grd2, blk, 0, ctx->stream>>>(ua);
+            else fluxdiv3d_vec<R, 2, false><<<grd2, blk, 0, ctx->stream>>>(ua);
+        } else fluxdiv3d_vec<R, 1, true><<<grd2, blk, 0, ctx->stream>>>(ua);
+        launch_count(ctx, "fluxdiv3d_vec");
+    }
 }
 
 // One time step of the flux-form physics in 3-D (plain or Born).  Returns false if the radius is

@@ -14,11 +14,11 @@ gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).
 q = ricker(nt, float(gm.critical_dt), 0.008)
 src = np.array([[3750., 3750., 50.]], dtype=np.float32)
 rec = np.array([[3000., 3000., 50.]], dtype=np.float32)
-for blk in [(32, 4, 1), (32, 4, 2), (32, 4, 4), (32, 2, 4), (32, 2, 8), (16, 8, 4), (16, 4, 8), (16, 8, 2), (16, 4, 4),
-            (32, 1, 8), (32, 1, 16), (16, 2, 16), (8, 8, 8), (8, 8, 4), (16, 16, 2), (32, 8, 2), (32, 8, 1)]:
-    ctx.set_option("flux_block", blk[0] | (blk[1] << 8) | (blk[2] << 16))
-    J.forward_rec(gm, src, q, rec)
+for mb in (0, 8, 10, 12):
+    ctx.set_option("flux_minb", mb)
+    d1 = J.forward_rec(gm, src, q, rec)[0]
     ctx.set_option("timing", 1); ctx.reset_stats()
     J.forward_rec(gm, src, q, rec)
     st = ctx.stencil_stats(); ctx.set_option("timing", 0)
-    print("block %-12s: %.4f ms/step" % (blk, st["ms"] / st["launches"]), flush=True)
+    if mb == 0: ref = d1
+    print("minb %3d: %.4f ms/step  same=%s" % (mb, st["ms"] / st["launches"], np.array_equal(d1, ref)), flush=True)
