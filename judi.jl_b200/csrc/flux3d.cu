@@ -73,7 +73,7 @@ __device__ __forceinline__ void grad4(const Grid &g, const Coefs &cf, const floa
     }
 }
 
-template <int R, bool TTI, bool IRHOF, int MINB = 4>
+template <int R, bool TTI, bool IRHOF, int MINB = 8>
 __global__ void __launch_bounds__(128, MINB) flux3d_vec(Flux3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;
@@ -189,7 +189,7 @@ __device__ __forceinline__ void div4(const Grid &g, const Coefs &cf, const float
     for (int e = 0; e < 4; e++) L[e] = (L[e] + az[e]) + ay[e];
 }
 
-template <int R, int NF, bool IRHOF, int MINB = 4>
+template <int R, int NF, bool IRHOF, int MINB = 8>
 __global__ void __launch_bounds__(128, MINB) fluxdiv3d_vec(FluxDiv3Args a)
 {
     constexpr int XE = ((R + 3) / 4) * 4;

@@ -625,7 +625,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                 pf.t_sub = mode == 1 ? k : 1;
                 pf.t_base = mode == 1 ? 0 : base;
             }
-            persist2d_run(M, W, born ? &WL : nullptr, ta, tb, 1, pSrc, &q,
+            persist2d_run(M, W, (born && record) ? &WL : nullptr, ta, tb, 1, pSrc, &q,
                           record ? &S_rec : nullptr, &rec,
                           (record && born && o->nlind) ? &recnl : nullptr, pf);
             return;
@@ -643,7 +643,8 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     if (!o->checkpointing) {
         fwd_range(1, nt - 2, 1, 0, true);
     } else {
-        JUDI_REQUIRE(!born, "optimal_checkpointing with born_fwd is not supported yet");
+        // with born_fwd only the background field is checkpointed: the recomputation needs the
+        // snapshots of u, not the linearised field
         ckpt.resize((size_t)nseg * 2 * nf);
         for (int s = 0; s < nseg; s++) {
             int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);

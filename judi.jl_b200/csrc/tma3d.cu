@@ -143,8 +143,7 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
     // STATIC: ring length == queue length, so ring slots are compile-time constants inside the
     // unrolled main loop and every shared-memory address is an immediate offset
     constexpr bool STATIC = ROT && (NS == NQ) && (NQ % NP == 0);
-    static_assert(STATIC || ((NS & (NS - 1)) == 0 && (NP & (NP - 1)) == 0),
-                  "dynamic ring sizes must be powers of 2");
+    // (ring lengths need not be powers of two: `% NS` with a constant is a multiply-shift)
     extern __shared__ unsigned char smem_raw[];
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float *ringP = ringU + NS * USTRIDE;              // [NP][2 NG][PSLOT]: u(t-1), m [, ul(t-1), dm]
@@ -520,7 +519,7 @@ static const int kNumVariants = 10;
 static int variant_of(const judi_model *M)
 {
     int v = M->ctx->opt_tile;
-    if ((v != 6 && v != 9) || M->r != 4) v = 8;
+    if ((v != 6 && v != 9) || (M->r != 4 && v == 9)) v = 8;
     return v;
 }
 
@@ -665,7 +664,12 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
     JUDI_REQUIRE(s.tmap && s.tmap_prev && s.tmap_m, "tensor maps missing");
     int v = variant_of(M);
     if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2>(M, s); return; }
-    if (M->r == 8) { launch_variant<8, 16, 16, 16, 4, 1>(M, s); return; }
+    if (M->r == 8) {
+        // so = 16: 80 x 32 haloed planes, 16-slot ring, one CTA per SM (0.33 ms/step on the C3
+        // grid; a 64 x 32 tile with a 10-slot ring and 512 consumers was slower: 0.41 ms)
+        launch_variant<8, 16, 16, 16, 4, 1>(M, s);
+        return;
+    }
     switch (v) {
     case 6: launch_variant<4, 16, 16, 8, 4, 2, 2>(M, s); break;          // rotated queue (x9 code)
     case 9: launch_variant<4, 32, 8, 8, 4, 2, 2, false>(M, s); break;   // 128 x 8 tile

@@ -173,6 +173,23 @@ def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_paddin
     return np.float32(host[n].item()), remove_padding(g, model.padsizes, true_adjoint=sum_padding)
 
 
+def forward_modeling(model, shots, born=False, **options):
+    """`F*q` / `J*dm` for a list of source experiments (judiModeling / judiJacobian applied through
+    `run_and_reduce` with no reduction, propagation.jl:23-50): shot i is modelled by rank
+    i mod world_size; returns {shot index: record (nt, nrec)} for this rank's shots -- shot
+    records stay with the worker that made them, there is no collective."""
+    from . import interface
+    dist = _dist()
+    ws = dist.get_world_size() if dist else 1
+    rk = dist.get_rank() if dist else 0
+    out = {}
+    for i in shot_partition(len(shots), ws, rk):
+        sc, q, rc = shots[i][:3]
+        fn = interface.born_rec if born else interface.forward_rec
+        out[i] = fn(model, sc, q, rc, **options)[0]
+    return out
+
+
 def fwi_objective(model, shots, **options):
     """fwi_objective (misfit_fg.jl:143-148): f = sum_i 1/2 dt ||F(m) q_i - d_i||^2 and its
     gradient w.r.t. the squared slowness."""

@@ -127,6 +127,10 @@ def test_fwi_objective_and_options(kind, ndim):
     flo, glo, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True)
     assert abs(float(fl) - float(flo)) <= 1e-4 * abs(float(flo))
     assert rel_l2(gl, glo) < TOL_GRAD
+    # ... and with checkpointing (only the background field is checkpointed / recomputed)
+    flc, glc, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True,
+                                 checkpointing=True)
+    assert flc == fl and np.array_equal(glc, gl)
 
 
 @pytest.mark.parametrize("ndim", [2, 3])
