@@ -318,3 +318,57 @@ def test_extended_and_wavefield_sources(kind, ndim):
     u1, _ = J.forward_wf_src_norec(gm, usrc)
     u1o, _ = O.forward_wf_src_norec(om, usrc)
     assert rel_l2(u1[2:nts - 1], u1o[2:nts - 1]) < TOL_SHOT
+
+
+# ---- BASELINE.json's full sizes: size-independent properties (no oracle run at these sizes) ------
+def _full_size(kind):
+    import judi_jl_b200 as J
+    from bench import velocity, smooth_model, ricker
+    if kind == "iso":
+        n = (401, 401, 201)           # C3 / C4 grid: padded 481 x 481 x 281
+        v = velocity(n)
+        v0 = smooth_model(v)
+        dm = (1 / v ** 2 - 1 / v0 ** 2).astype(np.float32)
+        gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40,
+                     m=(1 / v0 ** 2).astype(np.float32), dm=dm, dt=1.921)
+    else:
+        n = (301, 301, 201)           # C5 grid: padded 381 x 381 x 281
+        v = velocity(n)
+        dm = (0.02 * (v > 2.0) / v ** 2).astype(np.float32)
+        gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32),
+                     epsilon=(0.2 * (v - 1.5) / 4).astype(np.float32),
+                     delta=(0.1 * (v - 1.5) / 4).astype(np.float32),
+                     theta=(np.pi / 6 * (v - 1.5) / 4).astype(np.float32), phi=np.float32(np.pi / 8), dm=dm)
+    ex, ey = (n[0] - 1) * 25., (n[1] - 1) * 25.
+    src = np.array([[0.47 * ex, 0.52 * ey, 50.]], dtype=np.float32)
+    xr, yr = np.meshgrid(np.linspace(0.3 * ex, 0.7 * ex, 41), np.linspace(0.3 * ey, 0.7 * ey, 41), indexing="ij")
+    rec = np.stack([xr.ravel(), yr.ravel(), np.full(xr.size, 62.5)], axis=1).astype(np.float32)
+    nt = 120
+    dt = float(gm.critical_dt)
+    t = np.arange(nt) * dt
+    r = np.pi * 0.025 * (t - 40.)
+    q = ((1 - 2 * r ** 2) * np.exp(-r ** 2)).astype(np.float32).reshape(nt, 1)
+    return J, gm, src, rec, q, dt, dm
+
+
+@pytest.mark.parametrize("kind", ["iso", "tti"])
+def test_full_size_adjoint_and_linearity(kind):
+    """test_adjoint.jl:28-54 / test_linearity.jl:17 on the BASELINE grids (C3 and C5), short time
+    axis: <F q, y> = <q, F' y>, dt <J dm, y> = <dm, J' y>, F(a q) = a F(q), and the gradient is
+    independent of how the snapshots are kept (stored / checkpointed)."""
+    J, gm, src, rec, q, dt, dm = _full_size(kind)
+    d, _ = J.forward_rec(gm, src, q, rec)
+    assert np.isfinite(d).all() and np.linalg.norm(d) > 0
+    y = np.random.default_rng(20261019).standard_normal(d.shape).astype(np.float32)
+    qa, _ = J.forward_rec(gm, rec, y, src, fw=False)
+    a, b = np.vdot(d.astype(np.float64), y), np.vdot(q.astype(np.float64), qa)
+    assert abs((a - b) / (a + b)) < TOL_DOT
+    d2, _ = J.forward_rec(gm, src, (2.5 * q).astype(np.float32), rec)
+    assert rel_l2(d2, 2.5 * d) < 5e-5                        # test_linearity.jl:17 tolerance
+    dl, _ = J.born_rec(gm, src, q, rec)
+    g, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True)
+    dmp = np.pad(dm, gm.padsizes, mode="edge").astype(np.float64)
+    c, e = dt * np.vdot(dl.astype(np.float64), y), np.vdot(g.astype(np.float64), dmp)
+    assert abs((c - e) / (c + e)) < TOL_DOT
+    gc, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True, checkpointing=True)
+    assert np.array_equal(gc, g)
