@@ -95,6 +95,13 @@ typedef struct {
     int snapshot_region; /* JUDI_SNAP_* */
     const float *ws;   /* extended source weights (padded grid) instead of point sources, or NULL:
                           J_adjoint(ws=...) of python_interface.jl:179-198 */
+    /* on-the-fly DFT gradient (J_adjoint_freq, interface.py:348-408): nfreq > 0 replaces the
+     * wavefield snapshots by nfreq complex frequency slices accumulated every dft_sub steps
+     * (fields_exprs.py:140-169) and the imaging condition by sensitivity.py:72-104.
+     * freq_list: host array of nfreq frequencies in kHz. */
+    int nfreq;
+    int dft_sub;       /* DFT time subsampling factor (>= 1) */
+    const float *freq_list;
 } judi_jopts;
 
 /* optional host misfit callback, replaces `misfit=pyjl(runtime_misfit)`

@@ -37,7 +37,8 @@ class JudiJopts(ctypes.Structure):
     _fields_ = [("is_residual", ctypes.c_int), ("checkpointing", ctypes.c_int),
                 ("n_checkpoints", ctypes.c_int), ("t_sub", ctypes.c_int), ("ic", ctypes.c_int),
                 ("born_fwd", ctypes.c_int), ("nlind", ctypes.c_int), ("illum", ctypes.c_int),
-                ("snapshot_region", ctypes.c_int), ("ws", ctypes.c_void_p)]
+                ("snapshot_region", ctypes.c_int), ("ws", ctypes.c_void_p),
+                ("nfreq", ctypes.c_int), ("dft_sub", ctypes.c_int), ("freq_list", ctypes.c_void_p)]
 
 
 MISFIT_FN = ctypes.CFUNCTYPE(ctypes.c_float, c_float_p, c_float_p, c_float_p, ctypes.c_int,

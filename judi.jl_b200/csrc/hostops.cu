@@ -186,3 +186,62 @@ void run_time_resample(judi_ctx *ctx, const float *in, int nt_in, int np, float 
                                    cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
+
+// ---- on-the-fly DFT (fields_exprs.py:140-169, sensitivity.py:72-104) ------------------------------
+// uf layout: [field][freq][re, im][region slot].  cs: [nfreq][2] = (factor cos wt, -factor sin wt).
+__global__ void dft_accum_kernel(Grid g, Region reg, const float *__restrict__ u,
+                                 float *__restrict__ uf, int nfreq, const float *__restrict__ cs)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
+    const long long t = i / reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const float uv = u[g.at(x, y, z)];
+    const long long ri = reg.at(x, y, z);
+    for (int k = 0; k < nfreq; k++) {
+        float *p = uf + (size_t)(2 * k) * reg.slot + ri;
+        p[0] = __fmaf_rn(cs[2 * k], uv, p[0]);
+        p[reg.slot] = __fmaf_rn(cs[2 * k + 1], uv, p[reg.slot]);
+    }
+}
+
+// gradm -= sum_f w_f Re(uf e^{i w t}) v;   wc: [nfreq][2] = (w_f cos wt, -w_f sin wt)
+__global__ void dft_grad_kernel(Grid g, Region reg, const float *__restrict__ v,
+                                const float *__restrict__ uf, int nfreq,
+                                const float *__restrict__ wc, float *__restrict__ grad)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
+    const long long t = i / reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long ri = reg.at(x, y, z);
+    float acc = 0.f;
+    for (int k = 0; k < nfreq; k++) {
+        const float *p = uf + (size_t)(2 * k) * reg.slot + ri;
+        acc = __fmaf_rn(wc[2 * k], p[0], acc);
+        acc = __fmaf_rn(wc[2 * k + 1], p[reg.slot], acc);
+    }
+    grad[ri] = __fmaf_rn(-acc, v[g.at(x, y, z)], grad[ri]);
+}
+
+void dft_accumulate(const judi_model *M, const Region &reg, const float *u, float *uf, int nfreq,
+                    const float *cs_dev)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    dft_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, u, uf, nfreq,
+                                                                              cs_dev);
+    launch_count(M->ctx, "dft_accum");
+}
+
+void dft_gradient(const judi_model *M, const Region &reg, const float *v, const float *uf, int nfreq,
+                  const float *wc_dev, float *grad)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    dft_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, v, uf, nfreq,
+                                                                             wc_dev, grad);
+    launch_count(M->ctx, "dft_grad");
+}

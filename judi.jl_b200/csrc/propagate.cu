@@ -528,6 +528,14 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     bool born = o->born_fwd && M->has_dm;
     const int nf = M->tti ? 2 : 1;
     const int k = o->checkpointing ? 1 : o->t_sub;
+    // on-the-fly DFT (J_adjoint_freq, interface.py:348-408): frequency slices instead of snapshots
+    const bool dft = o->nfreq > 0;
+    const int dfac = std::max(o->dft_sub, 1);
+    if (dft) {
+        JUDI_REQUIRE(o->freq_list != nullptr, "freq_list is NULL");
+        JUDI_REQUIRE(o->ic == JUDI_IC_AS, "DFT gradients are implemented for the 'as' imaging condition");
+        JUDI_REQUIRE(!o->checkpointing, "DFT gradients do not use checkpointing");
+    }
     // ISIC/FWI differentiate the snapshot: it must cover the whole padded grid
     const Region reg = (o->snapshot_region == JUDI_SNAP_PHYSICAL && o->ic == JUDI_IC_AS)
                            ? M->phys : M->full;
@@ -559,7 +567,9 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     int seg = 0, nseg = 0;          // checkpointing: segment length / count
     int nslots;
     std::vector<DevBuf> ckpt;       // per segment: level t and level t-1 of every field
-    if (!o->checkpointing) {
+    if (dft) {
+        nslots = 0;
+    } else if (!o->checkpointing) {
         nslots = num_slots(nt, k);
     } else {
         // fixed-stride checkpoints + segment recompute: memory ~ seg snapshots + (nt/seg) states;
@@ -579,7 +589,8 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
         double avail = (double)free_b + (double)(reserved - used);
         double need = (double)nslots * slot_floats * 4.0 +
-                      (double)nseg * 2.0 * nf * (double)M->g.nalloc * 4.0;
+                      (double)nseg * 2.0 * nf * (double)M->g.nalloc * 4.0 +
+                      (dft ? 2.0 * o->nfreq * slot_floats * 4.0 : 0.0);
         if (need > 0.97 * avail) {
             char b[256];
             snprintf(b, sizeof(b),
@@ -591,6 +602,30 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     }
     DevBuf snaps(ctx, (size_t)nslots * slot_floats, false);
     auto slot_ptr = [&](int s, int f) { return snaps.p + ((size_t)s * nf + f) * reg.slot; };
+    // DFT: uf[field][freq][re,im] on the region, and per-step phase tables
+    //   forward  (fields_exprs.py:164-167): uf += factor exp(-i w t) u[t]        when t % factor == 0
+    //   gradient (sensitivity.py:94-103):   gradm -= w_f Re(uf exp(i w t)) v[t],  w_f = -(2 pi f)^2 / time_M
+    DevBuf uf, cs_tab, wc_tab;
+    const int ndft = dft ? (nt / dfac + 1) : 0;
+    if (dft) {
+        uf = DevBuf(ctx, (size_t)2 * o->nfreq * slot_floats, true);
+        std::vector<float> cs((size_t)ndft * 2 * o->nfreq), wc(cs.size());
+        for (int j = 0; j < ndft; j++)
+            for (int q_ = 0; q_ < o->nfreq; q_++) {
+                const double f = (double)o->freq_list[q_];
+                const double wt = 2.0 * M_PI * f * (double)(j * dfac) * (double)M->dt;
+                const double w = -(2.0 * M_PI * f) * (2.0 * M_PI * f) / (double)(nt - 2);
+                cs[((size_t)j * o->nfreq + q_) * 2] = (float)((double)dfac * std::cos(wt));
+                cs[((size_t)j * o->nfreq + q_) * 2 + 1] = (float)(-(double)dfac * std::sin(wt));
+                wc[((size_t)j * o->nfreq + q_) * 2] = (float)(w * std::cos(wt));
+                wc[((size_t)j * o->nfreq + q_) * 2 + 1] = (float)(-w * std::sin(wt));
+            }
+        cs_tab = DevBuf(ctx, cs.size(), false);
+        cs_tab.upload(cs);
+        wc_tab = DevBuf(ctx, wc.size(), false);
+        wc_tab.upload(wc);
+    }
+    auto uf_ptr = [&](int f) { return uf.p + (size_t)f * 2 * o->nfreq * reg.slot; };
 
     pc.mark("setup (sparse, traces, alloc)");
     Fuse fsave = no_fuse();
@@ -612,7 +647,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     // A range of forward steps.  mode 0: no snapshots; 1: slot t/k when t % k == 0; 2: slot t-base
     // (segment recomputation).  2-D constant-density models run the whole range inside one
     // persistent kernel (persist2d.cu), everything else steps kernel by kernel.
-    const bool p2 = persist2d_supported(M, o->ic) && !sh.ext_active();
+    const bool p2 = persist2d_supported(M, o->ic) && !sh.ext_active() && !dft;
     auto fwd_range = [&](int ta, int tb, int mode, int base, bool record) {
         if (tb < ta) return;
         if (p2) {
@@ -632,12 +667,17 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         }
         for (int t = ta; t <= tb; t++) {
             int slot = mode == 1 ? ((t % k) == 0 ? t / k : -1) : (mode == 2 ? t - base : -1);
+            if (dft) slot = -1;
             if (record) fwd_step(t, slot);
             else {
                 Fuse f = fsave;
                 for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot >= 0 ? slot_ptr(slot, ff) : nullptr;
                 sh.step_plain(W, t, &f, pSrc, &q, nullptr, nullptr, nullptr);
             }
+            if (dft && (t % dfac) == 0)   // level t sits in the "other" buffer after the swap
+                for (int ff = 0; ff < nf; ff++)
+                    dft_accumulate(M, reg, W.other(ff), uf_ptr(ff), o->nfreq,
+                                   cs_tab.p + (size_t)(t / dfac) * 2 * o->nfreq);
         }
     };
     if (!o->checkpointing) {
@@ -740,8 +780,13 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             persist2d_run(M, V, nullptr, ta, tb, -1, &S_rec, &rec, nullptr, nullptr, nullptr, pf);
             return;
         }
-        for (int t = ta; t >= tb; t--)
-            adj_step(t, mode == 1 ? ((t % k) == 0 ? t / k : -1) : t - base);
+        for (int t = ta; t >= tb; t--) {
+            adj_step(t, dft ? -1 : (mode == 1 ? ((t % k) == 0 ? t / k : -1) : t - base));
+            if (dft && (t % dfac) == 0)
+                for (int ff = 0; ff < nf; ff++)
+                    dft_gradient(M, reg, V.other(ff), uf_ptr(ff), o->nfreq,
+                                 wc_tab.p + (size_t)(t / dfac) * 2 * o->nfreq, grad.p);
+        }
     };
     if (!o->checkpointing) {
         adj_range(nt - 2, 1, 1, 0);

@@ -80,3 +80,7 @@ void run_remove_padding(const judi_model *M, const float *padded, int true_adjoi
                         int flags);
 void run_time_resample(judi_ctx *ctx, const float *in, int nt_in, int np, float t0_in, float dt_in,
                        float *out, int nt_out, float t0_out, float dt_out, int flags);
+void dft_accumulate(const judi_model *M, const Region &reg, const float *u, float *uf, int nfreq,
+                    const float *cs_dev);
+void dft_gradient(const judi_model *M, const Region &reg, const float *v, const float *uf, int nfreq,
+                  const float *wc_dev, float *grad);

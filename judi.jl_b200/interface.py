@@ -9,8 +9,7 @@ uses, so the `ccall` twin of these wrappers needs no copies.  When the wavelet /
 CUDA tensors (given time-fastest: contiguous (ntrace, nt)) everything stays in HBM and the
 results are written into the caller's `*_out` device tensors.
 
-Out of this backend's scope (raise NotImplementedError): on-the-fly DFT (`freq_list`) and
-`wri_func`.
+Out of this backend's scope (raise NotImplementedError): `wri_func`.
 """
 import ctypes
 import numpy as np
@@ -134,8 +133,6 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     `snapshot_region` ('padded' = reference semantics | 'physical'), and for device-resident
     runs `grad_out`, `f_out`, `illum_out=(Iu, Iv)`, `accumulate`.
     """
-    if freq_list is not None and len(freq_list) > 0:
-        raise NotImplementedError("on-the-fly DFT gradients are out of the B200 backend's scope")
     if not fw:
         raise NotImplementedError("J_adjoint with fw=False")
     dev = is_device_tensor(wavelet)
@@ -153,6 +150,13 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     o.illum = int(bool(illum))
     o.snapshot_region = L.SNAP_PHYSICAL if snapshot_region == "physical" else L.SNAP_PADDED
     o.ws = _ptr(wsp)
+    freqs = None
+    if freq_list is not None and len(freq_list) > 0:
+        # J_adjoint_freq (interface.py:348-408): frequencies in kHz, dft_sub in time steps
+        freqs = np.ascontiguousarray(freq_list, dtype=np.float32)
+        o.nfreq = int(freqs.size)
+        o.dft_sub = int(dft_sub) if dft_sub else 1
+        o.freq_list = freqs.ctypes.data
     flags = (L.DATA_ON_DEVICE if dev else 0) | (L.GRAD_ACCUMULATE if accumulate else 0)
     Iu = Iv = None
     if dev:

@@ -46,7 +46,8 @@ class Options(object):
 
     def __init__(self, space_order=8, free_surface=False, limit_m=False, buffer_size=1000.0,
                  optimal_checkpointing=False, subsampling_factor=1, sum_padding=False,
-                 dt_comp=None, IC="as", f0=0.015, snapshot_region="padded", nbl=40):
+                 dt_comp=None, IC="as", f0=0.015, snapshot_region="padded", nbl=40,
+                 frequencies=(), dft_subsampling_factor=1):
         self.space_order = space_order
         self.free_surface = free_surface
         self.limit_m = limit_m
@@ -59,6 +60,8 @@ class Options(object):
         self.f0 = f0
         self.snapshot_region = snapshot_region
         self.nbl = nbl
+        self.frequencies = list(frequencies)          # kHz; non-empty selects on-the-fly DFT
+        self.dft_subsampling_factor = dft_subsampling_factor
 
 
 # ---- time_resample ---------------------------------------------------------------------------
@@ -211,6 +214,8 @@ def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, 
         g, _, _ = interface.J_adjoint(model, sc, q_in[:nt], rc, d_in[:nt], is_residual=True,
                                       t_sub=o.subsampling_factor,
                                       checkpointing=o.optimal_checkpointing, ic=o.IC, f0=o.f0,
+                                      freq_list=o.frequencies or None,
+                                      dft_sub=o.dft_subsampling_factor,
                                       snapshot_region=o.snapshot_region)
         g = remove_padding(g, model, true_adjoint=o.sum_padding)
         if o.limit_m and tuple(shape) != full_shape:

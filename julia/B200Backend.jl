@@ -33,6 +33,7 @@ struct JudiJopts           # judi_jopts
     is_residual::Cint; checkpointing::Cint; n_checkpoints::Cint; t_sub::Cint; ic::Cint
     born_fwd::Cint; nlind::Cint; illum::Cint; snapshot_region::Cint
     ws::Ptr{Cfloat}        # extended-source weights on the padded grid, or C_NULL
+    nfreq::Cint; dft_sub::Cint; freq_list::Ptr{Cfloat}   # on-the-fly DFT (options.frequencies)
 end
 
 lasterr() = unsafe_string(ccall((:judi_last_error, LIB), Cstring, ()))
@@ -102,11 +103,14 @@ function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOption
                         is_residual=false, born_fwd=false, nlind=false, illum=false, misfit=nothing,
                         ws=nothing)
     nt = size(qIn, 1)
+    freqs = Float32.(options.frequencies)                     # python_interface.jl:112
     g = zeros(Float32, padded_shape(h, length(n))); f = Ref{Cfloat}(0)
     Iu = illum ? similar(g) : nothing; Iv = illum ? similar(g) : nothing
     o = JudiJopts(is_residual, options.optimal_checkpointing, 0, options.subsampling_factor,
                   IC[options.IC], born_fwd, nlind, illum, options.sum_padding ? 0 : 1,
-                  ws === nothing ? Ptr{Cfloat}(C_NULL) : pointer(ws))
+                  ws === nothing ? Ptr{Cfloat}(C_NULL) : pointer(ws),
+                  length(freqs), options.dft_subsampling_factor[1],
+                  isempty(freqs) ? Ptr{Cfloat}(C_NULL) : pointer(freqs))
     # custom misfit: judi_misfit_fn; the default mse (losses.jl:15-19) stays on the device (C_NULL)
     cb = misfit === nothing ? C_NULL :
         @cfunction($((ps, po, pr, nt_, nr_, _) -> begin

@@ -12,6 +12,7 @@ The classes/functions below restate, with the same names and argument meaning, t
   forward_rec / born_rec / J_adjoint / J_adjoint_standard / J_adjoint_checkpointing
                               interface.py:17-47, 208-241, 279-345, 411-470, 473-562
   Loss                 sensitivity.py:236-276
+  J_adjoint_freq       interface.py:348-408, fields_exprs.py:140-169, sensitivity.py:72-104
   remove_padding / pad_array  src/TimeModeling/Utils/auxiliaryFunctions.jl:52-89
   ricker_wavelet       src/TimeModeling/Utils/auxiliaryFunctions.jl:205-213
   time_resample        src/TimeModeling/Utils/time_utilities.jl:32-48, 84
@@ -580,6 +581,42 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     if return_obj:
         return f, g, Iu, Iv
     return g, Iu, Iv
+
+
+def J_adjoint_freq(model, src_coords, wavelet, rec_coords, recin, freq_list, dft_sub=None,
+                   is_residual=False, return_obj=False, born_fwd=False, nlind=False, misfit=None):
+    """interface.py:348-408 (on-the-fly DFT gradient), evaluated from the stored wavefield
+    histories instead of on the fly (small cases only):
+      forward  fields_exprs.py:140-169:  uf[f] = sum_{t=1, t % factor == 0}^{nt-2}
+                                                 factor * exp(-i 2 pi f t dt) * u[t]
+      gradient sensitivity.py:72-104:    gradm -= w_f * Re(uf[f] exp(i 2 pi f t dt)) * v[t] for
+               t = nt-2 .. 1 with t % factor == 0, w_f = -(2 pi f)^2 / time_M, time_M = nt - 2;
+               summed over frequencies and over the field pairs (u_i, v_i) of TTI.
+    The complex product is stored into the real `gradm`, i.e. its real part is kept."""
+    factor = int(dft_sub) if dft_sub else 1
+    nt = wavelet.shape[0]
+    if born_fwd:
+        rec, u, _ = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind)
+    else:
+        rec, u, _ = forward(model, src_coords, rec_coords, wavelet, save=True)
+    f, residual = Loss(rec, recin, float(model.critical_dt), is_residual=is_residual,
+                       misfit=misfit)
+    _, v, _ = forward(model, rec_coords, None, residual, save=True, fw=False)
+    dt = float(model.critical_dt)
+    freqs = np.asarray(freq_list, dtype=np.float64)
+    ts = np.array([t for t in range(1, nt - 1) if t % factor == 0], dtype=np.int64)
+    g = np.zeros(model.shape_pml, dtype=np.float64)
+    for fk in freqs:
+        ph = np.exp(-1j * 2 * np.pi * fk * ts * dt)
+        w = -(2 * np.pi * fk) ** 2 / (nt - 2)
+        for fld in range(model.nfields):
+            uf = factor * np.tensordot(ph, u[ts, fld].astype(np.float64), axes=(0, 0))
+            g -= w * np.tensordot(np.conj(ph), v[ts, fld].astype(np.float64), axes=(0, 0)).real * uf.real \
+                - w * np.tensordot(np.conj(ph), v[ts, fld].astype(np.float64), axes=(0, 0)).imag * uf.imag
+    g = g.astype(model.lib._dtype)
+    if return_obj:
+        return f, g
+    return g
 
 
 def set_fast(on, precision="f32"):
