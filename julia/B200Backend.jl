@@ -117,7 +117,7 @@ function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOption
             dsyn = unsafe_wrap(Array, ps, (Int(nt_), Int(nr_))); dobs = unsafe_wrap(Array, po, (Int(nt_), Int(nr_)))
             fv, r = misfit(dsyn, dobs); copyto!(unsafe_wrap(Array, pr, (Int(nt_), Int(nr_))), r); Cfloat(fv)
         end), Cfloat, (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cvoid}))
-    check(ccall((:judi_J_adjoint, LIB), Cint,
+    GC.@preserve freqs ws check(ccall((:judi_J_adjoint, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ref{JudiJopts},
                  Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
                 h, size(src_coords, 1), src_coords, qIn, nt, size(rec_coords, 1), rec_coords, dIn, o,
