@@ -142,6 +142,7 @@ struct judi_ctx {
     int opt_flux_block = 32 | (4 << 8) | (1 << 16);  // thread block of the 3-D flux kernels
     int opt_flux_minb = 8;      // tuning: occupancy target of the 3-D TTI flux kernels (8: 64 registers)
     int opt_flux_slab = 0;      // 3-D flux kernels: z planes per pass-1 / pass-2 slab (0: whole grid)
+    int opt_tti_fused = 0;      // 3-D TTI so=8: experimental single-pass kernel (tti3d.cu; slower)
     int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel

@@ -306,6 +306,9 @@ bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
 bool tma3d_step_born(const judi_model *M, const StepArgs &a);
 bool flux3d_step(const judi_model *M, const StepArgs &s);
+bool tti3d_supported(const judi_model *M);
+void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
+bool tti3d_step(const judi_model *M, const StepArgs &s);
 
 void Wavefield::init(const judi_model *M, bool born_scratch)
 {
@@ -329,6 +332,11 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
             for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
         tma3d_encode(M, M->m.p, nullptr, &tmap_m);
         if (M->dm.p) tma3d_encode(M, M->dm.p, nullptr, &tmap_dm);
+        has_tmap = true;
+    } else if (tti3d_supported(M)) {
+        for (int f = 0; f < nf; f++)
+            for (int s = 0; s < 2; s++) tti3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
+        tti3d_encode(M, M->m.p, nullptr, &tmap_m);
         has_tmap = true;
     }
 }
@@ -492,6 +500,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.qsrc = s.scratch->dd[0].p;
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
+    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && tti3d_step(M, s)) { /* single pass */ }
     else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && flux3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);

@@ -23,62 +23,7 @@
 //  Algorithmic HBM traffic: 16 B per grid-point update (u(t), u(t-1), m read; u(t+1) written).
 #include "common.cuh"
 
-// ---- PTX helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1,
-                                            int c2, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-        "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
+#include "tma_util.cuh"
 
 // ---- kernel ------------------------------------------------------------------------------
 struct TmaArgs {
@@ -529,7 +474,7 @@ bool tma3d_supported(const judi_model *M)
            M->ctx->encode_tiled != nullptr;
 }
 
-static void encode_box(const judi_model *M, const float *base, int bx, int by, CUtensorMap *out)
+void tma_encode_box(const judi_model *M, const float *base, int bx, int by, CUtensorMap *out)
 {
     const Grid &g = M->g;
     cuuint64_t dims[3] = {(cuuint64_t)g.px, (cuuint64_t)g.py, (cuuint64_t)g.pz};
@@ -553,8 +498,8 @@ void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map,
     int v = variant_of(M);
     int R = M->r, HR = ((R + 3) / 4) * 4;
     int tx = 4 * kVariants[v].txt, ty = kVariants[v].tyt;
-    if (halo_map) encode_box(M, base, tx + 2 * HR, ty + 2 * R, halo_map);
-    if (tile_map) encode_box(M, base, tx, ty, tile_map);
+    if (halo_map) tma_encode_box(M, base, tx + 2 * HR, ty + 2 * R, halo_map);
+    if (tile_map) tma_encode_box(M, base, tx, ty, tile_map);
 }
 
 template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW, bool ROT, int FUSE,
