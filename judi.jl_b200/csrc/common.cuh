@@ -142,6 +142,7 @@ struct judi_ctx {
     int opt_flux_block = 32 | (4 << 8) | (1 << 16);  // thread block of the 3-D flux kernels
     int opt_flux_minb = 8;      // tuning: occupancy target of the 3-D TTI flux kernels (8: 64 registers)
     int opt_flux_slab = 0;      // 3-D flux kernels: z planes per pass-1 / pass-2 slab (0: whole grid)
+    int opt_varc_fused = 1;     // 3-D variable density so=8: single-pass kernel (0: two passes)
     int opt_tti_fused = 0;      // 3-D TTI so=8: experimental single-pass kernel (tti3d.cu; slower)
     int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
@@ -287,7 +288,10 @@ struct Wavefield {
     CUtensorMap tmap_tile[2][2];  // [field][slot]: tile box
     CUtensorMap tmap_m;           // tile box over the model's m
     CUtensorMap tmap_dm;          // tile box over the model's dm (Born)
+    CUtensorMap tmap_coef;        // variable density: haloed box over irho ...
+    CUtensorMap tmap_irho;        // ... and its tile box
     bool has_tmap = false;
+    bool two_pass_only = false;   // flux-form physics: never take the single-pass kernels
     void init(const judi_model *M, bool born_scratch);
     void swap() { cur = 1 - cur; }
     float *level(int f) { return b[f][cur].p; }

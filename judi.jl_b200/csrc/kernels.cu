@@ -309,6 +309,10 @@ bool flux3d_step(const judi_model *M, const StepArgs &s);
 bool tti3d_supported(const judi_model *M);
 void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tti3d_step(const judi_model *M, const StepArgs &s);
+bool varc3d_supported(const judi_model *M);
+void varc3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
+void varc3d_encode_coef(const judi_model *M, const float *base, CUtensorMap *map);
+bool varc3d_step(const judi_model *M, const StepArgs &s);
 
 void Wavefield::init(const judi_model *M, bool born_scratch)
 {
@@ -332,6 +336,12 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
             for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
         tma3d_encode(M, M->m.p, nullptr, &tmap_m);
         if (M->dm.p) tma3d_encode(M, M->dm.p, nullptr, &tmap_dm);
+        has_tmap = true;
+    } else if (varc3d_supported(M)) {
+        for (int s = 0; s < 2; s++) varc3d_encode(M, b[0][s].p, &tmap_halo[0][s], &tmap_tile[0][s]);
+        varc3d_encode(M, M->m.p, nullptr, &tmap_m);
+        varc3d_encode(M, M->irho.p, nullptr, &tmap_irho);
+        varc3d_encode_coef(M, M->irho.p, &tmap_coef);
         has_tmap = true;
     } else if (tti3d_supported(M)) {
         for (int f = 0; f < nf; f++)
@@ -500,7 +510,8 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.qsrc = s.scratch->dd[0].p;
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
-    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && tti3d_step(M, s)) { /* single pass */ }
+    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->two_pass_only) &&
+             (tti3d_step(M, s) || varc3d_step(M, s))) { /* single pass */ }
     else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && flux3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);

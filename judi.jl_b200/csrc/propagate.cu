@@ -558,6 +558,10 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     Wavefield W, WL;
     W.init(M, born);
     if (born) WL.init(M, false);
+    // Checkpointing recomputes the background field with plain steps and must reproduce the Born
+    // forward sweep bit for bit; Born steps the flux-form physics (TTI, variable density) with
+    // the two-pass kernels, so every step of this wavefield does.
+    W.two_pass_only = born;
     DevBuf Iu, Iv, grad(ctx, (size_t)reg.slot, true);
     if (illum_u) Iu = DevBuf(ctx, (size_t)reg.slot, true);
     if (illum_v) Iv = DevBuf(ctx, (size_t)reg.slot, true);
