@@ -143,7 +143,7 @@ struct judi_ctx {
     int opt_flux_minb = 8;      // tuning: occupancy target of the 3-D TTI flux kernels (8: 64 registers)
     int opt_flux_slab = 0;      // 3-D flux kernels: z planes per pass-1 / pass-2 slab (0: whole grid)
     int opt_varc_fused = 1;     // 3-D variable density so=8: single-pass kernel (0: two passes)
-    int opt_tti_fused = 0;      // 3-D TTI so=8: experimental single-pass kernel (tti3d.cu; slower)
+    int opt_tti_fused = 1;      // 3-D TTI so=8: single-pass kernel (tti3d.cu); 2: shifted-queue variant; 0: two passes
     int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
@@ -202,6 +202,7 @@ struct judi_model {
     float irho_c = 1.f;
     DevBuf m, irho, eps, delta, theta, phi, dm;  // fields on `g` (edge-replicated into halo)
     DevBuf r3[3];                // 3-D TTI: symmetry axis (sin th cos ph, sin th sin ph, cos th)
+    DevBuf ttiABC[3];            // 3-D TTI, constant density: A0 = b delta~, B0 = b sqrt((eps~-delta~) delta~), C0 = b (eps~-delta~)
     DevBuf damp[3];              // 1-D damping profiles per dimension (value of `damp`)
     std::vector<float> damp_h[3];
     Region phys, full;
@@ -290,6 +291,7 @@ struct Wavefield {
     CUtensorMap tmap_dm;          // tile box over the model's dm (Born)
     CUtensorMap tmap_coef;        // variable density: haloed box over irho ...
     CUtensorMap tmap_irho;        // ... and its tile box
+    CUtensorMap tmap_par[6];      // 3-D TTI single pass: parameter planes A0, B0, C0, r
     bool has_tmap = false;
     bool two_pass_only = false;   // flux-form physics: never take the single-pass kernels
     void init(const judi_model *M, bool born_scratch);

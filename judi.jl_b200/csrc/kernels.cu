@@ -308,6 +308,7 @@ bool tma3d_step_born(const judi_model *M, const StepArgs &a);
 bool flux3d_step(const judi_model *M, const StepArgs &s);
 bool tti3d_supported(const judi_model *M);
 void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
+void tti3d_encode_coef(const judi_model *M, CUtensorMap *maps);
 bool tti3d_step(const judi_model *M, const StepArgs &s);
 bool varc3d_supported(const judi_model *M);
 void varc3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
@@ -347,6 +348,7 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         for (int f = 0; f < nf; f++)
             for (int s = 0; s < 2; s++) tti3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
         tti3d_encode(M, M->m.p, nullptr, &tmap_m);
+        tti3d_encode_coef(M, tmap_par);
         has_tmap = true;
     }
 }

@@ -258,6 +258,21 @@ __global__ void tti_axis_kernel(const float *__restrict__ theta, const float *__
     rz[i] = ct;
 }
 
+// point-wise TTI coefficients of the closed-form rotation (flux3d.cu), constant density b:
+// the same fp32 expressions the two-pass kernel evaluates per node and step
+__global__ void tti_abc_kernel(const float *__restrict__ eps, const float *__restrict__ delta, float b,
+                               long long n, float *__restrict__ A0, float *__restrict__ B0,
+                               float *__restrict__ C0)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float e = eps[i], d = delta[i];
+    const float emd = __fsub_rn(e, d);
+    A0[i] = __fmul_rn(b, d);
+    B0[i] = __fmul_rn(b, sqrtf(__fmul_rn(emd, d)));
+    C0[i] = __fmul_rn(b, emd);
+}
+
 void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
 {
     JUDI_REQUIRE(desc->ndim == 2 || desc->ndim == 3, "ndim must be 2 or 3");
@@ -342,6 +357,12 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
             tti_axis_kernel<<<nb, 256, 0, ctx->stream>>>(M->theta.p, M->phi.p, M->g.nalloc,
                                                          M->r3[0].p, M->r3[1].p, M->r3[2].p);
             launch_count(ctx, "tti_axis");
+            if (!M->irho_field && M->so == 8) {
+                for (int d = 0; d < 3; d++) M->ttiABC[d] = DevBuf(ctx, (size_t)M->g.nalloc, false);
+                tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c, M->g.nalloc,
+                                                            M->ttiABC[0].p, M->ttiABC[1].p, M->ttiABC[2].p);
+                launch_count(ctx, "tti_abc");
+            }
         }
         if (M->tti && !M->irho_field) {
             // the flux-form kernels read irho as a field
