@@ -143,7 +143,7 @@ struct judi_ctx {
     int opt_flux_minb = 8;      // tuning: occupancy target of the 3-D TTI flux kernels (8: 64 registers)
     int opt_flux_slab = 0;      // 3-D flux kernels: z planes per pass-1 / pass-2 slab (0: whole grid)
     int opt_varc_fused = 1;     // 3-D variable density so=8: single-pass kernel (0: two passes)
-    int opt_tti_fused = 1;      // 3-D TTI so=8: single-pass kernel (tti3d.cu); 2: shifted-queue variant; 0: two passes
+    int opt_tti_fused = 2;      // 3-D TTI so=8: single-pass kernel (tti3d.cu), 2: shifted queues, 1: rotated; 0: two passes
     int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel

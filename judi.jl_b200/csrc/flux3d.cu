@@ -347,14 +347,14 @@ bool flux3d_step(const judi_model *M, const StepArgs &s)
 {
     Wavefield *W = s.scratch;
     JUDI_REQUIRE(W != nullptr, "flux scratch not bound");
+    // isic / fwi imaging conditions and Born sources live in the generic kernels (kernels.cu)
+    if ((s.f.grad && s.f.ic != JUDI_IC_AS) || (s.born && s.born_ic != JUDI_IC_AS)) return false;
     auto run = [&](auto rtag) {
         constexpr int R = decltype(rtag)::value;
         if (!s.born) {
             flux3d_one<R>(M, W, s.u, s.up, nullptr, nullptr, s.f, s.qext, s.qext_scale);
             return;
         }
-        JUDI_REQUIRE(s.born_ic == JUDI_IC_AS,
-                     "isic/fwi Born sources are only implemented for constant-density acoustics");
         float *dd[2] = {W->dd[0].p, W->dd[1].p};
         const float *ddc[2] = {W->dd[0].p, W->dd[1].p};
         flux3d_one<R>(M, W, s.u, s.up, dd, nullptr, s.f, s.qext, s.qext_scale);

@@ -115,6 +115,27 @@ __device__ float lap_weighted(const Grid &g, const Coefs &cf, const float *__res
     return acc;
 }
 
+// the same with the node-valued coefficient c = c1 * c2 (dm * irho as fields: variable density, TTI)
+template <int NDIM, int R>
+__device__ float lap_weighted2(const Grid &g, const Coefs &cf, const float *__restrict__ u,
+                               const float *__restrict__ c1, const float *__restrict__ c2, long long i)
+{
+    float acc = 0.f;
+    const long long st[3] = {1, g.sy, g.sz};
+    const float *ws[3] = {cf.wx, cf.wy, cf.wz};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        if (d == 1 && NDIM == 2) continue;
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            long long ip = i + (k - 1) * st[d], im = i - k * st[d];
+            acc += ws[d][k] * (c1[ip] * c2[ip] * dplus<R>(u, ip, st[d], ws[d]) -
+                               c1[im] * c2[im] * dplus<R>(u, im, st[d], ws[d]));
+        }
+    }
+    return acc;
+}
+
 template <int NDIM, int R>
 __global__ void __launch_bounds__(256) acoustic_generic(AcArgs a)
 {
@@ -250,6 +271,8 @@ struct FluxUpdArgs {
     const float *dd_in[2];   // read delta of the background field (linearised pass of Born)
     const float *qext;       // extended / wavefield source, fed to every field
     float qext_scale;
+    int born_ic;             // imaging condition of the Born source (linearised pass)
+    const float *ub[2];      // isic / fwi Born source: background field(s), level t
     Fuse f;
 };
 
@@ -278,7 +301,16 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
         float upv = a.up[f][i];
         float d1 = uc[f] - upv;
         float q = 0.f;
-        if (a.dd_in[f]) q = -a.dm[i] * ir * a.dd_in[f][i];  // dt^2 * lin_src ("as")
+        if (a.dd_in[f]) {
+            // dt^2 * lin_src: "as" -dm irho u.dt2; isic / fwi -(dm irho u.dt2 m -+ laplacian(u, dm irho))
+            // (sensitivity.py:174-209)
+            if (a.born_ic == JUDI_IC_AS) q = -a.dm[i] * ir * a.dd_in[f][i];
+            else {
+                float ics = a.born_ic == JUDI_IC_FWI ? -1.f : 1.f;
+                q = -(a.dm[i] * ir * mm * a.dd_in[f][i] -
+                      ics * cf.dt2 * lap_weighted2<NDIM, R>(g, cf, a.ub[f], a.dm, a.irho, i));
+            }
+        }
         if (a.qext) q += a.qext_scale * a.qext[i];
         delta[f] = (cf.dt2 * L + q - sd * d1) * rden;
         a.up[f][i] = (uc[f] + d1) + delta[f];
@@ -293,7 +325,15 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
         for (int f = 0; f < NF; f++) {
             if (fz.snap[f]) fz.snap[f][ri] = uc[f];
             e2 += uc[f] * uc[f];
-            if (fz.grad) ic += fz.usnap[f][ri] * delta[f];
+            if (fz.grad) {
+                if (fz.ic == JUDI_IC_AS) ic += fz.usnap[f][ri] * delta[f];
+                else {
+                    // isic / fwi (sensitivity.py:106-122): u v.dt2 m +- grad u . grad v per field
+                    float ics = fz.ic == JUDI_IC_FWI ? -1.f : 1.f;
+                    float ig = inner_grad_snap<NDIM, R>(g, cf, fz.reg, fz.usnap[f], a.u[f], x, y, z);
+                    ic += fz.usnap[f][ri] * delta[f] * mm + ics * cf.dt2 * ig;
+                }
+            }
         }
         if (fz.illum) fz.illum[ri] += cf.dt * e2;
         if (fz.grad) fz.grad[ri] -= fz.gcoef * ir * ic;
@@ -381,7 +421,8 @@ static void launch_acoustic_generic(const judi_model *M, const StepArgs &s)
 template <int NDIM, int R>
 static void flux_one(const judi_model *M, Wavefield *W, const float *const *u, float *const *up,
                      float *const *dd_out, const float *const *dd_in, const Fuse &fuse,
-                     const float *qext = nullptr, float qext_scale = 0.f)
+                     const float *qext = nullptr, float qext_scale = 0.f, int born_ic = JUDI_IC_AS,
+                     const float *const *ub = nullptr)
 {
     judi_ctx *ctx = M->ctx;
     int nf = M->tti ? 2 : 1;
@@ -406,7 +447,9 @@ static void flux_one(const judi_model *M, Wavefield *W, const float *const *u, f
         ua.u[f] = u[f]; ua.up[f] = up[f];
         ua.dd_out[f] = dd_out ? dd_out[f] : nullptr;
         ua.dd_in[f] = dd_in ? dd_in[f] : nullptr;
+        ua.ub[f] = ub ? ub[f] : nullptr;
     }
+    ua.born_ic = born_ic;
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
     ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p;
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;
@@ -429,14 +472,13 @@ static void step_flux(const judi_model *M, const StepArgs &s)
         flux_one<NDIM, R>(M, W, s.u, s.up, nullptr, nullptr, s.f, s.qext, s.qext_scale);
         return;
     }
-    JUDI_REQUIRE(s.born_ic == JUDI_IC_AS,
-                 "isic/fwi Born sources are only implemented for constant-density acoustics");
     float *dd[2] = {W->dd[0].p, W->dd[1].p};
     const float *ddc[2] = {W->dd[0].p, W->dd[1].p};
     flux_one<NDIM, R>(M, W, s.u, s.up, dd, nullptr, s.f, s.qext, s.qext_scale);
     Fuse none;
     memset(&none, 0, sizeof(none));
-    flux_one<NDIM, R>(M, W, s.ul, s.ulp, nullptr, ddc, none);
+    // the background pass wrote level t+1 over level t-1: s.u still holds level t
+    flux_one<NDIM, R>(M, W, s.ul, s.ulp, nullptr, ddc, none, nullptr, 0.f, s.born_ic, s.u);
 }
 
 template <int NDIM>

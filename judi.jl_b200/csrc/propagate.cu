@@ -522,9 +522,6 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     JUDI_REQUIRE(o->t_sub >= 1, "t_sub must be >= 1");
     JUDI_REQUIRE(!(o->nlind && !o->born_fwd), "nlind requires born_fwd");
     JUDI_REQUIRE(o->ic >= JUDI_IC_AS && o->ic <= JUDI_IC_FWI, "unknown imaging condition");
-    bool flux = M->tti || M->irho_field;
-    JUDI_REQUIRE(o->ic == JUDI_IC_AS || !flux,
-                 "isic/fwi imaging conditions are only implemented for constant-density acoustics");
     bool born = o->born_fwd && M->has_dm;
     const int nf = M->tti ? 2 : 1;
     const int k = o->checkpointing ? 1 : o->t_sub;

@@ -7,28 +7,43 @@
 //   H0 = sum_d D-_d P_d,  H1 = sum_d D-_d M_d,   (P, M) = R^T [[A,B],[B,C]] R (G u1, G u2)
 //
 // needs the flux one stencil radius around every output point, and every flux node needs the full
-// staggered gradient of both fields.  One CTA owns a 32 x 16 (x,y) tile and marches along z.
-// Everything it reads arrives by TMA (one producer warp, three mbarrier rings): the haloed planes
-// of u1, u2 (48 x 30), the six parameter planes A0, B0, C0, r (40 x 23, precomputed per model) and
-// the tiles of u1(t-1), u2(t-1), m.  216 flux threads, one per group of 4 x-points of the
-// plus-shaped region (tile 128 + x halo 32 + y halo 56), keep the z-lines of u1, u2 of their own
-// column in register queues, take the x/y lines from the shared plane and evaluate the closed-form
-// rotation (flux3d.cu).  Halo threads publish P_x, M_x / P_y, M_y in a double-buffered shared
-// plane; after ONE named barrier per plane the 128 tile threads add D-_x + D-_y of both fields to
-// the divergence accumulator of that plane.  The z part never touches memory: a tile thread
-// scatters its own P_z, M_z into the 8 register accumulators of the output planes zf-3 .. zf+4, so
-// plane zf-3 is complete when flux plane zf is, and is updated in place (+ fused snapshot save /
-// imaging condition / illumination).
+// staggered gradient of both fields.  One CTA (12 warps) owns a 32 x 16 (x,y) tile and marches
+// along z.  Everything it reads arrives by TMA (one producer warp, three mbarrier rings): the
+// haloed planes of u1, u2 (48 x 30), the six parameter planes A0, B0, C0, r (40 x 23, precomputed
+// per model, model.cu) and the tiles of u1(t-1), u2(t-1), m.
+//
+//  F warps (7)  216 threads, one per group of 4 x-points of the plus-shaped region (tile 128 +
+//     x halo 32 + y halo 56), keep the z-lines of u1, u2 of their own column in register queues,
+//     take the x/y lines from the shared plane, evaluate the closed-form rotation (flux3d.cu) and
+//     publish P_x, M_x (x-extended), P_y, M_y (y-extended), P_z, M_z and u1, u2 of the output plane
+//     (tile only) in a double-buffered shared plane;
+//  D warps (4)  128 threads, one per tile group: D-_x + D-_y of both fields from the shared plane go
+//     to the register accumulator of that plane; the z part never meets memory again: P_z, M_z of
+//     flux plane zf are scattered into the 8 accumulators of the output planes zf-3 .. zf+4, so
+//     plane zf-3 is complete when flux plane zf is, and is updated in place (+ fused snapshot save /
+//     imaging condition / illumination, whose global loads are issued before the hand-over wait).
+//  The two roles run one plane apart and hand the flux plane over through two pairs of named
+//  barriers (bar.arrive / bar.sync: "full" F -> D, "free" D -> F), never a CTA-wide barrier.
 //
 // HBM traffic: 48 B per grid point (u1, u2, their previous level, m, six parameters: read; two
 // writes) + the plane halos that miss L2; the price is evaluating the flux on 864 instead of 512
 // nodes per tile plane (1.69x).
 //
-// History: the first single-pass kernel of the round (64 x 8 tile, 2.1x redundant flux, flux z
+// Measured (C5 grid, 40.8 M points): 0.69-0.72 ms/step plain, 0.74 save, 0.83 imaging condition,
+// against 1.15 / 1.15 / 1.17 ms for the two passes.  ncu (profiles/r01_ncu_tti3d.md): 339 M warp
+// instructions, 46% issue-active with 12 warps per SM (160-168 registers: the cap at 384 threads),
+// shared-memory pipe 60% busy (1344 wavefronts per tile plane: 26 LDS.128 per flux group, 29 per
+// output group), DRAM 3.7 TB/s: bound by shared-memory bandwidth and issue together, not by HBM.
+//
+// History: (1) the first single-pass kernel of the round (64 x 8 tile, 2.1x redundant flux, flux z
 // ring and parked partial sums in shared memory, D phase split by field) executed 660 M warp
 // instructions per step -- 115 M of them register-queue moves, 50 M spin-wait branches, local-
-// memory traffic for the dynamically indexed rings -- and ran 1.29 ms against 1.12 ms for the two
-// passes.  This version is the same mathematics with the bookkeeping removed.
+// memory traffic for the dynamically indexed rings -- and ran 1.29 ms; (2) the same mathematics
+// with the bookkeeping removed but F and D in the same 4 tile warps behind one barrier (245
+// registers, 8 warps) ran 0.85 ms: the tile warps' serial F + D chain at 0.2 IPC was the critical
+// path; (3) splitting the roles over 11 compute warps gave 0.72 ms.  The compile-time rotated
+// queues (ROT, option tti_fused=1) avoid 64 register moves per thread and plane but run slower
+// (0.80 ms) than the shifted queues (tti_fused=2, the default): 8x the code.
 #include "tma_util.cuh"
 
 namespace tti {
@@ -98,7 +113,7 @@ __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const f
     o1 = pk(o[2], o[3]);
 }
 
-template <int FUSE, bool ROT>
+template <int FUSE, bool ROTF, bool ROTD>
 __global__ void __launch_bounds__(tti::NTHREADS, 1)
     tti3d_tma(const __grid_constant__ TtiMaps tm, const TtiArgs a)
 {
@@ -176,9 +191,10 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
 
     // register slot of plane zf + k, k = -3 .. 4 (rotated at compile time, or shifted every plane)
 #define SL(k) (ROT ? ((ph + (k) + 2 * NQ - R) % NQ) : ((k) + R - 1))
-    constexpr int UNR = ROT ? NQ : 1;
 
     if (tid < NF) {
+        constexpr bool ROT = ROTF;
+        constexpr int UNR = ROT ? NQ : 1;
         // ===== F role: flux node group cx in -1..8 (groups of 4 x-points), cy in -4..18 ============
         const bool tile = tid < NI;                    // warps 0-3 (warp uniform)
         int cx, cy;
@@ -323,6 +339,8 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
     }
 
     // ===== D role: divergence, time update and fused extras of one tile group ======================
+    constexpr bool ROT = ROTD;
+    constexpr int UNR = ROT ? NQ : 1;
     const int dt_ = tid - NF;
     const int cx = dt_ & (TXG - 1), cy = dt_ / TXG;
     const int sfx = cy * FXW + 4 * (cx + 1), sfy = (cy + R) * TX + 4 * cx, st = cy * TX + 4 * cx;
@@ -561,12 +579,17 @@ template <int FUSE>
 static void tti3d_launch(const judi_model *M, const StepArgs &s)
 {
     judi_ctx *ctx = M->ctx;
-    const bool rot = ctx->opt_tti_fused != 2;
-    static bool configured = false;
-    if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(tti3d_tma<FUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tti::SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(tti3d_tma<FUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tti::SMEM));
-        configured = true;
+    // register queues: 2 shifted every plane (default), 1 rotated at compile time, 3 / 4 only the
+    // F / D role rotated
+    const int var = (ctx->opt_tti_fused == 1 || ctx->opt_tti_fused == 3 || ctx->opt_tti_fused == 4)
+                        ? ctx->opt_tti_fused : 2;
+    void (*kern)(const TtiMaps, const TtiArgs) =
+        var == 1 ? tti3d_tma<FUSE, true, true> : var == 3 ? tti3d_tma<FUSE, true, false>
+        : var == 4 ? tti3d_tma<FUSE, false, true> : tti3d_tma<FUSE, false, false>;
+    static bool configured[5] = {false, false, false, false, false};
+    if (!configured[var]) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tti::SMEM));
+        configured[var] = true;
     }
     Wavefield *W = s.scratch;
     TtiMaps tm;
@@ -586,8 +609,7 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s)
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     const dim3 grid(ntx, nty, nzc);
-    if (rot) tti3d_tma<FUSE, true><<<grid, tti::NTHREADS, tti::SMEM, ctx->stream>>>(tm, a);
-    else tti3d_tma<FUSE, false><<<grid, tti::NTHREADS, tti::SMEM, ctx->stream>>>(tm, a);
+    kern<<<grid, tti::NTHREADS, tti::SMEM, ctx->stream>>>(tm, a);
     launch_count(ctx, "tti3d_tma");
 }
 

@@ -133,10 +133,12 @@ def test_fwi_objective_and_options(kind, ndim):
     assert flc == fl and np.array_equal(glc, gl)
 
 
-@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("rho", 2), ("tti", 2), ("rho", 3), ("tti", 3)])
 @pytest.mark.parametrize("ic", ["isic", "fwi"])
-def test_isic_fwi_imaging_conditions(ndim, ic):
-    J, args, gm, om, src, rec, q, dt = both("iso", ndim, 8)
+def test_isic_fwi_imaging_conditions(kind, ndim, ic):
+    """test_all_options.jl:13-53 runs isic / fwi on the variable-density and the TTI model
+    (seismic_utils.jl:23-63): Born data and gradient against the oracle + the J dot test."""
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, 8)
     dl, _ = J.born_rec(gm, src, q, rec, ic=ic)
     dlo, _ = O.born_rec(om, src, q, rec, ic=ic)
     assert rel_l2(dl, dlo) < TOL_SHOT
