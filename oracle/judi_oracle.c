@@ -395,6 +395,51 @@ static inline real dminus(const ogrid *g, const real *f, size_t i, size_t s, rea
     return a * ih;
 }
 
+/* Point-wise part of sa_tti (FD_utils.py:84-105): (P, M) = R^T [[A,B],[B,C]] R (g1, g2) from the
+ * staggered gradients g1 = G u1, g2 = G u2 (x,y,z; y unused in 2-D) and the node parameters. */
+static inline void tti_flux_point(int nd, real b, real e, real dl, real theta, real phi,
+                                  const real *g1, const real *g2, real *P, real *M)
+{
+    real gx = g1[0], gy = nd == 3 ? g1[1] : 0, gz = g1[2];
+    real hx = g2[0], hy = nd == 3 ? g2[1] : 0, hz = g2[2];
+    real ct = RCOS(theta), st = RSIN(theta);
+    real cp = 1, sp = 0;
+    if (nd == 3) { cp = RCOS(phi); sp = RSIN(phi); }
+    /* R = r2(theta) * r3(phi):
+     *   [ ct*cp   ct*sp  -st ]
+     *   [  -sp     cp     0  ]
+     *   [ st*cp   st*sp   ct ]   (2-D: rows/cols 0 and 2 of r2(theta)) */
+    real R00 = ct * cp, R01 = ct * sp, R02 = -st;
+    real R10 = -sp, R11 = cp, R12 = 0;
+    real R20 = st * cp, R21 = st * sp, R22 = ct;
+    real A0 = b * dl, A2 = b;
+    real B0 = b * RSQRT((e - dl) * dl);
+    real C0 = b * (e - dl);
+    /* rotate */
+    real r1x = R00 * gx + R01 * gy + R02 * gz;
+    real r1y = R10 * gx + R11 * gy + R12 * gz;
+    real r1z = R20 * gx + R21 * gy + R22 * gz;
+    real r2x = R00 * hx + R01 * hy + R02 * hz;
+    real r2y = R10 * hx + R11 * hy + R12 * hz;
+    real r2z = R20 * hx + R21 * hy + R22 * hz;
+    (void)r2z;
+    real px = A0 * r1x + B0 * r2x, py = A0 * r1y + B0 * r2y, pz = A2 * r1z;
+    real mx = B0 * r1x + C0 * r2x, my = B0 * r1y + C0 * r2y, mz = 0;
+    if (nd == 2) { py = 0; my = 0; }
+    /* R^T */
+    P[0] = R00 * px + R10 * py + R20 * pz;
+    P[1] = R01 * px + R11 * py + R21 * pz;
+    P[2] = R02 * px + R12 * py + R22 * pz;
+    M[0] = R00 * mx + R10 * my + R20 * mz;
+    M[1] = R01 * mx + R11 * my + R21 * mz;
+    M[2] = R02 * mx + R12 * my + R22 * mz;
+}
+void oracle_tti_flux_point(int nd, real b, real e, real dl, real theta, real phi, const real *g1,
+                           const real *g2, real *P, real *M)
+{
+    tti_flux_point(nd, b, e, dl, theta, phi, g1, g2, P, M);
+}
+
 /* Flux fields for the div-grad forms.  nf = 1: F_d = irho * D+_d u   (FD_utils.py:16-17).
  * nf = 2 (TTI): P = R^T (A R G u1 + B R G u2), M = R^T (B R G u1 + C R G u2) (FD_utils.py:84-105),
  * with A = b diag(delta,delta,1), B = b sqrt((eps-delta) delta) diag(1,1,0),
@@ -425,39 +470,12 @@ static void fluxes(const ogrid *g, const real *u1, const real *u2, real **P, rea
                 real hx = dplus(g, u2, i, g->SX, ihx);
                 real hy = nd == 3 ? dplus(g, u2, i, g->SY, ihy) : 0;
                 real hz = dplus(g, u2, i, 1, ihz);
-                real ct = RCOS(g->theta[i]), st = RSIN(g->theta[i]);
-                real cp = 1, sp = 0;
-                if (nd == 3) { cp = RCOS(g->phi[i]); sp = RSIN(g->phi[i]); }
-                /* R = r2(theta) * r3(phi):
-                 *   [ ct*cp   ct*sp  -st ]
-                 *   [  -sp     cp     0  ]
-                 *   [ st*cp   st*sp   ct ]   (2-D: rows/cols 0 and 2 of r2(theta)) */
-                real R00 = ct * cp, R01 = ct * sp, R02 = -st;
-                real R10 = -sp, R11 = cp, R12 = 0;
-                real R20 = st * cp, R21 = st * sp, R22 = ct;
-                real e = g->eps[i], dl = g->delta[i];
-                real A0 = b * dl, A2 = b;
-                real B0 = b * RSQRT((e - dl) * dl);
-                real C0 = b * (e - dl);
-                /* rotate */
-                real r1x = R00 * gx + R01 * gy + R02 * gz;
-                real r1y = R10 * gx + R11 * gy + R12 * gz;
-                real r1z = R20 * gx + R21 * gy + R22 * gz;
-                real r2x = R00 * hx + R01 * hy + R02 * hz;
-                real r2y = R10 * hx + R11 * hy + R12 * hz;
-                real r2z = R20 * hx + R21 * hy + R22 * hz;
-                real px = A0 * r1x + B0 * r2x, py = A0 * r1y + B0 * r2y, pz = A2 * r1z;
-                real mx = B0 * r1x + C0 * r2x, my = B0 * r1y + C0 * r2y, mz = 0;
-                if (nd == 2) { py = 0; my = 0; }
-                /* R^T */
-                P[0][i] = R00 * px + R10 * py + R20 * pz;
-                P[2][i] = R02 * px + R12 * py + R22 * pz;
-                M[0][i] = R00 * mx + R10 * my + R20 * mz;
-                M[2][i] = R02 * mx + R12 * my + R22 * mz;
-                if (nd == 3) {
-                    P[1][i] = R01 * px + R11 * py + R21 * pz;
-                    M[1][i] = R01 * mx + R11 * my + R21 * mz;
-                }
+                real th = g->theta[i], ph = nd == 3 ? g->phi[i] : 0;
+                real g1[3] = {gx, gy, gz}, g2[3] = {hx, hy, hz}, Pp[3], Mp[3];
+                tti_flux_point(nd, b, g->eps[i], g->delta[i], th, ph, g1, g2, Pp, Mp);
+                P[0][i] = Pp[0]; P[2][i] = Pp[2];
+                M[0][i] = Mp[0]; M[2][i] = Mp[2];
+                if (nd == 3) { P[1][i] = Pp[1]; M[1][i] = Mp[1]; }
             }
 }
 
@@ -711,6 +729,26 @@ static inline real lap_weighted(const ogrid *g, const real *u, const real *c1, c
     return acc;
 }
 
+/* Point-wise imaging condition of one field (sensitivity.py:55-69, 106-122), without the weight
+ * w = t_sub*dt*irho:  "as" u v.dt2 ; "isic" u v.dt2 m + grad u . grad v ; "fwi" ... - ...        */
+static inline real ic_point(int ic, real us, real dt2v, real m, real ig)
+{
+    if (ic == 0) return dt2v * us;
+    return us * dt2v * m + (ic == 2 ? -1 : 1) * ig;
+}
+/* Point-wise linearised source of one field (sensitivity.py:157-209): "as" -dm irho u.dt2 ;
+ * "isic" / "fwi" -(dm irho u.dt2 m -+ laplacian(u, dm irho))                                      */
+static inline real linsrc_point(int ic, real dm, real irho, real m, real dt2u, real lapw)
+{
+    if (ic == 0) return -dm * irho * dt2u;
+    return -(dm * irho * dt2u * m - (ic == 2 ? -1 : 1) * lapw);
+}
+real oracle_ic_point(int ic, real us, real dt2v, real m, real ig) { return ic_point(ic, us, dt2v, m, ig); }
+real oracle_linsrc_point(int ic, real dm, real irho, real m, real dt2u, real lapw)
+{
+    return linsrc_point(ic, dm, irho, m, dt2u, lapw);
+}
+
 /* ic: 0 = "as", 1 = "isic", 2 = "fwi" */
 
 /* ------------------------------------------------------------------------------------------ */
@@ -741,7 +779,6 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
     if (recl_out) memset(recl_out, 0, sizeof(real) * (size_t)nt * rec->np);
     if (recnl_out) memset(recnl_out, 0, sizeof(real) * (size_t)nt * rec->np);
     real r1 = 1 / (g->dt * g->dt);
-    real ics = ic == 2 ? -1 : 1;
     int cur = 0;
     for (int t = 1; t <= nt - 2; t++) {
         real *u[2], *up[2], *ul[2], *ulp[2];
@@ -766,11 +803,8 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
                     size_t i = IDX(g, x, y, z);
                     for (int f = 0; f < nf; f++) {
                         real dt2u = (up[f][i] - 2 * u[f][i] + uprev_copy[f][i]) * r1;
-                        if (ic == 0)
-                            q[f][i] = -g->dm[i] * g->irho[i] * dt2u;
-                        else
-                            q[f][i] = -(g->dm[i] * g->irho[i] * dt2u * g->m[i] -
-                                        ics * lap_weighted(g, u[f], g->dm, g->irho, i));
+                        q[f][i] = linsrc_point(ic, g->dm[i], g->irho[i], g->m[i], dt2u,
+                                               ic == 0 ? 0 : lap_weighted(g, u[f], g->dm, g->irho, i));
                     }
                 }
         step_fields(g, &sc, nf, ul, ulp, ulp, (const real *const *)q);
@@ -821,7 +855,6 @@ int oracle_gradient(const ogrid *g, int nt, const osparse *rec, const real *resi
     real *I = illum ? (real *)calloc(g->ntot, sizeof(real)) : NULL;
     real r1 = 1 / (g->dt * g->dt);
     real wdt = (real)t_sub * g->dt;
-    real ics = ic == 2 ? -1 : 1;
     int cur = 0;
     for (int t = nt - 2; t >= 1; t--) {
         real *v[2], *vp[2];
@@ -849,8 +882,8 @@ int oracle_gradient(const ogrid *g, int nt, const osparse *rec, const real *resi
                         real e = 0;
                         for (int f = 0; f < nf; f++) {
                             real dt2v = (vp[f][i] - 2 * v[f][i] + vnext[f][i]) * r1;
-                            if (ic == 0) e += dt2v * us[f][i];
-                            else e += us[f][i] * dt2v * g->m[i] + ics * inner_grad(g, us[f], v[f], i);
+                            e += ic_point(ic, us[f][i], dt2v, g->m[i],
+                                          ic == 0 ? 0 : inner_grad(g, us[f], v[f], i));
                         }
                         G[i] -= w * e;
                     }

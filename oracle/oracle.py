@@ -72,6 +72,11 @@ def _lib(precision):
     lib.oracle_set_threads.argtypes = [ctypes.c_int]
     lib.oracle_set_threads.restype = ctypes.c_int
     lib.oracle_set_ext.argtypes = [P, P, P, P, P, P]
+    lib.oracle_tti_flux_point.argtypes = [ctypes.c_int, real, real, real, real, real, P, P, P, P]
+    lib.oracle_ic_point.argtypes = [ctypes.c_int, real, real, real, real]
+    lib.oracle_ic_point.restype = real
+    lib.oracle_linsrc_point.argtypes = [ctypes.c_int, real, real, real, real, real]
+    lib.oracle_linsrc_point.restype = real
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
     _LIBS[precision] = lib
@@ -498,6 +503,32 @@ def gradient(model, residual, rcv_coords, usave, t_sub=1, ic="as", illum=False):
     lib.oracle_gradient(model.handle(), nt, rec.h, _ptr(res), IC[ic], int(t_sub), _ptr(us),
                         _ptr(g), _ptr(I))
     return g, I
+
+
+# --------------------------------------------------------------------------------------------
+# point-wise algebra of the C loops, exposed so that tests can hold it against the vectors the
+# reference's own Python produces (tests/golden/make_reference_golden.py)
+_IC = {"as": 0, "isic": 1, "fwi": 2}
+
+
+def tti_flux_point(ndim, b, eps_t, delta_t, theta, phi, g1, g2, precision="f64"):
+    """(P, M) of FD_utils.sa_tti at one node from the staggered gradients g1, g2 (x, y, z)."""
+    lib = _lib(precision)
+    a1 = np.ascontiguousarray(g1, dtype=lib._dtype)
+    a2 = np.ascontiguousarray(g2, dtype=lib._dtype)
+    P, M = np.zeros(3, dtype=lib._dtype), np.zeros(3, dtype=lib._dtype)
+    lib.oracle_tti_flux_point(ndim, b, eps_t, delta_t, theta, phi, _ptr(a1), _ptr(a2), _ptr(P), _ptr(M))
+    return P, M
+
+
+def ic_point(ic, us, dt2v, m, inner_grad, precision="f64"):
+    """Imaging condition of one field at one point, without the weight t_sub*dt*irho."""
+    return float(_lib(precision).oracle_ic_point(_IC[ic], us, dt2v, m, inner_grad))
+
+
+def linsrc_point(ic, dm, irho, m, dt2u, lapw, precision="f64"):
+    """Linearised (Born) source of one field at one point."""
+    return float(_lib(precision).oracle_linsrc_point(_IC[ic], dm, irho, m, dt2u, lapw))
 
 
 # --------------------------------------------------------------------------------------------

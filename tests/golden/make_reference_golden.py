@@ -1,0 +1,289 @@
+"""Golden vectors produced by EXECUTING the reference's own Python (src/pysource) in this container.
+
+Devito is not installable here, so the Devito-generated stencil loops cannot run; but every part of
+the hot path that src/pysource states in plain Python / numpy / sympy can, once `devito` is
+replaced by an import stub that only provides symbols (no semantics of its own beyond sympy's):
+
+  * models.Model._cfl_coeff / _thomsen_scale / _max_vp / critical_dt / padsizes   (models.py:269-272, 430-482)
+  * FD_utils.sa_tti / R_mat / thomsen_mat: the rotated TTI flux (P, M) as a function of the
+    staggered gradients, with `grad` returning symbols and `div` capturing its argument   (FD_utils.py:24-105)
+  * sensitivity.crosscorr_time / isic_time / fwi_time / basic_src / isic_src / fwi_src: signs and
+    factors of the imaging conditions and Born sources, on symbolic fields   (sensitivity.py:55-69, 106-122, 157-233)
+  * sensitivity.Loss on numpy data (plain, is_residual, (background, linearised) tuple)   (sensitivity.py:236-276)
+  * fields.wavefield_subsampled: number of saved snapshots   (fields.py:123-153)
+
+Run from the repository root (needs /root/reference):  python tests/golden/make_reference_golden.py
+Output: tests/golden/reference_golden.json (committed; the tests never read /root/reference).
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import sympy as sp
+
+REF = os.environ.get("JUDI_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------
+# import stub for devito: symbols only
+class _Anything(object):
+    """Placeholder for every devito name the imported modules mention but this script never calls."""
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return _Anything()
+
+
+class _Module(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return _Anything
+
+
+def _as_tuple(x, type=None, length=None):
+    if x is None:
+        return ()
+    if isinstance(x, (tuple, list)):
+        return tuple(x)
+    return (x,)
+
+
+class _Trig(object):
+    def __init__(self, f):
+        self.f = f
+        self.__sympy_class__ = f
+
+    def __call__(self, *a):
+        return self.f(*a)
+
+
+CAPTURED = {}
+
+
+def _grad(u, shift=None):
+    assert shift == .5
+    return sp.Matrix([sp.Symbol("g%s_%s" % (u.name, d)) for d in "xyz"][:u.dim] if u.dim == 3 else
+                     [sp.Symbol("g%s_x" % u.name), sp.Symbol("g%s_z" % u.name)])
+
+
+def _div(v, shift=None):
+    assert shift == -.5
+    key = "div%d" % len(CAPTURED)
+    CAPTURED[key] = v
+    return sp.Symbol(key)
+
+
+def _tensor(name=None, grid=None, components=None, symmetric=None, diagonal=None):
+    return sp.Matrix(components)
+
+
+class Field(sp.Symbol):
+    """A symbolic (time) function: u, u.dt2 and its staggered gradient are independent symbols."""
+    def __new__(cls, name, dim=3):
+        obj = sp.Symbol.__new__(cls, name)
+        obj.dim = dim
+        return obj
+
+    @property
+    def dt2(self):
+        return sp.Symbol(self.name + "_dt2")
+
+    @property
+    def indices(self):
+        t = types.SimpleNamespace(spacing=sp.Symbol("dt_save"))
+        return (t,)
+
+
+def install_stub():
+    dv = _Module("devito")
+    dv.cos, dv.sin = _Trig(sp.cos), _Trig(sp.sin)
+    dv.grad, dv.div = _grad, _div
+    dv.TensorFunction = _tensor
+    dv.Differentiable = sp.Expr
+    dv.Function = type("Function", (), {})
+    dv.Constant = type("Constant", (), {})
+    dv.Eq = lambda *a, **k: ("Eq",) + a
+    dv.switchconfig = lambda **k: (lambda f: f)
+    tools = _Module("devito.tools")
+    tools.as_tuple = _as_tuple
+    tools.memoized_func = lambda f: f
+    sys.modules["devito"] = dv
+    sys.modules["devito.tools"] = tools
+    for sub in ("devito.types", "devito.builtins", "devito.arch", "devito.arch.compiler",
+                "devito.types.utils", "devito.symbolics", "devito.finite_differences"):
+        sys.modules[sub] = _Module(sub)
+    sys.path.insert(0, os.path.join(REF, "src", "pysource"))
+
+
+def main():
+    install_stub()
+    import models           # noqa: the reference's module, unmodified
+    import FD_utils
+    import sensitivity
+    import fields
+    out = {"reference": "slimgroup/JUDI.jl src/pysource executed with a devito import stub",
+           "cases": {}}
+    rng = np.random.default_rng(20261019)
+
+    # ---- 1. CFL / critical dt / padsizes ------------------------------------------------------
+    class Probe(object):
+        _cfl_coeff = models.Model._cfl_coeff
+        _thomsen_scale = models.Model._thomsen_scale
+        _max_vp = models.Model._max_vp
+        critical_dt = models.Model.critical_dt
+        padsizes = models.Model.padsizes
+        dt = property(lambda self: self._dt)
+
+    dts = []
+    for ndim in (2, 3):
+        for so in (4, 8, 12, 16):
+            for tti in (False, True):
+                for (vmax, h, user_dt) in ((1.5, 10., None), (4.7, 12.5, None), (5.5, 25., None),
+                                           (3.0, 10., 0.75), (3.0, 10., 5.0)):
+                    p = Probe()
+                    p.is_elastic = False
+                    p.is_tti = tti
+                    p.space_order = so
+                    p.grid = types.SimpleNamespace(dim=ndim)
+                    p.dim = ndim
+                    p.spacing = (h,) * ndim
+                    p.dtype = np.float32
+                    v = np.linspace(1.5, vmax, 7).astype(np.float32)
+                    p.m = (1 / v ** 2).astype(np.float32)
+                    eps = (0.25 * rng.random(7)).astype(np.float32)
+                    p.epsilon = (1 + 2 * eps).astype(np.float32)     # models.py:218
+                    p._dt = user_dt
+                    p.nbl, p.fs = 40, False
+                    import warnings
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        dt = p.critical_dt
+                    dts.append(dict(ndim=ndim, so=so, tti=tti, h=h, m=p.m.tolist(), eps=eps.tolist(),
+                                    user_dt=user_dt, cfl=float(p._cfl_coeff), dt=float(dt)))
+    out["cases"]["critical_dt"] = dts
+    pads = []
+    for ndim in (2, 3):
+        for fs in (False, True):
+            p = Probe()
+            p.nbl, p.fs, p.dim = 17, fs, ndim
+            pads.append(dict(ndim=ndim, fs=fs, nbl=17, padsizes=[list(t) for t in p.padsizes]))
+    out["cases"]["padsizes"] = pads
+
+    # ---- 2. rotated TTI flux --------------------------------------------------------------------
+    tti_cases = []
+    for ndim in (2, 3):
+        CAPTURED.clear()
+        model = types.SimpleNamespace(dim=ndim, grid=None, irho=sp.Symbol("b"), epsilon=sp.Symbol("eps"),
+                                      delta=sp.Symbol("delta"), theta=sp.Symbol("theta"))
+        if ndim == 3:
+            model.phi = sp.Symbol("phi")
+        u, v = Field("u", ndim), Field("v", ndim)
+        FD_utils.sa_tti(u, v, model)
+        PI, MI = CAPTURED["div0"], CAPTURED["div1"]
+        syms = sorted(PI.free_symbols | MI.free_symbols, key=lambda s: s.name)
+        fP = sp.lambdify(syms, PI, "numpy")
+        fM = sp.lambdify(syms, MI, "numpy")
+        for k in range(12):
+            vals = {}
+            for s in syms:
+                if s.name == "b":
+                    vals[s.name] = float(rng.uniform(0.4, 1.2))
+                elif s.name == "eps":
+                    vals[s.name] = 0.0
+                elif s.name == "delta":
+                    vals[s.name] = float(1 + 2 * rng.uniform(0.0, 0.15))
+                elif s.name in ("theta", "phi"):
+                    vals[s.name] = float(rng.uniform(-1.2, 1.2))
+                else:
+                    vals[s.name] = float(rng.standard_normal())
+            vals["eps"] = vals["delta"] + float(2 * rng.uniform(0.0, 0.2))   # eps~ >= delta~
+            args = [vals[s.name] for s in syms]
+            tti_cases.append(dict(ndim=ndim, inputs=vals,
+                                  P=[float(x) for x in np.array(fP(*args), dtype=np.float64).ravel()],
+                                  M=[float(x) for x in np.array(fM(*args), dtype=np.float64).ravel()]))
+    out["cases"]["tti_flux"] = tti_cases
+
+    # ---- 3. imaging conditions and Born sources (signs and factors) -------------------------------
+    ic_cases = []
+    for nf in (1, 2):
+        for name in ("as", "isic", "fwi"):
+            model = types.SimpleNamespace(irho=sp.Symbol("irho"), m=sp.Symbol("m"), dm=sp.Symbol("dm"),
+                                          is_tti=(nf == 2))
+            us = tuple(Field("u%d" % f) for f in range(nf))
+            vs = tuple(Field("v%d" % f) for f in range(nf))
+            expr = sensitivity.ic_dict[name](us, vs, model)
+            CAPTURED.clear()
+            src = sensitivity.ls_dict[name](model, us)
+            src = src if isinstance(src, tuple) else (src,)
+            # laplacian(u, dm*irho) went through FD_utils.laplacian -> div(c * grad): captured
+            lap = {k: list(vv) for k, vv in CAPTURED.items()}
+            syms = sorted(set().union(expr.free_symbols, *[s.free_symbols for s in src],
+                                      *[sp.Matrix(vv).free_symbols for vv in lap.values()]),
+                          key=lambda s: s.name)
+            vals = {s.name: float(rng.uniform(0.3, 1.7) * rng.choice([-1, 1])) for s in syms
+                    if not s.name.startswith("div")}
+            sub = {s: vals[s.name] for s in syms if s.name in vals}
+            # a captured div(c*grad u) is handed back as the symbol divK: give it a value too
+            for k in lap:
+                vals[k] = float(rng.standard_normal())
+                sub[sp.Symbol(k)] = vals[k]
+            ic_cases.append(dict(nf=nf, ic=name, inputs=vals,
+                                 grad_expr=float(expr.subs(sub)),
+                                 lin_src=[float(s.subs(sub)) for s in src],
+                                 div_args={k: [float(sp.sympify(c).subs(sub)) for c in vv]
+                                           for k, vv in lap.items()}))
+    out["cases"]["imaging"] = ic_cases
+
+    # ---- 4. Loss -------------------------------------------------------------------------------------
+    class Rec(object):
+        def __init__(self, a):
+            self.data = types.SimpleNamespace(_local=a.copy())
+
+    loss = []
+    nt, nr, dt = 23, 5, 1.375
+    dsyn = rng.standard_normal((nt, nr)).astype(np.float32)
+    dlin = rng.standard_normal((nt, nr)).astype(np.float32)
+    dobs = rng.standard_normal((nt, nr)).astype(np.float32)
+    for mode in ("plain", "is_residual", "nlind"):
+        if mode == "nlind":
+            f, r = sensitivity.Loss((Rec(dsyn), Rec(dlin)), dobs, dt)
+        else:
+            f, r = sensitivity.Loss(Rec(dsyn), dobs, dt, is_residual=(mode == "is_residual"))
+        loss.append(dict(mode=mode, dt=dt, f=float(f), residual=np.asarray(r, dtype=np.float64).tolist()))
+    out["cases"]["loss"] = dict(dsyn=dsyn.tolist(), dlin=dlin.tolist(), dobs=dobs.tolist(), results=loss)
+
+    # ---- 5. number of saved snapshots -------------------------------------------------------------------
+    saves = []
+
+    class TF(object):
+        def __init__(self, **kw):
+            self.kw = kw
+
+    fields.dvp = types.SimpleNamespace(TimeFunction=TF)
+    fields.ConditionalDimension = lambda **k: ("cd", k.get("factor"))
+    fields.compression_mode = lambda: None
+    model = types.SimpleNamespace(grid=types.SimpleNamespace(time_dim="time"))
+    for nt in (3, 10, 101, 260, 1042, 1705):
+        for t_sub in (1, 2, 4, 7, 16):
+            wf = fields.wavefield_subsampled(model, Field("u"), nt, t_sub)
+            saves.append(dict(nt=nt, t_sub=t_sub, nsave=None if wf is None else int(wf[0].kw["save"])))
+    out["cases"]["nsave"] = saves
+
+    path = os.path.join(HERE, "reference_golden.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

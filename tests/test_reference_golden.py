@@ -1,0 +1,141 @@
+"""The oracle (and, on a GPU box, the CUDA library) against vectors produced by EXECUTING the
+reference's own Python -- src/pysource with a `devito` import stub, see
+tests/golden/make_reference_golden.py, which also lists the reference file:line of every item.
+
+What this pins to the reference's executed code: the CFL coefficient and critical dt, padsizes,
+the rotated TTI flux algebra (R_mat / thomsen_mat / sa_tti), signs and factors of the "as" / "isic"
+/ "fwi" imaging conditions and Born sources, Loss, and the number of saved snapshots.  What it
+cannot pin: the Devito-generated stencil loops themselves.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))["cases"]
+
+
+def _model_kw(c):
+    nd = c["ndim"]
+    m = np.asarray(c["m"], dtype=np.float32)
+    shape = (len(m),) + (5,) * (nd - 1)
+    bc = m.reshape((-1,) + (1,) * (nd - 1)) * np.ones(shape, dtype=np.float32)
+    kw = dict(origin=(0.,) * nd, spacing=(c["h"],) * nd, shape=shape, space_order=c["so"], nbl=6,
+              m=bc.astype(np.float32))
+    if c["tti"]:
+        e = np.asarray(c["eps"], dtype=np.float32).reshape((-1,) + (1,) * (nd - 1))
+        kw["epsilon"] = (e * np.ones(shape, dtype=np.float32)).astype(np.float32)
+        kw["delta"] = (0.5 * kw["epsilon"]).astype(np.float32)
+        kw["theta"] = np.zeros(shape, dtype=np.float32)
+    if c["user_dt"] is not None:
+        kw["dt"] = c["user_dt"]
+    return kw
+
+
+@pytest.mark.parametrize("i", range(0, len(GOLD["critical_dt"]), 3))
+def test_cfl_and_critical_dt(i):
+    """models.py:440-482 executed: dt = f32("%.3e" % (cfl h / (sqrt(1 + 2 max eps) vmax)))."""
+    c = GOLD["critical_dt"][i]
+    assert O.cfl_coeff(c["so"], c["ndim"]) == pytest.approx(c["cfl"], rel=1e-14)
+    om = O.Model(precision="f32", **_model_kw(c))
+    assert np.float32(om.critical_dt) == np.float32(c["dt"])
+
+
+@pytest.mark.parametrize("c", GOLD["padsizes"], ids=lambda c: "%dd_fs%d" % (c["ndim"], c["fs"]))
+def test_padsizes(c):
+    nd = c["ndim"]
+    om = O.Model((0.,) * nd, (10.,) * nd, (9,) * nd, space_order=8, nbl=c["nbl"],
+                 m=np.full((9,) * nd, 0.25, dtype=np.float32), fs=c["fs"], precision="f32")
+    assert [list(p) for p in om.padsizes] == c["padsizes"]
+
+
+def _closed_form(ndim, b, e, d, theta, phi, g1, g2):
+    """The form the CUDA kernels evaluate (flux3d.cu / tti3d.cu): through the symmetry axis r."""
+    if ndim == 2:
+        r = np.array([np.sin(theta), 0., np.cos(theta)])
+    else:
+        r = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+    A0, B0, C0 = b * d, b * np.sqrt((e - d) * d), b * (e - d)
+    d1, d2 = r @ g1, r @ g2
+    P = A0 * g1 + B0 * g2 + ((b - A0) * d1 - B0 * d2) * r
+    M = B0 * g1 + C0 * g2 - (B0 * d1 + C0 * d2) * r
+    return P, M
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["tti_flux"])))
+def test_tti_flux_algebra(i):
+    """FD_utils.sa_tti executed symbolically (grad -> symbols, div -> captured argument)."""
+    c = GOLD["tti_flux"][i]
+    v, nd = c["inputs"], c["ndim"]
+    if nd == 3:
+        g1 = np.array([v["gu_x"], v["gu_y"], v["gu_z"]]); g2 = np.array([v["gv_x"], v["gv_y"], v["gv_z"]])
+        sel = [0, 1, 2]
+    else:
+        g1 = np.array([v["gu_x"], 0., v["gu_z"]]); g2 = np.array([v["gv_x"], 0., v["gv_z"]])
+        sel = [0, 2]
+    phi = v.get("phi", 0.)
+    P, M = O.tti_flux_point(nd, v["b"], v["eps"], v["delta"], v["theta"], phi, g1, g2, precision="f64")
+    assert np.allclose(P[sel], c["P"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(M[sel], c["M"], rtol=1e-12, atol=1e-14)
+    P32, M32 = O.tti_flux_point(nd, v["b"], v["eps"], v["delta"], v["theta"], phi, g1, g2, precision="f32")
+    assert np.allclose(P32[sel], c["P"], rtol=2e-5, atol=2e-6)
+    assert np.allclose(M32[sel], c["M"], rtol=2e-5, atol=2e-6)
+    Pc, Mc = _closed_form(nd, v["b"], v["eps"], v["delta"], v["theta"], phi, g1, g2)
+    assert np.allclose(Pc[sel], c["P"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(Mc[sel], c["M"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("c", GOLD["imaging"], ids=lambda c: "%s_nf%d" % (c["ic"], c["nf"]))
+def test_imaging_conditions_and_born_sources(c):
+    """sensitivity.py ic_dict / ls_dict executed on symbolic fields: gradm -= w * sum_f ic(u_f, v_f)
+    with w = dt_save * irho, and q_f = lin_src(u_f)."""
+    v = c["inputs"]
+    w = v["dt_save"] * v["irho"]
+    tot = 0.
+    for f in range(c["nf"]):
+        ig = 0.
+        if c["ic"] != "as":
+            ig = sum(v["gu%d_%s" % (f, d)] * v["gv%d_%s" % (f, d)] for d in "xyz")
+        tot += O.ic_point(c["ic"], v["u%d" % f], v["v%d_dt2" % f], v.get("m", 1.), ig)
+    assert w * tot == pytest.approx(c["grad_expr"], rel=1e-12)
+    for f in range(c["nf"]):
+        lapw = v.get("div%d" % f, 0.)
+        q = O.linsrc_point(c["ic"], v["dm"], v["irho"], v.get("m", 1.), v["u%d_dt2" % f], lapw)
+        assert q == pytest.approx(c["lin_src"][f], rel=1e-12)
+        if c["ic"] != "as":
+            # laplacian(u, dm*irho) = div(dm * irho * grad(u, +1/2), -1/2): node-valued coefficient
+            want = [v["dm"] * v["irho"] * v["gu%d_%s" % (f, d)] for d in "xyz"]
+            assert np.allclose(c["div_args"]["div%d" % f], want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("r", GOLD["loss"]["results"], ids=lambda r: r["mode"])
+def test_loss(r):
+    L = GOLD["loss"]
+    dsyn = np.asarray(L["dsyn"], dtype=np.float32)
+    dlin = np.asarray(L["dlin"], dtype=np.float32)
+    dobs = np.asarray(L["dobs"], dtype=np.float32)
+    if r["mode"] == "nlind":
+        f, res = O.Loss((dsyn, dlin), dobs, r["dt"])
+    else:
+        f, res = O.Loss(dsyn, dobs, r["dt"], is_residual=(r["mode"] == "is_residual"))
+    assert float(f) == pytest.approx(r["f"], rel=1e-6)
+    assert np.allclose(res, np.asarray(r["residual"]), rtol=1e-6, atol=1e-7)
+
+
+def test_number_of_saved_snapshots():
+    for c in GOLD["nsave"]:
+        if c["nsave"] is not None:
+            assert O.nsave(c["nt"], c["t_sub"]) == c["nsave"], c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(0, len(GOLD["critical_dt"]), 7))
+def test_library_critical_dt_matches_reference(i):
+    """judi_model_critical_dt (C-ABI) against the reference's executed formula."""
+    import judi_jl_b200 as J
+    c = GOLD["critical_dt"][i]
+    gm = J.Model(**_model_kw(c))
+    assert np.float32(gm.critical_dt) == np.float32(c["dt"])
