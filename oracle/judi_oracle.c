@@ -6,8 +6,12 @@
  * in the build container.  The reference ships no golden wavefield / shot-record / gradient
  * vectors for this path.  This file therefore restates the *published*
  * algorithm -- the symbolic equations in src/pysource plus Devito's documented lowering of them --
- * and is pinned only by the reference's own property tests (adjoint dot tests, Taylor rates,
- * linearity, lsrtm(dm=0,nlind)==fwi) which tests/ re-runs against it.
+ * and its time loops are pinned only by the reference's own property tests (adjoint dot tests,
+ * Taylor rates, linearity, lsrtm(dm=0,nlind)==fwi) which tests/ re-runs against it.
+ * PINNED to the reference's own Python executed in the build container (src/pysource with a devito
+ * import stub; tests/golden/make_reference_golden.py, tests/test_reference_golden.py): the
+ * point-wise algebra of this file -- tti_flux_point (FD_utils.sa_tti), ic_point / linsrc_point
+ * (sensitivity.py ic_dict / ls_dict) -- plus, in oracle.py, critical dt, padsizes, Loss, nsave.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (judi.jl_b200/csrc) never links or calls it.

@@ -1,7 +1,8 @@
 """
 CPU ORACLE (test infrastructure, NOT product code) -- numpy/ctypes front end of judi_oracle.c.
 
-PARITY UNPINNED: see the header of judi_oracle.c.  Nothing under judi.jl_b200/ may import this.
+STENCIL PARITY UNPINNED, host logic and point-wise algebra pinned to the executed reference: see
+the header of judi_oracle.c.  Nothing under judi.jl_b200/ may import this.
 
 The classes/functions below restate, with the same names and argument meaning, the part of
 /root/reference/src/pysource that sits above the Devito operators:
