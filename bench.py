@@ -54,7 +54,13 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    return ap.parse_args()
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 (default): the 3-D acoustic FWI gradient BASELINE.json's metric names; "
+                         "c5: secondary line, 3-D TTI forward + gradient on 301x301x201")
+    a = ap.parse_args()
+    if a.workload == "c5" and a.shape == list(SHAPE):
+        a.shape = [301, 301, 201]
+    return a
 
 
 # ---- synthetic "overthrust-shaped" model --------------------------------------------
@@ -96,10 +102,27 @@ def ricker(nt, dt, f0):
     return ((1 - 2 * r ** 2) * np.exp(-r ** 2)).astype(np.float32).reshape(nt, 1)
 
 
-def workload_name(shape, nt, t_sub, region):
-    return ("3D acoustic so=8 FWI gradient (fwd+snapshots, adj+IC), n=%dx%dx%d d=25m nbl=40, "
+def workload_name(shape, nt, t_sub, region, tti=False):
+    return ("3D %s so=8 FWI gradient (fwd+snapshots, adj+IC), n=%dx%dx%d d=25m nbl=40, "
             "10201 receivers, nt=%d, t_sub=%d, %s-domain snapshots, 1 shot/GPU/step"
-            % (shape[0], shape[1], shape[2], nt, t_sub, region))
+            % ("TTI" if tti else "acoustic", shape[0], shape[1], shape[2], nt, t_sub, region))
+
+
+def tti_params(v):
+    """eps = 0.2 (v - 1.5) / 4, delta = 0.1 (v - 1.5) / 4, theta = pi/6 (v - 1.5) / 4,
+    phi = pi / 8."""
+    return dict(epsilon=np.asfortranarray((0.2 * (v - 1.5) / 4).astype(np.float32)),
+                delta=np.asfortranarray((0.1 * (v - 1.5) / 4).astype(np.float32)),
+                theta=np.asfortranarray((np.pi / 6 * (v - 1.5) / 4).astype(np.float32)),
+                phi=np.float32(np.pi / 8))
+
+
+def model_dt(args):
+    """dt_comp of the workload.  C5: the TTI model's critical dt, models.py:459-482 literally --
+    sqrt(1 + 2 max(eps~)) with eps~ = 1 + 2 eps already applied (max eps = 0.2 here)."""
+    if args.workload != "c5":
+        return DT
+    return float(np.float32("%.3e" % (DT / np.sqrt(1 + 2 * (1 + 2 * 0.2)))))
 
 
 # ---- clocks -------------------------------------------------------------------------------------
@@ -156,15 +179,18 @@ class ClockSampler(object):
 
 
 # ---- CPU arm: the oracle on the host cores -------------------------------------------------------
-def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0):
+def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0, tti=False, dt=DT):
     """Times a bounded sample of the workload with the CPU oracle (all host threads):
     `ns` forward steps + `ns` adjoint+IC steps on the full grid, extrapolated to one shot."""
     from oracle import oracle as O
     O.build()
     ncores = O.set_threads(os.cpu_count() or 1)   # torchrun sets OMP_NUM_THREADS=1: override
     v0 = smooth_model(velocity(shape))
+    extra = {k_: np.ascontiguousarray(v_) for k_, v_ in tti_params(v0).items()} if tti else {}
+    if tti:
+        extra["phi"] = np.full(shape, extra["phi"], dtype=np.float32)
     model = O.Model((0., 0., 0.), SPACING, shape, space_order=SO, nbl=NBL,
-                    m=(1 / v0 ** 2).astype(np.float32), dt=DT, precision="f32")
+                    m=(1 / v0 ** 2).astype(np.float32), dt=dt, precision="f32", **extra)
     t1 = O.time_steps(model, 2, True, t_sub)          # calibration (also first-touch of memory)
     per_pair = max(t1 / 2, 1e-6)
     ns = int(max(4, min(nt - 2, seconds / per_pair)))
@@ -193,14 +219,15 @@ def run_reference(args):
     if rank != 0:
         return
     shape = tuple(args.shape)
-    nt = int(np.floor(args.tn / DT)) + 1
+    tti, dtc = args.workload == "c5", model_dt(args)
+    nt = int(np.floor(args.tn / dtc)) + 1
     r = cpu_sample(shape, nt, args.t_sub, args.cpu_seconds / 2, steps=args.steps,
-                   warmup=args.warmup)
+                   warmup=args.warmup, tti=tti, dt=dtc)
     line = {"impl": "reference", "metric": "fwi_gradient_shots_per_s", "value": r["value"],
             "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region),
+            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region, tti),
                        "note": "CPU arm: one process, all host threads, no GPU"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "gpts_per_s": r["gpts_per_s"],
@@ -226,15 +253,18 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     shape = tuple(args.shape)
-    nt = int(np.floor(args.tn / DT)) + 1
+    tti, dtc = args.workload == "c5", model_dt(args)
+    nt = int(np.floor(args.tn / dtc)) + 1
     v = velocity(shape)
     v0 = smooth_model(v)
     m_true = np.asfortranarray((1 / v ** 2).astype(np.float32))
     m0 = np.asfortranarray((1 / v0 ** 2).astype(np.float32))
     src, rec = geometry(shape, rank)
-    q = ricker(nt, DT, F0)
+    q = ricker(nt, dtc, F0)
     nrec = rec.shape[0]
-    kw = dict(space_order=SO, nbl=NBL, dt=DT)
+    kw = dict(space_order=SO, nbl=NBL, dt=dtc)
+    if tti:
+        kw.update(tti_params(v0))     # the same anisotropy for the true and the starting model
 
     # ---- untimed setup: observed data of this rank's shot from the true model ---------------
     mt = J.Model((0., 0., 0.), SPACING, shape, m=m_true, **kw)
@@ -252,7 +282,10 @@ def run_b200(args):
         m0_d = torch.from_numpy(np.ascontiguousarray(m0.transpose(2, 1, 0))).to(dev)
         q_d = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev)
         dobs_d = torch.from_numpy(np.ascontiguousarray(dobs.T)).to(dev)
-        model = J.Model((0., 0., 0.), SPACING, shape, m=m0_d, **kw)
+        kw_d = {k_: (torch.from_numpy(np.ascontiguousarray(v_.transpose(2, 1, 0))).to(dev)
+                     if isinstance(v_, np.ndarray) and v_.ndim == 3 else v_) for k_, v_ in kw.items()}
+        model = J.Model((0., 0., 0.), SPACING, shape, m=m0_d, **kw_d)
+        assert abs(float(model.critical_dt) - dtc) < 1e-6 * dtc, (model.critical_dt, dtc)
         npad = model.shape_pml
         ngrid = int(np.prod(npad))
         red = torch.zeros(ngrid + 1, dtype=torch.float32, device=dev)   # gradient + objective
@@ -354,19 +387,21 @@ def run_b200(args):
     nsave = len([t_ for t_ in range(1, nt - 1) if t_ % k == 0])
     # per shot: fwd launches 16 B/pt (+4 B per snapshot point when saving), adjoint launches
     # 16 B/pt (+12 B per snapshot point with the imaging condition: read u_s, RMW gradient)
-    bytes_shot = 2 * nsteps_t * 16.0 * npts + nsave * (4.0 + 12.0) * nphys
+    bpp, bsave, bic = (48.0, 8.0, 16.0) if tti else (16.0, 4.0, 12.0)
+    bytes_shot = 2 * nsteps_t * bpp * npts + nsave * (bsave + bic) * nphys
     alg_bytes_per_launch = bytes_shot / (2 * nsteps_t)
     ms_launch = stats["ms"] / max(stats["launches"], 1)
     achieved = alg_bytes_per_launch / (ms_launch * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-            "acoustic3d_tma_bytes_per_launch")
+            "tti3d_tma_bytes_per_launch" if tti else "acoustic3d_tma_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "acoustic3d_tma (fwd / fwd+save / adj / adj+IC launches averaged)",
+                "kernel": ("tti3d_tma" if tti else "acoustic3d_tma") +
+                          " (fwd / fwd+save / adj / adj+IC launches averaged)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": ms_launch, "launches_timed": stats["launches"],
                 "launches_in_region": 2 * nsteps_t * args.steps,
@@ -380,9 +415,10 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region),
-                       "padded_grid": list(npad), "nt": nt, "dt_ms": DT,
-                       "l2_policy": "inputs_larger_than_L2 (each field 260 MB vs 126 MB L2)",
+            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region, tti),
+                       "padded_grid": list(npad), "nt": nt, "dt_ms": dtc,
+                       "l2_policy": "inputs_larger_than_L2 (each field %.0f MB vs 126 MB L2)"
+                                    % (4e-6 * npts),
                        "parallelism": "shots partitioned over %d GPU(s), one all-reduce per step"
                                       % world},
             "gpts_per_s": shots * 2 * nsteps_t * npts / (ms * 1e-3) / 1e9,
@@ -392,7 +428,8 @@ def run_b200(args):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = {kk: vv for kk, vv in
-                                cpu_sample(shape, nt, args.t_sub, args.cpu_seconds).items()
+                                cpu_sample(shape, nt, args.t_sub, args.cpu_seconds, tti=tti,
+                                           dt=dtc).items()
                                 if kk in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
