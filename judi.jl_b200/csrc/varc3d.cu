@@ -7,38 +7,44 @@
 //
 // Unlike the TTI operator there are no cross terms: the flux F_d needs only the derivative along
 // its own axis, so the halo flux nodes are cheap (one 8-tap line each) and need no z history.
-// One CTA owns a 64 x 16 (x,y) tile and marches along z, two phases per plane around ONE named
-// barrier:
-//   F  every thread (4 consecutive x of one column): F_z from the register queue of u (kept in a
-//      second register queue), F_x and F_y of its own nodes from the shared u plane (TMA ring,
-//      haloed 80 x 32 boxes; c from a haloed 72 x 24 box) into a double-buffered shared flux plane;
-//      threads 0..31 add the 2 x-halo groups of a row, threads 0..127 the 8 y-halo rows;
-//   D  D-_x F_x + D-_y F_y from the shared plane, parked for R-1 planes in registers until D-_z
-//      completes, then the leapfrog update in place (+ snapshot save / imaging condition /
-//      illumination).
+// Same structure as tti3d.cu: one CTA of 12 warps owns a 32 x 16 (x,y) tile and marches along z;
+// a producer warp streams three TMA rings (haloed 48 x 30 planes of u, haloed 40 x 23 planes of c,
+// tiles of u(t-1), m, irho).
+//  F warps (7)  tile threads (4 warps, one per group of 4 x-points) keep the z-line of u in a
+//     register queue and publish F_x, F_y, F_z and u of the output plane; the x-halo warp adds F_x
+//     of one group left / right of every row, the two y-halo warps F_y of rows -4..-1, 16..18;
+//  D warps (4)  D-_x F_x + D-_y F_y from the shared plane into the register accumulator of that
+//     plane, F_z scattered into the 8 accumulators of output planes zf-3 .. zf+4, then the leapfrog
+//     update in place (+ snapshot save / imaging condition / illumination).
+// The roles hand the double-buffered flux plane over through named barriers (bar.arrive / bar.sync).
+// ~80 registers and 95 KB of shared memory: two CTAs per SM.
 // HBM traffic: 20 B per grid point (u, u(t-1), m, irho read; u(t+1) written) + halos that miss L2.
-// Measured (C5-size grid, 40.8 M points): 0.38 ms/step against 0.50 ms for the two passes.  ncu:
-// 183 M warp instructions, 40% issue-active with the 8 worker warps of the single resident CTA
-// (167 registers, 80 of them the three register queues; 148 KB shared): latency-, not HBM-bound.
+// History: the first version (64 x 16 tile, F and D in the same 8 warps behind one barrier, flux
+// and partial-sum queues in 167 registers, one CTA per SM) ran 0.38 ms/step on the C5-size grid
+// against 0.50 ms for the two passes; ncu: 40% issue-active, latency-bound.
 #include "tma_util.cuh"
 
 namespace varc {
-constexpr int R = 4, XE = 4;
-constexpr int TXT = 16, TY = 16, TX = 4 * TXT;
-constexpr int UPX = TX + 4 * XE, UPY = TY + 4 * R;     // haloed u plane 80 x 32 (halo 2R)
-constexpr int USLOT = UPX * UPY;
-constexpr int CPX = TX + 2 * XE, CPY = TY + 2 * R;     // haloed c plane 72 x 24 (halo R)
-constexpr int CSLOT = CPX * CPY;
+constexpr int R = 4;
+constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
+constexpr int UPX = TX + 16, UPY = TY + 14;        // haloed u plane 48 x 30, origin (x0-8, y0-7)
+constexpr int USLOT = UPX * UPY;                   // 1440 floats (multiple of 32)
+constexpr int CPX = TX + 8, CPY = TY + 7;          // coefficient plane 40 x 23, origin (x0-4, y0-4)
+constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;
 constexpr int PSLOT = TX * TY;
-constexpr int NS = 8, NC = 3, NP = 3;                  // ring depths: u planes, c planes, tiles
+constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, c planes, tiles
 constexpr int NQ = 2 * R;
-constexpr int NT = TXT * TY;                           // 256 worker threads
-constexpr int NCW = NT / 32;
-constexpr int NTHREADS = NT + 32;
-constexpr int FXW = (TXT + 2) * 4;                     // x-extended flux plane: 16 rows x 72
+constexpr int NI = TXG * TY;                       // 128 tile groups
+constexpr int NF = 224;                            // F warps: tile (0-3), x halo (4), y halo (5, 6)
+constexpr int ND = NI;                             // D warps (7-10)
+constexpr int NTHREADS = NF + ND + 32;             // + the producer warp
+constexpr int FXW = TX + 8;                        // row pitch of the x-extended flux plane (40)
 constexpr int FX = TY * FXW;
-constexpr int FY = (TY + 2 * R) * TX;                  // y-extended flux plane: 24 rows x 64
-constexpr int FBUF = FX + FY;
+constexpr int FY = CPY * TX;                       // y-extended flux plane (rows -4 .. 18)
+constexpr int FBUF = FX + FY + 2 * PSLOT;          // F_x, F_y of one plane + F_z, u tiles
+constexpr int LEADU = 3, LEADC = 2;                // producer run-ahead (planes)
+constexpr int WARM = 4 * R - 2;                    // iterations before the first output plane
+constexpr int FIRST = 2 * R - 1;                   // first flux iteration
 constexpr size_t SMEM = (size_t)(NS * USLOT + NC * CSLOT + NP * 3 * PSLOT + 2 * FBUF) * 4 +
                         (2 * NS + 2 * NC + 2 * NP) * 8 + 128;
 }  // namespace varc
@@ -59,32 +65,31 @@ struct VarcArgs {
 
 enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4 };
 
-// D+ along x of the 4 nodes of a group from the 12-float row window centred on it
-__device__ __forceinline__ void varc_dplus_x(const Coefs &cf, const float *w, f2 &g0, f2 &g1)
+// staggered first derivative along x at the 4 nodes of a group from the 12-float row window centred
+// on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2)
+template <bool PLUS>
+__device__ __forceinline__ void varc_dx(const float *wx, const float4 &l, const float4 &c,
+                                        const float4 &r, f2 &o0, f2 &o1)
 {
+    const float w[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
     float o[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 1; k <= varc::R; k++)
-            acc = __fmaf_rn(cf.wx[k], __fsub_rn(w[4 + e + k], w[4 + e - k + 1]), acc);
+        for (int k = 1; k <= varc::R; k++) {
+            const float d = PLUS ? __fsub_rn(w[4 + e + k], w[4 + e - k + 1])
+                                 : __fsub_rn(w[4 + e + k - 1], w[4 + e - k]);
+            acc = (k == 1) ? __fmul_rn(wx[1], d) : __fmaf_rn(wx[k], d, acc);
+        }
         o[e] = acc;
     }
-    g0 = pk(o[0], o[1]);
-    g1 = pk(o[2], o[3]);
-}
-
-__device__ __forceinline__ void varc_window(const float *p, float *w)
-{
-    const float4 l = *(const float4 *)(p - 4), c = *(const float4 *)p, r = *(const float4 *)(p + 4);
-    w[0] = l.x; w[1] = l.y; w[2] = l.z; w[3] = l.w;
-    w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
-    w[8] = r.x; w[9] = r.y; w[10] = r.z; w[11] = r.w;
+    o0 = pk(o[0], o[1]);
+    o1 = pk(o[2], o[3]);
 }
 
 template <int FUSE>
-__global__ void __launch_bounds__(varc::NTHREADS, 1)
+__global__ void __launch_bounds__(varc::NTHREADS, 2)
     varc3d_tma(const __grid_constant__ VarcMaps tm, const VarcArgs a)
 {
     using namespace varc;
@@ -106,251 +111,270 @@ __global__ void __launch_bounds__(varc::NTHREADS, 1)
     const int z0 = blockIdx.z * a.zchunk;
     const int z1 = min(z0 + a.zchunk, g.n[2]);
     const int nzc = z1 - z0;
-    // iteration j brings in u plane z0-2R+1+j; flux plane zf = z0-3R+1+j (from j = 2R-1, flux
-    // counter jf = j-2R+1); output plane zo = zf-R+1 = z0-4R+2+j (from j = 4R-2)
-    const int total = nzc + 4 * R - 2;
-    const int nflux = nzc + 2 * R - 1;
+    // iteration j brings in u plane z0-7+j; flux plane zf = z0-11+j (from j = 7); output plane
+    // zo = zf-3 = z0-14+j (from j = 14)
+    const int total = nzc + WARM;
+    constexpr int NSYNC = NF + ND;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NCW); }
-        for (int s = 0; s < NC; s++) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], NCW); }
-        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], NCW); }
+        // only the tile warps read the incoming plane and the u plane of the z-line; every F warp
+        // reads the flux plane's lines and the coefficient plane
+        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NF / 32); }
+        for (int s = 0; s < NC; s++) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], NF / 32); }
+        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], ND / 32); }
         fence_barrier_init();
     }
     __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31;
 
-    if (threadIdx.x >= NT) {
+    if (tid >= NF + ND) {
         // ===== producer warp ======================================================================
-        if ((threadIdx.x & 31) == 0) {
-            const int bx = g.hx + x0 - 2 * XE, by = g.hy + y0 - 2 * R, bz = g.hz + z0 - 2 * R + 1;
-            const int cbx = g.hx + x0 - XE, cby = g.hy + y0 - R, cbz = g.hz + z0 - R;
+        if (lane == 0) {
+            const int bx = g.hx + x0 - 8, by = g.hy + y0 - 7, bz = g.hz + z0 - 7;
+            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - 4, cz0 = g.hz + z0 - 4;
             const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
-            for (int j = 0; j < total; j++) {
-                const int s = j % NS;
-                if (j >= NS) mbar_wait(&emptyU[s], (uint32_t)(((j / NS) - 1) & 1));
-                mbar_arrive_expect_tx(&fullU[s], USLOT * 4);
-                tma_load_3d(ringU + s * USLOT, &tm.U, bx, by, bz + j, &fullU[s]);
-                // coefficient plane of flux counter jc, used at iteration jc + 2R-1: one early
-                const int jc = j - (2 * R - 1) + 1;
-                if (jc >= 0 && jc < nflux) {
-                    const int sc = jc % NC;
-                    if (jc >= NC) mbar_wait(&emptyC[sc], (uint32_t)(((jc / NC) - 1) & 1));
-                    mbar_arrive_expect_tx(&fullC[sc], CSLOT * 4);
-                    tma_load_3d(ringC + sc * CSLOT, &tm.C, cbx, cby, cbz + jc, &fullC[sc]);
+            for (int j = -LEADU; j < total; j++) {
+                const int pj = j + LEADU;                 // u plane (consumer iteration pj)
+                if (pj < total) {
+                    const int s = pj % NS;
+                    if (pj >= NS) mbar_wait_sleep(&emptyU[s], (uint32_t)(((pj / NS) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullU[s], USLOT * 4);
+                    tma_load_3d(ringU + s * USLOT, &tm.U, bx, by, bz + pj, &fullU[s]);
                 }
-                // tiles of output plane i, used at iteration i + 4R-2: one early
-                const int i = j - (4 * R - 2) + 1;
+                const int c = j + LEADC - FIRST;          // flux plane counter (iteration c + 7)
+                if (c >= 0 && c < total - FIRST) {
+                    const int s = c % NC;
+                    if (c >= NC) mbar_wait_sleep(&emptyC[s], (uint32_t)(((c / NC) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullC[s], CPX * CPY * 4);
+                    tma_load_3d(ringC + s * CSLOT, &tm.C, cx0, cy0, cz0 + c, &fullC[s]);
+                }
+                const int i = j + LEADC - WARM;           // output plane counter (iteration i + 14)
                 if (i >= 0 && i < nzc) {
-                    const int sp = i % NP;
-                    if (i >= NP) mbar_wait(&emptyP[sp], (uint32_t)(((i / NP) - 1) & 1));
-                    mbar_arrive_expect_tx(&fullP[sp], 3 * PSLOT * 4);
-                    tma_load_3d(ringP + sp * 3 * PSLOT, &tm.P, tx0, ty0, tz0 + i, &fullP[sp]);
-                    tma_load_3d(ringP + sp * 3 * PSLOT + PSLOT, &tm.M, tx0, ty0, tz0 + i, &fullP[sp]);
-                    tma_load_3d(ringP + sp * 3 * PSLOT + 2 * PSLOT, &tm.I, tx0, ty0, tz0 + i, &fullP[sp]);
+                    const int s = i % NP;
+                    if (i >= NP) mbar_wait_sleep(&emptyP[s], (uint32_t)(((i / NP) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullP[s], 3 * PSLOT * 4);
+                    tma_load_3d(ringP + s * 3 * PSLOT, &tm.P, tx0, ty0, tz0 + i, &fullP[s]);
+                    tma_load_3d(ringP + s * 3 * PSLOT + PSLOT, &tm.M, tx0, ty0, tz0 + i, &fullP[s]);
+                    tma_load_3d(ringP + s * 3 * PSLOT + 2 * PSLOT, &tm.I, tx0, ty0, tz0 + i, &fullP[s]);
                 }
             }
         }
         return;
     }
 
-    // ===== worker threads ===========================================================================
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int tx = tid % TXT, ty = tid / TXT;
-    const int x = x0 + 4 * tx, y = y0 + ty;
-    const bool act = x < g.n[0] && y < g.n[1];
-    const bool xfull = x + 3 < g.n[0];
-    const int su = (ty + 2 * R) * UPX + 4 * tx + 2 * XE;     // own group in a u plane
-    const int scn = (ty + R) * CPX + 4 * tx + XE;            // ... in a c plane
-    const int sfx = ty * FXW + 4 * (tx + 1);                 // ... in the x-extended flux plane
-    const int sfy = (ty + R) * TX + 4 * tx;                  // ... in the y-extended flux plane
-    const int st = ty * TX + 4 * tx;                         // ... in a tile
-    // extra halo work: threads 0..31 one x-halo group (row hxr, left/right), threads 0..127 one
-    // y-halo group (rows -4..-1 and 16..19)
-    const bool hx_on = tid < 2 * TY, hy_on = tid < TXT * 2 * R;
-    const int hxr = tid >> 1, hxg = (tid & 1) ? TXT : -1;
-    const int hx_u = (hxr + 2 * R) * UPX + 4 * hxg + 2 * XE, hx_c = (hxr + R) * CPX + 4 * hxg + XE;
-    const int hx_f = hxr * FXW + 4 * (hxg + 1);
-    const int hyh = tid / TXT, hyg = tid % TXT;
-    const int hyy = hyh < R ? hyh - R : hyh - R + TY;
-    const int hy_u = (hyy + 2 * R) * UPX + 4 * hyg + 2 * XE, hy_c = (hyy + R) * CPX + 4 * hyg + XE;
-    const int hy_f = (hyy + R) * TX + 4 * hyg;
-    long long gout = g.at(x, y, z0);
+    if (tid < NF) {
+        // ===== F role ================================================================================
+        const bool tile = tid < NI;                    // warps 0-3
+        const bool xh = !tile && tid < NI + 32;        // warp 4
+        int cx, cy;
+        bool wr = true;
+        if (tile) { cx = tid & (TXG - 1); cy = tid / TXG; }
+        else if (xh) {
+            const int h = tid - NI;
+            cx = (h & 1) ? TXG : -1;
+            cy = h >> 1;
+        } else {
+            const int h = tid - NI - 32, row = h / TXG;   // 0..7; the last row is idle (mirrors row 6)
+            cx = h & (TXG - 1);
+            cy = row < R ? row - R : TY + min(row, 2 * R - 2) - R;
+            wr = row < 2 * R - 1;
+        }
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;   // node group inside a u plane
+        const int sc = (cy + R) * CPX + 4 * cx + R;               // ... inside a coefficient plane
+        const int sfx = cy * FXW + 4 * (cx + 1);                  // ... inside the x-extended flux plane
+        const int sfy = (cy + R) * TX + 4 * cx;                   // ... inside the y-extended flux plane
+        const int st = cy * TX + 4 * cx;                          // ... inside a tile (tile threads)
 
-    float4 qu[NQ], qf[NQ], hq[R];
+        float4 q[NQ];   // u of planes zf-3 .. zf+4 at this node group (tile threads)
 #pragma unroll
-    for (int k = 0; k < NQ; k++) qu[k] = qf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < R; k++) hq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < NQ; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cslot = 0, cpar = 0;
 
+        for (int j = 0; j < total; j++) {
+#pragma unroll
+            for (int k = 0; k < NQ - 1; k++) q[k] = q[k + 1];
+            const int s_in = j & (NS - 1);
+            mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
+            if (tile) q[NQ - 1] = *(const float4 *)(ringU + s_in * USLOT + su);
+            if (j < FIRST) {
+                if (j < R - 1) {   // the first three planes of a chunk are never a flux plane
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&emptyU[s_in]);
+                }
+                continue;
+            }
+            const int zf = z0 - (3 * R - 1) + j;
+            const bool need_xy = zf >= z0 && zf < z1;       // its x / y flux is used
+            const int s_c = (j + NS - R) & (NS - 1);
+            float *fb = fbuf + (j & 1) * FBUF;
+            mbar_wait(&fullC[cslot], (uint32_t)cpar);
+            f2 fx0, fx1, fy0, fy1, fz0, fz1;
+            fx0 = fx1 = fy0 = fy1 = fz0 = fz1 = pk1(0.f);
+            if (tile || need_xy) {
+                const float *pl = ringU + s_c * USLOT + su;
+                const float4 c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
+                const float4 cen = tile ? q[R - 1] : *(const float4 *)pl;
+                if ((tile && need_xy) || xh) {
+                    f2 g0, g1;
+                    varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), g0, g1);
+                    fx0 = mul2(lo2(c4), g0); fx1 = mul2(hi2(c4), g1);
+                }
+                if ((tile && need_xy) || (!tile && !xh)) {
+                    f2 g0, g1;
+#pragma unroll
+                    for (int k = 1; k <= R; k++) {
+                        const float4 p = *(const float4 *)(pl + k * UPX);
+                        const float4 m = (k == 1) ? cen : *(const float4 *)(pl - (k - 1) * UPX);
+                        const f2 d0 = sub2(lo2(p), lo2(m)), d1 = sub2(hi2(p), hi2(m));
+                        if (k == 1) { g0 = mul2s(cf.wy[1], d0); g1 = mul2s(cf.wy[1], d1); }
+                        else { g0 = fma2s(cf.wy[k], d0, g0); g1 = fma2s(cf.wy[k], d1, g1); }
+                    }
+                    fy0 = mul2(lo2(c4), g0); fy1 = mul2(hi2(c4), g1);
+                }
+                if (tile) {
+                    f2 g0, g1;
+#pragma unroll
+                    for (int k = 1; k <= R; k++) {
+                        const float4 zp = q[R - 1 + k], zm = q[R - k];
+                        const f2 d0 = sub2(lo2(zp), lo2(zm)), d1 = sub2(hi2(zp), hi2(zm));
+                        if (k == 1) { g0 = mul2s(cf.wz[1], d0); g1 = mul2s(cf.wz[1], d1); }
+                        else { g0 = fma2s(cf.wz[k], d0, g0); g1 = fma2s(cf.wz[k], d1, g1); }
+                    }
+                    fz0 = mul2(lo2(c4), g0); fz1 = mul2(hi2(c4), g1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
+            if (++cslot == NC) { cslot = 0; cpar ^= 1; }
+            // the flux buffer of this parity was read by the D warps two planes ago
+            if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
+            if (need_xy && wr) {
+                if (tile || xh) *(float4 *)(fb + sfx) = cat4(fx0, fx1);
+                if (tile || !xh) *(float4 *)(fb + FX + sfy) = cat4(fy0, fy1);
+            }
+            if (tile) {
+                float *fz_ = fb + FX + FY + st;
+                *(float4 *)fz_ = cat4(fz0, fz1);
+                *(float4 *)(fz_ + PSLOT) = q[0];      // u of the output plane zf-3
+            }
+            __threadfence_block();
+            named_bar_arrive(1 + (j & 1), NSYNC);
+        }
+        return;
+    }
+
+    // ===== D role: divergence, time update and fused extras of one tile group ======================
+    const int dt_ = tid - NF;
+    const int cx = dt_ & (TXG - 1), cy = dt_ / TXG;
+    const int sfx = cy * FXW + 4 * (cx + 1), sfy = (cy + R) * TX + 4 * cx, st = cy * TX + 4 * cx;
+    const int ox = x0 + 4 * cx, oy = y0 + cy;
+    const bool act = ox < g.n[0] && oy < g.n[1];
+    const bool xfull = ox + 3 < g.n[0];
+    long long gout = g.at(ox, oy, z0);
     f2 dxy0 = pk1(0.f), dxy1 = pk1(0.f);
     if (act) {
-        const float4 d4 = *(const float4 *)(a.dx + x);
-        dxy0 = add2(lo2(d4), pk1(a.dy[y]));
-        dxy1 = add2(hi2(d4), pk1(a.dy[y]));
+        const float4 d4 = *(const float4 *)(a.dx + ox);
+        dxy0 = add2(lo2(d4), pk1(a.dy[oy]));
+        dxy1 = add2(hi2(d4), pk1(a.dy[oy]));
     }
     constexpr bool f_snap = (FUSE & VF_SNAP) != 0, f_grad = (FUSE & VF_GRAD) != 0;
     constexpr bool f_il = (FUSE & VF_ILLUM) != 0, f_reg = FUSE != 0;
     [[maybe_unused]] const Fuse &fz = a.f;
-    [[maybe_unused]] const bool f_xy = f_reg && act && y >= fz.reg.lo[1] && y < fz.reg.hi[1] &&
-                                       x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0];
-    [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && x >= fz.reg.lo[0] &&
-                                        x + 3 < fz.reg.hi[0];
-    [[maybe_unused]] long long ri = f_reg ? fz.reg.at(x, y, z0) : 0;
+    [[maybe_unused]] const bool f_xy = f_reg && act && oy >= fz.reg.lo[1] && oy < fz.reg.hi[1] &&
+                                       ox + 3 >= fz.reg.lo[0] && ox < fz.reg.hi[0];
+    [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && ox >= fz.reg.lo[0] &&
+                                        ox + 3 < fz.reg.hi[0];
+    [[maybe_unused]] long long ri = f_reg ? fz.reg.at(ox, oy, z0) : 0;
     [[maybe_unused]] const long long rstride = f_reg ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
 
-    for (int j = 0; j < total; j++) {
+    float4 acc[NQ];   // divergence accumulators of the output planes zf-3 .. zf+4
 #pragma unroll
-        for (int k = 0; k < NQ - 1; k++) qu[k] = qu[k + 1];
-        const int s_in = j % NS;
-        mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
-        qu[NQ - 1] = *(const float4 *)(ringU + s_in * USLOT + su);
-        if (j < 2 * R - 1) {
-            if (j >= R) {     // planes that are never a flux plane of this chunk
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyU[(j + NS - R) % NS]);
-            }
-            continue;
-        }
-        // ======== F phase: flux plane zf ==========================================================
-        const int jf = j - (2 * R - 1);
-        const int sc = (j + NS - R) % NS, scc = jf % NC;
-        const float *pu = ringU + sc * USLOT;
-        float *fb = fbuf + (j & 1) * FBUF;
-        mbar_wait(&fullC[scc], (uint32_t)((jf / NC) & 1));
-        const float *pc = ringC + scc * CSLOT;
-        {
-            const float4 c4 = *(const float4 *)(pc + scn);
-            const f2 c0 = lo2(c4), c1 = hi2(c4);
-            // F_z = c D+z u from the register queue
-            f2 gz0 = pk1(0.f), gz1 = pk1(0.f);
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const float4 zp = qu[R - 1 + k], zm = qu[R - k];
-                gz0 = fma2s(cf.wz[k], sub2(lo2(zp), lo2(zm)), gz0);
-                gz1 = fma2s(cf.wz[k], sub2(hi2(zp), hi2(zm)), gz1);
-            }
-#pragma unroll
-            for (int k = 0; k < NQ - 1; k++) qf[k] = qf[k + 1];
-            qf[NQ - 1] = cat4(mul2(c0, gz0), mul2(c1, gz1));
-            // F_x, F_y of the own nodes
-            float w[12];
-            varc_window(pu + su, w);
-            f2 gx0, gx1;
-            varc_dplus_x(cf, w, gx0, gx1);
-            *(float4 *)(fb + sfx) = cat4(mul2(c0, gx0), mul2(c1, gx1));
-            const float4 cen = qu[R - 1];
-            f2 gy0 = pk1(0.f), gy1 = pk1(0.f);
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const float4 p = *(const float4 *)(pu + su + k * UPX);
-                const float4 m = (k == 1) ? cen : *(const float4 *)(pu + su - (k - 1) * UPX);
-                gy0 = fma2s(cf.wy[k], sub2(lo2(p), lo2(m)), gy0);
-                gy1 = fma2s(cf.wy[k], sub2(hi2(p), hi2(m)), gy1);
-            }
-            *(float4 *)(fb + FX + sfy) = cat4(mul2(c0, gy0), mul2(c1, gy1));
-        }
-        if (hx_on) {
-            const float4 c4 = *(const float4 *)(pc + hx_c);
-            float w[12];
-            varc_window(pu + hx_u, w);
-            f2 gx0, gx1;
-            varc_dplus_x(cf, w, gx0, gx1);
-            *(float4 *)(fb + hx_f) = cat4(mul2(lo2(c4), gx0), mul2(hi2(c4), gx1));
-        }
-        if (hy_on) {
-            const float4 c4 = *(const float4 *)(pc + hy_c);
-            f2 gy0 = pk1(0.f), gy1 = pk1(0.f);
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const float4 p = *(const float4 *)(pu + hy_u + k * UPX);
-                const float4 m = *(const float4 *)(pu + hy_u - (k - 1) * UPX);
-                gy0 = fma2s(cf.wy[k], sub2(lo2(p), lo2(m)), gy0);
-                gy1 = fma2s(cf.wy[k], sub2(hi2(p), hi2(m)), gy1);
-            }
-            *(float4 *)(fb + FX + hy_f) = cat4(mul2(lo2(c4), gy0), mul2(hi2(c4), gy1));
-        }
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&emptyU[sc]); mbar_arrive(&emptyC[scc]); }
-        named_bar_sync(1, NT);
-        // ======== D phase =========================================================================
-        {
-            float w[12];
-            varc_window(fb + sfx, w);
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float acc = 0.f;
-#pragma unroll
-                for (int k = 1; k <= R; k++)
-                    acc = __fmaf_rn(cf.wx[k], __fsub_rn(w[4 + e + k - 1], w[4 + e - k]), acc);
-                o[e] = acc;
-            }
-            const float *py = fb + FX + sfy;
-            f2 ly0 = pk1(0.f), ly1 = pk1(0.f);
-#pragma unroll
-            for (int k = 1; k <= R; k++) {
-                const float4 p = *(const float4 *)(py + (k - 1) * TX);
-                const float4 m = *(const float4 *)(py - k * TX);
-                ly0 = fma2s(cf.wy[k], sub2(lo2(p), lo2(m)), ly0);
-                ly1 = fma2s(cf.wy[k], sub2(hi2(p), hi2(m)), ly1);
-            }
-#pragma unroll
-            for (int k = 0; k < R - 1; k++) hq[k] = hq[k + 1];
-            hq[R - 1] = cat4(add2(pk(o[0], o[1]), ly0), add2(pk(o[2], o[3]), ly1));
-        }
-        if (j >= 4 * R - 2) {
-            // ---- output plane zo = zf-R+1: hq[0] is its D-x + D-y, qf[] its z-line, qu[0] its u ----
-            const int i = j - (4 * R - 2);
-            const int z = z0 + i;
-            const int sp = i % NP;
-            [[maybe_unused]] bool fin = false, fvec = false;
-            [[maybe_unused]] float4 us4, g4, il4;
+    for (int k = 0; k < NQ; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int pslot = 0, ppar = 0;
+
+    for (int j = FIRST; j < total; j++) {
+        const int zf = z0 - (3 * R - 1) + j;
+        const bool need_xy = zf >= z0 && zf < z1;
+        const bool out = j >= WARM;
+        const int z = z0 + j - WARM;                  // output plane zo = zf - 3
+        const float *fb = fbuf + (j & 1) * FBUF;
+        // ---- everything that comes from global memory is requested before the hand-over wait -----
+        float dz_s = 0.f;
+        [[maybe_unused]] bool fin = false, fvec = false;
+        [[maybe_unused]] float4 us4, G4, I4;
+        if (out) {
+            dz_s = __ldg(a.dz + z);
             if (f_reg) {
                 const bool zin = z >= fz.reg.lo[2] && z < fz.reg.hi[2];
                 fin = f_xy && zin;
                 fvec = f_vec && zin;
-                if (f_grad && f_vec && z + 3 >= fz.reg.lo[2] && z + 3 < fz.reg.hi[2]) {
-                    prefetch_l2(fz.usnap[0] + ri + 3 * rstride);
-                    prefetch_l2(fz.grad + ri + 3 * rstride);
+                if ((f_grad || f_il) && f_vec && z + 3 >= fz.reg.lo[2] && z + 3 < fz.reg.hi[2]) {
+                    if (f_grad) {
+                        prefetch_l2(fz.usnap[0] + ri + 3 * rstride);
+                        prefetch_l2(fz.grad + ri + 3 * rstride);
+                    }
+                    if (f_il) prefetch_l2(fz.illum + ri + 3 * rstride);
                 }
                 if (fvec) {
                     if (f_grad) {
                         us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
-                        g4 = *(const float4 *)(fz.grad + ri);
+                        G4 = *(const float4 *)(fz.grad + ri);
                     }
-                    if (f_il) il4 = *(const float4 *)(fz.illum + ri);
+                    if (f_il) I4 = *(const float4 *)(fz.illum + ri);
                 }
             }
-            f2 L0 = lo2(hq[0]), L1 = hi2(hq[0]);
-            {
-                // D-z F_z at zo: planes zo+k-1 (queue index R-1+k) and zo-k (index R-k) of the
-                // flux queue, whose newest entry is plane zf = zo+R-1
-                f2 lz0 = pk1(0.f), lz1 = pk1(0.f);
+        }
+        named_bar_sync(1 + (j & 1), NSYNC);
+        // ---- D-_x F_x + D-_y F_y of flux plane zf go to the accumulator of output plane zf --------
+        if (need_xy) {
+            const float *px = fb + sfx;
+            f2 lx0, lx1;
+            varc_dx<false>(cf.wx, *(const float4 *)(px - 4), *(const float4 *)px, *(const float4 *)(px + 4),
+                           lx0, lx1);
+            const float *py = fb + FX + sfy;
+            f2 ly0, ly1;
 #pragma unroll
-                for (int k = 1; k <= R; k++) {
-                    const float4 p = qf[R - 1 + k], m = qf[R - k];
-                    lz0 = fma2s(cf.wz[k], sub2(lo2(p), lo2(m)), lz0);
-                    lz1 = fma2s(cf.wz[k], sub2(hi2(p), hi2(m)), lz1);
-                }
-                L0 = add2(L0, lz0);
-                L1 = add2(L1, lz1);
+            for (int k = 1; k <= R; k++) {
+                const float4 p = *(const float4 *)(py + (k - 1) * TX);
+                const float4 m = *(const float4 *)(py - k * TX);
+                const f2 d0 = sub2(lo2(p), lo2(m)), d1 = sub2(hi2(p), hi2(m));
+                if (k == 1) { ly0 = mul2s(cf.wy[1], d0); ly1 = mul2s(cf.wy[1], d1); }
+                else { ly0 = fma2s(cf.wy[k], d0, ly0); ly1 = fma2s(cf.wy[k], d1, ly1); }
             }
-            mbar_wait(&fullP[sp], (uint32_t)((i / NP) & 1));
-            const float *pt = ringP + sp * 3 * PSLOT + st;
+            acc[R - 1] = cat4(add2(lo2(acc[R - 1]), add2(lx0, ly0)), add2(hi2(acc[R - 1]), add2(lx1, ly1)));
+        }
+        // ---- z part: D-_z out[z] = sum_k wz[k] (F[z+k-1] - F[z-k]), scattered from F_z of plane zf ---
+        const float *fz_ = fb + FX + FY + st;
+        {
+            const float4 Fz = *(const float4 *)fz_;
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                float4 &ap = acc[R - k];      // plane zf-k+1
+                ap = cat4(fma2s(cf.wz[k], lo2(Fz), lo2(ap)), fma2s(cf.wz[k], hi2(Fz), hi2(ap)));
+                float4 &bp = acc[R - 1 + k];  // plane zf+k
+                if (k == R) bp = cat4(mul2s(-cf.wz[k], lo2(Fz)), mul2s(-cf.wz[k], hi2(Fz)));
+                else bp = cat4(fma2s(-cf.wz[k], lo2(Fz), lo2(bp)), fma2s(-cf.wz[k], hi2(Fz), hi2(bp)));
+            }
+        }
+        if (out) {
+            const float4 uc = *(const float4 *)(fz_ + PSLOT);
+            const float4 H = acc[0];
+            mbar_wait(&fullP[pslot], (uint32_t)ppar);
+            const float *pt = ringP + pslot * 3 * PSLOT + st;
             const float4 up4 = *(const float4 *)pt, m4 = *(const float4 *)(pt + PSLOT);
             const float4 ir4 = *(const float4 *)(pt + 2 * PSLOT);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyP[sp]);
-            const float4 uc = qu[0];
+            if (lane == 0) mbar_arrive(&emptyP[pslot]);
+            if (++pslot == NP) { pslot = 0; ppar ^= 1; }
             // delta = (dt^2 L - sd (u - u-)) / (m irho + sd),  u+ = (u + (u - u-)) + delta
-            const f2 dzv = pk1(a.dz[z]);
+            const f2 dzv = pk1(dz_s);
             const f2 sd0 = mul2s(cf.dt, add2(dxy0, dzv)), sd1 = mul2s(cf.dt, add2(dxy1, dzv));
             const f2 den0 = fma2(lo2(m4), lo2(ir4), sd0), den1 = fma2(hi2(m4), hi2(ir4), sd1);
             const f2 r0 = pk(__frcp_rn(den0.x), __frcp_rn(den0.y));
             const f2 r1 = pk(__frcp_rn(den1.x), __frcp_rn(den1.y));
             const f2 d10 = sub2(lo2(uc), lo2(up4)), d11 = sub2(hi2(uc), hi2(up4));
-            const f2 dl0 = mul2(fma2(mul2s(-1.f, sd0), d10, mul2s(cf.dt2, L0)), r0);
-            const f2 dl1 = mul2(fma2(mul2s(-1.f, sd1), d11, mul2s(cf.dt2, L1)), r1);
+            const f2 dl0 = mul2(fma2(mul2s(-1.f, sd0), d10, mul2s(cf.dt2, lo2(H))), r0);
+            const f2 dl1 = mul2(fma2(mul2s(-1.f, sd1), d11, mul2s(cf.dt2, hi2(H))), r1);
             const f2 un0 = add2(add2(lo2(uc), d10), dl0), un1 = add2(add2(hi2(uc), d11), dl1);
             if (act) {
                 float *o = a.up + gout;
@@ -359,20 +383,20 @@ __global__ void __launch_bounds__(varc::NTHREADS, 1)
                     const float v[4] = {un0.x, un0.y, un1.x, un1.y};
 #pragma unroll
                     for (int e = 0; e < 4; e++)
-                        if (x + e < g.n[0]) o[e] = v[e];
+                        if (ox + e < g.n[0]) o[e] = v[e];
                 }
             }
             if (f_reg && fin) {
                 if (fvec) {
                     if (f_snap) __stcs((float4 *)(fz.snap[0] + ri), uc);
                     if (f_il)
-                        *(float4 *)(fz.illum + ri) = cat4(fma2(mul2s(cf.dt, lo2(uc)), lo2(uc), lo2(il4)),
-                                                          fma2(mul2s(cf.dt, hi2(uc)), hi2(uc), hi2(il4)));
+                        *(float4 *)(fz.illum + ri) = cat4(fma2(mul2s(cf.dt, lo2(uc)), lo2(uc), lo2(I4)),
+                                                          fma2(mul2s(cf.dt, hi2(uc)), hi2(uc), hi2(I4)));
                     if (f_grad) {
-                        // gradm -= gcoef * irho * u_s * delta   (fluxdiv3d_vec)
+                        // gradm -= gcoef * irho * u_s * delta   (sensitivity.py:55-69)
                         const f2 w0 = mul2(mul2s(-fz.gcoef, lo2(ir4)), lo2(us4));
                         const f2 w1 = mul2(mul2s(-fz.gcoef, hi2(ir4)), hi2(us4));
-                        *(float4 *)(fz.grad + ri) = cat4(fma2(w0, dl0, lo2(g4)), fma2(w1, dl1, hi2(g4)));
+                        *(float4 *)(fz.grad + ri) = cat4(fma2(w0, dl0, lo2(G4)), fma2(w1, dl1, hi2(G4)));
                     }
                 } else {
                     const float ucs[4] = {uc.x, uc.y, uc.z, uc.w};
@@ -380,16 +404,22 @@ __global__ void __launch_bounds__(varc::NTHREADS, 1)
                     const float irs[4] = {ir4.x, ir4.y, ir4.z, ir4.w};
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
-                        if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
+                        if (ox + e < fz.reg.lo[0] || ox + e >= fz.reg.hi[0]) continue;
                         if (f_snap) fz.snap[0][ri + e] = ucs[e];
-                        if (f_il) fz.illum[ri + e] += cf.dt * ucs[e] * ucs[e];
-                        if (f_grad) fz.grad[ri + e] -= fz.gcoef * irs[e] * fz.usnap[0][ri + e] * dls[e];
+                        if (f_il) fz.illum[ri + e] = __fmaf_rn(__fmul_rn(cf.dt, ucs[e]), ucs[e], fz.illum[ri + e]);
+                        if (f_grad)
+                            fz.grad[ri + e] = __fmaf_rn(__fmul_rn(__fmul_rn(-fz.gcoef, irs[e]), fz.usnap[0][ri + e]),
+                                                        dls[e], fz.grad[ri + e]);
                     }
                 }
             }
             gout += g.sz;
             if (f_reg) ri += rstride;
         }
+        // this flux buffer may be overwritten by the F warps two planes from now
+        if (j + 2 < total) named_bar_arrive(3 + (j & 1), NSYNC);
+#pragma unroll
+        for (int k = 0; k < NQ - 1; k++) acc[k] = acc[k + 1];
     }
 }
 
@@ -437,10 +467,11 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s)
     const int ntx = (M->N[0] + varc::TX - 1) / varc::TX, nty = (M->N[1] + varc::TY - 1) / varc::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
-        // one CTA per SM: minimise waves x (planes per chunk + the 4R-2 warm-up planes of a chunk)
+        // two CTAs per SM: minimise waves x (planes per chunk + the 4R-2 warm-up planes of a chunk)
         long long best = -1;
         for (int c = 1; c <= 8 && c * 32 <= M->N[2]; c++) {
-            const long long waves = ((long long)ntx * nty * c + ctx->num_sms - 1) / ctx->num_sms;
+            const long long slots = 2LL * ctx->num_sms;
+            const long long waves = ((long long)ntx * nty * c + slots - 1) / slots;
             const long long cost = waves * ((M->N[2] + c - 1) / c + 4 * varc::R - 2);
             if (best < 0 || cost < best) { best = cost; nzc = c; }
         }

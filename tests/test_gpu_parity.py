@@ -90,7 +90,7 @@ def test_born_and_gradient_parity_and_dot(kind, ndim, so):
     assert abs((c - e) / (c + e)) < TOL_DOT
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3), ("tti", 3)])
 def test_fwi_objective_and_options(kind, ndim):
     """fwi objective value + gradient, t_sub, checkpointing, physical-domain snapshots,
     lsrtm (born_fwd, nlind), illumination (test_gradients.jl, test_all_options.jl)."""
@@ -264,7 +264,7 @@ def test_device_resident_path_matches_host_path():
     assert abs(float(red[-1].item()) - 2 * float(f)) <= 1e-5 * abs(2 * float(f))
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3)])
 def test_free_surface_parity(kind, ndim):
     """Options(free_surface=true): no layer above z=0 (models.py:174-176,269-272) and the mirror
     u(-k) = -u(k-1), u(0) = 0 after every update (fields_exprs.py:106-137)."""
@@ -285,7 +285,7 @@ def test_free_surface_parity(kind, ndim):
     assert rel_l2(g, go) < TOL_GRAD
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2), ("tti", 3)])
 def test_extended_and_wavefield_sources(kind, ndim):
     """The remaining entry points of src/pysource/interface.py: forward_rec_w (:50), adjoint_w
     (:174), born_rec_w (:244), J_adjoint(ws=...) and forward_wf_src / _norec (:114, :145);
