@@ -19,9 +19,14 @@
 // The roles hand the double-buffered flux plane over through named barriers (bar.arrive / bar.sync).
 // ~80 registers and 95 KB of shared memory: two CTAs per SM.
 // HBM traffic: 20 B per grid point (u, u(t-1), m, irho read; u(t+1) written) + halos that miss L2.
+// Measured (C5-size grid, 40.8 M points): plain 0.315 ms, save 0.345, imaging condition 0.48 ms
+// per step against 0.50 / 0.52 / 0.55 ms for the two passes.  ncu (gpurun_out/r01_varc3d_v2): 206 M
+// warp instructions, 63% issue-active with 24 warps per SM, DRAM 0.95 GB = 3.0 TB/s: bound by
+// instruction issue (only 29% of the instructions are arithmetic: register-queue moves 15%,
+// barrier / mbarrier / address bookkeeping the rest), not by HBM (20 B/pt = 0.125 ms).
 // History: the first version (64 x 16 tile, F and D in the same 8 warps behind one barrier, flux
-// and partial-sum queues in 167 registers, one CTA per SM) ran 0.38 ms/step on the C5-size grid
-// against 0.50 ms for the two passes; ncu: 40% issue-active, latency-bound.
+// and partial-sum queues in 167 registers, one CTA per SM) ran 0.38 ms/step; ncu: 40%
+// issue-active, latency-bound.
 #include "tma_util.cuh"
 
 namespace varc {
@@ -162,14 +167,82 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
         return;
     }
 
+    if (tid < NI) {
+        // ===== F role, tile warps: F_x, F_y, F_z of the own nodes ====================================
+        const int cx = tid & (TXG - 1), cy = tid / TXG;
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;   // node group inside a u plane
+        const int sc = (cy + R) * CPX + 4 * cx + R;               // ... inside a coefficient plane
+        const int sfx = cy * FXW + 4 * (cx + 1);                  // ... inside the x-extended flux plane
+        const int sfy = (cy + R) * TX + 4 * cx;                   // ... inside the y-extended flux plane
+        const int st = cy * TX + 4 * cx;                          // ... inside a tile
+        float4 q[NQ];   // u of planes zf-3 .. zf+4 at this node group
+#pragma unroll
+        for (int k = 0; k < NQ; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < FIRST; j++) {
+#pragma unroll
+            for (int k = 0; k < NQ - 1; k++) q[k] = q[k + 1];
+            mbar_wait(&fullU[j], 0);
+            q[NQ - 1] = *(const float4 *)(ringU + j * USLOT + su);
+            if (j < R - 1) {   // the first three planes of a chunk are never a flux plane
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyU[j]);
+            }
+        }
+        int cslot = 0, cpar = 0;
+        for (int j = FIRST; j < total; j++) {
+#pragma unroll
+            for (int k = 0; k < NQ - 1; k++) q[k] = q[k + 1];
+            const int s_in = j & (NS - 1), s_c = (j + NS - R) & (NS - 1);
+            mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
+            q[NQ - 1] = *(const float4 *)(ringU + s_in * USLOT + su);
+            const int zf = z0 - (3 * R - 1) + j;
+            const bool need_xy = zf >= z0 && zf < z1;       // its x / y flux is used
+            float *fb = fbuf + (j & 1) * FBUF;
+            mbar_wait(&fullC[cslot], (uint32_t)cpar);
+            const float *pl = ringU + s_c * USLOT + su;
+            const float4 c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
+            const float4 cen = q[R - 1];
+            f2 gx0, gx1, gy0, gy1, gz0, gz1;
+            varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), gx0, gx1);
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                const float4 p = *(const float4 *)(pl + k * UPX);
+                const float4 m = (k == 1) ? cen : *(const float4 *)(pl - (k - 1) * UPX);
+                const f2 dy0 = sub2(lo2(p), lo2(m)), dy1 = sub2(hi2(p), hi2(m));
+                const float4 zp = q[R - 1 + k], zm = q[R - k];
+                const f2 dz0 = sub2(lo2(zp), lo2(zm)), dz1 = sub2(hi2(zp), hi2(zm));
+                if (k == 1) {
+                    gy0 = mul2s(cf.wy[1], dy0); gy1 = mul2s(cf.wy[1], dy1);
+                    gz0 = mul2s(cf.wz[1], dz0); gz1 = mul2s(cf.wz[1], dz1);
+                } else {
+                    gy0 = fma2s(cf.wy[k], dy0, gy0); gy1 = fma2s(cf.wy[k], dy1, gy1);
+                    gz0 = fma2s(cf.wz[k], dz0, gz0); gz1 = fma2s(cf.wz[k], dz1, gz1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
+            if (++cslot == NC) { cslot = 0; cpar ^= 1; }
+            // the flux buffer of this parity was read by the D warps two planes ago
+            if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
+            if (need_xy) {
+                *(float4 *)(fb + sfx) = cat4(mul2(lo2(c4), gx0), mul2(hi2(c4), gx1));
+                *(float4 *)(fb + FX + sfy) = cat4(mul2(lo2(c4), gy0), mul2(hi2(c4), gy1));
+            }
+            float *fz_ = fb + FX + FY + st;
+            *(float4 *)fz_ = cat4(mul2(lo2(c4), gz0), mul2(hi2(c4), gz1));
+            *(float4 *)(fz_ + PSLOT) = q[0];      // u of the output plane zf-3
+            __threadfence_block();
+            named_bar_arrive(1 + (j & 1), NSYNC);
+        }
+        return;
+    }
     if (tid < NF) {
-        // ===== F role ================================================================================
-        const bool tile = tid < NI;                    // warps 0-3
-        const bool xh = !tile && tid < NI + 32;        // warp 4
+        // ===== F role, halo warps: F_x one group left / right of every row (warp 4), F_y of rows
+        // -4..-1 and 16..18 (warps 5, 6).  No z history: they only ever read the flux plane.
+        const bool xh = tid < NI + 32;
         int cx, cy;
         bool wr = true;
-        if (tile) { cx = tid & (TXG - 1); cy = tid / TXG; }
-        else if (xh) {
+        if (xh) {
             const int h = tid - NI;
             cx = (h & 1) ? TXG : -1;
             cy = h >> 1;
@@ -179,48 +252,27 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             cy = row < R ? row - R : TY + min(row, 2 * R - 2) - R;
             wr = row < 2 * R - 1;
         }
-        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;   // node group inside a u plane
-        const int sc = (cy + R) * CPX + 4 * cx + R;               // ... inside a coefficient plane
-        const int sfx = cy * FXW + 4 * (cx + 1);                  // ... inside the x-extended flux plane
-        const int sfy = (cy + R) * TX + 4 * cx;                   // ... inside the y-extended flux plane
-        const int st = cy * TX + 4 * cx;                          // ... inside a tile (tile threads)
-
-        float4 q[NQ];   // u of planes zf-3 .. zf+4 at this node group (tile threads)
-#pragma unroll
-        for (int k = 0; k < NQ; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;
+        const int sc = (cy + R) * CPX + 4 * cx + R;
+        const int sf = xh ? cy * FXW + 4 * (cx + 1) : FX + (cy + R) * TX + 4 * cx;
+        if (lane == 0)
+            for (int j = 0; j < R - 1; j++) mbar_arrive(&emptyU[j]);   // planes they never read
         int cslot = 0, cpar = 0;
-
-        for (int j = 0; j < total; j++) {
-#pragma unroll
-            for (int k = 0; k < NQ - 1; k++) q[k] = q[k + 1];
-            const int s_in = j & (NS - 1);
-            mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
-            if (tile) q[NQ - 1] = *(const float4 *)(ringU + s_in * USLOT + su);
-            if (j < FIRST) {
-                if (j < R - 1) {   // the first three planes of a chunk are never a flux plane
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&emptyU[s_in]);
-                }
-                continue;
-            }
-            const int zf = z0 - (3 * R - 1) + j;
-            const bool need_xy = zf >= z0 && zf < z1;       // its x / y flux is used
+        for (int j = FIRST; j < total; j++) {
             const int s_c = (j + NS - R) & (NS - 1);
+            const int zf = z0 - (3 * R - 1) + j;
+            const bool need_xy = zf >= z0 && zf < z1;
             float *fb = fbuf + (j & 1) * FBUF;
+            mbar_wait(&fullU[s_c], (uint32_t)(((j - R) / NS) & 1));
             mbar_wait(&fullC[cslot], (uint32_t)cpar);
-            f2 fx0, fx1, fy0, fy1, fz0, fz1;
-            fx0 = fx1 = fy0 = fy1 = fz0 = fz1 = pk1(0.f);
-            if (tile || need_xy) {
+            f2 g0 = pk1(0.f), g1 = pk1(0.f);
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (need_xy) {
                 const float *pl = ringU + s_c * USLOT + su;
-                const float4 c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
-                const float4 cen = tile ? q[R - 1] : *(const float4 *)pl;
-                if ((tile && need_xy) || xh) {
-                    f2 g0, g1;
-                    varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), g0, g1);
-                    fx0 = mul2(lo2(c4), g0); fx1 = mul2(hi2(c4), g1);
-                }
-                if ((tile && need_xy) || (!tile && !xh)) {
-                    f2 g0, g1;
+                c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
+                const float4 cen = *(const float4 *)pl;
+                if (xh) varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), g0, g1);
+                else {
 #pragma unroll
                     for (int k = 1; k <= R; k++) {
                         const float4 p = *(const float4 *)(pl + k * UPX);
@@ -229,34 +281,13 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                         if (k == 1) { g0 = mul2s(cf.wy[1], d0); g1 = mul2s(cf.wy[1], d1); }
                         else { g0 = fma2s(cf.wy[k], d0, g0); g1 = fma2s(cf.wy[k], d1, g1); }
                     }
-                    fy0 = mul2(lo2(c4), g0); fy1 = mul2(hi2(c4), g1);
-                }
-                if (tile) {
-                    f2 g0, g1;
-#pragma unroll
-                    for (int k = 1; k <= R; k++) {
-                        const float4 zp = q[R - 1 + k], zm = q[R - k];
-                        const f2 d0 = sub2(lo2(zp), lo2(zm)), d1 = sub2(hi2(zp), hi2(zm));
-                        if (k == 1) { g0 = mul2s(cf.wz[1], d0); g1 = mul2s(cf.wz[1], d1); }
-                        else { g0 = fma2s(cf.wz[k], d0, g0); g1 = fma2s(cf.wz[k], d1, g1); }
-                    }
-                    fz0 = mul2(lo2(c4), g0); fz1 = mul2(hi2(c4), g1);
                 }
             }
             __syncwarp();
             if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
             if (++cslot == NC) { cslot = 0; cpar ^= 1; }
-            // the flux buffer of this parity was read by the D warps two planes ago
             if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
-            if (need_xy && wr) {
-                if (tile || xh) *(float4 *)(fb + sfx) = cat4(fx0, fx1);
-                if (tile || !xh) *(float4 *)(fb + FX + sfy) = cat4(fy0, fy1);
-            }
-            if (tile) {
-                float *fz_ = fb + FX + FY + st;
-                *(float4 *)fz_ = cat4(fz0, fz1);
-                *(float4 *)(fz_ + PSLOT) = q[0];      // u of the output plane zf-3
-            }
+            if (need_xy && wr) *(float4 *)(fb + sf) = cat4(mul2(lo2(c4), g0), mul2(hi2(c4), g1));
             __threadfence_block();
             named_bar_arrive(1 + (j & 1), NSYNC);
         }
@@ -315,12 +346,9 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                     }
                     if (f_il) prefetch_l2(fz.illum + ri + 3 * rstride);
                 }
-                if (fvec) {
-                    if (f_grad) {
-                        us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
-                        G4 = *(const float4 *)(fz.grad + ri);
-                    }
-                    if (f_il) I4 = *(const float4 *)(fz.illum + ri);
+                if (fvec && f_grad) {
+                    us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
+                    G4 = *(const float4 *)(fz.grad + ri);
                 }
             }
         }
@@ -389,9 +417,11 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             if (f_reg && fin) {
                 if (fvec) {
                     if (f_snap) __stcs((float4 *)(fz.snap[0] + ri), uc);
-                    if (f_il)
+                    if (f_il) {
+                        I4 = *(const float4 *)(fz.illum + ri);
                         *(float4 *)(fz.illum + ri) = cat4(fma2(mul2s(cf.dt, lo2(uc)), lo2(uc), lo2(I4)),
                                                           fma2(mul2s(cf.dt, hi2(uc)), hi2(uc), hi2(I4)));
+                    }
                     if (f_grad) {
                         // gradm -= gcoef * irho * u_s * delta   (sensitivity.py:55-69)
                         const f2 w0 = mul2(mul2s(-fz.gcoef, lo2(ir4)), lo2(us4));
@@ -472,7 +502,9 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s)
         for (int c = 1; c <= 8 && c * 32 <= M->N[2]; c++) {
             const long long slots = 2LL * ctx->num_sms;
             const long long waves = ((long long)ntx * nty * c + slots - 1) / slots;
-            const long long cost = waves * ((M->N[2] + c - 1) / c + 4 * varc::R - 2);
+            // (a single chunk per tile column leaves the launch waiting for its slowest CTA:
+            // measured 0.323 vs 0.315 ms on the C5-size grid, hence the 6% handicap)
+            const long long cost = waves * ((M->N[2] + c - 1) / c + 4 * varc::R - 2) * (c == 1 ? 106 : 100);
             if (best < 0 || cost < best) { best = cost; nzc = c; }
         }
         if (nzc <= 0) nzc = 1;

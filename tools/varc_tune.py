@@ -1,25 +1,40 @@
-"""Variable-density single-pass kernel: z-chunk sweep on the C5-size grid."""
+"""Single-pass 3-D variable-density kernel against the two-pass form on the C5-size grid: time per
+step of the plain / save / IC flavours and relative difference of shot record and gradient.
+usage: python tools/varc_tune.py [nt] [zchunks e.g. 0,1,2]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import judi_jl_b200 as J
 from bench import velocity, ricker
-n = (301, 301, 201); nt = 22
+nt = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+zcs = [int(s) for s in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+n = (301, 301, 201)
 v = velocity(n)
 rho = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
 ctx = J.get_context(0)
 gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32), rho=rho)
-q = ricker(nt, float(gm.critical_dt), 0.008)
+dt = float(gm.critical_dt)
+q = ricker(nt, dt, 0.03)
 src = np.array([[3750., 3750., 50.]], dtype=np.float32)
-rec = np.array([[3000., 3000., 50.]], dtype=np.float32)
+xr, yr = np.meshgrid(np.linspace(3500., 4000., 11), np.linspace(3500., 4000., 11), indexing="ij")
+rec = np.stack([xr.ravel(), yr.ravel(), np.full(xr.size, 50.)], axis=1).astype(np.float32)
+dobs = np.zeros((nt, rec.shape[0]), dtype=np.float32)
 ref = None
-for fused, zc in [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 8)]:
-    ctx.set_option("varc_fused", fused); ctx.set_option("zchunks", zc)
-    gm2 = gm
-    d1 = J.forward_rec(gm2, src, q, rec)[0]
-    ctx.set_option("timing", 1); ctx.reset_stats()
-    J.forward_rec(gm2, src, q, rec)
-    st = ctx.stencil_stats(); ctx.set_option("timing", 0)
-    if ref is None: ref = d1
-    print("fused %d zchunks %d: %.4f ms/step  rel diff vs two-pass %.2e" % (
-        fused, zc, st["ms"] / st["launches"], np.linalg.norm(d1 - ref) / np.linalg.norm(ref)), flush=True)
+for fused in (0, 1):
+    for zc in (zcs if fused else [0]):
+        ctx.set_option("varc_fused", fused); ctx.set_option("zchunks", zc)
+        d1 = J.forward_rec(gm, src, q, rec)[0]
+        f, g = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=1, snapshot_region="physical")[:2]
+        ctx.set_option("timing", 1); ctx.reset_stats()
+        J.forward_rec(gm, src, q, rec)
+        st0 = ctx.stencil_stats(); ctx.reset_stats()
+        J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=1, snapshot_region="physical")
+        st = ctx.stencil_stats(); ctx.set_option("timing", 0)
+        if ref is None: ref = (d1, g)
+        ms = {k: v_["ms"] / v_["launches"] for k, v_ in st["kinds"].items()}
+        ms["plain"] = st0["ms"] / st0["launches"]
+        print("varc_fused %d zchunks %d: %s  |d|=%.4e |g|=%.4e  rel diff vs first: rec %.2e grad %.2e" % (
+            fused, zc, " ".join("%s %.4f ms" % kv for kv in sorted(ms.items())),
+            np.linalg.norm(d1), np.linalg.norm(g),
+            np.linalg.norm(d1 - ref[0]) / np.linalg.norm(ref[0]),
+            np.linalg.norm(g - ref[1]) / np.linalg.norm(ref[1])), flush=True)
