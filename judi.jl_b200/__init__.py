@@ -13,7 +13,7 @@ The directory name contains a dot, so the package is imported through the top-le
 `judi_jl_b200` (see /judi_jl_b200.py).
 """
 from ._lib import JudiB200Error, LIB_PATH  # noqa: F401
-from .models import Model, Context, get_context  # noqa: F401
+from .models import Model, Context, get_context, host_register, host_unregister  # noqa: F401
 from . import interface  # noqa: F401
 from .interface import (forward_rec, forward_no_rec, born_rec, J_adjoint, forward_rec_w,  # noqa: F401
                         adjoint_w, born_rec_w, forward_wf_src, forward_wf_src_norec)

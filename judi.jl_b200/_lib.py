@@ -51,6 +51,8 @@ SIGNATURES = {
     "judi_ctx_create": (ctypes.c_void_p, [ctypes.c_int]),
     "judi_ctx_destroy": (None, [ctypes.c_void_p]),
     "judi_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "judi_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "judi_ctx_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "judi_ctx_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "judi_ctx_stencil_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),

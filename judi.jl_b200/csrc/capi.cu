@@ -73,6 +73,27 @@ int judi_ctx_synchronize(judi_ctx *ctx)
 
 void *judi_ctx_stream(judi_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+int judi_host_register(void *ptr, size_t nbytes)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ptr != nullptr && nbytes > 0, "judi_host_register: empty range");
+    cudaError_t e = cudaHostRegister(ptr, nbytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return 0; }
+    CUDA_CHECK(e);
+    return 0;
+    API_END(1)
+}
+
+int judi_host_unregister(void *ptr)
+{
+    API_BEGIN
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { (void)cudaGetLastError(); return 0; }
+    CUDA_CHECK(e);
+    return 0;
+    API_END(1)
+}
+
 long long judi_ctx_launch_count(judi_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, double *points)

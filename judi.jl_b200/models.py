@@ -52,6 +52,18 @@ class Context(object):
         L.check(L.lib().judi_ctx_reset_stats(self.h))
 
 
+def host_register(a):
+    """Page-lock a host array that outlives many shots (model, observed data, gradient buffer):
+    later copies of it run at PCIe speed.  Returns the array."""
+    a = np.asarray(a)
+    L.check(L.lib().judi_host_register(ctypes.c_void_p(a.ctypes.data), a.nbytes))
+    return a
+
+
+def host_unregister(a):
+    L.check(L.lib().judi_host_unregister(ctypes.c_void_p(np.asarray(a).ctypes.data)))
+
+
 def get_context(device=None):
     """Context of `device` (default: LOCAL_RANK, else 0), created on first use."""
     import os

@@ -264,6 +264,25 @@ def test_device_resident_path_matches_host_path():
     assert abs(float(red[-1].item()) - 2 * float(f)) <= 1e-5 * abs(2 * float(f))
 
 
+def test_registered_host_arrays_give_identical_results():
+    """judi_host_register: page-locking the caller's arrays changes the copy path, not the result."""
+    J, args, gm, om, src, rec, q, dt = both("iso", 3, 8)
+    d, _ = J.forward_rec(gm, src, q, rec)
+    dobs = (0.9 * d).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    m_pin = J.host_register(np.array(args["m"], order="F"))
+    q_pin, dobs_pin = J.host_register(q.copy()), J.host_register(dobs.copy())
+    J.host_register(q_pin)                      # registering twice is not an error
+    try:
+        gm2 = J.Model(**dict(args, m=m_pin))
+        f2, g2, _, _ = J.J_adjoint(gm2, src, q_pin, rec, dobs_pin, return_obj=True)
+        assert f2 == f and np.array_equal(g2, g)
+    finally:
+        for a in (m_pin, q_pin, dobs_pin):
+            J.host_unregister(a)
+    J.host_unregister(q_pin)                    # neither is unregistering twice
+
+
 @pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3)])
 def test_free_surface_parity(kind, ndim):
     """Options(free_surface=true): no layer above z=0 (models.py:174-176,269-272) and the mirror
