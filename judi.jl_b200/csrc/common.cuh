@@ -276,6 +276,8 @@ struct StepArgs {
     const float *qsrc;         // TMA kernel, Born linearised pass: read delta of the background
 };
 void stencil_step(const judi_model *M, const StepArgs &a);
+// true if a Born step of this model (imaging condition "as") runs on the single-pass flux kernels
+bool flux_born_single_pass(const judi_model *M);
 
 // Working set of one propagation: wavefield buffers + scratch for the flux form + tensor maps
 struct Wavefield {
@@ -294,6 +296,7 @@ struct Wavefield {
     CUtensorMap tmap_par[6];      // 3-D TTI single pass: parameter planes A0, B0, C0, r
     bool has_tmap = false;
     bool two_pass_only = false;   // flux-form physics: never take the single-pass kernels
+    bool generic_only = false;    // flux-form physics: one-point-per-thread kernels only (isic / fwi Born)
     void init(const judi_model *M, bool born_scratch);
     void swap() { cur = 1 - cur; }
     float *level(int f) { return b[f][cur].p; }

@@ -502,6 +502,11 @@ static void step_ndim(const judi_model *M, const StepArgs &s)
 #undef DISPATCH_R
 }
 
+bool flux_born_single_pass(const judi_model *M)
+{
+    return M->ctx->opt_kernel3d == 1 && tti3d_supported(M);
+}
+
 // One leapfrog step of every field of the model (+ fused extras), timed with CUDA events when
 // the context asks for it.
 void stencil_step(const judi_model *M, const StepArgs &s)
@@ -554,9 +559,10 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.qsrc = s.scratch->dd[0].p;
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
-    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->two_pass_only) &&
-             (tti3d_step(M, s) || varc3d_step(M, s))) { /* single pass */ }
-    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && flux3d_step(M, s)) { /* vectorised */ }
+    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
+             !(s.scratch && s.scratch->two_pass_only) && (tti3d_step(M, s) || varc3d_step(M, s))) { /* single pass */ }
+    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
+             flux3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);
     if (timed) {

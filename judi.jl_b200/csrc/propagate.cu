@@ -556,9 +556,14 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     W.init(M, born);
     if (born) WL.init(M, false);
     // Checkpointing recomputes the background field with plain steps and must reproduce the Born
-    // forward sweep bit for bit; Born steps the flux-form physics (TTI, variable density) with
-    // the two-pass kernels, so every step of this wavefield does.
-    W.two_pass_only = born;
+    // forward sweep bit for bit, so every step of this wavefield takes the kernel family the Born
+    // step takes: single pass where it has a Born flavour (tti3d.cu), else the two-pass kernels;
+    // the one-point-per-thread kernels for the isic / fwi Born sources of the flux-form physics.
+    {
+        const bool fluxp = M->tti || M->irho_field;
+        W.generic_only = born && fluxp && o->ic != JUDI_IC_AS;
+        W.two_pass_only = born && !W.generic_only && !flux_born_single_pass(M);
+    }
     DevBuf Iu, Iv, grad(ctx, (size_t)reg.slot, true);
     if (illum_u) Iu = DevBuf(ctx, (size_t)reg.slot, true);
     if (illum_v) Iv = DevBuf(ctx, (size_t)reg.slot, true);

@@ -85,9 +85,14 @@ struct TtiArgs {
     float irho_c;
     int zchunk;
     Fuse f;
+    float *dd_out[2];        // Born background pass: write delta = u+ - 2u + u- of both fields
+    const float *dd_in[2];   // Born linearised pass: delta of the background fields ...
+    const float *dm;         // ... and the model perturbation: q_f = -dm irho delta_f
 };
 
-enum { TF_SNAP = 1, TF_GRAD = 2, TF_ILLUM = 4 };
+// what rides on the step (compile-time mask): snapshot save, imaging condition, illumination,
+// Born delta out (background field) / Born source in (linearised field)
+enum { TF_SNAP = 1, TF_GRAD = 2, TF_ILLUM = 4, TF_DDOUT = 8, TF_QSRC = 16 };
 
 // staggered first derivative along x at the 4 nodes of a group from the 12-float row window
 // centred on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2),
@@ -355,7 +360,8 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
         dxy1 = add2(hi2(d4), pk1(a.dy[oy]));
     }
     constexpr bool f_snap = (FUSE & TF_SNAP) != 0, f_grad = (FUSE & TF_GRAD) != 0;
-    constexpr bool f_il = (FUSE & TF_ILLUM) != 0, f_reg = FUSE != 0;
+    constexpr bool f_il = (FUSE & TF_ILLUM) != 0, f_reg = (FUSE & (TF_SNAP | TF_GRAD | TF_ILLUM)) != 0;
+    constexpr bool f_dd = (FUSE & TF_DDOUT) != 0, f_q = (FUSE & TF_QSRC) != 0;
     [[maybe_unused]] const Fuse &fz = a.f;
     [[maybe_unused]] const bool f_xy = f_reg && act && oy >= fz.reg.lo[1] && oy < fz.reg.hi[1] &&
                                        ox + 3 >= fz.reg.lo[0] && ox < fz.reg.hi[0];
@@ -384,8 +390,15 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
             float dz_s = 0.f;
             [[maybe_unused]] bool fin = false, fvec = false;
             [[maybe_unused]] float4 us1, us2, G4, I4;
+            [[maybe_unused]] float4 dq1 = make_float4(0.f, 0.f, 0.f, 0.f), dq2 = dq1, dm4 = dq1;
             if (out) {
                 dz_s = __ldg(a.dz + z);
+                if (f_q && act) {
+                    // (a partial group at the x edge reads into the zero halo of the allocation)
+                    dq1 = *(const float4 *)(a.dd_in[0] + gout);
+                    dq2 = *(const float4 *)(a.dd_in[1] + gout);
+                    dm4 = __ldg((const float4 *)(a.dm + gout));
+                }
                 if (f_reg) {
                     const bool zin = z >= fz.reg.lo[2] && z < fz.reg.hi[2];
                     fin = f_xy && zin;
@@ -474,17 +487,35 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                 for (int f = 0; f < 2; f++) {
                     const float4 uc = f ? uc2 : uc1, up = f ? up2 : up1, H = f ? H2 : H1;
                     const f2 d10 = sub2(lo2(uc), lo2(up)), d11 = sub2(hi2(uc), hi2(up));
-                    dl[f][0] = mul2(fma2(nsd0, d10, mul2s(cf.dt2, lo2(H))), r0);
-                    dl[f][1] = mul2(fma2(nsd1, d11, mul2s(cf.dt2, hi2(H))), r1);
-                    const f2 un0 = add2(add2(lo2(uc), d10), dl[f][0]), un1 = add2(add2(hi2(uc), d11), dl[f][1]);
+                    f2 h0 = mul2s(cf.dt2, lo2(H)), h1 = mul2s(cf.dt2, hi2(H));
+                    if (f_q) {
+                        // dt^2 * lin_src = -dm irho (u+ - 2u + u-) of the background field
+                        // (sensitivity.py:174-188; the post-injection part is added by sparse.cu)
+                        const float4 dq = f ? dq2 : dq1;
+                        const f2 w0 = mul2s(-a.irho_c, lo2(dm4)), w1 = mul2s(-a.irho_c, hi2(dm4));
+                        h0 = fma2(w0, lo2(dq), h0);
+                        h1 = fma2(w1, hi2(dq), h1);
+                    }
+                    // one explicit fma for the update: ptxas contracts a packed mul + add pair in the
+                    // flavours that do not also store delta, and the field must not depend on the flavour
+                    const f2 t0 = fma2(nsd0, d10, h0), t1 = fma2(nsd1, d11, h1);
+                    dl[f][0] = mul2(t0, r0);
+                    dl[f][1] = mul2(t1, r1);
+                    const f2 un0 = fma2(t0, r0, add2(lo2(uc), d10)), un1 = fma2(t1, r1, add2(hi2(uc), d11));
                     if (act) {
                         float *o = (f ? a.up2 : a.up1) + gout;
-                        if (xfull) *(float4 *)o = cat4(un0, un1);
-                        else {
+                        if (xfull) {
+                            *(float4 *)o = cat4(un0, un1);
+                            if (f_dd) *(float4 *)(a.dd_out[f] + gout) = cat4(dl[f][0], dl[f][1]);
+                        } else {
                             const float v[4] = {un0.x, un0.y, un1.x, un1.y};
+                            const float dv[4] = {dl[f][0].x, dl[f][0].y, dl[f][1].x, dl[f][1].y};
 #pragma unroll
                             for (int e = 0; e < 4; e++)
-                                if (ox + e < g.n[0]) o[e] = v[e];
+                                if (ox + e < g.n[0]) {
+                                    o[e] = v[e];
+                                    if (f_dd) a.dd_out[f][gout + e] = dv[e];
+                                }
                         }
                     }
                 }
@@ -575,8 +606,9 @@ static int tti3d_chunks(const judi_ctx *ctx, int ntiles, int nz)
     return best;
 }
 
+// lin: launch on the linearised wavefield (Born source in); otherwise on the background field
 template <int FUSE>
-static void tti3d_launch(const judi_model *M, const StepArgs &s)
+static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
 {
     judi_ctx *ctx = M->ctx;
     // register queues: 2 shifted every plane (default), 1 rotated at compile time, 3 / 4 only the
@@ -591,7 +623,7 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s)
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tti::SMEM));
         configured[var] = true;
     }
-    Wavefield *W = s.scratch;
+    Wavefield *W = lin ? s.lin : s.scratch;
     TtiMaps tm;
     tm.U1 = W->tmap_halo[0][W->cur]; tm.U2 = W->tmap_halo[1][W->cur];
     tm.P1 = W->tmap_tile[0][1 - W->cur]; tm.P2 = W->tmap_tile[1][1 - W->cur];
@@ -600,10 +632,15 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s)
     TtiArgs a;
     memset(&a, 0, sizeof(a));
     a.g = M->g; a.cf = M->cf;
-    a.up1 = s.up[0]; a.up2 = s.up[1];
+    a.up1 = lin ? s.ulp[0] : s.up[0]; a.up2 = lin ? s.ulp[1] : s.up[1];
+    if (FUSE & TF_DDOUT) { a.dd_out[0] = s.scratch->dd[0].p; a.dd_out[1] = s.scratch->dd[1].p; }
+    if (FUSE & TF_QSRC) {
+        a.dd_in[0] = s.scratch->dd[0].p; a.dd_in[1] = s.scratch->dd[1].p;
+        a.dm = M->dm.p;
+    }
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.irho_c = M->irho_c;
-    a.f = s.f;
+    if (!lin) a.f = s.f;
     const int ntx = (M->N[0] + tti::TX - 1) / tti::TX, nty = (M->N[1] + tti::TY - 1) / tti::TY;
     int nzc = tti3d_chunks(ctx, ntx * nty, M->N[2]);
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
@@ -616,9 +653,25 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s)
 // One fused TTI step; false if this combination has no single-pass instantiation.
 bool tti3d_step(const judi_model *M, const StepArgs &s)
 {
-    if (!tti3d_supported(M) || s.born || s.qext || s.f.wrec || !s.scratch || !s.scratch->has_tmap) return false;
+    if (!tti3d_supported(M) || s.qext || s.f.wrec || !s.scratch || !s.scratch->has_tmap) return false;
     if (s.f.grad && s.f.ic != JUDI_IC_AS) return false;
     const int mask = (s.f.snap[0] ? TF_SNAP : 0) | (s.f.grad ? TF_GRAD : 0) | (s.f.illum ? TF_ILLUM : 0);
+    if (s.born) {
+        // Born step: the background field writes its delta, the linearised field reads it back as
+        // its source -- two single-pass launches instead of four two-pass ones
+        if (s.born_ic != JUDI_IC_AS || s.f.grad || !s.lin || !s.lin->has_tmap || !s.scratch->dd[0].p ||
+            !s.scratch->dd[1].p || !M->dm.p)
+            return false;
+        switch (mask) {
+        case 0: tti3d_launch<TF_DDOUT>(M, s); break;
+        case TF_SNAP: tti3d_launch<TF_DDOUT | TF_SNAP>(M, s); break;
+        case TF_ILLUM: tti3d_launch<TF_DDOUT | TF_ILLUM>(M, s); break;
+        case TF_SNAP | TF_ILLUM: tti3d_launch<TF_DDOUT | TF_SNAP | TF_ILLUM>(M, s); break;
+        default: return false;
+        }
+        tti3d_launch<TF_QSRC>(M, s, true);
+        return true;
+    }
     switch (mask) {
     case 0: tti3d_launch<0>(M, s); return true;
     case TF_SNAP: tti3d_launch<TF_SNAP>(M, s); return true;

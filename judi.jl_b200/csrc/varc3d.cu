@@ -401,9 +401,12 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             const f2 r0 = pk(__frcp_rn(den0.x), __frcp_rn(den0.y));
             const f2 r1 = pk(__frcp_rn(den1.x), __frcp_rn(den1.y));
             const f2 d10 = sub2(lo2(uc), lo2(up4)), d11 = sub2(hi2(uc), hi2(up4));
-            const f2 dl0 = mul2(fma2(mul2s(-1.f, sd0), d10, mul2s(cf.dt2, lo2(H))), r0);
-            const f2 dl1 = mul2(fma2(mul2s(-1.f, sd1), d11, mul2s(cf.dt2, hi2(H))), r1);
-            const f2 un0 = add2(add2(lo2(uc), d10), dl0), un1 = add2(add2(hi2(uc), d11), dl1);
+            // one explicit fma for the update: ptxas contracts a packed mul + add pair in the flavours
+            // that do not also use delta, and the field must not depend on the flavour
+            const f2 t0 = fma2(mul2s(-1.f, sd0), d10, mul2s(cf.dt2, lo2(H)));
+            const f2 t1 = fma2(mul2s(-1.f, sd1), d11, mul2s(cf.dt2, hi2(H)));
+            [[maybe_unused]] const f2 dl0 = mul2(t0, r0), dl1 = mul2(t1, r1);
+            const f2 un0 = fma2(t0, r0, add2(lo2(uc), d10)), un1 = fma2(t1, r1, add2(hi2(uc), d11));
             if (act) {
                 float *o = a.up + gout;
                 if (xfull) *(float4 *)o = cat4(un0, un1);
