@@ -504,7 +504,7 @@ static void step_ndim(const judi_model *M, const StepArgs &s)
 
 bool flux_born_single_pass(const judi_model *M)
 {
-    return M->ctx->opt_kernel3d == 1 && tti3d_supported(M);
+    return M->ctx->opt_kernel3d == 1 && (tti3d_supported(M) || varc3d_supported(M));
 }
 
 // One leapfrog step of every field of the model (+ fused extras), timed with CUDA events when

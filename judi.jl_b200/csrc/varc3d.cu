@@ -66,9 +66,12 @@ struct VarcArgs {
     const float *dx, *dy, *dz;
     int zchunk;
     Fuse f;
+    float *dd_out;           // Born background pass: write delta = u+ - 2u + u-
+    const float *dd_in;      // Born linearised pass: delta of the background field ...
+    const float *dm;         // ... and the model perturbation: q = -dm irho delta
 };
 
-enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4 };
+enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4, VF_DDOUT = 8, VF_QSRC = 16 };
 
 // staggered first derivative along x at the 4 nodes of a group from the 12-float row window centred
 // on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2)
@@ -309,7 +312,8 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
         dxy1 = add2(hi2(d4), pk1(a.dy[oy]));
     }
     constexpr bool f_snap = (FUSE & VF_SNAP) != 0, f_grad = (FUSE & VF_GRAD) != 0;
-    constexpr bool f_il = (FUSE & VF_ILLUM) != 0, f_reg = FUSE != 0;
+    constexpr bool f_il = (FUSE & VF_ILLUM) != 0, f_reg = (FUSE & (VF_SNAP | VF_GRAD | VF_ILLUM)) != 0;
+    constexpr bool f_dd = (FUSE & VF_DDOUT) != 0, f_q = (FUSE & VF_QSRC) != 0;
     [[maybe_unused]] const Fuse &fz = a.f;
     [[maybe_unused]] const bool f_xy = f_reg && act && oy >= fz.reg.lo[1] && oy < fz.reg.hi[1] &&
                                        ox + 3 >= fz.reg.lo[0] && ox < fz.reg.hi[0];
@@ -333,8 +337,13 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
         float dz_s = 0.f;
         [[maybe_unused]] bool fin = false, fvec = false;
         [[maybe_unused]] float4 us4, G4, I4;
+        [[maybe_unused]] float4 dq4 = make_float4(0.f, 0.f, 0.f, 0.f), dm4 = dq4;
         if (out) {
             dz_s = __ldg(a.dz + z);
+            if (f_q && act) {
+                dq4 = *(const float4 *)(a.dd_in + gout);
+                dm4 = __ldg((const float4 *)(a.dm + gout));
+            }
             if (f_reg) {
                 const bool zin = z >= fz.reg.lo[2] && z < fz.reg.hi[2];
                 fin = f_xy && zin;
@@ -403,18 +412,31 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             const f2 d10 = sub2(lo2(uc), lo2(up4)), d11 = sub2(hi2(uc), hi2(up4));
             // one explicit fma for the update: ptxas contracts a packed mul + add pair in the flavours
             // that do not also use delta, and the field must not depend on the flavour
-            const f2 t0 = fma2(mul2s(-1.f, sd0), d10, mul2s(cf.dt2, lo2(H)));
-            const f2 t1 = fma2(mul2s(-1.f, sd1), d11, mul2s(cf.dt2, hi2(H)));
+            f2 h0 = mul2s(cf.dt2, lo2(H)), h1 = mul2s(cf.dt2, hi2(H));
+            if (f_q) {
+                // dt^2 * lin_src = -dm irho (u+ - 2u + u-) of the background field
+                // (sensitivity.py:174-188; the post-injection part is added by sparse.cu)
+                h0 = fma2(mul2(mul2s(-1.f, lo2(dm4)), lo2(ir4)), lo2(dq4), h0);
+                h1 = fma2(mul2(mul2s(-1.f, hi2(dm4)), hi2(ir4)), hi2(dq4), h1);
+            }
+            const f2 t0 = fma2(mul2s(-1.f, sd0), d10, h0);
+            const f2 t1 = fma2(mul2s(-1.f, sd1), d11, h1);
             [[maybe_unused]] const f2 dl0 = mul2(t0, r0), dl1 = mul2(t1, r1);
             const f2 un0 = fma2(t0, r0, add2(lo2(uc), d10)), un1 = fma2(t1, r1, add2(hi2(uc), d11));
             if (act) {
                 float *o = a.up + gout;
-                if (xfull) *(float4 *)o = cat4(un0, un1);
-                else {
+                if (xfull) {
+                    *(float4 *)o = cat4(un0, un1);
+                    if (f_dd) *(float4 *)(a.dd_out + gout) = cat4(dl0, dl1);
+                } else {
                     const float v[4] = {un0.x, un0.y, un1.x, un1.y};
+                    const float dv[4] = {dl0.x, dl0.y, dl1.x, dl1.y};
 #pragma unroll
                     for (int e = 0; e < 4; e++)
-                        if (ox + e < g.n[0]) o[e] = v[e];
+                        if (ox + e < g.n[0]) {
+                            o[e] = v[e];
+                            if (f_dd) a.dd_out[gout + e] = dv[e];
+                        }
                 }
             }
             if (f_reg && fin) {
@@ -474,8 +496,9 @@ void varc3d_encode_coef(const judi_model *M, const float *base, CUtensorMap *map
     tma_encode_box(M, base, varc::CPX, varc::CPY, map);
 }
 
+// lin: launch on the linearised wavefield (Born source in); otherwise on the background field
 template <int FUSE>
-static void varc3d_launch(const judi_model *M, const StepArgs &s)
+static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
 {
     judi_ctx *ctx = M->ctx;
     auto kern = varc3d_tma<FUSE>;
@@ -484,7 +507,7 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s)
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)varc::SMEM));
         configured = true;
     }
-    Wavefield *W = s.scratch;
+    Wavefield *W = lin ? s.lin : s.scratch;
     VarcMaps tm;
     tm.U = W->tmap_halo[0][W->cur];
     tm.P = W->tmap_tile[0][1 - W->cur];
@@ -494,9 +517,11 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s)
     VarcArgs a;
     memset(&a, 0, sizeof(a));
     a.g = M->g; a.cf = M->cf;
-    a.up = s.up[0];
+    a.up = lin ? s.ulp[0] : s.up[0];
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
-    a.f = s.f;
+    if (!lin) a.f = s.f;
+    if (FUSE & VF_DDOUT) a.dd_out = s.scratch->dd[0].p;
+    if (FUSE & VF_QSRC) { a.dd_in = s.scratch->dd[0].p; a.dm = M->dm.p; }
     const int ntx = (M->N[0] + varc::TX - 1) / varc::TX, nty = (M->N[1] + varc::TY - 1) / varc::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
@@ -522,9 +547,23 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s)
 // One fused variable-density step; false if this combination has no single-pass instantiation.
 bool varc3d_step(const judi_model *M, const StepArgs &s)
 {
-    if (!varc3d_supported(M) || s.born || s.qext || s.f.wrec || !s.scratch || !s.scratch->has_tmap) return false;
+    if (!varc3d_supported(M) || s.qext || s.f.wrec || !s.scratch || !s.scratch->has_tmap) return false;
     if (s.f.grad && s.f.ic != JUDI_IC_AS) return false;
     const int mask = (s.f.snap[0] ? VF_SNAP : 0) | (s.f.grad ? VF_GRAD : 0) | (s.f.illum ? VF_ILLUM : 0);
+    if (s.born) {
+        // Born step: two single-pass launches (background writes delta, linearised field reads it)
+        if (s.born_ic != JUDI_IC_AS || s.f.grad || !s.lin || !s.lin->has_tmap || !s.scratch->dd[0].p || !M->dm.p)
+            return false;
+        switch (mask) {
+        case 0: varc3d_launch<VF_DDOUT>(M, s); break;
+        case VF_SNAP: varc3d_launch<VF_DDOUT | VF_SNAP>(M, s); break;
+        case VF_ILLUM: varc3d_launch<VF_DDOUT | VF_ILLUM>(M, s); break;
+        case VF_SNAP | VF_ILLUM: varc3d_launch<VF_DDOUT | VF_SNAP | VF_ILLUM>(M, s); break;
+        default: return false;
+        }
+        varc3d_launch<VF_QSRC>(M, s, true);
+        return true;
+    }
     switch (mask) {
     case 0: varc3d_launch<0>(M, s); return true;
     case VF_SNAP: varc3d_launch<VF_SNAP>(M, s); return true;

@@ -12,7 +12,8 @@ n = (301, 301, 201)
 v = velocity(n)
 rho = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
 ctx = J.get_context(0)
-gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32), rho=rho)
+dm = (0.05 * (1 / v ** 2) * np.sin(np.arange(n[2]) / 7.)[None, None, :]).astype(np.float32)
+gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32), rho=rho, dm=dm)
 dt = float(gm.critical_dt)
 q = ricker(nt, dt, 0.03)
 src = np.array([[3750., 3750., 50.]], dtype=np.float32)
@@ -29,12 +30,16 @@ for fused in (0, 1):
         J.forward_rec(gm, src, q, rec)
         st0 = ctx.stencil_stats(); ctx.reset_stats()
         J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=1, snapshot_region="physical")
-        st = ctx.stencil_stats(); ctx.set_option("timing", 0)
-        if ref is None: ref = (d1, g)
+        st = ctx.stencil_stats(); ctx.reset_stats()
+        dl = J.born_rec(gm, src, q, rec)[0]
+        stb = ctx.stencil_stats(); ctx.set_option("timing", 0)
+        if ref is None: ref = (d1, g, dl)
         ms = {k: v_["ms"] / v_["launches"] for k, v_ in st["kinds"].items()}
+        ms["born"] = stb["ms"] / stb["launches"]
         ms["plain"] = st0["ms"] / st0["launches"]
-        print("varc_fused %d zchunks %d: %s  |d|=%.4e |g|=%.4e  rel diff vs first: rec %.2e grad %.2e" % (
+        print("varc_fused %d zchunks %d: %s  |d|=%.4e |g|=%.4e  rel diff vs first: rec %.2e grad %.2e born %.2e" % (
             fused, zc, " ".join("%s %.4f ms" % kv for kv in sorted(ms.items())),
             np.linalg.norm(d1), np.linalg.norm(g),
             np.linalg.norm(d1 - ref[0]) / np.linalg.norm(ref[0]),
-            np.linalg.norm(g - ref[1]) / np.linalg.norm(ref[1])), flush=True)
+            np.linalg.norm(g - ref[1]) / np.linalg.norm(ref[1]),
+            np.linalg.norm(dl - ref[2]) / np.linalg.norm(ref[2])), flush=True)
