@@ -26,6 +26,7 @@
  *   Born sources               sensitivity.py:157-209
  *   wavefield save / t_sub     fields.py:123-153, fields_exprs.py:12-36
  *   illumination               fields_exprs.py:240-255
+ *   visco-acoustic SLS         kernels.py:80-141 (memory variable fields.py:109-120)
  * Layout here is Devito's: C order over (x[,y],z) with z fastest, and a zero halo of
  * `space_order` cells around the padded grid (Dirichlet outside the absorbing layer).
  *
@@ -66,6 +67,9 @@ typedef struct {
     int irho_is_field;
     real irho_c;
     real *m, *damp, *irho, *eps, *delta, *theta, *phi, *dm;
+    int visco;      /* visco-acoustic SLS (kernels.py:80-141): quality factor field + peak frequency */
+    real *qp;
+    real f0;
     /* extended / wavefield sources and extended receiver of the current call (oracle_set_ext) */
     const real *ext_ws, *ext_wt;   /* q(x,t) = ws(x) * wt[t]        (fields_exprs.py:58-82) */
     real *ext_wr; const real *ext_wrt; /* wr(x) += dt * u[t](x) * wrt[t]  (fields_exprs.py:85-103) */
@@ -211,7 +215,7 @@ void oracle_destroy(ogrid *g)
 {
     if (!g) return;
     free(g->m); free(g->damp); free(g->irho); free(g->eps); free(g->delta);
-    free(g->theta); free(g->phi); free(g->dm);
+    free(g->theta); free(g->phi); free(g->dm); free(g->qp);
     free(g);
 }
 
@@ -233,6 +237,16 @@ int oracle_set_threads(int n)
 }
 
 void oracle_set_fs(ogrid *g, int fs) { g->fs = fs; }
+
+/* visco-acoustic model: qp on the padded grid (edge-replicated into the halo like every parameter)
+ * and the peak frequency f0 (kHz) of the call (propagators.py:46) */
+void oracle_set_visco(ogrid *g, const real *qp, real f0)
+{
+    free(g->qp);
+    g->qp = qp ? embed(g, qp, 1) : NULL;
+    g->visco = qp != NULL;
+    g->f0 = f0;
+}
 
 /* All arrays padded-grid sized, C order, no halo (ws, wr, qwf slices); wt / wrt have nt entries. */
 void oracle_set_ext(ogrid *g, const real *ws, const real *wt, real *wr, const real *wrt,
@@ -494,11 +508,20 @@ static inline real divergence(const ogrid *g, real *const *F, size_t i)
 typedef struct {
     real *P[3], *M[3];
     real *H[2];
+    /* visco-acoustic: memory variables of the background / linearised field, the adjoint's product
+     * field, and what the next step_fields call is: direction and which memory variable */
+    real *r[2], *w;
+    int adj, rsel;
 } oscratch;
 
 static void scratch_alloc(const ogrid *g, oscratch *s, int need_flux)
 {
     memset(s, 0, sizeof(*s));
+    if (g->visco) {
+        s->r[0] = (real *)calloc(g->ntot, sizeof(real));
+        s->r[1] = (real *)calloc(g->ntot, sizeof(real));
+        s->w = (real *)calloc(g->ntot, sizeof(real));
+    }
     if (!need_flux) return;
     for (int d = 0; d < 3; d++) {
         s->P[d] = (real *)calloc(g->ntot, sizeof(real));
@@ -508,9 +531,73 @@ static void scratch_alloc(const ogrid *g, oscratch *s, int need_flux)
 static void scratch_free(oscratch *s)
 {
     for (int d = 0; d < 3; d++) { free(s->P[d]); free(s->M[d]); }
+    free(s->r[0]); free(s->r[1]); free(s->w);
 }
 
 static int flux_form(const ogrid *g) { return g->tti || g->irho_is_field; }
+
+/* Visco-acoustic SLS step (kernels.py:80-141, SLS_2nd_order), pressure p and memory variable r.
+ * With b = irho, mb = m*b, the mask-type boundary field damp_mask = 1 - damp (models.py:73-93:
+ * 1 inside, decreasing in the layer), L(.) = laplacian(., b) (FD_utils.py:11-21) and, per point,
+ *   t_s = (sqrt(1 + 1/qp^2) - 1/qp) / f0,  t_ep = 1 / (f0^2 t_s),  tt = t_ep / t_s - 1:
+ * forward  r+ = damp_mask * solve(b r.dt - (tt/t_s) L(p) + (b/t_s) r, r+)
+ *          p+ = solve(mb p.dt2 - (1+tt) L(p) + b r+ - q + (1 - damp_mask) p.dt, p+)
+ * adjoint  r- = damp_mask * solve(r.dt.T + b p + r/t_s, r-)
+ *          p- = solve(mb p.dt2 - L((1+tt) p) - L((tt/(b t_s)) r-) + (1 - damp_mask) p.dt.T - q, p-)
+ * with the one-sided u.dt = (u+ - u)/dt, u.dt.T = (u- - u)/dt of SURVEY A.3.  pp holds the other
+ * time level on entry and the new one on return; r is updated in place. */
+static inline void sls_params(const ogrid *g, size_t i, real *tt, real *ts)
+{
+    real qp = g->qp[i];
+    real t_s = (RSQRT(1 + 1 / (qp * qp)) - 1 / qp) / g->f0;
+    real t_ep = 1 / (g->f0 * g->f0 * t_s);
+    *ts = t_s;
+    *tt = t_ep / t_s - 1;
+}
+
+static void step_visco(const ogrid *g, oscratch *sc, const real *p, real *pp, real *r, const real *q,
+                       int adj)
+{
+    int X = g->N[0], Y = g->N[1], Z = g->N[2];
+    real r1 = 1 / (g->dt * g->dt), r2 = 1 / g->dt;
+    int ff = flux_form(g);
+    const real *Lin = p;
+    if (adj) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = 0; x < X; x++)
+            for (int y = 0; y < Y; y++)
+                for (int z = 0; z < Z; z++) {
+                    size_t i = IDX(g, x, y, z);
+                    real tt, ts;
+                    sls_params(g, i, &tt, &ts);
+                    real b = g->irho[i];
+                    real rn = (1 - g->damp[i]) * ((r[i] * r2 - b * p[i] - r[i] / ts) / r2);
+                    r[i] = rn;
+                    sc->w[i] = (1 + tt) * p[i] + (tt / (b * ts)) * rn;
+                }
+        Lin = sc->w;
+    }
+    if (ff) fluxes(g, Lin, NULL, sc->P, sc->M);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int x = 0; x < X; x++)
+        for (int y = 0; y < Y; y++)
+            for (int z = 0; z < Z; z++) {
+                size_t i = IDX(g, x, y, z);
+                real b = g->irho[i], mb = g->m[i] * b, dl = g->damp[i];
+                real L = ff ? divergence(g, sc->P, i) : g->irho_c * lap_const(g, Lin, i);
+                real qq = q ? q[i] : 0;
+                real pc = p[i];
+                real rhs = mb * r1 * (2 * pc - pp[i]) + dl * r2 * pc + qq;
+                if (!adj) {
+                    real tt, ts;
+                    sls_params(g, i, &tt, &ts);
+                    real rn = (1 - dl) * ((b * r2 * r[i] + (tt / ts) * L - (b / ts) * r[i]) / (b * r2));
+                    r[i] = rn;
+                    rhs += (1 + tt) * L - b * rn;
+                } else rhs += L;
+                pp[i] = rhs / (mb * r1 + dl * r2);
+            }
+}
 
 /* One leapfrog update of every padded-grid point:
  *   un = ( a*(2u - up) + b*u + L(u) + q ) / (a + b),  a = m*irho/dt^2,  b = damp/dt
@@ -524,6 +611,11 @@ static void step_fields(const ogrid *g, oscratch *sc, int nf, real *const *u, re
     int X = g->N[0], Y = g->N[1], Z = g->N[2];
     real r1 = 1 / (g->dt * g->dt), r2 = 1 / g->dt;
     int ff = flux_form(g);
+    if (g->visco) {
+        /* un aliases up at every call site */
+        step_visco(g, sc, u[0], un[0], sc->r[sc->rsel], qsrc ? qsrc[0] : NULL, sc->adj);
+        return;
+    }
     if (ff) fluxes(g, u[0], nf == 2 ? u[1] : NULL, sc->P, sc->M);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int x = 0; x < X; x++)
@@ -600,7 +692,7 @@ DEFINE_FAST_STEP(8)
 
 static int fast_ok(const ogrid *g)
 {
-    return g_use_fast && !flux_form(g) && (g->r == 2 || g->r == 4 || g->r == 8);
+    return g_use_fast && !flux_form(g) && !g->visco && (g->r == 2 || g->r == 4 || g->r == 8);
 }
 
 static void fast_step(const ogrid *g, const real *u, real *up, const real *us, real *G, real wdt)
@@ -674,6 +766,7 @@ int oracle_forward(const ogrid *g, int fw, int nt, const osparse *src, const rea
         for (int f = 0; f < nf; f++) { u[f] = bufs[f][cur]; up[f] = bufs[f][1 - cur]; }
         int has_q = ext_source(g, t, nf, qe);
         ext_receiver(g, t, nf, u);
+        sc.adj = !fw; sc.rsel = 0;
         if (fast_ok(g) && !has_q) fast_step(g, u[0], up[0], NULL, NULL, 0);
         else step_fields(g, &sc, nf, u, up, up, has_q ? (const real *const *)qe : NULL);
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
@@ -793,6 +886,7 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
         }
         {
             int has_q = ext_source(g, t, nf, q); /* q[] is rebuilt below for the linearised field */
+            sc.adj = 0; sc.rsel = 0;
             step_fields(g, &sc, nf, u, up, up, has_q ? (const real *const *)q : NULL);
         }
         if (src) inject(g, src, wavelet + (size_t)t * src->np, up[0]);
@@ -811,6 +905,7 @@ int oracle_born(const ogrid *g, int nt, const osparse *src, const real *wavelet,
                                                ic == 0 ? 0 : lap_weighted(g, u[f], g->dm, g->irho, i));
                     }
                 }
+        sc.adj = 0; sc.rsel = 1;
         step_fields(g, &sc, nf, ul, ulp, ulp, (const real *const *)q);
         for (int f = 0; f < nf; f++) apply_fs(g, ulp[f]);
         if (save_mode && (t % t_sub) == 0)
@@ -866,6 +961,7 @@ int oracle_gradient(const ogrid *g, int nt, const osparse *rec, const real *resi
             v[f] = bv[f][cur]; vp[f] = bv[f][1 - cur];
             memcpy(vnext[f], vp[f], g->ntot * sizeof(real)); /* keep v[t+1] for v.dt2 */
         }
+        sc.adj = 1; sc.rsel = 0;
         step_fields(g, &sc, nf, v, vp, vp, NULL);
         inject(g, rec, residual + (size_t)t * rec->np, vp[0]);
         for (int f = 0; f < nf; f++) apply_fs(g, vp[f]);

@@ -70,6 +70,7 @@ def _lib(precision):
     lib.oracle_time_steps.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
     lib.oracle_set_fast.argtypes = [ctypes.c_int]
     lib.oracle_set_fs.argtypes = [P, ctypes.c_int]
+    lib.oracle_set_visco.argtypes = [P, P, real]
     lib.oracle_set_threads.argtypes = [ctypes.c_int]
     lib.oracle_set_threads.restype = ctypes.c_int
     lib.oracle_set_ext.argtypes = [P, P, P, P, P, P]
@@ -251,7 +252,7 @@ class Model(object):
 
     def __init__(self, origin, spacing, shape, space_order=8, nbl=40, m=None, epsilon=None,
                  delta=None, theta=None, phi=None, rho=None, b=None, dm=None, fs=False,
-                 dt=None, precision="f32"):
+                 dt=None, precision="f32", qp=None, f0=0.015):
         self.shape = tuple(int(s) for s in shape)
         self.dim = len(self.shape)
         self.nbl = int(nbl)
@@ -285,6 +286,11 @@ class Model(object):
             else:
                 self.irho_field = self._param(b)
         self.dm = None if dm is None or (np.ndim(dm) == 0 and dm == 0) else self._param(dm)
+        # visco-acoustic (models.py:208-214): quality factor field; f0 is the peak frequency the
+        # reference passes with every call (propagators.py:46), in kHz
+        self.is_viscoacoustic = qp is not None
+        self.qp = None if qp is None else self._param(np.broadcast_to(np.asarray(qp, dtype=np.float32), self.shape))
+        self.f0 = float(f0)
         self.is_tti = any(p is not None for p in (epsilon, delta, theta, phi))
         self.tti = {}
         self.scale = 1.0
@@ -361,7 +367,17 @@ class Model(object):
             _ptr(conv(g("phi", 0.0)[0])), lib._real(g("phi", 0.0)[1]),
             _ptr(conv(self.dm)))
         lib.oracle_set_fs(self._handle, int(bool(self.fs)))
+        if self.is_viscoacoustic:
+            lib.oracle_set_visco(self._handle, _ptr(conv(self.qp)), lib._real(self.f0))
         return self._handle
+
+    def set_f0(self, f0):
+        """Peak frequency (kHz) of the next calls (the reference's f0 keyword)."""
+        self.f0 = float(f0)
+        if self._handle is not None and self.is_viscoacoustic:
+            lib = _lib(self.precision)
+            lib.oracle_set_visco(self._handle, _ptr(np.ascontiguousarray(self.qp, dtype=lib._dtype)),
+                                 lib._real(self.f0))
 
     def __del__(self):
         try:

@@ -34,7 +34,7 @@ def dots(model, src, rec, q, dt, ic="as", t_sub=1, checkpointing=False):
     return (a - b) / (a + b), (c - e) / (c + e)
 
 
-@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti", "visco", "viscoc"])
 @pytest.mark.parametrize("so", [4, 8, 16])
 def test_adjoint_dot_fp64_2d(kind, so):
     _, model, src, rec, q, dt = setup(kind, 2, so)
@@ -42,14 +42,14 @@ def test_adjoint_dot_fp64_2d(kind, so):
     assert abs(eF) < 1e-11 and abs(eJ) < 1e-11
 
 
-@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti", "visco"])
 def test_adjoint_dot_fp64_3d(kind):
     _, model, src, rec, q, dt = setup(kind, 3, 8, n=(31, 29, 27), nbl=8)
     eF, eJ = dots(model, src, rec, q, dt)
     assert abs(eF) < 1e-11 and abs(eJ) < 1e-11
 
 
-@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti", "visco"])
 def test_adjoint_dot_fp32_reference_tolerance(kind):
     """test_adjoint.jl:21: |a-b|/(a+b) <= 5e-4 in single precision."""
     _, model, src, rec, q, dt = setup(kind, 2, 8, precision="f32")
