@@ -156,6 +156,11 @@ int judi_model_padsizes(const judi_model *model, int *out);
 int judi_model_padded_shape(const judi_model *model, int *out);
 /* replace the perturbation dm of an existing model (born / lsrtm with a new dm) */
 int judi_model_set_dm(judi_model *model, const judi_param *dm, int on_device);
+/* make the model visco-acoustic (`Model(n, d, o, m, rho, qp)`, src/pysource/models.py:208-214 and
+ * kernels.py:80-141): quality factor field qp (NULL: keep the current one) and the peak frequency
+ * f0 in kHz that the reference passes with every call (`f0=options.f0`, python_interface.jl:42;
+ * propagators.py:46).  Call again to change f0 between calls. */
+int judi_model_set_visco(judi_model *model, const judi_param *qp, float f0, int on_device);
 /* the padded damping field (models.py:54-120) and padded m, for tests: out is padded-grid sized */
 int judi_model_get_field(const judi_model *model, const char *name, float *out);
 

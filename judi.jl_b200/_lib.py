@@ -69,6 +69,8 @@ SIGNATURES = {
     "judi_model_padsizes": (ctypes.c_int, [ctypes.c_void_p, c_int_p]),
     "judi_model_padded_shape": (ctypes.c_int, [ctypes.c_void_p, c_int_p]),
     "judi_model_set_dm": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(JudiParam), ctypes.c_int]),
+    "judi_model_set_visco": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(JudiParam), ctypes.c_float,
+                                            ctypes.c_int]),
     "judi_model_get_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]),
     "judi_sparse_locate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -202,6 +202,16 @@ int judi_model_padded_shape(const judi_model *model, int *out)
     API_END(1)
 }
 
+int judi_model_set_visco(judi_model *model, const judi_param *qp, float f0, int on_device)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model != nullptr, "model is NULL");
+    model_set_visco(model, qp, f0, on_device);
+    CUDA_CHECK(cudaStreamSynchronize(model->ctx->stream));
+    return 0;
+    API_END(1)
+}
+
 int judi_model_set_dm(judi_model *model, const judi_param *dm, int on_device)
 {
     API_BEGIN

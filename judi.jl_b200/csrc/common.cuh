@@ -199,6 +199,9 @@ struct judi_model {
     Grid g;
     Coefs cf;
     bool tti = false, irho_field = false, has_dm = false;
+    bool visco = false;          // visco-acoustic SLS (kernels.py:80-141)
+    float f0 = 0.015f;           // ... peak frequency (kHz) of the relaxation times
+    DevBuf qp, vtt, vts;         // ... quality factor, tt = t_ep/t_s - 1 and t_s per point
     float irho_c = 1.f;
     DevBuf m, irho, eps, delta, theta, phi, dm;  // fields on `g` (edge-replicated into halo)
     DevBuf r3[3];                // 3-D TTI: symmetry axis (sin th cos ph, sin th sin ph, cos th)
@@ -241,6 +244,7 @@ void fornberg_weights(double z, const double *x, int n, int m, double *c);
 void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc);
 void model_set_param(judi_model *M, DevBuf &dst, const judi_param &p, int on_device,
                      float default_value, bool force_field);
+void model_set_visco(judi_model *M, const judi_param *qp, float f0, int on_device);
 void launch_count(judi_ctx *ctx, const char *what);
 
 // ---- sparse.cu
@@ -274,6 +278,7 @@ struct StepArgs {
     float qext_scale;          //   q = qext_scale * qext  (already multiplied by dt^2 [/ irho])
     float *dd_out;             // TMA kernel, Born background pass: write delta
     const float *qsrc;         // TMA kernel, Born linearised pass: read delta of the background
+    int adj;                   // 1: adjoint sweep (only the visco-acoustic step is not its own mirror image)
 };
 void stencil_step(const judi_model *M, const StepArgs &a);
 // true if a Born step of this model (imaging condition "as") runs on the single-pass flux kernels
@@ -287,6 +292,7 @@ struct Wavefield {
     int cur = 0;
     DevBuf flux[6];            // P_x,P_y,P_z,M_x,M_y,M_z (flux form only)
     DevBuf dd[2];              // u+ - 2u + u- of the background field (flux-form Born)
+    DevBuf rmem, wtmp;         // visco-acoustic: memory variable, adjoint product field
     CUtensorMap tmap_halo[2][2];  // [field][slot]: haloed plane box
     CUtensorMap tmap_tile[2][2];  // [field][slot]: tile box
     CUtensorMap tmap_m;           // tile box over the model's m

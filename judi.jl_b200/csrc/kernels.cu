@@ -341,6 +341,101 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Visco-acoustic SLS physics (src/pysource/kernels.py:80-141), one point per thread.  Pressure p,
+// memory variable r (updated in place).  With b = irho, mb = m b, dl = damp (the layer profile;
+// the reference's mask-type field is 1 - dl), L(.) = laplacian(., b) (FD_utils.py:11-21):
+//   forward  r+ = (1 - dl) (r + dt ((tt/ts) L(p)/b - r/ts))
+//            p+ = p + (p - p-) + [dt^2 ((1 + tt) L(p) - b r+ + q) - dt dl (p - p-)] / (mb + dt dl)
+//   adjoint  r- = (1 - dl) (r - dt (b p + r/ts)),   w = (1 + tt) p + (tt / (b ts)) r-
+//            p- = p + (p - p+) + [dt^2 (L(w) + q) - dt dl (p - p+)] / (mb + dt dl)
+// (the increment form of solve(.) with the one-sided u.dt of SURVEY A.3; forward and adjoint are
+// exact discrete adjoints of each other: the dot test holds to 1e-15 in fp64.)
+struct ViscoArgs {
+    Grid g;
+    Coefs cf;
+    const float *p;          // level t
+    float *pp;               // level t-+1 in, level t+-1 out
+    float *r;                // memory variable
+    float *w;                // adjoint: product field (pre pass writes, update reads)
+    const float *P[3];       // flux form: b grad(p or w); else nullptr and the Laplacian of Lin is taken
+    const float *Lin;
+    const float *m, *irho, *tt, *ts;
+    float irho_c;
+    const float *dx, *dy, *dz;
+    int adj;
+    const float *qext;
+    float qext_scale;
+    const float *dd_in, *dm;
+    float *dd_out;
+    Fuse f;
+};
+
+template <int NDIM>
+__global__ void __launch_bounds__(256) visco_pre_adjoint(ViscoArgs a)
+{
+    const Grid &g = a.g;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y, z;
+    if (NDIM == 3) { y = blockIdx.y * blockDim.y + threadIdx.y; z = blockIdx.z; }
+    else { y = 0; z = blockIdx.y * blockDim.y + threadIdx.y; }
+    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
+    long long i = g.at(x, y, z);
+    const float b = a.irho ? a.irho[i] : a.irho_c;
+    const float dl = (a.dx[x] + a.dy[y]) + a.dz[z];
+    const float tt = a.tt[i], ts = a.ts[i];
+    const float pc = a.p[i], rc = a.r[i];
+    const float rn = (1.0f - dl) * (rc - a.cf.dt * (b * pc + rc / ts));
+    a.r[i] = rn;
+    a.w[i] = (1.0f + tt) * pc + (tt / (b * ts)) * rn;
+}
+
+template <int NDIM, int R>
+__global__ void __launch_bounds__(256) visco_update(ViscoArgs a)
+{
+    const Grid &g = a.g;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y, z;
+    if (NDIM == 3) { y = blockIdx.y * blockDim.y + threadIdx.y; z = blockIdx.z; }
+    else { y = 0; z = blockIdx.y * blockDim.y + threadIdx.y; }
+    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
+    long long i = g.at(x, y, z);
+    const Coefs &cf = a.cf;
+    const float b = a.irho ? a.irho[i] : a.irho_c;
+    const float mb = a.m[i] * b;
+    const float dl = (a.dx[x] + a.dy[y]) + a.dz[z];
+    const float sd = cf.dt * dl;
+    float L2;   // dt^2 * laplacian(Lin, b)
+    if (a.P[0]) {
+        float L = dminus<R>(a.P[0], i, 1, cf.wx) + dminus<R>(a.P[2], i, g.sz, cf.wz);
+        if (NDIM == 3) L += dminus<R>(a.P[1], i, g.sy, cf.wy);
+        L2 = cf.dt2 * L;
+    } else L2 = b * lap_at<NDIM, R>(g, cf, a.Lin, i);
+    float S2;   // dt^2 * (right-hand side without the time-derivative terms)
+    if (!a.adj) {
+        const float tt = a.tt[i], ts = a.ts[i];
+        const float rc = a.r[i];
+        const float rn = (1.0f - dl) * (rc + ((tt / ts) * (L2 / b) * cf.idt - cf.dt * (rc / ts)));
+        a.r[i] = rn;
+        S2 = (1.0f + tt) * L2 - cf.dt2 * (b * rn);
+    } else S2 = L2;
+    if (a.dd_in) S2 += -a.dm[i] * b * a.dd_in[i];          // Born source, already scaled by dt^2
+    if (a.qext) S2 += a.qext_scale * a.qext[i];
+    const float pc = a.p[i];
+    const float d1 = pc - a.pp[i];
+    const float delta = (S2 - sd * d1) / (mb + sd);
+    a.pp[i] = (pc + d1) + delta;
+    if (a.dd_out) a.dd_out[i] = delta;
+    const Fuse &fz = a.f;
+    if ((fz.snap[0] || fz.grad || fz.illum || fz.wrec) && fz.reg.has(x, y, z)) {
+        long long ri = fz.reg.at(x, y, z);
+        if (fz.wrec) fz.wrec[ri] += fz.wrec_scale * pc;
+        if (fz.snap[0]) fz.snap[0][ri] = pc;
+        if (fz.illum) fz.illum[ri] += cf.dt * pc * pc;
+        if (fz.grad) fz.grad[ri] -= fz.gcoef * b * fz.usnap[0][ri] * delta;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
@@ -363,6 +458,11 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         for (int s = 0; s < 2; s++) b[f][s] = DevBuf(ctx, (size_t)M->g.nalloc, true);
     cur = 0;
     bool ff = M->tti || M->irho_field;
+    if (M->visco) {
+        rmem = DevBuf(ctx, (size_t)M->g.nalloc, true);
+        wtmp = DevBuf(ctx, (size_t)M->g.nalloc, true);
+        if (born_scratch && !ff) dd[0] = DevBuf(ctx, (size_t)M->g.nalloc, true);
+    }
     if (ff) {
         int nflux = M->tti ? 6 : 3;
         for (int k = 0; k < nflux; k++) flux[k] = DevBuf(ctx, (size_t)M->g.nalloc, true);
@@ -481,13 +581,75 @@ static void step_flux(const judi_model *M, const StepArgs &s)
     flux_one<NDIM, R>(M, W, s.ul, s.ulp, nullptr, ddc, none, nullptr, 0.f, s.born_ic, s.u);
 }
 
+// One visco-acoustic step (forward or adjoint, plain or Born): flux pass (density field) + update.
+template <int NDIM, int R>
+static void visco_one(const judi_model *M, Wavefield *W, const float *p, float *pp, float *r, int adj,
+                      const float *dd_in, float *dd_out, const Fuse &fuse, const float *qext,
+                      float qext_scale)
+{
+    judi_ctx *ctx = M->ctx;
+    ViscoArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = M->g; a.cf = M->cf;
+    a.p = p; a.pp = pp; a.r = r; a.w = W->wtmp.p;
+    a.m = M->m.p; a.irho = M->irho_field ? M->irho.p : nullptr; a.irho_c = M->irho_c;
+    a.tt = M->vtt.p; a.ts = M->vts.p;
+    a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
+    a.adj = adj;
+    a.qext = qext; a.qext_scale = qext_scale;
+    a.dd_in = dd_in; a.dm = M->dm.p; a.dd_out = dd_out;
+    a.f = fuse;
+    dim3 blk(64, 4, 1), grd;
+    if (NDIM == 3) grd = dim3((M->N[0] + 63) / 64, (M->N[1] + 3) / 4, M->N[2]);
+    else grd = dim3((M->N[0] + 63) / 64, (M->N[2] + 3) / 4, 1);
+    if (adj) {
+        visco_pre_adjoint<NDIM><<<grd, blk, 0, ctx->stream>>>(a);
+        launch_count(ctx, "visco_pre_adjoint");
+    }
+    a.Lin = adj ? W->wtmp.p : p;
+    if (M->irho_field) {
+        FluxArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.g = M->g; fa.cf = M->cf;
+        fa.u1 = a.Lin;
+        fa.irho = M->irho.p;
+        for (int d = 0; d < 3; d++) { fa.P[d] = W->flux[d].p; a.P[d] = W->flux[d].p; }
+        dim3 gf;
+        if (NDIM == 3) gf = dim3((M->N[0] + 2 * R + 63) / 64, (M->N[1] + 2 * R + 3) / 4, M->N[2] + 2 * R);
+        else gf = dim3((M->N[0] + 2 * R + 63) / 64, (M->N[2] + 2 * R + 3) / 4, 1);
+        flux_kernel<NDIM, R><<<gf, blk, 0, ctx->stream>>>(fa);
+        launch_count(ctx, "flux_kernel");
+    }
+    visco_update<NDIM, R><<<grd, blk, 0, ctx->stream>>>(a);
+    launch_count(ctx, "visco_update");
+}
+
+template <int NDIM, int R>
+static void step_visco(const judi_model *M, const StepArgs &s)
+{
+    Wavefield *W = s.scratch;
+    JUDI_REQUIRE(W != nullptr && W->rmem.p, "visco-acoustic scratch not bound");
+    JUDI_REQUIRE(!s.f.grad || s.f.ic == JUDI_IC_AS, "visco-acoustic gradients use the 'as' imaging condition");
+    if (!s.born) {
+        visco_one<NDIM, R>(M, W, s.u[0], s.up[0], W->rmem.p, s.adj, nullptr, nullptr, s.f, s.qext, s.qext_scale);
+        return;
+    }
+    JUDI_REQUIRE(s.born_ic == JUDI_IC_AS, "visco-acoustic Born modelling uses the 'as' source");
+    JUDI_REQUIRE(s.lin && s.lin->rmem.p && W->dd[0].p, "visco-acoustic Born scratch not bound");
+    visco_one<NDIM, R>(M, W, s.u[0], s.up[0], W->rmem.p, 0, nullptr, W->dd[0].p, s.f, s.qext, s.qext_scale);
+    Fuse none;
+    memset(&none, 0, sizeof(none));
+    visco_one<NDIM, R>(M, W, s.ul[0], s.ulp[0], s.lin->rmem.p, 0, W->dd[0].p, nullptr, none, nullptr, 0.f);
+}
+
 template <int NDIM>
 static void step_ndim(const judi_model *M, const StepArgs &s)
 {
     bool ff = M->tti || M->irho_field;
 #define DISPATCH_R(RR)                                                              \
     case RR:                                                                        \
-        if (ff) step_flux<NDIM, RR>(M, s);                                          \
+        if (M->visco) step_visco<NDIM, RR>(M, s);                                   \
+        else if (ff) step_flux<NDIM, RR>(M, s);                                     \
         else launch_acoustic_generic<NDIM, RR>(M, s);                               \
         break;
     switch (M->r) {
@@ -528,7 +690,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
     }
     bool ff = M->tti || M->irho_field;
-    bool use_tma = M->ndim == 3 && !ff && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
+    bool use_tma = M->ndim == 3 && !ff && !M->visco && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
                    (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && !s.qext && !s.f.wrec &&
                    (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
     bool born_done = false;
@@ -559,9 +721,9 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.qsrc = s.scratch->dd[0].p;
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
-    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
+    else if (M->ndim == 3 && ff && !M->visco && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
              !(s.scratch && s.scratch->two_pass_only) && (tti3d_step(M, s) || varc3d_step(M, s))) { /* single pass */ }
-    else if (M->ndim == 3 && ff && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
+    else if (M->ndim == 3 && ff && !M->visco && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
              flux3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);

@@ -273,6 +273,40 @@ __global__ void tti_abc_kernel(const float *__restrict__ eps, const float *__res
     C0[i] = __fmul_rn(b, emd);
 }
 
+// relaxation parameters of the SLS model (kernels.py:107-116), in the written expression order
+__global__ void visco_params_kernel(const float *__restrict__ qp, float f0, long long n,
+                                    float *__restrict__ tt, float *__restrict__ ts)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float q = qp[i];
+    const float t_s = __fdiv_rn(__fsub_rn(sqrtf(__fadd_rn(1.f, __fdiv_rn(1.f, __fmul_rn(q, q)))), __fdiv_rn(1.f, q)), f0);
+    const float t_ep = __fdiv_rn(1.f, __fmul_rn(__fmul_rn(f0, f0), t_s));
+    ts[i] = t_s;
+    tt[i] = __fsub_rn(__fdiv_rn(t_ep, t_s), 1.f);
+}
+
+// Visco-acoustic model (models.py:208-214): quality factor field qp (NULL keeps the current one) and
+// the peak frequency f0 the reference passes with every call (propagators.py:46).
+void model_set_visco(judi_model *M, const judi_param *qp, float f0, int on_device)
+{
+    judi_ctx *ctx = M->ctx;
+    JUDI_REQUIRE(!M->tti, "a model cannot be TTI and visco-acoustic");
+    JUDI_REQUIRE(!M->fs, "visco-acoustic propagation with a free surface is not implemented");
+    JUDI_REQUIRE(f0 > 0.f, "f0 must be positive");
+    if (qp && qp->kind != JUDI_PARAM_NONE) model_set_param(M, M->qp, *qp, on_device, 1.0f, true);
+    JUDI_REQUIRE(M->qp.p != nullptr, "visco-acoustic model without qp");
+    M->visco = true;
+    M->f0 = f0;
+    if (!M->vtt.p) {
+        M->vtt = DevBuf(ctx, (size_t)M->g.nalloc, false);
+        M->vts = DevBuf(ctx, (size_t)M->g.nalloc, false);
+    }
+    int nb = (int)((M->g.nalloc + 255) / 256);
+    visco_params_kernel<<<nb, 256, 0, ctx->stream>>>(M->qp.p, f0, M->g.nalloc, M->vtt.p, M->vts.p);
+    launch_count(ctx, "visco_params");
+}
+
 void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
 {
     JUDI_REQUIRE(desc->ndim == 2 || desc->ndim == 3, "ndim must be 2 or 3");

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) acoustic2d_persist(P2Args a)
 // ------------------------------------------------------------------------------------------
 bool persist2d_supported(const judi_model *M, int ic)
 {
-    return M->ndim == 2 && !M->tti && !M->irho_field && !M->fs && ic == JUDI_IC_AS &&
+    return M->ndim == 2 && !M->tti && !M->visco && !M->irho_field && !M->fs && ic == JUDI_IC_AS &&
            (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
 }
 

@@ -279,7 +279,7 @@ void Shot::bind_ext(const ExtSpec *ext, const float *wavelet, int nt, bool on_de
 
 void Shot::apply_ext(StepArgs &s, int t)
 {
-    const bool flux = M->tti || M->irho_field;
+    const bool flux = M->tti || M->irho_field || M->visco;
     const float base = flux ? M->cf.dt2 : M->cf.dt2 / M->irho_c;  // see the update formula
     if (ws_grid.p) {
         s.qext = ws_grid.p;
@@ -310,6 +310,7 @@ void Shot::make_args(StepArgs &s, Wavefield &W)
     s.tmap_prev = W.has_tmap ? &W.tmap_tile[0][1 - W.cur] : nullptr;
     s.tmap_m = W.has_tmap ? &W.tmap_m : nullptr;
     s.scratch = &W;
+    s.adj = adjoint ? 1 : 0;
 }
 
 // One forward (dir=+1) or backward (dir=-1) step of the background field at time index t.
@@ -384,6 +385,7 @@ void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
     const SparseSet *pS = nsrc > 0 ? &S_src : nullptr;
+    sh.adjoint = !fw;
     if (persist2d_supported(M, JUDI_IC_AS) && !sh.ext_active()) {
         P2Fuse pf;
         pf.reg = M->full;
@@ -435,6 +437,7 @@ void run_forward_no_rec(judi_model *M, int fw, int nsrc, const float *src_coords
     };
     if (dev) CUDA_CHECK(cudaMemsetAsync(u_out, 0, (size_t)nt * ng * sizeof(float), ctx->stream));
     else memset(u_out, 0, (size_t)nt * ng * sizeof(float));
+    sh.adjoint = !fw;
     if (fw) {
         for (int t = 1; t <= nt - 2; t++) {
             sh.step_plain(W, t, illum_out ? &fz : nullptr, pS, &q, nullptr, nullptr, nullptr);
@@ -573,6 +576,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     int seg = 0, nseg = 0;          // checkpointing: segment length / count
     int nslots;
     std::vector<DevBuf> ckpt;       // per segment: level t and level t-1 of every field
+    std::vector<DevBuf> ckpt_r;     // ... and the visco-acoustic memory variable
     if (dft) {
         nslots = 0;
     } else if (!o->checkpointing) {
@@ -640,6 +644,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
 
     // ---- forward sweep ---------------------------------------------------------------------
     auto fwd_step = [&](int t, int save_slot) {
+        sh.adjoint = false;
         Fuse f = fsave;
         if (save_slot >= 0)
             for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot_ptr(save_slot, ff);
@@ -676,6 +681,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             if (dft) slot = -1;
             if (record) fwd_step(t, slot);
             else {
+                sh.adjoint = false;
                 Fuse f = fsave;
                 for (int ff = 0; ff < nf; ff++) f.snap[ff] = slot >= 0 ? slot_ptr(slot, ff) : nullptr;
                 sh.step_plain(W, t, &f, pSrc, &q, nullptr, nullptr, nullptr);
@@ -692,8 +698,14 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         // with born_fwd only the background field is checkpointed: the recomputation needs the
         // snapshots of u, not the linearised field
         ckpt.resize((size_t)nseg * 2 * nf);
+        if (M->visco) ckpt_r.resize((size_t)nseg);   // the memory variable is part of the state
         for (int s = 0; s < nseg; s++) {
             int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
+            if (M->visco) {
+                ckpt_r[s] = DevBuf(ctx, (size_t)M->g.nalloc, false);
+                CUDA_CHECK(cudaMemcpyAsync(ckpt_r[s].p, W.rmem.p, (size_t)M->g.nalloc * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+            }
             for (int ff = 0; ff < nf; ff++) {
                 for (int lv = 0; lv < 2; lv++) {
                     DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];
@@ -766,6 +778,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             corr.reg = reg;
         }
         bool any = f.grad || f.illum;
+        sh.adjoint = true;
         sh.ext_on = false;  // the extended source drives the forward sweep only
         sh.step_plain(V, t, any ? &f : nullptr, &S_rec, &rec, slot >= 0 ? &corr : nullptr, nullptr,
                       nullptr);
@@ -801,6 +814,11 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
             // restore the state at the start of the segment and recompute its snapshots
             W.cur = 0;
+            if (M->visco) {
+                CUDA_CHECK(cudaMemcpyAsync(W.rmem.p, ckpt_r[s].p, (size_t)M->g.nalloc * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+                ckpt_r[s].reset();
+            }
             for (int ff = 0; ff < nf; ff++)
                 for (int lv = 0; lv < 2; lv++) {
                     DevBuf &c = ckpt[((size_t)s * nf + ff) * 2 + lv];

@@ -29,6 +29,7 @@ struct Shot {
     const float *qwf_dev = nullptr;
     DevBuf qwf_owned;
     bool ext_on = true;
+    bool adjoint = false;      // direction of the sweep being stepped (visco-acoustic steps differ)
     bool ext_active() const { return ext_on && (ws_grid.p || qwf_dev || wrec.p); }
     void bind_ext(const ExtSpec *ext, const float *wavelet, int nt, bool on_device);
     void apply_ext(StepArgs &s, int t);

@@ -470,7 +470,7 @@ static int variant_of(const judi_model *M)
 
 bool tma3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && !M->tti && !M->irho_field && (M->r == 2 || M->r == 4 || M->r == 8) &&
+    return M->ndim == 3 && !M->tti && !M->irho_field && !M->visco && (M->r == 2 || M->r == 4 || M->r == 8) &&
            M->ctx->encode_tiled != nullptr;
 }
 

@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
 // ---- host side ---------------------------------------------------------------------------------
 bool tti3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && M->tti && !M->irho_field && M->r == tti::R && M->ctx->encode_tiled != nullptr &&
+    return M->ndim == 3 && M->tti && !M->visco && !M->irho_field && M->r == tti::R && M->ctx->encode_tiled != nullptr &&
            M->ctx->opt_tti_fused && M->ttiABC[0].p != nullptr;
 }
 

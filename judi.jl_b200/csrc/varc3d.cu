@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
 // ---- host side ---------------------------------------------------------------------------------
 bool varc3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && !M->tti && M->irho_field && M->r == varc::R && M->ctx->encode_tiled != nullptr &&
+    return M->ndim == 3 && !M->tti && !M->visco && M->irho_field && M->r == varc::R && M->ctx->encode_tiled != nullptr &&
            M->ctx->opt_varc_fused;
 }
 

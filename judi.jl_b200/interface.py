@@ -49,6 +49,23 @@ def _ptr(a):
     return a.ctypes.data
 
 
+def _with_f0(fn):
+    """`f0` (kHz) only matters for visco-acoustic models: it sets the relaxation times of the next
+    call (propagators.py:46).  None keeps the model's value (reference default 0.015)."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        bound = sig.bind(*args, **kwargs)
+        model = bound.arguments.get("model")
+        if model is not None and hasattr(model, "set_f0"):
+            model.set_f0(bound.arguments.get("f0"))
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _grid_out(model, out):
     if out is not None:
         return out
@@ -56,7 +73,8 @@ def _grid_out(model, out):
 
 
 # Forward wrappers Pr*F*Ps'*q
-def forward_rec(model, src_coords, wavelet, rec_coords, f0=0.015, illum=False, fw=True,
+@_with_f0
+def forward_rec(model, src_coords, wavelet, rec_coords, f0=None, illum=False, fw=True,
                 rec_out=None, illum_out=None):
     """Modeling of a point source with receivers Pr*F*Ps^T*q (interface.py:17-47).
 
@@ -83,7 +101,8 @@ def forward_rec(model, src_coords, wavelet, rec_coords, f0=0.015, illum=False, f
 
 
 # F*Ps'*q
-def forward_no_rec(model, src_coords, wavelet, f0=0.015, illum=False, fw=True):
+@_with_f0
+def forward_no_rec(model, src_coords, wavelet, f0=None, illum=False, fw=True):
     """Forward modeling of a point source without receiver (interface.py:83-111): returns the
     wavefield history (nt, nx[,ny],nz) on the padded grid and the illumination."""
     sc = _coords(src_coords, model.dim)
@@ -96,7 +115,8 @@ def forward_no_rec(model, src_coords, wavelet, f0=0.015, illum=False, fw=True):
 
 
 # Linearized modeling d/dm (Pr*F*Ps'*q)
-def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=0.015, illum=False, fw=True,
+@_with_f0
+def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=None, illum=False, fw=True,
              rec_out=None, illum_out=None):
     """Linearized (Born) modeling of a point source for the model's dm (interface.py:208-241)."""
     if not fw:
@@ -119,9 +139,10 @@ def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=0.015, illum=Fa
     return rec, I
 
 
+@_with_f0
 def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
               checkpointing=False, n_checkpoints=None, t_sub=1, return_obj=False, freq_list=None,
-              dft_sub=None, ic="as", illum=False, ws=None, f0=0.015, born_fwd=False, nlind=False,
+              dft_sub=None, ic="as", illum=False, ws=None, f0=None, born_fwd=False, nlind=False,
               misfit=None, fw=True, snapshot_region="padded", grad_out=None, f_out=None,
               illum_out=None, accumulate=False):
     """Adjoint Jacobian on a shot record (interface.py:279-345): standard zero-lag
@@ -226,7 +247,8 @@ def _weights(model, w):
 
 
 # Pr*F*Pw'*w
-def forward_rec_w(model, weight, wavelet, rec_coords, f0=0.015, illum=False, fw=True):
+@_with_f0
+def forward_rec_w(model, weight, wavelet, rec_coords, f0=None, illum=False, fw=True):
     """Forward modeling of an extended source with receivers Pr*F*Pw^T*w (interface.py:50-80)."""
     rc = _coords(rec_coords, model.dim)
     q, nt, _ = _traces(wavelet)
@@ -239,7 +261,8 @@ def forward_rec_w(model, weight, wavelet, rec_coords, f0=0.015, illum=False, fw=
 
 
 # Pw*F'*Pr'*d_obs
-def adjoint_w(model, rec_coords, data, wavelet, f0=0.015, illum=False, fw=True):
+@_with_f0
+def adjoint_w(model, rec_coords, data, wavelet, f0=None, illum=False, fw=True):
     """Adjoint modeling of a shot record for an extended source Pw*F^T*Pr^T*d (interface.py:174-204):
     returns the spatial distribution on the padded grid."""
     rc = _coords(rec_coords, model.dim)
@@ -254,7 +277,8 @@ def adjoint_w(model, rec_coords, data, wavelet, f0=0.015, illum=False, fw=True):
 
 
 # d/dm (Pr*F*Pw'*w)
-def born_rec_w(model, weight, wavelet, rec_coords, ic="as", f0=0.015, illum=False, fw=True):
+@_with_f0
+def born_rec_w(model, weight, wavelet, rec_coords, ic="as", f0=None, illum=False, fw=True):
     """Linearized modeling of an extended source (interface.py:244-276)."""
     rc = _coords(rec_coords, model.dim)
     q, nt, _ = _traces(wavelet)
@@ -274,7 +298,8 @@ def _wf_src(model, u):
 
 
 # Pr*F*u
-def forward_wf_src(model, u, rec_coords, f0=0.015, illum=False, fw=True):
+@_with_f0
+def forward_wf_src(model, u, rec_coords, f0=None, illum=False, fw=True):
     """Forward modeling of a full wavefield source Pr*F*u (interface.py:114-142)."""
     rc = _coords(rec_coords, model.dim)
     us, nt = _wf_src(model, u)
@@ -286,7 +311,8 @@ def forward_wf_src(model, u, rec_coords, f0=0.015, illum=False, fw=True):
 
 
 # F*u
-def forward_wf_src_norec(model, u, f0=0.015, illum=False, fw=True):
+@_with_f0
+def forward_wf_src_norec(model, u, f0=None, illum=False, fw=True):
     """Forward modeling of a full wavefield source without receivers F*u (interface.py:145-171)."""
     us, nt = _wf_src(model, u)
     out = np.zeros(model.shape_pml + (nt,), dtype=np.float32, order="F")

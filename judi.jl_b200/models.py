@@ -113,15 +113,18 @@ class Model(object):
 
     Same signature as pysource `Model(origin, spacing, shape, space_order=8, nbl=40, m=...,
     epsilon=..., delta=..., theta=..., phi=..., rho=..., b=..., dm=..., fs=False, dt=...)`.
-    Visco-acoustic (`qp`) and elastic (`lam`, `mu`) models are outside this backend's path.
+    `qp` makes the model visco-acoustic (models.py:208-214, kernels.py:80-141); `f0` (kHz) is the
+    peak frequency of its relaxation times, the value the reference passes with every call
+    (`f0=options.f0`): set it here or per call with `set_f0`.  Elastic (`lam`, `mu`) models are
+    outside this backend's path.
     """
 
     def __init__(self, origin, spacing, shape, space_order=8, nbl=40, dtype=np.float32,
                  m=None, epsilon=None, delta=None, theta=None, phi=None, rho=None, b=None,
                  qp=None, lam=None, mu=None, dm=None, fs=False, context=None, **kwargs):
-        if qp is not None or lam is not None or mu is not None:
-            raise NotImplementedError("visco-acoustic / elastic models are out of the B200 "
-                                      "backend's scope (acoustic and TTI only)")
+        if lam is not None or mu is not None:
+            raise NotImplementedError("elastic models are out of the B200 backend's scope "
+                                      "(acoustic, visco-acoustic and TTI only)")
         if np.dtype(dtype) != np.float32:
             raise NotImplementedError("the B200 backend computes in float32 like the reference")
         if m is None:
@@ -136,7 +139,8 @@ class Model(object):
         self.space_order = int(space_order)
         self._dt = kwargs.get("dt")
         self.is_tti = any(p is not None for p in (epsilon, delta, theta, phi))
-        self.is_viscoacoustic = False
+        self.is_viscoacoustic = qp is not None
+        self.f0 = float(kwargs.get("f0", 0.015))
         self.is_elastic = False
         keep = []
         d = L.JudiModelDesc()
@@ -160,6 +164,17 @@ class Model(object):
         d.params_on_device = int(bool(on_dev) and all(on_dev))
         self.h = L.check_ptr(L.lib().judi_model_create(self.ctx.h, ctypes.byref(d)))
         self._has_dm = d.dm.kind == L.PARAM_ARRAY or (d.dm.kind == L.PARAM_SCALAR and d.dm.value != 0)
+        if self.is_viscoacoustic:
+            qv = qp if (is_device_tensor(qp) or np.ndim(qp) > 0) else np.full(self.shape, qp, dtype=np.float32)
+            pq, dev = _as_param(qv, self.shape, keep)
+            L.check(L.lib().judi_model_set_visco(self.h, ctypes.byref(pq), self.f0, int(dev)))
+
+    def set_f0(self, f0):
+        """Peak frequency (kHz) used by the following calls on a visco-acoustic model."""
+        if f0 is None or not self.is_viscoacoustic or float(f0) == self.f0:
+            return
+        self.f0 = float(f0)
+        L.check(L.lib().judi_model_set_visco(self.h, None, self.f0, 0))
 
     def __del__(self):
         try:

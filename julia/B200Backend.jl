@@ -78,6 +78,11 @@ function b200_model(model::AbstractModel, options::JUDIOptions, dm)
     h = GC.@preserve p dm ccall((:judi_model_create, LIB), Ptr{Cvoid},
                                 (Ptr{Cvoid}, Ref{JudiModelDesc}), ctx(), desc)
     h == C_NULL && error("judi_b200: " * lasterr())
+    if haskey(p, :qp)   # visco-acoustic model (Model(n, d, o, m, rho, qp)); f0 = options.f0 as the reference passes it
+        qp = param(p[:qp])
+        GC.@preserve p check(ccall((:judi_model_set_visco, LIB), Cint, (Ptr{Cvoid}, Ref{JudiParam}, Cfloat, Cint),
+                                   h, qp, options.f0, 0))
+    end
     return h
 end
 critical_dt(h) = ccall((:judi_model_critical_dt, LIB), Cfloat, (Ptr{Cvoid},), h)

@@ -33,7 +33,8 @@ def both(kind, ndim, so, nt=NT, **kw):
 
 
 CASES = [("iso", 2, 8), ("iso", 2, 4), ("iso", 2, 16), ("rho", 2, 8), ("tti", 2, 8),
-         ("iso", 3, 8), ("iso", 3, 4), ("iso", 3, 16), ("rho", 3, 8), ("tti", 3, 8)]
+         ("iso", 3, 8), ("iso", 3, 4), ("iso", 3, 16), ("rho", 3, 8), ("tti", 3, 8),
+         ("visco", 2, 8), ("viscoc", 2, 8), ("visco", 2, 4), ("visco", 3, 8), ("viscoc", 3, 8)]
 
 
 @pytest.mark.parametrize("kind,ndim,so", CASES)
@@ -90,7 +91,8 @@ def test_born_and_gradient_parity_and_dot(kind, ndim, so):
     assert abs((c - e) / (c + e)) < TOL_DOT
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3), ("tti", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3), ("tti", 3),
+                                       ("visco", 2), ("viscoc", 3)])
 def test_fwi_objective_and_options(kind, ndim):
     """fwi objective value + gradient, t_sub, checkpointing, physical-domain snapshots,
     lsrtm (born_fwd, nlind), illumination (test_gradients.jl, test_all_options.jl)."""
