@@ -555,11 +555,48 @@ static inline void sls_params(const ogrid *g, size_t i, real *tt, real *ts)
     *tt = t_ep / t_s - 1;
 }
 
+/* point-wise parts of the scheme (exposed for tests/test_reference_golden.py) */
+static inline real visco_r_adjoint(real dt, real ts, real b, real dl, real p, real r)
+{
+    real r2 = 1 / dt;
+    return (1 - dl) * ((r * r2 - b * p - r / ts) / r2);
+}
+static inline real visco_r_forward(real dt, real tt, real ts, real b, real dl, real r, real L)
+{
+    real r2 = 1 / dt;
+    return (1 - dl) * ((b * r2 * r + (tt / ts) * L - (b / ts) * r) / (b * r2));
+}
+/* new pressure level from the current one (pc), the other one (po), and S = the spatial / source
+ * terms: (1 + tt) L(p) - b r+ + q (forward),  L(w) + q (adjoint) */
+static inline real visco_p_update(real dt, real mb, real dl, real pc, real po, real S)
+{
+    real r1 = 1 / (dt * dt), r2 = 1 / dt;
+    return (mb * r1 * (2 * pc - po) + dl * r2 * pc + S) / (mb * r1 + dl * r2);
+}
+void oracle_visco_point(int adj, real dt, real f0, real qp, real b, real m, real dl, real pc, real po,
+                        real r, real L, real q, real *r_new, real *p_new, real *w_factor_p,
+                        real *w_factor_r)
+{
+    ogrid g;
+    g.f0 = f0; g.qp = &qp;
+    real tt, ts;
+    sls_params(&g, 0, &tt, &ts);
+    if (!adj) {
+        real rn = visco_r_forward(dt, tt, ts, b, dl, r, L);
+        *r_new = rn;
+        *p_new = visco_p_update(dt, m * b, dl, pc, po, (1 + tt) * L - b * rn + q);
+    } else {
+        *r_new = visco_r_adjoint(dt, ts, b, dl, pc, r);
+        *p_new = visco_p_update(dt, m * b, dl, pc, po, L + q);   /* L = laplacian(w, b) */
+    }
+    *w_factor_p = 1 + tt;            /* w = (1 + tt) p + (tt / (b t_s)) r- */
+    *w_factor_r = tt / (b * ts);
+}
+
 static void step_visco(const ogrid *g, oscratch *sc, const real *p, real *pp, real *r, const real *q,
                        int adj)
 {
     int X = g->N[0], Y = g->N[1], Z = g->N[2];
-    real r1 = 1 / (g->dt * g->dt), r2 = 1 / g->dt;
     int ff = flux_form(g);
     const real *Lin = p;
     if (adj) {
@@ -571,7 +608,7 @@ static void step_visco(const ogrid *g, oscratch *sc, const real *p, real *pp, re
                     real tt, ts;
                     sls_params(g, i, &tt, &ts);
                     real b = g->irho[i];
-                    real rn = (1 - g->damp[i]) * ((r[i] * r2 - b * p[i] - r[i] / ts) / r2);
+                    real rn = visco_r_adjoint(g->dt, ts, b, g->damp[i], p[i], r[i]);
                     r[i] = rn;
                     sc->w[i] = (1 + tt) * p[i] + (tt / (b * ts)) * rn;
                 }
@@ -585,17 +622,15 @@ static void step_visco(const ogrid *g, oscratch *sc, const real *p, real *pp, re
                 size_t i = IDX(g, x, y, z);
                 real b = g->irho[i], mb = g->m[i] * b, dl = g->damp[i];
                 real L = ff ? divergence(g, sc->P, i) : g->irho_c * lap_const(g, Lin, i);
-                real qq = q ? q[i] : 0;
-                real pc = p[i];
-                real rhs = mb * r1 * (2 * pc - pp[i]) + dl * r2 * pc + qq;
+                real S = L + (q ? q[i] : 0);
                 if (!adj) {
                     real tt, ts;
                     sls_params(g, i, &tt, &ts);
-                    real rn = (1 - dl) * ((b * r2 * r[i] + (tt / ts) * L - (b / ts) * r[i]) / (b * r2));
+                    real rn = visco_r_forward(g->dt, tt, ts, b, dl, r[i], L);
                     r[i] = rn;
-                    rhs += (1 + tt) * L - b * rn;
-                } else rhs += L;
-                pp[i] = rhs / (mb * r1 + dl * r2);
+                    S = (1 + tt) * L - b * rn + (q ? q[i] : 0);
+                }
+                pp[i] = visco_p_update(g->dt, mb, dl, p[i], pp[i], S);
             }
 }
 

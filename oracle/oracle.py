@@ -79,6 +79,7 @@ def _lib(precision):
     lib.oracle_ic_point.restype = real
     lib.oracle_linsrc_point.argtypes = [ctypes.c_int, real, real, real, real, real]
     lib.oracle_linsrc_point.restype = real
+    lib.oracle_visco_point.argtypes = [ctypes.c_int] + [real] * 11 + [P, P, P, P]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
     _LIBS[precision] = lib
@@ -546,6 +547,14 @@ def ic_point(ic, us, dt2v, m, inner_grad, precision="f64"):
 def linsrc_point(ic, dm, irho, m, dt2u, lapw, precision="f64"):
     """Linearised (Born) source of one field at one point."""
     return float(_lib(precision).oracle_linsrc_point(_IC[ic], dm, irho, m, dt2u, lapw))
+
+
+def visco_point(adj, dt, f0, qp, b, m, dl, pc, po, r, L, q=0.0, precision="f64"):
+    """One point of the visco-acoustic SLS step: (r_new, p_new, w factor of p, w factor of r-)."""
+    lib = _lib(precision)
+    out = [np.zeros(1, dtype=lib._dtype) for _ in range(4)]
+    lib.oracle_visco_point(int(adj), dt, f0, qp, b, m, dl, pc, po, r, L, q, *[_ptr(o) for o in out])
+    return tuple(float(o[0]) for o in out)
 
 
 # --------------------------------------------------------------------------------------------

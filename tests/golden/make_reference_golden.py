@@ -11,6 +11,9 @@ replaced by an import stub that only provides symbols (no semantics of its own b
     factors of the imaging conditions and Born sources, on symbolic fields   (sensitivity.py:55-69, 106-122, 157-233)
   * sensitivity.Loss on numpy data (plain, is_residual, (background, linearised) tuple)   (sensitivity.py:236-276)
   * fields.wavefield_subsampled: number of saved snapshots   (fields.py:123-153)
+  * kernels.SLS_2nd_order: the visco-acoustic update of memory variable and pressure, forward and
+    adjoint, with `solve` done by sympy after u.dt2, u.dt, u.dt.T are replaced by their time
+    stencils (the one-sided u.dt of SURVEY A.3 is THIS script's assumption, stated in the stub)   (kernels.py:80-141)
 
 Run from the repository root (needs /root/reference):  python tests/golden/make_reference_golden.py
 Output: tests/golden/reference_golden.json (committed; the tests never read /root/reference).
@@ -70,8 +73,15 @@ class _Trig(object):
 CAPTURED = {}
 
 
+GRAD_OF = {}
+
+
 def _grad(u, shift=None):
     assert shift == .5
+    if not isinstance(u, Field):       # gradient of an expression: fresh symbols, argument recorded
+        k = len(GRAD_OF)
+        GRAD_OF[k] = u
+        return sp.Matrix([sp.Symbol("gexpr%d_%s" % (k, d)) for d in "xyz"])
     return sp.Matrix([sp.Symbol("g%s_%s" % (u.name, d)) for d in "xyz"][:u.dim] if u.dim == 3 else
                      [sp.Symbol("g%s_x" % u.name), sp.Symbol("g%s_z" % u.name)])
 
@@ -87,11 +97,21 @@ def _tensor(name=None, grid=None, components=None, symmetric=None, diagonal=None
     return sp.Matrix(components)
 
 
+class _Dt(sp.Symbol):
+    @property
+    def T(self):
+        return sp.Symbol(self.name + "T")
+
+
+FIELDS = []
+
+
 class Field(sp.Symbol):
     """A symbolic (time) function: u, u.dt2 and its staggered gradient are independent symbols."""
     def __new__(cls, name, dim=3):
         obj = sp.Symbol.__new__(cls, name)
         obj.dim = dim
+        FIELDS.append(obj)
         return obj
 
     @property
@@ -99,9 +119,44 @@ class Field(sp.Symbol):
         return sp.Symbol(self.name + "_dt2")
 
     @property
+    def dt(self):
+        return _Dt(self.name + "_dt")
+
+    @property
+    def forward(self):
+        return sp.Symbol(self.name + "_f")
+
+    @property
+    def backward(self):
+        return sp.Symbol(self.name + "_b")
+
+    @property
+    def laplace(self):
+        return sp.Symbol(self.name + "_lap")
+
+    @property
     def indices(self):
         t = types.SimpleNamespace(spacing=sp.Symbol("dt_save"))
         return (t,)
+
+
+def _solve(expr, target):
+    """devito.solve for these linear equations, after writing the time derivatives as stencils:
+    u.dt2 = (u+ - 2u + u-)/dt^2, u.dt = (u+ - u)/dt (Devito's one-sided first derivative for
+    time_order 2, SURVEY A.3 [dv]) and its transpose u.dt.T = (u- - u)/dt."""
+    dt = sp.Symbol("dt")
+    byname = {}
+    for f in FIELDS:
+        u = sp.Symbol(f.name)
+        byname[f.name] = u
+        byname[f.name + "_dt2"] = (f.forward - 2 * u + f.backward) / dt ** 2
+        byname[f.name + "_dt"] = (f.forward - u) / dt
+        byname[f.name + "_dtT"] = (f.backward - u) / dt
+    expr = sp.sympify(expr)
+    expr = expr.xreplace({s_: byname[s_.name] for s_ in expr.free_symbols if s_.name in byname})
+    sol = sp.solve(expr, target)
+    assert len(sol) == 1
+    return sol[0]
 
 
 def install_stub():
@@ -113,6 +168,7 @@ def install_stub():
     dv.Function = type("Function", (), {})
     dv.Constant = type("Constant", (), {})
     dv.Eq = lambda *a, **k: ("Eq",) + a
+    dv.solve = _solve
     dv.switchconfig = lambda **k: (lambda f: f)
     tools = _Module("devito.tools")
     tools.as_tuple = _as_tuple
@@ -278,6 +334,47 @@ def main():
             wf = fields.wavefield_subsampled(model, Field("u"), nt, t_sub)
             saves.append(dict(nt=nt, t_sub=t_sub, nsave=None if wf is None else int(wf[0].kw["save"])))
     out["cases"]["nsave"] = saves
+
+    # ---- 6. visco-acoustic SLS update ---------------------------------------------------------------
+    import kernels
+    kernels.memory_field = lambda p: Field("r" + p.name)
+    visco = []
+    for fw in (True, False):
+        CAPTURED.clear(); GRAD_OF.clear()
+        model = types.SimpleNamespace(qp=sp.Symbol("qp"), irho=sp.Symbol("b"), damp=sp.Symbol("damp"),
+                                      m=sp.Symbol("m"))
+        pf = Field("p")
+        (u_r, u_p), _ = kernels.SLS_2nd_order(model, pf, fw=fw, q=sp.Symbol("q"), f0=sp.Symbol("f0"))
+        r_new, p_new = u_r[2], u_p[2]
+        tgt_r = sp.Symbol("rp_f" if fw else "rp_b")
+        assert u_r[1] == tgt_r and u_p[1] == sp.Symbol("p_f" if fw else "p_b")
+        # laplacian(v, b) = div(b * grad(v)): each captured div is one application of L
+        for k in range(6):
+            vals = dict(dt=float(rng.uniform(0.5, 2.0)), f0=float(rng.uniform(0.008, 0.03)),
+                        qp=float(rng.uniform(20., 200.)), b=float(rng.uniform(0.4, 1.2)),
+                        m=float(rng.uniform(0.05, 0.5)), damp=float(rng.uniform(0.7, 1.0)),
+                        p=float(rng.standard_normal()), rp=float(rng.standard_normal()),
+                        q=float(rng.standard_normal()))
+            vals["p_b" if fw else "p_f"] = float(rng.standard_normal())     # the other time level
+            for name in CAPTURED:
+                vals[name] = float(rng.standard_normal())
+            if fw:
+                vals["div1"] = vals["div0"]      # both are laplacian(p, b)
+            def nsub(e, extra={}):       # substitute by NAME (Field / _Dt are Symbol subclasses)
+                e = sp.sympify(e)
+                table = dict(vals, **extra)
+                return float(e.xreplace({s_: sp.Float(table[s_.name]) for s_ in e.free_symbols}))
+            rn = nsub(r_new)
+            pn = nsub(p_new, {tgt_r.name: rn})
+            entry = dict(fw=fw, inputs=vals, r_new=rn, p_new=pn)
+            if not fw:
+                # what the two Laplacians of the adjoint pressure equation are applied to, as the
+                # coefficients of p and of r- :  (1 + tt) p  and  (tt / (b t_s)) r-
+                e0, e1 = GRAD_OF[0], GRAD_OF[1]
+                entry["w_factor_p"] = nsub(e0) / vals["p"]
+                entry["w_factor_r"] = nsub(e1, {tgt_r.name: rn}) / rn
+            visco.append(entry)
+    out["cases"]["visco"] = visco
 
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:

@@ -4,7 +4,8 @@ tests/golden/make_reference_golden.py, which also lists the reference file:line 
 
 What this pins to the reference's executed code: the CFL coefficient and critical dt, padsizes,
 the rotated TTI flux algebra (R_mat / thomsen_mat / sa_tti), signs and factors of the "as" / "isic"
-/ "fwi" imaging conditions and Born sources, Loss, and the number of saved snapshots.  What it
+/ "fwi" imaging conditions and Born sources, Loss, the number of saved snapshots and the
+visco-acoustic SLS update (modulo the time-stencil convention the stub states).  What it
 cannot pin: the Devito-generated stencil loops themselves.
 """
 import json
@@ -123,6 +124,26 @@ def test_loss(r):
         f, res = O.Loss(dsyn, dobs, r["dt"], is_residual=(r["mode"] == "is_residual"))
     assert float(f) == pytest.approx(r["f"], rel=1e-6)
     assert np.allclose(res, np.asarray(r["residual"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["visco"])))
+def test_visco_acoustic_update(i):
+    """kernels.SLS_2nd_order executed symbolically (forward and adjoint): relaxation parameters,
+    signs, where b, m and the mask-type damp enter, and what the adjoint's Laplacians act on."""
+    c = GOLD["visco"][i]
+    v = c["inputs"]
+    dl = 1.0 - v["damp"]                      # the reference's field is the mask 1 - layer profile
+    if c["fw"]:
+        rn, pn, _, _ = O.visco_point(0, v["dt"], v["f0"], v["qp"], v["b"], v["m"], dl, v["p"], v["p_b"],
+                                     v["rp"], v["div0"], v["q"])
+    else:
+        L = v["div0"] + v["div1"]             # laplacian((1+tt) p, b) + laplacian((tt/(b t_s)) r-, b)
+        rn, pn, wp, wr = O.visco_point(1, v["dt"], v["f0"], v["qp"], v["b"], v["m"], dl, v["p"], v["p_f"],
+                                       v["rp"], L, v["q"])
+        assert wp == pytest.approx(c["w_factor_p"], rel=1e-11)
+        assert wr == pytest.approx(c["w_factor_r"], rel=1e-9)
+    assert rn == pytest.approx(c["r_new"], rel=1e-11)
+    assert pn == pytest.approx(c["p_new"], rel=1e-10)
 
 
 def test_number_of_saved_snapshots():
