@@ -634,6 +634,18 @@ static void step_visco(const ogrid *g, oscratch *sc, const real *p, real *pp, re
             }
 }
 
+/* The leapfrog update of one point (kernels.py:61-71 / 161-175): a = m irho / dt^2, b = damp / dt,
+ * inv = 1 / (a + b), S = L(u) + q.  Exposed for tests/test_reference_golden.py. */
+static inline real leapfrog_point(real a, real b, real inv, real uc, real uo, real S)
+{
+    return (a * (2 * uc - uo) + b * uc + S) * inv;
+}
+real oracle_leapfrog_point(real dt, real m, real irho, real damp, real uc, real uo, real S)
+{
+    real a = m * irho / (dt * dt), b = damp / dt;
+    return leapfrog_point(a, b, 1 / (a + b), uc, uo, S);
+}
+
 /* One leapfrog update of every padded-grid point:
  *   un = ( a*(2u - up) + b*u + L(u) + q ) / (a + b),  a = m*irho/dt^2,  b = damp/dt
  * `un` may alias `up` (2-slot buffer, fields.py:42).  Forward and adjoint are mirror images
@@ -665,8 +677,7 @@ static void step_fields(const ogrid *g, oscratch *sc, int nf, real *const *u, re
                     if (!ff) L = g->irho_c * lap_const(g, u[f], i);
                     else L = divergence(g, f == 0 ? sc->P : sc->M, i);
                     real q = qsrc ? qsrc[f][i] : 0;
-                    real uc = u[f][i];
-                    un[f][i] = (a * (2 * uc - up[f][i]) + b * uc + L + q) * inv;
+                    un[f][i] = leapfrog_point(a, b, inv, u[f][i], up[f][i], L + q);
                 }
             }
 }

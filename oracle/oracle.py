@@ -79,6 +79,8 @@ def _lib(precision):
     lib.oracle_ic_point.restype = real
     lib.oracle_linsrc_point.argtypes = [ctypes.c_int, real, real, real, real, real]
     lib.oracle_linsrc_point.restype = real
+    lib.oracle_leapfrog_point.argtypes = [real] * 7
+    lib.oracle_leapfrog_point.restype = real
     lib.oracle_visco_point.argtypes = [ctypes.c_int] + [real] * 11 + [P, P, P, P]
     lib._real = real
     lib._dtype = np.float32 if precision == "f32" else np.float64
@@ -547,6 +549,11 @@ def ic_point(ic, us, dt2v, m, inner_grad, precision="f64"):
 def linsrc_point(ic, dm, irho, m, dt2u, lapw, precision="f64"):
     """Linearised (Born) source of one field at one point."""
     return float(_lib(precision).oracle_linsrc_point(_IC[ic], dm, irho, m, dt2u, lapw))
+
+
+def leapfrog_point(dt, m, irho, damp, uc, uo, S, precision="f64"):
+    """New time level of one point of the acoustic / TTI update from S = L(u) + q."""
+    return float(_lib(precision).oracle_leapfrog_point(dt, m, irho, damp, uc, uo, S))
 
 
 def visco_point(adj, dt, f0, qp, b, m, dl, pc, po, r, L, q=0.0, precision="f64"):

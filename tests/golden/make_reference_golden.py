@@ -376,6 +376,44 @@ def main():
             visco.append(entry)
     out["cases"]["visco"] = visco
 
+    # ---- 7. acoustic and TTI time update ------------------------------------------------------------
+    upd = []
+    for kind in ("acoustic", "acoustic_rho", "tti"):
+        for fw in (True, False):
+            CAPTURED.clear()
+            model = types.SimpleNamespace(irho=(sp.Symbol("b") if kind != "acoustic" else 0.8),
+                                          m=sp.Symbol("m"), damp=sp.Symbol("damp"), fs=False,
+                                          physical=None, dim=3, grid=None, epsilon=sp.Symbol("eps"),
+                                          delta=sp.Symbol("delta"), theta=sp.Symbol("theta"),
+                                          phi=sp.Symbol("phi"))
+            if kind == "tti":
+                u1, u2 = Field("u1"), Field("u2")
+                eqs, _ = kernels.tti_kernel(model, u1, u2, fw=fw, q=(sp.Symbol("q1"), sp.Symbol("q2")))
+                names = ["u1", "u2"]
+            else:
+                u1 = Field("u1")
+                eqs, _ = kernels.acoustic_kernel(model, u1, fw=fw, q=sp.Symbol("q1"))
+                names = ["u1"]
+            for k in range(3):
+                vals = dict(dt=float(rng.uniform(0.5, 2.0)), b=float(rng.uniform(0.4, 1.2)),
+                            m=float(rng.uniform(0.05, 0.5)), damp=float(rng.uniform(0.0, 0.05)))
+                for n_ in names:
+                    vals[n_] = float(rng.standard_normal())
+                    vals[n_ + ("_b" if fw else "_f")] = float(rng.standard_normal())
+                    vals["q" + n_[1]] = float(rng.standard_normal())
+                    vals[n_ + "_lap"] = float(rng.standard_normal())
+                for name in CAPTURED:
+                    vals[name] = float(rng.standard_normal())
+
+                def nsub(e):
+                    e = sp.sympify(e)
+                    return float(e.xreplace({s_: sp.Float(vals[s_.name]) for s_ in e.free_symbols}))
+                # which spatial term each equation carries: b * u.laplace (scalar density) or a
+                # captured div(...) symbol (density field / TTI: div0 -> H0, div1 -> H1)
+                upd.append(dict(kind=kind, fw=fw, inputs=vals, irho=(0.8 if kind == "acoustic" else vals["b"]),
+                                new=[nsub(e[2]) for e in eqs]))
+    out["cases"]["update"] = upd
+
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0)

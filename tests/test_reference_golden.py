@@ -146,6 +146,24 @@ def test_visco_acoustic_update(i):
     assert pn == pytest.approx(c["p_new"], rel=1e-10)
 
 
+@pytest.mark.parametrize("i", range(len(GOLD["update"])))
+def test_acoustic_and_tti_time_update(i):
+    """kernels.acoustic_kernel / tti_kernel executed symbolically, forward and adjoint:
+    solve(m irho u.dt2 + damp u.dt[.T] - L - q, u+-) with L = irho * u.laplace for a scalar density,
+    div(irho grad u) for a density field, (H0, H1) of sa_tti for TTI."""
+    c = GOLD["update"][i]
+    v = c["inputs"]
+    other = "_b" if c["fw"] else "_f"
+    for f, name in enumerate(["u1", "u2"][:len(c["new"])]):
+        if c["kind"] == "acoustic":
+            L = c["irho"] * v[name + "_lap"]
+        else:
+            L = v["div%d" % f]
+        S = L + v["q%d" % (f + 1)]
+        un = O.leapfrog_point(v["dt"], v["m"], c["irho"], v["damp"], v[name], v[name + other], S)
+        assert un == pytest.approx(c["new"][f], rel=1e-10)
+
+
 def test_number_of_saved_snapshots():
     for c in GOLD["nsave"]:
         if c["nsave"] is not None:
