@@ -551,6 +551,16 @@ def linsrc_point(ic, dm, irho, m, dt2u, lapw, precision="f64"):
     return float(_lib(precision).oracle_linsrc_point(_IC[ic], dm, irho, m, dt2u, lapw))
 
 
+def fd_weights(model):
+    """(centred 2nd-derivative weights c2[0..r], staggered 1st-derivative weights w1[1..r]) of the
+    C loops, in units of 1/h^2 and 1/h."""
+    lib = model.lib
+    c2 = np.zeros(9, dtype=lib._dtype); w1 = np.zeros(9, dtype=lib._dtype)
+    lib.oracle_weights(model.handle(), _ptr(c2), _ptr(w1))
+    r = model.space_order // 2
+    return c2[:r + 1].copy(), w1[1:r + 1].copy()
+
+
 def leapfrog_point(dt, m, irho, damp, uc, uo, S, precision="f64"):
     """New time level of one point of the acoustic / TTI update from S = L(u) + q."""
     return float(_lib(precision).oracle_leapfrog_point(dt, m, irho, damp, uc, uo, S))

@@ -178,3 +178,20 @@ def test_library_critical_dt_matches_reference(i):
     c = GOLD["critical_dt"][i]
     gm = J.Model(**_model_kw(c))
     assert np.float32(gm.critical_dt) == np.float32(c["dt"])
+
+
+@pytest.mark.parametrize("so", [4, 8, 12, 16])
+def test_finite_difference_weights_are_sympy_taylor_weights(so):
+    """Devito builds its stencils from sympy.finite_diff_weights (the same function models.py:5,452
+    imports for the CFL number): centred 2nd derivative on so+1 points, and the staggered first
+    derivative evaluated half a cell off its so points (grad(., shift=.5) / div(., shift=-.5))."""
+    from sympy import finite_diff_weights, Rational
+    r = so // 2
+    om = O.Model((0., 0.), (10., 10.), (9, 9), space_order=so, nbl=6,
+                 m=np.full((9, 9), 0.25, dtype=np.float32), precision="f64")
+    c2, w1 = O.fd_weights(om)
+    ref2 = finite_diff_weights(2, list(range(-r, r + 1)), 0)[2][-1]
+    assert np.allclose(c2, [float(ref2[r + k]) for k in range(r + 1)], rtol=1e-13, atol=0)
+    pts = [Rational(2 * k - 1, 2) for k in range(-r + 1, r + 1)]          # -r+1/2 .. r-1/2
+    ref1 = finite_diff_weights(1, pts, 0)[1][-1]
+    assert np.allclose(w1, [float(ref1[r + k - 1]) for k in range(1, r + 1)], rtol=1e-13, atol=0)
