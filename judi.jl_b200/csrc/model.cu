@@ -250,9 +250,9 @@ __global__ void tti_axis_kernel(const float *__restrict__ theta, const float *__
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float st, ct, sp, cp;
+    float st, ct, sp = 0.f, cp = 1.f;
     sincosf(theta[i], &st, &ct);
-    sincosf(phi[i], &sp, &cp);
+    if (phi) sincosf(phi[i], &sp, &cp);   // 2-D: no azimuth, r = (sin theta, 0, cos theta)
     rx[i] = st * cp;
     ry[i] = st * sp;
     rz[i] = ct;
@@ -385,12 +385,14 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
         affine_kernel<<<nb, 256, 0, ctx->stream>>>(M->delta.p, M->g.nalloc, 2.0f, 1.0f);
         launch_count(ctx, "affine");
         model_set_param(M, M->theta, desc->theta, dev, 0.0f, true);
-        if (M->ndim == 3) {
-            model_set_param(M, M->phi, desc->phi, dev, 0.0f, true);
+        if (M->ndim == 3) model_set_param(M, M->phi, desc->phi, dev, 0.0f, true);
+        {
             for (int d = 0; d < 3; d++) M->r3[d] = DevBuf(ctx, (size_t)M->g.nalloc, true);
-            tti_axis_kernel<<<nb, 256, 0, ctx->stream>>>(M->theta.p, M->phi.p, M->g.nalloc,
-                                                         M->r3[0].p, M->r3[1].p, M->r3[2].p);
+            tti_axis_kernel<<<nb, 256, 0, ctx->stream>>>(M->theta.p, M->ndim == 3 ? M->phi.p : nullptr,
+                                                         M->g.nalloc, M->r3[0].p, M->r3[1].p, M->r3[2].p);
             launch_count(ctx, "tti_axis");
+        }
+        if (M->ndim == 3) {
             if (!M->irho_field && M->so == 8) {
                 for (int d = 0; d < 3; d++) M->ttiABC[d] = DevBuf(ctx, (size_t)M->g.nalloc, false);
                 tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c, M->g.nalloc,

@@ -1,5 +1,5 @@
-// persist2d.cu -- 2-D isotropic acoustic (constant density) time loop as ONE persistent
-// cooperative kernel.
+// persist2d.cu -- 2-D time loops as ONE persistent cooperative kernel: isotropic acoustic with
+// constant density (acoustic2d_persist) and the flux-form physics (flux2d_persist, below).
 //
 // A 2-D grid of the reference's test/FWI sizes (481x201 points) is ~1 us of HBM time per step, so a
 // launch-per-step schedule is pure launch latency.  This kernel keeps the whole loop of one sweep
@@ -141,10 +141,226 @@ __global__ void __launch_bounds__(256) acoustic2d_persist(P2Args a)
 }
 
 // ------------------------------------------------------------------------------------------
-bool persist2d_supported(const judi_model *M, int ic)
+// The same persistent time loop for the flux-form physics in 2-D (variable density, TTI):
+// per step  receivers  ->  flux pass (P, M on the grid extended by R nodes)  -> grid barrier ->
+// divergence + update + injection + fused extras -> grid barrier.  Two barriers per step instead
+// of three launches (flux_kernel, flux_update, sparse_kernel: 12.8 us per step measured on the C2
+// grid).  Plain / save / imaging condition "as" / illumination; Born keeps the launch-per-step path.
+struct P2FluxArgs {
+    Grid g;
+    Coefs cf;
+    float *b[2][2];       // [field][buffer]; level t of field f is b[f][cur]
+    float *P[2], *Mx[2];  // flux scratch: P_x, P_z and M_x, M_z
+    int cur;
+    const float *m, *irho, *eps, *delta, *st, *ct;
+    const float *dx, *dz;
+    int t0, t1, dir;
+    const int *cellmap;
+    const int *cell_start, *ent_trace;
+    const float *ent_w, *cell_scale;
+    const float *src;
+    int nsrc;
+    int nrec;
+    const long long *coff;
+    const float *cw;
+    float *rec;
+    float *snap;          // snapshot pool: slot s of field f at snap + (s * nf + f) * slot
+    const float *usnap;
+    float *grad, *illum;
+    long long slot;
+    int t_sub;
+    float gcoef;
+    int t_base;
+    Region reg;
+};
+
+template <int R, bool TTI>
+__global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
 {
-    return M->ndim == 2 && !M->tti && !M->visco && !M->irho_field && !M->fs && ic == JUDI_IC_AS &&
+    cg::grid_group grid = cg::this_grid();
+    const Grid &g = a.g;
+    const Coefs &cf = a.cf;
+    constexpr int NF = TTI ? 2 : 1;
+    const int TX = 32, TZ = 8;
+    const int tx = threadIdx.x % TX, tz = threadIdx.x / TX;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    // flux nodes: x in [-R, nx + R), z in [-R, nz + R)
+    const int fnx = g.n[0] + 2 * R, fnz = g.n[2] + 2 * R;
+    const int ftx = (fnx + TX - 1) / TX, ftiles = ftx * ((fnz + TZ - 1) / TZ);
+    const int ntx = (g.n[0] + TX - 1) / TX, ntiles = ntx * ((g.n[2] + TZ - 1) / TZ);
+    int cur = a.cur;
+    for (int t = a.t0;; t += a.dir) {
+        const float *u1 = a.b[0][cur], *u2 = TTI ? a.b[1][cur] : nullptr;
+        // ---- receivers sample level t of the first field -------------------------------------
+        for (long long p = gtid; p < a.nrec; p += gthreads) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const long long o = a.coff[p * 4 + c];
+                if (o >= 0) acc += a.cw[p * 4 + c] * u1[o];
+            }
+            a.rec[(long long)t * a.nrec + p] = acc;
+        }
+        // ---- pass 1: rotated fluxes (FD_utils.py:24-105) or irho * grad ------------------------
+        for (int tile = blockIdx.x; tile < ftiles; tile += gridDim.x) {
+            const int x = (tile % ftx) * TX + tx - R, z = (tile / ftx) * TZ + tz - R;
+            if (x >= g.n[0] + R || z >= g.n[2] + R) continue;
+            const long long i = g.at(x, 0, z);
+            float g1x = 0.f, g1z = 0.f, g2x = 0.f, g2z = 0.f;
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                g1x += cf.wx[k] * (u1[i + k] - u1[i - (k - 1)]);
+                g1z += cf.wz[k] * (u1[i + k * g.sz] - u1[i - (k - 1) * g.sz]);
+                if (TTI) {
+                    g2x += cf.wx[k] * (u2[i + k] - u2[i - (k - 1)]);
+                    g2z += cf.wz[k] * (u2[i + k * g.sz] - u2[i - (k - 1) * g.sz]);
+                }
+            }
+            const float bb = a.irho[i];
+            if (!TTI) {
+                a.P[0][i] = bb * g1x;
+                a.P[1][i] = bb * g1z;
+            } else {
+                // closed form through the symmetry axis r = (sin theta, cos theta) (flux3d.cu)
+                const float e = a.eps[i], dl = a.delta[i], rx = a.st[i], rz = a.ct[i];
+                const float A0 = bb * dl, B0 = bb * sqrtf((e - dl) * dl), C0 = bb * (e - dl);
+                const float d1 = rx * g1x + rz * g1z, d2 = rx * g2x + rz * g2z;
+                const float sP = (bb - A0) * d1 - B0 * d2, sM = -(B0 * d1 + C0 * d2);
+                a.P[0][i] = (A0 * g1x + B0 * g2x) + sP * rx;
+                a.P[1][i] = (A0 * g1z + B0 * g2z) + sP * rz;
+                a.Mx[0][i] = (B0 * g1x + C0 * g2x) + sM * rx;
+                a.Mx[1][i] = (B0 * g1z + C0 * g2z) + sM * rz;
+            }
+        }
+        grid.sync();
+        // ---- pass 2: divergence, update, injection, fused extras -------------------------------
+        const bool fused_t = ((t - a.t_base) % a.t_sub) == 0;
+        const long long sidx = (long long)((t - a.t_base) / a.t_sub) * NF * a.slot;
+        float *snap_t = (a.snap && fused_t) ? a.snap + sidx : nullptr;
+        const float *usnap_t = (a.grad && fused_t) ? a.usnap + sidx : nullptr;
+        const float *src_row = a.src ? a.src + (long long)t * a.nsrc : nullptr;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int x = (tile % ntx) * TX + tx, z = (tile / ntx) * TZ + tz;
+            if (x >= g.n[0] || z >= g.n[2]) continue;
+            const long long i = g.at(x, 0, z);
+            const float ir = a.irho[i];
+            const float sd = cf.dt * ((a.dx[x] + 0.f) + a.dz[z]);
+            const float rden = 1.0f / (a.m[i] * ir + sd);
+            float inj = 0.f;
+            int row = -1;
+            if (a.cellmap && (row = a.cellmap[i]) >= 0) {
+                float acc = 0.f;
+                for (int e = a.cell_start[row]; e < a.cell_start[row + 1]; e++)
+                    acc += a.ent_w[e] * src_row[a.ent_trace[e]];
+                inj = acc * a.cell_scale[row];
+            }
+            float ucv[NF], delta[NF];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const float *Fx = f == 0 ? a.P[0] : a.Mx[0], *Fz = f == 0 ? a.P[1] : a.Mx[1];
+                float L = 0.f, Lz = 0.f;
+#pragma unroll
+                for (int k = 1; k <= R; k++) {
+                    L += cf.wx[k] * (Fx[i + (k - 1)] - Fx[i - k]);
+                    Lz += cf.wz[k] * (Fz[i + (k - 1) * g.sz] - Fz[i - k * g.sz]);
+                }
+                L += Lz;
+                const float *uc = a.b[f][cur];
+                float *un = a.b[f][1 - cur];
+                ucv[f] = uc[i];
+                const float d1 = ucv[f] - un[i];
+                delta[f] = (cf.dt2 * L - sd * d1) * rden;
+                // point sources drive the first field only (geom_utils.py:81)
+                const float add = f == 0 ? inj : 0.f;
+                un[i] = ((ucv[f] + d1) + delta[f]) + add;
+                delta[f] += add;     // post-injection u+ - 2u + u-
+            }
+            if ((snap_t || usnap_t || a.illum) && a.reg.has(x, 0, z)) {
+                const long long ri = a.reg.at(x, 0, z);
+                float e2 = 0.f, ic = 0.f;
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    if (snap_t) snap_t[f * a.slot + ri] = ucv[f];
+                    e2 += ucv[f] * ucv[f];
+                    if (usnap_t) ic += usnap_t[f * a.slot + ri] * delta[f];
+                }
+                if (a.illum) a.illum[ri] += cf.dt * e2;
+                if (usnap_t) a.grad[ri] -= a.gcoef * ir * ic;
+            }
+        }
+        grid.sync();
+        cur = 1 - cur;
+        if (t == a.t1) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+bool persist2d_supported(const judi_model *M, int ic, bool born)
+{
+    const bool flux = M->tti || M->irho_field;
+    if (flux && (born || M->r != 4 || (M->tti && !M->r3[0].p))) return false;   // flux form: so = 8, no Born
+    return M->ndim == 2 && !M->visco && !M->fs && ic == JUDI_IC_AS &&
            (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
+}
+
+static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
+                               const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
+                               Traces *out, const P2Fuse &fz)
+{
+    judi_ctx *ctx = M->ctx;
+    const int nsteps = (t1 - t0) * dir + 1;
+    P2FluxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = M->g; a.cf = M->cf;
+    const int nf = M->tti ? 2 : 1;
+    for (int f = 0; f < nf; f++) { a.b[f][0] = W.b[f][0].p; a.b[f][1] = W.b[f][1].p; }
+    a.P[0] = W.flux[0].p; a.P[1] = W.flux[2].p;
+    if (M->tti) { a.Mx[0] = W.flux[3].p; a.Mx[1] = W.flux[5].p; }
+    a.cur = W.cur;
+    a.m = M->m.p; a.irho = M->irho.p; a.eps = M->eps.p; a.delta = M->delta.p;
+    a.st = M->r3[0].p; a.ct = M->r3[2].p;
+    a.dx = M->damp[0].p; a.dz = M->damp[2].p;
+    a.t0 = t0; a.t1 = t1; a.dir = dir;
+    if (S_in && in && S_in->ncell > 0) {
+        a.cellmap = S_in->cellmap.p;
+        a.cell_start = S_in->cell_start.p;
+        a.ent_trace = S_in->ent_trace.p;
+        a.ent_w = S_in->ent_w.p;
+        a.cell_scale = S_in->cell_scale.p;
+        a.src = in->buf.p;
+        a.nsrc = in->np;
+    }
+    if (S_out && out && S_out->np > 0) {
+        a.nrec = S_out->np;
+        a.coff = S_out->corner_off.p;
+        a.cw = S_out->corner_w.p;
+        a.rec = out->buf.p;
+    }
+    a.snap = fz.snap; a.usnap = fz.usnap; a.grad = fz.grad; a.illum = fz.illum;
+    a.slot = fz.slot / nf;   // P2Fuse::slot counts all fields of a snapshot
+    a.t_sub = fz.t_sub > 0 ? fz.t_sub : 1; a.gcoef = fz.gcoef;
+    a.reg = fz.reg;
+    a.t_base = fz.t_base;
+    void *kern = M->tti ? (void *)flux2d_persist<4, true> : (void *)flux2d_persist<4, false>;
+    static int max_blocks[2] = {0, 0};
+    int &mb = max_blocks[M->tti ? 1 : 0];
+    if (!mb) {
+        int per_sm = 0;
+        if (M->tti) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flux2d_persist<4, true>, 256, 0));
+        else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flux2d_persist<4, false>, 256, 0));
+        mb = per_sm * ctx->num_sms;
+    }
+    const int ftiles = ((M->N[0] + 8 + 31) / 32) * ((M->N[2] + 8 + 7) / 8);
+    const int nb = std::min(ftiles, mb);
+    void *args[] = {(void *)&a};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(nb), dim3(256), args, 0, ctx->stream));
+    launch_count(ctx, "flux2d_persist");
+    if (nsteps & 1) W.swap();
+    if (ctx->timing) {
+        ctx->stencil_launches += 1;
+        ctx->stencil_points += (double)nsteps * M->N[0] * M->N[2];
+    }
 }
 
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced
@@ -157,6 +373,11 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
     judi_ctx *ctx = M->ctx;
     int nsteps = (t1 - t0) * dir + 1;
     if (nsteps <= 0) return;
+    if (M->tti || M->irho_field) {
+        JUDI_REQUIRE(WL == nullptr && out_bg == nullptr, "persistent 2-D flux kernel has no Born mode");
+        persist2d_run_flux(M, W, t0, t1, dir, S_in, in, S_out, out, fz);
+        return;
+    }
     P2Args a;
     memset(&a, 0, sizeof(a));
     a.g = M->g;

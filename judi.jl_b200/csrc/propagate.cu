@@ -490,7 +490,7 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    if (persist2d_supported(M, ic) && !sh.ext_active()) {
+    if (persist2d_supported(M, ic, true) && !sh.ext_active()) {
         P2Fuse pf;
         pf.reg = M->full;
         pf.illum = fz.illum;
@@ -658,7 +658,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     // A range of forward steps.  mode 0: no snapshots; 1: slot t/k when t % k == 0; 2: slot t-base
     // (segment recomputation).  2-D constant-density models run the whole range inside one
     // persistent kernel (persist2d.cu), everything else steps kernel by kernel.
-    const bool p2 = persist2d_supported(M, o->ic) && !sh.ext_active() && !dft;
+    const bool p2 = persist2d_supported(M, o->ic, born) && !sh.ext_active() && !dft;
     auto fwd_range = [&](int ta, int tb, int mode, int base, bool record) {
         if (tb < ta) return;
         if (p2) {

@@ -53,7 +53,7 @@ struct P2Fuse {
     float gcoef = 0;
     Region reg;
 };
-bool persist2d_supported(const judi_model *M, int ic);
+bool persist2d_supported(const judi_model *M, int ic, bool born = false);
 void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int t1, int dir,
                    const SparseSet *S_in, const Traces *in, const SparseSet *S_out, Traces *out,
                    Traces *out_bg, const P2Fuse &fz);
