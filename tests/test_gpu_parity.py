@@ -266,6 +266,28 @@ def test_device_resident_path_matches_host_path():
     assert abs(float(red[-1].item()) - 2 * float(f)) <= 1e-5 * abs(2 * float(f))
 
 
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+@pytest.mark.parametrize("n,nbl", [((23, 17, 13), 5), ((34, 9, 40), 4), ((7, 50, 21), 6), ((65, 33, 10), 9)])
+def test_odd_3d_shapes(kind, n, nbl):
+    """Tile edges of the TMA kernels: grids that are not multiples of the 64x16 / 32x16 tiles or of
+    the 4-point groups, thinner than a tile, with layers thinner than the stencil radius + 3."""
+    J, args, gm, om, src, rec, q, dt = both(kind, 3, 8, nt=90, n=n, nbl=nbl)
+    ext = np.array([(s - 1) * h for s, h in zip(n, args["spacing"])], dtype=np.float32)
+    src = np.minimum(src, ext * 0.6).astype(np.float32)
+    rec = np.minimum(rec, ext).astype(np.float32)
+    d, _ = J.forward_rec(gm, src, q, rec)
+    do, _ = O.forward_rec(om, src, q, rec)
+    assert np.linalg.norm(do) > 0 and rel_l2(d, do) < TOL_SHOT
+    dobs = (0.7 * do).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=2)
+    fo, go, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, t_sub=2)
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, go) < TOL_GRAD
+    _, gp, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=2, snapshot_region="physical")
+    crop = tuple(slice(l, m_ - r) for (l, r), m_ in zip(gm.padsizes, g.shape))
+    assert np.array_equal(gp[crop], g[crop])
+
+
 def test_registered_host_arrays_give_identical_results():
     """judi_host_register: page-locking the caller's arrays changes the copy path, not the result."""
     J, args, gm, om, src, rec, q, dt = both("iso", 3, 8)
