@@ -376,6 +376,12 @@ def _full_size(kind):
         dm = (1 / v ** 2 - 1 / v0 ** 2).astype(np.float32)
         gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40,
                      m=(1 / v0 ** 2).astype(np.float32), dm=dm, dt=1.921)
+    elif kind == "rho":
+        n = (301, 301, 201)           # C5-size grid with a density field (Gardner)
+        v = velocity(n)
+        dm = (0.02 * (v > 2.0) / v ** 2).astype(np.float32)
+        gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32),
+                     rho=(0.31 * (v * 1000.) ** 0.25).astype(np.float32), dm=dm)
     else:
         n = (301, 301, 201)           # C5 grid: padded 381 x 381 x 281
         v = velocity(n)
@@ -396,7 +402,7 @@ def _full_size(kind):
     return J, gm, src, rec, q, dt, dm
 
 
-@pytest.mark.parametrize("kind", ["iso", "tti"])
+@pytest.mark.parametrize("kind", ["iso", "tti", "rho"])
 def test_full_size_adjoint_and_linearity(kind):
     """test_adjoint.jl:28-54 / test_linearity.jl:17 on the BASELINE grids (C3 and C5), short time
     axis: <F q, y> = <q, F' y>, dt <J dm, y> = <dm, J' y>, F(a q) = a F(q), and the gradient is
