@@ -25,6 +25,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// predicated arrive: no divergent branch around the single arriving lane
+__device__ __forceinline__ void mbar_arrive_if(uint64_t *bar, bool pred)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "setp.ne.b32 P1, %1, 0;\n"
+        "@P1 mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"((int)pred)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                     // the first three planes of a chunk are never a flux plane: release them now
                     if (j < R - 1) {
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&emptyU[s_in]);
+                        mbar_arrive_if(&emptyU[s_in], lane == 0);
                     }
                     continue;
                 }
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                 }
                 // plane zf and its parameters are dead for this warp
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
+                mbar_arrive_if(&emptyU[s_c], lane == 0); mbar_arrive_if(&emptyC[cslot], lane == 0);
                 if (++cslot == NC) { cslot = 0; cpar ^= 1; }
                 // the flux buffer of this parity was read by the D warps two planes ago
                 if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                 const float4 up1 = *(const float4 *)pt, up2 = *(const float4 *)(pt + PSLOT);
                 const float4 m4 = *(const float4 *)(pt + 2 * PSLOT);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyP[pslot]);
+                mbar_arrive_if(&emptyP[pslot], lane == 0);
                 if (++pslot == NP) { pslot = 0; ppar ^= 1; }
                 // delta = (dt^2 H - sd (u - u-)) / (m irho + sd),  u+ = (u + (u - u-)) + delta
                 const f2 dzv = pk1(dz_s);

@@ -96,7 +96,7 @@ __device__ __forceinline__ void varc_dx(const float *wx, const float4 &l, const 
     o1 = pk(o[2], o[3]);
 }
 
-template <int FUSE>
+template <int FUSE, bool ROTD>
 __global__ void __launch_bounds__(varc::NTHREADS, 2)
     varc3d_tma(const __grid_constant__ VarcMaps tm, const VarcArgs a)
 {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             q[NQ - 1] = *(const float4 *)(ringU + j * USLOT + su);
             if (j < R - 1) {   // the first three planes of a chunk are never a flux plane
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyU[j]);
+                mbar_arrive_if(&emptyU[j], lane == 0);
             }
         }
         int cslot = 0, cpar = 0;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                 }
             }
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
+            mbar_arrive_if(&emptyU[s_c], lane == 0); mbar_arrive_if(&emptyC[cslot], lane == 0);
             if (++cslot == NC) { cslot = 0; cpar ^= 1; }
             // the flux buffer of this parity was read by the D warps two planes ago
             if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                 }
             }
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&emptyU[s_c]); mbar_arrive(&emptyC[cslot]); }
+            mbar_arrive_if(&emptyU[s_c], lane == 0); mbar_arrive_if(&emptyC[cslot], lane == 0);
             if (++cslot == NC) { cslot = 0; cpar ^= 1; }
             if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
             if (need_xy && wr) *(float4 *)(fb + sf) = cat4(mul2(lo2(c4), g0), mul2(hi2(c4), g1));
@@ -327,7 +327,15 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
     for (int k = 0; k < NQ; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int pslot = 0, ppar = 0;
 
-    for (int j = FIRST; j < total; j++) {
+    // accumulator slot of output plane zf + d, d = -3 .. 4: rotated at compile time (loop unrolled by
+    // 8) or shifted by 7 register moves per plane
+#define AS(d) (ROTD ? ((ph + (d) + 2 * NQ) % NQ) : ((d) + R - 1))
+    constexpr int UNR = ROTD ? NQ : 1;
+    for (int j0 = FIRST; j0 < total; j0 += UNR) {
+#pragma unroll
+      for (int ph = 0; ph < UNR; ph++) {
+        const int j = j0 + ph;
+        if (ROTD && j >= total) break;
         const int zf = z0 - (3 * R - 1) + j;
         const bool need_xy = zf >= z0 && zf < z1;
         const bool out = j >= WARM;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                 if (k == 1) { ly0 = mul2s(cf.wy[1], d0); ly1 = mul2s(cf.wy[1], d1); }
                 else { ly0 = fma2s(cf.wy[k], d0, ly0); ly1 = fma2s(cf.wy[k], d1, ly1); }
             }
-            acc[R - 1] = cat4(add2(lo2(acc[R - 1]), add2(lx0, ly0)), add2(hi2(acc[R - 1]), add2(lx1, ly1)));
+            acc[AS(0)] = cat4(add2(lo2(acc[AS(0)]), add2(lx0, ly0)), add2(hi2(acc[AS(0)]), add2(lx1, ly1)));
         }
         // ---- z part: D-_z out[z] = sum_k wz[k] (F[z+k-1] - F[z-k]), scattered from F_z of plane zf ---
         const float *fz_ = fb + FX + FY + st;
@@ -386,22 +394,22 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             const float4 Fz = *(const float4 *)fz_;
 #pragma unroll
             for (int k = 1; k <= R; k++) {
-                float4 &ap = acc[R - k];      // plane zf-k+1
+                float4 &ap = acc[AS(1 - k)];  // plane zf-k+1
                 ap = cat4(fma2s(cf.wz[k], lo2(Fz), lo2(ap)), fma2s(cf.wz[k], hi2(Fz), hi2(ap)));
-                float4 &bp = acc[R - 1 + k];  // plane zf+k
+                float4 &bp = acc[AS(k)];      // plane zf+k
                 if (k == R) bp = cat4(mul2s(-cf.wz[k], lo2(Fz)), mul2s(-cf.wz[k], hi2(Fz)));
                 else bp = cat4(fma2s(-cf.wz[k], lo2(Fz), lo2(bp)), fma2s(-cf.wz[k], hi2(Fz), hi2(bp)));
             }
         }
         if (out) {
             const float4 uc = *(const float4 *)(fz_ + PSLOT);
-            const float4 H = acc[0];
+            const float4 H = acc[AS(1 - R)];
             mbar_wait(&fullP[pslot], (uint32_t)ppar);
             const float *pt = ringP + pslot * 3 * PSLOT + st;
             const float4 up4 = *(const float4 *)pt, m4 = *(const float4 *)(pt + PSLOT);
             const float4 ir4 = *(const float4 *)(pt + 2 * PSLOT);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyP[pslot]);
+            mbar_arrive_if(&emptyP[pslot], lane == 0);
             if (++pslot == NP) { pslot = 0; ppar ^= 1; }
             // delta = (dt^2 L - sd (u - u-)) / (m irho + sd),  u+ = (u + (u - u-)) + delta
             const f2 dzv = pk1(dz_s);
@@ -473,9 +481,13 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
         }
         // this flux buffer may be overwritten by the F warps two planes from now
         if (j + 2 < total) named_bar_arrive(3 + (j & 1), NSYNC);
+        if (!ROTD) {
 #pragma unroll
-        for (int k = 0; k < NQ - 1; k++) acc[k] = acc[k + 1];
+            for (int k = 0; k < NQ - 1; k++) acc[k] = acc[k + 1];
+        }
+      }
     }
+#undef AS
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -501,11 +513,13 @@ template <int FUSE>
 static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
 {
     judi_ctx *ctx = M->ctx;
-    auto kern = varc3d_tma<FUSE>;
-    static bool configured = false;
-    if (!configured) {
+    // option varc_fused: 1 shifted accumulators, 2 accumulators rotated at compile time
+    const int var = ctx->opt_varc_fused == 2 ? 1 : 0;
+    void (*kern)(const VarcMaps, const VarcArgs) = var ? varc3d_tma<FUSE, true> : varc3d_tma<FUSE, false>;
+    static bool configured[2] = {false, false};
+    if (!configured[var]) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)varc::SMEM));
-        configured = true;
+        configured[var] = true;
     }
     Wavefield *W = lin ? s.lin : s.scratch;
     VarcMaps tm;

@@ -21,7 +21,7 @@ xr, yr = np.meshgrid(np.linspace(3500., 4000., 11), np.linspace(3500., 4000., 11
 rec = np.stack([xr.ravel(), yr.ravel(), np.full(xr.size, 50.)], axis=1).astype(np.float32)
 dobs = np.zeros((nt, rec.shape[0]), dtype=np.float32)
 ref = None
-for fused in (0, 1):
+for fused in (0, 1, 2):
     for zc in (zcs if fused else [0]):
         ctx.set_option("varc_fused", fused); ctx.set_option("zchunks", zc)
         d1 = J.forward_rec(gm, src, q, rec)[0]
