@@ -191,6 +191,28 @@ int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const f
                    const judi_jopts *opts, judi_misfit_fn misfit, void *user, float *f_out,
                    float *grad_out, float *illum_u, float *illum_v, int flags);
 
+/* One source experiment of a multi-shot objective: geometry, wavelet and observed data (or residual)
+ * as the per-shot arguments of judi_J_adjoint. */
+typedef struct {
+    int nsrc;
+    const float *src_coords; /* nsrc x ndim */
+    const float *wavelet;    /* nt x nsrc, time fastest */
+    int nt;
+    int nrec;
+    const float *rec_coords; /* nrec x ndim */
+    const float *recin;      /* nt x nrec, time fastest */
+} judi_shot;
+
+/* Objective and gradient of `nshots` source experiments on this context's GPU, summed in HBM:
+ * the per-worker part of multi_src_fg! (src/TimeModeling/Modeling/propagation.jl:93-107) with the
+ * local reduction of distributed.jl:6-22 -- one call per worker instead of one per shot, one copy
+ * of the gradient back instead of one per shot.  f_out / grad_out (padded grid) receive the sums;
+ * with JUDI_OUT_ON_DEVICE they are device pointers, so the caller can all-reduce over GPUs (NCCL)
+ * before anything crosses PCIe; JUDI_GRAD_ACCUMULATE adds to their current content.  The shots'
+ * own pointers are host pointers unless JUDI_DATA_ON_DEVICE is set. */
+int judi_fg_multishot(judi_model *model, int nshots, const judi_shot *shots, const judi_jopts *opts,
+                      judi_misfit_fn misfit, void *user, float *f_out, float *grad_out, int flags);
+
 /* forward_no_rec (interface.py:83-111; python_interface.jl:56): the full wavefield history,
  * u_out is nt x padded grid (time slowest).  TTI returns the first field like the reference. */
 int judi_forward_no_rec(judi_model *model, int fw, int nsrc, const float *src_coords,

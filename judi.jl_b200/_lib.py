@@ -41,6 +41,12 @@ class JudiJopts(ctypes.Structure):
                 ("nfreq", ctypes.c_int), ("dft_sub", ctypes.c_int), ("freq_list", ctypes.c_void_p)]
 
 
+class JudiShot(ctypes.Structure):
+    _fields_ = [("nsrc", ctypes.c_int), ("src_coords", ctypes.c_void_p), ("wavelet", ctypes.c_void_p),
+                ("nt", ctypes.c_int), ("nrec", ctypes.c_int), ("rec_coords", ctypes.c_void_p),
+                ("recin", ctypes.c_void_p)]
+
+
 MISFIT_FN = ctypes.CFUNCTYPE(ctypes.c_float, c_float_p, c_float_p, c_float_p, ctypes.c_int,
                              ctypes.c_int, ctypes.c_void_p)
 
@@ -86,6 +92,9 @@ SIGNATURES = {
                                       ctypes.c_void_p, ctypes.POINTER(JudiJopts), ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_fg_multishot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(JudiShot),
+                                         ctypes.POINTER(JudiJopts), ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "judi_forward_no_rec": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),

@@ -63,6 +63,17 @@ void judi_ctx_destroy(judi_ctx *ctx)
     delete ctx;
 }
 
+__global__ void axpy_kernel(float *__restrict__ y, const float *__restrict__ x, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+static void axpy_device(judi_ctx *ctx, float *y, const float *x, size_t n)
+{
+    axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(y, x, n);
+    launch_count(ctx, "axpy");
+}
+
 int judi_ctx_synchronize(judi_ctx *ctx)
 {
     API_BEGIN
@@ -337,6 +348,56 @@ int judi_J_adjoint(judi_model *model, int nsrc, const float *src_coords, const f
     if (!o.illum) { illum_u = nullptr; illum_v = nullptr; }
     run_J_adjoint(model, nsrc, src_coords, wavelet, nt, nrec, rec_coords, recin, &o, misfit, user,
                   f_out, grad_out, illum_u, illum_v, flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_fg_multishot(judi_model *model, int nshots, const judi_shot *shots, const judi_jopts *opts,
+                      judi_misfit_fn misfit, void *user, float *f_out, float *grad_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && opts && grad_out && f_out && (shots || nshots == 0), "null argument");
+    JUDI_REQUIRE(nshots >= 0, "negative shot count");
+    judi_ctx *ctx = model->ctx;
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t ng = (size_t)model->N[0] * model->N[1] * model->N[2];
+    const bool out_dev = (flags & JUDI_OUT_ON_DEVICE) || (flags & JUDI_DATA_ON_DEVICE);
+    const bool accumulate = flags & JUDI_GRAD_ACCUMULATE;
+    judi_jopts o = *opts;
+    o.illum = 0;
+    // the accumulator of this call: the caller's device buffers, or a temporary one in HBM
+    DevBuf acc;
+    float *g_dev = grad_out, *f_dev = f_out;
+    if (!out_dev) {
+        acc = DevBuf(ctx, ng + 1, true);
+        g_dev = acc.p;
+        f_dev = acc.p + ng;
+    } else if (!accumulate) {
+        CUDA_CHECK(cudaMemsetAsync(g_dev, 0, ng * sizeof(float), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(f_dev, 0, sizeof(float), ctx->stream));
+    }
+    const int shot_flags = (flags & JUDI_DATA_ON_DEVICE) | JUDI_OUT_ON_DEVICE | JUDI_GRAD_ACCUMULATE;
+    for (int i = 0; i < nshots; i++) {
+        const judi_shot &sh = shots[i];
+        JUDI_REQUIRE(sh.wavelet && sh.rec_coords && sh.recin, "shot with a null pointer");
+        JUDI_REQUIRE((sh.src_coords && sh.nsrc > 0) || o.ws, "shot without a source");
+        run_J_adjoint(model, sh.nsrc, sh.src_coords, sh.wavelet, sh.nt, sh.nrec, sh.rec_coords, sh.recin,
+                      &o, misfit, user, f_dev, g_dev, nullptr, nullptr, shot_flags);
+    }
+    if (!out_dev) {
+        std::vector<float> fsum(1);
+        CUDA_CHECK(cudaMemcpyAsync(fsum.data(), f_dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (accumulate) {
+            // add to the caller's host arrays: stage through a second device buffer
+            DevBuf prev(ctx, ng, false);
+            CUDA_CHECK(cudaMemcpyAsync(prev.p, grad_out, ng * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            axpy_device(ctx, g_dev, prev.p, ng);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(grad_out, g_dev, ng * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        *f_out = accumulate ? *f_out + fsum[0] : fsum[0];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
     API_END(1)
 }

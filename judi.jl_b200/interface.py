@@ -235,6 +235,41 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     return g, Iu, Iv
 
 
+def fg_multishot(model, shots, grad_out, f_out, is_residual=False, checkpointing=False,
+                 n_checkpoints=None, t_sub=1, ic="as", born_fwd=False, nlind=False,
+                 snapshot_region="padded", accumulate=False, f0=None):
+    """Objective and gradient of several source experiments in ONE library call, summed in HBM
+    (`judi_fg_multishot`: the per-worker part of multi_src_fg!, propagation.jl:93-107).
+
+    `shots`: sequence of (src_coords, wavelet, rec_coords, dobs) with host arrays; `grad_out`
+    (padded grid) and `f_out` (one float) are device tensors that receive the sums."""
+    model.set_f0(f0)
+    assert is_device_tensor(grad_out) and is_device_tensor(f_out)
+    o = L.JudiJopts()
+    o.is_residual = int(bool(is_residual))
+    o.checkpointing = int(bool(checkpointing))
+    o.n_checkpoints = int(n_checkpoints) if n_checkpoints else 0
+    o.t_sub = int(t_sub)
+    o.ic = L.IC_CODES[ic]
+    o.born_fwd = int(bool(born_fwd))
+    o.nlind = int(bool(nlind))
+    o.snapshot_region = L.SNAP_PHYSICAL if snapshot_region == "physical" else L.SNAP_PADDED
+    arr = (L.JudiShot * len(shots))()
+    keep = []
+    for k, (src_coords, wavelet, rec_coords, recin) in enumerate(shots):
+        sc, rc = _coords(src_coords, model.dim), _coords(rec_coords, model.dim)
+        q, nt, nsrc = _traces(wavelet)
+        d, ntd, nrec = _traces(recin)
+        assert ntd == nt and nrec == rc.shape[0], "data shape does not match geometry / wavelet"
+        keep += [sc, rc, q, d]
+        arr[k].nsrc, arr[k].src_coords, arr[k].wavelet = nsrc, sc.ctypes.data, q.ctypes.data
+        arr[k].nt, arr[k].nrec, arr[k].rec_coords, arr[k].recin = nt, nrec, rc.ctypes.data, d.ctypes.data
+    flags = L.OUT_ON_DEVICE | (L.GRAD_ACCUMULATE if accumulate else 0)
+    L.check(L.lib().judi_fg_multishot(model.h, len(shots), arr, ctypes.byref(o), None, None,
+                                      f_out.data_ptr(), grad_out.data_ptr(), flags))
+    return f_out, grad_out
+
+
 def _weights(model, w):
     """Extended-source weights on the padded grid (python_interface.jl:129 zero-pads them)."""
     if is_device_tensor(w):

@@ -128,6 +128,7 @@ def multi_src_fg(model, shots, dm=None, lin=False, nlind=False, misfit=None, red
 
 
 _hbm_acc = {}
+_MULTISHOT_OPTIONS = {"is_residual", "checkpointing", "n_checkpoints", "t_sub", "ic", "snapshot_region", "f0"}
 
 
 def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_padding, options):
@@ -151,11 +152,17 @@ def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_paddin
     nccl = reduce and dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
     with torch.cuda.stream(stream):
         red.zero_()
-        for i in mine:
-            sc, q, rc, dobs = shots[i]
-            interface.J_adjoint(model, sc, q, rc, dobs, return_obj=True, born_fwd=lin, nlind=nlind,
-                                misfit=misfit, grad_out=red[:n], f_out=red[n:], accumulate=True,
-                                **options)
+        if misfit is None and not (set(options) - _MULTISHOT_OPTIONS) and mine:
+            # one library call for all shots of this rank (judi_fg_multishot)
+            stream.synchronize()
+            interface.fg_multishot(model, [shots[i] for i in mine], red[:n], red[n:], born_fwd=lin,
+                                   nlind=nlind, accumulate=True, **options)
+        else:
+            for i in mine:
+                sc, q, rc, dobs = shots[i]
+                interface.J_adjoint(model, sc, q, rc, dobs, return_obj=True, born_fwd=lin, nlind=nlind,
+                                    misfit=misfit, grad_out=red[:n], f_out=red[n:], accumulate=True,
+                                    **options)
         if nccl:
             dist.all_reduce(red, op=dist.ReduceOp.SUM)
         if nccl or not (reduce and dist is not None and dist.get_world_size() > 1):

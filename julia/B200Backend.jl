@@ -144,6 +144,24 @@ function b200_J_adjoint(h, src_coords, qIn, rec_coords, dIn, options::JUDIOption
     return illum ? (f[], g, Iu, Iv) : (f[], g)
 end
 
+# (f, g) summed over several shots of this worker in ONE call (multi_src_fg!, propagation.jl:93-107)
+struct JudiShot            # judi_shot
+    nsrc::Cint; src_coords::Ptr{Cfloat}; wavelet::Ptr{Cfloat}; nt::Cint
+    nrec::Cint; rec_coords::Ptr{Cfloat}; recin::Ptr{Cfloat}
+end
+function b200_fg_multishot(h, shots::Vector{<:NTuple{4,Array{Float32}}}, options::JUDIOptions, n;
+                           born_fwd=false, nlind=false)
+    g = pin!(zeros(Float32, padded_shape(h, length(n)))); f = Ref{Cfloat}(0)
+    o = JudiJopts(false, options.optimal_checkpointing, 0, options.subsampling_factor, IC[options.IC],
+                  born_fwd, nlind, false, options.sum_padding ? 0 : 1, Ptr{Cfloat}(C_NULL), 0, 1, Ptr{Cfloat}(C_NULL))
+    cs = [JudiShot(size(sc, 1), pointer(sc), pointer(q), size(q, 1), size(rc, 1), pointer(rc), pointer(d))
+          for (sc, q, rc, d) in shots]
+    GC.@preserve shots cs check(ccall((:judi_fg_multishot, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{JudiShot}, Ref{JudiJopts}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cfloat}, Ptr{Cfloat}, Cint),
+                h, length(cs), cs, o, C_NULL, C_NULL, f, g, 0))
+    return f[], g
+end
+
 # ---- extended and wavefield sources (python_interface.jl:58-81, 124-198 -> interface.py:50-204, 244-276)
 # `weights` arrive on the physical grid; JUDI zero-pads them (python_interface.jl:129)
 function b200_forward_rec_w(h, wpad::Array{Float32}, qIn, rec_coords, fw::Bool)

@@ -288,6 +288,51 @@ def test_odd_3d_shapes(kind, n, nbl):
     assert np.array_equal(gp[crop], g[crop])
 
 
+def test_fg_multishot_equals_the_sum_of_single_shots():
+    """judi_fg_multishot (the per-worker part of multi_src_fg!, propagation.jl:93-107): host
+    pointers in, host sums out, with and without accumulation; and the device-accumulator mode
+    through objectives.fwi_objective."""
+    import ctypes
+    from judi_jl_b200 import _lib as L
+    from judi_jl_b200.interface import _coords, _traces
+    J, args, gm, om, src, rec, q, dt = both("iso", 2, 8)
+    shots, fsum, gsum = [], 0.0, 0.0
+    for k in range(3):
+        s_k = (src + np.float32([[50. * (k - 1), 0.]])).astype(np.float32)
+        d_k, _ = J.forward_rec(gm, s_k, q, rec)
+        dobs = (0.8 * d_k).astype(np.float32)
+        shots.append((s_k, q, rec, dobs))
+        f_k, g_k, _, _ = J.J_adjoint(gm, s_k, q, rec, dobs, return_obj=True, t_sub=2)
+        fsum += float(f_k)
+        gsum = gsum + g_k.astype(np.float64)
+    arr = (L.JudiShot * 3)()
+    keep = []
+    for k, (sc, w, rc, d) in enumerate(shots):
+        sc, rc = _coords(sc, 2), _coords(rc, 2)
+        w, nt, nsrc = _traces(w)
+        d, _, nrec = _traces(d)
+        keep += [sc, rc, w, d]
+        arr[k].nsrc, arr[k].src_coords, arr[k].wavelet = nsrc, sc.ctypes.data, w.ctypes.data
+        arr[k].nt, arr[k].nrec, arr[k].rec_coords, arr[k].recin = nt, nrec, rc.ctypes.data, d.ctypes.data
+    o = L.JudiJopts()
+    o.t_sub = 2
+    g = np.zeros(gm.shape_pml, dtype=np.float32, order="F")
+    f = ctypes.c_float(0.)
+    L.check(L.lib().judi_fg_multishot(gm.h, 3, arr, ctypes.byref(o), None, None,
+                                      ctypes.addressof(f), g.ctypes.data, 0))
+    assert abs(f.value - fsum) <= 1e-5 * abs(fsum)
+    assert rel_l2(g, gsum) < 1e-5
+    # accumulate on top of the previous result: twice the sums
+    L.check(L.lib().judi_fg_multishot(gm.h, 3, arr, ctypes.byref(o), None, None,
+                                      ctypes.addressof(f), g.ctypes.data, L.GRAD_ACCUMULATE))
+    assert abs(f.value - 2 * fsum) <= 1e-5 * abs(fsum)
+    assert rel_l2(g, 2 * gsum) < 1e-5
+    fo, go = J.objectives.fwi_objective(gm, shots, t_sub=2)
+    crop = tuple(slice(l, n_ - r) for (l, r), n_ in zip(gm.padsizes, g.shape))
+    assert abs(float(fo) - fsum) <= 1e-5 * abs(fsum)
+    assert rel_l2(go, gsum[crop]) < 1e-5
+
+
 def test_registered_host_arrays_give_identical_results():
     """judi_host_register: page-locking the caller's arrays changes the copy path, not the result."""
     J, args, gm, om, src, rec, q, dt = both("iso", 3, 8)
