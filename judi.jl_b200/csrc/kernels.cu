@@ -367,6 +367,8 @@ struct ViscoArgs {
     float qext_scale;
     const float *dd_in, *dm;
     float *dd_out;
+    int born_ic;             // imaging condition of the Born source (linearised pass)
+    const float *ub;         // isic / fwi Born source: background pressure, level t
     Fuse f;
 };
 
@@ -418,7 +420,16 @@ __global__ void __launch_bounds__(256) visco_update(ViscoArgs a)
         a.r[i] = rn;
         S2 = (1.0f + tt) * L2 - cf.dt2 * (b * rn);
     } else S2 = L2;
-    if (a.dd_in) S2 += -a.dm[i] * b * a.dd_in[i];          // Born source, already scaled by dt^2
+    if (a.dd_in) {
+        // dt^2 * lin_src of the background pressure (sensitivity.py:174-209)
+        if (a.born_ic == JUDI_IC_AS) S2 += -a.dm[i] * b * a.dd_in[i];
+        else {
+            const float ics = a.born_ic == JUDI_IC_FWI ? -1.f : 1.f;
+            const float lw = a.irho ? lap_weighted2<NDIM, R>(g, cf, a.ub, a.dm, a.irho, i)
+                                    : b * lap_weighted<NDIM, R>(g, cf, a.ub, a.dm, i);
+            S2 += -(a.dm[i] * b * a.m[i] * a.dd_in[i] - ics * cf.dt2 * lw);
+        }
+    }
     if (a.qext) S2 += a.qext_scale * a.qext[i];
     const float pc = a.p[i];
     const float d1 = pc - a.pp[i];
@@ -431,7 +442,15 @@ __global__ void __launch_bounds__(256) visco_update(ViscoArgs a)
         if (fz.wrec) fz.wrec[ri] += fz.wrec_scale * pc;
         if (fz.snap[0]) fz.snap[0][ri] = pc;
         if (fz.illum) fz.illum[ri] += cf.dt * pc * pc;
-        if (fz.grad) fz.grad[ri] -= fz.gcoef * b * fz.usnap[0][ri] * delta;
+        if (fz.grad) {
+            const float us = fz.usnap[0][ri];
+            if (fz.ic == JUDI_IC_AS) fz.grad[ri] -= fz.gcoef * b * us * delta;
+            else {
+                const float ics = fz.ic == JUDI_IC_FWI ? -1.f : 1.f;
+                const float ig = inner_grad_snap<NDIM, R>(g, cf, fz.reg, fz.usnap[0], a.p, x, y, z);
+                fz.grad[ri] -= fz.gcoef * b * (us * delta * a.m[i] + ics * cf.dt2 * ig);
+            }
+        }
     }
 }
 
@@ -585,7 +604,7 @@ static void step_flux(const judi_model *M, const StepArgs &s)
 template <int NDIM, int R>
 static void visco_one(const judi_model *M, Wavefield *W, const float *p, float *pp, float *r, int adj,
                       const float *dd_in, float *dd_out, const Fuse &fuse, const float *qext,
-                      float qext_scale)
+                      float qext_scale, int born_ic = JUDI_IC_AS, const float *ub = nullptr)
 {
     judi_ctx *ctx = M->ctx;
     ViscoArgs a;
@@ -598,6 +617,7 @@ static void visco_one(const judi_model *M, Wavefield *W, const float *p, float *
     a.adj = adj;
     a.qext = qext; a.qext_scale = qext_scale;
     a.dd_in = dd_in; a.dm = M->dm.p; a.dd_out = dd_out;
+    a.born_ic = born_ic; a.ub = ub;
     a.f = fuse;
     dim3 blk(64, 4, 1), grd;
     if (NDIM == 3) grd = dim3((M->N[0] + 63) / 64, (M->N[1] + 3) / 4, M->N[2]);
@@ -629,17 +649,17 @@ static void step_visco(const judi_model *M, const StepArgs &s)
 {
     Wavefield *W = s.scratch;
     JUDI_REQUIRE(W != nullptr && W->rmem.p, "visco-acoustic scratch not bound");
-    JUDI_REQUIRE(!s.f.grad || s.f.ic == JUDI_IC_AS, "visco-acoustic gradients use the 'as' imaging condition");
     if (!s.born) {
         visco_one<NDIM, R>(M, W, s.u[0], s.up[0], W->rmem.p, s.adj, nullptr, nullptr, s.f, s.qext, s.qext_scale);
         return;
     }
-    JUDI_REQUIRE(s.born_ic == JUDI_IC_AS, "visco-acoustic Born modelling uses the 'as' source");
     JUDI_REQUIRE(s.lin && s.lin->rmem.p && W->dd[0].p, "visco-acoustic Born scratch not bound");
     visco_one<NDIM, R>(M, W, s.u[0], s.up[0], W->rmem.p, 0, nullptr, W->dd[0].p, s.f, s.qext, s.qext_scale);
     Fuse none;
     memset(&none, 0, sizeof(none));
-    visco_one<NDIM, R>(M, W, s.ul[0], s.ulp[0], s.lin->rmem.p, 0, W->dd[0].p, nullptr, none, nullptr, 0.f);
+    // the background pass wrote level t+1 over level t-1: s.u[0] still holds level t
+    visco_one<NDIM, R>(M, W, s.ul[0], s.ulp[0], s.lin->rmem.p, 0, W->dd[0].p, nullptr, none, nullptr, 0.f,
+                       s.born_ic, s.u[0]);
 }
 
 template <int NDIM>

@@ -135,7 +135,8 @@ def test_fwi_objective_and_options(kind, ndim):
     assert flc == fl and np.array_equal(glc, gl)
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("rho", 2), ("tti", 2), ("rho", 3), ("tti", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("rho", 2), ("tti", 2), ("rho", 3), ("tti", 3),
+                                       ("visco", 2), ("viscoc", 3)])
 @pytest.mark.parametrize("ic", ["isic", "fwi"])
 def test_isic_fwi_imaging_conditions(kind, ndim, ic):
     """test_all_options.jl:13-53 runs isic / fwi on the variable-density and the TTI model

@@ -67,11 +67,12 @@ def test_free_surface_dot_test_reference_tolerance(kind):
     assert abs(eF) < tol and abs(eJ) < tol
 
 
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti", "visco"])
 @pytest.mark.parametrize("ic", ["isic", "fwi"])
-def test_imaging_conditions_are_adjoint_pairs(ic):
-    """test_all_options.jl:13-53 (rtol 5e-2 there): Born source and imaging condition of the
-    same name are exact discrete adjoints of each other."""
-    _, model, src, rec, q, dt = setup("iso", 2, 8)
+def test_imaging_conditions_are_adjoint_pairs(ic, kind):
+    """test_all_options.jl:13-53 (rtol 5e-2 there; run on the density, TTI and visco-acoustic
+    models too): Born source and imaging condition of the same name are exact discrete adjoints."""
+    _, model, src, rec, q, dt = setup(kind, 2, 8)
     _, eJ = dots(model, src, rec, q, dt, ic=ic)
     assert abs(eJ) < 1e-11
 
