@@ -58,7 +58,8 @@ def test_oracle_dft_gradient_approaches_time_domain_gradient():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,ndim,dft_sub", [("iso", 2, None), ("iso", 2, 4), ("iso", 3, 2),
-                                               ("tti", 2, 3), ("tti", 3, None), ("rho", 3, 4)])
+                                               ("tti", 2, 3), ("tti", 3, None), ("rho", 3, 4),
+                                               ("rho", 2, 2), ("visco", 2, None), ("viscoc", 3, 3)])
 def test_dft_gradient_parity(kind, ndim, dft_sub):
     import judi_jl_b200 as J
     args, om, src, rec, q, dt = _setup(kind, ndim, with_dm=True)

@@ -353,7 +353,7 @@ def test_registered_host_arrays_give_identical_results():
     J.host_unregister(q_pin)                    # neither is unregistering twice
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3), ("rho", 2)])
 def test_free_surface_parity(kind, ndim):
     """Options(free_surface=true): no layer above z=0 (models.py:174-176,269-272) and the mirror
     u(-k) = -u(k-1), u(0) = 0 after every update (fields_exprs.py:106-137)."""
@@ -374,7 +374,7 @@ def test_free_surface_parity(kind, ndim):
     assert rel_l2(g, go) < TOL_GRAD
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2), ("tti", 3)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2), ("tti", 3), ("visco", 2)])
 def test_extended_and_wavefield_sources(kind, ndim):
     """The remaining entry points of src/pysource/interface.py: forward_rec_w (:50), adjoint_w
     (:174), born_rec_w (:244), J_adjoint(ws=...) and forward_wf_src / _norec (:114, :145);
