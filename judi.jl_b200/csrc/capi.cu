@@ -156,6 +156,7 @@ int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value)
     else if (k == "born_fused") ctx->opt_born_fused = value;
     else if (k == "tti_fused") ctx->opt_tti_fused = value;
     else if (k == "varc_fused") ctx->opt_varc_fused = value;
+    else if (k == "persist_blocks") ctx->opt_persist_blocks = value;
     else if (k == "flux_slab") ctx->opt_flux_slab = value;
     else if (k == "flux_minb") ctx->opt_flux_minb = value;
     else if (k == "flux_block") ctx->opt_flux_block = value;

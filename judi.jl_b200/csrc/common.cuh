@@ -147,6 +147,7 @@ struct judi_ctx {
     int opt_born_fused = 1;     // 3-D Born: one fused launch (0: two launches through HBM)
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
+    int opt_persist_blocks = 0; // ... with at most this many CTAs (0: as many tiles as fit)
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
 

@@ -352,7 +352,8 @@ static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1
         mb = per_sm * ctx->num_sms;
     }
     const int ftiles = ((M->N[0] + 8 + 31) / 32) * ((M->N[2] + 8 + 7) / 8);
-    const int nb = std::min(ftiles, mb);
+    int nb = std::min(ftiles, mb);
+    if (ctx->opt_persist_blocks > 0) nb = std::min(nb, ctx->opt_persist_blocks);
     void *args[] = {(void *)&a};
     CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(nb), dim3(256), args, 0, ctx->stream));
     launch_count(ctx, "flux2d_persist");
@@ -421,6 +422,7 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
         }
         int ntiles = ((M->N[0] + 31) / 32) * ((M->N[2] + 7) / 8);
         int nb = std::min(ntiles, max_blocks);
+        if (ctx->opt_persist_blocks > 0) nb = std::min(nb, ctx->opt_persist_blocks);
         void *args[] = {(void *)&a};
         CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(nb), dim3(256), args, 0,
                                                ctx->stream));

@@ -11,7 +11,8 @@ v = np.clip(1.5 + (z / 3000.) * 3.0 + 0.4 * np.sin(2 * np.pi * x / 5000.) * (z /
 v[:, :21] = 1.5
 src = np.array([[5000., 50.]], dtype=np.float32)
 rec = np.stack([np.linspace(0, 10000., 401), np.full(401, 50.)], axis=1).astype(np.float32)
-for kind in sys.argv[1:] or ["iso", "rho", "tti"]:
+blocks = [int(b) for b in os.environ.get("PERSIST_BLOCKS", "0").split(",")]
+for kind in [a for a in sys.argv[1:]] or ["iso", "rho", "tti"]:
     kw = {}
     if kind == "rho": kw["rho"] = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
     if kind == "tti":
@@ -21,11 +22,13 @@ for kind in sys.argv[1:] or ["iso", "rho", "tti"]:
     dt = float(gm.critical_dt); nt = int(3000. / dt) + 1
     q = ricker(nt, dt, 0.008)
     d0, _ = J.forward_rec(gm, src, q, rec); dobs = (0.9 * d0).astype(np.float32)
-    J.J_adjoint(gm, src, q, rec, dobs, return_obj=True); ctx.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3): J.forward_rec(gm, src, q, rec)
-    ctx.synchronize(); t1 = time.perf_counter()
-    for _ in range(3): J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
-    ctx.synchronize(); t2 = time.perf_counter()
-    print("%s 2-D 481x201 nt=%d: forward %.2f ms  fwi gradient %.2f ms  (%.2f us per step pair)" % (
-        kind, nt, 1e3 * (t1 - t0) / 3, 1e3 * (t2 - t1) / 3, 1e6 * (t2 - t1) / 3 / nt), flush=True)
+    for nb in blocks:
+        ctx.set_option("persist_blocks", nb)
+        J.J_adjoint(gm, src, q, rec, dobs, return_obj=True); ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3): J.forward_rec(gm, src, q, rec)
+        ctx.synchronize(); t1 = time.perf_counter()
+        for _ in range(3): J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+        ctx.synchronize(); t2 = time.perf_counter()
+        print("%s 2-D 481x201 nt=%d blocks<=%d: forward %.2f ms  fwi gradient %.2f ms  (%.2f us per step pair)" % (
+            kind, nt, nb, 1e3 * (t1 - t0) / 3, 1e3 * (t2 - t1) / 3, 1e6 * (t2 - t1) / 3 / nt), flush=True)
