@@ -378,7 +378,9 @@ int judi_fg_multishot(judi_model *model, int nshots, const judi_shot *shots, con
         CUDA_CHECK(cudaMemsetAsync(f_dev, 0, sizeof(float), ctx->stream));
     }
     const int shot_flags = (flags & JUDI_DATA_ON_DEVICE) | JUDI_OUT_ON_DEVICE | JUDI_GRAD_ACCUMULATE;
-    for (int i = 0; i < nshots; i++) {
+    // small 2-D shots: all of them in lockstep inside one cooperative launch per sweep
+    const bool batched = !misfit && run_fg_batch2d(model, nshots, shots, &o, f_dev, g_dev, shot_flags);
+    for (int i = 0; i < nshots && !batched; i++) {
         const judi_shot &sh = shots[i];
         JUDI_REQUIRE(sh.wavelet && sh.rec_coords && sh.recin, "shot with a null pointer");
         JUDI_REQUIRE((sh.src_coords && sh.nsrc > 0) || o.ws, "shot without a source");

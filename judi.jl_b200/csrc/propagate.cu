@@ -512,6 +512,118 @@ static int num_slots(int nt, int t_sub)
     return t_sub == 1 ? nt : (int)std::ceil((double)(nt + t_sub) / (double)t_sub);
 }
 
+// ---- several 2-D shots in lockstep (judi_fg_multishot fast path) -----------------------------------
+// Small 2-D shots are bound by the grid barrier of the persistent kernel, not by bandwidth: all
+// shots of the call (same model, same time axis) step together inside one cooperative launch per
+// sweep, one barrier per time step for all of them.  Covers the plain FWI gradient of a constant-
+// density acoustic model (imaging condition "as", stored snapshots, on-device L2 misfit); anything
+// else returns false and the caller loops over run_J_adjoint.
+bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const judi_jopts *o,
+                    float *f_dev, float *g_dev, int flags)
+{
+    judi_ctx *ctx = M->ctx;
+    if (nshots < 2 || !persist2d_batch_supported(M, o->ic) || o->checkpointing || o->nfreq > 0 ||
+        o->born_fwd || o->ws || o->illum || !ctx->opt_persist2d)
+        return false;
+    const int nt = shots[0].nt;
+    if (nt < 3) return false;
+    for (int s = 0; s < nshots; s++)
+        if (shots[s].nt != nt || shots[s].nsrc <= 0 || shots[s].nrec <= 0) return false;
+    const bool dev = flags & JUDI_DATA_ON_DEVICE;
+    const int k = std::max(1, o->t_sub);
+    const Region reg = o->snapshot_region == JUDI_SNAP_PHYSICAL ? M->phys : M->full;
+    const int nslots = num_slots(nt, k);
+    // how many shots fit at once: snapshots + two wavefields + gradient per shot
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    unsigned long long reserved = 0, used = 0;
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    const double avail = 0.8 * ((double)free_b + (double)(reserved - used));
+    const double per_shot = 4.0 * ((double)nslots * reg.slot + 4.0 * M->g.nalloc + reg.slot) +
+                            12.0 * (double)nt * shots[0].nrec;
+    const int chunk = (int)std::max(1.0, std::min((double)std::min(nshots, 32), avail / per_shot));
+    if (chunk < 2) return false;
+    double fsum = 0.0;
+    PhaseClock pc(ctx);
+    for (int s0 = 0; s0 < nshots; s0 += chunk) {
+        const int n = std::min(chunk, nshots - s0);
+        std::vector<SparseSet> S_src((size_t)n), S_rec((size_t)n);
+        std::vector<Traces> q((size_t)n), obs((size_t)n), rec((size_t)n);
+        std::vector<Wavefield> W((size_t)n), V((size_t)n);
+        std::vector<DevBuf> snaps((size_t)n), grad((size_t)n);
+        std::vector<P2Fuse> pf((size_t)n);
+        std::vector<Wavefield *> pW((size_t)n), pV((size_t)n);
+        std::vector<const SparseSet *> pSs((size_t)n), pSr((size_t)n);
+        std::vector<const Traces *> pq((size_t)n), pres((size_t)n);
+        std::vector<Traces *> prec((size_t)n);
+        for (int s = 0; s < n; s++) {
+            const judi_shot &sh = shots[s0 + s];
+            sparse_build(M, sh.nsrc, sh.src_coords, S_src[s]);
+            sparse_build(M, sh.nrec, sh.rec_coords, S_rec[s]);
+            q[s].load(ctx, sh.wavelet, nt, sh.nsrc, dev);
+            obs[s].load(ctx, sh.recin, nt, sh.nrec, dev);
+            rec[s].alloc(ctx, nt, sh.nrec);
+            W[s].init(M, false);
+            snaps[s] = DevBuf(ctx, (size_t)nslots * reg.slot, false);
+            grad[s] = DevBuf(ctx, (size_t)reg.slot, true);
+            pf[s].reg = reg;
+            pf[s].snap = snaps[s].p;
+            pf[s].slot = (long long)reg.slot;
+            pf[s].t_sub = k;
+            pf[s].t_base = 0;
+            pW[s] = &W[s]; pSs[s] = &S_src[s]; pSr[s] = &S_rec[s]; pq[s] = &q[s]; prec[s] = &rec[s];
+        }
+        pc.mark("batch setup (sparse, traces, alloc)");
+        // forward sweeps with snapshots
+        persist2d_run_batch(M, n, pW.data(), 1, nt - 2, 1, pSs.data(), pq.data(), pSr.data(), prec.data(),
+                            pf.data());
+        pc.mark("batch forward sweep");
+        // misfit and residual (sensitivity.py:236-276), one small launch per shot
+        DevArr<double> fd(ctx, (size_t)n, true);
+        for (int s = 0; s < n; s++) {
+            const long long nn = (long long)nt * shots[s0 + s].nrec;
+            const int nb = (int)std::max<long long>(1, std::min<long long>((nn + 255) / 256, 1024));
+            loss_kernel<<<nb, 256, 0, ctx->stream>>>(nn, rec[s].buf.p, nullptr, obs[s].buf.p,
+                                                     o->is_residual ? 1 : 0, fd.p + s, 0.5f * M->dt);
+            launch_count(ctx, "loss");
+        }
+        // adjoint sweeps with the imaging condition
+        for (int s = 0; s < n; s++) {
+            V[s].init(M, false);
+            W[s] = Wavefield();           // the forward fields are no longer needed
+            pV[s] = &V[s];
+            pres[s] = &rec[s];
+            pf[s] = P2Fuse();
+            pf[s].reg = reg;
+            pf[s].grad = grad[s].p;
+            pf[s].usnap = snaps[s].p;
+            pf[s].slot = (long long)reg.slot;
+            pf[s].t_sub = k;
+            pf[s].t_base = 0;
+            pf[s].gcoef = (float)((double)k / (double)M->dt);
+        }
+        pc.mark("batch misfit + adjoint setup");
+        persist2d_run_batch(M, n, pV.data(), nt - 2, 1, -1, pSr.data(), pres.data(), nullptr, nullptr,
+                            pf.data());
+        pc.mark("batch adjoint sweep");
+        for (int s = 0; s < n; s++) region_output(M, reg, grad[s].p, g_dev, true, true);
+        std::vector<double> fh((size_t)n);
+        CUDA_CHECK(cudaMemcpyAsync(fh.data(), fd.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (int s = 0; s < n; s++) fsum += fh[s];
+        pc.mark("batch outputs");
+    }
+    float prev = 0.f;
+    CUDA_CHECK(cudaMemcpyAsync(&prev, f_dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    prev += (float)fsum;
+    CUDA_CHECK(cudaMemcpyAsync(f_dev, &prev, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->flush_timing();
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return true;
+}
+
 void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float *wavelet, int nt,
                    int nrec, const float *rec_coords, const float *recin, const judi_jopts *o,
                    judi_misfit_fn misfit, void *user, float *f_out, float *grad_out,

@@ -26,6 +26,7 @@ m0 = np.asfortranarray((1 / v0 ** 2).astype(np.float32))
 def run():
     gm = J.Model((0., 0.), d, n, m=m0, dt=dt, **kw)
     return J.objectives.fwi_objective(gm, shots)
+ctx.set_option("persist_blocks", int(os.environ.get("PERSIST_BLOCKS", "0")))
 run(); ctx.synchronize()
 reps = 5
 t0 = time.perf_counter()
@@ -35,6 +36,9 @@ wall = (time.perf_counter() - t0) / reps
 N = 481 * 201
 print("C2 fwi_objective, 16 shots, nt=%d: %.1f ms per gradient (%.2f ms per shot, %.1f shots/s, %.1f Gpt/s)  f=%.4e |g|=%.4e" % (
     nt, 1e3 * wall, 1e3 * wall / 16, 16 / wall, 16 * 2 * nt * N / wall / 1e9, float(f), float(np.linalg.norm(g))), flush=True)
+ctx.set_option("profile", 1)
+run()
+ctx.set_option("profile", 0)
 # per-phase wall times of one shot
 gm = J.Model((0., 0.), d, n, m=m0, dt=dt, **kw)
 ctx.set_option("profile", 1)
