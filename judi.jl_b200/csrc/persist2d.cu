@@ -201,7 +201,7 @@ struct P2FluxArgs {
 };
 
 template <int R, bool TTI>
-__global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
+__device__ __forceinline__ void flux2d_body(const P2FluxArgs &a, const int lb, const int nb)
 {
     cg::grid_group grid = cg::this_grid();
     const Grid &g = a.g;
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
     constexpr int NF = TTI ? 2 : 1;
     const int TX = 32, TZ = 8;
     const int tx = threadIdx.x % TX, tz = threadIdx.x / TX;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)lb * blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)nb * blockDim.x;
     // flux nodes: x in [-R, nx + R), z in [-R, nz + R)
     const int fnx = g.n[0] + 2 * R, fnz = g.n[2] + 2 * R;
     const int ftx = (fnx + TX - 1) / TX, ftiles = ftx * ((fnz + TZ - 1) / TZ);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
             a.rec[(long long)t * a.nrec + p] = acc;
         }
         // ---- pass 1: rotated fluxes (FD_utils.py:24-105) or irho * grad ------------------------
-        for (int tile = blockIdx.x; tile < ftiles; tile += gridDim.x) {
+        for (int tile = lb; tile < ftiles; tile += nb) {
             const int x = (tile % ftx) * TX + tx - R, z = (tile / ftx) * TZ + tz - R;
             if (x >= g.n[0] + R || z >= g.n[2] + R) continue;
             const long long i = g.at(x, 0, z);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
         float *snap_t = (a.snap && fused_t) ? a.snap + sidx : nullptr;
         const float *usnap_t = (a.grad && fused_t) ? a.usnap + sidx : nullptr;
         const float *src_row = a.src ? a.src + (long long)t * a.nsrc : nullptr;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = lb; tile < ntiles; tile += nb) {
             const int x = (tile % ntx) * TX + tx, z = (tile / ntx) * TZ + tz;
             if (x >= g.n[0] || z >= g.n[2]) continue;
             const long long i = g.at(x, 0, z);
@@ -321,6 +321,26 @@ __global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
     }
 }
 
+template <int R, bool TTI>
+__global__ void __launch_bounds__(256) flux2d_persist(P2FluxArgs a)
+{
+    flux2d_body<R, TTI>(a, blockIdx.x, gridDim.x);
+}
+
+// several shots in lockstep (see acoustic2d_persist_batch)
+template <int R, bool TTI>
+__global__ void __launch_bounds__(256) flux2d_persist_batch(const P2FluxArgs *__restrict__ batch, int per_shot)
+{
+    __shared__ P2FluxArgs sa;
+    {
+        const int *src = (const int *)(batch + blockIdx.x / per_shot);
+        int *dst = (int *)&sa;
+        for (int i = threadIdx.x; i < (int)(sizeof(P2FluxArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    flux2d_body<R, TTI>(sa, blockIdx.x % per_shot, per_shot);
+}
+
 // ------------------------------------------------------------------------------------------
 bool persist2d_supported(const judi_model *M, int ic, bool born)
 {
@@ -330,13 +350,10 @@ bool persist2d_supported(const judi_model *M, int ic, bool born)
            (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
 }
 
-static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
-                               const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
-                               Traces *out, const P2Fuse &fz)
+static void p2flux_fill(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
+                        const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
+                        Traces *out, const P2Fuse &fz, P2FluxArgs &a)
 {
-    judi_ctx *ctx = M->ctx;
-    const int nsteps = (t1 - t0) * dir + 1;
-    P2FluxArgs a;
     memset(&a, 0, sizeof(a));
     a.g = M->g; a.cf = M->cf;
     const int nf = M->tti ? 2 : 1;
@@ -368,6 +385,16 @@ static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1
     a.t_sub = fz.t_sub > 0 ? fz.t_sub : 1; a.gcoef = fz.gcoef;
     a.reg = fz.reg;
     a.t_base = fz.t_base;
+}
+
+static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
+                               const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
+                               Traces *out, const P2Fuse &fz)
+{
+    judi_ctx *ctx = M->ctx;
+    const int nsteps = (t1 - t0) * dir + 1;
+    P2FluxArgs a;
+    p2flux_fill(M, W, t0, t1, dir, S_in, in, S_out, out, fz, a);
     void *kern = M->tti ? (void *)flux2d_persist<4, true> : (void *)flux2d_persist<4, false>;
     static int max_blocks[2] = {0, 0};
     int &mb = max_blocks[M->tti ? 1 : 0];
@@ -476,7 +503,7 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
 // ---- several shots in one cooperative launch -------------------------------------------------------
 bool persist2d_batch_supported(const judi_model *M, int ic)
 {
-    return persist2d_supported(M, ic, false) && !M->tti && !M->irho_field;
+    return persist2d_supported(M, ic, false);
 }
 
 // One sweep (t0, t0+dir, ..., t1) of `n` shots of the same model in lockstep.  W[s] is advanced.
@@ -487,6 +514,39 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     judi_ctx *ctx = M->ctx;
     const int nsteps = (t1 - t0) * dir + 1;
     if (nsteps <= 0 || n <= 0) return;
+    if (M->tti || M->irho_field) {
+        std::vector<P2FluxArgs> fargs((size_t)n);
+        for (int s = 0; s < n; s++)
+            p2flux_fill(M, *W[s], t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,
+                        S_out ? S_out[s] : nullptr, out ? out[s] : nullptr, fz[s], fargs[(size_t)s]);
+        DevArr<P2FluxArgs> dfa(ctx, (size_t)n, false);
+        dfa.upload(fargs);
+        void *kern = M->tti ? (void *)flux2d_persist_batch<4, true> : (void *)flux2d_persist_batch<4, false>;
+        static int max_blocks[2] = {0, 0};
+        int &mb = max_blocks[M->tti ? 1 : 0];
+        if (!mb) {
+            int per_sm = 0;
+            if (M->tti) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flux2d_persist_batch<4, true>, 256, 0));
+            else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flux2d_persist_batch<4, false>, 256, 0));
+            mb = per_sm * ctx->num_sms;
+        }
+        const int ftiles = ((M->N[0] + 8 + 31) / 32) * ((M->N[2] + 8 + 7) / 8);
+        int cap = mb;
+        if (ctx->opt_persist_blocks > 0) cap = std::min(cap, ctx->opt_persist_blocks);
+        int per_shot = std::max(1, std::min(ftiles, cap / n));
+        const P2FluxArgs *dp = dfa.p;
+        void *kargs[] = {(void *)&dp, (void *)&per_shot};
+        CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(per_shot * n), dim3(256), kargs, 0, ctx->stream));
+        launch_count(ctx, "flux2d_persist_batch");
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (nsteps & 1)
+            for (int s = 0; s < n; s++) W[s]->swap();
+        if (ctx->timing) {
+            ctx->stencil_launches += 1;
+            ctx->stencil_points += (double)n * nsteps * M->N[0] * M->N[2];
+        }
+        return;
+    }
     std::vector<P2Args> args((size_t)n);
     for (int s = 0; s < n; s++)
         p2_fill(M, *W[s], nullptr, t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,

@@ -533,14 +533,16 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
     const int k = std::max(1, o->t_sub);
     const Region reg = o->snapshot_region == JUDI_SNAP_PHYSICAL ? M->phys : M->full;
     const int nslots = num_slots(nt, k);
-    // how many shots fit at once: snapshots + two wavefields + gradient per shot
+    const int nf = M->tti ? 2 : 1;
+    const size_t slot_floats = (size_t)reg.slot * nf;
+    // how many shots fit at once: snapshots + wavefields (+ flux scratch) + gradient per shot
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     unsigned long long reserved = 0, used = 0;
     cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
     cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
     const double avail = 0.8 * ((double)free_b + (double)(reserved - used));
-    const double per_shot = 4.0 * ((double)nslots * reg.slot + 4.0 * M->g.nalloc + reg.slot) +
+    const double per_shot = 4.0 * ((double)nslots * slot_floats + (4.0 * nf + 12.0) * M->g.nalloc + reg.slot) +
                             12.0 * (double)nt * shots[0].nrec;
     const int chunk = (int)std::max(1.0, std::min((double)std::min(nshots, 32), avail / per_shot));
     if (chunk < 2) return false;
@@ -565,11 +567,11 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
             obs[s].load(ctx, sh.recin, nt, sh.nrec, dev);
             rec[s].alloc(ctx, nt, sh.nrec);
             W[s].init(M, false);
-            snaps[s] = DevBuf(ctx, (size_t)nslots * reg.slot, false);
+            snaps[s] = DevBuf(ctx, (size_t)nslots * slot_floats, false);
             grad[s] = DevBuf(ctx, (size_t)reg.slot, true);
             pf[s].reg = reg;
             pf[s].snap = snaps[s].p;
-            pf[s].slot = (long long)reg.slot;
+            pf[s].slot = (long long)slot_floats;
             pf[s].t_sub = k;
             pf[s].t_base = 0;
             pW[s] = &W[s]; pSs[s] = &S_src[s]; pSr[s] = &S_rec[s]; pq[s] = &q[s]; prec[s] = &rec[s];
@@ -598,7 +600,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
             pf[s].reg = reg;
             pf[s].grad = grad[s].p;
             pf[s].usnap = snaps[s].p;
-            pf[s].slot = (long long)reg.slot;
+            pf[s].slot = (long long)slot_floats;
             pf[s].t_sub = k;
             pf[s].t_base = 0;
             pf[s].gcoef = (float)((double)k / (double)M->dt);

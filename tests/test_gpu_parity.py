@@ -289,14 +289,15 @@ def test_odd_3d_shapes(kind, n, nbl):
     assert np.array_equal(gp[crop], g[crop])
 
 
-def test_fg_multishot_equals_the_sum_of_single_shots():
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+def test_fg_multishot_equals_the_sum_of_single_shots(kind):
     """judi_fg_multishot (the per-worker part of multi_src_fg!, propagation.jl:93-107): host
     pointers in, host sums out, with and without accumulation; and the device-accumulator mode
     through objectives.fwi_objective."""
     import ctypes
     from judi_jl_b200 import _lib as L
     from judi_jl_b200.interface import _coords, _traces
-    J, args, gm, om, src, rec, q, dt = both("iso", 2, 8)
+    J, args, gm, om, src, rec, q, dt = both(kind, 2, 8)
     shots, fsum, gsum = [], 0.0, 0.0
     for k in range(3):
         s_k = (src + np.float32([[50. * (k - 1), 0.]])).astype(np.float32)

@@ -13,6 +13,12 @@ v = np.clip(1.5 + (z / 3000.) * 3.0 + 0.4 * np.sin(2 * np.pi * x / 5000.) * (z /
 v[:, :21] = 1.5
 v0 = gaussian_filter1d(v, sigma=10, axis=1, mode="nearest").astype(np.float32); v0[:, :21] = 1.5
 kw = dict(space_order=8, nbl=40)
+kind = os.environ.get("KIND", "iso")
+if kind == "rho":
+    kw["rho"] = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
+if kind == "tti":
+    kw.update(epsilon=(0.2 * (v - 1.5) / 4).astype(np.float32), delta=(0.1 * (v - 1.5) / 4).astype(np.float32),
+              theta=(np.pi / 6 * (v - 1.5) / 4).astype(np.float32))
 mt = J.Model((0., 0.), d, n, m=(1 / v ** 2).astype(np.float32), **kw)
 dt = float(mt.critical_dt); nt = int(3000. / dt) + 1
 q = ricker(nt, dt, 0.008)
@@ -34,6 +40,7 @@ for _ in range(reps): f, g = run()
 ctx.synchronize()
 wall = (time.perf_counter() - t0) / reps
 N = 481 * 201
+print("C2 (%s) fwi_objective, 16 shots" % kind)
 print("C2 fwi_objective, 16 shots, nt=%d: %.1f ms per gradient (%.2f ms per shot, %.1f shots/s, %.1f Gpt/s)  f=%.4e |g|=%.4e" % (
     nt, 1e3 * wall, 1e3 * wall / 16, 16 / wall, 16 * 2 * nt * N / wall / 1e9, float(f), float(np.linalg.norm(g))), flush=True)
 ctx.set_option("profile", 1)
