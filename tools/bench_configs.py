@@ -33,6 +33,19 @@ def c2_2d():
     N = np.prod(gm.shape_pml)
     rep("C2 2D fwi shot 481x201 nt=%d" % nt, wall_ms=wall * 1e3, stencil_ms=ms, launches=nl, us_per_step=wall * 1e6 / (2 * nt), gpts=2 * nt * N / wall / 1e9, shots_per_s=1 / wall)
 
+def c3_forward(n=(401, 401, 201), nt=1042):
+    v = velocity(n)
+    gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=np.asfortranarray((1 / v ** 2).astype(np.float32)), dt=1.921)
+    q = ricker(nt, 1.921, 0.008)
+    src = np.array([[5000., 5000., 50.]], dtype=np.float32)
+    xr, yr = np.meshgrid(np.linspace(0., 10000., 101), np.linspace(0., 10000., 101), indexing="ij")
+    rec = np.stack([xr.ravel(), yr.ravel(), np.full(xr.size, 50.)], axis=1).astype(np.float32)
+    N = float(np.prod(gm.shape_pml))
+    wall, ms, nl, pts, out = timed(lambda: J.forward_rec(gm, src, q, rec), reps=2)
+    rep("C3 3D forward shot nt=%d (10201 rec)" % nt, wall_ms=wall * 1e3, ms_per_step=wall * 1e3 / (nt - 2),
+        gpts=(nt - 2) * N / wall / 1e9, shots_per_s=1 / wall, norm=float(np.linalg.norm(out[0])))
+
+
 def c4_born(n=(401, 401, 201), nt=120):
     v = velocity(n); v0 = smooth_model(v)
     dm = (1 / v ** 2 - 1 / v0 ** 2).astype(np.float32)
@@ -71,8 +84,9 @@ def c5_tti(n=(301, 301, 201), nt=60):
     rep("C5 3D TTI fwi gradient shot nt=%d" % nt, wall_ms=wall * 1e3, ms_per_step_pair=wall * 1e3 / (nt - 2), f=float(out[0]))
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c2", "c4", "c5"]
+    which = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
     if "c2" in which: c2_2d()
+    if "c3" in which: c3_forward()
     if "c4" in which: c4_born()
     if "c5" in which: c5_tti()
     os.makedirs("gpurun_out", exist_ok=True)
