@@ -509,12 +509,14 @@ bool persist2d_batch_supported(const judi_model *M, int ic)
 // One sweep (t0, t0+dir, ..., t1) of `n` shots of the same model in lockstep.  W[s] is advanced.
 void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0, int t1, int dir,
                          const SparseSet *const *S_in, const Traces *const *in,
-                         const SparseSet *const *S_out, Traces *const *out, const P2Fuse *fz)
+                         const SparseSet *const *S_out, Traces *const *out, const P2Fuse *fz,
+                         Wavefield *const *WL, Traces *const *out_bg)
 {
     judi_ctx *ctx = M->ctx;
     const int nsteps = (t1 - t0) * dir + 1;
     if (nsteps <= 0 || n <= 0) return;
     if (M->tti || M->irho_field) {
+        JUDI_REQUIRE(WL == nullptr, "persistent 2-D flux kernel has no Born mode");
         std::vector<P2FluxArgs> fargs((size_t)n);
         for (int s = 0; s < n; s++)
             p2flux_fill(M, *W[s], t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,
@@ -549,8 +551,9 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     }
     std::vector<P2Args> args((size_t)n);
     for (int s = 0; s < n; s++)
-        p2_fill(M, *W[s], nullptr, t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,
-                S_out ? S_out[s] : nullptr, out ? out[s] : nullptr, nullptr, fz[s], args[(size_t)s]);
+        p2_fill(M, *W[s], WL ? WL[s] : nullptr, t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,
+                S_out ? S_out[s] : nullptr, out ? out[s] : nullptr, out_bg ? out_bg[s] : nullptr, fz[s],
+                args[(size_t)s]);
     DevArr<P2Args> dargs(ctx, (size_t)n, false);
     dargs.upload(args);
     auto launch = [&](auto rtag) {
@@ -579,7 +582,10 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dargs is freed on return
     if (nsteps & 1)
-        for (int s = 0; s < n; s++) W[s]->swap();
+        for (int s = 0; s < n; s++) {
+            W[s]->swap();
+            if (WL) WL[s]->swap();
+        }
     if (ctx->timing) {
         ctx->stencil_launches += 1;
         ctx->stencil_points += (double)n * nsteps * M->N[0] * M->N[2];

@@ -523,8 +523,12 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
 {
     judi_ctx *ctx = M->ctx;
     if (nshots < 2 || !persist2d_batch_supported(M, o->ic) || o->checkpointing || o->nfreq > 0 ||
-        o->born_fwd || o->ws || o->illum || !ctx->opt_persist2d)
+        o->ws || o->illum || !ctx->opt_persist2d)
         return false;
+    // lsrtm_objective: Born forward sweeps (constant-density kernel only)
+    const bool born = o->born_fwd && M->has_dm;
+    if (born && (M->tti || M->irho_field)) return false;
+    if (o->nlind && !o->born_fwd) return false;
     const int nt = shots[0].nt;
     if (nt < 3) return false;
     for (int s = 0; s < nshots; s++)
@@ -551,8 +555,10 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
     for (int s0 = 0; s0 < nshots; s0 += chunk) {
         const int n = std::min(chunk, nshots - s0);
         std::vector<SparseSet> S_src((size_t)n), S_rec((size_t)n);
-        std::vector<Traces> q((size_t)n), obs((size_t)n), rec((size_t)n);
-        std::vector<Wavefield> W((size_t)n), V((size_t)n);
+        std::vector<Traces> q((size_t)n), obs((size_t)n), rec((size_t)n), recnl((size_t)n);
+        std::vector<Wavefield> W((size_t)n), V((size_t)n), WLs((size_t)n);
+        std::vector<Wavefield *> pWL((size_t)n);
+        std::vector<Traces *> pnl((size_t)n);
         std::vector<DevBuf> snaps((size_t)n), grad((size_t)n);
         std::vector<P2Fuse> pf((size_t)n);
         std::vector<Wavefield *> pW((size_t)n), pV((size_t)n);
@@ -567,6 +573,12 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
             obs[s].load(ctx, sh.recin, nt, sh.nrec, dev);
             rec[s].alloc(ctx, nt, sh.nrec);
             W[s].init(M, false);
+            if (born) {
+                WLs[s].init(M, false);
+                if (o->nlind) recnl[s].alloc(ctx, nt, sh.nrec);
+            }
+            pWL[s] = &WLs[s];
+            pnl[s] = &recnl[s];
             snaps[s] = DevBuf(ctx, (size_t)nslots * slot_floats, false);
             grad[s] = DevBuf(ctx, (size_t)reg.slot, true);
             pf[s].reg = reg;
@@ -579,14 +591,15 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
         pc.mark("batch setup (sparse, traces, alloc)");
         // forward sweeps with snapshots
         persist2d_run_batch(M, n, pW.data(), 1, nt - 2, 1, pSs.data(), pq.data(), pSr.data(), prec.data(),
-                            pf.data());
+                            pf.data(), born ? pWL.data() : nullptr, (born && o->nlind) ? pnl.data() : nullptr);
         pc.mark("batch forward sweep");
         // misfit and residual (sensitivity.py:236-276), one small launch per shot
         DevArr<double> fd(ctx, (size_t)n, true);
         for (int s = 0; s < n; s++) {
             const long long nn = (long long)nt * shots[s0 + s].nrec;
             const int nb = (int)std::max<long long>(1, std::min<long long>((nn + 255) / 256, 1024));
-            loss_kernel<<<nb, 256, 0, ctx->stream>>>(nn, rec[s].buf.p, nullptr, obs[s].buf.p,
+            loss_kernel<<<nb, 256, 0, ctx->stream>>>(nn, rec[s].buf.p,
+                                                     (born && o->nlind) ? recnl[s].buf.p : nullptr, obs[s].buf.p,
                                                      o->is_residual ? 1 : 0, fd.p + s, 0.5f * M->dt);
             launch_count(ctx, "loss");
         }
@@ -594,6 +607,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
         for (int s = 0; s < n; s++) {
             V[s].init(M, false);
             W[s] = Wavefield();           // the forward fields are no longer needed
+            WLs[s] = Wavefield();
             pV[s] = &V[s];
             pres[s] = &rec[s];
             pf[s] = P2Fuse();

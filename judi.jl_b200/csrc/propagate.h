@@ -61,7 +61,8 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
 bool persist2d_batch_supported(const judi_model *M, int ic);
 void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0, int t1, int dir,
                          const SparseSet *const *S_in, const Traces *const *in,
-                         const SparseSet *const *S_out, Traces *const *out, const P2Fuse *fz);
+                         const SparseSet *const *S_out, Traces *const *out, const P2Fuse *fz,
+                         Wavefield *const *WL = nullptr, Traces *const *out_bg = nullptr);
 // judi_fg_multishot fast path: all shots of a 2-D constant-density model in lockstep; false if the
 // combination is not covered (the caller then loops over run_J_adjoint)
 bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const judi_jopts *o,

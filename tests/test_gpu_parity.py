@@ -333,6 +333,15 @@ def test_fg_multishot_equals_the_sum_of_single_shots(kind):
     crop = tuple(slice(l, n_ - r) for (l, r), n_ in zip(gm.padsizes, g.shape))
     assert abs(float(fo) - fsum) <= 1e-5 * abs(fsum)
     assert rel_l2(go, gsum[crop]) < 1e-5
+    # lsrtm_objective (born_fwd, nlind) through the same entry point
+    fl, gl = 0.0, 0.0
+    for (s_k, w, rc, dobs) in shots:
+        f_k, g_k, _, _ = J.J_adjoint(gm, s_k, w, rc, dobs, return_obj=True, born_fwd=True, nlind=True)
+        fl += float(f_k)
+        gl = gl + g_k.astype(np.float64)
+    flo, glo = J.objectives.lsrtm_objective(gm, shots, args["dm"], nlind=True)
+    assert abs(float(flo) - fl) <= 1e-5 * abs(fl)
+    assert rel_l2(glo, gl[crop]) < 1e-5
 
 
 def test_registered_host_arrays_give_identical_results():
