@@ -292,7 +292,6 @@ void model_set_visco(judi_model *M, const judi_param *qp, float f0, int on_devic
 {
     judi_ctx *ctx = M->ctx;
     JUDI_REQUIRE(!M->tti, "a model cannot be TTI and visco-acoustic");
-    JUDI_REQUIRE(!M->fs, "visco-acoustic propagation with a free surface is not implemented");
     JUDI_REQUIRE(f0 > 0.f, "f0 must be positive");
     if (qp && qp->kind != JUDI_PARAM_NONE) model_set_param(M, M->qp, *qp, on_device, 1.0f, true);
     JUDI_REQUIRE(M->qp.p != nullptr, "visco-acoustic model without qp");

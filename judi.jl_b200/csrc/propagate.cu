@@ -325,7 +325,7 @@ void Shot::step_plain(Wavefield &W, int t, const Fuse *fuse, const SparseSet *S_
     stencil_step(M, s);
     sparse_step(M, S_in, in ? in->row(t) : nullptr, W.other(0), corr, S_out, W.level(0),
                 out ? out->row(t) : nullptr, nullptr, nullptr, nullptr);
-    if (M->fs)
+    if (M->fs && !M->visco)   // SLS_2nd_order carries no mirror equations (kernels.py:141)
         for (int f = 0; f < W.nf; f++) free_surface(M, W.other(f));
     W.swap();
 }
@@ -349,7 +349,7 @@ void Shot::step_born(Wavefield &W, Wavefield &WL, int t, int ic, const Fuse *fus
     sparse_step(M, S_src, S_src ? q->row(t) : nullptr, W.other(0), &corr, S_rec, WL.level(0),
                 recl ? recl->row(t) : nullptr, recnl ? S_rec : nullptr, W.level(0),
                 recnl ? recnl->row(t) : nullptr);
-    if (M->fs)
+    if (M->fs && !M->visco)   // SLS_2nd_order carries no mirror equations (kernels.py:141)
         for (int f = 0; f < W.nf; f++) { free_surface(M, W.other(f)); free_surface(M, WL.other(f)); }
     W.swap();
     WL.swap();

@@ -259,7 +259,9 @@ void oracle_set_ext(ogrid *g, const real *ws, const real *wt, real *wr, const re
  * placed after the injection (`extra` in operators.py:131,188,231). */
 static void apply_fs(const ogrid *g, real *u)
 {
-    if (!g->fs) return;
+    /* SLS_2nd_order returns no free-surface equations (kernels.py:141: `return [u_r, u_p], []`):
+     * a visco-acoustic model with fs only loses the layer above z = 0 */
+    if (!g->fs || g->visco) return;
     for (int x = 0; x < g->N[0]; x++)
         for (int y = 0; y < g->N[1]; y++) {
             size_t i0 = IDX(g, x, y, 0);

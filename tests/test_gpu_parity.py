@@ -363,7 +363,8 @@ def test_registered_host_arrays_give_identical_results():
     J.host_unregister(q_pin)                    # neither is unregistering twice
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3), ("rho", 2)])
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 3), ("tti", 3), ("rho", 2),
+                                       ("visco", 2)])
 def test_free_surface_parity(kind, ndim):
     """Options(free_surface=true): no layer above z=0 (models.py:174-176,269-272) and the mirror
     u(-k) = -u(k-1), u(0) = 0 after every update (fields_exprs.py:106-137)."""
