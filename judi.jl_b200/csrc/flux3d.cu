@@ -265,6 +265,224 @@ __global__ void __launch_bounds__(128, MINB) fluxdiv3d_vec(FluxDiv3Args a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Visco-acoustic SLS step in 3-D (src/pysource/kernels.py:80-141; the one-point-per-thread form
+// and the equations are in kernels.cu), four x-points per thread with 128-bit accesses.  The
+// Laplacian is either the divergence of the fluxes written by flux3d_vec (density field) or the
+// centred stencil times the constant irho.
+struct Visco3Args {
+    Grid g;
+    Coefs cf;
+    const float *p;          // level t
+    float *pp;               // level t-+1 in, level t+-1 out
+    float *r;                // memory variable
+    float *w;                // adjoint: product field written by the pre pass
+    const float *P[3];       // flux form: irho grad(p or w)
+    const float *Lin;        // constant density: field the Laplacian is taken of
+    const float *m, *irho, *tt, *ts;
+    float irho_c;
+    const float *dx, *dy, *dz;
+    int adj;
+    const float *qext;
+    float qext_scale;
+    const float *dd_in, *dm;
+    float *dd_out;
+    Fuse f;
+};
+
+__global__ void __launch_bounds__(128) visco3d_pre_adjoint_vec(Visco3Args a)
+{
+    const Grid &g = a.g;
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
+    const long long i = g.at(x, y, z);
+    float pc[4], rc[4], tt[4], ts[4], b[4], dxv[4], rn[4], w[4];
+    ld4(a.p + i, pc); ld4(a.r + i, rc); ld4(a.tt + i, tt); ld4(a.ts + i, ts); ld4(a.dx + x, dxv);
+    if (a.irho) ld4(a.irho + i, b);
+    else b[0] = b[1] = b[2] = b[3] = a.irho_c;
+    const float dyz = a.dy[y], dzv = a.dz[z];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float dl = (dxv[e] + dyz) + dzv;
+        rn[e] = (1.0f - dl) * (rc[e] - a.cf.dt * (b[e] * pc[e] + rc[e] / ts[e]));
+        w[e] = (1.0f + tt[e]) * pc[e] + (tt[e] / (b[e] * ts[e])) * rn[e];
+    }
+    // the halo of r and w stays zero: only domain points are written
+    if (x + 3 < g.n[0]) { st4(a.r + i, rn); st4(a.w + i, w); }
+    else
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (x + e < g.n[0]) { a.r[i + e] = rn[e]; a.w[i + e] = w[e]; }
+}
+
+template <int R, bool FLUX>
+__global__ void __launch_bounds__(128) visco3d_update_vec(Visco3Args a)
+{
+    constexpr int XE = ((R + 3) / 4) * 4;
+    const Grid &g = a.g;
+    const Coefs &cf = a.cf;
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= g.n[0] || y >= g.n[1] || z >= g.n[2]) return;
+    const long long i = g.at(x, y, z);
+    float b[4], L2[4];
+    if (a.irho) ld4(a.irho + i, b);
+    else b[0] = b[1] = b[2] = b[3] = a.irho_c;
+    if (FLUX) {
+        div4<R, XE>(g, cf, a.P, i, L2);
+#pragma unroll
+        for (int e = 0; e < 4; e++) L2[e] *= cf.dt2;
+    } else {
+        // same summation order as lap_at (kernels.cu): centre, z, x, y
+        const float *u = a.Lin;
+        float wv[4 + 2 * XE], c[4];
+#pragma unroll
+        for (int v = 0; v < 1 + 2 * (XE / 4); v++) ld4(u + i - XE + 4 * v, wv + 4 * v);
+#pragma unroll
+        for (int e = 0; e < 4; e++) c[e] = cf.c0 * wv[XE + e];
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            float pz[4], qz[4];
+            ld4(u + i + k * g.sz, pz); ld4(u + i - k * g.sz, qz);
+#pragma unroll
+            for (int e = 0; e < 4; e++) c[e] += cf.cz[k] * (pz[e] + qz[e]);
+        }
+#pragma unroll
+        for (int k = 1; k <= R; k++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) c[e] += cf.cx[k] * (wv[XE + e + k] + wv[XE + e - k]);
+#pragma unroll
+        for (int k = 1; k <= R; k++) {
+            float py[4], qy[4];
+            ld4(u + i + k * g.sy, py); ld4(u + i - k * g.sy, qy);
+#pragma unroll
+            for (int e = 0; e < 4; e++) c[e] += cf.cy[k] * (py[e] + qy[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) L2[e] = b[e] * c[e];
+    }
+    float mm[4], dxv[4], pc[4], po[4], pn[4], delta[4], rn[4], rc[4], tt[4], ts[4];
+    ld4(a.m + i, mm); ld4(a.dx + x, dxv); ld4(a.p + i, pc); ld4(a.pp + i, po);
+    if (!a.adj) { ld4(a.r + i, rc); ld4(a.tt + i, tt); ld4(a.ts + i, ts); }
+    float ddv[4] = {0.f, 0.f, 0.f, 0.f}, dmv[4] = {0.f, 0.f, 0.f, 0.f}, qe[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.dd_in) { ld4(a.dd_in + i, ddv); ld4(a.dm + i, dmv); }
+    if (a.qext) ld4(a.qext + i, qe);
+    const float dyz = a.dy[y], dzv = a.dz[z];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float dl = (dxv[e] + dyz) + dzv;
+        const float sd = cf.dt * dl;
+        float S2;
+        if (!a.adj) {
+            rn[e] = (1.0f - dl) * (rc[e] + ((tt[e] / ts[e]) * (L2[e] / b[e]) * cf.idt - cf.dt * (rc[e] / ts[e])));
+            S2 = (1.0f + tt[e]) * L2[e] - cf.dt2 * (b[e] * rn[e]);
+        } else S2 = L2[e];
+        if (a.dd_in) S2 += -dmv[e] * b[e] * ddv[e];
+        if (a.qext) S2 += a.qext_scale * qe[e];
+        const float d1 = pc[e] - po[e];
+        delta[e] = (S2 - sd * d1) / (mm[e] * b[e] + sd);
+        pn[e] = (pc[e] + d1) + delta[e];
+    }
+    if (x + 3 < g.n[0]) {
+        st4(a.pp + i, pn);
+        if (!a.adj) st4(a.r + i, rn);
+        if (a.dd_out) st4(a.dd_out + i, delta);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (x + e < g.n[0]) {
+                a.pp[i + e] = pn[e];
+                if (!a.adj) a.r[i + e] = rn[e];
+                if (a.dd_out) a.dd_out[i + e] = delta[e];
+            }
+    }
+    const Fuse &fz = a.f;
+    if ((fz.snap[0] || fz.grad || fz.illum || fz.wrec) && y >= fz.reg.lo[1] && y < fz.reg.hi[1] &&
+        z >= fz.reg.lo[2] && z < fz.reg.hi[2]) {
+        const long long ri = fz.reg.at(x, y, z);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (x + e < fz.reg.lo[0] || x + e >= fz.reg.hi[0]) continue;
+            if (fz.wrec) fz.wrec[ri + e] += fz.wrec_scale * pc[e];
+            if (fz.snap[0]) fz.snap[0][ri + e] = pc[e];
+            if (fz.illum) fz.illum[ri + e] += cf.dt * pc[e] * pc[e];
+            if (fz.grad) fz.grad[ri + e] -= fz.gcoef * b[e] * fz.usnap[0][ri + e] * delta[e];
+        }
+    }
+}
+
+template <int R>
+static void visco3d_one(const judi_model *M, Wavefield *W, const float *p, float *pp, float *r, int adj,
+                        const float *dd_in, float *dd_out, const Fuse &fuse, const float *qext,
+                        float qext_scale)
+{
+    constexpr int XE = ((R + 3) / 4) * 4;
+    judi_ctx *ctx = M->ctx;
+    Visco3Args a;
+    memset(&a, 0, sizeof(a));
+    a.g = M->g; a.cf = M->cf;
+    a.p = p; a.pp = pp; a.r = r; a.w = W->wtmp.p;
+    a.m = M->m.p; a.irho = M->irho_field ? M->irho.p : nullptr; a.irho_c = M->irho_c;
+    a.tt = M->vtt.p; a.ts = M->vts.p;
+    a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
+    a.adj = adj;
+    a.qext = qext; a.qext_scale = qext_scale;
+    a.dd_in = dd_in; a.dm = M->dm.p; a.dd_out = dd_out;
+    a.f = fuse;
+    const dim3 blk(32, 4, 1);
+    const dim3 grd(((M->N[0] + 3) / 4 + blk.x - 1) / blk.x, (M->N[1] + blk.y - 1) / blk.y, M->N[2]);
+    if (adj) {
+        visco3d_pre_adjoint_vec<<<grd, blk, 0, ctx->stream>>>(a);
+        launch_count(ctx, "visco3d_pre_adjoint_vec");
+    }
+    a.Lin = adj ? W->wtmp.p : p;
+    if (M->irho_field) {
+        Flux3Args fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.g = M->g; fa.cf = M->cf;
+        fa.u1 = a.Lin;
+        fa.irho = M->irho.p; fa.irho_c = M->irho_c;
+        for (int d = 0; d < 3; d++) { fa.P[d] = W->flux[d].p; a.P[d] = W->flux[d].p; }
+        fa.z0 = -R; fa.z1 = M->N[2] + R;
+        const int nxt = (M->N[0] + R + XE + 3) / 4;
+        const dim3 gf((nxt + blk.x - 1) / blk.x, (M->N[1] + 2 * R + blk.y - 1) / blk.y, M->N[2] + 2 * R);
+        flux3d_vec<R, false, true><<<gf, blk, 0, ctx->stream>>>(fa);
+        launch_count(ctx, "flux3d_vec");
+        visco3d_update_vec<R, true><<<grd, blk, 0, ctx->stream>>>(a);
+    } else visco3d_update_vec<R, false><<<grd, blk, 0, ctx->stream>>>(a);
+    launch_count(ctx, "visco3d_update_vec");
+}
+
+// One 3-D visco-acoustic step with the vectorised kernels; false if the combination is not covered
+// (isic / fwi conditions and sources, space orders without an instantiation): kernels.cu then runs it.
+bool visco3d_step(const judi_model *M, const StepArgs &s)
+{
+    Wavefield *W = s.scratch;
+    if (!M->visco || M->ndim != 3 || !W || !W->rmem.p) return false;
+    if ((s.f.grad && s.f.ic != JUDI_IC_AS) || (s.born && s.born_ic != JUDI_IC_AS)) return false;
+    if (s.born && (!s.lin || !s.lin->rmem.p || !W->dd[0].p)) return false;
+    auto run = [&](auto rtag) {
+        constexpr int R = decltype(rtag)::value;
+        if (!s.born) {
+            visco3d_one<R>(M, W, s.u[0], s.up[0], W->rmem.p, s.adj, nullptr, nullptr, s.f, s.qext, s.qext_scale);
+            return;
+        }
+        visco3d_one<R>(M, W, s.u[0], s.up[0], W->rmem.p, 0, nullptr, W->dd[0].p, s.f, s.qext, s.qext_scale);
+        Fuse none;
+        memset(&none, 0, sizeof(none));
+        visco3d_one<R>(M, W, s.ul[0], s.ulp[0], s.lin->rmem.p, 0, W->dd[0].p, nullptr, none, nullptr, 0.f);
+    };
+    switch (M->r) {
+    case 2: run(std::integral_constant<int, 2>()); return true;
+    case 4: run(std::integral_constant<int, 4>()); return true;
+    case 8: run(std::integral_constant<int, 8>()); return true;
+    default: return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 template <int R>
 static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u, float *const *up,
                        float *const *dd_out, const float *const *dd_in, const Fuse &fuse,

@@ -460,6 +460,7 @@ bool tma3d_supported(const judi_model *M);
 void tma3d_step(const judi_model *M, const StepArgs &a);
 bool tma3d_step_born(const judi_model *M, const StepArgs &a);
 bool flux3d_step(const judi_model *M, const StepArgs &s);
+bool visco3d_step(const judi_model *M, const StepArgs &s);
 bool tti3d_supported(const judi_model *M);
 void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 void tti3d_encode_coef(const judi_model *M, CUtensorMap *maps);
@@ -745,6 +746,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
              !(s.scratch && s.scratch->two_pass_only) && (tti3d_step(M, s) || varc3d_step(M, s))) { /* single pass */ }
     else if (M->ndim == 3 && ff && !M->visco && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&
              flux3d_step(M, s)) { /* vectorised */ }
+    else if (M->ndim == 3 && M->visco && ctx->opt_kernel3d == 1 && visco3d_step(M, s)) { /* vectorised */ }
     else if (M->ndim == 3) step_ndim<3>(M, s);
     else step_ndim<2>(M, s);
     if (timed) {
