@@ -337,13 +337,19 @@ def run_b200(args):
             keep_m, m0_h = pinned(m0)
             keep_q, q_h = pinned(q)
             keep_d, d_h = pinned(dobs)
+            # every model array lives in page-locked host memory (C5: the TTI parameter fields too)
+            keep_kw, kw_h = [], dict(kw)
+            for k_, v_ in kw.items():
+                if isinstance(v_, np.ndarray) and v_.ndim == 3:
+                    t_, kw_h[k_] = pinned(v_)
+                    keep_kw.append(t_)
             # the public call: fwi_objective over `world` shots, shot i -> rank i.  Each rank
             # builds its model from host arrays, propagates its shot from host wavelet / data,
             # sums in HBM, one NCCL all-reduce, and every rank copies the cropped gradient back.
             shots = [(src, q_h, rec, d_h) if i == rank else None for i in range(world)]
 
             def step_host():
-                mh = J.Model((0., 0., 0.), SPACING, shape, m=m0_h, **kw)
+                mh = J.Model((0., 0., 0.), SPACING, shape, m=m0_h, **kw_h)
                 return J.objectives.fwi_objective(mh, shots, t_sub=args.t_sub,
                                                   snapshot_region=args.snapshot_region)
             for _ in range(min(args.warmup, 2)):
@@ -358,7 +364,8 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-            h2d = world * (m0.nbytes + q.nbytes + dobs.nbytes)
+            h2d = world * (m0.nbytes + q.nbytes + dobs.nbytes +
+                           sum(v_.nbytes for v_ in kw.values() if isinstance(v_, np.ndarray)))
             d2h = world * (4 * int(np.prod(shape)) + 4)
             e2e = {"value": world * args.steps / wall, "unit": "shots/s",
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

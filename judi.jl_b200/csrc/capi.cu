@@ -59,6 +59,7 @@ void judi_ctx_destroy(judi_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->arena_p) cudaFree(ctx->arena_p);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

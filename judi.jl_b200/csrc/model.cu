@@ -23,6 +23,31 @@ void judi_ctx::free(void *p)
     if (p) cudaFreeAsync(p, stream);
 }
 
+float *judi_ctx::arena(size_t nfloat)
+{
+    if (nfloat <= arena_floats && arena_p) return arena_p;
+    if (arena_p) {
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaFree(arena_p));
+        arena_p = nullptr;
+        arena_floats = 0;
+    }
+    // plain cudaMalloc: outside the pool, so pool reuse patterns cannot split it
+    const size_t bytes = std::max<size_t>(nfloat, 4) * sizeof(float);
+    cudaError_t e = cudaMalloc((void **)&arena_p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        // give the pool's cached blocks back to the driver and retry
+        (void)cudaGetLastError();
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaMemPoolTrimTo(pool, 0));
+        e = cudaMalloc((void **)&arena_p, bytes);
+    }
+    if (e != cudaSuccess) arena_p = nullptr;
+    CUDA_CHECK(e);
+    arena_floats = nfloat;
+    return arena_p;
+}
+
 void launch_count(judi_ctx *ctx, const char *what)
 {
     ctx->launches++;

@@ -725,7 +725,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         unsigned long long reserved = 0, used = 0;
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
-        double avail = (double)free_b + (double)(reserved - used);
+        double avail = (double)free_b + (double)(reserved - used) + 4.0 * (double)ctx->arena_floats;
         double need = (double)nslots * slot_floats * 4.0 +
                       (double)nseg * 2.0 * nf * (double)M->g.nalloc * 4.0 +
                       (dft ? 2.0 * o->nfreq * slot_floats * 4.0 : 0.0);
@@ -738,7 +738,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             throw JudiError(b);
         }
     }
-    DevBuf snaps(ctx, (size_t)nslots * slot_floats, false);
+    struct { float *p; } snaps = {ctx->arena((size_t)nslots * slot_floats)};
     auto slot_ptr = [&](int s, int f) { return snaps.p + ((size_t)s * nf + f) * reg.slot; };
     // DFT: uf[field][freq][re,im] on the region, and per-step phase tables
     //   forward  (fields_exprs.py:164-167): uf += factor exp(-i w t) u[t]        when t % factor == 0
