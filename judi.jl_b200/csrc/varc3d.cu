@@ -20,7 +20,7 @@
 // ~80 registers and 95 KB of shared memory: two CTAs per SM.
 // HBM traffic: 20 B per grid point (u, u(t-1), m, irho read; u(t+1) written) + halos that miss L2.
 // Measured (C5-size grid, 40.8 M points): plain 0.315 ms, save 0.345, imaging condition 0.48 ms
-// per step against 0.50 / 0.52 / 0.55 ms for the two passes.  ncu (gpurun_out/r01_varc3d_v2): 206 M
+// per step against 0.50 / 0.52 / 0.55 ms for the two passes.  ncu (profiles/r01_ncu_varc3d.md): 206 M
 // warp instructions, 63% issue-active with 24 warps per SM, DRAM 0.95 GB = 3.0 TB/s: bound by
 // instruction issue (only 29% of the instructions are arithmetic: register-queue moves 15%,
 // barrier / mbarrier / address bookkeeping the rest), not by HBM (20 B/pt = 0.125 ms).
