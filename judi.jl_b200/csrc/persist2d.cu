@@ -342,11 +342,178 @@ __global__ void __launch_bounds__(256) flux2d_persist_batch(const P2FluxArgs *__
 }
 
 // ------------------------------------------------------------------------------------------
+// The persistent 2-D time loop of the visco-acoustic SLS physics (kernels.cu has the equations):
+// forward  [flux of p] -> barrier -> r, p update ;  adjoint  r-, w -> barrier -> [flux of w] ->
+// barrier -> p update.  The flux pass exists only with a density field.
+struct P2ViscoArgs {
+    Grid g;
+    Coefs cf;
+    float *b[2];          // pressure buffers; level t is b[cur]
+    float *r, *w;         // memory variable, adjoint product field
+    float *P[2];          // flux scratch (density field)
+    int cur;
+    const float *m, *irho, *tt, *ts;
+    float irho_c;
+    const float *dx, *dz;
+    int t0, t1, dir, adj;
+    const int *cellmap;
+    const int *cell_start, *ent_trace;
+    const float *ent_w, *cell_scale;
+    const float *src;
+    int nsrc;
+    int nrec;
+    const long long *coff;
+    const float *cw;
+    float *rec;
+    float *snap;
+    const float *usnap;
+    float *grad, *illum;
+    long long slot;
+    int t_sub;
+    float gcoef;
+    int t_base;
+    Region reg;
+};
+
+template <int R>
+__device__ __forceinline__ void visco2d_body(const P2ViscoArgs &a, const int lb, const int nb)
+{
+    cg::grid_group grid = cg::this_grid();
+    const Grid &g = a.g;
+    const Coefs &cf = a.cf;
+    const int TX = 32, TZ = 8;
+    const int tx = threadIdx.x % TX, tz = threadIdx.x / TX;
+    const long long gtid = (long long)lb * blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)nb * blockDim.x;
+    const int fnx = g.n[0] + 2 * R, fnz = g.n[2] + 2 * R;
+    const int ftx = (fnx + TX - 1) / TX, ftiles = ftx * ((fnz + TZ - 1) / TZ);
+    const int ntx = (g.n[0] + TX - 1) / TX, ntiles = ntx * ((g.n[2] + TZ - 1) / TZ);
+    int cur = a.cur;
+    for (int t = a.t0;; t += a.dir) {
+        const float *pcur = a.b[cur];
+        float *pnew = a.b[1 - cur];
+        for (long long p = gtid; p < a.nrec; p += gthreads) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const long long o = a.coff[p * 4 + c];
+                if (o >= 0) acc += a.cw[p * 4 + c] * pcur[o];
+            }
+            a.rec[(long long)t * a.nrec + p] = acc;
+        }
+        if (a.adj) {
+            // r- = (1 - dl) (r - dt (b p + r / ts)),  w = (1 + tt) p + (tt / (b ts)) r-
+            for (int tile = lb; tile < ntiles; tile += nb) {
+                const int x = (tile % ntx) * TX + tx, z = (tile / ntx) * TZ + tz;
+                if (x >= g.n[0] || z >= g.n[2]) continue;
+                const long long i = g.at(x, 0, z);
+                const float bb = a.irho ? a.irho[i] : a.irho_c;
+                const float dl = (a.dx[x] + 0.f) + a.dz[z];
+                const float tt = a.tt[i], ts = a.ts[i], pc = pcur[i], rc = a.r[i];
+                const float rn = (1.0f - dl) * (rc - cf.dt * (bb * pc + rc / ts));
+                a.r[i] = rn;
+                a.w[i] = (1.0f + tt) * pc + (tt / (bb * ts)) * rn;
+            }
+            grid.sync();
+        }
+        const float *Ls = a.adj ? a.w : pcur;
+        if (a.irho) {
+            for (int tile = lb; tile < ftiles; tile += nb) {
+                const int x = (tile % ftx) * TX + tx - R, z = (tile / ftx) * TZ + tz - R;
+                if (x >= g.n[0] + R || z >= g.n[2] + R) continue;
+                const long long i = g.at(x, 0, z);
+                float gx = 0.f, gz = 0.f;
+#pragma unroll
+                for (int k = 1; k <= R; k++) {
+                    gx += cf.wx[k] * (Ls[i + k] - Ls[i - (k - 1)]);
+                    gz += cf.wz[k] * (Ls[i + k * g.sz] - Ls[i - (k - 1) * g.sz]);
+                }
+                const float bb = a.irho[i];
+                a.P[0][i] = bb * gx;
+                a.P[1][i] = bb * gz;
+            }
+            grid.sync();
+        }
+        const bool fused_t = ((t - a.t_base) % a.t_sub) == 0;
+        const long long sidx = (long long)((t - a.t_base) / a.t_sub) * a.slot;
+        float *snap_t = (a.snap && fused_t) ? a.snap + sidx : nullptr;
+        const float *usnap_t = (a.grad && fused_t) ? a.usnap + sidx : nullptr;
+        const float *src_row = a.src ? a.src + (long long)t * a.nsrc : nullptr;
+        for (int tile = lb; tile < ntiles; tile += nb) {
+            const int x = (tile % ntx) * TX + tx, z = (tile / ntx) * TZ + tz;
+            if (x >= g.n[0] || z >= g.n[2]) continue;
+            const long long i = g.at(x, 0, z);
+            const float bb = a.irho ? a.irho[i] : a.irho_c;
+            const float mb = a.m[i] * bb;
+            const float dl = (a.dx[x] + 0.f) + a.dz[z];
+            const float sd = cf.dt * dl;
+            float L2;
+            if (a.irho) {
+                float L = 0.f, Lz = 0.f;
+#pragma unroll
+                for (int k = 1; k <= R; k++) {
+                    L += cf.wx[k] * (a.P[0][i + (k - 1)] - a.P[0][i - k]);
+                    Lz += cf.wz[k] * (a.P[1][i + (k - 1) * g.sz] - a.P[1][i - k * g.sz]);
+                }
+                L2 = cf.dt2 * (L + Lz);
+            } else L2 = bb * lap2d<R>(g, cf, Ls, i);
+            float S2 = L2;
+            if (!a.adj) {
+                const float tt = a.tt[i], ts = a.ts[i], rc = a.r[i];
+                const float rn = (1.0f - dl) * (rc + ((tt / ts) * (L2 / bb) * cf.idt - cf.dt * (rc / ts)));
+                a.r[i] = rn;
+                S2 = (1.0f + tt) * L2 - cf.dt2 * (bb * rn);
+            }
+            float inj = 0.f;
+            int row = -1;
+            if (a.cellmap && (row = a.cellmap[i]) >= 0) {
+                float acc = 0.f;
+                for (int e = a.cell_start[row]; e < a.cell_start[row + 1]; e++)
+                    acc += a.ent_w[e] * src_row[a.ent_trace[e]];
+                inj = acc * a.cell_scale[row];
+            }
+            const float pc = pcur[i];
+            const float d1 = pc - pnew[i];
+            const float delta = (S2 - sd * d1) / (mb + sd);
+            pnew[i] = ((pc + d1) + delta) + inj;
+            if ((snap_t || usnap_t || a.illum) && a.reg.has(x, 0, z)) {
+                const long long ri = a.reg.at(x, 0, z);
+                if (snap_t) snap_t[ri] = pc;
+                if (a.illum) a.illum[ri] += cf.dt * pc * pc;
+                if (usnap_t) a.grad[ri] -= a.gcoef * bb * usnap_t[ri] * (delta + inj);
+            }
+        }
+        grid.sync();
+        cur = 1 - cur;
+        if (t == a.t1) break;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) visco2d_persist(P2ViscoArgs a)
+{
+    visco2d_body<R>(a, blockIdx.x, gridDim.x);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) visco2d_persist_batch(const P2ViscoArgs *__restrict__ batch, int per_shot)
+{
+    __shared__ P2ViscoArgs sa;
+    {
+        const int *src = (const int *)(batch + blockIdx.x / per_shot);
+        int *dst = (int *)&sa;
+        for (int i = threadIdx.x; i < (int)(sizeof(P2ViscoArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    visco2d_body<R>(sa, blockIdx.x % per_shot, per_shot);
+}
+
+// ------------------------------------------------------------------------------------------
 bool persist2d_supported(const judi_model *M, int ic, bool born)
 {
-    const bool flux = M->tti || M->irho_field;
-    if (flux && (born || M->r != 4 || (M->tti && !M->r3[0].p))) return false;   // flux form: so = 8, no Born
-    return M->ndim == 2 && !M->visco && !M->fs && ic == JUDI_IC_AS &&
+    const bool flux = M->tti || M->irho_field || M->visco;
+    if (flux && (born || M->r != 4 || (M->tti && !M->r3[0].p))) return false;   // flux form / visco: so = 8, no Born
+    return M->ndim == 2 && !M->fs && ic == JUDI_IC_AS &&
            (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
 }
 
@@ -417,6 +584,76 @@ static void persist2d_run_flux(const judi_model *M, Wavefield &W, int t0, int t1
     }
 }
 
+static void p2visco_fill(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
+                         const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
+                         Traces *out, const P2Fuse &fz, P2ViscoArgs &a)
+{
+    memset(&a, 0, sizeof(a));
+    a.g = M->g; a.cf = M->cf;
+    a.b[0] = W.b[0][0].p; a.b[1] = W.b[0][1].p;
+    a.r = W.rmem.p; a.w = W.wtmp.p;
+    if (M->irho_field) { a.P[0] = W.flux[0].p; a.P[1] = W.flux[2].p; a.irho = M->irho.p; }
+    a.irho_c = M->irho_c;
+    a.cur = W.cur;
+    a.m = M->m.p; a.tt = M->vtt.p; a.ts = M->vts.p;
+    a.dx = M->damp[0].p; a.dz = M->damp[2].p;
+    a.t0 = t0; a.t1 = t1; a.dir = dir;
+    a.adj = dir < 0;      // the reverse sweep is the adjoint scheme
+    if (S_in && in && S_in->ncell > 0) {
+        a.cellmap = S_in->cellmap.p;
+        a.cell_start = S_in->cell_start.p;
+        a.ent_trace = S_in->ent_trace.p;
+        a.ent_w = S_in->ent_w.p;
+        a.cell_scale = S_in->cell_scale.p;
+        a.src = in->buf.p;
+        a.nsrc = in->np;
+    }
+    if (S_out && out && S_out->np > 0) {
+        a.nrec = S_out->np;
+        a.coff = S_out->corner_off.p;
+        a.cw = S_out->corner_w.p;
+        a.rec = out->buf.p;
+    }
+    a.snap = fz.snap; a.usnap = fz.usnap; a.grad = fz.grad; a.illum = fz.illum;
+    a.slot = fz.slot;
+    a.t_sub = fz.t_sub > 0 ? fz.t_sub : 1; a.gcoef = fz.gcoef;
+    a.reg = fz.reg;
+    a.t_base = fz.t_base;
+}
+
+static int p2visco_blocks(const judi_model *M, bool batch)
+{
+    static int mb[2] = {0, 0};
+    if (!mb[batch]) {
+        int per_sm = 0;
+        if (batch) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, visco2d_persist_batch<4>, 256, 0));
+        else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, visco2d_persist<4>, 256, 0));
+        mb[batch] = per_sm * M->ctx->num_sms;
+    }
+    return mb[batch];
+}
+
+static void persist2d_run_visco(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
+                                const SparseSet *S_in, const Traces *in, const SparseSet *S_out,
+                                Traces *out, const P2Fuse &fz)
+{
+    judi_ctx *ctx = M->ctx;
+    const int nsteps = (t1 - t0) * dir + 1;
+    P2ViscoArgs a;
+    p2visco_fill(M, W, t0, t1, dir, S_in, in, S_out, out, fz, a);
+    const int ftiles = ((M->N[0] + 8 + 31) / 32) * ((M->N[2] + 8 + 7) / 8);
+    int nb = std::min(ftiles, p2visco_blocks(M, false));
+    if (ctx->opt_persist_blocks > 0) nb = std::min(nb, ctx->opt_persist_blocks);
+    void *args[] = {(void *)&a};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void *)visco2d_persist<4>, dim3(nb), dim3(256), args, 0, ctx->stream));
+    launch_count(ctx, "visco2d_persist");
+    if (nsteps & 1) W.swap();
+    if (ctx->timing) {
+        ctx->stencil_launches += 1;
+        ctx->stencil_points += (double)nsteps * M->N[0] * M->N[2];
+    }
+}
+
 static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int t1, int dir,
                     const SparseSet *S_in, const Traces *in, const SparseSet *S_out, Traces *out,
                     Traces *out_bg, const P2Fuse &fz, P2Args &a)
@@ -464,6 +701,11 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
     judi_ctx *ctx = M->ctx;
     int nsteps = (t1 - t0) * dir + 1;
     if (nsteps <= 0) return;
+    if (M->visco) {
+        JUDI_REQUIRE(WL == nullptr && out_bg == nullptr, "persistent 2-D visco-acoustic kernel has no Born mode");
+        persist2d_run_visco(M, W, t0, t1, dir, S_in, in, S_out, out, fz);
+        return;
+    }
     if (M->tti || M->irho_field) {
         JUDI_REQUIRE(WL == nullptr && out_bg == nullptr, "persistent 2-D flux kernel has no Born mode");
         persist2d_run_flux(M, W, t0, t1, dir, S_in, in, S_out, out, fz);
@@ -515,6 +757,32 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     judi_ctx *ctx = M->ctx;
     const int nsteps = (t1 - t0) * dir + 1;
     if (nsteps <= 0 || n <= 0) return;
+    if (M->visco) {
+        JUDI_REQUIRE(WL == nullptr, "persistent 2-D visco-acoustic kernel has no Born mode");
+        std::vector<P2ViscoArgs> vargs((size_t)n);
+        for (int s = 0; s < n; s++)
+            p2visco_fill(M, *W[s], t0, t1, dir, S_in ? S_in[s] : nullptr, in ? in[s] : nullptr,
+                         S_out ? S_out[s] : nullptr, out ? out[s] : nullptr, fz[s], vargs[(size_t)s]);
+        DevArr<P2ViscoArgs> dva(ctx, (size_t)n, false);
+        dva.upload(vargs);
+        const int ftiles = ((M->N[0] + 8 + 31) / 32) * ((M->N[2] + 8 + 7) / 8);
+        int cap = p2visco_blocks(M, true);
+        if (ctx->opt_persist_blocks > 0) cap = std::min(cap, ctx->opt_persist_blocks);
+        int per_shot = std::max(1, std::min(ftiles, cap / n));
+        const P2ViscoArgs *dp = dva.p;
+        void *kargs[] = {(void *)&dp, (void *)&per_shot};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((void *)visco2d_persist_batch<4>, dim3(per_shot * n), dim3(256),
+                                               kargs, 0, ctx->stream));
+        launch_count(ctx, "visco2d_persist_batch");
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (nsteps & 1)
+            for (int s = 0; s < n; s++) W[s]->swap();
+        if (ctx->timing) {
+            ctx->stencil_launches += 1;
+            ctx->stencil_points += (double)n * nsteps * M->N[0] * M->N[2];
+        }
+        return;
+    }
     if (M->tti || M->irho_field) {
         JUDI_REQUIRE(WL == nullptr, "persistent 2-D flux kernel has no Born mode");
         std::vector<P2FluxArgs> fargs((size_t)n);

@@ -527,7 +527,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
         return false;
     // lsrtm_objective: Born forward sweeps (constant-density kernel only)
     const bool born = o->born_fwd && M->has_dm;
-    if (born && (M->tti || M->irho_field)) return false;
+    if (born && (M->tti || M->irho_field || M->visco)) return false;
     if (o->nlind && !o->born_fwd) return false;
     const int nt = shots[0].nt;
     if (nt < 3) return false;

@@ -12,9 +12,13 @@ v[:, :21] = 1.5
 src = np.array([[5000., 50.]], dtype=np.float32)
 rec = np.stack([np.linspace(0, 10000., 401), np.full(401, 50.)], axis=1).astype(np.float32)
 blocks = [int(b) for b in os.environ.get("PERSIST_BLOCKS", "0").split(",")]
+ctx.set_option("persist2d", int(os.environ.get("PERSIST2D", "1")))
 for kind in [a for a in sys.argv[1:]] or ["iso", "rho", "tti"]:
     kw = {}
     if kind == "rho": kw["rho"] = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
+    if kind in ("visco", "viscorho"):
+        kw["qp"] = (3.516 * ((v * 1000.) ** 2.2) * 1e-6).astype(np.float32); kw["f0"] = 0.008
+        if kind == "viscorho": kw["rho"] = (0.31 * (v * 1000.) ** 0.25).astype(np.float32)
     if kind == "tti":
         kw.update(epsilon=(0.2 * (v - 1.5) / 4).astype(np.float32), delta=(0.1 * (v - 1.5) / 4).astype(np.float32),
                   theta=(np.pi / 6 * (v - 1.5) / 4).astype(np.float32))
