@@ -363,11 +363,9 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
         }
     }
     for (int d = 0; d < 3; d++) M->N[d] = M->n[d] + M->padl[d] + M->padr[d];
-    // the two-pass flux form (TTI / variable density) differentiates twice: halo of 2R
-    bool flux_form = desc->rho.kind == JUDI_PARAM_ARRAY || desc->b.kind == JUDI_PARAM_ARRAY ||
-                     desc->epsilon.kind != JUDI_PARAM_NONE || desc->delta.kind != JUDI_PARAM_NONE ||
-                     desc->theta.kind != JUDI_PARAM_NONE || desc->phi.kind != JUDI_PARAM_NONE;
-    M->g = make_grid(M->ndim, M->N, (flux_form && 2 * M->r > JUDI_HALO) ? 2 * M->r : JUDI_HALO);
+    // the two-pass flux form (TTI / variable density) and the isic / fwi Born sources of every
+    // physics differentiate twice: halo of 2R
+    M->g = make_grid(M->ndim, M->N, 2 * M->r > JUDI_HALO ? 2 * M->r : JUDI_HALO);
     {
         int lo[3] = {0, 0, 0};
         M->full = make_region(lo, M->N);

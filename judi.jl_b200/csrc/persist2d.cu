@@ -45,6 +45,7 @@ struct P2Args {
     int t_sub;
     float gcoef;
     int t_base;        // snapshot slot of time index t is (t - t_base) / t_sub
+    int ic;            // JUDI_IC_*: imaging condition of the gradient and of the Born source
     Region reg;
 };
 
@@ -60,10 +61,57 @@ __device__ __forceinline__ float lap2d(const Grid &g, const Coefs &cf, const flo
     return acc;
 }
 
+// staggered first derivative D+ of a Grid field along stride s (value at i + 1/2)
+template <int R>
+__device__ __forceinline__ float dplus2d(const float *__restrict__ f, long long i, long long s, const float *w)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 1; k <= R; k++) acc += w[k] * (f[i + k * s] - f[i - (k - 1) * s]);
+    return acc;
+}
+
+// grad(u_s, +1/2) . grad(v, +1/2) with the snapshot read through its region (zero outside):
+// the isic / fwi imaging conditions (sensitivity.py:106-122, 212-228)
+template <int R>
+__device__ float inner_grad2d(const Grid &g, const Coefs &cf, const Region &reg, const float *us,
+                              const float *__restrict__ v, int x, int z)
+{
+    float gux = 0.f, guz = 0.f;
+#pragma unroll
+    for (int k = 1; k <= R; k++) {
+        const float xp = reg.has(x + k, 0, z) ? us[reg.at(x + k, 0, z)] : 0.f;
+        const float xm = reg.has(x - (k - 1), 0, z) ? us[reg.at(x - (k - 1), 0, z)] : 0.f;
+        const float zp = reg.has(x, 0, z + k) ? us[reg.at(x, 0, z + k)] : 0.f;
+        const float zm = reg.has(x, 0, z - (k - 1)) ? us[reg.at(x, 0, z - (k - 1))] : 0.f;
+        gux += cf.wx[k] * (xp - xm);
+        guz += cf.wz[k] * (zp - zm);
+    }
+    const long long i = g.at(x, 0, z);
+    return gux * dplus2d<R>(v, i, 1, cf.wx) + guz * dplus2d<R>(v, i, g.sz, cf.wz);
+}
+
+// div(dm grad(u, +1/2), -1/2): the isic / fwi Born sources (sensitivity.py:191-209), constant irho
+template <int R>
+__device__ float lap_weighted2d(const Grid &g, const Coefs &cf, const float *__restrict__ u,
+                                const float *__restrict__ c, long long i)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 1; k <= R; k++) {
+        const long long xp = i + (k - 1), xm = i - k, zp = i + (k - 1) * g.sz, zm = i - k * g.sz;
+        acc += cf.wx[k] * (c[xp] * dplus2d<R>(u, xp, 1, cf.wx) - c[xm] * dplus2d<R>(u, xm, 1, cf.wx));
+        acc += cf.wz[k] * (c[zp] * dplus2d<R>(u, zp, g.sz, cf.wz) - c[zm] * dplus2d<R>(u, zm, g.sz, cf.wz));
+    }
+    return acc;
+}
+
 // lb / nb: index of this CTA among the nb CTAs that work on the shot described by `a`.
 // (Staging the haloed tile of u(t) in shared memory was measured slower in the batched launch, 55
 // vs 34 ms for the forward sweeps of 16 C2 shots: the L1 already serves the stencil's reuse.)
-template <int R>
+// XIC: compiled with the isic / fwi imaging conditions and Born sources (more registers: the "as"
+// instantiation keeps its occupancy)
+template <int R, bool XIC>
 __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, const int nb)
 {
     cg::grid_group grid = cg::this_grid();
@@ -126,15 +174,28 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
                 const float lcv = lc[i];
                 const float lapl = lap2d<R>(g, a.cf, lc, i);
                 const float d1l = lcv - ln[i];
-                // Born source from the post-injection u+ - 2u + u-  (sensitivity.py:174-188)
-                const float q = -a.dm[i] * (delta + inj);
+                // Born source from the post-injection u+ - 2u + u-  (sensitivity.py:174-209)
+                float q;
+                if (!XIC || a.ic == JUDI_IC_AS) q = -a.dm[i] * (delta + inj);
+                else {
+                    const float ics = a.ic == JUDI_IC_FWI ? -1.f : 1.f;
+                    q = -(a.dm[i] * mm * (delta + inj) -
+                          ics * a.cf.dt2 * lap_weighted2d<R>(g, a.cf, uc, a.dm, i));
+                }
                 ln[i] = (lcv + d1l) + (lapl - s * d1l + q) * rden;
             }
             if ((snap_t || usnap_t || a.illum) && a.reg.has(x, 0, z)) {
                 const long long ri = a.reg.at(x, 0, z);
                 if (snap_t) snap_t[ri] = ucv;
                 if (a.illum) a.illum[ri] += a.cf.dt * ucv * ucv;
-                if (usnap_t) a.grad[ri] -= a.gcoef * a.irho_c * usnap_t[ri] * (delta + inj);
+                if (usnap_t) {
+                    if (!XIC || a.ic == JUDI_IC_AS) a.grad[ri] -= a.gcoef * a.irho_c * usnap_t[ri] * (delta + inj);
+                    else {
+                        const float ics = a.ic == JUDI_IC_FWI ? -1.f : 1.f;
+                        const float ig = inner_grad2d<R>(g, a.cf, a.reg, usnap_t, uc, x, z);
+                        a.grad[ri] -= a.gcoef * a.irho_c * (usnap_t[ri] * (delta + inj) * mm + ics * a.cf.dt2 * ig);
+                    }
+                }
             }
         }
         grid.sync();
@@ -143,15 +204,15 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
     }
 }
 
-template <int R>
+template <int R, bool XIC>
 __global__ void __launch_bounds__(256) acoustic2d_persist(P2Args a)
 {
-    acoustic2d_body<R>(a, blockIdx.x, gridDim.x);
+    acoustic2d_body<R, XIC>(a, blockIdx.x, gridDim.x);
 }
 
 // Several shots of the same model and time axis in lockstep: CTA b works on shot b / per_shot.
 // One grid barrier per time step serves all of them (judi_fg_multishot on small 2-D grids).
-template <int R>
+template <int R, bool XIC>
 __global__ void __launch_bounds__(256) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
 {
     // the shot's arguments go to shared memory once: read through the global pointer, every stencil
@@ -163,7 +224,7 @@ __global__ void __launch_bounds__(256) acoustic2d_persist_batch(const P2Args *__
         for (int i = threadIdx.x; i < (int)(sizeof(P2Args) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    acoustic2d_body<R>(sa, blockIdx.x % per_shot, per_shot);
+    acoustic2d_body<R, XIC>(sa, blockIdx.x % per_shot, per_shot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -512,9 +573,9 @@ __global__ void __launch_bounds__(256) visco2d_persist_batch(const P2ViscoArgs *
 bool persist2d_supported(const judi_model *M, int ic, bool born)
 {
     const bool flux = M->tti || M->irho_field || M->visco;
-    if (flux && (born || M->r != 4 || (M->tti && !M->r3[0].p))) return false;   // flux form / visco: so = 8, no Born
-    return M->ndim == 2 && !M->fs && ic == JUDI_IC_AS &&
-           (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
+    // flux form / visco: so = 8, no Born, "as" only; constant density: every imaging condition
+    if (flux && (born || M->r != 4 || ic != JUDI_IC_AS || (M->tti && !M->r3[0].p))) return false;
+    return M->ndim == 2 && !M->fs && (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
 }
 
 static void p2flux_fill(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
@@ -689,6 +750,7 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
     a.slot = fz.slot; a.t_sub = fz.t_sub > 0 ? fz.t_sub : 1; a.gcoef = fz.gcoef;
     a.reg = fz.reg;
     a.t_base = fz.t_base;
+    a.ic = fz.ic;
 }
 
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced
@@ -713,9 +775,9 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
     }
     P2Args a;
     p2_fill(M, W, WL, t0, t1, dir, S_in, in, S_out, out, out_bg, fz, a);
-    auto launch = [&](auto rtag) {
+    auto launch = [&](auto rtag, auto xtag) {
         constexpr int R = decltype(rtag)::value;
-        auto kern = acoustic2d_persist<R>;
+        auto kern = acoustic2d_persist<R, decltype(xtag)::value>;
         static int max_blocks = 0;
         if (!max_blocks) {
             int per_sm = 0;
@@ -730,11 +792,15 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
                                                ctx->stream));
         launch_count(ctx, "acoustic2d_persist");
     };
-    switch (M->r) {
-    case 2: launch(std::integral_constant<int, 2>()); break;
-    case 4: launch(std::integral_constant<int, 4>()); break;
-    default: launch(std::integral_constant<int, 8>()); break;
-    }
+    auto launch_r = [&](auto xtag) {
+        switch (M->r) {
+        case 2: launch(std::integral_constant<int, 2>(), xtag); break;
+        case 4: launch(std::integral_constant<int, 4>(), xtag); break;
+        default: launch(std::integral_constant<int, 8>(), xtag); break;
+        }
+    };
+    if (a.ic != JUDI_IC_AS && (a.grad || WL)) launch_r(std::true_type());
+    else launch_r(std::false_type());
     if (nsteps & 1) { W.swap(); if (WL) WL->swap(); }
     if (ctx->timing) {
         ctx->stencil_launches += 1;
@@ -824,9 +890,9 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
                 args[(size_t)s]);
     DevArr<P2Args> dargs(ctx, (size_t)n, false);
     dargs.upload(args);
-    auto launch = [&](auto rtag) {
+    auto launch = [&](auto rtag, auto xtag) {
         constexpr int R = decltype(rtag)::value;
-        auto kern = acoustic2d_persist_batch<R>;
+        auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value>;
         static int max_blocks = 0;
         if (!max_blocks) {
             int per_sm = 0;
@@ -843,11 +909,15 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
                                                ctx->stream));
         launch_count(ctx, "acoustic2d_persist_batch");
     };
-    switch (M->r) {
-    case 2: launch(std::integral_constant<int, 2>()); break;
-    case 4: launch(std::integral_constant<int, 4>()); break;
-    default: launch(std::integral_constant<int, 8>()); break;
-    }
+    auto launch_r = [&](auto xtag) {
+        switch (M->r) {
+        case 2: launch(std::integral_constant<int, 2>(), xtag); break;
+        case 4: launch(std::integral_constant<int, 4>(), xtag); break;
+        default: launch(std::integral_constant<int, 8>(), xtag); break;
+        }
+    };
+    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type());
+    else launch_r(std::false_type());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dargs is freed on return
     if (nsteps & 1)
         for (int s = 0; s < n; s++) {

@@ -493,6 +493,7 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     if (persist2d_supported(M, ic, true) && !sh.ext_active()) {
         P2Fuse pf;
         pf.reg = M->full;
+        pf.ic = ic;
         pf.illum = fz.illum;
         persist2d_run(M, W, &WL, 1, nt - 2, 1, pS, &q, &S_rec, &rec, nullptr, pf);
     } else {
@@ -535,7 +536,8 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
         if (shots[s].nt != nt || shots[s].nsrc <= 0 || shots[s].nrec <= 0) return false;
     const bool dev = flags & JUDI_DATA_ON_DEVICE;
     const int k = std::max(1, o->t_sub);
-    const Region reg = o->snapshot_region == JUDI_SNAP_PHYSICAL ? M->phys : M->full;
+    // ISIC/FWI differentiate the snapshot: it must cover the whole padded grid
+    const Region reg = (o->snapshot_region == JUDI_SNAP_PHYSICAL && o->ic == JUDI_IC_AS) ? M->phys : M->full;
     const int nslots = num_slots(nt, k);
     const int nf = M->tti ? 2 : 1;
     const size_t slot_floats = (size_t)reg.slot * nf;
@@ -582,6 +584,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
             snaps[s] = DevBuf(ctx, (size_t)nslots * slot_floats, false);
             grad[s] = DevBuf(ctx, (size_t)reg.slot, true);
             pf[s].reg = reg;
+            pf[s].ic = o->ic;
             pf[s].snap = snaps[s].p;
             pf[s].slot = (long long)slot_floats;
             pf[s].t_sub = k;
@@ -612,6 +615,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
             pres[s] = &rec[s];
             pf[s] = P2Fuse();
             pf[s].reg = reg;
+            pf[s].ic = o->ic;
             pf[s].grad = grad[s].p;
             pf[s].usnap = snaps[s].p;
             pf[s].slot = (long long)slot_floats;
@@ -792,6 +796,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         if (p2) {
             P2Fuse pf;
             pf.reg = reg;
+            pf.ic = o->ic;
             pf.illum = fsave.illum;
             if (mode) {
                 pf.snap = snaps.p;
@@ -917,6 +922,7 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         if (p2) {
             P2Fuse pf;
             pf.reg = reg;
+            pf.ic = o->ic;
             pf.illum = fadj.illum;
             pf.grad = grad.p;
             pf.usnap = snaps.p;

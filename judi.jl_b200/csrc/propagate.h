@@ -51,6 +51,7 @@ struct P2Fuse {
     long long slot = 0;           // floats per snapshot slot
     int t_sub = 1, t_base = 0;    // slot of time index t is (t - t_base) / t_sub
     float gcoef = 0;
+    int ic = JUDI_IC_AS;          // imaging condition of the gradient / Born source
     Region reg;
 };
 bool persist2d_supported(const judi_model *M, int ic, bool born = false);

@@ -135,13 +135,14 @@ def test_fwi_objective_and_options(kind, ndim):
     assert flc == fl and np.array_equal(glc, gl)
 
 
-@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("rho", 2), ("tti", 2), ("rho", 3), ("tti", 3),
-                                       ("visco", 2), ("viscoc", 3)])
+@pytest.mark.parametrize("kind,ndim,so", [("iso", 2, 8), ("iso", 3, 8), ("rho", 2, 8), ("tti", 2, 8), ("rho", 3, 8),
+                                          ("tti", 3, 8), ("visco", 2, 8), ("viscoc", 3, 8),
+                                          ("iso", 2, 4), ("iso", 2, 16), ("iso", 3, 16)])
 @pytest.mark.parametrize("ic", ["isic", "fwi"])
-def test_isic_fwi_imaging_conditions(kind, ndim, ic):
+def test_isic_fwi_imaging_conditions(kind, ndim, so, ic):
     """test_all_options.jl:13-53 runs isic / fwi on the variable-density and the TTI model
     (seismic_utils.jl:23-63): Born data and gradient against the oracle + the J dot test."""
-    J, args, gm, om, src, rec, q, dt = both(kind, ndim, 8)
+    J, args, gm, om, src, rec, q, dt = both(kind, ndim, so)
     dl, _ = J.born_rec(gm, src, q, rec, ic=ic)
     dlo, _ = O.born_rec(om, src, q, rec, ic=ic)
     assert rel_l2(dl, dlo) < TOL_SHOT
@@ -342,6 +343,15 @@ def test_fg_multishot_equals_the_sum_of_single_shots(kind):
         fl += float(f_k)
         gl = gl + g_k.astype(np.float64)
     flo, glo = J.objectives.lsrtm_objective(gm, shots, args["dm"], nlind=True)
+    assert abs(float(flo) - fl) <= 1e-5 * abs(fl)
+    assert rel_l2(glo, gl[crop]) < 1e-5
+    # the isic imaging condition (lsrtm_2D.jl:47) in lockstep: Born source and gradient
+    fl, gl = 0.0, 0.0
+    for (s_k, w, rc, dobs) in shots:
+        f_k, g_k, _, _ = J.J_adjoint(gm, s_k, w, rc, dobs, return_obj=True, born_fwd=True, ic="isic")
+        fl += float(f_k)
+        gl = gl + g_k.astype(np.float64)
+    flo, glo = J.objectives.lsrtm_objective(gm, shots, args["dm"], ic="isic")
     assert abs(float(flo) - fl) <= 1e-5 * abs(fl)
     assert rel_l2(glo, gl[crop]) < 1e-5
 
