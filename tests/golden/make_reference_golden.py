@@ -15,6 +15,11 @@ replaced by an import stub that only provides symbols (no semantics of its own b
     adjoint, with `solve` done by sympy after u.dt2, u.dt, u.dt.T are replaced by their time
     stencils (the one-sided u.dt of SURVEY A.3 is THIS script's assumption, stated in the stub)   (kernels.py:80-141)
 
+  * models.damp_op: the list of Eq / Inc over left / right SubDimensions that initialises the
+    absorbing-layer field, interpreted by this script on a numpy array (SubDimension.left covers
+    the first `thickness` indices of its parent, .right the last ones: Devito's documented
+    meaning, [dv]) for both abc types, with and without free surface   (models.py:53-98)
+
 Run from the repository root (needs /root/reference):  python tests/golden/make_reference_golden.py
 Output: tests/golden/reference_golden.json (committed; the tests never read /root/reference).
 """
@@ -138,6 +143,73 @@ class Field(sp.Symbol):
     def indices(self):
         t = types.SimpleNamespace(spacing=sp.Symbol("dt_save"))
         return (t,)
+
+
+# ---------------------------------------------------------------------------------------------
+# damp_op (models.py:53-98): symbols for the Devito objects + an interpreter of the Eq / Inc list
+class _Dim(object):
+    def __init__(self, name):
+        self.name = name
+        self.spacing = sp.Symbol("h_" + name)
+        self.symbolic_min = sp.Symbol(name + "_m")
+        self.symbolic_max = sp.Symbol(name + "_M")
+
+
+class _SubDim(sp.Symbol):
+    def __new__(cls, name, parent, thickness, side):
+        obj = sp.Symbol.__new__(cls, name)
+        obj.parent, obj.thickness, obj.side = parent, int(thickness), side
+        return obj
+
+    @classmethod
+    def left(cls, name=None, parent=None, thickness=None):
+        return cls(name, parent, thickness, "left")
+
+    @classmethod
+    def right(cls, name=None, parent=None, thickness=None):
+        return cls(name, parent, thickness, "right")
+
+
+class _DampFunction(object):
+    def __init__(self, name=None, grid=None, space_order=0):
+        self.dimensions = grid.dimensions
+
+    def subs(self, mapping):
+        (d, sub), = mapping.items()
+        return ("on", d, sub)
+
+
+class _Grid(object):
+    def __init__(self, shape):
+        self.dimensions = tuple(_Dim(n) for n in ("x", "y", "z")[:len(shape) - 1] + ("z",))[:len(shape)]
+        if len(shape) == 2:
+            self.dimensions = (_Dim("x"), _Dim("z"))
+
+
+def run_damp_eqs(eqs, shape, spacing):
+    """Apply the Eq / Inc list to a float64 array of `shape` (index ranges as Devito defines them
+    for left / right SubDimensions of thickness t: [0, t) and [N - t, N))."""
+    out = None
+    for e in eqs:
+        if e[0] == "Eq":
+            out = np.full(shape, float(e[2]), dtype=np.float64)
+            continue
+        assert e[0] == "Inc"
+        _, (_, d, sub), val = e
+        ax = [dd.name for dd in DAMP_DIMS].index(d.name)
+        N = shape[ax]
+        idx = range(0, sub.thickness) if sub.side == "left" else range(N - sub.thickness, N)
+        for i in idx:
+            v = float(sp.sympify(val).xreplace({sub: sp.Integer(i), d.symbolic_min: sp.Integer(0),
+                                                d.symbolic_max: sp.Integer(N - 1),
+                                                d.spacing: sp.Float(spacing[ax])}))
+            sl = [slice(None)] * len(shape)
+            sl[ax] = i
+            out[tuple(sl)] += v
+    return out
+
+
+DAMP_DIMS = ()
 
 
 def _solve(expr, target):
@@ -413,6 +485,42 @@ def main():
                 upd.append(dict(kind=kind, fw=fw, inputs=vals, irho=(0.8 if kind == "acoustic" else vals["b"]),
                                 new=[nsub(e[2]) for e in eqs]))
     out["cases"]["update"] = upd
+
+
+    # ---- 8. absorbing-layer field ---------------------------------------------------------------------
+    global DAMP_DIMS
+    models.Grid = _Grid
+    models.Function = _DampFunction
+    models.SubDimension = _SubDim
+    models.Abs, models.sin = sp.Abs, sp.sin
+    models.Eq = lambda *a, **k: ("Eq",) + a
+    models.Inc = lambda *a, **k: ("Inc",) + a
+    models.Operator = lambda eqs, **k: eqs
+    damps = []
+    for ndim, nbl, n, h in ((2, 9, (7, 5), (10., 12.5)), (2, 40, (5, 4), (25., 25.)),
+                            (3, 5, (3, 2, 3), (10., 20., 15.))):
+        for fs in (False, True):
+            for abc in ("damp", "mask"):
+                pads = tuple((nbl, nbl) for _ in range(ndim - 1)) + (((0 if fs else nbl), nbl),)
+                shape = tuple(n_ + l + r for n_, (l, r) in zip(n, pads))
+                g = _Grid(shape)
+                DAMP_DIMS = g.dimensions
+                _orig = models.Grid
+                models.Grid = lambda shp, _g=g: _g
+                eqs = models.damp_op(ndim, pads, abc, fs)
+                models.Grid = _orig
+                arr = run_damp_eqs(eqs, shape, h)
+                entry = dict(ndim=ndim, nbl=nbl, shape=list(n), spacing=list(h), fs=fs, abc=abc,
+                             padsizes=[list(t) for t in pads])
+                if arr.size <= 2100:
+                    entry["damp"] = np.round(arr, 13).tolist()
+                else:       # the reference's default layer width: axis lines through the middle + diagonal
+                    mid = tuple(s_ // 2 for s_ in shape)
+                    entry["lines"] = [np.round(arr[tuple(slice(None) if a == ax else mid[a] for a in range(ndim))], 13).tolist()
+                                      for ax in range(ndim)]
+                    entry["diag"] = [round(float(arr[(i,) * ndim]), 13) for i in range(min(shape))]
+                damps.append(entry)
+    out["cases"]["damp"] = damps
 
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:

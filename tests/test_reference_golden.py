@@ -4,8 +4,9 @@ tests/golden/make_reference_golden.py, which also lists the reference file:line 
 
 What this pins to the reference's executed code: the CFL coefficient and critical dt, padsizes,
 the rotated TTI flux algebra (R_mat / thomsen_mat / sa_tti), signs and factors of the "as" / "isic"
-/ "fwi" imaging conditions and Born sources, Loss, the number of saved snapshots and the
-visco-acoustic SLS update (modulo the time-stencil convention the stub states).  What it
+/ "fwi" imaging conditions and Born sources, Loss, the number of saved snapshots, the
+visco-acoustic SLS update (modulo the time-stencil convention the stub states) and the
+absorbing-layer field of both abc types (damp_op's Eq / Inc list, interpreted on numpy).  What it
 cannot pin: the Devito-generated stencil loops themselves.
 """
 import json
@@ -168,6 +169,52 @@ def test_number_of_saved_snapshots():
     for c in GOLD["nsave"]:
         if c["nsave"] is not None:
             assert O.nsave(c["nt"], c["t_sub"]) == c["nsave"], c
+
+
+def _damp_model_kw(c):
+    n = tuple(c["shape"])
+    return dict(origin=(0.,) * c["ndim"], spacing=tuple(c["spacing"]), shape=n, space_order=8,
+                nbl=c["nbl"], fs=c["fs"], m=np.full(n, 0.25, dtype=np.float32))
+
+
+def _check_damp(c, damp):
+    """`damp` (abc_type "damp", padded grid) against the entry's full array or its lines."""
+    sign, base = (1., 0.) if c["abc"] == "damp" else (-1., 1.)    # mask = 1 - damp (models.py:73-93)
+    got = base + sign * np.asarray(damp, dtype=np.float64)
+    if "damp" in c:
+        ref = np.asarray(c["damp"])
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 3e-7 * max(np.abs(ref).max(), 1.)
+        return
+    nd = c["ndim"]
+    mid = tuple(s // 2 for s in got.shape)
+    for ax in range(nd):
+        line = got[tuple(slice(None) if a == ax else mid[a] for a in range(nd))]
+        ref = np.asarray(c["lines"][ax])
+        assert np.abs(line - ref).max() <= 3e-7 * max(np.abs(ref).max(), 1.)
+    diag = np.array([got[(i,) * nd] for i in range(min(got.shape))])
+    assert np.abs(diag - np.asarray(c["diag"])).max() <= 3e-7 * max(np.abs(diag).max(), 1.)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["damp"])))
+def test_absorbing_layer_field(i):
+    """models.py:53-98 (damp_op) executed: layer width nbl - 3, coefficient 1.5 ln(1000) / (nbl - 3),
+    the +1 in the position, division by the spacing of each dimension, no top layer with a free
+    surface, and the mask form 1 - profile the visco-acoustic equations use."""
+    c = GOLD["damp"][i]
+    om = O.Model(precision="f32", **_damp_model_kw(c))
+    assert [list(t) for t in om.padsizes] == c["padsizes"]
+    _check_damp(c, om.damp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(0, len(GOLD["damp"]), 2))
+def test_library_absorbing_layer_matches_reference(i):
+    """The separable 1-D profiles of the CUDA library, summed on the device, against the same vectors."""
+    import judi_jl_b200 as J
+    c = GOLD["damp"][i]
+    gm = J.Model(**_damp_model_kw(c))
+    _check_damp(c, gm.get_field("damp"))
 
 
 @pytest.mark.gpu
