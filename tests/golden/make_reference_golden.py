@@ -20,6 +20,11 @@ replaced by an import stub that only provides symbols (no semantics of its own b
     the first `thickness` indices of its parent, .right the last ones: Devito's documented
     meaning, [dv]) for both abc types, with and without free surface   (models.py:53-98)
 
+  * geom_utils.geom_expr: which field and time level the source is injected into (forward /
+    adjoint, single field / TTI pair), the injected expression src * dt^2 / (m * irho), and what
+    the receivers interpolate, with PointSource / Receiver replaced by capturing symbols;
+    sources.RickerSource.wavelet and sources.TimeAxis on numpy   (geom_utils.py:31-96, sources.py:11-176)
+
 Run from the repository root (needs /root/reference):  python tests/golden/make_reference_golden.py
 Output: tests/golden/reference_golden.json (committed; the tests never read /root/reference).
 """
@@ -247,7 +252,10 @@ def install_stub():
     tools.memoized_func = lambda f: f
     sys.modules["devito"] = dv
     sys.modules["devito.tools"] = tools
-    for sub in ("devito.types", "devito.builtins", "devito.arch", "devito.arch.compiler",
+    types_mod = _Module("devito.types")
+    types_mod.SparseTimeFunction = type("SparseTimeFunction", (), {"__rkwargs__": ()})
+    sys.modules["devito.types"] = types_mod
+    for sub in ("devito.builtins", "devito.arch", "devito.arch.compiler",
                 "devito.types.utils", "devito.symbolics", "devito.finite_differences"):
         sys.modules[sub] = _Module(sub)
     sys.path.insert(0, os.path.join(REF, "src", "pysource"))
@@ -521,6 +529,60 @@ def main():
                     entry["diag"] = [round(float(arr[(i,) * ndim]), 13) for i in range(min(shape))]
                 damps.append(entry)
     out["cases"]["damp"] = damps
+
+    # ---- 9. source injection / receiver interpolation expressions, Ricker wavelet, time axis ---------
+    import geom_utils
+    import sources
+
+    class Sparse(sp.Symbol):
+        def __new__(cls, name=None, grid=None, ntime=None, coordinates=None):
+            obj = sp.Symbol.__new__(cls, name)
+            obj.data = np.zeros((ntime, coordinates.shape[0]), dtype=np.float32)
+            return obj
+
+        def inject(self, field=None, expr=None):
+            return [("inject", str(field), expr)]
+
+        def interpolate(self, expr=None):
+            return [("interpolate", str(expr))]
+
+    geom_utils.PointSource = Sparse
+    geom_utils.Receiver = Sparse
+    geo = []
+    for tti in (False, True):
+        for fw in (True, False):
+            model = types.SimpleNamespace(irho=sp.Symbol("b"), m=sp.Symbol("m"), is_elastic=False, is_tti=tti,
+                                          fs=False, grid=types.SimpleNamespace(time_dim=types.SimpleNamespace(
+                                              spacing=sp.Symbol("dt"))),
+                                          __init_abox__=lambda *a, **k: None)
+            u = (Field("u1"), Field("u2")) if tti else Field("u1")
+            ex = geom_utils.geom_expr(model, u, src_coords=np.zeros((2, 3)), rec_coords=np.zeros((3, 3)),
+                                      wavelet=np.ones((7, 2), dtype=np.float32), fw=fw)
+            inj = [e for e in ex if e[0] == "inject"]
+            itp = [e for e in ex if e[0] == "interpolate"]
+            assert len(inj) == 1 and len(itp) == 1
+            vals = dict(b=float(rng.uniform(0.4, 1.2)), m=float(rng.uniform(0.05, 0.5)),
+                        dt=float(rng.uniform(0.5, 2.0)))
+            src_sym = [s_ for s_ in inj[0][2].free_symbols if s_.name.startswith("src")][0]
+            vals[src_sym.name] = float(rng.standard_normal())
+            geo.append(dict(tti=tti, fw=fw, inject_field=inj[0][1], interpolate=itp[0][1], inputs=vals,
+                            src_name=src_sym.name,
+                            injected=float(inj[0][2].xreplace({s_: sp.Float(vals[s_.name])
+                                                               for s_ in inj[0][2].free_symbols}))))
+    out["cases"]["geometry"] = geo
+    rick = []
+    # the Julia helper the oracle restates spreads nt = floor(tmax / dt) + 1 samples over [0, tmax];
+    # the two time axes coincide when tmax is a multiple of dt, where the wavelets are compared
+    for (f0, dt_, tmax) in ((0.008, 2.0, 2000.), (0.010, 0.5, 1000.), (0.025, 4.0, 1200.),
+                            (0.008, 1.921, 2000.), (0.010, 0.75, 1000.)):
+        ax = sources.TimeAxis(start=0., step=dt_, stop=tmax)
+        self_ = types.SimpleNamespace(f0=f0, a=None, t0=None)
+        w = sources.RickerSource.wavelet(self_, ax.time_values)
+        entry = dict(f0=f0, dt=dt_, tmax=tmax, num=int(ax.num), stop=float(ax.stop))
+        if abs(ax.stop - tmax) < 1e-9:
+            entry["wavelet"] = [float(x) for x in np.round(w[:160], 12)]
+        rick.append(entry)
+    out["cases"]["ricker"] = rick
 
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:

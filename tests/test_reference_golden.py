@@ -6,7 +6,9 @@ What this pins to the reference's executed code: the CFL coefficient and critica
 the rotated TTI flux algebra (R_mat / thomsen_mat / sa_tti), signs and factors of the "as" / "isic"
 / "fwi" imaging conditions and Born sources, Loss, the number of saved snapshots, the
 visco-acoustic SLS update (modulo the time-stencil convention the stub states) and the
-absorbing-layer field of both abc types (damp_op's Eq / Inc list, interpreted on numpy).  What it
+absorbing-layer field of both abc types (damp_op's Eq / Inc list, interpreted on numpy), which
+field / time level the source goes into with which factor and what the receivers read
+(geom_expr), and the Ricker wavelet / time axis of sources.py.  What it
 cannot pin: the Devito-generated stencil loops themselves.
 """
 import json
@@ -169,6 +171,78 @@ def test_number_of_saved_snapshots():
     for c in GOLD["nsave"]:
         if c["nsave"] is not None:
             assert O.nsave(c["nt"], c["t_sub"]) == c["nsave"], c
+
+
+def _one_step_setup(c, ndim=2):
+    """A model with varying m and density (and Thomsen parameters), one source exactly on a grid
+    node: after the first time step from rest the wavefield holds nothing but the injection."""
+    n = (9, 8) if ndim == 2 else (7, 6, 8)
+    rng = np.random.default_rng(3)
+    kw = dict(origin=(0.,) * ndim, spacing=(10.,) * ndim, shape=n, space_order=8, nbl=6,
+              m=rng.uniform(0.1, 0.4, n).astype(np.float32), rho=rng.uniform(0.9, 2.2, n).astype(np.float32))
+    if c["tti"]:
+        kw.update(epsilon=rng.uniform(0.1, 0.2, n).astype(np.float32), delta=rng.uniform(0., 0.1, n).astype(np.float32),
+                  theta=rng.uniform(-.5, .5, n).astype(np.float32))
+    node = tuple(s // 2 for s in n)
+    src = np.array([[10. * i for i in node]], dtype=np.float32)
+    q = np.array([[0.3], [-1.7], [0.9], [0.2]], dtype=np.float32)
+    return kw, node, src, q
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["geometry"])))
+def test_injection_target_and_factor(i):
+    """geom_utils.py:61-96 executed: the source goes into the NEW time level (u.forward, or
+    u.backward for the adjoint) of the FIRST field only, as src * dt^2 / (m * irho); receivers
+    read the first field at the current level."""
+    c = GOLD["geometry"][i]
+    assert c["inject_field"] == ("u1_f" if c["fw"] else "u1_b") and c["interpolate"] == "u1"
+    v = c["inputs"]
+    assert np.isclose(c["injected"], v[c["src_name"]] * v["dt"] ** 2 / (v["m"] * v["b"]), rtol=1e-12)
+    kw, node, src, q = _one_step_setup(c)
+    om = O.Model(precision="f64", **kw)
+    dt = float(om.critical_dt)
+    _, usave, _ = O.forward(om, src, None, q, save=True, fw=c["fw"])
+    pn = tuple(i_ + l for i_, (l, r) in zip(node, om.padsizes))
+    m, b = float(kw["m"][node]), 1.0 / float(kw["rho"][node])
+    # forward: the first step is t = 1 (writes level 2 from src[1]); adjoint: t = nt - 2 (writes
+    # level nt - 3 from src[nt - 2])
+    lvl, row = (2, 1) if c["fw"] else (q.shape[0] - 3, q.shape[0] - 2)
+    expect = float(q[row, 0]) * dt ** 2 / (m * b)
+    got = usave[lvl, 0]
+    assert np.isclose(got[pn], expect, rtol=1e-6)
+    assert np.count_nonzero(got) == 1
+    if c["tti"]:
+        assert np.count_nonzero(usave[lvl, 1]) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("tti", [False, True])
+def test_library_injection_target_and_factor(tti, ndim):
+    """The same known answer through the C-ABI (judi_forward_no_rec returns the wavefield history)."""
+    import judi_jl_b200 as J
+    c = dict(tti=tti, fw=True)
+    kw, node, src, q = _one_step_setup(c, ndim)
+    gm = J.Model(**kw)
+    dt = float(gm.critical_dt)
+    u, _ = J.forward_no_rec(gm, src, q)
+    pn = tuple(i_ + l for i_, (l, r) in zip(node, gm.padsizes))
+    expect = float(q[1, 0]) * dt ** 2 / (float(kw["m"][node]) / float(kw["rho"][node]))
+    assert np.isclose(u[2][pn], expect, rtol=1e-5)
+    assert np.count_nonzero(u[2]) == 1
+
+
+@pytest.mark.parametrize("c", GOLD["ricker"])
+def test_ricker_wavelet_and_time_axis(c):
+    """sources.py:11-66 (TimeAxis) and :160-176 (RickerSource.wavelet) executed, against the
+    oracle's restatement of the Julia helper the reference's scripts use (auxiliaryFunctions.jl:205-213)."""
+    t0, dt, nt = O.time_axis(c["dt"], c["tmax"])
+    assert nt == c["num"]
+    if "wavelet" not in c:
+        return
+    w = O.ricker_wavelet(c["tmax"], c["dt"], c["f0"])[:160, 0]
+    ref = np.asarray(c["wavelet"])[:len(w)]
+    assert np.abs(w - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
 def _damp_model_kw(c):
