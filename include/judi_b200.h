@@ -83,7 +83,7 @@ enum {
 };
 
 /* options of J_adjoint: the keyword arguments of src/pysource/interface.py:279-282 that this
- * path supports (freq_list/dft_sub are out of scope) */
+ * path supports */
 typedef struct {
     int is_residual;   /* recin is already the residual (J' as an operator, python_interface.jl:119) */
     int checkpointing; /* Options(optimal_checkpointing): recompute segments from HBM checkpoints */
@@ -98,7 +98,8 @@ typedef struct {
                           J_adjoint(ws=...) of python_interface.jl:179-198 */
     /* on-the-fly DFT gradient (J_adjoint_freq, interface.py:348-408): nfreq > 0 replaces the
      * wavefield snapshots by nfreq complex frequency slices accumulated every dft_sub steps
-     * (fields_exprs.py:140-169) and the imaging condition by sensitivity.py:72-104.
+     * (fields_exprs.py:140-169) and the imaging condition by sensitivity.py:72-104, which the
+     * reference applies on every adjoint step whatever dft_sub is (grad_expr, sensitivity.py:50).
      * freq_list: host array of nfreq frequencies in kHz. */
     int nfreq;
     int dft_sub;       /* DFT time subsampling factor (>= 1) */

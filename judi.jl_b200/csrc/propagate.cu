@@ -747,21 +747,27 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     // DFT: uf[field][freq][re,im] on the region, and per-step phase tables
     //   forward  (fields_exprs.py:164-167): uf += factor exp(-i w t) u[t]        when t % factor == 0
     //   gradient (sensitivity.py:94-103):   gradm -= w_f Re(uf exp(i w t)) v[t],  w_f = -(2 pi f)^2 / time_M
+    // on EVERY step: grad_expr passes dft_sub to the imaging condition as `factor=` (sensitivity.py:50),
+    // a keyword crosscorr_freq does not have, so the adjoint correlation is never subsampled.
     DevBuf uf, cs_tab, wc_tab;
     const int ndft = dft ? (nt / dfac + 1) : 0;
     if (dft) {
         uf = DevBuf(ctx, (size_t)2 * o->nfreq * slot_floats, true);
-        std::vector<float> cs((size_t)ndft * 2 * o->nfreq), wc(cs.size());
-        for (int j = 0; j < ndft; j++)
-            for (int q_ = 0; q_ < o->nfreq; q_++) {
-                const double f = (double)o->freq_list[q_];
+        std::vector<float> cs((size_t)ndft * 2 * o->nfreq), wc((size_t)nt * 2 * o->nfreq);
+        for (int q_ = 0; q_ < o->nfreq; q_++) {
+            const double f = (double)o->freq_list[q_];
+            const double w = -(2.0 * M_PI * f) * (2.0 * M_PI * f) / (double)(nt - 2);
+            for (int j = 0; j < ndft; j++) {
                 const double wt = 2.0 * M_PI * f * (double)(j * dfac) * (double)M->dt;
-                const double w = -(2.0 * M_PI * f) * (2.0 * M_PI * f) / (double)(nt - 2);
                 cs[((size_t)j * o->nfreq + q_) * 2] = (float)((double)dfac * std::cos(wt));
                 cs[((size_t)j * o->nfreq + q_) * 2 + 1] = (float)(-(double)dfac * std::sin(wt));
-                wc[((size_t)j * o->nfreq + q_) * 2] = (float)(w * std::cos(wt));
-                wc[((size_t)j * o->nfreq + q_) * 2 + 1] = (float)(-w * std::sin(wt));
             }
+            for (int t = 0; t < nt; t++) {
+                const double wt = 2.0 * M_PI * f * (double)t * (double)M->dt;
+                wc[((size_t)t * o->nfreq + q_) * 2] = (float)(w * std::cos(wt));
+                wc[((size_t)t * o->nfreq + q_) * 2 + 1] = (float)(-w * std::sin(wt));
+            }
+        }
         cs_tab = DevBuf(ctx, cs.size(), false);
         cs_tab.upload(cs);
         wc_tab = DevBuf(ctx, wc.size(), false);
@@ -935,10 +941,10 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         }
         for (int t = ta; t >= tb; t--) {
             adj_step(t, dft ? -1 : (mode == 1 ? ((t % k) == 0 ? t / k : -1) : t - base));
-            if (dft && (t % dfac) == 0)
+            if (dft)
                 for (int ff = 0; ff < nf; ff++)
                     dft_gradient(M, reg, V.other(ff), uf_ptr(ff), o->nfreq,
-                                 wc_tab.p + (size_t)(t / dfac) * 2 * o->nfreq, grad.p);
+                                 wc_tab.p + (size_t)t * 2 * o->nfreq, grad.p);
         }
     };
     if (!o->checkpointing) {

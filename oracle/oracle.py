@@ -657,18 +657,37 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     return g, Iu, Iv
 
 
+def dft_gradient(u, v, dt, freq_list, factor=1):
+    """On-the-fly DFT gradient from wavefield histories u, v of shape (nt, nfields, ...):
+      forward  fields_exprs.py:140-169:  uf[f] = sum_{t=1, t % factor == 0}^{nt-2}
+                                                 factor * exp(-i 2 pi f t dt) * u[t]
+      gradient sensitivity.py:72-104:    gradm -= w_f * Re(uf[f] exp(i 2 pi f t dt) v[t]) for EVERY
+               t = nt-2 .. 1, w_f = -(2 pi f)^2 / time_M, time_M = nt - 2, summed over frequencies
+               and over the field pairs (u_i, v_i) of TTI.  grad_expr hands dft_sub to the imaging
+               condition as `factor=` (sensitivity.py:50), which crosscorr_freq's signature does
+               not take: its own dft_sub stays None and the correlation is never subsampled
+               (tests/golden/make_reference_golden.py section 10 executes exactly this).
+    The complex product is stored into the real `gradm`, i.e. its real part is kept."""
+    nt = u.shape[0]
+    factor = int(factor) if factor else 1
+    tf = np.array([t for t in range(1, nt - 1) if t % factor == 0], dtype=np.int64)
+    ta = np.arange(1, nt - 1, dtype=np.int64)
+    g = np.zeros(u.shape[2:], dtype=np.float64)
+    for fk in np.asarray(freq_list, dtype=np.float64):
+        phf = np.exp(-1j * 2 * np.pi * fk * tf * dt)
+        pha = np.exp(1j * 2 * np.pi * fk * ta * dt)
+        w = -(2 * np.pi * fk) ** 2 / (nt - 2)
+        for fld in range(u.shape[1]):
+            uf = factor * np.tensordot(phf, u[tf, fld].astype(np.float64), axes=(0, 0))
+            vf = np.tensordot(pha, v[ta, fld].astype(np.float64), axes=(0, 0))
+            g -= w * (uf * vf).real
+    return g
+
+
 def J_adjoint_freq(model, src_coords, wavelet, rec_coords, recin, freq_list, dft_sub=None,
                    is_residual=False, return_obj=False, born_fwd=False, nlind=False, misfit=None):
     """interface.py:348-408 (on-the-fly DFT gradient), evaluated from the stored wavefield
-    histories instead of on the fly (small cases only):
-      forward  fields_exprs.py:140-169:  uf[f] = sum_{t=1, t % factor == 0}^{nt-2}
-                                                 factor * exp(-i 2 pi f t dt) * u[t]
-      gradient sensitivity.py:72-104:    gradm -= w_f * Re(uf[f] exp(i 2 pi f t dt)) * v[t] for
-               t = nt-2 .. 1 with t % factor == 0, w_f = -(2 pi f)^2 / time_M, time_M = nt - 2;
-               summed over frequencies and over the field pairs (u_i, v_i) of TTI.
-    The complex product is stored into the real `gradm`, i.e. its real part is kept."""
-    factor = int(dft_sub) if dft_sub else 1
-    nt = wavelet.shape[0]
+    histories instead of on the fly (small cases only), see dft_gradient."""
     if born_fwd:
         rec, u, _ = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind)
     else:
@@ -676,17 +695,7 @@ def J_adjoint_freq(model, src_coords, wavelet, rec_coords, recin, freq_list, dft
     f, residual = Loss(rec, recin, float(model.critical_dt), is_residual=is_residual,
                        misfit=misfit)
     _, v, _ = forward(model, rec_coords, None, residual, save=True, fw=False)
-    dt = float(model.critical_dt)
-    freqs = np.asarray(freq_list, dtype=np.float64)
-    ts = np.array([t for t in range(1, nt - 1) if t % factor == 0], dtype=np.int64)
-    g = np.zeros(model.shape_pml, dtype=np.float64)
-    for fk in freqs:
-        ph = np.exp(-1j * 2 * np.pi * fk * ts * dt)
-        w = -(2 * np.pi * fk) ** 2 / (nt - 2)
-        for fld in range(model.nfields):
-            uf = factor * np.tensordot(ph, u[ts, fld].astype(np.float64), axes=(0, 0))
-            g -= w * np.tensordot(np.conj(ph), v[ts, fld].astype(np.float64), axes=(0, 0)).real * uf.real \
-                - w * np.tensordot(np.conj(ph), v[ts, fld].astype(np.float64), axes=(0, 0)).imag * uf.imag
+    g = dft_gradient(u, v, float(model.critical_dt), freq_list, dft_sub)
     g = g.astype(model.lib._dtype)
     if return_obj:
         return f, g

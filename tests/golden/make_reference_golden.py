@@ -25,6 +25,12 @@ replaced by an import stub that only provides symbols (no semantics of its own b
     the receivers interpolate, with PointSource / Receiver replaced by capturing symbols;
     sources.RickerSource.wavelet and sources.TimeAxis on numpy   (geom_utils.py:31-96, sources.py:11-176)
 
+  * fields_exprs.otf_dft and sensitivity.grad_expr -> crosscorr_freq: the on-the-fly DFT of the
+    forward wavefield and the frequency-domain imaging condition, evaluated on random time series
+    of one grid point (ConditionalDimension(factor=k): tsave = time / k on the steps with
+    time % k == 0, [dv]; the complex right-hand side stored into the real gradm keeps its real part, [dv])
+    (fields_exprs.py:140-169, 195-212, sensitivity.py:27-52, 72-104)
+
 Run from the repository root (needs /root/reference):  python tests/golden/make_reference_golden.py
 Output: tests/golden/reference_golden.json (committed; the tests never read /root/reference).
 """
@@ -583,6 +589,78 @@ def main():
             entry["wavelet"] = [float(x) for x in np.round(w[:160], 12)]
         rick.append(entry)
     out["cases"]["ricker"] = rick
+
+    # ---- 10. on-the-fly DFT and the frequency-domain imaging condition ---------------------------------
+    import fields_exprs
+
+    class TimeDim(sp.Symbol):
+        def __new__(cls, name):
+            obj = sp.Symbol.__new__(cls, name, integer=True)
+            obj.spacing = sp.Symbol("dt")
+            obj.symbolic_max = sp.Symbol("time_M")
+            return obj
+
+    class Mode(sp.Symbol):
+        """A DFT mode uf[freq_dim, x, ...]: indexing gives something with `.dimensions`."""
+        def __getitem__(self, i):
+            return types.SimpleNamespace(dimensions=(sp.Symbol("freq_dim"),))
+
+    time = TimeDim("time")
+    fields_exprs.ConditionalDimension = lambda name=None, parent=None, factor=None: sp.Symbol("tsave", integer=True)
+    fields_exprs.Inc = lambda *a, **k: ("Inc",) + a
+    fields_exprs.exp = sp.exp
+    sensitivity.exp = sp.exp
+    sensitivity.Eq = lambda *a, **k: ("Eq",) + a
+    fsym = sp.Symbol("f")
+    sensitivity.frequencies = lambda freq, fdim=None: (fsym, len(freq))
+    dfts = []
+    for nfld in (1, 2):
+        for factor in (None, 1, 2, 3):
+            us = tuple(Field("u%d" % (i_ + 1)) for i_ in range(nfld))
+            for u_ in us:
+                u_.grid = types.SimpleNamespace(time_dim=time)
+            modes = tuple(Mode("uf%d" % (i_ + 1)) for i_ in range(nfld))
+            fields_exprs.fourier_modes = lambda u, freq, _m=modes: (_m, fsym)
+            freqs = [0.004, 0.011]
+            fwd = fields_exprs.otf_dft(us, freqs, sp.Symbol("dt"), factor=factor)
+            assert len(fwd) == nfld and all(e[0] == "Inc" and e[1] == m_ for e, m_ in zip(fwd, modes))
+            model = types.SimpleNamespace(grid=types.SimpleNamespace(time_dim=time), physical=None)
+            vs = tuple(Field("v%d" % (i_ + 1)) for i_ in range(nfld))
+            gradm = sp.Symbol("gradm")
+            (eq,) = sensitivity.grad_expr(gradm, modes, vs, model, w=None, freq=freqs, dft_sub=factor, ic="as")
+            assert eq[0] == "Eq" and eq[1] == gradm
+            rhs = eq[2]
+            names = sorted(s_.name for s_ in rhs.free_symbols)
+            # evaluate both on random time series of one grid point
+            nt, dtv = 14, 1.75
+            useries = rng.standard_normal((nt, nfld))
+            vseries = rng.standard_normal((nt, nfld))
+            k = factor or 1
+            uf = np.zeros((len(freqs), nfld), dtype=np.complex128)
+            for t in range(1, nt - 1):
+                if t % k:
+                    continue
+                for qi, fv in enumerate(freqs):
+                    for fi in range(nfld):
+                        e = fwd[fi][2]
+                        sub = {fsym: sp.Float(fv), sp.Symbol("dt"): sp.Float(dtv), us[fi]: sp.Float(useries[t, fi]),
+                               time: sp.Integer(t), sp.Symbol("tsave", integer=True): sp.Integer(t // k)}
+                        uf[qi, fi] += complex(e.xreplace(sub))
+            g = 0.0
+            for t in range(nt - 2, 0, -1):
+                for qi, fv in enumerate(freqs):
+                    sub = {fsym: sp.Float(fv), sp.Symbol("dt"): sp.Float(dtv), time: sp.Integer(t),
+                           sp.Symbol("tsave", integer=True): sp.Integer(t // k),
+                           sp.Symbol("time_M"): sp.Integer(nt - 2), gradm: sp.Float(0)}
+                    for fi in range(nfld):
+                        sub[modes[fi]] = sp.sympify(complex(uf[qi, fi]))
+                        sub[vs[fi]] = sp.Float(vseries[t, fi])
+                    g += complex(rhs.xreplace(sub)).real
+            dfts.append(dict(nfields=nfld, dft_sub=factor, freqs=freqs, nt=nt, dt=dtv,
+                             forward_symbols=sorted(s_.name for s_ in fwd[0][2].free_symbols),
+                             gradient_symbols=names, u=useries.tolist(), v=vseries.tolist(),
+                             uf_re=uf.real.tolist(), uf_im=uf.imag.tolist(), gradm=g))
+    out["cases"]["dft"] = dfts
 
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:

@@ -245,6 +245,20 @@ def test_ricker_wavelet_and_time_axis(c):
     assert np.abs(w - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("i", range(len(GOLD["dft"])))
+def test_on_the_fly_dft_and_frequency_imaging_condition(i):
+    """fields_exprs.otf_dft + sensitivity.grad_expr / crosscorr_freq executed on the time series
+    of one grid point: the forward DFT is subsampled by dft_sub (and scaled by it); the adjoint
+    correlation runs over `time`, never `tsave` -- every step, whatever dft_sub is."""
+    c = GOLD["dft"][i]
+    assert "tsave" not in c["gradient_symbols"] and "time" in c["gradient_symbols"]
+    assert ("tsave" in c["forward_symbols"]) == bool(c["dft_sub"] and c["dft_sub"] > 1)
+    u = np.asarray(c["u"])[:, :, None]
+    v = np.asarray(c["v"])[:, :, None]
+    g = O.dft_gradient(u, v, c["dt"], c["freqs"], c["dft_sub"])
+    assert np.isclose(g[0], c["gradm"], rtol=1e-10, atol=1e-14)
+
+
 def _damp_model_kw(c):
     n = tuple(c["shape"])
     return dict(origin=(0.,) * c["ndim"], spacing=tuple(c["spacing"]), shape=n, space_order=8,
