@@ -123,6 +123,11 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
     const long long gtid = (long long)lb * blockDim.x + threadIdx.x;
     const long long gthreads = (long long)nb * blockDim.x;
     int cur = a.cur;
+    // snapshot phase and slot offset of time index t, advanced step by step (no division in the loop)
+    int ph = (a.t0 - a.t_base) % a.t_sub;
+    long long sidx = (long long)((a.t0 - a.t_base) / a.t_sub) * a.slot;
+    // grid coordinates of this thread's first tile (the only one when the grid has a CTA per tile)
+    const int x0 = (lb % ntx) * TX + tx, z0 = (lb / ntx) * TZ + tz;
     for (int t = a.t0;; t += a.dir) {
         const float *uc = a.b[cur];
         float *un = a.b[1 - cur];
@@ -144,14 +149,17 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
             a.rec[(long long)t * a.nrec + p] = acc;
             if (a.rec_bg) a.rec_bg[(long long)t * a.nrec + p] = acc2;
         }
-        const bool fused_t = ((t - a.t_base) % a.t_sub) == 0;
-        const long long sidx = (long long)((t - a.t_base) / a.t_sub) * a.slot;
+        const bool fused_t = ph == 0;
         float *snap_t = (a.snap && fused_t) ? a.snap + sidx : nullptr;
         const float *usnap_t = (a.grad && fused_t) ? a.usnap + sidx : nullptr;
         const float *src_row = a.src ? a.src + (long long)t * a.nsrc : nullptr;
+        if (a.dir > 0) { if (++ph == a.t_sub) { ph = 0; sidx += a.slot; } }
+        else if (ph == 0) { ph = a.t_sub - 1; sidx -= a.slot; }
+        else ph--;
         // ---- stencil + injection + fused extras, tile by tile --------------------------------
         for (int tile = lb; tile < ntiles; tile += nb) {
-            const int x = (tile % ntx) * TX + tx, z = (tile / ntx) * TZ + tz;
+            int x = x0, z = z0;
+            if (tile != lb) { x = (tile % ntx) * TX + tx; z = (tile / ntx) * TZ + tz; }
             if (x >= g.n[0] || z >= g.n[2]) continue;
             const long long i = g.at(x, 0, z);
             const float ucv = uc[i];
@@ -205,7 +213,7 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
 }
 
 template <int R, bool XIC>
-__global__ void __launch_bounds__(256) acoustic2d_persist(P2Args a)
+__global__ void __launch_bounds__(256, XIC ? 2 : 4) acoustic2d_persist(P2Args a)
 {
     acoustic2d_body<R, XIC>(a, blockIdx.x, gridDim.x);
 }
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(256) acoustic2d_persist(P2Args a)
 // Several shots of the same model and time axis in lockstep: CTA b works on shot b / per_shot.
 // One grid barrier per time step serves all of them (judi_fg_multishot on small 2-D grids).
 template <int R, bool XIC>
-__global__ void __launch_bounds__(256) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
+__global__ void __launch_bounds__(256, XIC ? 2 : 4) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
 {
     // the shot's arguments go to shared memory once: read through the global pointer, every stencil
     // coefficient would be a load from L1/L2 instead of a constant-bank operand
