@@ -99,7 +99,8 @@ typedef struct {
     /* on-the-fly DFT gradient (J_adjoint_freq, interface.py:348-408): nfreq > 0 replaces the
      * wavefield snapshots by nfreq complex frequency slices accumulated every dft_sub steps
      * (fields_exprs.py:140-169) and the imaging condition by sensitivity.py:72-104, which the
-     * reference applies on every adjoint step whatever dft_sub is (grad_expr, sensitivity.py:50).
+     * reference applies on every adjoint step whatever dft_sub is (grad_expr, sensitivity.py:50);
+     * with ic = isic / fwi by sensitivity.py:125-154, applied every dft_sub steps.
      * freq_list: host array of nfreq frequencies in kHz. */
     int nfreq;
     int dft_sub;       /* DFT time subsampling factor (>= 1) */

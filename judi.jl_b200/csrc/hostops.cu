@@ -245,3 +245,75 @@ void dft_gradient(const judi_model *M, const Region &reg, const float *v, const 
                                                                              wc_dev, grad);
     launch_count(M->ctx, "dft_grad");
 }
+
+// isic / fwi in the frequency domain (sensitivity.py:125-154), on the steps with t % factor == 0:
+//   gradm -= Re( w_f U v m - w2 inner_grad(U, v) ),  U = uf e^{i w t},  w2 = +-factor / time_M.
+// Pass 1: gradm -= m v sum_f w_f Re(U_f) and B = sum_f Re(U_f) (w2 does not depend on f);
+// pass 2: gradm += w2 inner_grad(B, v) with B read through its region (zero outside).
+// ec: [nfreq][2] = (cos wt, -sin wt).
+__global__ void dft_grad_isic1_kernel(Grid g, Region reg, const float *__restrict__ v,
+                                      const float *__restrict__ m, const float *__restrict__ uf, int nfreq,
+                                      const float *__restrict__ wc, const float *__restrict__ ec,
+                                      float *__restrict__ B, float *__restrict__ grad)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
+    const long long t = i / reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long ri = reg.at(x, y, z), gi = g.at(x, y, z);
+    float aw = 0.f, ab = 0.f;
+    for (int k = 0; k < nfreq; k++) {
+        const float *p = uf + (size_t)(2 * k) * reg.slot + ri;
+        const float re = p[0], im = p[reg.slot];
+        aw = __fmaf_rn(wc[2 * k], re, aw);
+        aw = __fmaf_rn(wc[2 * k + 1], im, aw);
+        ab = __fmaf_rn(ec[2 * k], re, ab);
+        ab = __fmaf_rn(ec[2 * k + 1], im, ab);
+    }
+    B[ri] = ab;
+    grad[ri] = __fmaf_rn(-aw * m[gi], v[gi], grad[ri]);
+}
+
+__global__ void dft_grad_isic2_kernel(Grid g, Coefs cf, int R, int ndim, Region reg,
+                                      const float *__restrict__ v, const float *__restrict__ B, float w2,
+                                      float *__restrict__ grad)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
+    const long long t = i / reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long gi = g.at(x, y, z);
+    const long long st[3] = {1, g.sy, g.sz};
+    const float *ws[3] = {cf.wx, cf.wy, cf.wz};
+    float s = 0.f;
+    for (int d = 0; d < 3; d++) {
+        if (d == 1 && ndim == 2) continue;
+        float gb = 0.f, gv = 0.f;
+        for (int k = 1; k <= R; k++) {
+            int p[3] = {x, y, z}, q[3] = {x, y, z};
+            p[d] += k; q[d] -= k - 1;
+            const float bp = reg.has(p[0], p[1], p[2]) ? B[reg.at(p[0], p[1], p[2])] : 0.f;
+            const float bm = reg.has(q[0], q[1], q[2]) ? B[reg.at(q[0], q[1], q[2])] : 0.f;
+            gb += ws[d][k] * (bp - bm);
+            gv += ws[d][k] * (v[gi + k * st[d]] - v[gi - (k - 1) * st[d]]);
+        }
+        s += gb * gv;
+    }
+    const long long ri = reg.at(x, y, z);
+    grad[ri] = __fmaf_rn(w2, s, grad[ri]);
+}
+
+void dft_gradient_isic(const judi_model *M, const Region &reg, const float *v, const float *uf, int nfreq,
+                       const float *wc_dev, const float *ec_dev, float w2, float *B, float *grad)
+{
+    const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    dft_grad_isic1_kernel<<<nb, 256, 0, M->ctx->stream>>>(M->g, reg, v, M->m.p, uf, nfreq, wc_dev, ec_dev, B, grad);
+    launch_count(M->ctx, "dft_grad_isic1");
+    dft_grad_isic2_kernel<<<nb, 256, 0, M->ctx->stream>>>(M->g, M->cf, M->r, M->ndim, reg, v, B, w2, grad);
+    launch_count(M->ctx, "dft_grad_isic2");
+}

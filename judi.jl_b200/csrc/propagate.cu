@@ -665,7 +665,6 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     const int dfac = std::max(o->dft_sub, 1);
     if (dft) {
         JUDI_REQUIRE(o->freq_list != nullptr, "freq_list is NULL");
-        JUDI_REQUIRE(o->ic == JUDI_IC_AS, "DFT gradients are implemented for the 'as' imaging condition");
         JUDI_REQUIRE(!o->checkpointing, "DFT gradients do not use checkpointing");
     }
     // ISIC/FWI differentiate the snapshot: it must cover the whole padded grid
@@ -749,11 +748,14 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     //   gradient (sensitivity.py:94-103):   gradm -= w_f Re(uf exp(i w t)) v[t],  w_f = -(2 pi f)^2 / time_M
     // on EVERY step: grad_expr passes dft_sub to the imaging condition as `factor=` (sensitivity.py:50),
     // a keyword crosscorr_freq does not have, so the adjoint correlation is never subsampled.
-    DevBuf uf, cs_tab, wc_tab;
+    // isic_freq / fwi_freq (sensitivity.py:125-154) do read it: they run when t % factor == 0, with
+    // gradm -= Re(w_f U v m - w2 inner_grad(U, v)),  U = uf e^{i w t},  w2 = +-factor / time_M.
+    DevBuf uf, cs_tab, wc_tab, ec_tab, dftB;
+    const float dft_w2 = (o->ic == JUDI_IC_FWI ? -1.f : 1.f) * (float)dfac / (float)(nt - 2);
     const int ndft = dft ? (nt / dfac + 1) : 0;
     if (dft) {
         uf = DevBuf(ctx, (size_t)2 * o->nfreq * slot_floats, true);
-        std::vector<float> cs((size_t)ndft * 2 * o->nfreq), wc((size_t)nt * 2 * o->nfreq);
+        std::vector<float> cs((size_t)ndft * 2 * o->nfreq), wc((size_t)nt * 2 * o->nfreq), ec(wc.size());
         for (int q_ = 0; q_ < o->nfreq; q_++) {
             const double f = (double)o->freq_list[q_];
             const double w = -(2.0 * M_PI * f) * (2.0 * M_PI * f) / (double)(nt - 2);
@@ -766,12 +768,19 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                 const double wt = 2.0 * M_PI * f * (double)t * (double)M->dt;
                 wc[((size_t)t * o->nfreq + q_) * 2] = (float)(w * std::cos(wt));
                 wc[((size_t)t * o->nfreq + q_) * 2 + 1] = (float)(-w * std::sin(wt));
+                ec[((size_t)t * o->nfreq + q_) * 2] = (float)std::cos(wt);
+                ec[((size_t)t * o->nfreq + q_) * 2 + 1] = (float)(-std::sin(wt));
             }
         }
         cs_tab = DevBuf(ctx, cs.size(), false);
         cs_tab.upload(cs);
         wc_tab = DevBuf(ctx, wc.size(), false);
         wc_tab.upload(wc);
+        if (o->ic != JUDI_IC_AS) {
+            ec_tab = DevBuf(ctx, ec.size(), false);
+            ec_tab.upload(ec);
+            dftB = DevBuf(ctx, (size_t)reg.slot, false);
+        }
     }
     auto uf_ptr = [&](int f) { return uf.p + (size_t)f * 2 * o->nfreq * reg.slot; };
 
@@ -941,10 +950,15 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         }
         for (int t = ta; t >= tb; t--) {
             adj_step(t, dft ? -1 : (mode == 1 ? ((t % k) == 0 ? t / k : -1) : t - base));
-            if (dft)
+            if (dft && o->ic == JUDI_IC_AS)
                 for (int ff = 0; ff < nf; ff++)
                     dft_gradient(M, reg, V.other(ff), uf_ptr(ff), o->nfreq,
                                  wc_tab.p + (size_t)t * 2 * o->nfreq, grad.p);
+            else if (dft && (t % dfac) == 0)
+                for (int ff = 0; ff < nf; ff++)
+                    dft_gradient_isic(M, reg, V.other(ff), uf_ptr(ff), o->nfreq,
+                                      wc_tab.p + (size_t)t * 2 * o->nfreq, ec_tab.p + (size_t)t * 2 * o->nfreq,
+                                      dft_w2, dftB.p, grad.p);
         }
     };
     if (!o->checkpointing) {

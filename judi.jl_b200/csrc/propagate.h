@@ -96,3 +96,5 @@ void dft_accumulate(const judi_model *M, const Region &reg, const float *u, floa
                     const float *cs_dev);
 void dft_gradient(const judi_model *M, const Region &reg, const float *v, const float *uf, int nfreq,
                   const float *wc_dev, float *grad);
+void dft_gradient_isic(const judi_model *M, const Region &reg, const float *v, const float *uf, int nfreq,
+                       const float *wc_dev, const float *ec_dev, float w2, float *B, float *grad);

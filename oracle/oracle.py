@@ -657,45 +657,86 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     return g, Iu, Iv
 
 
-def dft_gradient(u, v, dt, freq_list, factor=1):
+def inner_grad_np(model):
+    """sensitivity.py:212-223 on padded-grid arrays: sum_d D+_d a * D+_d b, D+ the staggered first
+    derivative at +1/2 (zero outside the padded grid: Devito's halo), combined point by point."""
+    _, w1 = fd_weights(model)
+    r = len(w1)
+
+    def dplus(a, ax):
+        pad = [(0, 0)] * a.ndim
+        pad[ax] = (r, r)
+        ap = np.pad(a, pad)
+        n = a.shape[ax]
+        out = np.zeros_like(a, dtype=np.float64)
+        for k in range(1, r + 1):
+            hi = [slice(None)] * a.ndim
+            lo = [slice(None)] * a.ndim
+            hi[ax] = slice(r + k, r + k + n)
+            lo[ax] = slice(r - (k - 1), r - (k - 1) + n)
+            out += w1[k - 1] * (ap[tuple(hi)] - ap[tuple(lo)])
+        return out / float(model.spacing[ax])
+
+    def inner(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return sum(dplus(a, ax) * dplus(b, ax) for ax in range(a.ndim))
+    return inner
+
+
+def dft_gradient(u, v, dt, freq_list, factor=1, ic="as", m=None, inner_grad=None):
     """On-the-fly DFT gradient from wavefield histories u, v of shape (nt, nfields, ...):
       forward  fields_exprs.py:140-169:  uf[f] = sum_{t=1, t % factor == 0}^{nt-2}
                                                  factor * exp(-i 2 pi f t dt) * u[t]
-      gradient sensitivity.py:72-104:    gradm -= w_f * Re(uf[f] exp(i 2 pi f t dt) v[t]) for EVERY
+      "as"     sensitivity.py:72-104:    gradm -= w_f * Re(uf[f] exp(i 2 pi f t dt) v[t]) for EVERY
                t = nt-2 .. 1, w_f = -(2 pi f)^2 / time_M, time_M = nt - 2, summed over frequencies
                and over the field pairs (u_i, v_i) of TTI.  grad_expr hands dft_sub to the imaging
                condition as `factor=` (sensitivity.py:50), which crosscorr_freq's signature does
-               not take: its own dft_sub stays None and the correlation is never subsampled
-               (tests/golden/make_reference_golden.py section 10 executes exactly this).
-    The complex product is stored into the real `gradm`, i.e. its real part is kept."""
+               not take: its own dft_sub stays None and the correlation is never subsampled.
+      "isic" / "fwi"  sensitivity.py:125-154:  gradm -= Re( w_f U v m - w2 inner_grad(U, v) ),
+               U = uf[f] exp(i 2 pi f t dt), w2 = +-factor / time_M; isic_freq does read `factor`:
+               these run on the steps with t % factor == 0 only.
+      (tests/golden/make_reference_golden.py section 10 executes exactly these functions.)
+    The complex product is stored into the real `gradm`, i.e. its real part is kept.
+    m: padded-grid m (isic / fwi); inner_grad(a, b): the bilinear form of sensitivity.py:212-223."""
     nt = u.shape[0]
     factor = int(factor) if factor else 1
     tf = np.array([t for t in range(1, nt - 1) if t % factor == 0], dtype=np.int64)
-    ta = np.arange(1, nt - 1, dtype=np.int64)
+    ta = np.arange(1, nt - 1, dtype=np.int64) if ic == "as" else tf
+    ics = {"as": 0.0, "isic": 1.0, "fwi": -1.0}[ic]
     g = np.zeros(u.shape[2:], dtype=np.float64)
     for fk in np.asarray(freq_list, dtype=np.float64):
         phf = np.exp(-1j * 2 * np.pi * fk * tf * dt)
-        pha = np.exp(1j * 2 * np.pi * fk * ta * dt)
         w = -(2 * np.pi * fk) ** 2 / (nt - 2)
+        w2 = ics * factor / (nt - 2)
         for fld in range(u.shape[1]):
             uf = factor * np.tensordot(phf, u[tf, fld].astype(np.float64), axes=(0, 0))
-            vf = np.tensordot(pha, v[ta, fld].astype(np.float64), axes=(0, 0))
-            g -= w * (uf * vf).real
+            if ic == "as":
+                pha = np.exp(1j * 2 * np.pi * fk * ta * dt)
+                vf = np.tensordot(pha, v[ta, fld].astype(np.float64), axes=(0, 0))
+                g -= w * (uf * vf).real
+                continue
+            for t in ta:
+                U = uf * np.exp(1j * 2 * np.pi * fk * t * dt)
+                vt = v[t, fld].astype(np.float64)
+                g -= w * U.real * vt * m - w2 * inner_grad(U.real, vt)
     return g
 
 
 def J_adjoint_freq(model, src_coords, wavelet, rec_coords, recin, freq_list, dft_sub=None,
-                   is_residual=False, return_obj=False, born_fwd=False, nlind=False, misfit=None):
+                   is_residual=False, return_obj=False, born_fwd=False, nlind=False, misfit=None,
+                   ic="as"):
     """interface.py:348-408 (on-the-fly DFT gradient), evaluated from the stored wavefield
     histories instead of on the fly (small cases only), see dft_gradient."""
     if born_fwd:
-        rec, u, _ = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind)
+        rec, u, _ = born(model, src_coords, rec_coords, wavelet, save=True, nlind=nlind, ic=ic)
     else:
         rec, u, _ = forward(model, src_coords, rec_coords, wavelet, save=True)
     f, residual = Loss(rec, recin, float(model.critical_dt), is_residual=is_residual,
                        misfit=misfit)
     _, v, _ = forward(model, rec_coords, None, residual, save=True, fw=False)
-    g = dft_gradient(u, v, float(model.critical_dt), freq_list, dft_sub)
+    g = dft_gradient(u, v, float(model.critical_dt), freq_list, dft_sub, ic=ic,
+                     m=model.m.astype(np.float64) if ic != "as" else None,
+                     inner_grad=inner_grad_np(model) if ic != "as" else None)
     g = g.astype(model.lib._dtype)
     if return_obj:
         return f, g

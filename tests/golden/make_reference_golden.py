@@ -614,7 +614,12 @@ def main():
     fsym = sp.Symbol("f")
     sensitivity.frequencies = lambda freq, fdim=None: (fsym, len(freq))
     dfts = []
-    for nfld in (1, 2):
+    kappa = sp.Symbol("kappa")
+    # inner_grad(a, b) = grad(a).grad(b) is bilinear: a stand-in kappa * a * b keeps every factor visible
+    sensitivity.inner_grad = lambda a_, b_: kappa * a_ * b_
+    tsave_sym = sp.Symbol("tsave", integer=True)
+    for ic_name in ("as", "isic", "fwi"):
+      for nfld in (1, 2):
         for factor in (None, 1, 2, 3):
             us = tuple(Field("u%d" % (i_ + 1)) for i_ in range(nfld))
             for u_ in us:
@@ -624,15 +629,17 @@ def main():
             freqs = [0.004, 0.011]
             fwd = fields_exprs.otf_dft(us, freqs, sp.Symbol("dt"), factor=factor)
             assert len(fwd) == nfld and all(e[0] == "Inc" and e[1] == m_ for e, m_ in zip(fwd, modes))
-            model = types.SimpleNamespace(grid=types.SimpleNamespace(time_dim=time), physical=None)
+            model = types.SimpleNamespace(grid=types.SimpleNamespace(time_dim=time), physical=None,
+                                          m=sp.Symbol("m"), irho=sp.Symbol("b"))
             vs = tuple(Field("v%d" % (i_ + 1)) for i_ in range(nfld))
             gradm = sp.Symbol("gradm")
-            (eq,) = sensitivity.grad_expr(gradm, modes, vs, model, w=None, freq=freqs, dft_sub=factor, ic="as")
+            (eq,) = sensitivity.grad_expr(gradm, modes, vs, model, w=None, freq=freqs, dft_sub=factor, ic=ic_name)
             assert eq[0] == "Eq" and eq[1] == gradm
             rhs = eq[2]
             names = sorted(s_.name for s_ in rhs.free_symbols)
             # evaluate both on random time series of one grid point
             nt, dtv = 14, 1.75
+            mv, kv = float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.2, 2.0))
             useries = rng.standard_normal((nt, nfld))
             vseries = rng.standard_normal((nt, nfld))
             k = factor or 1
@@ -644,19 +651,23 @@ def main():
                     for fi in range(nfld):
                         e = fwd[fi][2]
                         sub = {fsym: sp.Float(fv), sp.Symbol("dt"): sp.Float(dtv), us[fi]: sp.Float(useries[t, fi]),
-                               time: sp.Integer(t), sp.Symbol("tsave", integer=True): sp.Integer(t // k)}
+                               time: sp.Integer(t), tsave_sym: sp.Integer(t // k)}
                         uf[qi, fi] += complex(e.xreplace(sub))
+            # an equation that mentions the conditional dimension runs on its steps only [dv]
+            gk = k if tsave_sym in rhs.free_symbols else 1
             g = 0.0
             for t in range(nt - 2, 0, -1):
+                if t % gk:
+                    continue
                 for qi, fv in enumerate(freqs):
                     sub = {fsym: sp.Float(fv), sp.Symbol("dt"): sp.Float(dtv), time: sp.Integer(t),
-                           sp.Symbol("tsave", integer=True): sp.Integer(t // k),
-                           sp.Symbol("time_M"): sp.Integer(nt - 2), gradm: sp.Float(0)}
+                           tsave_sym: sp.Integer(t // gk), sp.Symbol("time_M"): sp.Integer(nt - 2),
+                           gradm: sp.Float(0), sp.Symbol("m"): sp.Float(mv), kappa: sp.Float(kv)}
                     for fi in range(nfld):
                         sub[modes[fi]] = sp.sympify(complex(uf[qi, fi]))
                         sub[vs[fi]] = sp.Float(vseries[t, fi])
                     g += complex(rhs.xreplace(sub)).real
-            dfts.append(dict(nfields=nfld, dft_sub=factor, freqs=freqs, nt=nt, dt=dtv,
+            dfts.append(dict(ic=ic_name, nfields=nfld, dft_sub=factor, freqs=freqs, nt=nt, dt=dtv, m=mv, kappa=kv,
                              forward_symbols=sorted(s_.name for s_ in fwd[0][2].free_symbols),
                              gradient_symbols=names, u=useries.tolist(), v=vseries.tolist(),
                              uf_re=uf.real.tolist(), uf_im=uf.imag.tolist(), gradm=g))

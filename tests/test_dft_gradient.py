@@ -82,10 +82,51 @@ def test_dft_gradient_parity(kind, ndim, dft_sub):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,ndim,dft_sub", [("iso", 2, None), ("iso", 2, 3), ("iso", 3, 2), ("tti", 2, 2),
+                                               ("rho", 2, None), ("tti", 3, None), ("visco", 2, 2)])
+@pytest.mark.parametrize("ic", ["isic", "fwi"])
+def test_dft_gradient_isic_fwi_parity(kind, ndim, dft_sub, ic):
+    """test_all_options.jl:133-172: IC="isic" / "fwi" together with frequencies -- isic_freq /
+    fwi_freq (sensitivity.py:125-154), which subsample the adjoint correlation by dft_sub."""
+    import judi_jl_b200 as J
+    args, om, src, rec, q, dt = _setup(kind, ndim, with_dm=True)
+    gm = J.Model(**args)
+    do, _ = O.forward_rec(om, src, q, rec)
+    dobs = (0.9 * do).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, freq_list=FREQS, dft_sub=dft_sub, ic=ic)
+    fo, go = O.J_adjoint_freq(om, src, q, rec, dobs, FREQS, dft_sub=dft_sub, return_obj=True, ic=ic)
+    assert np.isfinite(g).all() and np.linalg.norm(go) > 0
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, go) < 1e-3                                 # north-star gradient tolerance
+    ga, _, _ = J.J_adjoint(gm, src, q, rec, dobs, freq_list=FREQS, dft_sub=dft_sub)
+    assert rel_l2(g, ga) > 1e-2                                 # and it is not the "as" gradient
+
+
+@pytest.mark.gpu
 def test_dft_options_fail_loudly():
     import judi_jl_b200 as J
     args, om, src, rec, q, dt = _setup("iso", 2, with_dm=False)
     gm = J.Model(**args)
     y = np.zeros((NT, rec.shape[0]), np.float32)
-    with pytest.raises(J.JudiB200Error, match="imaging condition"):
-        J.J_adjoint(gm, src, q, rec, y, is_residual=True, freq_list=FREQS, ic="isic")
+    with pytest.raises(J.JudiB200Error, match="checkpointing"):
+        J.J_adjoint(gm, src, q, rec, y, is_residual=True, freq_list=FREQS, checkpointing=True)
+
+
+def test_numpy_inner_grad_is_the_c_loops_inner_grad():
+    """The numpy inner_grad of the frequency-domain conditions against the C oracle's time-domain
+    isic gradient, rebuilt from the wavefield histories: gradm -= dt irho (u v.dt2 m + inner_grad(u, v))."""
+    args, om, src, rec, q, dt = _setup("iso", 2, with_dm=False, n=(31, 27), nbl=6)
+    om = O.Model(precision="f64", **args)
+    nt = 60
+    q = q[:nt]
+    do, u, _ = O.forward(om, src, rec, q, save=True)
+    y = 0.1 * do
+    g, _, _ = O.J_adjoint(om, src, q, rec, y, is_residual=True, ic="isic")
+    _, v, _ = O.forward(om, rec, None, y, save=True, fw=False)
+    inner = O.inner_grad_np(om)
+    m = om.m.astype(np.float64)
+    ref = np.zeros(om.shape_pml)
+    for t in range(1, nt - 1):
+        vdt2 = (v[t + 1, 0] - 2 * v[t, 0] + v[t - 1, 0]) / dt ** 2
+        ref -= dt * om.irho_const * (u[t, 0] * vdt2 * m + inner(u[t, 0], v[t, 0]))
+    assert rel_l2(ref, g) < 1e-12

@@ -247,15 +247,19 @@ def test_ricker_wavelet_and_time_axis(c):
 
 @pytest.mark.parametrize("i", range(len(GOLD["dft"])))
 def test_on_the_fly_dft_and_frequency_imaging_condition(i):
-    """fields_exprs.otf_dft + sensitivity.grad_expr / crosscorr_freq executed on the time series
-    of one grid point: the forward DFT is subsampled by dft_sub (and scaled by it); the adjoint
-    correlation runs over `time`, never `tsave` -- every step, whatever dft_sub is."""
+    """fields_exprs.otf_dft + sensitivity.grad_expr -> crosscorr_freq / isic_freq / fwi_freq executed
+    on the time series of one grid point: the forward DFT is subsampled by dft_sub (and scaled by
+    it); the "as" correlation runs over `time`, never `tsave` -- every step, whatever dft_sub
+    is -- while isic_freq / fwi_freq do read `factor` and run on the subsampled steps, with
+    w2 = +-factor / time_M on the inner_grad term (a bilinear stand-in kappa * a * b in the vectors)."""
     c = GOLD["dft"][i]
-    assert "tsave" not in c["gradient_symbols"] and "time" in c["gradient_symbols"]
-    assert ("tsave" in c["forward_symbols"]) == bool(c["dft_sub"] and c["dft_sub"] > 1)
+    sub = bool(c["dft_sub"] and c["dft_sub"] > 1)
+    assert ("tsave" in c["forward_symbols"]) == sub
+    assert ("tsave" in c["gradient_symbols"]) == (sub and c["ic"] != "as")
     u = np.asarray(c["u"])[:, :, None]
     v = np.asarray(c["v"])[:, :, None]
-    g = O.dft_gradient(u, v, c["dt"], c["freqs"], c["dft_sub"])
+    g = O.dft_gradient(u, v, c["dt"], c["freqs"], c["dft_sub"], ic=c["ic"], m=c["m"],
+                       inner_grad=lambda a, b: c["kappa"] * a * b)
     assert np.isclose(g[0], c["gradm"], rtol=1e-10, atol=1e-14)
 
 
