@@ -661,11 +661,11 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     const int nf = M->tti ? 2 : 1;
     const int k = o->checkpointing ? 1 : o->t_sub;
     // on-the-fly DFT (J_adjoint_freq, interface.py:348-408): frequency slices instead of snapshots
-    const bool dft = o->nfreq > 0;
+    // checkpointing wins over frequencies, as in the reference's dispatch (interface.py:331-345)
+    const bool dft = o->nfreq > 0 && !o->checkpointing;
     const int dfac = std::max(o->dft_sub, 1);
     if (dft) {
         JUDI_REQUIRE(o->freq_list != nullptr, "freq_list is NULL");
-        JUDI_REQUIRE(!o->checkpointing, "DFT gradients do not use checkpointing");
     }
     // ISIC/FWI differentiate the snapshot: it must cover the whole padded grid
     const Region reg = (o->snapshot_region == JUDI_SNAP_PHYSICAL && o->ic == JUDI_IC_AS)

@@ -402,6 +402,15 @@ def main():
         else:
             f, r = sensitivity.Loss(Rec(dsyn), dobs, dt, is_residual=(mode == "is_residual"))
         loss.append(dict(mode=mode, dt=dt, f=float(f), residual=np.asarray(r, dtype=np.float64).tolist()))
+    # user misfit (sensitivity.py:255-263): f scaled by dt, residual as returned; with the
+    # (background, linearised) tuple the callback sees dsyn[0] and dobs - dsyn[1]
+    l1 = lambda a_, b_: (float(np.sum(np.abs(a_ - b_))), np.sign(a_ - b_).astype(np.float32))
+    for mode in ("misfit", "misfit_nlind"):
+        if mode == "misfit_nlind":
+            f, r = sensitivity.Loss((Rec(dsyn), Rec(dlin)), dobs, dt, misfit=l1)
+        else:
+            f, r = sensitivity.Loss(Rec(dsyn), dobs, dt, misfit=l1)
+        loss.append(dict(mode=mode, dt=dt, f=float(f), residual=np.asarray(r, dtype=np.float64).tolist()))
     out["cases"]["loss"] = dict(dsyn=dsyn.tolist(), dlin=dlin.tolist(), dobs=dobs.tolist(), results=loss)
 
     # ---- 5. number of saved snapshots -------------------------------------------------------------------

@@ -121,8 +121,13 @@ def test_loss(r):
     dsyn = np.asarray(L["dsyn"], dtype=np.float32)
     dlin = np.asarray(L["dlin"], dtype=np.float32)
     dobs = np.asarray(L["dobs"], dtype=np.float32)
+    l1 = lambda a, b: (float(np.sum(np.abs(a - b))), np.sign(a - b).astype(np.float32))
     if r["mode"] == "nlind":
         f, res = O.Loss((dsyn, dlin), dobs, r["dt"])
+    elif r["mode"] == "misfit":
+        f, res = O.Loss(dsyn, dobs, r["dt"], misfit=l1)
+    elif r["mode"] == "misfit_nlind":
+        f, res = O.Loss((dsyn, dlin), dobs, r["dt"], misfit=l1)
     else:
         f, res = O.Loss(dsyn, dobs, r["dt"], is_residual=(r["mode"] == "is_residual"))
     assert float(f) == pytest.approx(r["f"], rel=1e-6)
