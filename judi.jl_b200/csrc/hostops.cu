@@ -189,15 +189,18 @@ void run_time_resample(judi_ctx *ctx, const float *in, int nt_in, int np, float 
 
 // ---- on-the-fly DFT (fields_exprs.py:140-169, sensitivity.py:72-104) ------------------------------
 // uf layout: [field][freq][re, im][region slot].  cs: [nfreq][2] = (factor cos wt, -factor sin wt).
+template <typename I>
 __global__ void dft_accum_kernel(Grid g, Region reg, const float *__restrict__ u,
                                  float *__restrict__ uf, int nfreq, const float *__restrict__ cs)
 {
+    // I = unsigned when the region has fewer than 2^31 points: 32-bit divisions
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
-    const long long t = i / reg.ext[0];
-    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long i64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i64 >= n) return;
+    const I i = (I)i64;
+    const int x = reg.lo[0] + (int)(i % (I)reg.ext[0]);
+    const I t = i / (I)reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % (I)reg.ext[1]), z = reg.lo[2] + (int)(t / (I)reg.ext[1]);
     const float uv = u[g.at(x, y, z)];
     const long long ri = reg.at(x, y, z);
     for (int k = 0; k < nfreq; k++) {
@@ -208,16 +211,19 @@ __global__ void dft_accum_kernel(Grid g, Region reg, const float *__restrict__ u
 }
 
 // gradm -= sum_f w_f Re(uf e^{i w t}) v;   wc: [nfreq][2] = (w_f cos wt, -w_f sin wt)
+template <typename I>
 __global__ void dft_grad_kernel(Grid g, Region reg, const float *__restrict__ v,
                                 const float *__restrict__ uf, int nfreq,
                                 const float *__restrict__ wc, float *__restrict__ grad)
 {
+    // I = unsigned when the region has fewer than 2^31 points: 32-bit divisions
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
-    const long long t = i / reg.ext[0];
-    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long i64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i64 >= n) return;
+    const I i = (I)i64;
+    const int x = reg.lo[0] + (int)(i % (I)reg.ext[0]);
+    const I t = i / (I)reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % (I)reg.ext[1]), z = reg.lo[2] + (int)(t / (I)reg.ext[1]);
     const long long ri = reg.at(x, y, z);
     float acc = 0.f;
     for (int k = 0; k < nfreq; k++) {
@@ -232,8 +238,10 @@ void dft_accumulate(const judi_model *M, const Region &reg, const float *u, floa
                     const float *cs_dev)
 {
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    dft_accum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, u, uf, nfreq,
-                                                                              cs_dev);
+    if (n < (1LL << 31))
+        dft_accum_kernel<unsigned><<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, u, uf, nfreq, cs_dev);
+    else
+        dft_accum_kernel<long long><<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, u, uf, nfreq, cs_dev);
     launch_count(M->ctx, "dft_accum");
 }
 
@@ -241,8 +249,10 @@ void dft_gradient(const judi_model *M, const Region &reg, const float *v, const 
                   const float *wc_dev, float *grad)
 {
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    dft_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, v, uf, nfreq,
-                                                                             wc_dev, grad);
+    if (n < (1LL << 31))
+        dft_grad_kernel<unsigned><<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, v, uf, nfreq, wc_dev, grad);
+    else
+        dft_grad_kernel<long long><<<(unsigned)((n + 255) / 256), 256, 0, M->ctx->stream>>>(M->g, reg, v, uf, nfreq, wc_dev, grad);
     launch_count(M->ctx, "dft_grad");
 }
 
@@ -251,17 +261,20 @@ void dft_gradient(const judi_model *M, const Region &reg, const float *v, const 
 // Pass 1: gradm -= m v sum_f w_f Re(U_f) and B = sum_f Re(U_f) (w2 does not depend on f);
 // pass 2: gradm += w2 inner_grad(B, v) with B read through its region (zero outside).
 // ec: [nfreq][2] = (cos wt, -sin wt).
+template <typename I>
 __global__ void dft_grad_isic1_kernel(Grid g, Region reg, const float *__restrict__ v,
                                       const float *__restrict__ m, const float *__restrict__ uf, int nfreq,
                                       const float *__restrict__ wc, const float *__restrict__ ec,
                                       float *__restrict__ B, float *__restrict__ grad)
 {
+    // I = unsigned when the region has fewer than 2^31 points: 32-bit divisions
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
-    const long long t = i / reg.ext[0];
-    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long i64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i64 >= n) return;
+    const I i = (I)i64;
+    const int x = reg.lo[0] + (int)(i % (I)reg.ext[0]);
+    const I t = i / (I)reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % (I)reg.ext[1]), z = reg.lo[2] + (int)(t / (I)reg.ext[1]);
     const long long ri = reg.at(x, y, z), gi = g.at(x, y, z);
     float aw = 0.f, ab = 0.f;
     for (int k = 0; k < nfreq; k++) {
@@ -276,16 +289,19 @@ __global__ void dft_grad_isic1_kernel(Grid g, Region reg, const float *__restric
     grad[ri] = __fmaf_rn(-aw * m[gi], v[gi], grad[ri]);
 }
 
+template <typename I>
 __global__ void dft_grad_isic2_kernel(Grid g, Coefs cf, int R, int ndim, Region reg,
                                       const float *__restrict__ v, const float *__restrict__ B, float w2,
                                       float *__restrict__ grad)
 {
+    // I = unsigned when the region has fewer than 2^31 points: 32-bit divisions
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = reg.lo[0] + (int)(i % reg.ext[0]);
-    const long long t = i / reg.ext[0];
-    const int y = reg.lo[1] + (int)(t % reg.ext[1]), z = reg.lo[2] + (int)(t / reg.ext[1]);
+    const long long i64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i64 >= n) return;
+    const I i = (I)i64;
+    const int x = reg.lo[0] + (int)(i % (I)reg.ext[0]);
+    const I t = i / (I)reg.ext[0];
+    const int y = reg.lo[1] + (int)(t % (I)reg.ext[1]), z = reg.lo[2] + (int)(t / (I)reg.ext[1]);
     const long long gi = g.at(x, y, z);
     const long long st[3] = {1, g.sy, g.sz};
     const float *ws[3] = {cf.wx, cf.wy, cf.wz};
@@ -312,8 +328,14 @@ void dft_gradient_isic(const judi_model *M, const Region &reg, const float *v, c
 {
     const long long n = (long long)reg.ext[0] * reg.ext[1] * reg.ext[2];
     const unsigned nb = (unsigned)((n + 255) / 256);
-    dft_grad_isic1_kernel<<<nb, 256, 0, M->ctx->stream>>>(M->g, reg, v, M->m.p, uf, nfreq, wc_dev, ec_dev, B, grad);
+    if (n < (1LL << 31))
+        dft_grad_isic1_kernel<unsigned><<<nb, 256, 0, M->ctx->stream>>>(M->g, reg, v, M->m.p, uf, nfreq, wc_dev, ec_dev, B, grad);
+    else
+        dft_grad_isic1_kernel<long long><<<nb, 256, 0, M->ctx->stream>>>(M->g, reg, v, M->m.p, uf, nfreq, wc_dev, ec_dev, B, grad);
     launch_count(M->ctx, "dft_grad_isic1");
-    dft_grad_isic2_kernel<<<nb, 256, 0, M->ctx->stream>>>(M->g, M->cf, M->r, M->ndim, reg, v, B, w2, grad);
+    if (n < (1LL << 31))
+        dft_grad_isic2_kernel<unsigned><<<nb, 256, 0, M->ctx->stream>>>(M->g, M->cf, M->r, M->ndim, reg, v, B, w2, grad);
+    else
+        dft_grad_isic2_kernel<long long><<<nb, 256, 0, M->ctx->stream>>>(M->g, M->cf, M->r, M->ndim, reg, v, B, w2, grad);
     launch_count(M->ctx, "dft_grad_isic2");
 }
