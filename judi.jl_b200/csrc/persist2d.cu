@@ -47,6 +47,12 @@ struct P2Args {
     int t_base;        // snapshot slot of time index t is (t - t_base) / t_sub
     int ic;            // JUDI_IC_*: imaging condition of the gradient and of the Born source
     Region reg;
+    // space-time source of the background field / extended receiver (fields_exprs.py:58-103)
+    const float *qext, *qwt, *qwf;
+    float qbase;
+    float *wrec;
+    const float *wrt;
+    float wdt;
 };
 
 template <int R>
@@ -163,7 +169,9 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
             if (x >= g.n[0] || z >= g.n[2]) continue;
             const long long i = g.at(x, 0, z);
             const float ucv = uc[i];
-            const float lap = lap2d<R>(g, a.cf, uc, i);
+            float lap = lap2d<R>(g, a.cf, uc, i);
+            if (a.qext) lap += (a.qbase * a.qwt[t]) * a.qext[i];
+            else if (a.qwf) lap += a.qbase * a.qwf[((long long)t * g.n[2] + z) * g.n[0] + x];
             const float s = ((a.dx[x] + 0.f) + a.dz[z]) * a.sdamp;
             const float mm = a.m[i];
             const float rden = 1.0f / (mm + s);
@@ -192,8 +200,9 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
                 }
                 ln[i] = (lcv + d1l) + (lapl - s * d1l + q) * rden;
             }
-            if ((snap_t || usnap_t || a.illum) && a.reg.has(x, 0, z)) {
+            if ((snap_t || usnap_t || a.illum || a.wrec) && a.reg.has(x, 0, z)) {
                 const long long ri = a.reg.at(x, 0, z);
+                if (a.wrec) a.wrec[ri] += (a.wdt * a.wrt[t]) * ucv;
                 if (snap_t) snap_t[ri] = ucv;
                 if (a.illum) a.illum[ri] += a.cf.dt * ucv * ucv;
                 if (usnap_t) {
@@ -759,6 +768,8 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
     a.reg = fz.reg;
     a.t_base = fz.t_base;
     a.ic = fz.ic;
+    a.qext = fz.qext; a.qwt = fz.qwt; a.qwf = fz.qwf; a.qbase = fz.qbase;
+    a.wrec = fz.wrec; a.wrt = fz.wrt; a.wdt = fz.wdt;
 }
 
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced

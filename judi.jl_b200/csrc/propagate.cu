@@ -265,11 +265,15 @@ void Shot::bind_ext(const ExtSpec *ext, const float *wavelet, int nt, bool on_de
         padded_to_grid(M, d, ws_grid.p);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         wt_host = first_column(ctx, wavelet, nt, on_device);
+        wt_dev = DevBuf(ctx, (size_t)nt, false);
+        wt_dev.upload(wt_host);
     }
     if (ext->wr_wavelet) {
         JUDI_REQUIRE(ext->w_out != nullptr, "extended receiver needs an output array");
         wrec = DevBuf(ctx, (size_t)M->full.slot, true);
         wrt_host = first_column(ctx, ext->wr_wavelet, nt, on_device);
+        wrt_dev = DevBuf(ctx, (size_t)nt, false);
+        wrt_dev.upload(wrt_host);
     }
     if (ext->qwf) {
         qwf_dev = to_dev(ext->qwf, ng * (size_t)nt, qwf_owned);
@@ -295,6 +299,24 @@ void Shot::apply_ext(StepArgs &s, int t)
         s.f.wrec = wrec.p;
         s.f.wrec_scale = M->dt * wrt_host[t];
     }
+}
+
+// The same description for the persistent 2-D kernel (constant-density acoustic only).
+bool persist2d_bind_ext(const judi_model *M, const Shot &sh, P2Fuse &fz)
+{
+    if (!sh.ext_active()) return true;
+    if (M->tti || M->irho_field || M->visco) return false;
+    fz.qbase = M->cf.dt2 / M->irho_c;
+    if (sh.ws_grid.p) { fz.qext = sh.ws_grid.p; fz.qwt = sh.wt_dev.p; }
+    else if (sh.qwf_dev) fz.qwf = sh.qwf_dev;
+    if (sh.wrec.p) {
+        fz.wrec = sh.wrec.p;
+        fz.wrt = sh.wrt_dev.p;
+        fz.wdt = M->dt;
+        if (!(fz.snap || fz.grad || fz.illum)) fz.reg = M->full;
+        else if (!(fz.reg.slot == M->full.slot)) return false;   // wrec is laid out on the full region
+    }
+    return true;
 }
 
 void Shot::finish_ext(const ExtSpec *ext, bool on_device)
@@ -386,10 +408,10 @@ void run_forward_rec(judi_model *M, int fw, int nsrc, const float *src_coords,
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
     const SparseSet *pS = nsrc > 0 ? &S_src : nullptr;
     sh.adjoint = !fw;
-    if (persist2d_supported(M, JUDI_IC_AS) && !sh.ext_active()) {
-        P2Fuse pf;
-        pf.reg = M->full;
-        pf.illum = fz.illum;
+    P2Fuse pf;
+    pf.reg = M->full;
+    pf.illum = fz.illum;
+    if (persist2d_supported(M, JUDI_IC_AS) && persist2d_bind_ext(M, sh, pf)) {
         persist2d_run(M, W, nullptr, fw ? 1 : nt - 2, fw ? nt - 2 : 1, fw ? 1 : -1, pS, &q,
                       nrec > 0 ? &S_rec : nullptr, &rec, nullptr, pf);
     } else if (fw) {
@@ -490,11 +512,11 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     Fuse fz = no_fuse();
     fz.reg = M->full;
     if (illum_out) { illum = DevBuf(ctx, (size_t)M->full.slot, true); fz.illum = illum.p; }
-    if (persist2d_supported(M, ic, true) && !sh.ext_active()) {
-        P2Fuse pf;
-        pf.reg = M->full;
-        pf.ic = ic;
-        pf.illum = fz.illum;
+    P2Fuse pf;
+    pf.reg = M->full;
+    pf.ic = ic;
+    pf.illum = fz.illum;
+    if (persist2d_supported(M, ic, true) && persist2d_bind_ext(M, sh, pf)) {
         persist2d_run(M, W, &WL, 1, nt - 2, 1, pS, &q, &S_rec, &rec, nullptr, pf);
     } else {
         for (int t = 1; t <= nt - 2; t++)
@@ -805,11 +827,12 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     // A range of forward steps.  mode 0: no snapshots; 1: slot t/k when t % k == 0; 2: slot t-base
     // (segment recomputation).  2-D constant-density models run the whole range inside one
     // persistent kernel (persist2d.cu), everything else steps kernel by kernel.
-    const bool p2 = persist2d_supported(M, o->ic, born) && !sh.ext_active() && !dft;
+    P2Fuse pf_ext;      // J_adjoint(ws=...): the extended source drives the forward sweeps
+    const bool p2 = persist2d_supported(M, o->ic, born) && persist2d_bind_ext(M, sh, pf_ext) && !dft;
     auto fwd_range = [&](int ta, int tb, int mode, int base, bool record) {
         if (tb < ta) return;
         if (p2) {
-            P2Fuse pf;
+            P2Fuse pf = pf_ext;
             pf.reg = reg;
             pf.ic = o->ic;
             pf.illum = fsave.illum;

@@ -26,6 +26,7 @@ struct Shot {
     // device-side state of the ExtSpec of the current call
     DevBuf ws_grid, qgrid, wrec;
     std::vector<float> wt_host, wrt_host;
+    DevBuf wt_dev, wrt_dev;    // the same time series on the device (persistent 2-D kernel)
     const float *qwf_dev = nullptr;
     DevBuf qwf_owned;
     bool ext_on = true;
@@ -53,7 +54,17 @@ struct P2Fuse {
     float gcoef = 0;
     int ic = JUDI_IC_AS;          // imaging condition of the gradient / Born source
     Region reg;
+    // space-time sources / extended receiver (fields_exprs.py:58-103), constant-density kernel only
+    const float *qext = nullptr, *qwt = nullptr;   // q = qbase * qwt[t] * qext(x)   (Grid layout)
+    const float *qwf = nullptr;                    // q = qbase * qwf[t](x)          (padded layout, nt slices)
+    float qbase = 0;
+    float *wrec = nullptr;                         // wrec += wdt * wrt[t] * u[t]    (region `reg`)
+    const float *wrt = nullptr;
+    float wdt = 0;
 };
+struct Shot;
+// fills the extended-source members of fz from the shot's bound ExtSpec; false when the kernel cannot take it
+bool persist2d_bind_ext(const judi_model *M, const Shot &sh, P2Fuse &fz);
 bool persist2d_supported(const judi_model *M, int ic, bool born = false);
 void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int t1, int dir,
                    const SparseSet *S_in, const Traces *in, const SparseSet *S_out, Traces *out,
