@@ -236,6 +236,7 @@ int judi_model_set_dm(judi_model *model, const judi_param *dm, int on_device)
     }
     model_set_param(model, model->dm, *dm, on_device, 0.f, true);
     model->has_dm = true;
+    model_update_dm_src(model);
     CUDA_CHECK(cudaStreamSynchronize(model->ctx->stream));
     return 0;
     API_END(1)

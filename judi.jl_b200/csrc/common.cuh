@@ -212,6 +212,12 @@ struct judi_model {
     DevBuf qp, vtt, vts;         // ... quality factor, tt = t_ep/t_s - 1 and t_s per point
     float irho_c = 1.f;
     DevBuf m, irho, eps, delta, theta, phi, dm;  // fields on `g` (edge-replicated into halo)
+    // dm as the factor of u.dt2 in the Born source.  With a free surface the reference evaluates the
+    // source after the mirror equations (operators.py:188), where u(z=0) is identically zero: the
+    // surface row contributes nothing.  dm_src = dm with that row zeroed (dm itself when !fs); the
+    // div(dm grad u) part of the isic / fwi sources keeps reading dm.
+    DevBuf dm_src_buf;
+    const float *dm_src() const { return dm_src_buf.p ? dm_src_buf.p : dm.p; }
     DevBuf r3[3];                // 3-D TTI: symmetry axis (sin th cos ph, sin th sin ph, cos th)
     DevBuf ttiABC[3];            // 3-D TTI, constant density: A0 = b delta~, B0 = b sqrt((eps~-delta~) delta~), C0 = b (eps~-delta~)
     DevBuf damp[3];              // 1-D damping profiles per dimension (value of `damp`)
@@ -248,6 +254,7 @@ struct SparseCorr {
 
 // ---- model.cu
 Grid make_grid(int ndim, const int *N, int halo);
+void model_update_dm_src(judi_model *M);
 void fornberg_weights(double z, const double *x, int n, int m, double *c);
 void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc);
 void model_set_param(judi_model *M, DevBuf &dst, const judi_param &p, int on_device,

@@ -517,7 +517,7 @@ static void flux3d_one(const judi_model *M, Wavefield *W, const float *const *u,
         ua.dd_in[f] = dd_in ? dd_in[f] : nullptr;
     }
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
-    ua.m = M->m.p; ua.dm = M->dm.p;
+    ua.m = M->m.p; ua.dm = M->dm_src();
     ua.irho = M->irho_field ? M->irho.p : nullptr;
     ua.irho_c = M->irho_c;
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;

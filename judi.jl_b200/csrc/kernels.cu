@@ -26,6 +26,7 @@ struct AcArgs {
     const float *ul;            // Born (nullptr: off)
     float *ulp;
     const float *dm;
+    const float *dms;           // dm as the factor of u.dt2 (judi_model::dm_src)
     int born_ic;
     const float *qext;          // extended / wavefield source (nullptr: off)
     float qext_scale;
@@ -162,10 +163,10 @@ __global__ void __launch_bounds__(256) acoustic_generic(AcArgs a)
         float ulpv = a.ulp[i];
         float d1l = ulc - ulpv;
         float q;  // (dt^2/irho) * lin_src   (sensitivity.py:174-209)
-        if (a.born_ic == JUDI_IC_AS) q = -a.dm[i] * delta;
+        if (a.born_ic == JUDI_IC_AS) q = -a.dms[i] * delta;
         else {
             float ics = a.born_ic == JUDI_IC_FWI ? -1.f : 1.f;
-            q = -(a.dm[i] * mm * delta -
+            q = -(a.dms[i] * mm * delta -
                   ics * a.cf.dt2 * lap_weighted<NDIM, R>(g, a.cf, a.u, a.dm, i));
         }
         float deltal = (lapl - s * d1l + q) * rden;
@@ -265,7 +266,7 @@ struct FluxUpdArgs {
     const float *u[2];
     float *up[2];
     const float *P[3], *M[3];
-    const float *m, *irho, *dm;
+    const float *m, *irho, *dm, *dms;
     const float *dx, *dy, *dz;
     float *dd_out[2];        // write delta of each field (background pass of Born)
     const float *dd_in[2];   // read delta of the background field (linearised pass of Born)
@@ -304,10 +305,10 @@ __global__ void __launch_bounds__(256) flux_update(FluxUpdArgs a)
         if (a.dd_in[f]) {
             // dt^2 * lin_src: "as" -dm irho u.dt2; isic / fwi -(dm irho u.dt2 m -+ laplacian(u, dm irho))
             // (sensitivity.py:174-209)
-            if (a.born_ic == JUDI_IC_AS) q = -a.dm[i] * ir * a.dd_in[f][i];
+            if (a.born_ic == JUDI_IC_AS) q = -a.dms[i] * ir * a.dd_in[f][i];
             else {
                 float ics = a.born_ic == JUDI_IC_FWI ? -1.f : 1.f;
-                q = -(a.dm[i] * ir * mm * a.dd_in[f][i] -
+                q = -(a.dms[i] * ir * mm * a.dd_in[f][i] -
                       ics * cf.dt2 * lap_weighted2<NDIM, R>(g, cf, a.ub[f], a.dm, a.irho, i));
             }
         }
@@ -496,7 +497,7 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         for (int f = 0; f < nf; f++)
             for (int s = 0; s < 2; s++) tma3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
         tma3d_encode(M, M->m.p, nullptr, &tmap_m);
-        if (M->dm.p) tma3d_encode(M, M->dm.p, nullptr, &tmap_dm);
+        if (M->dm.p) tma3d_encode(M, M->dm_src(), nullptr, &tmap_dm);
         has_tmap = true;
     } else if (varc3d_supported(M)) {
         for (int s = 0; s < 2; s++) varc3d_encode(M, b[0][s].p, &tmap_halo[0][s], &tmap_tile[0][s]);
@@ -527,7 +528,7 @@ static void launch_acoustic_generic(const judi_model *M, const StepArgs &s)
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.sdamp = M->dt / M->irho_c;
     a.irho_c = M->irho_c;
-    if (s.born) { a.ul = s.ul[0]; a.ulp = s.ulp[0]; a.dm = M->dm.p; a.born_ic = s.born_ic; }
+    if (s.born) { a.ul = s.ul[0]; a.ulp = s.ulp[0]; a.dm = M->dm.p; a.dms = M->dm_src(); a.born_ic = s.born_ic; }
     a.qext = s.qext;
     a.qext_scale = s.qext_scale;
     a.f = s.f;
@@ -571,7 +572,7 @@ static void flux_one(const judi_model *M, Wavefield *W, const float *const *u, f
     }
     ua.born_ic = born_ic;
     for (int d = 0; d < 3; d++) { ua.P[d] = W->flux[d].p; ua.M[d] = W->flux[3 + d].p; }
-    ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p;
+    ua.m = M->m.p; ua.irho = M->irho.p; ua.dm = M->dm.p; ua.dms = M->dm_src();
     ua.dx = M->damp[0].p; ua.dy = M->damp[1].p; ua.dz = M->damp[2].p;
     ua.qext = qext;
     ua.qext_scale = qext_scale;

@@ -212,6 +212,26 @@ static void field_minmax(const judi_model *M, const float *f, float &lo, float &
 
 // Upload one physical parameter into a Grid-layout field.  Scalars become constant fields when
 // `force_field` (m, Thomsen parameters); otherwise the caller keeps the scalar.
+__global__ void zero_surface_row_kernel(Grid g, float *__restrict__ f)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= g.n[0] || y >= g.n[1]) return;
+    f[g.at(x, y, 0)] = 0.f;
+}
+
+void model_update_dm_src(judi_model *M)
+{
+    if (!M->fs || !M->dm.p) { M->dm_src_buf = DevBuf(); return; }
+    judi_ctx *ctx = M->ctx;
+    if (!M->dm_src_buf.p) M->dm_src_buf = DevBuf(ctx, (size_t)M->g.nalloc, false);
+    CUDA_CHECK(cudaMemcpyAsync(M->dm_src_buf.p, M->dm.p, (size_t)M->g.nalloc * sizeof(float),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+    dim3 blk(128, 1), grd((M->N[0] + 127) / 128, M->N[1]);
+    zero_surface_row_kernel<<<grd, blk, 0, ctx->stream>>>(M->g, M->dm_src_buf.p);
+    launch_count(ctx, "zero_surface_row");
+}
+
 void model_set_param(judi_model *M, DevBuf &dst, const judi_param &p, int on_device,
                      float default_value, bool force_field)
 {
@@ -437,6 +457,7 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
         (desc->dm.kind == JUDI_PARAM_SCALAR && desc->dm.value != 0.0f)) {
         model_set_param(M, M->dm, desc->dm, dev, 0.0f, true);
         M->has_dm = true;
+        model_update_dm_src(M);
     }
 
     // ---- damping profiles (separable: damp = sum_d profile_d, models.py:54-96) -------------

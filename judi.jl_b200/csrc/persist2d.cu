@@ -22,7 +22,7 @@ struct P2Args {
     float *b[2];       // background field buffers; level t is b[cur]
     float *l[2];       // linearised field buffers (Born) or nullptr
     int cur;
-    const float *m, *dx, *dz, *dm;
+    const float *m, *dx, *dz, *dm, *dms;   // dms: dm as the factor of u.dt2 (judi_model::dm_src)
     float sdamp, irho_c;
     int t0, t1, dir;   // time indices t0, t0+dir, ..., t1
     // injected traces (sorted cell layout, see sparse.cu)
@@ -53,6 +53,7 @@ struct P2Args {
     float *wrec;
     const float *wrt;
     float wdt;
+    int fs;            // free surface: mirror the new level about z = 0 (fields_exprs.py:106-137)
 };
 
 template <int R>
@@ -185,20 +186,26 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
                     acc += a.ent_w[e] * src_row[a.ent_trace[e]];
                 inj = acc * a.cell_scale[row];
             }
-            un[i] = ((ucv + d1) + delta) + inj;
+            const float unew = ((ucv + d1) + delta) + inj;
+            // free surface after the injection: u(-k) = -u(k-1), k = 1..R, then u(0) = 0 -- every
+            // mirrored value comes from the thread that owns its source point
+            if (a.fs && z < R) un[i - (long long)(2 * z + 1) * g.sz] = -unew;
+            un[i] = (a.fs && z == 0) ? 0.f : unew;
             if (ln) {
                 const float lcv = lc[i];
                 const float lapl = lap2d<R>(g, a.cf, lc, i);
                 const float d1l = lcv - ln[i];
                 // Born source from the post-injection u+ - 2u + u-  (sensitivity.py:174-209)
                 float q;
-                if (!XIC || a.ic == JUDI_IC_AS) q = -a.dm[i] * (delta + inj);
+                if (!XIC || a.ic == JUDI_IC_AS) q = -a.dms[i] * (delta + inj);
                 else {
                     const float ics = a.ic == JUDI_IC_FWI ? -1.f : 1.f;
-                    q = -(a.dm[i] * mm * (delta + inj) -
+                    q = -(a.dms[i] * mm * (delta + inj) -
                           ics * a.cf.dt2 * lap_weighted2d<R>(g, a.cf, uc, a.dm, i));
                 }
-                ln[i] = (lcv + d1l) + (lapl - s * d1l + q) * rden;
+                const float lnew = (lcv + d1l) + (lapl - s * d1l + q) * rden;
+                if (a.fs && z < R) ln[i - (long long)(2 * z + 1) * g.sz] = -lnew;
+                ln[i] = (a.fs && z == 0) ? 0.f : lnew;
             }
             if ((snap_t || usnap_t || a.illum || a.wrec) && a.reg.has(x, 0, z)) {
                 const long long ri = a.reg.at(x, 0, z);
@@ -591,8 +598,8 @@ bool persist2d_supported(const judi_model *M, int ic, bool born)
 {
     const bool flux = M->tti || M->irho_field || M->visco;
     // flux form / visco: so = 8, no Born, "as" only; constant density: every imaging condition
-    if (flux && (born || M->r != 4 || ic != JUDI_IC_AS || (M->tti && !M->r3[0].p))) return false;
-    return M->ndim == 2 && !M->fs && (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
+    if (flux && (born || M->fs || M->r != 4 || ic != JUDI_IC_AS || (M->tti && !M->r3[0].p))) return false;
+    return M->ndim == 2 && (M->r == 2 || M->r == 4 || M->r == 8) && M->ctx->opt_persist2d;
 }
 
 static void p2flux_fill(const judi_model *M, Wavefield &W, int t0, int t1, int dir,
@@ -742,7 +749,7 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
     a.b[0] = W.b[0][0].p; a.b[1] = W.b[0][1].p;
     if (WL) { a.l[0] = WL->b[0][0].p; a.l[1] = WL->b[0][1].p; }
     a.cur = W.cur;
-    a.m = M->m.p; a.dx = M->damp[0].p; a.dz = M->damp[2].p; a.dm = M->dm.p;
+    a.m = M->m.p; a.dx = M->damp[0].p; a.dz = M->damp[2].p; a.dm = M->dm.p; a.dms = M->dm_src();
     a.sdamp = M->dt / M->irho_c;
     a.irho_c = M->irho_c;
     a.t0 = t0; a.t1 = t1; a.dir = dir;
@@ -770,6 +777,7 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
     a.ic = fz.ic;
     a.qext = fz.qext; a.qwt = fz.qwt; a.qwf = fz.qwf; a.qbase = fz.qbase;
     a.wrec = fz.wrec; a.wrt = fz.wrt; a.wdt = fz.wdt;
+    a.fs = M->fs ? 1 : 0;
 }
 
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced

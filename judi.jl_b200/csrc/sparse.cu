@@ -152,7 +152,7 @@ void sparse_build(const judi_model *M, int np, const float *coords, SparseSet &S
     if (S.ncell > 0) {
         sparse_cell_setup<<<(S.ncell + 127) / 128, 128, 0, ctx->stream>>>(
             S.ncell, S.cell_off.p, S.cell_ijk.p, M->m.p, M->irho.p, M->irho_c,
-            M->has_dm ? M->dm.p : nullptr, M->damp[0].p, M->damp[1].p, M->damp[2].p, M->dt,
+            M->has_dm ? (M->visco ? M->dm.p : M->dm_src()) : nullptr, M->damp[0].p, M->damp[1].p, M->damp[2].p, M->dt,
             S.cell_scale.p, S.cell_born.p);
         launch_count(ctx, "sparse_cell_setup");
     }

@@ -530,7 +530,7 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
     a.f = s.f;
     a.dd_out = s.dd_out;
     a.qsrc = s.qsrc;
-    a.dm = s.qsrc ? M->dm.p : nullptr;
+    a.dm = s.qsrc ? M->dm_src() : nullptr;
     TmaMaps tm;
     tm.U = *s.tmap; tm.P = *s.tmap_prev; tm.M = *s.tmap_m;
     if (DUAL) {

@@ -636,7 +636,7 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = fals
     if (FUSE & TF_DDOUT) { a.dd_out[0] = s.scratch->dd[0].p; a.dd_out[1] = s.scratch->dd[1].p; }
     if (FUSE & TF_QSRC) {
         a.dd_in[0] = s.scratch->dd[0].p; a.dd_in[1] = s.scratch->dd[1].p;
-        a.dm = M->dm.p;
+        a.dm = M->dm_src();
     }
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.irho_c = M->irho_c;

@@ -535,7 +535,7 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = fal
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     if (!lin) a.f = s.f;
     if (FUSE & VF_DDOUT) a.dd_out = s.scratch->dd[0].p;
-    if (FUSE & VF_QSRC) { a.dd_in = s.scratch->dd[0].p; a.dm = M->dm.p; }
+    if (FUSE & VF_QSRC) { a.dd_in = s.scratch->dd[0].p; a.dm = M->dm_src(); }
     const int ntx = (M->N[0] + varc::TX - 1) / varc::TX, nty = (M->N[1] + varc::TY - 1) / varc::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
