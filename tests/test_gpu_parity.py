@@ -429,6 +429,11 @@ def test_free_surface_born_with_a_perturbation_on_the_surface_row(kind, ndim, ic
     finally:
         ctx.set_option("persist2d", 1)
     assert rel_l2(dl2, dlo) < TOL_SHOT
+    # and the matching imaging condition under the free surface (snapshots carry no mirrored halo)
+    y = np.random.default_rng(2).standard_normal(dl.shape).astype(np.float32)
+    g, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True, ic=ic)
+    go, _, _ = O.J_adjoint(om, src, q, rec, y, is_residual=True, ic=ic)
+    assert rel_l2(g, go) < TOL_GRAD
 
 
 @pytest.mark.parametrize("kind,ndim", [("iso", 2), ("iso", 3), ("tti", 2), ("rho", 2), ("tti", 3), ("visco", 2)])
