@@ -147,6 +147,27 @@ int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value);
 int judi_host_register(void *ptr, size_t nbytes);
 int judi_host_unregister(void *ptr);
 
+/* Give the memory this context caches (snapshot arena, reduction buffer, freed pool blocks) back
+ * to the driver, e.g. before another library of the host process needs the HBM.  The context
+ * allocates from a private stream-ordered pool, never from the device's default one. */
+int judi_ctx_trim(judi_ctx *ctx);
+
+/* ---- multi-GPU reduction ---------------------------------------------------------------
+ * Replaces `reduce!` / `run_and_reduce` (src/TimeModeling/Modeling/distributed.jl:60-95,
+ * propagation.jl:23-50): the binary tree over Julia Futures that sums (objective, gradient) of
+ * the workers.  One process per GPU; rank 0 calls judi_comm_unique_id and hands the 128 bytes
+ * to every rank over the host's own channel (Distributed.jl / MPI / a TCP store); every rank
+ * then calls judi_comm_init on its context.  NCCL is loaded at run time (dlopen of
+ * $JUDI_NCCL_LIB, else libnccl.so.2); nranks == 1 needs no NCCL at all. */
+#define JUDI_COMM_ID_BYTES 128
+int judi_comm_unique_id(void *id128);
+int judi_comm_init(judi_ctx *ctx, int nranks, int rank, const void *id128);
+int judi_comm_destroy(judi_ctx *ctx);
+int judi_comm_size(judi_ctx *ctx);
+int judi_comm_rank(judi_ctx *ctx);
+/* in-place sum over the ranks of n floats in HBM, on the context stream (ncclAllReduce) */
+int judi_comm_allreduce(judi_ctx *ctx, float *dev, size_t n);
+
 /* ---- model ----------------------------------------------------------------------------- */
 judi_model *judi_model_create(judi_ctx *ctx, const judi_model_desc *desc);
 void judi_model_destroy(judi_model *model);
@@ -263,6 +284,26 @@ int judi_remove_padding(const judi_model *model, const float *padded, int true_a
  * everything else is sinc interpolation.  Flags as for judi_remove_padding. */
 int judi_time_resample(judi_ctx *ctx, const float *in, int nt_in, int ntrace, float t0_in,
                        float dt_in, float *out, int nt_out, float t0_out, float dt_out, int flags);
+
+/* The reduction + post-processing of multi_src_fg! (propagation.jl:99-106, distributed.jl:60-95,
+ * misfit_fg.jl:77) in one call: `grad_padded_dev` (padded grid, device) and `f_dev` (device scalar
+ * or NULL) are this rank's accumulators as filled by judi_J_adjoint / judi_fg_multishot with
+ * JUDI_OUT_ON_DEVICE | JUDI_GRAD_ACCUMULATE.  The gradient is cropped (true_adjoint: pad folded
+ * into the edges) on the device, the objective appended, and ONE all-reduce of prod(n)+1 floats
+ * sums them over the ranks of the context's communicator (none: the local values); the result is
+ * written to `grad_out` (physical grid, x fastest) and `f_out` -- host pointers, or device
+ * pointers with JUDI_OUT_ON_DEVICE. */
+int judi_fg_reduce(judi_model *model, const float *grad_padded_dev, const float *f_dev,
+                   int true_adjoint, float *grad_out, float *f_out, int flags);
+
+/* multi_src_fg! + reduce! for one worker in ONE call (SURVEY 8b `judi_fg_multishot`): this
+ * rank's `nshots` experiments (0 is allowed: the rank still takes part in the reduction) are
+ * summed in HBM as by judi_fg_multishot, then reduced over the communicator as by
+ * judi_fg_reduce.  Every rank receives the gradient on the PHYSICAL grid and the objective, summed
+ * over all shots of all ranks (host pointers, or device pointers with JUDI_OUT_ON_DEVICE). */
+int judi_fg_multishot_reduced(judi_model *model, int nshots, const judi_shot *shots,
+                              const judi_jopts *opts, judi_misfit_fn misfit, void *user,
+                              int true_adjoint, float *f_out, float *grad_out, int flags);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,18 @@ SIGNATURES = {
                                                    ctypes.POINTER(ctypes.c_longlong)]),
     "judi_ctx_reset_stats": (ctypes.c_int, [ctypes.c_void_p]),
     "judi_ctx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    "judi_ctx_trim": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "judi_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_comm_size": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_comm_rank": (ctypes.c_int, [ctypes.c_void_p]),
+    "judi_comm_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "judi_fg_reduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "judi_fg_multishot_reduced": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(JudiShot),
+                                                 ctypes.POINTER(JudiJopts), ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "judi_model_create": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.POINTER(JudiModelDesc)]),
     "judi_model_destroy": (None, [ctypes.c_void_p]),
     "judi_model_critical_dt": (ctypes.c_float, [ctypes.c_void_p]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjudi_b200.so")
-SOURCES = ["capi.cu", "model.cu", "sparse.cu", "kernels.cu", "tma3d.cu", "tti3d.cu", "varc3d.cu", "flux3d.cu", "persist2d.cu", "propagate.cu", "hostops.cu"]
+SOURCES = ["capi.cu", "model.cu", "sparse.cu", "kernels.cu", "tma3d.cu", "tti3d.cu", "varc3d.cu", "flux3d.cu", "persist2d.cu", "propagate.cu", "hostops.cu", "comm.cu"]
 HEADERS = ["common.cuh", "tma_util.cuh", "propagate.h", os.path.join("..", "..", "include", "judi_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -46,7 +46,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = ["nvcc", "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = ["nvcc", "-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -41,7 +41,16 @@ judi_ctx *judi_ctx_create(int device)
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&ctx->pool, device));
+    // a PRIVATE stream-ordered pool: the release threshold below must not change the behaviour of
+    // other cudaMallocAsync users of the host process (CUDA.jl, torch's async allocator)
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    CUDA_CHECK(cudaMemPoolCreate(&ctx->pool, &pp));
+    ctx->own_pool = true;
     unsigned long long thresh = ~0ull;  // keep freed blocks: shots reuse the same buffers
     CUDA_CHECK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     cudaDriverEntryPointQueryResult qres;
@@ -59,8 +68,11 @@ void judi_ctx_destroy(judi_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
+    comm_destroy(ctx);
+    if (ctx->red_p) cudaFreeAsync(ctx->red_p, ctx->stream);
     if (ctx->arena_p) cudaFree(ctx->arena_p);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->own_pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -407,6 +419,27 @@ int judi_fg_multishot(judi_model *model, int nshots, const judi_shot *shots, con
     API_END(1)
 }
 
+int judi_fg_multishot_reduced(judi_model *model, int nshots, const judi_shot *shots, const judi_jopts *opts,
+                              judi_misfit_fn misfit, void *user, int true_adjoint, float *f_out,
+                              float *grad_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && opts && grad_out && f_out, "null argument");
+    judi_ctx *ctx = model->ctx;
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t ng = (size_t)model->N[0] * model->N[1] * model->N[2];
+    DevBuf acc(ctx, ng + 1, true);
+    // this rank's shots, summed in HBM (a rank may hold no shot at all: it still joins the reduction)
+    if (nshots > 0) {
+        int rc = judi_fg_multishot(model, nshots, shots, opts, misfit, user, acc.p + ng, acc.p,
+                                   (flags & JUDI_DATA_ON_DEVICE) | JUDI_OUT_ON_DEVICE | JUDI_GRAD_ACCUMULATE);
+        if (rc != 0) return rc;
+    }
+    run_fg_reduce(model, acc.p, acc.p + ng, true_adjoint, grad_out, f_out, flags & JUDI_OUT_ON_DEVICE);
+    return 0;
+    API_END(1)
+}
+
 int judi_forward_rec_w(judi_model *model, int fw, const float *weight, const float *wavelet, int nt,
                        int nrec, const float *rec_coords, float *rec_out, float *illum_out,
                        int flags)
@@ -496,6 +529,73 @@ int judi_time_resample(judi_ctx *ctx, const float *in, int nt_in, int ntrace, fl
     JUDI_REQUIRE(ctx && in && out, "null argument");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     run_time_resample(ctx, in, nt_in, ntrace, t0_in, dt_in, out, nt_out, t0_out, dt_out, flags);
+    return 0;
+    API_END(1)
+}
+
+int judi_ctx_trim(judi_ctx *ctx)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx, "null context");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->red_p) { CUDA_CHECK(cudaFreeAsync(ctx->red_p, ctx->stream)); ctx->red_p = nullptr; ctx->red_floats = 0; }
+    if (ctx->arena_p) { CUDA_CHECK(cudaFree(ctx->arena_p)); ctx->arena_p = nullptr; ctx->arena_floats = 0; }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaMemPoolTrimTo(ctx->pool, 0));
+    return 0;
+    API_END(1)
+}
+
+int judi_comm_unique_id(void *id128)
+{
+    API_BEGIN
+    JUDI_REQUIRE(id128, "null argument");
+    comm_unique_id(id128);
+    return 0;
+    API_END(1)
+}
+
+int judi_comm_init(judi_ctx *ctx, int nranks, int rank, const void *id128)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx && (id128 || nranks == 1), "null argument");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    comm_init(ctx, nranks, rank, id128);
+    return 0;
+    API_END(1)
+}
+
+int judi_comm_destroy(judi_ctx *ctx)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx, "null context");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    comm_destroy(ctx);
+    return 0;
+    API_END(1)
+}
+
+int judi_comm_size(judi_ctx *ctx) { return ctx ? ctx->comm_size : 0; }
+int judi_comm_rank(judi_ctx *ctx) { return ctx ? ctx->comm_rank : -1; }
+
+int judi_comm_allreduce(judi_ctx *ctx, float *dev, size_t n)
+{
+    API_BEGIN
+    JUDI_REQUIRE(ctx && dev, "null argument");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    comm_allreduce(ctx, dev, n);
+    return 0;
+    API_END(1)
+}
+
+int judi_fg_reduce(judi_model *model, const float *grad_padded_dev, const float *f_dev, int true_adjoint,
+                   float *grad_out, float *f_out, int flags)
+{
+    API_BEGIN
+    JUDI_REQUIRE(model && grad_padded_dev && grad_out, "null argument");
+    CUDA_CHECK(cudaSetDevice(model->ctx->device));
+    run_fg_reduce(model, grad_padded_dev, f_dev, true_adjoint, grad_out, f_out, flags);
     return 0;
     API_END(1)
 }

@@ -121,6 +121,7 @@ struct judi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaMemPool_t pool = nullptr;
+    bool own_pool = false;
     long long launches = 0;
     // stencil timing (CUDA events on `stream`)
     int timing = 0;             // 0 off, k: time every k-th stencil launch
@@ -164,6 +165,12 @@ struct judi_ctx {
     float *arena_p = nullptr;
     size_t arena_floats = 0;
     float *arena(size_t nfloat);
+    // multi-GPU reduction (comm.cu): NCCL communicator of this rank, reduction staging buffer
+    void *comm = nullptr;
+    int comm_size = 1, comm_rank = 0;
+    long long collectives = 0;
+    float *red_p = nullptr;
+    size_t red_floats = 0;
 };
 
 // RAII device buffer on the context's stream-ordered pool
@@ -261,6 +268,14 @@ void model_set_param(judi_model *M, DevBuf &dst, const judi_param &p, int on_dev
                      float default_value, bool force_field);
 void model_set_visco(judi_model *M, const judi_param *qp, float f0, int on_device);
 void launch_count(judi_ctx *ctx, const char *what);
+
+// ---- comm.cu
+void comm_unique_id(void *id128);
+void comm_init(judi_ctx *ctx, int nranks, int rank, const void *id128);
+void comm_destroy(judi_ctx *ctx);
+void comm_allreduce(judi_ctx *ctx, float *dev, size_t n);
+void run_fg_reduce(judi_model *M, const float *grad_padded_dev, const float *f_dev, int true_adjoint,
+                   float *grad_out, float *f_out, int flags);
 
 // ---- sparse.cu
 void sparse_locate_host(const judi_model *M, int np, const float *coords, std::vector<int> &ijk,

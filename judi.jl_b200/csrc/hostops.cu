@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) time_resample_kernel(ResampleArgs a,
             const int j = j0 + 128 * k;
             if (j < a.nt_out) {
                 const long long i = ((long long)j + a.idx0) * a.rate;
-                out[(size_t)p * a.nt_out + j] = i < a.nt_in ? src[i] : 0.f;
+                out[(size_t)p * a.nt_out + j] = (i >= 0 && i < a.nt_in) ? src[i] : 0.f;
             }
         }
         return;
@@ -177,6 +177,9 @@ void run_time_resample(judi_ctx *ctx, const float *in, int nt_in, int np, float 
         a.rate = (int)(dt_out / dt_in);
         a.idx0 = (int)((t0_out - t0_in) / dt_out);
     }
+    // data[idx1:end] with idx1 < 1 throws in the reference (time_utilities.jl:35,40): a new axis
+    // that starts before the data is an error, not an out-of-bounds read
+    JUDI_REQUIRE(a.idx0 >= 0, "time_resample: the new time axis starts before the data");
     constexpr int TJ = 4;
     dim3 grd((nt_out + 128 * TJ - 1) / (128 * TJ), np);
     time_resample_kernel<TJ><<<grd, 128, 0, ctx->stream>>>(a, src, dst);

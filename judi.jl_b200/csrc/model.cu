@@ -13,7 +13,7 @@ void *judi_ctx::alloc_bytes(size_t nbytes, bool zero)
 {
     void *p = nullptr;
     if (nbytes == 0) nbytes = 16;
-    CUDA_CHECK(cudaMallocAsync(&p, nbytes, stream));
+    CUDA_CHECK(cudaMallocFromPoolAsync(&p, nbytes, pool, stream));
     if (zero) CUDA_CHECK(cudaMemsetAsync(p, 0, nbytes, stream));
     return p;
 }

@@ -79,7 +79,9 @@ void Traces::load(judi_ctx *ctx, const float *user, int nt_, int np_, bool on_de
         CUDA_CHECK(cudaMemcpyAsync(tmp.p, user, n * sizeof(float), cudaMemcpyHostToDevice,
                                    ctx->stream));
         transpose(ctx, tmp.p, buf.p, np, nt);
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        // no stream sync: the staging buffer is freed in stream order, and a copy from pageable
+        // host memory has been staged by the time cudaMemcpyAsync returns; page-locked caller
+        // arrays must stay untouched until the call returns (every run_* ends with a sync)
     }
 }
 
@@ -94,7 +96,8 @@ void Traces::store(judi_ctx *ctx, float *user, bool on_device) const
         transpose(ctx, buf.p, tmp.p, nt, np);
         CUDA_CHECK(cudaMemcpyAsync(user, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost,
                                    ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        // completed by the stream synchronisation that ends every run_* call (or by the caller
+        // before it reads `user` on the host)
     }
 }
 
@@ -191,6 +194,14 @@ __global__ void loss_kernel(long long n, float *__restrict__ a, const float *__r
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
         atomicAdd(fout, s * (double)half_dt);
     }
+}
+
+// *dst (+)= the objective value: from the device scalar of the loss kernel, or the host value of a
+// misfit callback
+__global__ void scalar_out_kernel(float *dst, const double *src_dev, double host_val, int accumulate)
+{
+    const float v = (float)(src_dev ? *src_dev : host_val);
+    *dst = accumulate ? *dst + v : v;
 }
 
 // Free surface (fields_exprs.py:106-137, applied to the new level after the injection, see the
@@ -528,6 +539,13 @@ void run_born_rec(judi_model *M, int nsrc, const float *src_coords, const float 
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
+__global__ void batch_sum_kernel(double *acc, const double *f, int n)
+{
+    double s = *acc;
+    for (int i = 0; i < n; i++) s += f[i];
+    *acc = s;
+}
+
 // ---- J_adjoint -----------------------------------------------------------------------------------
 static int num_slots(int nt, int t_sub)
 {
@@ -574,7 +592,7 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
                             12.0 * (double)nt * shots[0].nrec;
     const int chunk = (int)std::max(1.0, std::min((double)std::min(nshots, 32), avail / per_shot));
     if (chunk < 2) return false;
-    double fsum = 0.0;
+    DevArr<double> fsum_dev(ctx, 1, true);
     PhaseClock pc(ctx);
     for (int s0 = 0; s0 < nshots; s0 += chunk) {
         const int n = std::min(chunk, nshots - s0);
@@ -618,6 +636,11 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
         persist2d_run_batch(M, n, pW.data(), 1, nt - 2, 1, pSs.data(), pq.data(), pSr.data(), prec.data(),
                             pf.data(), born ? pWL.data() : nullptr, (born && o->nlind) ? pnl.data() : nullptr);
         pc.mark("batch forward sweep");
+        // born_fwd without a perturbation: zero linearised record (propagators.py:181-194)
+        if (o->born_fwd && !born && !o->nlind)
+            for (int s = 0; s < n; s++)
+                CUDA_CHECK(cudaMemsetAsync(rec[s].buf.p, 0, (size_t)nt * shots[s0 + s].nrec * sizeof(float),
+                                           ctx->stream));
         // misfit and residual (sensitivity.py:236-276), one small launch per shot
         DevArr<double> fd(ctx, (size_t)n, true);
         for (int s = 0; s < n; s++) {
@@ -650,17 +673,13 @@ bool run_fg_batch2d(judi_model *M, int nshots, const judi_shot *shots, const jud
                             pf.data());
         pc.mark("batch adjoint sweep");
         for (int s = 0; s < n; s++) region_output(M, reg, grad[s].p, g_dev, true, true);
-        std::vector<double> fh((size_t)n);
-        CUDA_CHECK(cudaMemcpyAsync(fh.data(), fd.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        for (int s = 0; s < n; s++) fsum += fh[s];
+        batch_sum_kernel<<<1, 1, 0, ctx->stream>>>(fsum_dev.p, fd.p, n);
+        launch_count(ctx, "batch_sum");
         pc.mark("batch outputs");
     }
-    float prev = 0.f;
-    CUDA_CHECK(cudaMemcpyAsync(&prev, f_dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    prev += (float)fsum;
-    CUDA_CHECK(cudaMemcpyAsync(f_dev, &prev, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // f_dev += (float)(sum of the shots' objectives), on the device
+    scalar_out_kernel<<<1, 1, 0, ctx->stream>>>(f_dev, fsum_dev.p, 0.0, 1);
+    launch_count(ctx, "scalar_out");
     ctx->flush_timing();
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return true;
@@ -892,8 +911,14 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     }
 
     pc.mark("forward sweep");
+    // born_fwd without a perturbation (propagators.py:181-194): the reference runs the plain
+    // forward operator for the wavefield and returns the untouched, zero linearised record -- the
+    // background data only reach the Loss through `rnl` when nlind is set.
+    if (o->born_fwd && !born && !o->nlind)
+        CUDA_CHECK(cudaMemsetAsync(rec.buf.p, 0, (size_t)nt * std::max(nrec, 1) * sizeof(float), ctx->stream));
     // ---- misfit (sensitivity.py:236-276) ---------------------------------------------------
     double fval = 0.0;
+    DevArr<double> fd;      // the on-device misfit value (stays in HBM when the output does)
     if (misfit) {
         size_t n = (size_t)nt * nrec;
         std::vector<float> hsyn(n), hobs(n), hres(n);
@@ -903,16 +928,18 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             rec.store(ctx, hsyn.data(), false);
             recnl.store(ctx, hnl.data(), false);
             obs.store(ctx, hobs.data(), false);
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             for (size_t i = 0; i < n; i++) hobs[i] -= hnl[i];
         } else {
             rec.store(ctx, hsyn.data(), false);
             obs.store(ctx, hobs.data(), false);
         }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         float fv = misfit(hsyn.data(), hobs.data(), hres.data(), nt, nrec, user);
         fval = (double)M->dt * (double)fv;
         rec.load(ctx, hres.data(), nt, nrec, false);
     } else {
-        DevArr<double> fd(ctx, 1, true);
+        fd = DevArr<double>(ctx, 1, true);
         long long n = (long long)nt * nrec;
         int nb = (int)std::min<long long>((n + 255) / 256, 1024);
         if (nb < 1) nb = 1;
@@ -921,9 +948,11 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
                                                  obs.buf.p, o->is_residual ? 1 : 0, fd.p,
                                                  0.5f * M->dt);
         launch_count(ctx, "loss");
-        CUDA_CHECK(cudaMemcpyAsync(&fval, fd.p, sizeof(double), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (f_out && !dev_out) {
+            CUDA_CHECK(cudaMemcpyAsync(&fval, fd.p, sizeof(double), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
     }
     // rec now holds the adjoint source (residual)
 
@@ -1016,16 +1045,9 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     if (illum_v) region_output(M, reg, Iv.p, illum_v, dev_out, false);
     if (f_out) {
         if (dev_out) {
-            // device scalar: keep the reduction on the GPU side of the boundary
-            float fv = (float)fval, prev = 0.f;
-            if (accumulate) {
-                CUDA_CHECK(cudaMemcpyAsync(&prev, f_out, sizeof(float), cudaMemcpyDeviceToHost,
-                                           ctx->stream));
-                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            }
-            fv += prev;
-            CUDA_CHECK(cudaMemcpyAsync(f_out, &fv, sizeof(float), cudaMemcpyHostToDevice,
-                                       ctx->stream));
+            // device scalar: the objective never leaves HBM (one-thread add, no stream sync)
+            scalar_out_kernel<<<1, 1, 0, ctx->stream>>>(f_out, fd.p, fval, accumulate ? 1 : 0);
+            launch_count(ctx, "scalar_out");
         } else {
             if (accumulate) *f_out += (float)fval;
             else *f_out = (float)fval;

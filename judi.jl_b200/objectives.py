@@ -5,8 +5,10 @@ pool replaced by one process per GPU and a single all-reduce of (gradient, objec
 
 Shots are independent until the final sum, so they are partitioned round-robin over the ranks
 (shot i -> rank i mod world_size); every rank accumulates its shots locally (in HBM when the
-inputs are device resident) and one `torch.distributed.all_reduce(SUM)` -- NCCL over NVLink on
-GPUs, gloo in the CPU tests -- replaces `reduce!`'s binary tree over Futures.
+inputs are device resident) and ONE all-reduce replaces `reduce!`'s binary tree over Futures: on
+GPUs it is issued inside the C-ABI (`judi_fg_reduce`: crop on the device, ncclAllReduce of the
+physical-grid gradient + objective on the library's stream; torch.distributed only carries the
+128-byte NCCL id at start-up), in the CPU tests it is a gloo all-reduce of host arrays.
 """
 import numpy as np
 
@@ -127,6 +129,76 @@ def multi_src_fg(model, shots, dm=None, lin=False, nlind=False, misfit=None, red
     return np.float32(f), remove_padding(g, model.padsizes, true_adjoint=sum_padding)
 
 
+def _nccl_library():
+    """Path of the NCCL library the process should bind (torch's bundled copy when torch.distributed
+    already runs over NCCL, so that one libnccl serves both), or None for the loader's default."""
+    try:
+        import nvidia.nccl as _n
+        import os as _os
+        for d in list(getattr(_n, "__path__", [])):
+            f = _os.path.join(d, "lib", "libnccl.so.2")
+            if _os.path.exists(f):
+                return f
+    except ImportError:
+        pass
+    return None
+
+
+def init_comm(ctx):
+    """Create the library's own NCCL communicator for this rank's context (judi_comm_init):
+    rank 0 draws the unique id, the 128 bytes travel over the host-side rendezvous
+    (torch.distributed's store -- control plane only, as Julia's Distributed would do it), and
+    from then on the data-plane reduction is `judi_fg_reduce`, inside the C-ABI.
+    No-op when already initialised or when there is one rank."""
+    import ctypes
+    import os
+    from . import _lib as L
+    dist = _dist()
+    ws = dist.get_world_size() if dist else 1
+    if L.lib().judi_comm_size(ctx.h) == ws and (ws == 1 or getattr(ctx, "_comm_ready", False)):
+        return ws
+    rk = dist.get_rank() if dist else 0
+    if ws == 1:
+        L.check(L.lib().judi_comm_init(ctx.h, 1, 0, None))
+        ctx._comm_ready = True
+        return 1
+    if "JUDI_NCCL_LIB" not in os.environ:
+        f = _nccl_library()
+        if f:
+            os.environ["JUDI_NCCL_LIB"] = f
+    ident = ctypes.create_string_buffer(128)
+    if rk == 0:
+        L.check(L.lib().judi_comm_unique_id(ident))
+    box = [ident.raw]
+    dist.broadcast_object_list(box, src=0)
+    ident = ctypes.create_string_buffer(box[0], 128)
+    L.check(L.lib().judi_comm_init(ctx.h, ws, rk, ident))
+    ctx._comm_ready = True
+    return ws
+
+
+def fg_reduce(model, grad_padded_dev, f_dev, sum_padding=False, out=None):
+    """judi_fg_reduce: crop / fold the padded device accumulator, append the objective, ONE
+    ncclAllReduce of prod(n)+1 floats on the library's stream, result in page-locked host memory.
+    `grad_padded_dev`, `f_dev`: torch CUDA tensors (or raw device pointers)."""
+    import ctypes
+    from . import _lib as L
+    ptr = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else int(t)
+    if out is not None and hasattr(out, "data_ptr"):
+        # device output: `out` holds prod(n)+1 floats, gradient then objective (stays in HBM)
+        nphys = int(np.prod(model.shape))
+        assert out.numel() >= nphys + 1
+        L.check(L.lib().judi_fg_reduce(model.h, ptr(grad_padded_dev), ptr(f_dev), int(bool(sum_padding)),
+                                       out.data_ptr(), out.data_ptr() + 4 * nphys, L.OUT_ON_DEVICE))
+        return out[nphys], out[:nphys]
+    g = out if out is not None else np.zeros(model.shape, dtype=np.float32, order="F")
+    assert g.flags.f_contiguous and g.shape == tuple(model.shape)
+    f = ctypes.c_float(0)
+    L.check(L.lib().judi_fg_reduce(model.h, ptr(grad_padded_dev), ptr(f_dev), int(bool(sum_padding)),
+                                   g.ctypes.data, ctypes.addressof(f), 0))
+    return np.float32(f.value), g
+
+
 _hbm_acc = {}
 _MULTISHOT_OPTIONS = {"is_residual", "checkpointing", "n_checkpoints", "t_sub", "ic", "snapshot_region", "f0"}
 
@@ -150,6 +222,8 @@ def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_paddin
     red, host = _hbm_acc[key]
     stream = torch.cuda.ExternalStream(model.ctx.stream, device=dev)
     nccl = reduce and dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+    if nccl:
+        init_comm(model.ctx)
     with torch.cuda.stream(stream):
         red.zero_()
         if misfit is None and not (set(options) - _MULTISHOT_OPTIONS) and mine:
@@ -163,16 +237,15 @@ def _multi_src_fg_hbm(model, shots, mine, lin, nlind, misfit, reduce, sum_paddin
                 interface.J_adjoint(model, sc, q, rc, dobs, return_obj=True, born_fwd=lin, nlind=nlind,
                                     misfit=misfit, grad_out=red[:n], f_out=red[n:], accumulate=True,
                                     **options)
-        if nccl:
-            dist.all_reduce(red, op=dist.ReduceOp.SUM)
         if nccl or not (reduce and dist is not None and dist.get_world_size() > 1):
-            # crop (or fold the pad) on the device: only prod(n_physical)+1 floats cross PCIe
-            from .time_modeling import remove_padding as remove_padding_device
+            # the collective lives behind the C-ABI (judi_fg_reduce): crop (or fold the pad) on the
+            # device, all-reduce prod(n_physical)+1 floats over NCCL on the library's stream, and
+            # only those cross PCIe -- no torch.distributed on the data plane
             nphys = int(np.prod(model.shape))
             g = host[:nphys].numpy().reshape(tuple(model.shape)[::-1]).T
             stream.synchronize()
-            remove_padding_device(red[:n], model, true_adjoint=sum_padding, out=g)
-            return np.float32(red[n].item()), g
+            f, g = fg_reduce(model, red[:n], red[n:], sum_padding=sum_padding, out=g)
+            return f, g
         host.copy_(red, non_blocking=True)      # non-NCCL process group: reduce on the host
         stream.synchronize()
         dist.all_reduce(host, op=dist.ReduceOp.SUM)

@@ -202,11 +202,12 @@ def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, 
     q_in = time_resample_to_dt(src_data, src_geom, dt_comp, context=model.ctx)
     sc, rc = src_geom.coords(ndim), rec_geom.coords(ndim)
     if op in ("forward", "adjoint") and rec_data is None:
-        rec, _ = interface.forward_rec(model, sc, q_in, rc, f0=o.f0, illum=illum,
-                                       fw=(op == "forward") == fw)
+        # `op` only selects the post-processing; the direction is `fw` alone, as `_prop_fw(F)`
+        # hands it to devito_interface (propagation.jl:9,52-54; python_interface.jl:42)
+        rec, _ = interface.forward_rec(model, sc, q_in, rc, f0=o.f0, illum=illum, fw=fw)
         return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
     if op == "born":
-        rec, _ = interface.born_rec(model, sc, q_in, rc, ic=o.IC, f0=o.f0, illum=illum)
+        rec, _ = interface.born_rec(model, sc, q_in, rc, ic=o.IC, f0=o.f0, illum=illum, fw=fw)
         return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
     if op == "adjoint_born":
         d_in = time_resample_to_dt(rec_data, rec_geom, dt_comp, context=model.ctx)
@@ -215,7 +216,7 @@ def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, 
                                       t_sub=o.subsampling_factor,
                                       checkpointing=o.optimal_checkpointing, ic=o.IC, f0=o.f0,
                                       freq_list=o.frequencies or None,
-                                      dft_sub=o.dft_subsampling_factor,
+                                      dft_sub=o.dft_subsampling_factor, fw=fw,
                                       snapshot_region=o.snapshot_region)
         g = remove_padding(g, model, true_adjoint=o.sum_padding)
         if o.limit_m and tuple(shape) != full_shape:

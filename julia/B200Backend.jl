@@ -162,6 +162,27 @@ function b200_fg_multishot(h, shots::Vector{<:NTuple{4,Array{Float32}}}, options
     return f[], g
 end
 
+# ---- the sum over workers behind the C-ABI (replaces reduce! / run_and_reduce, distributed.jl:60-95,
+# propagation.jl:23-50).  One Julia worker per GPU: worker 1 draws the NCCL id, the 128 bytes travel
+# over Distributed (`id = remotecall_fetch(b200_comm_id, 1)`), every worker calls b200_comm_init.
+b200_comm_id() = (id = zeros(UInt8, 128); check(ccall((:judi_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
+b200_comm_init(id::Vector{UInt8}, nranks::Int, rank::Int) =
+    check(ccall((:judi_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx(), nranks, rank, id))
+# multi_src_fg! of this worker's shots + the reduction over all workers: every worker gets the
+# physical-grid gradient and the objective of ALL shots (propagation.jl:99-106, misfit_fg.jl:77)
+function b200_fg_multishot_reduced(h, shots::Vector{<:NTuple{4,Array{Float32}}}, options::JUDIOptions, n;
+                                   born_fwd=false, nlind=false)
+    g = pin!(zeros(Float32, n)); f = Ref{Cfloat}(0)
+    o = JudiJopts(false, options.optimal_checkpointing, 0, options.subsampling_factor, IC[options.IC],
+                  born_fwd, nlind, false, options.sum_padding ? 0 : 1, Ptr{Cfloat}(C_NULL), 0, 1, Ptr{Cfloat}(C_NULL))
+    cs = [JudiShot(size(sc, 1), pointer(sc), pointer(q), size(q, 1), size(rc, 1), pointer(rc), pointer(d))
+          for (sc, q, rc, d) in shots]
+    GC.@preserve shots cs check(ccall((:judi_fg_multishot_reduced, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{JudiShot}, Ref{JudiJopts}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Cfloat}, Ptr{Cfloat}, Cint),
+                h, length(cs), cs, o, C_NULL, C_NULL, options.sum_padding, f, g, 0))
+    return f[], g
+end
+
 # ---- extended and wavefield sources (python_interface.jl:58-81, 124-198 -> interface.py:50-204, 244-276)
 # `weights` arrive on the physical grid; JUDI zero-pads them (python_interface.jl:129)
 function b200_forward_rec_w(h, wpad::Array{Float32}, qIn, rec_coords, fw::Bool)

@@ -1,0 +1,141 @@
+"""Known answers printed by the reference's own notebook
+/root/reference/examples/notebooks/03_constrained_fwi.ipynb (a fully specified, deterministic
+experiment: cells 4-6 model, 20-22 geometry, 26-29 modelling, 35 `scale`, 42-48 objective and
+gradient):
+
+    scale  = 10 / sqrt(norm(dobs)^2 / length(dobs.data)) = 0.018069575143305386     (cell 35)
+    phi    = .5 norm(F0 q - dobs)^2                      = 8.04513e+05               (cell 48, it. 0)
+    gscale = .25 / maximum(J'(F0 q - dobs) .* wb_mask)   = 3.15937f-5                (cell 44)
+
+n = (251, 251), d = 15 m, 1.7 km/s box `[101:150, 101:150]` in 1.5 km/s, 8 sources on the left edge
+(x = 15 m), 251 receivers on the right edge (x = 3735 m), tn = 4000 ms, dt = 2 ms, Ricker 5 Hz,
+default Options; `dobs.data` is a vector of 8 shot records, so `length(dobs.data) == 8`.
+
+WHAT THIS FILE PINS, AND WHAT IT DOES NOT.  The notebook's outputs were produced with Julia 1.6.3
+(kernelspec of the notebook), i.e. a 2021 JUDI/Devito, not with the v4.1.7 sources under
+/root/reference: the restatement of v4.1.7 (oracle, fp64) gives scale = 0.0160153 (-11.4 %),
+phi = 9.381e5 (+16.6 %), gscale = 2.718e-5 (-14.0 %), with either judiVector norm convention
+(src/TimeModeling/Types/abstract.jl:116-126, dt-weighted, is the closer one: the unweighted one is
+off by +25 % / -42 %).  Sources and receivers of this experiment sit ON the edge of the absorbing
+layer, which makes all three numbers functions of the layer rather than of the stencil: widening
+the layer from 40 to 120 cells moves `scale` by +5.2 %, scaling the damping profile by 4 by -7.9 %,
+while the damping-profile change between the two code generations we can reconstruct (layer of nbl
+instead of nbl-3 cells) and the older dt (0.42 h / vmax) move it by 0.2 %.  The residual
+therefore cannot be attributed to any [dv] item of SURVEY Appendix A, and these numbers cannot pin
+the stencil to better than ~15 %.  They are kept here as (1) an end-to-end regression of the
+JUDI-level driver (time_resample -> propagate -> time_resample, judiVector norm, remove_padding)
+on a published experiment, GPU against oracle at the north-star tolerances, and (2) a recorded,
+bounded deviation from the reference's printed values (asserted within 20 %).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+NB_SCALE = 0.018069575143305386
+NB_PHI = 8.04513e+05
+NB_GSCALE = 3.15937e-5
+
+N = (251, 251)
+D = (15., 15.)
+ORG = (0., 0.)
+TN, DT, F0 = 4000., np.float32(2.), 0.005
+NSRC, NREC = 8, 251
+
+
+def _models():
+    m = np.float32(1.5) ** -2 * np.ones(N, np.float32)
+    m[100:150, 100:150] = np.float32(1.7) ** -2           # Julia m[101:150, 101:150]
+    m0 = (np.float32(1) / np.float32(1.5) ** 2) * np.ones(N, np.float32)
+    return m, m0
+
+
+def _geometry():
+    zsrc = np.linspace(np.float32(0), np.float32((N[1] - 1) * D[1]), NSRC, dtype=np.float32)
+    zrec = np.linspace(np.float32(0), np.float32((N[1] - 1) * D[1]), NREC, dtype=np.float32)
+    xrec = np.full(NREC, (N[0] - 2) * D[0], np.float32)
+    return zsrc, np.stack([xrec, zrec], axis=1)
+
+
+def _wb_mask():
+    wb = np.ones(N, np.float32)
+    wb[:5, :] = 0      # wb_mask[1:5, :] .= 0
+    wb[-6:, :] = 0     # wb_mask[end-5:end, :] .= 0
+    return wb
+
+
+def oracle_numbers(precision="f64"):
+    m, m0 = _models()
+    zsrc, rec = _geometry()
+    q = O.ricker_wavelet(TN, DT, F0)
+    nt = q.shape[0]
+    M = O.Model(ORG, D, N, space_order=8, nbl=40, m=m, precision=precision)
+    M0 = O.Model(ORG, D, N, space_order=8, nbl=40, m=m0, precision=precision)
+
+    def resampled(model):
+        dtc = np.float32(model.critical_dt)
+        ntc = int(np.floor(np.float32(TN) / dtc)) + 1
+        return dtc, ntc, O.time_resample(q, (0, DT, nt), (0, dtc, ntc))
+    dtc, ntc, qc = resampled(M)
+    dt0, nt0, q0 = resampled(M0)
+    nd, phi, G = 0., 0., np.zeros(N)
+    for i in range(NSRC):
+        src = np.array([[D[0], zsrc[i]]], np.float32)
+        r, _ = O.forward_rec(M, src, qc, rec)
+        dobs = O.time_resample(r, (0, dtc, r.shape[0]), (0, DT, nt))
+        nd += float(DT) * float(np.sum(dobs.astype(np.float64) ** 2))
+        r0, _ = O.forward_rec(M0, src, q0, rec)
+        d0 = O.time_resample(r0, (0, dt0, r0.shape[0]), (0, DT, nt))
+        res = d0 - dobs
+        phi += 0.5 * float(DT) * float(np.sum(res.astype(np.float64) ** 2))
+        resc = O.time_resample(res, (0, DT, nt), (0, dt0, nt0))
+        g, _, _ = O.J_adjoint(M0, src, q0, rec, resc, is_residual=True)
+        G += O.remove_padding(g, M0.padsizes)
+    return 10.0 / np.sqrt(nd / NSRC), phi, 0.25 / float((G * _wb_mask()).max()), G
+
+
+def test_notebook_03_known_answers_oracle_f64():
+    scale, phi, gscale, _ = oracle_numbers("f64")
+    dev = [scale / NB_SCALE - 1, phi / NB_PHI - 1, gscale / NB_GSCALE - 1]
+    print("notebook 03: scale %.7f (%+.1f%%), phi %.5e (%+.1f%%), gscale %.5e (%+.1f%%)"
+          % (scale, 100 * dev[0], phi, 100 * dev[1], gscale, 100 * dev[2]))
+    # regression pins of the v4.1.7 restatement on this experiment
+    assert abs(scale - 0.0160153) < 2e-6
+    assert abs(phi / 9.3808e5 - 1) < 2e-4
+    assert abs(gscale / 2.7179e-5 - 1) < 2e-4
+    # recorded deviation from the values a 2021 JUDI printed (see the module docstring)
+    assert max(abs(x) for x in dev) < 0.20
+
+
+@pytest.mark.gpu
+def test_notebook_03_through_time_modeling_on_the_gpu():
+    """The same experiment through the library's per-shot driver (judi.jl_b200.time_modeling:
+    device time_resample, propagation, device remove_padding) against the fp64 oracle."""
+    import judi_jl_b200 as J
+    from judi_jl_b200 import time_modeling as TM
+    m, m0 = _models()
+    zsrc, rec = _geometry()
+    q = O.ricker_wavelet(TN, DT, F0)
+    scale_o, phi_o, gscale_o, G_o = oracle_numbers("f64")
+    rgeom = TM.Geometry(rec[:, 0], None, rec[:, 1], DT, TN)
+    opt = TM.Options()
+    nd, phi, G = 0., 0., np.zeros(N)
+    for i in range(NSRC):
+        sgeom = TM.Geometry([D[0]], None, [zsrc[i]], DT, TN)
+        dobs = TM.time_modeling(ORG, D, N, {"m": m}, sgeom, q, rgeom, None, None, "forward", opt)
+        d0 = TM.time_modeling(ORG, D, N, {"m": m0}, sgeom, q, rgeom, None, None, "forward", opt)
+        assert dobs.shape == (2001, NREC)
+        nd += float(DT) * float(np.sum(dobs.astype(np.float64) ** 2))
+        res = np.asfortranarray(d0 - dobs)
+        phi += 0.5 * float(DT) * float(np.sum(res.astype(np.float64) ** 2))
+        G += TM.time_modeling(ORG, D, N, {"m": m0}, sgeom, q, rgeom, res, None, "adjoint_born", opt)
+    scale = 10.0 / np.sqrt(nd / NSRC)
+    gscale = 0.25 / float((G * _wb_mask()).max())
+    print("GPU vs fp64 oracle: scale %.3e, phi %.3e, gscale %.3e, gradient rel-L2 %.3e"
+          % (abs(scale / scale_o - 1), abs(phi / phi_o - 1), abs(gscale / gscale_o - 1),
+             np.linalg.norm(G - G_o) / np.linalg.norm(G_o)))
+    assert abs(scale / scale_o - 1) < 1e-4
+    assert abs(phi / phi_o - 1) < 1e-3          # a difference of two nearly equal records
+    assert abs(gscale / gscale_o - 1) < 1e-3
+    assert np.linalg.norm(G - G_o) / np.linalg.norm(G_o) < 1e-3
+    assert abs(scale / NB_SCALE - 1) < 0.20
