@@ -54,9 +54,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5", "c3fwd", "c4"],
                     help="c3 (default): the 3-D acoustic FWI gradient BASELINE.json's metric names; "
-                         "c5: secondary line, 3-D TTI forward + gradient on 301x301x201")
+                         "c5: 3-D TTI forward + gradient on 301x301x201; c3fwd: forward modelling "
+                         "of shots on the C3 grid, no collective; c4: LS-RTM on the C3 grid, Born "
+                         "modelling + adjoint Jacobian with in-HBM checkpointing (secondary lines)")
     a = ap.parse_args()
     if a.workload == "c5" and a.shape == list(SHAPE):
         a.shape = [301, 301, 201]
@@ -102,10 +104,32 @@ def ricker(nt, dt, f0):
     return ((1 - 2 * r ** 2) * np.exp(-r ** 2)).astype(np.float32).reshape(nt, 1)
 
 
-def workload_name(shape, nt, t_sub, region, tti=False):
-    return ("3D %s so=8 FWI gradient (fwd+snapshots, adj+IC), n=%dx%dx%d d=25m nbl=40, "
-            "10201 receivers, nt=%d, t_sub=%d, %s-domain snapshots, 1 shot/GPU/step"
-            % ("TTI" if tti else "acoustic", shape[0], shape[1], shape[2], nt, t_sub, region))
+METRIC = {"c3": "fwi_gradient_shots_per_s", "c5": "fwi_gradient_shots_per_s",
+          "c3fwd": "forward_modeling_shots_per_s", "c4": "lsrtm_born_plus_adjoint_shots_per_s"}
+
+
+def workload_name(shape, nt, t_sub, region, workload="c3"):
+    head = "3D %s so=8" % ("TTI" if workload == "c5" else "acoustic")
+    tail = "n=%dx%dx%d d=25m nbl=40, 10201 receivers, nt=%d" % (shape[0], shape[1], shape[2], nt)
+    if workload == "c3fwd":
+        return "%s forward modelling (one shot record), %s, 1 shot/GPU/step, no collective" % (head, tail)
+    if workload == "c4":
+        return ("%s LS-RTM: Born modelling J*dm + adjoint Jacobian J'*d with in-HBM checkpointing "
+                "(%s-domain snapshots), %s, 1 shot/GPU/step" % (head, region, tail))
+    return ("%s FWI gradient (fwd+snapshots, adj+IC), %s, t_sub=%d, %s-domain snapshots, "
+            "1 shot/GPU/step" % (head, tail, t_sub, region))
+
+
+def config_dict(args, nt, dtc):
+    """The SAME dict for the GPU arm and the CPU (`--impl reference`) arm."""
+    shape = tuple(args.shape)
+    npad = [n + 2 * NBL for n in shape]
+    npts = float(np.prod(npad))
+    return {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region, args.workload),
+            "padded_grid": npad, "nt": nt, "dt_ms": dtc,
+            "l2_policy": "inputs_larger_than_L2 (each field %.0f MB vs 126 MB L2)" % (4e-6 * npts),
+            "parallelism": "shots partitioned over %d GPU(s), %s" % (
+                args.gpus, "no collective" if args.workload == "c3fwd" else "one all-reduce per step")}
 
 
 def tti_params(v):
@@ -179,9 +203,14 @@ class ClockSampler(object):
 
 
 # ---- CPU arm: the oracle on the host cores -------------------------------------------------------
-def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0, tti=False, dt=DT):
-    """Times a bounded sample of the workload with the CPU oracle (all host threads):
-    `ns` forward steps + `ns` adjoint+IC steps on the full grid, extrapolated to one shot."""
+def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0, tti=False, dt=DT, workload="c3"):
+    """Times a bounded sample of the workload with the CPU oracle (all host threads) on the full
+    grid and extrapolates linearly to one shot:
+      c3 / c5  ns forward steps + ns adjoint+IC steps
+      c3fwd    ns forward steps
+      c4       Born sweep (two fields = 2 forward steps per time step) + J' with checkpointing
+               (forward, recomputed forward, adjoint+IC): 4 forward steps + 1 adjoint+IC step per
+               time step, from the forward-only and the forward+adjoint samples"""
     from oracle import oracle as O
     O.build()
     ncores = O.set_threads(os.cpu_count() or 1)   # torchrun sets OMP_NUM_THREADS=1: override
@@ -191,26 +220,45 @@ def cpu_sample(shape, nt, t_sub, seconds, steps=1, warmup=0, tti=False, dt=DT):
         extra["phi"] = np.full(shape, extra["phi"], dtype=np.float32)
     model = O.Model((0., 0., 0.), SPACING, shape, space_order=SO, nbl=NBL,
                     m=(1 / v0 ** 2).astype(np.float32), dt=dt, precision="f32", **extra)
-    t1 = O.time_steps(model, 2, True, t_sub)          # calibration (also first-touch of memory)
-    per_pair = max(t1 / 2, 1e-6)
+    grad = workload != "c3fwd"
+    k = 1 if workload == "c4" else t_sub
+    t1 = O.time_steps(model, 2, grad, k)          # calibration (also first-touch of memory)
+    per_pair = max(t1 / 2, 1e-6) * (2.5 if workload == "c4" else 1.0)
     ns = int(max(4, min(nt - 2, seconds / per_pair)))
-    ns -= ns % t_sub
-    ns = max(ns, t_sub)
-    times = []
+    ns -= ns % k
+    ns = max(ns, k)
+    times, fwd_times = [], []
     for _ in range(warmup + steps):
-        times.append(O.time_steps(model, ns, True, t_sub))
-    times = times[warmup:]
-    sec_per_shot = float(np.mean(times)) / ns * (nt - 2)
+        times.append(O.time_steps(model, ns, grad, k))
+        if workload == "c4":
+            fwd_times.append(O.time_steps(model, ns, False, 1))
+    times, fwd_times = times[warmup:], fwd_times[warmup:]
+    per_step = float(np.mean(times)) / ns
     npts = float(np.prod(model.shape_pml))
+    if workload == "c4":
+        per_step += 3.0 * float(np.mean(fwd_times)) / ns
+        what = ("%d of %d time steps of [forward + adjoint+IC] and of [forward] on the full "
+                "%dx%dx%d padded grid; one LS-RTM shot = Born sweep (2 forward steps per time step) + "
+                "J' with checkpointing (forward, recomputed forward, adjoint+IC), i.e. 3 x forward + "
+                "(forward + adjoint+IC) per time step" % (ns, nt - 2, model.shape_pml[0],
+                                                           model.shape_pml[1], model.shape_pml[2]))
+        sweeps = 5
+    elif workload == "c3fwd":
+        what = "%d of %d forward time steps on the full %dx%dx%d padded grid" % (
+            ns, nt - 2, model.shape_pml[0], model.shape_pml[1], model.shape_pml[2])
+        sweeps = 1
+    else:
+        what = ("%d of %d forward + %d of %d adjoint+IC time steps on the full %dx%dx%d padded grid "
+                "(t_sub=%d)" % (ns, nt - 2, ns, nt - 2, model.shape_pml[0], model.shape_pml[1],
+                                model.shape_pml[2], t_sub))
+        sweeps = 2
+    sec_per_shot = per_step * (nt - 2)
     return {"value": 1.0 / sec_per_shot, "unit": "shots/s", "cores": ncores,
             "kind": "port",
-            "sample": "%d of %d forward + %d of %d adjoint+IC time steps on the full %dx%dx%d "
-                      "padded grid (t_sub=%d), extrapolated linearly to one shot; OpenMP, all %d "
-                      "host threads; oracle = C port of the reference's Devito schedule (Devito "
-                      "itself is not installable offline)"
-                      % (ns, nt - 2, ns, nt - 2, model.shape_pml[0], model.shape_pml[1],
-                         model.shape_pml[2], t_sub, ncores),
-            "gpts_per_s": 2 * ns * npts / float(np.mean(times)) / 1e9,
+            "sample": what + ", extrapolated linearly to one shot; OpenMP, all %d host threads; "
+                      "oracle = C port of the reference's Devito schedule (Devito itself is not "
+                      "installable offline)" % ncores,
+            "gpts_per_s": sweeps * npts / per_step / 1e9,
             "ms_per_step": 1e3 * sec_per_shot}
 
 
@@ -222,13 +270,15 @@ def run_reference(args):
     tti, dtc = args.workload == "c5", model_dt(args)
     nt = int(np.floor(args.tn / dtc)) + 1
     r = cpu_sample(shape, nt, args.t_sub, args.cpu_seconds / 2, steps=args.steps,
-                   warmup=args.warmup, tti=tti, dt=dtc)
-    line = {"impl": "reference", "metric": "fwi_gradient_shots_per_s", "value": r["value"],
+                   warmup=args.warmup, tti=tti, dt=dtc, workload=args.workload)
+    line = {"impl": "reference", "impl_kind": "cpu_port",
+            "metric": METRIC[args.workload], "value": r["value"],
             "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region, tti),
-                       "note": "CPU arm: one process, all host threads, no GPU"},
+            "config": config_dict(args, nt, dtc),
+            "note": "CPU arm: the oracle (a C port of the reference's Devito schedule, NOT Devito "
+                    "itself), one process, all host threads, no GPU; bounded sample, extrapolated",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "gpts_per_s": r["gpts_per_s"],
             "e2e": {"value": r["value"], "unit": "shots/s", "h2d_bytes_per_step": 0,
@@ -247,18 +297,23 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # torch.distributed: rendezvous, barriers and the max-over-ranks of the timings only; the
+        # data-plane all-reduce is the library's own (judi_fg_reduce, NCCL bound inside the C-ABI)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = J.get_context(local)
+    J.objectives.init_comm(ctx)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
+    wl = args.workload
     shape = tuple(args.shape)
-    tti, dtc = args.workload == "c5", model_dt(args)
+    tti, dtc = wl == "c5", model_dt(args)
     nt = int(np.floor(args.tn / dtc)) + 1
     v = velocity(shape)
     v0 = smooth_model(v)
     m_true = np.asfortranarray((1 / v ** 2).astype(np.float32))
     m0 = np.asfortranarray((1 / v0 ** 2).astype(np.float32))
+    dm = np.asfortranarray(m_true - m0) if wl == "c4" else None
     src, rec = geometry(shape, rank)
     q = ricker(nt, dtc, F0)
     nrec = rec.shape[0]
@@ -267,37 +322,52 @@ def run_b200(args):
         kw.update(tti_params(v0))     # the same anisotropy for the true and the starting model
 
     # ---- untimed setup: observed data of this rank's shot from the true model ---------------
-    mt = J.Model((0., 0., 0.), SPACING, shape, m=m_true, **kw)
-    dobs, _ = J.forward_rec(mt, src, q, rec)
-    del mt
-    npad = None
+    dobs = None
+    if wl in ("c3", "c5"):
+        mt = J.Model((0., 0., 0.), SPACING, shape, m=m_true, **kw)
+        dobs, _ = J.forward_rec(mt, src, q, rec)
+        del mt
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def to_dev(a):      # x fastest == reversed shape, contiguous
+        return torch.from_numpy(np.ascontiguousarray(a.transpose(*range(a.ndim - 1, -1, -1)))).to(dev)
+
     with torch.cuda.stream(stream):
-        # device-resident inputs (x fastest == reversed shape, contiguous)
-        m0_d = torch.from_numpy(np.ascontiguousarray(m0.transpose(2, 1, 0))).to(dev)
-        q_d = torch.from_numpy(np.ascontiguousarray(q.T)).to(dev)
-        dobs_d = torch.from_numpy(np.ascontiguousarray(dobs.T)).to(dev)
-        kw_d = {k_: (torch.from_numpy(np.ascontiguousarray(v_.transpose(2, 1, 0))).to(dev)
-                     if isinstance(v_, np.ndarray) and v_.ndim == 3 else v_) for k_, v_ in kw.items()}
+        m0_d, q_d = to_dev(m0), to_dev(q)
+        kw_d = {k_: (to_dev(v_) if isinstance(v_, np.ndarray) and v_.ndim == 3 else v_)
+                for k_, v_ in kw.items()}
+        if dm is not None:
+            kw_d["dm"] = to_dev(dm)
         model = J.Model((0., 0., 0.), SPACING, shape, m=m0_d, **kw_d)
         assert abs(float(model.critical_dt) - dtc) < 1e-6 * dtc, (model.critical_dt, dtc)
         npad = model.shape_pml
-        ngrid = int(np.prod(npad))
-        red = torch.zeros(ngrid + 1, dtype=torch.float32, device=dev)   # gradient + objective
+        ngrid, nphys_i = int(np.prod(npad)), int(np.prod(shape))
+        red = torch.zeros(ngrid + 1, dtype=torch.float32, device=dev)    # padded accumulator + objective
+        out = torch.zeros(nphys_i + 1, dtype=torch.float32, device=dev)  # reduced physical gradient + objective
         grad_d, f_d = red[:ngrid], red[ngrid:]
-        opts = dict(return_obj=True, t_sub=args.t_sub, snapshot_region=args.snapshot_region,
-                    grad_out=grad_d, f_out=f_d)
+        rec_d = torch.zeros((nrec, nt), dtype=torch.float32, device=dev)
+        if dobs is not None:
+            rec_d.copy_(to_dev(dobs))
+        ckpt = wl == "c4"
+        opts = dict(return_obj=True, t_sub=1 if ckpt else args.t_sub, checkpointing=ckpt,
+                    snapshot_region=args.snapshot_region, grad_out=grad_d, f_out=f_d)
 
         def step_device():
+            if wl == "c3fwd":
+                J.forward_rec(model, src, q_d, rec, rec_out=rec_d)
+                return
             red.zero_()
-            J.J_adjoint(model, src, q_d, rec, dobs_d, accumulate=True, **opts)
-            if world > 1:
-                dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            if wl == "c4":
+                J.born_rec(model, src, q_d, rec, rec_out=rec_d)                  # d_lin = J dm
+                J.J_adjoint(model, src, q_d, rec, rec_d, is_residual=True, accumulate=True, **opts)
+            else:
+                J.J_adjoint(model, src, q_d, rec, rec_d, accumulate=True, **opts)
+            # crop on the device + ONE ncclAllReduce of prod(n)+1 floats inside the library
+            J.objectives.fg_reduce(model, grad_d, f_d, out=out)
 
         # CUDA events around every 7th stencil launch (7 is coprime with t_sub, so the sample holds
         # the plain / save / imaging-condition flavours in their true proportions); bracketing
@@ -307,6 +377,7 @@ def run_b200(args):
             step_device()
         barrier()
         ctx.reset_stats()
+        launches0 = ctx.launch_count
         clocks = ClockSampler(local)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -317,16 +388,19 @@ def run_b200(args):
         clk = clocks.stop()
         ms = e0.elapsed_time(e1)
         stats = ctx.stencil_stats()
-        launches = ctx.launch_count
-        fval = float(f_d.item())
-        gnorm = float(torch.linalg.vector_norm(grad_d).item())
+        launches = ctx.launch_count - launches0
+        if wl == "c3fwd":
+            fval, gnorm = None, float(torch.linalg.vector_norm(rec_d).item())
+        else:
+            fval = float(out[nphys_i].item())
+            gnorm = float(torch.linalg.vector_norm(out[:nphys_i]).item())
         ctx.set_option("timing", 0)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-        # ---- e2e: host buffers in, host gradient out, every step --------------------------------
+        # ---- e2e: host buffers in, host result out, every step ----------------------------------
         e2e = None
         if not args.no_e2e:
             def pinned(a):
@@ -336,20 +410,30 @@ def run_b200(args):
                 return tt, h
             keep_m, m0_h = pinned(m0)
             keep_q, q_h = pinned(q)
-            keep_d, d_h = pinned(dobs)
+            keep_d, d_h = pinned(dobs if dobs is not None else np.zeros((nt, nrec), np.float32))
+            keep_dm, dm_h = pinned(dm) if dm is not None else (None, None)
             # every model array lives in page-locked host memory (C5: the TTI parameter fields too)
             keep_kw, kw_h = [], dict(kw)
             for k_, v_ in kw.items():
                 if isinstance(v_, np.ndarray) and v_.ndim == 3:
                     t_, kw_h[k_] = pinned(v_)
                     keep_kw.append(t_)
-            # the public call: fwi_objective over `world` shots, shot i -> rank i.  Each rank
-            # builds its model from host arrays, propagates its shot from host wavelet / data,
-            # sums in HBM, one NCCL all-reduce, and every rank copies the cropped gradient back.
+            # the public call: the objective / modelling over `world` shots, shot i -> rank i.  Each
+            # rank builds its model from host arrays, propagates its shot from host wavelet / data,
+            # sums in HBM, one all-reduce inside the library, and every rank copies the cropped
+            # gradient (c3fwd: its shot record) back.
             shots = [(src, q_h, rec, d_h) if i == rank else None for i in range(world)]
 
             def step_host():
                 mh = J.Model((0., 0., 0.), SPACING, shape, m=m0_h, **kw_h)
+                if wl == "c3fwd":
+                    return None, J.objectives.forward_modeling(mh, shots)[rank]
+                if wl == "c4":
+                    mh.set_dm(dm_h)
+                    dl, _ = J.born_rec(mh, src, q_h, rec)
+                    sh = [(src, q_h, rec, dl) if i == rank else None for i in range(world)]
+                    return J.objectives.multi_src_fg(mh, sh, is_residual=True, checkpointing=True,
+                                                     snapshot_region=args.snapshot_region)
                 return J.objectives.fwi_objective(mh, shots, t_sub=args.t_sub,
                                                   snapshot_region=args.snapshot_region)
             for _ in range(min(args.warmup, 2)):
@@ -364,16 +448,24 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-            h2d = world * (m0.nbytes + q.nbytes + dobs.nbytes +
+            h2d = world * (m0.nbytes + q.nbytes + (dobs.nbytes if dobs is not None else 0) +
+                           (dm.nbytes if dm is not None else 0) +
                            sum(v_.nbytes for v_ in kw.values() if isinstance(v_, np.ndarray)))
-            d2h = world * (4 * int(np.prod(shape)) + 4)
+            if wl == "c4":
+                h2d += world * 4 * nt * nrec          # the Born data go back in as J' input
+            d2h = world * (4 * nt * nrec if wl in ("c3fwd", "c4") else 0) + \
+                (world * (4 * nphys_i + 4) if wl != "c3fwd" else 0)
             e2e = {"value": world * args.steps / wall, "unit": "shots/s",
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": 1e3 * wall / args.steps,
-                   "call": "fwi_objective(Model(host arrays), host wavelet/data) -> host gradient "
-                           "on the physical grid; bytes summed over ranks",
-                   "f_matches_device_path": bool(abs(float(fh) - fval) <= 1e-3 * abs(fval)),
-                   "gradient_l2": float(np.linalg.norm(gh.ravel(order="K").astype(np.float64)))}
+                   "call": {"c3fwd": "forward_modeling(Model(host arrays), host wavelet) -> host shot record",
+                            "c4": "born_rec(Model(host arrays), dm) -> host data; multi_src_fg(is_residual, "
+                                  "checkpointing) -> host gradient on the physical grid"}.get(
+                       wl, "fwi_objective(Model(host arrays), host wavelet/data) -> host gradient on the "
+                           "physical grid") + "; bytes summed over ranks",
+                   "result_l2": float(np.linalg.norm(gh.ravel(order="K").astype(np.float64)))}
+            if fval is not None:
+                e2e["f_matches_device_path"] = bool(abs(float(fh) - fval) <= 1e-3 * abs(fval))
 
     if rank != 0:
         if world > 1:
@@ -388,55 +480,64 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     npts = float(ngrid)
-    nphys = float(np.prod(shape)) if args.snapshot_region == "physical" else npts
+    nphys = float(nphys_i) if args.snapshot_region == "physical" else npts
     k = args.t_sub
     nsteps_t = nt - 2
     nsave = len([t_ for t_ in range(1, nt - 1) if t_ % k == 0])
-    # per shot: fwd launches 16 B/pt (+4 B per snapshot point when saving), adjoint launches
-    # 16 B/pt (+12 B per snapshot point with the imaging condition: read u_s, RMW gradient)
-    bpp, bsave, bic = (48.0, 8.0, 16.0) if tti else (16.0, 4.0, 12.0)   # DESIGN.md section 5
-    bytes_shot = 2 * nsteps_t * bpp * npts + nsave * (bsave + bic) * nphys
-    alg_bytes_per_launch = bytes_shot / (2 * nsteps_t)
+    # algorithmic bytes per grid point: step, + snapshot save, + imaging condition
+    bpp, bsave, bic = (48.0, 8.0, 16.0) if tti else (16.0, 4.0, 12.0)
+    if wl == "c3fwd":
+        bytes_shot, nlaunch = nsteps_t * bpp * npts, nsteps_t
+    elif wl == "c4":
+        # Born sweep: fused two-field launches at 32 B/pt; J' with checkpointing: forward sweep,
+        # recomputed forward sweep saving every level of a segment, adjoint sweep with the IC
+        bytes_shot = nsteps_t * 32.0 * npts + 3 * nsteps_t * bpp * npts + nsteps_t * (bsave + bic) * nphys
+        nlaunch = 4 * nsteps_t
+    else:
+        # forward launches (+ save when t % t_sub == 0), adjoint launches (+ IC on the same steps)
+        bytes_shot, nlaunch = 2 * nsteps_t * bpp * npts + nsave * (bsave + bic) * nphys, 2 * nsteps_t
+    alg_bytes_per_launch = bytes_shot / nlaunch
     ms_launch = stats["ms"] / max(stats["launches"], 1)
     achieved = alg_bytes_per_launch / (ms_launch * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-            "tti3d_tma_bytes_per_launch" if tti else "acoustic3d_tma_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("tti3d_tma_bytes_per_launch" if tti else "acoustic3d_tma_bytes_per_launch")
+        traffic_src = tj.get("source")
     except Exception:
         pass
+    kname = "tti3d_tma" if tti else "acoustic3d_tma"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("tti3d_tma" if tti else "acoustic3d_tma") +
-                          " (fwd / fwd+save / adj / adj+IC launches averaged)",
+                "traffic_source": "ncu --set full capture committed under profiles/ (%s); not "
+                                  "re-measured in this run" % traffic_src,
+                "kernel": kname + " (all stencil launches of the step averaged)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "avg_launch_ms": ms_launch, "launches_timed": stats["launches"],
-                "launches_in_region": 2 * nsteps_t * args.steps,
+                "launches_in_region": nlaunch * args.steps,
                 "avg_launch_ms_by_flavour": {k_: v_["ms"] / v_["launches"]
                                              for k_, v_ in stats["kinds"].items()},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
                                "fallback 6650 GB/s (of fallback)"}
 
     shots = world * args.steps
-    line = {"metric": "fwi_gradient_shots_per_s", "value": shots / (ms * 1e-3), "unit": "shots/s",
+    sweeps = {"c3fwd": 1, "c4": 5}.get(wl, 2)       # grid sweeps per time step (c4: the Born step updates two fields)
+    line = {"metric": METRIC[wl], "value": shots / (ms * 1e-3), "unit": "shots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, nt, args.t_sub, args.snapshot_region, tti),
-                       "padded_grid": list(npad), "nt": nt, "dt_ms": dtc,
-                       "l2_policy": "inputs_larger_than_L2 (each field %.0f MB vs 126 MB L2)"
-                                    % (4e-6 * npts),
-                       "parallelism": "shots partitioned over %d GPU(s), one all-reduce per step"
-                                      % world},
-            "gpts_per_s": shots * 2 * nsteps_t * npts / (ms * 1e-3) / 1e9,
+            "config": config_dict(args, nt, dtc),
+            "gpts_per_s": shots * sweeps * nsteps_t * npts / (ms * 1e-3) / 1e9,
             "clocks": clk, "gpu_launches": int(launches), "roofline": roofline,
-            "objective": fval, "gradient_l2": gnorm}
+            "collective": "none" if wl == "c3fwd" else
+                          "ncclAllReduce of %d floats inside libjudi_b200 (judi_fg_reduce)" % (nphys_i + 1),
+            "objective": fval, "result_l2": gnorm}
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = {kk: vv for kk, vv in
                                 cpu_sample(shape, nt, args.t_sub, args.cpu_seconds, tti=tti,
-                                           dt=dtc).items()
+                                           dt=dtc, workload=wl).items()
                                 if kk in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -213,3 +213,92 @@ def test_fwi_objective_hbm_accumulation_matches_oracle_sum():
         assert g.shape == args["shape"]
         assert abs(float(f) - fs) <= 1e-4 * abs(fs)
         assert rel_l2(g, gref) < 1e-3
+
+
+@pytest.mark.gpu
+def test_time_modeling_direction_comes_from_fw_alone():
+    """_time_modeling: `op` selects the post-processing, the direction is `fw` (propagation.jl:9,
+    52-54 -> python_interface.jl:42).  F' is called as op=:adjoint, fw=false."""
+    import judi_jl_b200 as J
+    args = model_args("iso", 2, 8, with_dm=False, n=(61, 51), nbl=12)
+    om = O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dtc = float(om.critical_dt)
+    nt = 150
+    T = np.float32((nt - 1) * dtc)
+    # y lives on the receiver geometry; F' injects it there and records at the source position
+    rg = J.Geometry(rec[:, 0], None, rec[:, 1], dt=dtc, t=T)
+    sg = J.Geometry(src[:, 0], None, src[:, 1], dt=dtc, t=T)
+    y = np.random.default_rng(4).standard_normal((rg.nt, rec.shape[0])).astype(np.float32)
+    opt = J.Options(space_order=8, nbl=12)
+    params = {"m": args["m"]}
+    qa = J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, rg, y, sg,
+                                       None, None, "adjoint", opt, fw=False)
+    qao, _ = O.forward_rec(om, rec, y[:rg.nt], src, fw=False)
+    assert rel_l2(qa, qao[:qa.shape[0]]) < 1e-4
+    qf = J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, rg, y, sg,
+                                       None, None, "adjoint", opt, fw=True)
+    assert rel_l2(qf, qao[:qf.shape[0]]) > 0.5       # the forward propagator is something else
+    # the Jacobian of F' is not built: it must raise, not run J of F
+    with pytest.raises(NotImplementedError):
+        J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, sg,
+                                      O.ricker_wavelet(T, dtc, 0.02), rg, None,
+                                      np.ones(args["shape"], np.float32), "born", opt, fw=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_lsrtm_objective_without_a_perturbation(ndim):
+    """born_fwd with dm = None (propagators.py:181-194): the linearised record stays zero, so
+    nlind=False gives residual = -dobs, f = dt/2 |dobs|^2, and nlind=True is the fwi objective."""
+    import judi_jl_b200 as J
+    args = model_args("iso", ndim, 8, with_dm=False)
+    gm, om = J.Model(**args), O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dt = float(om.critical_dt)
+    q = O.ricker_wavelet(119 * dt, dt, 0.02)[:120]
+    d, _ = O.forward_rec(om, src, q, rec)
+    dobs = (0.8 * d).astype(np.float32)
+    f, g, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=False)
+    fo, go, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=False)
+    assert abs(float(fo) - 0.5 * dt * np.linalg.norm(dobs) ** 2) <= 1e-5 * abs(float(fo))
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, go) < 1e-3
+    f2, g2, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, born_fwd=True, nlind=True)
+    f3, g3, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True)
+    assert f2 == f3 and np.array_equal(g2, g3)
+    # the multi-shot entry point (2-D: lockstep batch) follows the same rule
+    fm, gmm = J.objectives.lsrtm_objective(gm, [(src, q, rec, dobs), (src, q, rec, dobs)], dm=None)
+    assert abs(float(fm) - 2 * float(fo)) <= 1e-4 * abs(2 * float(fo))
+    assert rel_l2(gmm, 2 * O.remove_padding(go, om.padsizes)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_time_resample_rejects_an_axis_that_starts_before_the_data():
+    import judi_jl_b200 as J
+    a = np.ones((50, 3), np.float32)
+    with pytest.raises(J.JudiB200Error, match="starts before"):
+        J.time_modeling.time_resample(a, (8., 2., 50), (0., 2., 50))
+
+
+@pytest.mark.gpu
+def test_single_rank_communicator_and_trim():
+    """judi_comm_init with one rank needs no NCCL; judi_fg_reduce then returns the local sums;
+    judi_ctx_trim gives cached memory back and the context keeps working."""
+    import ctypes
+    import judi_jl_b200 as J
+    from judi_jl_b200 import _lib as L
+    ctx = J.get_context()
+    assert J.objectives.init_comm(ctx) == 1
+    assert L.lib().judi_comm_size(ctx.h) == 1 and L.lib().judi_comm_rank(ctx.h) == 0
+    L.check(L.lib().judi_ctx_trim(ctx.h))
+    args = model_args("iso", 2, 8, with_dm=False, n=(61, 51), nbl=12)
+    gm, om = J.Model(**args), O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dt = float(om.critical_dt)
+    q = O.ricker_wavelet(99 * dt, dt, 0.02)[:100]
+    d, _ = O.forward_rec(om, src, q, rec)
+    f, g = J.objectives.fwi_objective(gm, [(src, q, rec, (0.5 * d).astype(np.float32))])
+    fo, go, _, _ = O.J_adjoint(om, src, q, rec, (0.5 * d).astype(np.float32), return_obj=True)
+    assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
+    assert rel_l2(g, O.remove_padding(go, om.padsizes)) < 1e-3
