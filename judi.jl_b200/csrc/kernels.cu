@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(256) visco_update(ViscoArgs a)
 // ------------------------------------------------------------------------------------------
 void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 bool tma3d_supported(const judi_model *M);
+bool tma3d_fuse_supported(const StepArgs &s);
 void tma3d_step(const judi_model *M, const StepArgs &a);
 bool tma3d_step_born(const judi_model *M, const StepArgs &a);
 bool flux3d_step(const judi_model *M, const StepArgs &s);
@@ -713,7 +714,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     }
     bool ff = M->tti || M->irho_field;
     bool use_tma = M->ndim == 3 && !ff && !M->visco && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
-                   (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && !s.qext && !s.f.wrec &&
+                   (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && tma3d_fuse_supported(s) &&
                    (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
     bool born_done = false;
     if (use_tma && s.born && ctx->opt_born_fused) {
@@ -736,6 +737,7 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         StepArgs a2 = s;
         memset(&a2.f, 0, sizeof(a2.f));
         a2.born = 0;
+        a2.qext = nullptr;      // the space-time source drives the background field only
         a2.u[0] = s.ul[0];
         a2.up[0] = s.ulp[0];
         a2.tmap = &s.lin->tmap_halo[0][s.lin->cur];

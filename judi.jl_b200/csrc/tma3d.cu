@@ -40,6 +40,8 @@ struct TmaArgs {
     const float *qsrc;   // Born, linearised pass: delta of the background field ...
     const float *dm;     // ... and the perturbation: source term -dm * qsrc
     float *ulp;          // fused Born (DUAL): output of the linearised field, in place
+    const float *qext;   // F_QEXT: space-time source of this step (Grid layout), added as
+    float qext_scale;    //   qext_scale * qext  (= dt^2 / irho * wavelet[t], fields_exprs.py:58-81)
 };
 
 // DUAL: fused Born step.  Two groups of consumer warps share one CTA: group 0 steps the background
@@ -69,7 +71,9 @@ struct TmaCfg {
 // FUSE is a compile-time mask of what rides on the step, so that each flavour of launch carries
 // only its own instructions (the all-in-one fused instantiation executed 33% more instructions
 // than the plain one for a single extra store):
-enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16 };
+// F_QEXT: extended / full-wavefield source read from one more field (+4 B per point);
+// F_WREC: extended receiver  wrec += dt wavelet[t] u[t]  (fields_exprs.py:85-103, +8 B per point)
+enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16, F_QEXT = 32, F_WREC = 64 };
 
 struct TmaMaps {   // tensor maps of one launch (kernel parameter, __grid_constant__)
     CUtensorMap U, P, M;      // haloed u(t), tile u(t-1), tile m
@@ -203,8 +207,10 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
     [[maybe_unused]] const Fuse &fz = a.f;
     constexpr bool f_snap = (FUSE & F_SNAP) != 0, f_grad = (FUSE & F_GRAD) != 0;
     constexpr bool f_il = (FUSE & F_ILLUM) != 0, f_dd = (FUSE & F_DDOUT) != 0;
-    constexpr bool f_reg = f_snap || f_grad || f_il;   // anything stored in the region layout
+    constexpr bool f_wr = (FUSE & F_WREC) != 0;
+    constexpr bool f_reg = f_snap || f_grad || f_il || f_wr;   // anything stored in the region layout
     [[maybe_unused]] const bool f_born = (FUSE & F_QSRC) != 0 && act;
+    [[maybe_unused]] const bool f_qx = (FUSE & F_QEXT) != 0 && act;
     [[maybe_unused]] const bool f_xy = f_reg && act && grp == 0 && y >= fz.reg.lo[1] &&
                                        y < fz.reg.hi[1] && x + 3 >= fz.reg.lo[0] && x < fz.reg.hi[0];
     [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 3) == 0 && x >= fz.reg.lo[0] &&
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
             // fused extras: issue their point-wise global loads before waiting on the pipeline so
             // that their latency hides behind the stencil arithmetic of this plane
             [[maybe_unused]] bool fin = false, fvec = false;
-            [[maybe_unused]] float4 us4, g4, il4, qs4, dm4;
+            [[maybe_unused]] float4 us4, g4, il4, qs4, dm4, qx4, wr4;
             if (FUSE != 0 && jt >= 2 * R) {
                 const int z = z0 + jt - 2 * R;
                 const bool zin = z >= rz0 && z < rz1;
@@ -247,13 +253,16 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                     prefetch_l2(fz.usnap[0] + ri + 3 * rstride);
                     prefetch_l2(fz.grad + ri + 3 * rstride);
                 }
-                if ((f_grad || f_il) && fvec) {
+                if ((f_grad || f_il || f_wr) && fvec) {
                     if (f_grad) {
                         us4 = __ldg((const float4 *)(fz.usnap[0] + ri));
                         g4 = *(const float4 *)(fz.grad + ri);
                     }
                     if (f_il) il4 = *(const float4 *)(fz.illum + ri);
+                    if (f_wr) wr4 = *(const float4 *)(fz.wrec + ri);
                 }
+                // (a partial group at the x edge reads into the zero halo of the allocation)
+                if (f_qx) qx4 = __ldg((const float4 *)(a.qext + goff));
                 if (f_born) {
                     qs4 = *(const float4 *)(a.qsrc + goff);
                     dm4 = __ldg((const float4 *)(a.dm + goff));
@@ -352,6 +361,10 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                     lz0.x = __fmaf_rn(-dm4.x, qs4.x, lz0.x); lz0.y = __fmaf_rn(-dm4.y, qs4.y, lz0.y);
                     lz1.x = __fmaf_rn(-dm4.z, qs4.z, lz1.x); lz1.y = __fmaf_rn(-dm4.w, qs4.w, lz1.y);
                 }
+                if (f_qx) {    // + dt^2 / irho * q(x, t)
+                    lz0 = fma2s(a.qext_scale, lo2(qx4), lz0);
+                    lz1 = fma2s(a.qext_scale, hi2(qx4), lz1);
+                }
                 // explicit rn operations: the plain and the fused instantiation must produce
                 // bit-identical wavefields (checkpoint recomputation relies on it)
                 const f2 lap0 = add2(add2(lz0, lxp[0]), ly0), lap1 = add2(add2(lz1, lxp[1]), ly1);
@@ -420,6 +433,9 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                                 const f2 G1 = fma2(mul2s(-gc, hi2(us4)), dl1, hi2(g4));
                                 *(float4 *)(fz.grad + ri) = cat4(G0, G1);
                             }
+                            if (f_wr)
+                                *(float4 *)(fz.wrec + ri) = cat4(fma2s(fz.wrec_scale, uc0, lo2(wr4)),
+                                                                 fma2s(fz.wrec_scale, uc1, hi2(wr4)));
                         } else {
                             const float uc[4] = {cq.x, cq.y, cq.z, cq.w};
                             const float delta[4] = {dl0.x, dl0.y, dl1.x, dl1.y};
@@ -432,6 +448,7 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                                 if (f_grad)
                                     fz.grad[ri + e] = __fmaf_rn(__fmul_rn(-gc, fz.usnap[0][ri + e]), delta[e],
                                                                 fz.grad[ri + e]);
+                                if (f_wr) fz.wrec[ri + e] = __fmaf_rn(fz.wrec_scale, uc[e], fz.wrec[ri + e]);
                             }
                         }
                     }
@@ -466,6 +483,22 @@ static int variant_of(const judi_model *M)
     int v = M->ctx->opt_tile;
     if ((v != 6 && v != 9) || (M->r != 4 && v == 9)) v = 8;
     return v;
+}
+
+// the combinations of fused extras launch_variant has an instantiation for
+bool tma3d_fuse_supported(const StepArgs &s)
+{
+    const int m = (s.f.snap[0] ? F_SNAP : 0) | (s.f.grad ? F_GRAD : 0) | (s.f.illum ? F_ILLUM : 0) |
+                  (s.qext ? F_QEXT : 0) | (s.f.wrec ? F_WREC : 0);
+    if (!(m & (F_QEXT | F_WREC))) return true;
+    if (s.born) return m == F_QEXT || m == (F_QEXT | F_SNAP);
+    switch (m) {
+    case F_QEXT: case F_QEXT | F_SNAP: case F_QEXT | F_ILLUM: case F_QEXT | F_SNAP | F_ILLUM:
+    case F_WREC: case F_WREC | F_ILLUM:
+        return true;
+    default:
+        return false;
+    }
 }
 
 bool tma3d_supported(const judi_model *M)
@@ -531,6 +564,8 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
     a.dd_out = s.dd_out;
     a.qsrc = s.qsrc;
     a.dm = s.qsrc ? M->dm_src() : nullptr;
+    a.qext = s.qext;
+    a.qext_scale = s.qext_scale;
     TmaMaps tm;
     tm.U = *s.tmap; tm.P = *s.tmap_prev; tm.M = *s.tmap_m;
     if (DUAL) {
@@ -562,7 +597,8 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
 static int fuse_mask(const StepArgs &s)
 {
     return (s.f.snap[0] ? F_SNAP : 0) | (s.f.grad ? F_GRAD : 0) | (s.f.illum ? F_ILLUM : 0) |
-           (s.dd_out ? F_DDOUT : 0) | (s.qsrc ? F_QSRC : 0);
+           (s.dd_out ? F_DDOUT : 0) | (s.qsrc ? F_QSRC : 0) | (s.qext ? F_QEXT : 0) |
+           (s.f.wrec ? F_WREC : 0);
 }
 
 template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
@@ -581,6 +617,16 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
         FUSE_CASE(F_DDOUT | F_ILLUM)
         FUSE_CASE(F_DDOUT | F_SNAP | F_ILLUM)
         FUSE_CASE(F_QSRC)
+        // extended / full-wavefield sources (forward_rec_w, forward_wf_src, J_adjoint(ws=...),
+        // born_rec_w) and the extended receiver of adjoint_w (interface.py:50-204, 244-276)
+        FUSE_CASE(F_QEXT)
+        FUSE_CASE(F_QEXT | F_SNAP)
+        FUSE_CASE(F_QEXT | F_ILLUM)
+        FUSE_CASE(F_QEXT | F_SNAP | F_ILLUM)
+        FUSE_CASE(F_QEXT | F_DDOUT)
+        FUSE_CASE(F_QEXT | F_DDOUT | F_SNAP)
+        FUSE_CASE(F_WREC)
+        FUSE_CASE(F_WREC | F_ILLUM)
     default:
         throw JudiError("acoustic3d_tma: unsupported combination of fused extras");
     }
@@ -591,7 +637,7 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
 // has no fused instantiation (the caller then runs the two-launch form).
 bool tma3d_step_born(const judi_model *M, const StepArgs &s)
 {
-    if (variant_of(M) != 8 || s.f.grad || s.dd_out || s.qsrc) return false;
+    if (variant_of(M) != 8 || s.f.grad || s.dd_out || s.qsrc || s.qext || s.f.wrec) return false;
     const int mask = (s.f.snap[0] ? F_SNAP : 0) | (s.f.illum ? F_ILLUM : 0);
 #define BORN_CASE(RR, F) \
     case F: launch_fused<RR, 16, 16, 8, 4, 1, 2, false, F, true>(M, s); return true;
