@@ -165,6 +165,7 @@ int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value)
     else if (k == "atomic_inject") ctx->opt_atomic_inject = value;
     else if (k == "timing") ctx->timing = value;
     else if (k == "persist2d") ctx->opt_persist2d = value;
+    else if (k == "persist_vec") ctx->opt_persist_vec = value;
     else if (k == "profile") ctx->opt_profile = value;
     else if (k == "born_fused") ctx->opt_born_fused = value;
     else if (k == "tti_fused") ctx->opt_tti_fused = value;

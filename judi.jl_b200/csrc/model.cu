@@ -435,7 +435,7 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
             launch_count(ctx, "tti_axis");
         }
         if (M->ndim == 3) {
-            if (!M->irho_field && M->so == 8) {
+            if (!M->irho_field && (M->so == 8 || M->so == 4)) {
                 for (int d = 0; d < 3; d++) M->ttiABC[d] = DevBuf(ctx, (size_t)M->g.nalloc, false);
                 tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c, M->g.nalloc,
                                                             M->ttiABC[0].p, M->ttiABC[1].p, M->ttiABC[2].p);

@@ -118,7 +118,12 @@ __device__ float lap_weighted2d(const Grid &g, const Coefs &cf, const float *__r
 // vs 34 ms for the forward sweeps of 16 C2 shots: the L1 already serves the stencil's reuse.)
 // XIC: compiled with the isic / fwi imaging conditions and Born sources (more registers: the "as"
 // instantiation keeps its occupancy)
-template <int R, bool XIC>
+// VEC: every thread owns 4 consecutive x-points (128-bit loads and stores, a 128 x 8 tile per CTA
+// visit).  The one-point-per-thread body spends two thirds of its instructions on index arithmetic
+// and runs 16 C2 shots in lockstep at 60 Gpt/s, close to its own issue limit; the vector body
+// amortises that arithmetic over 4 points.  Plain / save / imaging condition "as" / illumination
+// of the constant-density kernel without free surface, space-time sources or Born (host: p2_vec_ok).
+template <int R, bool XIC, bool VEC = false>
 __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, const int nb)
 {
     cg::grid_group grid = cg::this_grid();
@@ -164,6 +169,98 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
         else if (ph == 0) { ph = a.t_sub - 1; sidx -= a.slot; }
         else ph--;
         // ---- stencil + injection + fused extras, tile by tile --------------------------------
+        if constexpr (VEC) {
+            constexpr int NV = (R + 3) / 4, HRV = 4 * NV, NW = 4 + 2 * HRV;
+            const int ntxv = (g.n[0] + 4 * TX - 1) / (4 * TX);
+            const int ntilesv = ntxv * ntz;
+            const bool reg_al = (a.reg.lo[0] & 3) == 0;
+            for (int tile = lb; tile < ntilesv; tile += nb) {
+                const int x = (tile % ntxv) * (4 * TX) + 4 * tx, z = (tile / ntxv) * TZ + tz;
+                if (x >= g.n[0] || z >= g.n[2]) continue;
+                const long long i = g.at(x, 0, z);
+                float w[NW];
+#pragma unroll
+                for (int v = 0; v < NW / 4; v++) {
+                    const float4 t4 = *(const float4 *)(uc + i - HRV + 4 * v);
+                    w[4 * v] = t4.x; w[4 * v + 1] = t4.y; w[4 * v + 2] = t4.z; w[4 * v + 3] = t4.w;
+                }
+                float lap[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) lap[e] = a.cf.c0 * w[HRV + e];
+#pragma unroll
+                for (int k = 1; k <= R; k++) {
+                    const float4 p4 = *(const float4 *)(uc + i + k * g.sz), m4 = *(const float4 *)(uc + i - k * g.sz);
+                    lap[0] += a.cf.cz[k] * (p4.x + m4.x); lap[1] += a.cf.cz[k] * (p4.y + m4.y);
+                    lap[2] += a.cf.cz[k] * (p4.z + m4.z); lap[3] += a.cf.cz[k] * (p4.w + m4.w);
+                }
+#pragma unroll
+                for (int k = 1; k <= R; k++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) lap[e] += a.cf.cx[k] * (w[HRV + e + k] + w[HRV + e - k]);
+                const float4 dx4 = *(const float4 *)(a.dx + x), mm4 = *(const float4 *)(a.m + i);
+                const float4 up4 = *(const float4 *)(un + i);
+                const float dxs[4] = {dx4.x, dx4.y, dx4.z, dx4.w}, mms[4] = {mm4.x, mm4.y, mm4.z, mm4.w};
+                const float ups[4] = {up4.x, up4.y, up4.z, up4.w};
+                const float dzv = a.dz[z];
+                int rows[4] = {-1, -1, -1, -1};
+                if (a.cellmap) {
+                    const int4 r4 = *(const int4 *)(a.cellmap + i);
+                    rows[0] = r4.x; rows[1] = r4.y; rows[2] = r4.z; rows[3] = r4.w;
+                }
+                float dl[4], unew[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float ucv = w[HRV + e];
+                    const float s_ = ((dxs[e] + 0.f) + dzv) * a.sdamp;
+                    const float rden = 1.0f / (mms[e] + s_);
+                    const float d1 = ucv - ups[e];
+                    const float delta = (lap[e] - s_ * d1) * rden;
+                    float inj = 0.f;
+                    if (rows[e] >= 0 && x + e < g.n[0]) {
+                        float acc = 0.f;
+                        for (int en = a.cell_start[rows[e]]; en < a.cell_start[rows[e] + 1]; en++)
+                            acc += a.ent_w[en] * src_row[a.ent_trace[en]];
+                        inj = acc * a.cell_scale[rows[e]];
+                    }
+                    unew[e] = ((ucv + d1) + delta) + inj;
+                    dl[e] = delta + inj;
+                }
+                if (x + 3 < g.n[0]) *(float4 *)(un + i) = make_float4(unew[0], unew[1], unew[2], unew[3]);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (x + e < g.n[0]) un[i + e] = unew[e];
+                }
+                if ((snap_t || usnap_t || a.illum) && z >= a.reg.lo[2] && z < a.reg.hi[2] &&
+                    x + 3 >= a.reg.lo[0] && x < a.reg.hi[0]) {
+                    const long long ri = a.reg.at(x, 0, z);
+                    if (reg_al && x >= a.reg.lo[0] && x + 3 < a.reg.hi[0]) {
+                        if (snap_t) *(float4 *)(snap_t + ri) = make_float4(w[HRV], w[HRV + 1], w[HRV + 2], w[HRV + 3]);
+                        if (a.illum) {
+                            float4 I4 = *(float4 *)(a.illum + ri);
+                            I4.x += a.cf.dt * w[HRV] * w[HRV]; I4.y += a.cf.dt * w[HRV + 1] * w[HRV + 1];
+                            I4.z += a.cf.dt * w[HRV + 2] * w[HRV + 2]; I4.w += a.cf.dt * w[HRV + 3] * w[HRV + 3];
+                            *(float4 *)(a.illum + ri) = I4;
+                        }
+                        if (usnap_t) {
+                            const float4 us4 = *(const float4 *)(usnap_t + ri);
+                            float4 G4 = *(float4 *)(a.grad + ri);
+                            G4.x -= a.gcoef * a.irho_c * us4.x * dl[0]; G4.y -= a.gcoef * a.irho_c * us4.y * dl[1];
+                            G4.z -= a.gcoef * a.irho_c * us4.z * dl[2]; G4.w -= a.gcoef * a.irho_c * us4.w * dl[3];
+                            *(float4 *)(a.grad + ri) = G4;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            if (x + e < a.reg.lo[0] || x + e >= a.reg.hi[0]) continue;
+                            if (snap_t) snap_t[ri + e] = w[HRV + e];
+                            if (a.illum) a.illum[ri + e] += a.cf.dt * w[HRV + e] * w[HRV + e];
+                            if (usnap_t) a.grad[ri + e] -= a.gcoef * a.irho_c * usnap_t[ri + e] * dl[e];
+                        }
+                    }
+                }
+            }
+        } else
         for (int tile = lb; tile < ntiles; tile += nb) {
             int x = x0, z = z0;
             if (tile != lb) { x = (tile % ntx) * TX + tx; z = (tile / ntx) * TZ + tz; }
@@ -228,16 +325,16 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
     }
 }
 
-template <int R, bool XIC>
-__global__ void __launch_bounds__(256, XIC ? 2 : 4) acoustic2d_persist(P2Args a)
+template <int R, bool XIC, bool VEC = false>
+__global__ void __launch_bounds__(256, (XIC || VEC) ? 2 : 4) acoustic2d_persist(P2Args a)
 {
-    acoustic2d_body<R, XIC>(a, blockIdx.x, gridDim.x);
+    acoustic2d_body<R, XIC, VEC>(a, blockIdx.x, gridDim.x);
 }
 
 // Several shots of the same model and time axis in lockstep: CTA b works on shot b / per_shot.
 // One grid barrier per time step serves all of them (judi_fg_multishot on small 2-D grids).
-template <int R, bool XIC>
-__global__ void __launch_bounds__(256, XIC ? 2 : 4) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
+template <int R, bool XIC, bool VEC = false>
+__global__ void __launch_bounds__(256, (XIC || VEC) ? 2 : 4) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
 {
     // the shot's arguments go to shared memory once: read through the global pointer, every stencil
     // coefficient would be a load from L1/L2 instead of a constant-bank operand
@@ -248,7 +345,7 @@ __global__ void __launch_bounds__(256, XIC ? 2 : 4) acoustic2d_persist_batch(con
         for (int i = threadIdx.x; i < (int)(sizeof(P2Args) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    acoustic2d_body<R, XIC>(sa, blockIdx.x % per_shot, per_shot);
+    acoustic2d_body<R, XIC, VEC>(sa, blockIdx.x % per_shot, per_shot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -780,6 +877,12 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
     a.fs = M->fs ? 1 : 0;
 }
 
+// what the 4-points-per-thread body covers
+static bool p2_vec_ok(const P2Args &a)
+{
+    return !a.fs && !a.qext && !a.qwf && !a.wrec && !a.l[0] && a.ic == JUDI_IC_AS;
+}
+
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced
 // accordingly.  S_in/in: injected traces; S_out/out: interpolated traces (of WL when Born, with
 // out_bg sampling W for nlind).
@@ -802,16 +905,17 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
     }
     P2Args a;
     p2_fill(M, W, WL, t0, t1, dir, S_in, in, S_out, out, out_bg, fz, a);
-    auto launch = [&](auto rtag, auto xtag) {
+    auto launch = [&](auto rtag, auto xtag, auto vtag) {
         constexpr int R = decltype(rtag)::value;
-        auto kern = acoustic2d_persist<R, decltype(xtag)::value>;
+        constexpr bool VEC = decltype(vtag)::value;
+        auto kern = acoustic2d_persist<R, decltype(xtag)::value, VEC>;
         static int max_blocks = 0;
         if (!max_blocks) {
             int per_sm = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
             max_blocks = per_sm * ctx->num_sms;
         }
-        int ntiles = ((M->N[0] + 31) / 32) * ((M->N[2] + 7) / 8);
+        int ntiles = ((M->N[0] + (VEC ? 127 : 31)) / (VEC ? 128 : 32)) * ((M->N[2] + 7) / 8);
         int nb = std::min(ntiles, max_blocks);
         if (ctx->opt_persist_blocks > 0) nb = std::min(nb, ctx->opt_persist_blocks);
         void *args[] = {(void *)&a};
@@ -819,15 +923,16 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
                                                ctx->stream));
         launch_count(ctx, "acoustic2d_persist");
     };
-    auto launch_r = [&](auto xtag) {
+    auto launch_r = [&](auto xtag, auto vtag) {
         switch (M->r) {
-        case 2: launch(std::integral_constant<int, 2>(), xtag); break;
-        case 4: launch(std::integral_constant<int, 4>(), xtag); break;
-        default: launch(std::integral_constant<int, 8>(), xtag); break;
+        case 2: launch(std::integral_constant<int, 2>(), xtag, vtag); break;
+        case 4: launch(std::integral_constant<int, 4>(), xtag, vtag); break;
+        default: launch(std::integral_constant<int, 8>(), xtag, vtag); break;
         }
     };
-    if (a.ic != JUDI_IC_AS && (a.grad || WL)) launch_r(std::true_type());
-    else launch_r(std::false_type());
+    if (a.ic != JUDI_IC_AS && (a.grad || WL)) launch_r(std::true_type(), std::false_type());
+    else if (ctx->opt_persist_vec == 2 && p2_vec_ok(a)) launch_r(std::false_type(), std::true_type());
+    else launch_r(std::false_type(), std::false_type());
     if (nsteps & 1) { W.swap(); if (WL) WL->swap(); }
     if (ctx->timing) {
         ctx->stencil_launches += 1;
@@ -917,34 +1022,40 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
                 args[(size_t)s]);
     DevArr<P2Args> dargs(ctx, (size_t)n, false);
     dargs.upload(args);
-    auto launch = [&](auto rtag, auto xtag) {
+    auto launch = [&](auto rtag, auto xtag, auto vtag) {
         constexpr int R = decltype(rtag)::value;
-        auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value>;
+        constexpr bool VEC = decltype(vtag)::value;
+        auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value, VEC>;
         static int max_blocks = 0;
         if (!max_blocks) {
             int per_sm = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
             max_blocks = per_sm * ctx->num_sms;
         }
-        const int ntiles = ((M->N[0] + 31) / 32) * ((M->N[2] + 7) / 8);
+        const int ntiles = ((M->N[0] + (VEC ? 127 : 31)) / (VEC ? 128 : 32)) * ((M->N[2] + 7) / 8);
         int cap = max_blocks;
         if (ctx->opt_persist_blocks > 0) cap = std::min(cap, ctx->opt_persist_blocks);
         int per_shot = std::max(1, std::min(ntiles, cap / n));
+        // as few CTAs as the same number of tile rounds needs (whole rounds, no idle tail)
+        if (VEC) per_shot = (ntiles + (ntiles + per_shot - 1) / per_shot - 1) / ((ntiles + per_shot - 1) / per_shot);
         const P2Args *dp = dargs.p;
         void *kargs[] = {(void *)&dp, (void *)&per_shot};
         CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kern, dim3(per_shot * n), dim3(256), kargs, 0,
                                                ctx->stream));
         launch_count(ctx, "acoustic2d_persist_batch");
     };
-    auto launch_r = [&](auto xtag) {
+    auto launch_r = [&](auto xtag, auto vtag) {
         switch (M->r) {
-        case 2: launch(std::integral_constant<int, 2>(), xtag); break;
-        case 4: launch(std::integral_constant<int, 4>(), xtag); break;
-        default: launch(std::integral_constant<int, 8>(), xtag); break;
+        case 2: launch(std::integral_constant<int, 2>(), xtag, vtag); break;
+        case 4: launch(std::integral_constant<int, 4>(), xtag, vtag); break;
+        default: launch(std::integral_constant<int, 8>(), xtag, vtag); break;
         }
     };
-    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type());
-    else launch_r(std::false_type());
+    bool vec = ctx->opt_persist_vec != 0;
+    for (int s = 0; s < n; s++) vec = vec && p2_vec_ok(args[(size_t)s]);
+    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type(), std::false_type());
+    else if (vec) launch_r(std::false_type(), std::true_type());
+    else launch_r(std::false_type(), std::false_type());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dargs is freed on return
     if (nsteps & 1)
         for (int s = 0; s < n; s++) {

@@ -1,4 +1,5 @@
-// tti3d.cu -- single-pass 3-D TTI time step for sm_100a (space order 8, constant density).
+// tti3d.cu -- single-pass 3-D TTI time step for sm_100a (space orders 4 and 8: a template on the
+// stencil radius R; constant density; the figures below are for R = 4).
 // Replaces the Devito loop nest of tti_kernel (src/pysource/kernels.py:144-182 with the rotated
 // self-adjoint operator of FD_utils.py:24-105) -- and the two-pass form of flux3d.cu, whose six
 // flux fields cost 48 of its 119 B per grid point in HBM round trips and whose synchronous
@@ -46,34 +47,41 @@
 // (0.80 ms) than the shifted queues (tti_fused=2, the default): 8x the code.
 #include "tma_util.cuh"
 
-namespace tti {
-constexpr int R = 4;
-constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
-constexpr int UPX = TX + 16, UPY = TY + 14;        // haloed u plane 48 x 30, origin (x0-8, y0-7)
-constexpr int USLOT = UPX * UPY;                   // 1440 floats (multiple of 32)
-constexpr int CPX = TX + 8, CPY = TY + 7;          // parameter plane 40 x 23, origin (x0-4, y0-4)
-constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;  // 928 floats (128-byte aligned slots)
-constexpr int NPAR = 6;                            // A0, B0, C0, rx, ry, rz
-constexpr int PSLOT = TX * TY;
-constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, parameter planes, tiles
-constexpr int NQ = 2 * R;                          // z-queue: planes zf-3 .. zf+4
-constexpr int NI = TXG * TY;                       // 128 tile groups
-constexpr int NF = 224;                            // F warps: tile (0-3), x halo (4), y halo (5, 6)
-constexpr int ND = NI;                             // D warps (7-10): one thread per tile group
-constexpr int NTHREADS = NF + ND + 32;             // + the producer warp
-constexpr int FXW = TX + 8;                        // row pitch of the x-extended flux plane (40)
-constexpr int FX = TY * FXW;                       // floats per field
-constexpr int FY = CPY * TX;                       // y-extended flux plane (rows -4 .. 18)
-constexpr int FBUF = 2 * FX + 2 * FY + 4 * PSLOT;  // P_x, M_x, P_y, M_y of one plane + P_z, M_z, u1, u2 tiles
-constexpr int LEADU = 3, LEADC = 2;                // producer run-ahead (planes)
-constexpr int WARM = 4 * R - 2;                    // iterations before the first output plane
-constexpr size_t SMEM = (size_t)(NS * 2 * USLOT + NC * NPAR * CSLOT + NP * 3 * PSLOT + 2 * FBUF) * 4 +
-                        (2 * NS + 2 * NC + 2 * NP) * 8 + 128;
-}  // namespace tti
+// Geometry of one CTA for stencil radius R = space_order / 2 (2 or 4).  The x layout works in groups
+// of 4 points and keeps one halo group per side whatever R <= 4 is; the y / z extents follow R.
+template <int R_>
+struct TtiC {
+    static constexpr int R = R_;
+    static constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
+    static constexpr int UPX = TX + 16, UPY = TY + 4 * R - 2; // haloed u plane, origin (x0-8, y0-(2R-1))
+    static constexpr int USLOT = ((UPX * UPY + 31) / 32) * 32;
+    static constexpr int CPX = TX + 8, CPY = TY + 2 * R - 1;  // parameter plane, origin (x0-4, y0-R)
+    static constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;  // 128-byte aligned slots
+    static constexpr int NPAR = 6;                            // A0, B0, C0, rx, ry, rz
+    static constexpr int PSLOT = TX * TY;
+    static constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, parameter planes, tiles
+    static constexpr int NQ = 2 * R;                          // z-queue: planes zf-(R-1) .. zf+R
+    static constexpr int NI = TXG * TY;                       // 128 tile groups
+    static constexpr int NYH = (((2 * R - 1) * TXG + 31) / 32) * 32;  // y-halo threads (whole warps)
+    static constexpr int NF = NI + 32 + NYH;                  // F warps: tile, x halo, y halo
+    static constexpr int ND = NI;                             // D warps: one thread per tile group
+    static constexpr int NTHREADS = NF + ND + 32;             // + the producer warp
+    static constexpr int FXW = TX + 8;                        // row pitch of the x-extended flux plane (40)
+    static constexpr int FX = TY * FXW;                       // floats per field
+    static constexpr int FY = CPY * TX;                       // y-extended flux plane (rows -R .. TY+R-2)
+    static constexpr int FBUF = 2 * FX + 2 * FY + 4 * PSLOT;  // P_x, M_x, P_y, M_y of one plane + P_z, M_z, u1, u2 tiles
+    static constexpr int LEADU = 3, LEADC = 2;                // producer run-ahead (planes)
+    static constexpr int WARM = 4 * R - 2;                    // iterations before the first output plane
+    static constexpr size_t SMEM = (size_t)(NS * 2 * USLOT + NC * NPAR * CSLOT + NP * 3 * PSLOT + 2 * FBUF) * 4 +
+                                   (2 * NS + 2 * NC + 2 * NP) * 8 + 128;
+    static_assert(R == 2 || R == 4, "x halo of one 4-point group: R <= 4");
+    static_assert(R + 1 + LEADU <= NS, "u ring too short");
+};
+constexpr int TTI_NPAR = 6;
 
 struct TtiMaps {
     CUtensorMap U1, U2;        // haloed planes of u1(t), u2(t)
-    CUtensorMap C[tti::NPAR];  // parameter planes
+    CUtensorMap C[TTI_NPAR];  // parameter planes
     CUtensorMap P1, P2, M;     // tiles of u1(t-1), u2(t-1), m
 };
 
@@ -97,7 +105,7 @@ enum { TF_SNAP = 1, TF_GRAD = 2, TF_ILLUM = 4, TF_DDOUT = 8, TF_QSRC = 16 };
 // staggered first derivative along x at the 4 nodes of a group from the 12-float row window
 // centred on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2),
 // sum_k w_k (F[e+k-1] - F[e-k]).  Odd offsets straddle register pairs: scalar arithmetic.
-template <bool PLUS>
+template <bool PLUS, int R>
 __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const float4 &c,
                                        const float4 &r, f2 &o0, f2 &o1)
 {
@@ -107,7 +115,7 @@ __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const f
     for (int e = 0; e < 4; e++) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 1; k <= tti::R; k++) {
+        for (int k = 1; k <= R; k++) {
             const float d = PLUS ? __fsub_rn(w[4 + e + k], w[4 + e - k + 1])
                                  : __fsub_rn(w[4 + e + k - 1], w[4 + e - k]);
             acc = (k == 1) ? __fmul_rn(wx[1], d) : __fmaf_rn(wx[k], d, acc);
@@ -118,11 +126,16 @@ __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const f
     o1 = pk(o[2], o[3]);
 }
 
-template <int FUSE, bool ROTF, bool ROTD>
-__global__ void __launch_bounds__(tti::NTHREADS, 1)
+template <int R, int FUSE, bool ROTF, bool ROTD>
+__global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     tti3d_tma(const __grid_constant__ TtiMaps tm, const TtiArgs a)
 {
-    using namespace tti;
+    typedef TtiC<R> C;
+    constexpr int TXG = C::TXG, TX = C::TX, TY = C::TY, UPX = C::UPX, USLOT = C::USLOT, CPX = C::CPX;
+    constexpr int CPY = C::CPY, CSLOT = C::CSLOT, NPAR = C::NPAR, PSLOT = C::PSLOT, NS = C::NS, NC = C::NC;
+    constexpr int NP = C::NP, NQ = C::NQ, NI = C::NI, NF = C::NF, ND = C::ND, FXW = C::FXW, FX = C::FX;
+    constexpr int FY = C::FY, FBUF = C::FBUF, LEADU = C::LEADU, LEADC = C::LEADC, WARM = C::WARM;
+    static_assert(!(ROTF || ROTD) || NS == NQ, "rotated queues need ring length == queue length");
     extern __shared__ unsigned char smem_raw[];
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float *ringC = ringU + NS * 2 * USLOT;       // [NC][NPAR][CSLOT]
@@ -141,8 +154,8 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
     const int z0 = blockIdx.z * a.zchunk;
     const int z1 = min(z0 + a.zchunk, g.n[2]);
     const int nzc = z1 - z0;
-    // iteration j brings in u plane z0-7+j; flux plane zf = z0-11+j (from j = 7); output plane
-    // zo = zf-3 = z0-14+j (from j = 14)
+    // iteration j brings in u plane z0-(2R-1)+j; flux plane zf = z0-(3R-1)+j (from j = 2R-1); output
+    // plane zo = zf-(R-1) = z0-(4R-2)+j (from j = 4R-2)
     const int total = nzc + WARM;
     constexpr int FIRST = 2 * R - 1;             // first flux iteration
     constexpr int NSYNC = NF + ND;               // threads of the F <-> D hand-over barriers
@@ -159,15 +172,15 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
     if (tid >= NF + ND) {
         // ===== producer warp: one lane issues the three streams, each a fixed distance ahead ======
         if (lane == 0) {
-            const int bx = g.hx + x0 - 8, by = g.hy + y0 - 7, bz = g.hz + z0 - 7;
-            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - 4, cz0 = g.hz + z0 - 4;
+            const int bx = g.hx + x0 - 8, by = g.hy + y0 - (2 * R - 1), bz = g.hz + z0 - (2 * R - 1);
+            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - R, cz0 = g.hz + z0 - R;
             const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
             for (int j = -LEADU; j < total; j++) {
                 const int pj = j + LEADU;                 // u plane (consumer iteration pj)
                 if (pj < total) {
                     const int s = pj % NS;
                     if (pj >= NS) mbar_wait_sleep(&emptyU[s], (uint32_t)(((pj / NS) - 1) & 1));
-                    mbar_arrive_expect_tx(&fullU[s], 2 * USLOT * 4);
+                    mbar_arrive_expect_tx(&fullU[s], 2 * UPX * C::UPY * 4);
                     tma_load_3d(ringU + s * 2 * USLOT, &tm.U1, bx, by, bz + pj, &fullU[s]);
                     tma_load_3d(ringU + s * 2 * USLOT + USLOT, &tm.U2, bx, by, bz + pj, &fullU[s]);
                 }
@@ -211,13 +224,13 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
             cy = h >> 1;
             wr_x = true;
         } else {
-            const int h = tid - NI - 32, row = h / TXG;   // 0..7; the last row is idle (mirrors row 6)
+            const int h = tid - NI - 32, row = h / TXG;   // rows beyond 2R-2 are idle (mirror the last one)
             cx = h & (TXG - 1);
             cy = row < R ? row - R : TY + min(row, 2 * R - 2) - R;
             wr_y = row < 2 * R - 1;
         }
-        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;   // node group inside a u plane
-        const int sc = (cy + R) * CPX + 4 * cx + R;               // ... inside a parameter plane
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 8;       // node group inside a u plane
+        const int sc = (cy + R) * CPX + 4 * cx + 4;               // ... inside a parameter plane
         const int sfx = cy * FXW + 4 * (cx + 1);                  // ... inside the x-extended flux plane
         const int sfy = (cy + R) * TX + 4 * cx;                   // ... inside the y-extended flux plane
         const int st = cy * TX + 4 * cx;                          // ... inside a tile (tile threads)
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                         const float *pl = ringU + s_c * 2 * USLOT + f * USLOT + su;
                         const float4 *q = f ? q2 : q1;
                         const float4 c = q[SL(0)];
-                        tti_dx<true>(cf.wx, *(const float4 *)(pl - 4), c, *(const float4 *)(pl + 4),
+                        tti_dx<true, R>(cf.wx, *(const float4 *)(pl - 4), c, *(const float4 *)(pl + 4),
                                      G[f][0][0], G[f][0][1]);
                         f2 gy0, gy1, gz0, gz1;
 #pragma unroll
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
                 for (int f = 0; f < 2; f++) {
                     const float *px = fb + f * FX + sfx;
                     f2 lx0, lx1;
-                    tti_dx<false>(cf.wx, *(const float4 *)(px - 4), *(const float4 *)px,
+                    tti_dx<false, R>(cf.wx, *(const float4 *)(px - 4), *(const float4 *)px,
                                   *(const float4 *)(px + 4), lx0, lx1);
                     const float *py = fb + 2 * FX + f * FY + sfy;
                     f2 ly0, ly1;
@@ -574,24 +587,25 @@ __global__ void __launch_bounds__(tti::NTHREADS, 1)
 // ---- host side ---------------------------------------------------------------------------------
 bool tti3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && M->tti && !M->visco && !M->irho_field && M->r == tti::R && M->ctx->encode_tiled != nullptr &&
+    return M->ndim == 3 && M->tti && !M->visco && !M->irho_field && (M->r == 4 || M->r == 2) && M->ctx->encode_tiled != nullptr &&
            M->ctx->opt_tti_fused && M->ttiABC[0].p != nullptr;
 }
 
 void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map)
 {
-    if (halo_map) tma_encode_box(M, base, tti::UPX, tti::UPY, halo_map);
-    if (tile_map) tma_encode_box(M, base, tti::TX, tti::TY, tile_map);
+    if (halo_map) tma_encode_box(M, base, TtiC<4>::UPX, M->r == 2 ? TtiC<2>::UPY : TtiC<4>::UPY, halo_map);
+    if (tile_map) tma_encode_box(M, base, TtiC<4>::TX, TtiC<4>::TY, tile_map);
 }
 
 void tti3d_encode_coef(const judi_model *M, CUtensorMap *maps)
 {
-    for (int p = 0; p < 3; p++) tma_encode_box(M, M->ttiABC[p].p, tti::CPX, tti::CPY, &maps[p]);
-    for (int p = 0; p < 3; p++) tma_encode_box(M, M->r3[p].p, tti::CPX, tti::CPY, &maps[3 + p]);
+    const int cpy = M->r == 2 ? TtiC<2>::CPY : TtiC<4>::CPY;
+    for (int p = 0; p < 3; p++) tma_encode_box(M, M->ttiABC[p].p, TtiC<4>::CPX, cpy, &maps[p]);
+    for (int p = 0; p < 3; p++) tma_encode_box(M, M->r3[p].p, TtiC<4>::CPX, cpy, &maps[3 + p]);
 }
 
 // z-chunks per tile column: whole waves of one CTA per SM, counting the 14 warm-up planes
-static int tti3d_chunks(const judi_ctx *ctx, int ntiles, int nz)
+static int tti3d_chunks(const judi_ctx *ctx, int ntiles, int nz, int warm)
 {
     if (ctx->opt_zchunks > 0) return std::min(ctx->opt_zchunks, nz);
     int best = 1;
@@ -600,27 +614,30 @@ static int tti3d_chunks(const judi_ctx *ctx, int ntiles, int nz)
         const int zc = (nz + c - 1) / c;
         const long long ctas = (long long)ntiles * ((nz + zc - 1) / zc);
         const double waves = (double)((ctas + ctx->num_sms - 1) / ctx->num_sms);
-        const double cost = waves * (zc + tti::WARM);
+        const double cost = waves * (zc + warm);
         if (cost < best_cost * 0.999) { best_cost = cost; best = c; }
     }
     return best;
 }
 
 // lin: launch on the linearised wavefield (Born source in); otherwise on the background field
-template <int FUSE>
-static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
+template <int R, int FUSE>
+static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
 {
+    typedef TtiC<R> C;
     judi_ctx *ctx = M->ctx;
     // register queues: 2 shifted every plane (default), 1 rotated at compile time, 3 / 4 only the
     // F / D role rotated
-    const int var = (ctx->opt_tti_fused == 1 || ctx->opt_tti_fused == 3 || ctx->opt_tti_fused == 4)
+    // (the rotated variants need ring length == queue length: R = 4 only)
+    constexpr bool CANROT = C::NS == C::NQ;
+    const int var = (CANROT && (ctx->opt_tti_fused == 1 || ctx->opt_tti_fused == 3 || ctx->opt_tti_fused == 4))
                         ? ctx->opt_tti_fused : 2;
     void (*kern)(const TtiMaps, const TtiArgs) =
-        var == 1 ? tti3d_tma<FUSE, true, true> : var == 3 ? tti3d_tma<FUSE, true, false>
-        : var == 4 ? tti3d_tma<FUSE, false, true> : tti3d_tma<FUSE, false, false>;
+        var == 1 ? tti3d_tma<R, FUSE, CANROT, CANROT> : var == 3 ? tti3d_tma<R, FUSE, CANROT, false>
+        : var == 4 ? tti3d_tma<R, FUSE, false, CANROT> : tti3d_tma<R, FUSE, false, false>;
     static bool configured[5] = {false, false, false, false, false};
     if (!configured[var]) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tti::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured[var] = true;
     }
     Wavefield *W = lin ? s.lin : s.scratch;
@@ -628,7 +645,7 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = fals
     tm.U1 = W->tmap_halo[0][W->cur]; tm.U2 = W->tmap_halo[1][W->cur];
     tm.P1 = W->tmap_tile[0][1 - W->cur]; tm.P2 = W->tmap_tile[1][1 - W->cur];
     tm.M = W->tmap_m;
-    for (int p = 0; p < tti::NPAR; p++) tm.C[p] = W->tmap_par[p];
+    for (int p = 0; p < TTI_NPAR; p++) tm.C[p] = W->tmap_par[p];
     TtiArgs a;
     memset(&a, 0, sizeof(a));
     a.g = M->g; a.cf = M->cf;
@@ -641,13 +658,20 @@ static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = fals
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.irho_c = M->irho_c;
     if (!lin) a.f = s.f;
-    const int ntx = (M->N[0] + tti::TX - 1) / tti::TX, nty = (M->N[1] + tti::TY - 1) / tti::TY;
-    int nzc = tti3d_chunks(ctx, ntx * nty, M->N[2]);
+    const int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
+    int nzc = tti3d_chunks(ctx, ntx * nty, M->N[2], C::WARM);
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     const dim3 grid(ntx, nty, nzc);
-    kern<<<grid, tti::NTHREADS, tti::SMEM, ctx->stream>>>(tm, a);
+    kern<<<grid, C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
     launch_count(ctx, "tti3d_tma");
+}
+
+template <int FUSE>
+static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
+{
+    if (M->r == 2) tti3d_launch_r<2, FUSE>(M, s, lin);
+    else tti3d_launch_r<4, FUSE>(M, s, lin);
 }
 
 // One fused TTI step; false if this combination has no single-pass instantiation.

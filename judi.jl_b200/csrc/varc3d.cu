@@ -1,4 +1,5 @@
-// varc3d.cu -- single-pass 3-D variable-density acoustic time step for sm_100a (space order 8).
+// varc3d.cu -- single-pass 3-D variable-density acoustic time step for sm_100a (space orders 4 and 8:
+// the kernel is a template on the stencil radius R; figures below are for R = 4).
 // Replaces the Devito loop nest of acoustic_kernel with a density field
 // (src/pysource/kernels.py:46-77, FD_utils.py:16-17: `div(irho * grad(u, .5), -.5)`), and the
 // two-pass form of flux3d.cu whose three flux fields cost 24 of its 52 B per grid point.
@@ -29,30 +30,36 @@
 // issue-active, latency-bound.
 #include "tma_util.cuh"
 
-namespace varc {
-constexpr int R = 4;
-constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
-constexpr int UPX = TX + 16, UPY = TY + 14;        // haloed u plane 48 x 30, origin (x0-8, y0-7)
-constexpr int USLOT = UPX * UPY;                   // 1440 floats (multiple of 32)
-constexpr int CPX = TX + 8, CPY = TY + 7;          // coefficient plane 40 x 23, origin (x0-4, y0-4)
-constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;
-constexpr int PSLOT = TX * TY;
-constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, c planes, tiles
-constexpr int NQ = 2 * R;
-constexpr int NI = TXG * TY;                       // 128 tile groups
-constexpr int NF = 224;                            // F warps: tile (0-3), x halo (4), y halo (5, 6)
-constexpr int ND = NI;                             // D warps (7-10)
-constexpr int NTHREADS = NF + ND + 32;             // + the producer warp
-constexpr int FXW = TX + 8;                        // row pitch of the x-extended flux plane (40)
-constexpr int FX = TY * FXW;
-constexpr int FY = CPY * TX;                       // y-extended flux plane (rows -4 .. 18)
-constexpr int FBUF = FX + FY + 2 * PSLOT;          // F_x, F_y of one plane + F_z, u tiles
-constexpr int LEADU = 3, LEADC = 2;                // producer run-ahead (planes)
-constexpr int WARM = 4 * R - 2;                    // iterations before the first output plane
-constexpr int FIRST = 2 * R - 1;                   // first flux iteration
-constexpr size_t SMEM = (size_t)(NS * USLOT + NC * CSLOT + NP * 3 * PSLOT + 2 * FBUF) * 4 +
-                        (2 * NS + 2 * NC + 2 * NP) * 8 + 128;
-}  // namespace varc
+// Geometry of one CTA for stencil radius R = space_order / 2 (2 or 4).  The x layout works in groups
+// of 4 points and keeps one halo group per side whatever R <= 4 is; the y / z extents follow R.
+template <int R_>
+struct VarcC {
+    static constexpr int R = R_;
+    static constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
+    static constexpr int UPX = TX + 16, UPY = TY + 4 * R - 2; // haloed u plane, origin (x0-8, y0-(2R-1))
+    static constexpr int USLOT = ((UPX * UPY + 31) / 32) * 32;
+    static constexpr int CPX = TX + 8, CPY = TY + 2 * R - 1;  // coefficient plane, origin (x0-4, y0-R)
+    static constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;
+    static constexpr int PSLOT = TX * TY;
+    static constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, c planes, tiles
+    static constexpr int NQ = 2 * R;
+    static constexpr int NI = TXG * TY;                       // 128 tile groups
+    static constexpr int NYH = (((2 * R - 1) * TXG + 31) / 32) * 32;  // y-halo threads (whole warps)
+    static constexpr int NF = NI + 32 + NYH;                  // F warps: tile, x halo, y halo
+    static constexpr int ND = NI;                             // D warps: one thread per tile group
+    static constexpr int NTHREADS = NF + ND + 32;             // + the producer warp
+    static constexpr int FXW = TX + 8;                        // row pitch of the x-extended flux plane (40)
+    static constexpr int FX = TY * FXW;
+    static constexpr int FY = CPY * TX;                       // y-extended flux plane (rows -R .. TY+R-2)
+    static constexpr int FBUF = FX + FY + 2 * PSLOT;          // F_x, F_y of one plane + F_z, u tiles
+    static constexpr int LEADU = 3, LEADC = 2;                // producer run-ahead (planes)
+    static constexpr int WARM = 4 * R - 2;                    // iterations before the first output plane
+    static constexpr int FIRST = 2 * R - 1;                   // first flux iteration
+    static constexpr size_t SMEM = (size_t)(NS * USLOT + NC * CSLOT + NP * 3 * PSLOT + 2 * FBUF) * 4 +
+                                   (2 * NS + 2 * NC + 2 * NP) * 8 + 128;
+    static_assert(R == 2 || R == 4, "x halo of one 4-point group: R <= 4");
+    static_assert(R + 1 + LEADU <= NS, "u ring too short");
+};
 
 struct VarcMaps {
     CUtensorMap U, C;          // haloed planes of u(t) and of the coefficient c
@@ -75,7 +82,7 @@ enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4, VF_DDOUT = 8, VF_QSRC = 16 };
 
 // staggered first derivative along x at the 4 nodes of a group from the 12-float row window centred
 // on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2)
-template <bool PLUS>
+template <bool PLUS, int R>
 __device__ __forceinline__ void varc_dx(const float *wx, const float4 &l, const float4 &c,
                                         const float4 &r, f2 &o0, f2 &o1)
 {
@@ -85,7 +92,7 @@ __device__ __forceinline__ void varc_dx(const float *wx, const float4 &l, const 
     for (int e = 0; e < 4; e++) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 1; k <= varc::R; k++) {
+        for (int k = 1; k <= R; k++) {
             const float d = PLUS ? __fsub_rn(w[4 + e + k], w[4 + e - k + 1])
                                  : __fsub_rn(w[4 + e + k - 1], w[4 + e - k]);
             acc = (k == 1) ? __fmul_rn(wx[1], d) : __fmaf_rn(wx[k], d, acc);
@@ -96,11 +103,15 @@ __device__ __forceinline__ void varc_dx(const float *wx, const float4 &l, const 
     o1 = pk(o[2], o[3]);
 }
 
-template <int FUSE, bool ROTD>
-__global__ void __launch_bounds__(varc::NTHREADS, 2)
+template <int R, int FUSE, bool ROTD>
+__global__ void __launch_bounds__(VarcC<R>::NTHREADS, 2)
     varc3d_tma(const __grid_constant__ VarcMaps tm, const VarcArgs a)
 {
-    using namespace varc;
+    typedef VarcC<R> C;
+    constexpr int TXG = C::TXG, TX = C::TX, TY = C::TY, UPX = C::UPX, USLOT = C::USLOT, CPX = C::CPX;
+    constexpr int CPY = C::CPY, CSLOT = C::CSLOT, PSLOT = C::PSLOT, NS = C::NS, NC = C::NC, NP = C::NP;
+    constexpr int NQ = C::NQ, NI = C::NI, NF = C::NF, ND = C::ND, FXW = C::FXW, FX = C::FX, FY = C::FY;
+    constexpr int FBUF = C::FBUF, LEADU = C::LEADU, LEADC = C::LEADC, WARM = C::WARM, FIRST = C::FIRST;
     extern __shared__ unsigned char smem_raw[];
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float *ringC = ringU + NS * USLOT;
@@ -119,8 +130,8 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
     const int z0 = blockIdx.z * a.zchunk;
     const int z1 = min(z0 + a.zchunk, g.n[2]);
     const int nzc = z1 - z0;
-    // iteration j brings in u plane z0-7+j; flux plane zf = z0-11+j (from j = 7); output plane
-    // zo = zf-3 = z0-14+j (from j = 14)
+    // iteration j brings in u plane z0-(2R-1)+j; flux plane zf = z0-(3R-1)+j (from j = 2R-1); output
+    // plane zo = zf-(R-1) = z0-(4R-2)+j (from j = 4R-2)
     const int total = nzc + WARM;
     constexpr int NSYNC = NF + ND;
 
@@ -138,15 +149,15 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
     if (tid >= NF + ND) {
         // ===== producer warp ======================================================================
         if (lane == 0) {
-            const int bx = g.hx + x0 - 8, by = g.hy + y0 - 7, bz = g.hz + z0 - 7;
-            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - 4, cz0 = g.hz + z0 - 4;
+            const int bx = g.hx + x0 - 8, by = g.hy + y0 - (2 * R - 1), bz = g.hz + z0 - (2 * R - 1);
+            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - R, cz0 = g.hz + z0 - R;
             const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
             for (int j = -LEADU; j < total; j++) {
                 const int pj = j + LEADU;                 // u plane (consumer iteration pj)
                 if (pj < total) {
                     const int s = pj % NS;
                     if (pj >= NS) mbar_wait_sleep(&emptyU[s], (uint32_t)(((pj / NS) - 1) & 1));
-                    mbar_arrive_expect_tx(&fullU[s], USLOT * 4);
+                    mbar_arrive_expect_tx(&fullU[s], UPX * C::UPY * 4);
                     tma_load_3d(ringU + s * USLOT, &tm.U, bx, by, bz + pj, &fullU[s]);
                 }
                 const int c = j + LEADC - FIRST;          // flux plane counter (iteration c + 7)
@@ -173,8 +184,8 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
     if (tid < NI) {
         // ===== F role, tile warps: F_x, F_y, F_z of the own nodes ====================================
         const int cx = tid & (TXG - 1), cy = tid / TXG;
-        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;   // node group inside a u plane
-        const int sc = (cy + R) * CPX + 4 * cx + R;               // ... inside a coefficient plane
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 8;       // node group inside a u plane
+        const int sc = (cy + R) * CPX + 4 * cx + 4;               // ... inside a coefficient plane
         const int sfx = cy * FXW + 4 * (cx + 1);                  // ... inside the x-extended flux plane
         const int sfy = (cy + R) * TX + 4 * cx;                   // ... inside the y-extended flux plane
         const int st = cy * TX + 4 * cx;                          // ... inside a tile
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             const float4 c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
             const float4 cen = q[R - 1];
             f2 gx0, gx1, gy0, gy1, gz0, gz1;
-            varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), gx0, gx1);
+            varc_dx<true, R>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), gx0, gx1);
 #pragma unroll
             for (int k = 1; k <= R; k++) {
                 const float4 p = *(const float4 *)(pl + k * UPX);
@@ -250,13 +261,13 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
             cx = (h & 1) ? TXG : -1;
             cy = h >> 1;
         } else {
-            const int h = tid - NI - 32, row = h / TXG;   // 0..7; the last row is idle (mirrors row 6)
+            const int h = tid - NI - 32, row = h / TXG;   // rows beyond 2R-2 are idle (mirror the last one)
             cx = h & (TXG - 1);
             cy = row < R ? row - R : TY + min(row, 2 * R - 2) - R;
             wr = row < 2 * R - 1;
         }
-        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 2 * R;
-        const int sc = (cy + R) * CPX + 4 * cx + R;
+        const int su = (cy + 2 * R - 1) * UPX + 4 * cx + 8;
+        const int sc = (cy + R) * CPX + 4 * cx + 4;
         const int sf = xh ? cy * FXW + 4 * (cx + 1) : FX + (cy + R) * TX + 4 * cx;
         if (lane == 0)
             for (int j = 0; j < R - 1; j++) mbar_arrive(&emptyU[j]);   // planes they never read
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
                 const float *pl = ringU + s_c * USLOT + su;
                 c4 = *(const float4 *)(ringC + cslot * CSLOT + sc);
                 const float4 cen = *(const float4 *)pl;
-                if (xh) varc_dx<true>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), g0, g1);
+                if (xh) varc_dx<true, R>(cf.wx, *(const float4 *)(pl - 4), cen, *(const float4 *)(pl + 4), g0, g1);
                 else {
 #pragma unroll
                     for (int k = 1; k <= R; k++) {
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
         if (need_xy) {
             const float *px = fb + sfx;
             f2 lx0, lx1;
-            varc_dx<false>(cf.wx, *(const float4 *)(px - 4), *(const float4 *)px, *(const float4 *)(px + 4),
+            varc_dx<false, R>(cf.wx, *(const float4 *)(px - 4), *(const float4 *)px, *(const float4 *)(px + 4),
                            lx0, lx1);
             const float *py = fb + FX + sfy;
             f2 ly0, ly1;
@@ -493,32 +504,34 @@ __global__ void __launch_bounds__(varc::NTHREADS, 2)
 // ---- host side ---------------------------------------------------------------------------------
 bool varc3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && !M->tti && !M->visco && M->irho_field && M->r == varc::R && M->ctx->encode_tiled != nullptr &&
+    return M->ndim == 3 && !M->tti && !M->visco && M->irho_field && (M->r == 4 || M->r == 2) && M->ctx->encode_tiled != nullptr &&
            M->ctx->opt_varc_fused;
 }
 
 void varc3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map)
 {
-    if (halo_map) tma_encode_box(M, base, varc::UPX, varc::UPY, halo_map);
-    if (tile_map) tma_encode_box(M, base, varc::TX, varc::TY, tile_map);
+    const int upy = M->r == 2 ? VarcC<2>::UPY : VarcC<4>::UPY;
+    if (halo_map) tma_encode_box(M, base, VarcC<4>::UPX, upy, halo_map);
+    if (tile_map) tma_encode_box(M, base, VarcC<4>::TX, VarcC<4>::TY, tile_map);
 }
 
 void varc3d_encode_coef(const judi_model *M, const float *base, CUtensorMap *map)
 {
-    tma_encode_box(M, base, varc::CPX, varc::CPY, map);
+    tma_encode_box(M, base, VarcC<4>::CPX, M->r == 2 ? VarcC<2>::CPY : VarcC<4>::CPY, map);
 }
 
 // lin: launch on the linearised wavefield (Born source in); otherwise on the background field
-template <int FUSE>
-static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
+template <int R, int FUSE>
+static void varc3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
 {
+    typedef VarcC<R> C;
     judi_ctx *ctx = M->ctx;
     // option varc_fused: 1 shifted accumulators, 2 accumulators rotated at compile time
     const int var = ctx->opt_varc_fused == 2 ? 1 : 0;
-    void (*kern)(const VarcMaps, const VarcArgs) = var ? varc3d_tma<FUSE, true> : varc3d_tma<FUSE, false>;
+    void (*kern)(const VarcMaps, const VarcArgs) = var ? varc3d_tma<R, FUSE, true> : varc3d_tma<R, FUSE, false>;
     static bool configured[2] = {false, false};
     if (!configured[var]) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)varc::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured[var] = true;
     }
     Wavefield *W = lin ? s.lin : s.scratch;
@@ -536,7 +549,7 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = fal
     if (!lin) a.f = s.f;
     if (FUSE & VF_DDOUT) a.dd_out = s.scratch->dd[0].p;
     if (FUSE & VF_QSRC) { a.dd_in = s.scratch->dd[0].p; a.dm = M->dm_src(); }
-    const int ntx = (M->N[0] + varc::TX - 1) / varc::TX, nty = (M->N[1] + varc::TY - 1) / varc::TY;
+    const int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
     int nzc = ctx->opt_zchunks;
     if (nzc <= 0) {
         // two CTAs per SM: minimise waves x (planes per chunk + the 4R-2 warm-up planes of a chunk)
@@ -546,7 +559,7 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = fal
             const long long waves = ((long long)ntx * nty * c + slots - 1) / slots;
             // (a single chunk per tile column leaves the launch waiting for its slowest CTA:
             // measured 0.323 vs 0.315 ms on the C5-size grid, hence the 6% handicap)
-            const long long cost = waves * ((M->N[2] + c - 1) / c + 4 * varc::R - 2) * (c == 1 ? 106 : 100);
+            const long long cost = waves * ((M->N[2] + c - 1) / c + C::WARM) * (c == 1 ? 106 : 100);
             if (best < 0 || cost < best) { best = cost; nzc = c; }
         }
         if (nzc <= 0) nzc = 1;
@@ -554,8 +567,15 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = fal
     nzc = std::min(nzc, M->N[2]);
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
-    kern<<<dim3(ntx, nty, nzc), varc::NTHREADS, varc::SMEM, ctx->stream>>>(tm, a);
+    kern<<<dim3(ntx, nty, nzc), C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
     launch_count(ctx, "varc3d_tma");
+}
+
+template <int FUSE>
+static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
+{
+    if (M->r == 2) varc3d_launch_r<2, FUSE>(M, s, lin);
+    else varc3d_launch_r<4, FUSE>(M, s, lin);
 }
 
 // One fused variable-density step; false if this combination has no single-pass instantiation.

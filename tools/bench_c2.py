@@ -33,6 +33,7 @@ def run():
     gm = J.Model((0., 0.), d, n, m=m0, dt=dt, **kw)
     return J.objectives.fwi_objective(gm, shots)
 ctx.set_option("persist_blocks", int(os.environ.get("PERSIST_BLOCKS", "0")))
+ctx.set_option("persist_vec", int(os.environ.get("PERSIST_VEC", "1")))
 run(); ctx.synchronize()
 reps = 5
 t0 = time.perf_counter()
