@@ -309,6 +309,7 @@ struct StepArgs {
     float qext_scale;          //   q = qext_scale * qext  (already multiplied by dt^2 [/ irho])
     float *dd_out;             // TMA kernel, Born background pass: write delta
     const float *qsrc;         // TMA kernel, Born linearised pass: read delta of the background
+    const float *sfield;       // ... isic / fwi: dt^2 div(dm grad u) of the background (varc3d_lapw)
     int adj;                   // 1: adjoint sweep (only the visco-acoustic step is not its own mirror image)
 };
 void stencil_step(const judi_model *M, const StepArgs &a);
@@ -323,6 +324,10 @@ struct Wavefield {
     int cur = 0;
     DevBuf flux[6];            // P_x,P_y,P_z,M_x,M_y,M_z (flux form only)
     DevBuf dd[2];              // u+ - 2u + u- of the background field (flux-form Born)
+    DevBuf lapw;               // dt^2 div(dm grad u): isic / fwi Born source of the 3-D acoustic kernel
+    CUtensorMap tmap_halo_v[2];   // ... haloed boxes of the background field in the varc3d geometry
+    CUtensorMap tmap_dmc;         // ... and the coefficient box over dm
+    bool has_lapw = false;
     DevBuf rmem, wtmp;         // visco-acoustic: memory variable, adjoint product field
     CUtensorMap tmap_halo[2][2];  // [field][slot]: haloed plane box
     CUtensorMap tmap_tile[2][2];  // [field][slot]: tile box

@@ -471,6 +471,8 @@ bool varc3d_supported(const judi_model *M);
 void varc3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 void varc3d_encode_coef(const judi_model *M, const float *base, CUtensorMap *map);
 bool varc3d_step(const judi_model *M, const StepArgs &s);
+bool varc3d_lapw_supported(const judi_model *M);
+void varc3d_lapw(const judi_model *M, const CUtensorMap &umap, const CUtensorMap &cmap, float *out);
 
 void Wavefield::init(const judi_model *M, bool born_scratch)
 {
@@ -500,6 +502,13 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
         tma3d_encode(M, M->m.p, nullptr, &tmap_m);
         if (M->dm.p) tma3d_encode(M, M->dm_src(), nullptr, &tmap_dm);
         has_tmap = true;
+        if (born_scratch && M->dm.p && varc3d_lapw_supported(M)) {
+            // isic / fwi Born source on the single-pass flux machinery (varc3d_lapw)
+            lapw = DevBuf(ctx, (size_t)M->g.nalloc, true);
+            for (int s = 0; s < 2; s++) varc3d_encode(M, b[0][s].p, &tmap_halo_v[s], nullptr);
+            varc3d_encode_coef(M, M->dm.p, &tmap_dmc);
+            has_lapw = true;
+        }
     } else if (varc3d_supported(M)) {
         for (int s = 0; s < 2; s++) varc3d_encode(M, b[0][s].p, &tmap_halo[0][s], &tmap_tile[0][s]);
         varc3d_encode(M, M->m.p, nullptr, &tmap_m);
@@ -715,9 +724,10 @@ void stencil_step(const judi_model *M, const StepArgs &s)
     bool ff = M->tti || M->irho_field;
     bool use_tma = M->ndim == 3 && !ff && !M->visco && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
                    (s.f.ic == JUDI_IC_AS || !s.f.grad) && s.tmap != nullptr && tma3d_fuse_supported(s) &&
-                   (!s.born || (s.born_ic == JUDI_IC_AS && s.lin && s.scratch && s.scratch->dd[0].p));
+                   (!s.born || (s.lin && s.scratch && s.scratch->dd[0].p &&
+                                (s.born_ic == JUDI_IC_AS || (s.scratch->has_lapw && !s.qext))));
     bool born_done = false;
-    if (use_tma && s.born && ctx->opt_born_fused) {
+    if (use_tma && s.born && ctx->opt_born_fused && s.born_ic == JUDI_IC_AS) {
         // fused Born (32 B/pt): both fields in one launch, delta handed over in shared memory
         StepArgs a = s;
         a.born = 0;
@@ -743,6 +753,12 @@ void stencil_step(const judi_model *M, const StepArgs &s)
         a2.tmap = &s.lin->tmap_halo[0][s.lin->cur];
         a2.tmap_prev = &s.lin->tmap_tile[0][1 - s.lin->cur];
         a2.qsrc = s.scratch->dd[0].p;
+        if (s.born_ic != JUDI_IC_AS) {
+            // isic / fwi: + ics dt^2 div(dm grad u(t)) from one single-pass flux launch on u(t)
+            Wavefield *W = s.scratch;
+            varc3d_lapw(M, W->tmap_halo_v[W->cur], W->tmap_dmc, W->lapw.p);
+            a2.sfield = W->lapw.p;
+        }
         tma3d_step(M, a2);
     } else if (use_tma) tma3d_step(M, s);
     else if (M->ndim == 3 && ff && !M->visco && ctx->opt_kernel3d == 1 && !(s.scratch && s.scratch->generic_only) &&

@@ -42,6 +42,8 @@ struct TmaArgs {
     float *ulp;          // fused Born (DUAL): output of the linearised field, in place
     const float *qext;   // F_QEXT: space-time source of this step (Grid layout), added as
     float qext_scale;    //   qext_scale * qext  (= dt^2 / irho * wavelet[t], fields_exprs.py:58-81)
+    const float *sfield; // F_QISIC: dt^2 div(dm grad u) of the background field (varc3d_lapw) ...
+    float ics;           // ... and its sign: +1 isic, -1 fwi  (sensitivity.py:191-209)
 };
 
 // DUAL: fused Born step.  Two groups of consumer warps share one CTA: group 0 steps the background
@@ -73,7 +75,8 @@ struct TmaCfg {
 // than the plain one for a single extra store):
 // F_QEXT: extended / full-wavefield source read from one more field (+4 B per point);
 // F_WREC: extended receiver  wrec += dt wavelet[t] u[t]  (fields_exprs.py:85-103, +8 B per point)
-enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16, F_QEXT = 32, F_WREC = 64 };
+// F_QISIC (with F_QSRC): the isic / fwi Born source  -(dm m delta) + ics dt^2 div(dm grad u)
+enum { F_SNAP = 1, F_GRAD = 2, F_ILLUM = 4, F_DDOUT = 8, F_QSRC = 16, F_QEXT = 32, F_WREC = 64, F_QISIC = 128 };
 
 struct TmaMaps {   // tensor maps of one launch (kernel parameter, __grid_constant__)
     CUtensorMap U, P, M;      // haloed u(t), tile u(t-1), tile m
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
             // fused extras: issue their point-wise global loads before waiting on the pipeline so
             // that their latency hides behind the stencil arithmetic of this plane
             [[maybe_unused]] bool fin = false, fvec = false;
-            [[maybe_unused]] float4 us4, g4, il4, qs4, dm4, qx4, wr4;
+            [[maybe_unused]] float4 us4, g4, il4, qs4, dm4, qx4, wr4, sf4;
             if (FUSE != 0 && jt >= 2 * R) {
                 const int z = z0 + jt - 2 * R;
                 const bool zin = z >= rz0 && z < rz1;
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                 if (f_born) {
                     qs4 = *(const float4 *)(a.qsrc + goff);
                     dm4 = __ldg((const float4 *)(a.dm + goff));
+                    if (FUSE & F_QISIC) sf4 = *(const float4 *)(a.sfield + goff);
                 }
             }
             mbar_wait(&fullU[st], (uint32_t)((jt / NS) & 1));
@@ -357,7 +361,13 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                     lz0.x = __fmaf_rn(-dmt4.x, dd4.x, lz0.x); lz0.y = __fmaf_rn(-dmt4.y, dd4.y, lz0.y);
                     lz1.x = __fmaf_rn(-dmt4.z, dd4.z, lz1.x); lz1.y = __fmaf_rn(-dmt4.w, dd4.w, lz1.y);
                 }
-                if (f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
+                if (f_born && (FUSE & F_QISIC)) {
+                    // isic / fwi Born source (dt^2/irho) q = -(dm m delta) + ics dt^2 div(dm grad u)
+                    const f2 q0 = fma2s(a.ics, lo2(sf4), mul2(mul2(mul2s(-1.f, lo2(dm4)), lo2(m4)), lo2(qs4)));
+                    const f2 q1 = fma2s(a.ics, hi2(sf4), mul2(mul2(mul2s(-1.f, hi2(dm4)), hi2(m4)), hi2(qs4)));
+                    lz0 = add2(lz0, q0);
+                    lz1 = add2(lz1, q1);
+                } else if (f_born) {  // Born source (dt^2/irho) q = -dm * (u+ - 2u + u-)
                     lz0.x = __fmaf_rn(-dm4.x, qs4.x, lz0.x); lz0.y = __fmaf_rn(-dm4.y, qs4.y, lz0.y);
                     lz1.x = __fmaf_rn(-dm4.z, qs4.z, lz1.x); lz1.y = __fmaf_rn(-dm4.w, qs4.w, lz1.y);
                 }
@@ -566,6 +576,8 @@ static void launch_fused(const judi_model *M, const StepArgs &s)
     a.dm = s.qsrc ? M->dm_src() : nullptr;
     a.qext = s.qext;
     a.qext_scale = s.qext_scale;
+    a.sfield = s.sfield;
+    a.ics = s.born_ic == JUDI_IC_FWI ? -1.f : 1.f;
     TmaMaps tm;
     tm.U = *s.tmap; tm.P = *s.tmap_prev; tm.M = *s.tmap_m;
     if (DUAL) {
@@ -598,7 +610,7 @@ static int fuse_mask(const StepArgs &s)
 {
     return (s.f.snap[0] ? F_SNAP : 0) | (s.f.grad ? F_GRAD : 0) | (s.f.illum ? F_ILLUM : 0) |
            (s.dd_out ? F_DDOUT : 0) | (s.qsrc ? F_QSRC : 0) | (s.qext ? F_QEXT : 0) |
-           (s.f.wrec ? F_WREC : 0);
+           (s.f.wrec ? F_WREC : 0) | ((s.qsrc && s.sfield) ? F_QISIC : 0);
 }
 
 template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
@@ -617,6 +629,7 @@ static void launch_variant(const judi_model *M, const StepArgs &s)
         FUSE_CASE(F_DDOUT | F_ILLUM)
         FUSE_CASE(F_DDOUT | F_SNAP | F_ILLUM)
         FUSE_CASE(F_QSRC)
+        FUSE_CASE(F_QSRC | F_QISIC)
         // extended / full-wavefield sources (forward_rec_w, forward_wf_src, J_adjoint(ws=...),
         // born_rec_w) and the extended receiver of adjoint_w (interface.py:50-204, 244-276)
         FUSE_CASE(F_QEXT)

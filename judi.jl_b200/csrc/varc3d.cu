@@ -76,9 +76,13 @@ struct VarcArgs {
     float *dd_out;           // Born background pass: write delta = u+ - 2u + u-
     const float *dd_in;      // Born linearised pass: delta of the background field ...
     const float *dm;         // ... and the model perturbation: q = -dm irho delta
+    float *lap_out;          // VF_LAPOUT: dt^2 div(c grad u)  (Grid layout)
 };
 
-enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4, VF_DDOUT = 8, VF_QSRC = 16 };
+// VF_LAPOUT: no time update at all -- the launch writes dt^2 div(c grad u) of the haloed field to
+// `lap_out` (the isic / fwi Born source `laplacian(u, dm irho)`, sensitivity.py:191-209, with the
+// perturbation dm as the coefficient plane); the tile ring (u(t-1), m, irho) is not streamed.
+enum { VF_SNAP = 1, VF_GRAD = 2, VF_ILLUM = 4, VF_DDOUT = 8, VF_QSRC = 16, VF_LAPOUT = 32 };
 
 // staggered first derivative along x at the 4 nodes of a group from the 12-float row window centred
 // on it: PLUS: D+ (node + 1/2), sum_k w_k (u[e+k] - u[e-k+1]); else D- (node - 1/2)
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(VarcC<R>::NTHREADS, 2)
                     tma_load_3d(ringC + s * CSLOT, &tm.C, cx0, cy0, cz0 + c, &fullC[s]);
                 }
                 const int i = j + LEADC - WARM;           // output plane counter (iteration i + 14)
-                if (i >= 0 && i < nzc) {
+                if (!(FUSE & VF_LAPOUT) && i >= 0 && i < nzc) {
                     const int s = i % NP;
                     if (i >= NP) mbar_wait_sleep(&emptyP[s], (uint32_t)(((i / NP) - 1) & 1));
                     mbar_arrive_expect_tx(&fullP[s], 3 * PSLOT * 4);
@@ -412,7 +416,21 @@ __global__ void __launch_bounds__(VarcC<R>::NTHREADS, 2)
                 else bp = cat4(fma2s(-cf.wz[k], lo2(Fz), lo2(bp)), fma2s(-cf.wz[k], hi2(Fz), hi2(bp)));
             }
         }
-        if (out) {
+        if (out && (FUSE & VF_LAPOUT)) {
+            const float4 H = acc[AS(1 - R)];
+            const f2 h0 = mul2s(cf.dt2, lo2(H)), h1 = mul2s(cf.dt2, hi2(H));
+            if (act) {
+                float *o = a.lap_out + gout;
+                if (xfull) *(float4 *)o = cat4(h0, h1);
+                else {
+                    const float v[4] = {h0.x, h0.y, h1.x, h1.y};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (ox + e < g.n[0]) o[e] = v[e];
+                }
+            }
+            gout += g.sz;
+        } else if (out) {
             const float4 uc = *(const float4 *)(fz_ + PSLOT);
             const float4 H = acc[AS(1 - R)];
             mbar_wait(&fullP[pslot], (uint32_t)ppar);
@@ -576,6 +594,55 @@ static void varc3d_launch(const judi_model *M, const StepArgs &s, bool lin = fal
 {
     if (M->r == 2) varc3d_launch_r<2, FUSE>(M, s, lin);
     else varc3d_launch_r<4, FUSE>(M, s, lin);
+}
+
+// dt^2 div(c grad u) of a constant-density model's field u (tensor map `umap`: haloed varc box over
+// the field, `cmap`: coefficient box over c) into `out`: the isic / fwi Born source term.
+template <int R>
+static void varc3d_lapw_r(const judi_model *M, const CUtensorMap &umap, const CUtensorMap &cmap, float *out)
+{
+    typedef VarcC<R> C;
+    judi_ctx *ctx = M->ctx;
+    void (*kern)(const VarcMaps, const VarcArgs) = varc3d_tma<R, VF_LAPOUT, false>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    VarcMaps tm;
+    tm.U = umap; tm.C = cmap;
+    tm.P = umap; tm.M = umap; tm.I = umap;   // not streamed by this flavour
+    VarcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = M->g; a.cf = M->cf;
+    a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
+    a.lap_out = out;
+    const int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
+    int nzc = 1;
+    {
+        long long best = -1;
+        for (int c = 1; c <= 8 && c * 32 <= M->N[2]; c++) {
+            const long long slots = 2LL * ctx->num_sms;
+            const long long waves = ((long long)ntx * nty * c + slots - 1) / slots;
+            const long long cost = waves * ((M->N[2] + c - 1) / c + C::WARM) * (c == 1 ? 106 : 100);
+            if (best < 0 || cost < best) { best = cost; nzc = c; }
+        }
+    }
+    a.zchunk = (M->N[2] + nzc - 1) / nzc;
+    nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
+    kern<<<dim3(ntx, nty, nzc), C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
+    launch_count(ctx, "varc3d_tma");
+}
+
+bool varc3d_lapw_supported(const judi_model *M)
+{
+    return M->ndim == 3 && (M->r == 4 || M->r == 2) && M->ctx->encode_tiled != nullptr;
+}
+
+void varc3d_lapw(const judi_model *M, const CUtensorMap &umap, const CUtensorMap &cmap, float *out)
+{
+    if (M->r == 2) varc3d_lapw_r<2>(M, umap, cmap, out);
+    else varc3d_lapw_r<4>(M, umap, cmap, out);
 }
 
 // One fused variable-density step; false if this combination has no single-pass instantiation.

@@ -171,7 +171,7 @@ def test_fwi_objective_and_options(kind, ndim):
 
 @pytest.mark.parametrize("kind,ndim,so", [("iso", 2, 8), ("iso", 3, 8), ("rho", 2, 8), ("tti", 2, 8), ("rho", 3, 8),
                                           ("tti", 3, 8), ("visco", 2, 8), ("viscoc", 3, 8),
-                                          ("iso", 2, 4), ("iso", 2, 16), ("iso", 3, 16)])
+                                          ("iso", 2, 4), ("iso", 2, 16), ("iso", 3, 16), ("iso", 3, 4)])
 @pytest.mark.parametrize("ic", ["isic", "fwi"])
 def test_isic_fwi_imaging_conditions(kind, ndim, so, ic):
     """test_all_options.jl:13-53 runs isic / fwi on the variable-density and the TTI model
@@ -301,6 +301,45 @@ def test_tma_kernel_extended_source_and_receiver_flavours(so):
     ctx.set_option("timing", 0)
     # one stencil launch per time step, at TMA-kernel speed (the generic kernel is ~5x slower)
     assert st["launches"] == nt - 2
+
+
+@pytest.mark.parametrize("so", [8, 4])
+@pytest.mark.parametrize("ic", ["isic", "fwi"])
+def test_isic_born_fast_path_matches_generic_kernel(so, ic):
+    """3-D isic / fwi Born step on the single-pass machinery (background TMA launch writing delta,
+    one flux launch for dt^2 div(dm grad u), linearised TMA launch with the F_QISIC source) against
+    the one-thread-per-point kernel, partial tiles and several z-chunks included; LS-RTM gradient
+    with stored and checkpointed wavefields."""
+    import judi_jl_b200 as J
+    n = (90, 50, 70)
+    rng = np.random.default_rng(13)
+    v = (1.5 + rng.random(n) * 2.0).astype(np.float32)
+    dm = (0.02 * rng.standard_normal(n)).astype(np.float32)
+    args = dict(origin=(0., 0., 0.), spacing=(10., 12., 8.), shape=n, space_order=so, nbl=11,
+                m=(1 / v ** 2).astype(np.float32), dm=dm)
+    ctx = J.get_context()
+    gm = J.Model(**args)
+    dt = float(gm.critical_dt)
+    nt = 48
+    q = O.ricker_wavelet((nt - 1) * dt, dt, 0.03)[:nt]
+    src = np.array([[430., 300., 250.]], dtype=np.float32)
+    rec = (rng.random((150, 3)) * np.array([890., 588., 552.])).astype(np.float32)
+    y = rng.standard_normal((nt, rec.shape[0])).astype(np.float32)
+    out = {}
+    try:
+        for kern in (0, 1):
+            ctx.set_option("acoustic3d_kernel", kern)
+            dl, _ = J.born_rec(gm, src, q, rec, ic=ic)
+            f, g, _, _ = J.J_adjoint(gm, src, q, rec, y, return_obj=True, ic=ic, born_fwd=True, nlind=True)
+            out[kern] = (dl, g, f)
+    finally:
+        ctx.set_option("acoustic3d_kernel", 1)
+    assert np.linalg.norm(out[0][0]) > 0
+    assert rel_l2(out[1][0], out[0][0]) < 2e-5
+    assert rel_l2(out[1][1], out[0][1]) < 2e-5
+    fc, gc, _, _ = J.J_adjoint(gm, src, q, rec, y, return_obj=True, ic=ic, born_fwd=True, nlind=True,
+                               checkpointing=True)
+    assert fc == out[1][2] and np.array_equal(gc, out[1][1])
 
 
 def test_misfit_callback_and_forward_no_rec():
