@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjudi_b200.so")
-SOURCES = ["capi.cu", "model.cu", "sparse.cu", "kernels.cu", "tma3d.cu", "tti3d.cu", "varc3d.cu", "flux3d.cu", "persist2d.cu", "propagate.cu", "hostops.cu", "comm.cu"]
+SOURCES = ["capi.cu", "model.cu", "sparse.cu", "kernels.cu", "tma3d.cu", "tti3d.cu", "varc3d.cu", "flux3d.cu", "persist2d.cu", "propagate.cu", "hostops.cu", "comm.cu", "isic3d.cu"]
 HEADERS = ["common.cuh", "tma_util.cuh", "propagate.h", os.path.join("..", "..", "include", "judi_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

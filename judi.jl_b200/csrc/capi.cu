@@ -166,6 +166,8 @@ int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value)
     else if (k == "timing") ctx->timing = value;
     else if (k == "persist2d") ctx->opt_persist2d = value;
     else if (k == "persist_vec") ctx->opt_persist_vec = value;
+    else if (k == "ckpt_direct") ctx->opt_ckpt_direct = value;
+    else if (k == "isic_fast") ctx->opt_isic_fast = value;
     else if (k == "profile") ctx->opt_profile = value;
     else if (k == "born_fused") ctx->opt_born_fused = value;
     else if (k == "tti_fused") ctx->opt_tti_fused = value;

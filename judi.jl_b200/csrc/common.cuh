@@ -149,6 +149,8 @@ struct judi_ctx {
     int opt_profile = 0;        // print per-phase wall times of J_adjoint to stderr
     int opt_persist2d = 1;      // 2-D: whole time loop in one persistent cooperative kernel
     int opt_persist_blocks = 0; // ... with at most this many CTAs (0: as many tiles as fit)
+    int opt_isic_fast = 1;      // 3-D acoustic isic / fwi imaging step: TMA step + vectorised pass (0: generic kernel)
+    int opt_ckpt_direct = 1;    // checkpointing: keep as many trailing snapshots in HBM as fit (0: always recompute)
     int opt_persist_vec = 1;    // 2-D acoustic: 4 points per thread; 1: lockstep batches only, 2: single shots too, 0: off
     int num_sms = 148;
     void *encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point

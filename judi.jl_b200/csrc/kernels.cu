@@ -471,6 +471,8 @@ bool varc3d_supported(const judi_model *M);
 void varc3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map);
 void varc3d_encode_coef(const judi_model *M, const float *base, CUtensorMap *map);
 bool varc3d_step(const judi_model *M, const StepArgs &s);
+bool isic3d_supported(const judi_model *M);
+void isic3d_apply(const judi_model *M, const Fuse &f, const float *v, const float *dd, float *usg);
 bool varc3d_lapw_supported(const judi_model *M);
 void varc3d_lapw(const judi_model *M, const CUtensorMap &umap, const CUtensorMap &cmap, float *out);
 
@@ -727,6 +729,25 @@ void stencil_step(const judi_model *M, const StepArgs &s)
                    (!s.born || (s.lin && s.scratch && s.scratch->dd[0].p &&
                                 (s.born_ic == JUDI_IC_AS || (s.scratch->has_lapw && !s.qext))));
     bool born_done = false;
+    // isic / fwi imaging step of the 3-D acoustic gradient: TMA step that also writes delta, then
+    // one vectorised imaging pass (isic3d.cu) instead of the one-point-per-thread kernel
+    const bool isic_fast = M->ndim == 3 && !ff && !M->visco && ctx->opt_kernel3d == 1 && tma3d_supported(M) &&
+                           isic3d_supported(M) && s.f.grad && s.f.ic != JUDI_IC_AS && !s.born && !s.qext &&
+                           !s.f.wrec && !s.f.snap[0] && s.tmap != nullptr && s.scratch != nullptr &&
+                           ctx->opt_isic_fast;
+    if (isic_fast) {
+        Wavefield *W = s.scratch;
+        if (!W->dd[0].p) W->dd[0] = DevBuf(ctx, (size_t)M->g.nalloc, true);
+        if (!W->lapw.p) W->lapw = DevBuf(ctx, (size_t)M->g.nalloc, true);
+        StepArgs a1 = s;
+        a1.f.grad = nullptr;
+        a1.f.usnap[0] = nullptr;
+        a1.dd_out = W->dd[0].p;
+        tma3d_step(M, a1);
+        // s.u[0] is still level t (the step wrote the new level over level t-+1)
+        isic3d_apply(M, s.f, s.u[0], W->dd[0].p, W->lapw.p);
+        born_done = true;
+    } else
     if (use_tma && s.born && ctx->opt_born_fused && s.born_ic == JUDI_IC_AS) {
         // fused Born (32 B/pt): both fields in one launch, delta handed over in shared memory
         StepArgs a = s;

@@ -745,34 +745,69 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
 
     // ---- snapshot storage ------------------------------------------------------------------
     const size_t slot_floats = (size_t)reg.slot * nf;
+    // Checkpointing in HBM (interface.py:473-562 replaces pyrevolve's schedule): the time steps
+    // 1 .. T are split into   [ segments of `seg` steps, each with a checkpointed state ] [ the
+    // last `ndirect` steps ].  The snapshots of the last `ndirect` levels are written by the
+    // first forward sweep and stay in HBM (they are the first ones the reverse sweep needs); only
+    // the segments are recomputed, one at a time, into a buffer of `seg` snapshots.  With 180 GB
+    // of HBM the whole history often fits (C3: 1040 physical-domain levels = 135 GB): then
+    // ndirect = T, nothing is checkpointed and nothing recomputed -- what Revolve's schedule
+    // degenerates to when it is given as many checkpoints as time steps.  A user-given
+    // n_checkpoints keeps its meaning (a budget of states): seg = nt / n_checkpoints, ndirect = 0.
     int seg = 0, nseg = 0;          // checkpointing: segment length / count
+    int ndirect = 0;                // checkpointing: trailing time levels kept as snapshots
     int nslots;
     std::vector<DevBuf> ckpt;       // per segment: level t and level t-1 of every field
     std::vector<DevBuf> ckpt_r;     // ... and the visco-acoustic memory variable
-    if (dft) {
-        nslots = 0;
-    } else if (!o->checkpointing) {
-        nslots = num_slots(nt, k);
-    } else {
-        // fixed-stride checkpoints + segment recompute: memory ~ seg snapshots + (nt/seg) states;
-        // seg ~ sqrt(nt * state/snapshot) balances the two, bounded by n_checkpoints if given.
-        double state = 2.0 * nf * (double)M->g.nalloc, snapf = (double)slot_floats;
-        seg = (int)std::ceil(std::sqrt((double)nt * state / snapf));
-        if (o->n_checkpoints > 0) seg = std::max(1, (nt + o->n_checkpoints - 1) / o->n_checkpoints);
-        seg = std::max(1, std::min(seg, nt));
-        nseg = (nt - 2 + seg - 1) / seg;
-        nslots = seg;
-    }
+    double avail = 0.0, fixed_need = 0.0;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         unsigned long long reserved = 0, used = 0;
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
         cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
-        double avail = (double)free_b + (double)(reserved - used) + 4.0 * (double)ctx->arena_floats;
+        avail = (double)free_b + (double)(reserved - used) + 4.0 * (double)ctx->arena_floats;
+        // what the sweeps allocate besides snapshots: the adjoint wavefield V (W and WL exist
+        // already), the flux-form or Born scratch of each wavefield, gradient and illumination
+        const bool fluxp = M->tti || M->irho_field;
+        const double field = (double)M->g.nalloc * 4.0;
+        const double scratch = (fluxp ? (M->tti ? 6.0 : 3.0) : 0.0) + (born ? 2.0 * nf : 0.0);
+        fixed_need = (2.0 * nf + scratch) * field + 3.0 * (double)reg.slot * 4.0 +
+                     (dft ? 2.0 * o->nfreq * slot_floats * 4.0 : 0.0);
+    }
+    if (dft) {
+        nslots = 0;
+    } else if (!o->checkpointing) {
+        nslots = num_slots(nt, k);
+    } else {
+        const int T = nt - 2;
+        const double state = (2.0 * nf + (M->visco ? 1.0 : 0.0)) * (double)M->g.nalloc * 4.0;
+        const double snapb = (double)slot_floats * 4.0;
+        const double budget = 0.90 * avail - fixed_need;
+        // (option ckpt_direct = N > 1 forces a tail of exactly N levels: test hook of the hybrid path)
+        const int forced = ctx->opt_ckpt_direct > 1 ? std::min(ctx->opt_ckpt_direct, T - 1) : -1;
+        if (o->n_checkpoints <= 0 && ctx->opt_ckpt_direct == 1 && (double)T * snapb <= budget) {
+            ndirect = T;            // everything fits: store, never recompute
+        } else {
+            // fixed-stride checkpoints + segment recompute: memory ~ seg snapshots + (T/seg) states;
+            // seg ~ sqrt(T * state/snapshot) balances the two
+            seg = (int)std::ceil(std::sqrt((double)nt * state / snapb));
+            if (o->n_checkpoints > 0) seg = std::max(1, (nt + o->n_checkpoints - 1) / o->n_checkpoints);
+            seg = std::max(1, std::min(seg, T));
+            if (o->n_checkpoints <= 0 && ctx->opt_ckpt_direct) {
+                // whatever HBM is left after the recompute buffer and the states holds the tail
+                const double left = budget - (double)seg * snapb - std::ceil((double)T / seg) * state;
+                ndirect = (int)std::max(0.0, std::min((double)(T - 1), std::floor(left / snapb)));
+                if (forced >= 0) ndirect = forced;
+            }
+            nseg = (T - ndirect + seg - 1) / seg;
+        }
+        nslots = seg + ndirect;
+    }
+    {
+        const double field = (double)M->g.nalloc * 4.0;
         double need = (double)nslots * slot_floats * 4.0 +
-                      (double)nseg * 2.0 * nf * (double)M->g.nalloc * 4.0 +
-                      (dft ? 2.0 * o->nfreq * slot_floats * 4.0 : 0.0);
+                      (double)nseg * (2.0 * nf + (M->visco ? 1.0 : 0.0)) * field + fixed_need;
         if (need > 0.97 * avail) {
             char b[256];
             snprintf(b, sizeof(b),
@@ -889,8 +924,9 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
         // snapshots of u, not the linearised field
         ckpt.resize((size_t)nseg * 2 * nf);
         if (M->visco) ckpt_r.resize((size_t)nseg);   // the memory variable is part of the state
+        const int tseg_end = nt - 2 - ndirect;     // last time step covered by a segment
         for (int s = 0; s < nseg; s++) {
-            int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
+            int ts = 1 + s * seg, te = std::min(ts + seg - 1, tseg_end);
             if (M->visco) {
                 ckpt_r[s] = DevBuf(ctx, (size_t)M->g.nalloc, false);
                 CUDA_CHECK(cudaMemcpyAsync(ckpt_r[s].p, W.rmem.p, (size_t)M->g.nalloc * sizeof(float),
@@ -907,6 +943,8 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
             }
             fwd_range(ts, te, 0, 0, true);
         }
+        // the trailing levels go straight to their slots (behind the recompute buffer of `seg` slots)
+        if (ndirect > 0) fwd_range(tseg_end + 1, nt - 2, 2, tseg_end + 1 - seg, true);
         fsave.illum = nullptr;  // the recomputation must not add to the illumination again
     }
 
@@ -1016,8 +1054,10 @@ void run_J_adjoint(judi_model *M, int nsrc, const float *src_coords, const float
     if (!o->checkpointing) {
         adj_range(nt - 2, 1, 1, 0);
     } else {
+        const int tseg_end = nt - 2 - ndirect;
+        if (ndirect > 0) adj_range(nt - 2, tseg_end + 1, 2, tseg_end + 1 - seg);
         for (int s = nseg - 1; s >= 0; s--) {
-            int ts = 1 + s * seg, te = std::min(ts + seg - 1, nt - 2);
+            int ts = 1 + s * seg, te = std::min(ts + seg - 1, tseg_end);
             // restore the state at the start of the segment and recompute its snapshots
             W.cur = 0;
             if (M->visco) {

@@ -151,6 +151,16 @@ def test_fwi_objective_and_options(kind, ndim):
     fc2, gc2, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, checkpointing=True,
                                  n_checkpoints=7)
     assert np.array_equal(gc2, g)
+    # the three schedules of the in-HBM checkpointing: everything kept (default on a grid this
+    # small), everything recomputed segment by segment, and a tail of 37 levels kept
+    ctx = J.get_context()
+    try:
+        for mode in (0, 37):
+            ctx.set_option("ckpt_direct", mode)
+            fcm, gcm, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, checkpointing=True)
+            assert fcm == f and np.array_equal(gcm, g), mode
+    finally:
+        ctx.set_option("ckpt_direct", 1)
     # physical-domain snapshots: same gradient inside, zero in the absorbing layer
     _, gp, _, _ = J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, snapshot_region="physical")
     crop = tuple(slice(l, n - r) for (l, r), n in zip(gm.padsizes, g.shape))
