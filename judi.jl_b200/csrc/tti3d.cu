@@ -126,7 +126,11 @@ __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const f
     o1 = pk(o[2], o[3]);
 }
 
-template <int R, int FUSE, bool ROTF, bool ROTD>
+// UF / UD: how the register queues of the F / D role advance: 1 = shifted by one slot every plane
+// (2R-1 float4 moves per field), 2 = main loop unrolled by two with one spare slot, shifted by two
+// every second plane (half the moves, twice the code), NQ = rotated at compile time (no moves,
+// NQ times the code).
+template <int R, int FUSE, int UF, int UD>
 __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     tti3d_tma(const __grid_constant__ TtiMaps tm, const TtiArgs a)
 {
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     constexpr int CPY = C::CPY, CSLOT = C::CSLOT, NPAR = C::NPAR, PSLOT = C::PSLOT, NS = C::NS, NC = C::NC;
     constexpr int NP = C::NP, NQ = C::NQ, NI = C::NI, NF = C::NF, ND = C::ND, FXW = C::FXW, FX = C::FX;
     constexpr int FY = C::FY, FBUF = C::FBUF, LEADU = C::LEADU, LEADC = C::LEADC, WARM = C::WARM;
-    static_assert(!(ROTF || ROTD) || NS == NQ, "rotated queues need ring length == queue length");
+    static_assert(!(UF == NQ || UD == NQ) || NS == NQ, "rotated queues need ring length == queue length");
     extern __shared__ unsigned char smem_raw[];
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float *ringC = ringU + NS * 2 * USLOT;       // [NC][NPAR][CSLOT]
@@ -208,11 +212,12 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     }
 
     // register slot of plane zf + k, k = -3 .. 4 (rotated at compile time, or shifted every plane)
-#define SL(k) (ROT ? ((ph + (k) + 2 * NQ - R) % NQ) : ((k) + R - 1))
+#define SL(k) (ROT ? ((ph + (k) + 2 * NQ - R) % NQ) : (ph + (k) + R - 1))
 
     if (tid < NF) {
-        constexpr bool ROT = ROTF;
-        constexpr int UNR = ROT ? NQ : 1;
+        constexpr bool ROT = UF == NQ;
+        constexpr int UNR = UF;
+        constexpr int NQL = ROT ? NQ : NQ + UNR - 1;
         // ===== F role: flux node group cx in -1..8 (groups of 4 x-points), cy in -4..18 ============
         const bool tile = tid < NI;                    // warps 0-3 (warp uniform)
         int cx, cy;
@@ -236,19 +241,19 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
         const int st = cy * TX + 4 * cx;                          // ... inside a tile (tile threads)
         const f2 bb = pk1(a.irho_c);
 
-        float4 q1[NQ], q2[NQ];   // u1, u2 of planes zf-3 .. zf+4 at this node group
+        float4 q1[NQL], q2[NQL];   // u1, u2 of planes zf-3 .. zf+4 at this node group
 #pragma unroll
-        for (int k = 0; k < NQ; k++) q1[k] = q2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < NQL; k++) q1[k] = q2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         int cslot = 0, cpar = 0;   // parameter ring position / parity
 
         for (int j0 = 0; j0 < total; j0 += UNR) {
 #pragma unroll
             for (int ph = 0; ph < UNR; ph++) {
                 const int j = j0 + ph;
-                if (ROT && j >= total) break;
-                if (!ROT) {
+                if (UNR > 1 && j >= total) break;
+                if (!ROT && ph == 0) {
 #pragma unroll
-                    for (int k = 0; k < NQ - 1; k++) { q1[k] = q1[k + 1]; q2[k] = q2[k + 1]; }
+                    for (int k = 0; k < NQL - UNR; k++) { q1[k] = q1[k + UNR]; q2[k] = q2[k + UNR]; }
                 }
                 const int s_in = ROT ? ph : (j & (NS - 1));
                 mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
@@ -357,8 +362,9 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     }
 
     // ===== D role: divergence, time update and fused extras of one tile group ======================
-    constexpr bool ROT = ROTD;
-    constexpr int UNR = ROT ? NQ : 1;
+    constexpr bool ROT = UD == NQ;
+    constexpr int UNR = UD;
+    constexpr int NQL = ROT ? NQ : NQ + UNR - 1;
     const int dt_ = tid - NF;
     const int cx = dt_ & (TXG - 1), cy = dt_ / TXG;
     const int sfx = cy * FXW + 4 * (cx + 1), sfy = (cy + R) * TX + 4 * cx, st = cy * TX + 4 * cx;
@@ -384,16 +390,16 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     [[maybe_unused]] const long long rstride = f_reg ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
     [[maybe_unused]] const float gc = f_grad ? fz.gcoef * a.irho_c : 0.f;
 
-    float4 aP[NQ], aM[NQ];   // divergence accumulators of the output planes zf-3 .. zf+4
+    float4 aP[NQL], aM[NQL];   // divergence accumulators of the output planes zf-3 .. zf+4
 #pragma unroll
-    for (int k = 0; k < NQ; k++) aP[k] = aM[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < NQL; k++) aP[k] = aM[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int pslot = 0, ppar = 0;   // tile ring position / parity
 
     for (int j0 = FIRST; j0 < total; j0 += UNR) {
 #pragma unroll
         for (int ph = 0; ph < UNR; ph++) {
             const int j = j0 + ph;
-            if (ROT && j >= total) break;
+            if (UNR > 1 && j >= total) break;
             const int zf = z0 - (3 * R - 1) + j;
             const bool need_xy = zf >= z0 && zf < z1;
             const bool out = j >= WARM;
@@ -575,9 +581,9 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
             }
             // this flux buffer may be overwritten by the F warps two planes from now
             if (j + 2 < total) named_bar_arrive(3 + (j & 1), NSYNC);
-            if (!ROT) {
+            if (!ROT && ph == UNR - 1) {
 #pragma unroll
-                for (int k = 0; k < NQ - 1; k++) { aP[k] = aP[k + 1]; aM[k] = aM[k + 1]; }
+                for (int k = 0; k < NQL - UNR; k++) { aP[k] = aP[k + UNR]; aM[k] = aM[k + UNR]; }
             }
         }
     }
@@ -628,14 +634,16 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
     judi_ctx *ctx = M->ctx;
     // register queues: 2 shifted every plane (default), 1 rotated at compile time, 3 / 4 only the
     // F / D role rotated
-    // (the rotated variants need ring length == queue length: R = 4 only)
-    constexpr bool CANROT = C::NS == C::NQ;
-    const int var = (CANROT && (ctx->opt_tti_fused == 1 || ctx->opt_tti_fused == 3 || ctx->opt_tti_fused == 4))
-                        ? ctx->opt_tti_fused : 2;
+    // option tti_fused: 2 shifted queues, 1 rotated (needs ring length == queue length: R = 4 only),
+    // 5 / 6 / 7: loops unrolled by two in both roles / in F only / in D only
+    constexpr int ROTQ = C::NS == C::NQ ? C::NQ : 1;
+    int var = ctx->opt_tti_fused;
+    if (var == 1 && ROTQ == 1) var = 2;
+    if (var != 1 && var != 5 && var != 6 && var != 7) var = 2;
     void (*kern)(const TtiMaps, const TtiArgs) =
-        var == 1 ? tti3d_tma<R, FUSE, CANROT, CANROT> : var == 3 ? tti3d_tma<R, FUSE, CANROT, false>
-        : var == 4 ? tti3d_tma<R, FUSE, false, CANROT> : tti3d_tma<R, FUSE, false, false>;
-    static bool configured[5] = {false, false, false, false, false};
+        var == 1 ? tti3d_tma<R, FUSE, ROTQ, ROTQ> : var == 5 ? tti3d_tma<R, FUSE, 2, 2>
+        : var == 6 ? tti3d_tma<R, FUSE, 2, 1> : var == 7 ? tti3d_tma<R, FUSE, 1, 2> : tti3d_tma<R, FUSE, 1, 1>;
+    static bool configured[8] = {false, false, false, false, false, false, false, false};
     if (!configured[var]) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured[var] = true;
