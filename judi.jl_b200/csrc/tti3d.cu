@@ -590,6 +590,392 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
 #undef SL
 }
 
+// ================================================================================================
+// tti3d_h: the same step with HALF-WIDTH threads (2 x-points per thread instead of 4), R = 4.
+// tti3d_tma is latency-bound, not issue-bound: 12 warps per SM at 160 registers, 46 % of the issue
+// slots used, and halving its register-queue moves does not change its time (option tti_fused =
+// 5/6/7).  What raises the number of warps is fewer registers per thread, and the z-queues of the
+// two fields are 64 of them: with 2 x-points per thread they are 32, the kernel fits 23 warps
+// (448 F + 256 D + 32 producer threads) under an 88-register cap.  The price: the x windows are no
+// longer amortised over 4 points (+15 % shared-memory wavefronts).  Same shared-memory layout,
+// producer and hand-over protocol as tti3d_tma<4>; plain / save / imaging-condition flavours.
+namespace ttih {
+typedef TtiC<4> C;
+constexpr int R = 4;
+constexpr int TXP = C::TX / 2;                  // 16 pairs per tile row
+constexpr int NFT = TXP * C::TY;                // 256 tile threads
+constexpr int NFX = 4 * C::TY;                  // x halo: pairs -2, -1, 16, 17 of every row
+constexpr int NFY = 128;                        // y halo: 7 rows x 16 pairs (112) in whole warps
+constexpr int NF = NFT + NFX + NFY;             // 448
+constexpr int ND = NFT;                         // 256
+constexpr int NTHREADS = NF + ND + 32;          // 736
+}  // namespace ttih
+
+// D+ (PLUS) / D- along x at the 2 nodes of a pair from the 10-float window w (w[4] = own.x)
+template <bool PLUS>
+__device__ __forceinline__ f2 ttih_dx(const float *wx, const float2 &l0, const float2 &l1, const float2 &c,
+                                      const float2 &r0, const float2 &r1)
+{
+    const float w[10] = {l0.x, l0.y, l1.x, l1.y, c.x, c.y, r0.x, r0.y, r1.x, r1.y};
+    float o[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 1; k <= ttih::R; k++) {
+            const float d = PLUS ? __fsub_rn(w[4 + e + k], w[4 + e - k + 1])
+                                 : __fsub_rn(w[4 + e + k - 1], w[4 + e - k]);
+            acc = (k == 1) ? __fmul_rn(wx[1], d) : __fmaf_rn(wx[k], d, acc);
+        }
+        o[e] = acc;
+    }
+    return pk(o[0], o[1]);
+}
+
+template <int FUSE>
+__global__ void __launch_bounds__(ttih::NTHREADS, 1)
+    tti3d_h(const __grid_constant__ TtiMaps tm, const TtiArgs a)
+{
+    typedef TtiC<4> C;
+    constexpr int R = 4;
+    constexpr int TX = C::TX, TY = C::TY, UPX = C::UPX, USLOT = C::USLOT, CPX = C::CPX;
+    constexpr int CPY = C::CPY, CSLOT = C::CSLOT, NPAR = C::NPAR, PSLOT = C::PSLOT, NS = C::NS, NC = C::NC;
+    constexpr int NP = C::NP, NQ = C::NQ, FXW = C::FXW, FX = C::FX;
+    constexpr int FY = C::FY, FBUF = C::FBUF, LEADU = C::LEADU, LEADC = C::LEADC, WARM = C::WARM;
+    constexpr int TXP = ttih::TXP, NFT = ttih::NFT, NFX = ttih::NFX, NF = ttih::NF, ND = ttih::ND;
+    extern __shared__ unsigned char smem_raw[];
+    float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    float *ringC = ringU + NS * 2 * USLOT;
+    float *ringP = ringC + NC * NPAR * CSLOT;
+    float *fbuf = ringP + NP * 3 * PSLOT;
+    uint64_t *fullU = (uint64_t *)(fbuf + 2 * FBUF);
+    uint64_t *emptyU = fullU + NS;
+    uint64_t *fullC = emptyU + NS;
+    uint64_t *emptyC = fullC + NC;
+    uint64_t *fullP = emptyC + NC;
+    uint64_t *emptyP = fullP + NP;
+
+    const Grid &g = a.g;
+    const Coefs &cf = a.cf;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int z0 = blockIdx.z * a.zchunk;
+    const int z1 = min(z0 + a.zchunk, g.n[2]);
+    const int nzc = z1 - z0;
+    const int total = nzc + WARM;
+    constexpr int FIRST = 2 * R - 1;
+    constexpr int NSYNC = NF + ND;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NF / 32); }
+        for (int s = 0; s < NC; s++) { mbar_init(&fullC[s], 1); mbar_init(&emptyC[s], NF / 32); }
+        for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], ND / 32); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (tid >= NF + ND) {
+        // ===== producer warp (identical to tti3d_tma<4>) ===========================================
+        if (lane == 0) {
+            const int bx = g.hx + x0 - 8, by = g.hy + y0 - (2 * R - 1), bz = g.hz + z0 - (2 * R - 1);
+            const int cx0 = g.hx + x0 - 4, cy0 = g.hy + y0 - R, cz0 = g.hz + z0 - R;
+            const int tx0 = g.hx + x0, ty0 = g.hy + y0, tz0 = g.hz + z0;
+            for (int j = -LEADU; j < total; j++) {
+                const int pj = j + LEADU;
+                if (pj < total) {
+                    const int s = pj % NS;
+                    if (pj >= NS) mbar_wait_sleep(&emptyU[s], (uint32_t)(((pj / NS) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullU[s], 2 * UPX * C::UPY * 4);
+                    tma_load_3d(ringU + s * 2 * USLOT, &tm.U1, bx, by, bz + pj, &fullU[s]);
+                    tma_load_3d(ringU + s * 2 * USLOT + USLOT, &tm.U2, bx, by, bz + pj, &fullU[s]);
+                }
+                const int c = j + LEADC - FIRST;
+                if (c >= 0 && c < total - FIRST) {
+                    const int s = c % NC;
+                    if (c >= NC) mbar_wait_sleep(&emptyC[s], (uint32_t)(((c / NC) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullC[s], NPAR * CPX * CPY * 4);
+#pragma unroll
+                    for (int p = 0; p < NPAR; p++)
+                        tma_load_3d(ringC + (s * NPAR + p) * CSLOT, &tm.C[p], cx0, cy0, cz0 + c, &fullC[s]);
+                }
+                const int i = j + LEADC - WARM;
+                if (i >= 0 && i < nzc) {
+                    const int s = i % NP;
+                    if (i >= NP) mbar_wait_sleep(&emptyP[s], (uint32_t)(((i / NP) - 1) & 1));
+                    mbar_arrive_expect_tx(&fullP[s], 3 * PSLOT * 4);
+                    tma_load_3d(ringP + s * 3 * PSLOT, &tm.P1, tx0, ty0, tz0 + i, &fullP[s]);
+                    tma_load_3d(ringP + s * 3 * PSLOT + PSLOT, &tm.P2, tx0, ty0, tz0 + i, &fullP[s]);
+                    tma_load_3d(ringP + s * 3 * PSLOT + 2 * PSLOT, &tm.M, tx0, ty0, tz0 + i, &fullP[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    if (tid < NF) {
+        // ===== F role: flux at the pair cx2 in -2..17 (x = 2 cx2), row cy in -4..18 ==================
+        const bool tile = tid < NFT;
+        int cx2, cy;
+        bool wr_x = false, wr_y = false;
+        if (tile) { cx2 = tid & (TXP - 1); cy = tid / TXP; wr_x = wr_y = true; }
+        else if (tid < NFT + NFX) {
+            const int h = tid - NFT, pp = h & 3;
+            cx2 = pp < 2 ? pp - 2 : TXP - 2 + pp;
+            cy = h >> 2;
+            wr_x = true;
+        } else {
+            const int h = tid - NFT - NFX, row = h / TXP;   // rows beyond 2R-2 are idle (mirror the last one)
+            cx2 = h & (TXP - 1);
+            cy = row < R ? row - R : TY + min(row, 2 * R - 2) - R;
+            wr_y = row < 2 * R - 1;
+        }
+        const int su = (cy + 2 * R - 1) * UPX + 2 * cx2 + 8;
+        const int sc = (cy + R) * CPX + 2 * cx2 + 4;
+        const int sfx = cy * FXW + 2 * cx2 + 4;
+        const int sfy = (cy + R) * TX + 2 * cx2;
+        const int st = cy * TX + 2 * cx2;
+        const f2 bb = pk1(a.irho_c);
+
+        float2 q1[NQ], q2[NQ];   // u1, u2 of planes zf-3 .. zf+4 at this pair
+#pragma unroll
+        for (int k = 0; k < NQ; k++) q1[k] = q2[k] = make_float2(0.f, 0.f);
+        int cslot = 0, cpar = 0;
+
+        for (int j = 0; j < total; j++) {
+#pragma unroll
+            for (int k = 0; k < NQ - 1; k++) { q1[k] = q1[k + 1]; q2[k] = q2[k + 1]; }
+            const int s_in = j & (NS - 1);
+            mbar_wait(&fullU[s_in], (uint32_t)((j / NS) & 1));
+            q1[NQ - 1] = *(const float2 *)(ringU + s_in * 2 * USLOT + su);
+            q2[NQ - 1] = *(const float2 *)(ringU + s_in * 2 * USLOT + USLOT + su);
+            if (j < FIRST) {
+                if (j < R - 1) {
+                    __syncwarp();
+                    mbar_arrive_if(&emptyU[s_in], lane == 0);
+                }
+                continue;
+            }
+            const int zf = z0 - (3 * R - 1) + j;
+            const bool need_xy = zf >= z0 && zf < z1;
+            const bool work = tile || need_xy;
+            const int s_c = (j + NS - R) & (NS - 1);
+            float *fb = fbuf + (j & 1) * FBUF;
+            f2 G[2][3];
+            mbar_wait(&fullC[cslot], (uint32_t)cpar);
+            if (work) {
+#pragma unroll
+                for (int f = 0; f < 2; f++) {
+                    const float *pl = ringU + s_c * 2 * USLOT + f * USLOT + su;
+                    const float2 *q = f ? q2 : q1;
+                    const float2 c = q[R - 1];
+                    G[f][0] = ttih_dx<true>(cf.wx, *(const float2 *)(pl - 4), *(const float2 *)(pl - 2), c,
+                                            *(const float2 *)(pl + 2), *(const float2 *)(pl + 4));
+                    f2 gy, gz;
+#pragma unroll
+                    for (int k = 1; k <= R; k++) {
+                        const float2 p = *(const float2 *)(pl + k * UPX);
+                        const float2 m = (k == 1) ? c : *(const float2 *)(pl - (k - 1) * UPX);
+                        const f2 dy = sub2(p, m);
+                        const f2 dz = sub2(q[R - 1 + k], q[R - k]);
+                        if (k == 1) { gy = mul2s(cf.wy[1], dy); gz = mul2s(cf.wz[1], dz); }
+                        else { gy = fma2s(cf.wy[k], dy, gy); gz = fma2s(cf.wz[k], dz, gz); }
+                    }
+                    G[f][1] = gy;
+                    G[f][2] = gz;
+                }
+            }
+            // the flux buffer of this parity was read by the D warps two planes ago
+            if (j >= FIRST + 2) named_bar_sync(3 + (j & 1), NSYNC);
+            if (work) {
+                // closed-form rotation: P = A0 g1 + B0 g2 + sP r, M = B0 g1 + C0 g2 + sM r; every
+                // component goes to shared memory as soon as it exists (few live registers)
+                const float *pc = ringC + cslot * NPAR * CSLOT + sc;
+                const f2 A0 = *(const f2 *)pc, B0 = *(const f2 *)(pc + CSLOT), C0 = *(const f2 *)(pc + 2 * CSLOT);
+                const f2 rx = *(const f2 *)(pc + 3 * CSLOT), ry = *(const f2 *)(pc + 4 * CSLOT);
+                const f2 rz = *(const f2 *)(pc + 5 * CSLOT);
+                const f2 d1 = fma2(rz, G[0][2], fma2(ry, G[0][1], mul2(rx, G[0][0])));
+                const f2 d2 = fma2(rz, G[1][2], fma2(ry, G[1][1], mul2(rx, G[1][0])));
+                const f2 nB0 = mul2s(-1.f, B0);
+                const f2 sP = fma2(nB0, d2, mul2(sub2(bb, A0), d1));
+                const f2 sM = fma2(nB0, d1, mul2(mul2s(-1.f, C0), d2));
+                if (need_xy && wr_x) {
+                    *(f2 *)(fb + sfx) = fma2(sP, rx, fma2(B0, G[1][0], mul2(A0, G[0][0])));
+                    *(f2 *)(fb + FX + sfx) = fma2(sM, rx, fma2(C0, G[1][0], mul2(B0, G[0][0])));
+                }
+                if (need_xy && wr_y) {
+                    *(f2 *)(fb + 2 * FX + sfy) = fma2(sP, ry, fma2(B0, G[1][1], mul2(A0, G[0][1])));
+                    *(f2 *)(fb + 2 * FX + FY + sfy) = fma2(sM, ry, fma2(C0, G[1][1], mul2(B0, G[0][1])));
+                }
+                if (tile) {
+                    float *fz_ = fb + 2 * FX + 2 * FY + st;
+                    *(f2 *)fz_ = fma2(sP, rz, fma2(B0, G[1][2], mul2(A0, G[0][2])));
+                    *(f2 *)(fz_ + PSLOT) = fma2(sM, rz, fma2(C0, G[1][2], mul2(B0, G[0][2])));
+                    *(float2 *)(fz_ + 2 * PSLOT) = q1[0];     // u1, u2 of the output plane zf-3
+                    *(float2 *)(fz_ + 3 * PSLOT) = q2[0];
+                }
+            }
+            // plane zf and its parameters are dead for this warp
+            __syncwarp();
+            mbar_arrive_if(&emptyU[s_c], lane == 0); mbar_arrive_if(&emptyC[cslot], lane == 0);
+            if (++cslot == NC) { cslot = 0; cpar ^= 1; }
+            __threadfence_block();
+            named_bar_arrive(1 + (j & 1), NSYNC);
+        }
+        return;
+    }
+
+    // ===== D role: divergence, time update and fused extras of one pair =============================
+    const int dt_ = tid - NF;
+    const int cx2 = dt_ & (TXP - 1), cy = dt_ / TXP;
+    const int sfx = cy * FXW + 2 * cx2 + 4, sfy = (cy + R) * TX + 2 * cx2, st = cy * TX + 2 * cx2;
+    const int ox = x0 + 2 * cx2, oy = y0 + cy;
+    const bool act = ox < g.n[0] && oy < g.n[1];
+    const bool xfull = ox + 1 < g.n[0];
+    long long gout = g.at(ox, oy, z0);
+    f2 dxy = pk1(0.f);
+    if (act) {
+        const float2 d2_ = *(const float2 *)(a.dx + ox);
+        dxy = add2(d2_, pk1(a.dy[oy]));
+    }
+    constexpr bool f_snap = (FUSE & TF_SNAP) != 0, f_grad = (FUSE & TF_GRAD) != 0;
+    constexpr bool f_reg = f_snap || f_grad;
+    [[maybe_unused]] const Fuse &fz = a.f;
+    [[maybe_unused]] const bool f_xy = f_reg && act && oy >= fz.reg.lo[1] && oy < fz.reg.hi[1] &&
+                                       ox + 1 >= fz.reg.lo[0] && ox < fz.reg.hi[0];
+    [[maybe_unused]] const bool f_vec = f_xy && (fz.reg.lo[0] & 1) == 0 && ox >= fz.reg.lo[0] &&
+                                        ox + 1 < fz.reg.hi[0];
+    [[maybe_unused]] long long ri = f_reg ? fz.reg.at(ox, oy, z0) : 0;
+    [[maybe_unused]] const long long rstride = f_reg ? (long long)fz.reg.pitch * fz.reg.ext[1] : 0;
+    [[maybe_unused]] const float gc = f_grad ? fz.gcoef * a.irho_c : 0.f;
+
+    float2 aP[NQ], aM[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; k++) aP[k] = aM[k] = make_float2(0.f, 0.f);
+    int pslot = 0, ppar = 0;
+
+    for (int j = FIRST; j < total; j++) {
+        const int zf = z0 - (3 * R - 1) + j;
+        const bool need_xy = zf >= z0 && zf < z1;
+        const bool out = j >= WARM;
+        const int z = z0 + j - WARM;
+        const float *fb = fbuf + (j & 1) * FBUF;
+        float dz_s = 0.f;
+        [[maybe_unused]] bool fin = false, fvec = false;
+        [[maybe_unused]] float2 us1, us2, G2;
+        if (out) {
+            dz_s = __ldg(a.dz + z);
+            if (f_reg) {
+                const bool zin = z >= fz.reg.lo[2] && z < fz.reg.hi[2];
+                fin = f_xy && zin;
+                fvec = f_vec && zin;
+                if (f_grad && f_vec && (cx2 & 1) == 0 && z + 3 >= fz.reg.lo[2] && z + 3 < fz.reg.hi[2]) {
+                    prefetch_l2(fz.usnap[0] + ri + 3 * rstride);
+                    prefetch_l2(fz.usnap[1] + ri + 3 * rstride);
+                    prefetch_l2(fz.grad + ri + 3 * rstride);
+                }
+                if (fvec && f_grad) {
+                    us1 = __ldg((const float2 *)(fz.usnap[0] + ri));
+                    us2 = __ldg((const float2 *)(fz.usnap[1] + ri));
+                    G2 = *(const float2 *)(fz.grad + ri);
+                }
+            }
+        }
+        named_bar_sync(1 + (j & 1), NSYNC);
+        if (need_xy) {
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                const float *px = fb + f * FX + sfx;
+                const f2 lx = ttih_dx<false>(cf.wx, *(const float2 *)(px - 4), *(const float2 *)(px - 2),
+                                             *(const float2 *)px, *(const float2 *)(px + 2), *(const float2 *)(px + 4));
+                const float *py = fb + 2 * FX + f * FY + sfy;
+                f2 ly;
+#pragma unroll
+                for (int k = 1; k <= R; k++) {
+                    const f2 d = sub2(*(const f2 *)(py + (k - 1) * TX), *(const f2 *)(py - k * TX));
+                    if (k == 1) ly = mul2s(cf.wy[1], d);
+                    else ly = fma2s(cf.wy[k], d, ly);
+                }
+                float2 &acc = f ? aM[R - 1] : aP[R - 1];
+                acc = add2(acc, add2(lx, ly));
+            }
+        }
+        {
+            const float *fz_ = fb + 2 * FX + 2 * FY + st;
+            const f2 Pz = *(const f2 *)fz_, Mz = *(const f2 *)(fz_ + PSLOT);
+#pragma unroll
+            for (int k = 1; k <= R; k++) {
+                aP[R - k] = fma2s(cf.wz[k], Pz, aP[R - k]);
+                aM[R - k] = fma2s(cf.wz[k], Mz, aM[R - k]);
+                if (k == R) {
+                    aP[R - 1 + k] = mul2s(-cf.wz[k], Pz);
+                    aM[R - 1 + k] = mul2s(-cf.wz[k], Mz);
+                } else {
+                    aP[R - 1 + k] = fma2s(-cf.wz[k], Pz, aP[R - 1 + k]);
+                    aM[R - 1 + k] = fma2s(-cf.wz[k], Mz, aM[R - 1 + k]);
+                }
+            }
+        }
+        if (out) {
+            const float *fz_ = fb + 2 * FX + 2 * FY + st;
+            const f2 uc1 = *(const f2 *)(fz_ + 2 * PSLOT), uc2 = *(const f2 *)(fz_ + 3 * PSLOT);
+            const f2 H1 = aP[0], H2 = aM[0];
+            mbar_wait(&fullP[pslot], (uint32_t)ppar);
+            const float *pt = ringP + pslot * 3 * PSLOT + st;
+            const f2 up1 = *(const f2 *)pt, up2 = *(const f2 *)(pt + PSLOT), m2 = *(const f2 *)(pt + 2 * PSLOT);
+            __syncwarp();
+            mbar_arrive_if(&emptyP[pslot], lane == 0);
+            if (++pslot == NP) { pslot = 0; ppar ^= 1; }
+            const f2 sd = mul2s(cf.dt, add2(dxy, pk1(dz_s)));
+            const f2 den = fma2s(a.irho_c, m2, sd);
+            const f2 r = pk(__frcp_rn(den.x), __frcp_rn(den.y));
+            const f2 nsd = mul2s(-1.f, sd);
+            f2 dl[2];
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                const f2 uc = f ? uc2 : uc1, up = f ? up2 : up1, H = f ? H2 : H1;
+                const f2 d1 = sub2(uc, up);
+                const f2 t = fma2(nsd, d1, mul2s(cf.dt2, H));
+                dl[f] = mul2(t, r);
+                const f2 un = fma2(t, r, add2(uc, d1));
+                if (act) {
+                    float *o = (f ? a.up2 : a.up1) + gout;
+                    if (xfull) *(f2 *)o = un;
+                    else o[0] = un.x;
+                }
+            }
+            if (f_reg && fin) {
+                if (fvec) {
+                    if (f_snap) {
+                        __stcs((float2 *)(fz.snap[0] + ri), uc1);
+                        __stcs((float2 *)(fz.snap[1] + ri), uc2);
+                    }
+                    if (f_grad) {
+                        const f2 ic = fma2(us2, dl[1], mul2(us1, dl[0]));
+                        *(f2 *)(fz.grad + ri) = fma2s(-gc, ic, G2);
+                    }
+                } else {
+                    const float u1v[2] = {uc1.x, uc1.y}, u2v[2] = {uc2.x, uc2.y};
+                    const float d1v[2] = {dl[0].x, dl[0].y}, d2v[2] = {dl[1].x, dl[1].y};
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        if (ox + e < fz.reg.lo[0] || ox + e >= fz.reg.hi[0] || ox + e >= g.n[0]) continue;
+                        if (f_snap) { fz.snap[0][ri + e] = u1v[e]; fz.snap[1][ri + e] = u2v[e]; }
+                        if (f_grad) {
+                            const float ic = __fmaf_rn(fz.usnap[1][ri + e], d2v[e], __fmul_rn(fz.usnap[0][ri + e], d1v[e]));
+                            fz.grad[ri + e] = __fmaf_rn(-gc, ic, fz.grad[ri + e]);
+                        }
+                    }
+                }
+            }
+            gout += g.sz;
+            if (f_reg) ri += rstride;
+        }
+        if (j + 2 < total) named_bar_arrive(3 + (j & 1), NSYNC);
+#pragma unroll
+        for (int k = 0; k < NQ - 1; k++) { aP[k] = aP[k + 1]; aM[k] = aM[k + 1]; }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 bool tti3d_supported(const judi_model *M)
 {
@@ -648,6 +1034,20 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured[var] = true;
     }
+    // option tti_fused = 8: the half-width-thread kernel (R = 4; plain / save / imaging condition)
+    constexpr bool HOK = R == 4 && (FUSE == 0 || FUSE == TF_SNAP || FUSE == TF_GRAD);
+    bool half = false;
+    if constexpr (HOK) {
+        if (ctx->opt_tti_fused == 8) {
+            half = true;
+            kern = tti3d_h<FUSE>;
+            static bool hconf = false;
+            if (!hconf) {
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+                hconf = true;
+            }
+        }
+    }
     Wavefield *W = lin ? s.lin : s.scratch;
     TtiMaps tm;
     tm.U1 = W->tmap_halo[0][W->cur]; tm.U2 = W->tmap_halo[1][W->cur];
@@ -671,7 +1071,7 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
     a.zchunk = (M->N[2] + nzc - 1) / nzc;
     nzc = (M->N[2] + a.zchunk - 1) / a.zchunk;
     const dim3 grid(ntx, nty, nzc);
-    kern<<<grid, C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
+    kern<<<grid, half ? ttih::NTHREADS : C::NTHREADS, C::SMEM, ctx->stream>>>(tm, a);
     launch_count(ctx, "tti3d_tma");
 }
 
