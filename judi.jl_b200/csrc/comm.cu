@@ -36,10 +36,17 @@ struct NcclApi {
     fn_GetVersion GetVersion = nullptr;
 };
 
+// loaded once per process (thread-safe: function-local static initialised by a lambda)
+NcclApi load_nccl();
 NcclApi &nccl()
 {
-    static NcclApi api;
-    if (api.h) return api;
+    static NcclApi api = load_nccl();
+    return api;
+}
+
+NcclApi load_nccl()
+{
+    NcclApi api;
     const char *env = getenv("JUDI_NCCL_LIB");
     const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
     std::string tried;
