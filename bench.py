@@ -439,11 +439,13 @@ def run_b200(args):
             for _ in range(min(args.warmup, 2)):
                 step_host()
             barrier()
+            clocks_e2e = ClockSampler(local)
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 fh, gh = step_host()
             barrier()
             wall = time.perf_counter() - t0
+            clk_e2e = clocks_e2e.stop()
             t = torch.tensor([wall], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -463,7 +465,8 @@ def run_b200(args):
                                   "checkpointing) -> host gradient on the physical grid"}.get(
                        wl, "fwi_objective(Model(host arrays), host wavelet/data) -> host gradient on the "
                            "physical grid") + "; bytes summed over ranks",
-                   "result_l2": float(np.linalg.norm(gh.ravel(order="K").astype(np.float64)))}
+                   "result_l2": float(np.linalg.norm(gh.ravel(order="K").astype(np.float64))),
+                   "clocks": clk_e2e}
             if fval is not None:
                 e2e["f_matches_device_path"] = bool(abs(float(fh) - fval) <= 1e-3 * abs(fval))
 
