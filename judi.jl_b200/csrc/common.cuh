@@ -195,9 +195,11 @@ struct DevArr {
     }
     void reset() { if (p && ctx) ctx->free(p); p = nullptr; n = 0; }
     void upload(const std::vector<T> &h) {
+        // h is pageable host memory (a std::vector, possibly a temporary): cudaMemcpyAsync copies it
+        // to the driver's staging buffer before it returns, so no stream synchronisation is needed
+        // (CUDA runtime, "API synchronization behavior": pageable host -> device)
         CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice,
                                    ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h may be a temporary
     }
     ~DevArr() { reset(); }
 };
