@@ -123,7 +123,7 @@ __device__ float lap_weighted2d(const Grid &g, const Coefs &cf, const float *__r
 // and runs 16 C2 shots in lockstep at 60 Gpt/s, close to its own issue limit; the vector body
 // amortises that arithmetic over 4 points.  Plain / save / imaging condition "as" / illumination
 // of the constant-density kernel without free surface, space-time sources or Born (host: p2_vec_ok).
-template <int R, bool XIC, bool VEC = false>
+template <int R, bool XIC, int VEC = 0>
 __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, const int nb)
 {
     cg::grid_group grid = cg::this_grid();
@@ -325,16 +325,17 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
     }
 }
 
-template <int R, bool XIC, bool VEC = false>
-__global__ void __launch_bounds__(256, (XIC || VEC) ? 2 : 4) acoustic2d_persist(P2Args a)
+// VEC: 0 = one point per thread; n > 0 = four points per thread, compiled for n CTAs per SM
+template <int R, bool XIC, int VEC = 0>
+__global__ void __launch_bounds__(256, VEC ? VEC : (XIC ? 2 : 4)) acoustic2d_persist(P2Args a)
 {
     acoustic2d_body<R, XIC, VEC>(a, blockIdx.x, gridDim.x);
 }
 
 // Several shots of the same model and time axis in lockstep: CTA b works on shot b / per_shot.
 // One grid barrier per time step serves all of them (judi_fg_multishot on small 2-D grids).
-template <int R, bool XIC, bool VEC = false>
-__global__ void __launch_bounds__(256, (XIC || VEC) ? 2 : 4) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
+template <int R, bool XIC, int VEC = 0>
+__global__ void __launch_bounds__(256, VEC ? VEC : (XIC ? 2 : 4)) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
 {
     // the shot's arguments go to shared memory once: read through the global pointer, every stencil
     // coefficient would be a load from L1/L2 instead of a constant-bank operand
@@ -907,7 +908,7 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
     p2_fill(M, W, WL, t0, t1, dir, S_in, in, S_out, out, out_bg, fz, a);
     auto launch = [&](auto rtag, auto xtag, auto vtag) {
         constexpr int R = decltype(rtag)::value;
-        constexpr bool VEC = decltype(vtag)::value;
+        constexpr int VEC = decltype(vtag)::value;
         auto kern = acoustic2d_persist<R, decltype(xtag)::value, VEC>;
         static int max_blocks = 0;
         if (!max_blocks) {
@@ -930,9 +931,10 @@ void persist2d_run(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, int
         default: launch(std::integral_constant<int, 8>(), xtag, vtag); break;
         }
     };
-    if (a.ic != JUDI_IC_AS && (a.grad || WL)) launch_r(std::true_type(), std::false_type());
-    else if (ctx->opt_persist_vec == 2 && p2_vec_ok(a)) launch_r(std::false_type(), std::true_type());
-    else launch_r(std::false_type(), std::false_type());
+    typedef std::integral_constant<int, 0> V0;
+    if (a.ic != JUDI_IC_AS && (a.grad || WL)) launch_r(std::true_type(), V0());
+    else if (ctx->opt_persist_vec == 2 && p2_vec_ok(a)) launch_r(std::false_type(), std::integral_constant<int, 2>());
+    else launch_r(std::false_type(), V0());
     if (nsteps & 1) { W.swap(); if (WL) WL->swap(); }
     if (ctx->timing) {
         ctx->stencil_launches += 1;
@@ -1024,7 +1026,7 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     dargs.upload(args);
     auto launch = [&](auto rtag, auto xtag, auto vtag) {
         constexpr int R = decltype(rtag)::value;
-        constexpr bool VEC = decltype(vtag)::value;
+        constexpr int VEC = decltype(vtag)::value;
         auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value, VEC>;
         static int max_blocks = 0;
         if (!max_blocks) {
@@ -1053,9 +1055,14 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
     };
     bool vec = ctx->opt_persist_vec != 0;
     for (int s = 0; s < n; s++) vec = vec && p2_vec_ok(args[(size_t)s]);
-    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type(), std::false_type());
-    else if (vec) launch_r(std::false_type(), std::true_type());
-    else launch_r(std::false_type(), std::false_type());
+    // option persist_vec: 1 / 2 = vector body at 3 CTAs per SM (80 registers), 3 = at 2 CTAs per SM (118),
+    // 4 = at 4 CTAs per SM (64 registers, 84 bytes of spills)
+    typedef std::integral_constant<int, 0> V0;
+    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type(), V0());
+    else if (vec && ctx->opt_persist_vec == 3) launch_r(std::false_type(), std::integral_constant<int, 2>());
+    else if (vec && ctx->opt_persist_vec == 4) launch_r(std::false_type(), std::integral_constant<int, 4>());
+    else if (vec) launch_r(std::false_type(), std::integral_constant<int, 3>());
+    else launch_r(std::false_type(), V0());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dargs is freed on return
     if (nsteps & 1)
         for (int s = 0; s < n; s++) {
