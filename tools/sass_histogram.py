@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "judi.jl_b200", "libjudi_b200.so")
 KEY = ("UTMALDG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "LDS.128",
-       "LDS", "STS.128", "STS", "LDG.E.128", "LDG", "STG.E.128", "STG", "BAR", "MOV", "BRA",
+       "LDS", "STS.128", "STS", "LDG.E.128", "LDG", "LD.E.128", "STG.E.128", "STG", "ST.E.128", "BAR", "MOV", "BRA",
        "IMAD", "MUFU.RCP")
 
 
