@@ -270,6 +270,42 @@ def fg_multishot(model, shots, grad_out, f_out, is_residual=False, checkpointing
     return f_out, grad_out
 
 
+def fg_multishot_reduced(model, shots, sum_padding=False, is_residual=False, checkpointing=False,
+                         n_checkpoints=None, t_sub=1, ic="as", born_fwd=False, nlind=False,
+                         snapshot_region="padded", f0=None):
+    """multi_src_fg! + reduce! + remove_padding of one worker in ONE library call
+    (`judi_fg_multishot_reduced`; propagation.jl:93-107, distributed.jl:60-95, misfit_fg.jl:77):
+    this rank's `shots` (possibly none) are summed in HBM, cropped on the device and all-reduced
+    over the context's communicator.  Host arrays in, (f, physical-grid gradient) of ALL ranks' shots
+    out -- the call `julia/B200Backend.jl:b200_fg_multishot_reduced` makes."""
+    model.set_f0(f0)
+    o = L.JudiJopts()
+    o.is_residual = int(bool(is_residual))
+    o.checkpointing = int(bool(checkpointing))
+    o.n_checkpoints = int(n_checkpoints) if n_checkpoints else 0
+    o.t_sub = int(t_sub)
+    o.ic = L.IC_CODES[ic]
+    o.born_fwd = int(bool(born_fwd))
+    o.nlind = int(bool(nlind))
+    o.snapshot_region = L.SNAP_PHYSICAL if snapshot_region == "physical" else L.SNAP_PADDED
+    arr = (L.JudiShot * max(len(shots), 1))()
+    keep = []
+    for k, (src_coords, wavelet, rec_coords, recin) in enumerate(shots):
+        sc, rc = _coords(src_coords, model.dim), _coords(rec_coords, model.dim)
+        q, nt, nsrc = _traces(wavelet)
+        d, ntd, nrec = _traces(recin)
+        assert ntd == nt and nrec == rc.shape[0], "data shape does not match geometry / wavelet"
+        keep += [sc, rc, q, d]
+        arr[k].nsrc, arr[k].src_coords, arr[k].wavelet = nsrc, sc.ctypes.data, q.ctypes.data
+        arr[k].nt, arr[k].nrec, arr[k].rec_coords, arr[k].recin = nt, nrec, rc.ctypes.data, d.ctypes.data
+    g = np.zeros(model.shape, dtype=np.float32, order="F")
+    f = ctypes.c_float(0)
+    L.check(L.lib().judi_fg_multishot_reduced(model.h, len(shots), arr, ctypes.byref(o), None, None,
+                                              int(bool(sum_padding)), ctypes.addressof(f),
+                                              g.ctypes.data, 0))
+    return np.float32(f.value), g
+
+
 def _weights(model, w):
     """Extended-source weights on the padded grid (python_interface.jl:129 zero-pads them)."""
     if is_device_tensor(w):

@@ -302,3 +302,35 @@ def test_single_rank_communicator_and_trim():
     fo, go, _, _ = O.J_adjoint(om, src, q, rec, (0.5 * d).astype(np.float32), return_obj=True)
     assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
     assert rel_l2(g, O.remove_padding(go, om.padsizes)) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_fg_multishot_reduced_single_rank(ndim):
+    """judi_fg_multishot_reduced (multi_src_fg! + reduce! + remove_padding in one call, the entry
+    point of julia/B200Backend.jl): host arrays in, physical-grid gradient out; also with no shot
+    at all on this rank (it still takes part in the reduction and returns zeros)."""
+    import judi_jl_b200 as J
+    args = model_args("iso", ndim, 8, with_dm=False)
+    gm, om = J.Model(**args), O.Model(precision="f32", **args)
+    J.objectives.init_comm(gm.ctx)
+    src0, rec = geometry(args)
+    dt = float(om.critical_dt)
+    q = O.ricker_wavelet(99 * dt, dt, 0.02)[:100]
+    shots, fs, gs = [], 0.0, 0.0
+    for i in range(3):
+        src = src0.copy()
+        src[0, 0] += 30.0 * (i - 1)
+        d, _ = O.forward_rec(om, src, q, rec)
+        dobs = (0.9 * d).astype(np.float32)
+        shots.append((src, q, rec, dobs))
+        f, g, _, _ = O.J_adjoint(om, src, q, rec, dobs, return_obj=True)
+        fs += float(f)
+        gs = gs + g
+    for fold in (False, True):
+        f, g = J.interface.fg_multishot_reduced(gm, shots, sum_padding=fold)
+        assert g.shape == args["shape"]
+        assert abs(float(f) - fs) <= 1e-4 * abs(fs)
+        assert rel_l2(g, O.remove_padding(gs, om.padsizes, true_adjoint=fold)) < 1e-3
+    f0, g0 = J.interface.fg_multishot_reduced(gm, [])
+    assert float(f0) == 0.0 and not g0.any()
