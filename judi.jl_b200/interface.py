@@ -115,12 +115,36 @@ def forward_no_rec(model, src_coords, wavelet, f0=None, illum=False, fw=True):
 
 
 # Linearized modeling d/dm (Pr*F*Ps'*q)
+def _reverse_time(a):
+    """(nt, ntrace) host traces with the time axis reversed (F-ordered copy)."""
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a[::-1])
+
+
+def _require_time_reversible(model, traces, what):
+    if getattr(model, "is_viscoacoustic", False):
+        raise NotImplementedError("%s with fw=False on a visco-acoustic model (its adjoint scheme is "
+                                  "not the time mirror of the forward one)" % what)
+    if is_device_tensor(traces):
+        raise NotImplementedError("%s with fw=False takes host traces" % what)
+
+
 @_with_f0
 def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=None, illum=False, fw=True,
              rec_out=None, illum_out=None):
-    """Linearized (Born) modeling of a point source for the model's dm (interface.py:208-241)."""
+    """Linearized (Born) modeling of a point source for the model's dm (interface.py:208-241).
+
+    fw=False (the Jacobian of the adjoint propagator F', `born(..., fw=False)`): for every
+    propagator but the visco-acoustic one the adjoint scheme is the forward scheme run in reversed
+    time (`u.dt.T` is the time mirror of `u.dt`, kernels.py:61-69; checked bitwise on the oracle), so
+    the call is the forward Born modelling of the time-reversed wavelet, reversed."""
     if not fw:
-        raise NotImplementedError("born_rec with fw=False")
+        _require_time_reversible(model, wavelet, "born_rec")
+        rec, I = born_rec(model, src_coords, _reverse_time(wavelet), rec_coords, ic=ic, f0=f0,
+                          illum=illum, fw=True, illum_out=illum_out)
+        return _reverse_time(rec), I
     dev = is_device_tensor(wavelet)
     sc = _coords(src_coords, model.dim)
     rc = _coords(rec_coords, model.dim)
@@ -155,7 +179,26 @@ def J_adjoint(model, src_coords, wavelet, rec_coords, recin, is_residual=False,
     runs `grad_out`, `f_out`, `illum_out=(Iu, Iv)`, `accumulate`.
     """
     if not fw:
-        raise NotImplementedError("J_adjoint with fw=False")
+        # Jacobian of the adjoint propagator (`gradient(..., fw=False)`): the time mirror of the
+        # forward problem (see born_rec).  Exact when the snapshots are taken on every step (or on a
+        # pattern that is symmetric under time reversal); the on-the-fly DFT keeps its own path.
+        _require_time_reversible(model, wavelet, "J_adjoint")
+        nt_ = np.asarray(wavelet).shape[0]
+        if freq_list is not None or not (t_sub == 1 or checkpointing or (nt_ - 1) % t_sub == 0):
+            raise NotImplementedError("J_adjoint with fw=False needs t_sub = 1 (or checkpointing, or "
+                                      "(nt - 1) % t_sub == 0) and no frequency list")
+        if misfit is not None:
+            user_misfit = misfit
+
+            def misfit(dsyn, dobs):     # the callback sees the traces in their own time order
+                fv, r = user_misfit(dsyn[::-1], dobs[::-1])
+                return fv, np.asarray(r)[::-1]
+        return J_adjoint(model, src_coords, _reverse_time(wavelet), rec_coords, _reverse_time(recin),
+                         is_residual=is_residual, checkpointing=checkpointing,
+                         n_checkpoints=n_checkpoints, t_sub=t_sub, return_obj=return_obj, ic=ic,
+                         illum=illum, ws=ws, f0=f0, born_fwd=born_fwd, nlind=nlind, misfit=misfit,
+                         fw=True, snapshot_region=snapshot_region, grad_out=grad_out, f_out=f_out,
+                         illum_out=illum_out, accumulate=accumulate)
     dev = is_device_tensor(wavelet)
     sc = _coords(src_coords, model.dim) if src_coords is not None else None
     rc = _coords(rec_coords, model.dim)

@@ -106,15 +106,19 @@ function b200_interface(h, srcGeometry::Geometry, srcData::Array, recGeometry::G
 end
 
 # d_lin = J*dm         (python_interface.jl:83-99 -> interface.py:208)
-function b200_born(h, srcGeometry, srcData, recGeometry, options::JUDIOptions, illum::Bool, n)
+# fw=false (the Jacobian of F'): the adjoint scheme is the forward scheme in reversed time for every
+# propagator but the visco-acoustic one, so J(F')*dm = reverse(J(F; reverse(q))*dm) -- reverse qIn
+# before the call and the record after it (judi.jl_b200/interface.py:born_rec does the same).
+function b200_born(h, srcGeometry, srcData, recGeometry, options::JUDIOptions, illum::Bool, n; fw::Bool=true)
     dtComp = critical_dt(h)
     qIn = _maybe_pad_t0(time_resample(srcData, srcGeometry, dtComp), srcGeometry, recGeometry, dtComp)
+    fw || (qIn = reverse(qIn, dims=1))
     sc = Float32.(setup_grid(srcGeometry, n)); rc = Float32.(setup_grid(recGeometry, n))
     nt = size(qIn, 1); rec = zeros(Float32, nt, size(rc, 1))
     check(ccall((:judi_born_rec, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cint, Ptr{Cfloat}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Cint),
                 h, size(sc, 1), sc, qIn, nt, size(rc, 1), rc, IC[options.IC], rec, C_NULL, 0))
-    return rec
+    return fw ? rec : reverse(rec, dims=1)
 end
 
 # (f, g) of one shot   (misfit_fg.jl:69-73 / python_interface.jl:102-121 -> interface.py:279)

@@ -239,11 +239,53 @@ def test_time_modeling_direction_comes_from_fw_alone():
     qf = J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, rg, y, sg,
                                        None, None, "adjoint", opt, fw=True)
     assert rel_l2(qf, qao[:qf.shape[0]]) > 0.5       # the forward propagator is something else
-    # the Jacobian of F' is not built: it must raise, not run J of F
+    # the Jacobian of F' goes through (time mirror of the forward problem), it is NOT J of F
+    dm = np.zeros(args["shape"], np.float32)
+    dm[20:40, 15:35] = 0.02
+    ql = O.ricker_wavelet(T, dtc, 0.02)
+    dla = J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, sg, ql, rg,
+                                        None, dm, "born", opt, fw=False)
+    dlf = J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, sg, ql, rg,
+                                        None, dm, "born", opt, fw=True)
+    assert np.linalg.norm(dla) > 0 and rel_l2(dla, dlf) > 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3)])
+def test_jacobian_of_the_adjoint_propagator(kind, ndim):
+    """born_rec / J_adjoint with fw=False (`born(..., fw=False)`, `gradient(..., fw=False)`,
+    propagators.py:98-230): J(F') dm against a finite difference of the tested F' path, and the dot
+    test of the pair."""
+    import judi_jl_b200 as J
+    args = model_args(kind, ndim, 8)
+    # one user time step below the critical one of all three models (models.py:476-481: the smaller wins)
+    args["dt"] = np.float32(0.9 * float(J.Model(**args).critical_dt))
+    gm = J.Model(**args)
+    src, rec = geometry(args)
+    dt = float(gm.critical_dt)
+    assert dt <= float(args["dt"]) + 1e-6
+    nt = 160
+    # the adjoint propagator runs from the end of the time axis: a wavelet that fires late
+    q = O.ricker_wavelet((nt - 1) * dt, dt, 0.02)[:nt][::-1].copy()
+    dm = args["dm"]
+    dl, _ = J.born_rec(gm, src, q, rec, fw=False)
+    eps = 1e-2
+    a0 = dict(args)
+    a0.pop("dm")
+    mp, mn = (J.Model(**dict(a0, m=(args["m"] + s_ * eps * dm).astype(np.float32))) for s_ in (1, -1))
+    assert float(mp.critical_dt) == float(mn.critical_dt) == float(gm.critical_dt)
+    dp, _ = J.forward_rec(mp, src, q, rec, fw=False)
+    dmn, _ = J.forward_rec(mn, src, q, rec, fw=False)
+    fd = (dp.astype(np.float64) - dmn) / (2 * eps)
+    assert np.linalg.norm(fd) > 0
+    assert rel_l2(dl, fd) < 2e-2                      # O(eps^2) + fp32 cancellation of the difference
+    y = np.random.default_rng(3).standard_normal(dl.shape).astype(np.float32)
+    g, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True, fw=False)
+    dmp = np.pad(dm, gm.padsizes, mode="edge").astype(np.float64)
+    c, e = dt * np.vdot(dl.astype(np.float64), y), np.vdot(g.astype(np.float64), dmp)
+    assert abs((c - e) / (c + e)) < 1e-4
     with pytest.raises(NotImplementedError):
-        J.time_modeling.time_modeling(args["origin"], args["spacing"], args["shape"], params, sg,
-                                      O.ricker_wavelet(T, dtc, 0.02), rg, None,
-                                      np.ones(args["shape"], np.float32), "born", opt, fw=False)
+        J.J_adjoint(gm, src, q, rec, y, is_residual=True, fw=False, t_sub=7)
 
 
 @pytest.mark.gpu
