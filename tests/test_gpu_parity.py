@@ -4,7 +4,7 @@ the CPU oracle on the same seeded inputs.
 Tolerances are the north-star ones (BASELINE.json): shot records <= 1e-4 relative L2, gradients
 <= 1e-3 relative L2, source/receiver indexing bit-exact, adjoint dot tests <= 1e-5.
 
-Dot tests come in two recipes (tools/dot_report.py prints both for every case next to the fp32 and
+Dot tests come in two recipes (tests/tools/dot_report.py prints both for every case next to the fp32 and
 fp64 oracle; profiles/r02_dot_report.log):
   * the reference's own (test/test_adjoint.jl:67-76, src/pysource/adjoint_test_F.py:75-88):
     y = F q, q_rand = (.5 + rand) .* q.  Measured on the B200: F <= 2.8e-7, J <= 1.3e-6 over all 20

@@ -1,6 +1,6 @@
 """First-contact GPU check: runs every path against the oracle and prints a table (no asserts)."""
 import sys, os, time, json, traceback
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import judi_jl_b200 as J
 from oracle import oracle as O
