@@ -138,7 +138,7 @@ def born_rec(model, src_coords, wavelet, rec_coords, ic="as", f0=None, illum=Fal
 
     fw=False (the Jacobian of the adjoint propagator F', `born(..., fw=False)`): for every
     propagator but the visco-acoustic one the adjoint scheme is the forward scheme run in reversed
-    time (`u.dt.T` is the time mirror of `u.dt`, kernels.py:61-69; checked bitwise on the oracle), so
+    time (`u.dt.T` is the time mirror of `u.dt`, kernels.py:61-69; checked bitwise in tests/), so
     the call is the forward Born modelling of the time-reversed wavelet, reversed."""
     if not fw:
         _require_time_reversible(model, wavelet, "born_rec")
