@@ -194,3 +194,25 @@ def test_homogeneous_arrival_time():
         # 2-D far field: peak of |trace| near r/v + 1/f0 (Ricker delay), up to the 2-D tail
         t_peak = np.argmax(np.abs(d[:, j])) * dt
         assert abs(t_peak - (r / v + 1 / f0)) < 12.0, (t_peak, r / v + 1 / f0)
+
+
+@pytest.mark.parametrize("kind", ["iso", "rho", "tti"])
+def test_adjoint_scheme_is_the_forward_scheme_in_reversed_time(kind):
+    """kernels.py:61-69: the adjoint update uses `u.dt.T`, the time mirror of `u.dt`, and runs the
+    loop backwards -- so F' y = reverse(F reverse(y)) bit for bit for every propagator but the
+    visco-acoustic one.  The library serves `born_rec` / `J_adjoint` with fw=False through this
+    identity (judi.jl_b200/interface.py)."""
+    from conftest import model_args, geometry
+    args = model_args(kind, 2, 8)
+    om = O.Model(precision="f64", **args)
+    src, rec = geometry(args)
+    y = np.random.default_rng(0).standard_normal((120, rec.shape[0])).astype(np.float32)
+    a, _ = O.forward_rec(om, rec, y, src, fw=False)
+    b, _ = O.forward_rec(om, rec, y[::-1].copy(), src, fw=True)
+    assert np.array_equal(a, b[::-1])
+    # ... and NOT for the visco-acoustic scheme (its adjoint is a different discretisation)
+    vargs = model_args("visco", 2, 8)
+    vm = O.Model(precision="f64", **vargs)
+    av, _ = O.forward_rec(vm, rec, y, src, fw=False)
+    bv, _ = O.forward_rec(vm, rec, y[::-1].copy(), src, fw=True)
+    assert not np.array_equal(av, bv[::-1])
