@@ -114,11 +114,60 @@ def time_resample_to_dt(data, geometry, dt_new, context=None):
     return time_resample(data, geometry.taxis, (t0, np.float32(dt_new), n_new), context=context)
 
 
-def time_resample_to_geometry(data, dt_in, geometry, context=None):
-    """time_resample(data, dt_in, G_out) (time_utilities.jl:66-69)."""
+def time_resample_to_geometry(data, dt_in, geometry, geometry_in=None, context=None):
+    """time_resample(data, dt_in, G_out) (time_utilities.jl:66-69) and, with the source geometry,
+    time_resample(data, dt_in, G_in, G_out) (:71-79, what post_process_src calls): the modelled
+    traces start at t0 = min(t0 of the source, t0 of the receivers)."""
     nt_in = data.shape[1] if is_device_tensor(data) else np.asarray(data).shape[0]
-    return time_resample(data, (np.float32(0), np.float32(dt_in), nt_in), geometry.taxis,
-                         context=context)
+    t0 = np.float32(0) if geometry_in is None else np.float32(min(geometry_in.t0, geometry.t0))
+    return time_resample(data, (t0, np.float32(dt_in), nt_in), geometry.taxis, context=context)
+
+
+# ---- _maybe_pad_t0 ---------------------------------------------------------------------------
+def _jdiv(a, b):
+    """Julia's div(a, b) on Float32 (rounds towards zero)."""
+    return int(np.trunc(np.float32(a) / np.float32(b)))
+
+
+def maybe_pad_t0(q, q_geom, d, d_geom, dt):
+    """_maybe_pad_t0 (time_utilities.jl:92-139): zero-pad the source and the data so that both cover
+    min(t0) .. max(t) when their geometries start or end at different times (SEG-Y data with a
+    recording delay).  `d` = None stands for "no data yet" (forward modelling, :153-154): only the
+    padded source is returned."""
+    only_q = d is None
+    if only_q:
+        nd = int(np.floor(np.float32(d_geom.t - d_geom.t0) / np.float32(dt))) + 1
+        d = np.zeros((nd, 1), dtype=np.float32)
+    q = np.asarray(q, dtype=np.float32)
+    d = np.asarray(d, dtype=np.float32)
+    z = lambda n, like: np.zeros((max(n, 0), like.shape[1]), dtype=np.float32)
+    dt0 = np.float32(d_geom.t0 - q_geom.t0)
+    Dt = np.float32(d_geom.t - q_geom.t)
+    dsize = q.shape[0] - d.shape[0]
+    if dsize == 0 and dt0 == 0 and Dt == 0:
+        pass
+    elif dsize == 0 and dt0 != 0 and Dt != 0:
+        assert np.sign(dt0) == np.sign(Dt), "source and data are shifted in opposite directions"
+        pad = _jdiv(abs(dt0), dt)
+        if dt0 > 0:
+            d, q = np.vstack([z(pad, d), d]), np.vstack([q, z(pad, q)])
+        else:
+            d, q = np.vstack([d, z(pad, d)]), np.vstack([z(pad, q), q])
+    elif dsize != 0:
+        ts, te = min(q_geom.t0, d_geom.t0), max(q_geom.t, d_geom.t)
+        d = np.vstack([z(_jdiv(d_geom.t0 - ts, dt), d), d, z(_jdiv(te - d_geom.t, dt), d)])
+        q = np.vstack([z(_jdiv(q_geom.t0 - ts, dt), q), q, z(_jdiv(te - q_geom.t, dt), q)])
+        left = q.shape[0] - d.shape[0]
+        if left > 0:
+            d = np.vstack([d, z(left, d)])
+        elif left < 0:
+            q = np.vstack([q, z(-left, q)])
+    else:
+        raise ValueError("data and source have different t0 %s and t %s and are not compatible in size "
+                         "for padding: %s" % ((d_geom.t0, q_geom.t0), (d_geom.t, q_geom.t),
+                                              (q.shape[0], d.shape[0])))
+    q = np.asfortranarray(q)
+    return q if only_q else (q, np.asfortranarray(d))
 
 
 # ---- remove_padding --------------------------------------------------------------------------
@@ -201,18 +250,20 @@ def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, 
     dt_comp = np.float32(model.critical_dt)
     q_in = time_resample_to_dt(src_data, src_geom, dt_comp, context=model.ctx)
     sc, rc = src_geom.coords(ndim), rec_geom.coords(ndim)
+    if op != "adjoint_born":
+        q_in = maybe_pad_t0(q_in, src_geom, None, rec_geom, dt_comp)     # python_interface.jl:34, 88
     if op in ("forward", "adjoint") and rec_data is None:
         # `op` only selects the post-processing; the direction is `fw` alone, as `_prop_fw(F)`
         # hands it to devito_interface (propagation.jl:9,52-54; python_interface.jl:42)
         rec, _ = interface.forward_rec(model, sc, q_in, rc, f0=o.f0, illum=illum, fw=fw)
-        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, geometry_in=src_geom, context=model.ctx)
     if op == "born":
         rec, _ = interface.born_rec(model, sc, q_in, rc, ic=o.IC, f0=o.f0, illum=illum, fw=fw)
-        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, geometry_in=src_geom, context=model.ctx)
     if op == "adjoint_born":
         d_in = time_resample_to_dt(rec_data, rec_geom, dt_comp, context=model.ctx)
-        nt = min(q_in.shape[0], d_in.shape[0])
-        g, _, _ = interface.J_adjoint(model, sc, q_in[:nt], rc, d_in[:nt], is_residual=True,
+        q_in, d_in = maybe_pad_t0(q_in, src_geom, d_in, rec_geom, dt_comp)   # python_interface.jl:109
+        g, _, _ = interface.J_adjoint(model, sc, q_in, rc, d_in, is_residual=True,
                                       t_sub=o.subsampling_factor,
                                       checkpointing=o.optimal_checkpointing, ic=o.IC, f0=o.f0,
                                       freq_list=o.frequencies or None,

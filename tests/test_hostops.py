@@ -376,3 +376,22 @@ def test_fg_multishot_reduced_single_rank(ndim):
         assert rel_l2(g, O.remove_padding(gs, om.padsizes, true_adjoint=fold)) < 1e-3
     f0, g0 = J.interface.fg_multishot_reduced(gm, [])
     assert float(f0) == 0.0 and not g0.any()
+
+
+def test_maybe_pad_t0_cases():
+    """_maybe_pad_t0 (time_utilities.jl:92-139): equal axes untouched, a pure shift pads both by
+    the shift, different lengths pad to min(t0) .. max(t)."""
+    import judi_jl_b200 as J
+    TM = J.time_modeling
+    G = lambda t0, t: TM.Geometry([0.], None, [0.], dt=2., t=t, t0=t0)
+    q, d = np.ones((51, 1), np.float32), np.ones((51, 3), np.float32)
+    a, b = TM.maybe_pad_t0(q, G(0, 100), d, G(0, 100), 2.)
+    assert a.shape == (51, 1) and b.shape == (51, 3)
+    a, b = TM.maybe_pad_t0(q, G(0, 100), d, G(20, 120), 2.)          # data recorded 20 ms late
+    assert a.shape == (61, 1) and b.shape == (61, 3) and not b[:10].any() and not a[-10:].any()
+    a, b = TM.maybe_pad_t0(q, G(20, 120), d, G(0, 100), 2.)          # source fires 20 ms late
+    assert not a[:10].any() and not b[-10:].any() and a[10:].all() and b[:51].all()
+    a, b = TM.maybe_pad_t0(q, G(0, 100), np.ones((31, 3), np.float32), G(20, 80), 2.)
+    assert a.shape == (51, 1) and b.shape == (51, 3)
+    assert not b[:10].any() and not b[41:].any() and b[10:41].all()
+    assert TM.maybe_pad_t0(q, G(0, 100), None, G(0, 140), 2.).shape == (71, 1)
