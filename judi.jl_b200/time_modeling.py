@@ -280,3 +280,46 @@ def time_modeling(origin, spacing, shape, params, src_geom, src_data, rec_geom, 
             return full
         return g
     raise ValueError("unknown operator %r" % (op,))
+
+
+def multi_src_fg(origin, spacing, shape, params, src_geom, src_data, rec_geom, rec_data, dm=None,
+                 options=None, nlind=False, lin=False, misfit=None, illum=False, context=None):
+    """_multi_src_fg (misfit_fg.jl:8-91) for ONE source experiment given on its own geometries'
+    time axes: limit the model, build it, resample source and data to the computational time step,
+    pad for different recording delays, `J_adjoint(..., return_obj=True, is_residual=False)`, crop
+    (or fold) the gradient.  Returns (f, gradient on the full physical grid[, Iu, Iv]) -- the
+    per-shot work of `fwi_objective` (`lin=False`) and `lsrtm_objective` (`lin=True`, with `dm`)."""
+    o = options or Options()
+    ndim = len(shape)
+    full_shape, full_origin = tuple(shape), tuple(origin)
+    if o.limit_m:
+        origin, shape, params, dm = limit_model_to_receiver_area(
+            src_geom, rec_geom, origin, spacing, shape, o.buffer_size, params, pert=dm)
+    kw = dict(params)
+    if dm is not None:
+        kw["dm"] = np.asarray(dm, dtype=np.float32).reshape(shape)
+    model = Model(origin, spacing, shape, space_order=o.space_order, nbl=o.nbl,
+                  fs=o.free_surface, dt=o.dt_comp, context=context, **kw)
+    dt_comp = np.float32(model.critical_dt)
+    q_in = time_resample_to_dt(src_data, src_geom, dt_comp, context=model.ctx)
+    d_in = time_resample_to_dt(rec_data, rec_geom, dt_comp, context=model.ctx)
+    q_in, d_in = maybe_pad_t0(q_in, src_geom, d_in, rec_geom, dt_comp)
+    sc, rc = src_geom.coords(ndim), rec_geom.coords(ndim)
+    f, g, Iu, Iv = interface.J_adjoint(model, sc, q_in, rc, d_in, is_residual=False,
+                                       t_sub=o.subsampling_factor, checkpointing=o.optimal_checkpointing,
+                                       freq_list=o.frequencies or None, dft_sub=o.dft_subsampling_factor,
+                                       ic=o.IC, f0=o.f0, born_fwd=lin, nlind=nlind, misfit=misfit,
+                                       return_obj=True, illum=illum, snapshot_region=o.snapshot_region)
+
+    def post(a, fold):
+        a = remove_padding(a, model, true_adjoint=fold)
+        if o.limit_m and tuple(shape) != full_shape:
+            full = np.zeros(full_shape, dtype=np.float32, order="F")
+            start = [int(round(float((origin[d] - full_origin[d]) / spacing[d]))) for d in range(ndim)]
+            full[tuple(slice(s_, s_ + n) for s_, n in zip(start, shape))] = a
+            return full
+        return np.array(a, copy=True, order="F")
+    out = (np.float32(f), post(g, o.sum_padding))
+    if illum:
+        out += (post(Iu, False), post(Iv, False))
+    return out
