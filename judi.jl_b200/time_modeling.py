@@ -323,3 +323,49 @@ def multi_src_fg(origin, spacing, shape, params, src_geom, src_data, rec_geom, r
     if illum:
         out += (post(Iu, False), post(Iv, False))
     return out
+
+
+def time_modeling_w(origin, spacing, shape, params, weights, wavelet, rec_geom, rec_data, dm, op,
+                    options=None, fw=True, illum=False, context=None):
+    """The extended-source methods of `devito_interface` (python_interface.jl:124-198) behind
+    `_time_modeling`: `weights` are the judiWeights of one experiment on the physical grid,
+    `wavelet` the judiLRWF time signature sampled on the receiver geometry's time axis.
+
+      op = "forward"        d   = Pr F Pw' w           -> (nt_rec, nrec)        (:125-140)
+      op = "adjoint"        w   = Pw F' Pr' d          -> physical grid          (:143-158)
+      op = "born"           d   = Jw dm                -> (nt_rec, nrec)        (:161-176)
+      op = "adjoint_born"   g   = Jw' d                -> physical grid          (:179-198)
+    """
+    o = options or Options()
+    ndim = len(shape)
+    kw = dict(params)
+    if dm is not None:
+        kw["dm"] = np.asarray(dm, dtype=np.float32).reshape(shape)
+    model = Model(origin, spacing, shape, space_order=o.space_order, nbl=o.nbl,
+                  fs=o.free_surface, dt=o.dt_comp, context=context, **kw)
+    dt_comp = np.float32(model.critical_dt)
+    rc = rec_geom.coords(ndim)
+    q_in = time_resample_to_dt(wavelet, rec_geom, dt_comp, context=model.ctx)
+    wpad = None
+    if weights is not None:
+        # pad_array(reshape(weights, shape), modelPy.padsizes; mode=:zeros)
+        wpad = np.asfortranarray(np.pad(np.asarray(weights, dtype=np.float32).reshape(shape),
+                                        model.padsizes, mode="constant"))
+    if op == "forward":
+        rec, _ = interface.forward_rec_w(model, wpad, q_in, rc, f0=o.f0, illum=illum, fw=fw)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+    if op == "born":
+        rec, _ = interface.born_rec_w(model, wpad, q_in, rc, ic=o.IC, f0=o.f0, illum=illum)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+    d_in = time_resample_to_dt(rec_data, rec_geom, dt_comp, context=model.ctx)
+    q_in, d_in = maybe_pad_t0(q_in, rec_geom, d_in, rec_geom, dt_comp)
+    if op == "adjoint":
+        w, _ = interface.adjoint_w(model, rc, d_in, q_in, f0=o.f0, illum=illum, fw=fw)
+        return np.array(remove_padding(w, model, true_adjoint=False), copy=True, order="F")
+    if op == "adjoint_born":
+        g, _, _ = interface.J_adjoint(model, None, q_in, rc, d_in, is_residual=True, ws=wpad,
+                                      t_sub=o.subsampling_factor, checkpointing=o.optimal_checkpointing,
+                                      freq_list=o.frequencies or None, dft_sub=o.dft_subsampling_factor,
+                                      ic=o.IC, f0=o.f0, snapshot_region=o.snapshot_region)
+        return np.array(remove_padding(g, model, true_adjoint=o.sum_padding), copy=True, order="F")
+    raise ValueError("unknown operator %r" % (op,))

@@ -425,3 +425,42 @@ def test_multi_src_fg_driver_with_resampling_and_a_recording_delay():
     fo, go, _, _ = O.J_adjoint(om, src, qi, rec, di, return_obj=True)
     assert abs(float(f) - float(fo)) <= 1e-4 * abs(float(fo))
     assert rel_l2(g, O.remove_padding(go, om.padsizes, true_adjoint=True)) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_time_modeling_with_extended_sources(ndim):
+    """The judiWeights / judiLRWF methods of devito_interface (python_interface.jl:124-198): weights
+    on the physical grid are zero-padded, the wavelet lives on the receiver geometry's time axis."""
+    import judi_jl_b200 as J
+    TM = J.time_modeling
+    args = model_args("iso", ndim, 8)
+    om = O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dtc = np.float32(om.critical_dt)
+    nt = 130
+    T = np.float32((nt - 1) * dtc)
+    rg = TM.Geometry(rec[:, 0], rec[:, 1] if ndim == 3 else None, rec[:, -1], dt=dtc, t=T)
+    assert rg.nt == nt
+    q = O.ricker_wavelet(T, dtc, 0.02)[:nt]
+    rng = np.random.default_rng(5)
+    w = np.zeros(args["shape"], np.float32)
+    box = tuple(slice(s // 2 - 4, s // 2 + 4) for s in args["shape"])
+    w[box] = rng.standard_normal(w[box].shape).astype(np.float32)
+    wpad = np.pad(w, om.padsizes, mode="constant")
+    opt = TM.Options(space_order=8, nbl=args["nbl"])
+    params = {"m": args["m"]}
+    a = (args["origin"], args["spacing"], args["shape"], params)
+    d = TM.time_modeling_w(*a, w, q, rg, None, None, "forward", opt)
+    do, _ = O.forward_rec_w(om, wpad, q, rec)
+    assert rel_l2(d, do) < 1e-4
+    y = rng.standard_normal(d.shape).astype(np.float32)
+    wa = TM.time_modeling_w(*a, None, q, rg, y, None, "adjoint", opt, fw=False)
+    wao, _ = O.adjoint_w(om, rec, y, q, fw=False)
+    assert wa.shape == args["shape"] and rel_l2(wa, O.remove_padding(wao, om.padsizes)) < 1e-4
+    dl = TM.time_modeling_w(*a, w, q, rg, None, args["dm"], "born", opt)
+    dlo, _ = O.born_rec_w(om, wpad, q, rec)
+    assert rel_l2(dl, dlo) < 1e-4
+    g = TM.time_modeling_w(*a, w, q, rg, y, None, "adjoint_born", opt)
+    go, _, _ = O.J_adjoint(om, None, q, rec, y, is_residual=True, ws=wpad)
+    assert rel_l2(g, O.remove_padding(go, om.padsizes)) < 1e-3
