@@ -369,3 +369,30 @@ def time_modeling_w(origin, spacing, shape, params, weights, wavelet, rec_geom, 
                                       ic=o.IC, f0=o.f0, snapshot_region=o.snapshot_region)
         return np.array(remove_padding(g, model, true_adjoint=o.sum_padding), copy=True, order="F")
     raise ValueError("unknown operator %r" % (op,))
+
+
+def time_modeling_wf(origin, spacing, shape, params, src_geom, src_data, rec_geom, options=None,
+                     fw=True, illum=False, context=None):
+    """The full-wavefield methods of `devito_interface` (python_interface.jl:44-81):
+
+      src_geom given, rec_geom None    u     = F Ps' q      wavefield history (nt, padded grid), :45-56
+      src_geom None,  rec_geom given   d_obs = Pr F u       shot record on the receiver time axis, :59-69
+      both None                        u_out = F u_in       wavefield history, :72-80
+
+    A wavefield source `src_data` is (nt, padded grid) on the computational time axis, as a
+    judiWavefield carries it; wavefield results come back the same way with their dt (what
+    `post_process(..., Val(:forward))` wraps into a judiWavefield)."""
+    o = options or Options()
+    ndim = len(shape)
+    model = Model(origin, spacing, shape, space_order=o.space_order, nbl=o.nbl,
+                  fs=o.free_surface, dt=o.dt_comp, context=context, **dict(params))
+    dt_comp = np.float32(model.critical_dt)
+    if src_geom is not None:
+        q_in = time_resample_to_dt(src_data, src_geom, dt_comp, context=model.ctx)
+        u, _ = interface.forward_no_rec(model, src_geom.coords(ndim), q_in, f0=o.f0, illum=illum, fw=fw)
+        return u, dt_comp
+    if rec_geom is not None:
+        rec, _ = interface.forward_wf_src(model, src_data, rec_geom.coords(ndim), f0=o.f0, illum=illum, fw=fw)
+        return time_resample_to_geometry(rec, dt_comp, rec_geom, context=model.ctx)
+    u, _ = interface.forward_wf_src_norec(model, src_data, f0=o.f0, illum=illum, fw=fw)
+    return u, dt_comp

@@ -464,3 +464,34 @@ def test_time_modeling_with_extended_sources(ndim):
     g = TM.time_modeling_w(*a, w, q, rg, y, None, "adjoint_born", opt)
     go, _, _ = O.J_adjoint(om, None, q, rec, y, is_residual=True, ws=wpad)
     assert rel_l2(g, O.remove_padding(go, om.padsizes)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_time_modeling_with_wavefield_sources():
+    """python_interface.jl:44-81: F Ps' q -> wavefield, Pr F u -> record, F u_in -> wavefield, and
+    their consistency: sampling F Ps' q at the receivers reproduces Pr F Ps' q."""
+    import judi_jl_b200 as J
+    TM = J.time_modeling
+    args = model_args("iso", 2, 8, with_dm=False)
+    om = O.Model(precision="f32", **args)
+    src, rec = geometry(args)
+    dtc = np.float32(om.critical_dt)
+    nt = 90
+    T = np.float32((nt - 1) * dtc)
+    sg = TM.Geometry(src[:, 0], None, src[:, 1], dt=dtc, t=T)
+    rg = TM.Geometry(rec[:, 0], None, rec[:, 1], dt=dtc, t=T)
+    q = O.ricker_wavelet(T, dtc, 0.02)[:nt]
+    a = (args["origin"], args["spacing"], args["shape"], {"m": args["m"]})
+    opt = TM.Options(space_order=8, nbl=args["nbl"])
+    u, dt_u = TM.time_modeling_wf(*a, sg, q, None, opt)
+    assert u.shape == (nt,) + om.shape_pml and dt_u == dtc
+    _, uo, _ = O.forward(om, src, None, q, save=True)
+    assert rel_l2(u[2:nt - 1], uo[2:nt - 1, 0]) < 1e-4
+    usrc = np.zeros((nt,) + om.shape_pml, np.float32)
+    usrc[:, 50:54, 40:44] = np.random.default_rng(2).standard_normal((nt, 4, 4)).astype(np.float32)
+    d = TM.time_modeling_wf(*a, None, usrc, rg, opt)
+    do, _ = O.forward_wf_src(om, usrc, rec)
+    assert d.shape == (nt, rec.shape[0]) and rel_l2(d, do) < 1e-4
+    u2, _ = TM.time_modeling_wf(*a, None, usrc, None, opt)
+    u2o, _ = O.forward_wf_src_norec(om, usrc)
+    assert rel_l2(u2[2:nt - 1], np.asarray(u2o)[2:nt - 1].reshape(u2[2:nt - 1].shape)) < 1e-4
