@@ -123,7 +123,7 @@ __device__ float lap_weighted2d(const Grid &g, const Coefs &cf, const float *__r
 // and runs 16 C2 shots in lockstep at 60 Gpt/s, close to its own issue limit; the vector body
 // amortises that arithmetic over 4 points.  Plain / save / imaging condition "as" / illumination
 // of the constant-density kernel without free surface, space-time sources or Born (host: p2_vec_ok).
-template <int R, bool XIC, int VEC = 0>
+template <int R, bool XIC, int VEC = 0, bool VBORN = false>
 __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, const int nb)
 {
     cg::grid_group grid = cg::this_grid();
@@ -208,11 +208,13 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
                     rows[0] = r4.x; rows[1] = r4.y; rows[2] = r4.z; rows[3] = r4.w;
                 }
                 float dl[4], unew[4];
+                [[maybe_unused]] float sv[4], rd[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const float ucv = w[HRV + e];
                     const float s_ = ((dxs[e] + 0.f) + dzv) * a.sdamp;
                     const float rden = 1.0f / (mms[e] + s_);
+                    if (VBORN) { sv[e] = s_; rd[e] = rden; }
                     const float d1 = ucv - ups[e];
                     const float delta = (lap[e] - s_ * d1) * rden;
                     float inj = 0.f;
@@ -230,6 +232,45 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
 #pragma unroll
                     for (int e = 0; e < 4; e++)
                         if (x + e < g.n[0]) un[i + e] = unew[e];
+                }
+                if constexpr (VBORN) {
+                    // linearised field with the Born source -dm (u+ - 2u + u-), post-injection
+                    // (sensitivity.py:174-188), same arithmetic as the one-point-per-thread body
+                    float wl[NW];
+#pragma unroll
+                    for (int v = 0; v < NW / 4; v++) {
+                        const float4 t4 = *(const float4 *)(lc + i - HRV + 4 * v);
+                        wl[4 * v] = t4.x; wl[4 * v + 1] = t4.y; wl[4 * v + 2] = t4.z; wl[4 * v + 3] = t4.w;
+                    }
+                    float lapl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) lapl[e] = a.cf.c0 * wl[HRV + e];
+#pragma unroll
+                    for (int k = 1; k <= R; k++) {
+                        const float4 p4 = *(const float4 *)(lc + i + k * g.sz), m4 = *(const float4 *)(lc + i - k * g.sz);
+                        lapl[0] += a.cf.cz[k] * (p4.x + m4.x); lapl[1] += a.cf.cz[k] * (p4.y + m4.y);
+                        lapl[2] += a.cf.cz[k] * (p4.z + m4.z); lapl[3] += a.cf.cz[k] * (p4.w + m4.w);
+                    }
+#pragma unroll
+                    for (int k = 1; k <= R; k++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) lapl[e] += a.cf.cx[k] * (wl[HRV + e + k] + wl[HRV + e - k]);
+                    const float4 lp4 = *(const float4 *)(ln + i), dm4 = *(const float4 *)(a.dms + i);
+                    const float lps[4] = {lp4.x, lp4.y, lp4.z, lp4.w}, dmv[4] = {dm4.x, dm4.y, dm4.z, dm4.w};
+                    float lnew[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float lcv = wl[HRV + e];
+                        const float d1l = lcv - lps[e];
+                        const float q = -dmv[e] * dl[e];
+                        lnew[e] = (lcv + d1l) + (lapl[e] - sv[e] * d1l + q) * rd[e];
+                    }
+                    if (x + 3 < g.n[0]) *(float4 *)(ln + i) = make_float4(lnew[0], lnew[1], lnew[2], lnew[3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (x + e < g.n[0]) ln[i + e] = lnew[e];
+                    }
                 }
                 if ((snap_t || usnap_t || a.illum) && z >= a.reg.lo[2] && z < a.reg.hi[2] &&
                     x + 3 >= a.reg.lo[0] && x < a.reg.hi[0]) {
@@ -334,8 +375,8 @@ __global__ void __launch_bounds__(256, VEC ? VEC : (XIC ? 2 : 4)) acoustic2d_per
 
 // Several shots of the same model and time axis in lockstep: CTA b works on shot b / per_shot.
 // One grid barrier per time step serves all of them (judi_fg_multishot on small 2-D grids).
-template <int R, bool XIC, int VEC = 0>
-__global__ void __launch_bounds__(256, VEC ? VEC : (XIC ? 2 : 4)) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
+template <int R, bool XIC, int VEC = 0, bool VBORN = false>
+__global__ void __launch_bounds__(256, VEC ? (VBORN ? 2 : VEC) : (XIC ? 2 : 4)) acoustic2d_persist_batch(const P2Args *__restrict__ batch, int per_shot)
 {
     // the shot's arguments go to shared memory once: read through the global pointer, every stencil
     // coefficient would be a load from L1/L2 instead of a constant-bank operand
@@ -346,7 +387,7 @@ __global__ void __launch_bounds__(256, VEC ? VEC : (XIC ? 2 : 4)) acoustic2d_per
         for (int i = threadIdx.x; i < (int)(sizeof(P2Args) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    acoustic2d_body<R, XIC, VEC>(sa, blockIdx.x % per_shot, per_shot);
+    acoustic2d_body<R, XIC, VEC, VBORN>(sa, blockIdx.x % per_shot, per_shot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -879,9 +920,9 @@ static void p2_fill(const judi_model *M, Wavefield &W, Wavefield *WL, int t0, in
 }
 
 // what the 4-points-per-thread body covers
-static bool p2_vec_ok(const P2Args &a)
+static bool p2_vec_ok(const P2Args &a, bool born = false)
 {
-    return !a.fs && !a.qext && !a.qwf && !a.wrec && !a.l[0] && a.ic == JUDI_IC_AS;
+    return !a.fs && !a.qext && !a.qwf && !a.wrec && (born || !a.l[0]) && a.ic == JUDI_IC_AS;
 }
 
 // Runs time indices t0, t0+dir, ..., t1 of one sweep.  W (and WL for Born) are advanced
@@ -1024,10 +1065,11 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
                 args[(size_t)s]);
     DevArr<P2Args> dargs(ctx, (size_t)n, false);
     dargs.upload(args);
-    auto launch = [&](auto rtag, auto xtag, auto vtag) {
+    auto launch = [&](auto rtag, auto xtag, auto vtag, auto btag) {
         constexpr int R = decltype(rtag)::value;
         constexpr int VEC = decltype(vtag)::value;
-        auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value, VEC>;
+        constexpr bool VBORN = decltype(btag)::value;
+        auto kern = acoustic2d_persist_batch<R, decltype(xtag)::value, VEC, VBORN>;
         static int max_blocks = 0;
         if (!max_blocks) {
             int per_sm = 0;
@@ -1046,23 +1088,24 @@ void persist2d_run_batch(const judi_model *M, int n, Wavefield *const *W, int t0
                                                ctx->stream));
         launch_count(ctx, "acoustic2d_persist_batch");
     };
-    auto launch_r = [&](auto xtag, auto vtag) {
+    auto launch_r = [&](auto xtag, auto vtag, auto btag) {
         switch (M->r) {
-        case 2: launch(std::integral_constant<int, 2>(), xtag, vtag); break;
-        case 4: launch(std::integral_constant<int, 4>(), xtag, vtag); break;
-        default: launch(std::integral_constant<int, 8>(), xtag, vtag); break;
+        case 2: launch(std::integral_constant<int, 2>(), xtag, vtag, btag); break;
+        case 4: launch(std::integral_constant<int, 4>(), xtag, vtag, btag); break;
+        default: launch(std::integral_constant<int, 8>(), xtag, vtag, btag); break;
         }
     };
     bool vec = ctx->opt_persist_vec != 0;
-    for (int s = 0; s < n; s++) vec = vec && p2_vec_ok(args[(size_t)s]);
+    for (int s = 0; s < n; s++) vec = vec && p2_vec_ok(args[(size_t)s], WL != nullptr);
     // option persist_vec: 1 / 2 = vector body at 3 CTAs per SM (80 registers), 3 = at 2 CTAs per SM (118),
     // 4 = at 4 CTAs per SM (64 registers, 84 bytes of spills)
     typedef std::integral_constant<int, 0> V0;
-    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type(), V0());
-    else if (vec && ctx->opt_persist_vec == 3) launch_r(std::false_type(), std::integral_constant<int, 2>());
-    else if (vec && ctx->opt_persist_vec == 4) launch_r(std::false_type(), std::integral_constant<int, 4>());
-    else if (vec) launch_r(std::false_type(), std::integral_constant<int, 3>());
-    else launch_r(std::false_type(), V0());
+    if (args[0].ic != JUDI_IC_AS && (args[0].grad || WL)) launch_r(std::true_type(), V0(), std::false_type());
+    else if (vec && WL) launch_r(std::false_type(), std::integral_constant<int, 3>(), std::true_type());
+    else if (vec && ctx->opt_persist_vec == 3) launch_r(std::false_type(), std::integral_constant<int, 2>(), std::false_type());
+    else if (vec && ctx->opt_persist_vec == 4) launch_r(std::false_type(), std::integral_constant<int, 4>(), std::false_type());
+    else if (vec) launch_r(std::false_type(), std::integral_constant<int, 3>(), std::false_type());
+    else launch_r(std::false_type(), V0(), std::false_type());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dargs is freed on return
     if (nsteps & 1)
         for (int s = 0; s < n; s++) {

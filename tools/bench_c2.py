@@ -29,8 +29,12 @@ for sx in np.linspace(500., 9500., 16):
     dobs, _ = J.forward_rec(mt, src, q, rec)
     shots.append((src, q, rec, dobs))
 m0 = np.asfortranarray((1 / v0 ** 2).astype(np.float32))
+lsrtm = os.environ.get("LSRTM", "0") == "1"     # LS-RTM objective (Born forward sweeps) instead of FWI
+dm0 = np.asfortranarray((1 / v ** 2 - 1 / v0 ** 2).astype(np.float32))
 def run():
     gm = J.Model((0., 0.), d, n, m=m0, dt=dt, **kw)
+    if lsrtm:
+        return J.objectives.lsrtm_objective(gm, shots, dm0, nlind=True)
     return J.objectives.fwi_objective(gm, shots)
 ctx.set_option("persist_blocks", int(os.environ.get("PERSIST_BLOCKS", "0")))
 ctx.set_option("persist_vec", int(os.environ.get("PERSIST_VEC", "1")))
@@ -41,7 +45,7 @@ for _ in range(reps): f, g = run()
 ctx.synchronize()
 wall = (time.perf_counter() - t0) / reps
 N = 481 * 201
-print("C2 (%s) fwi_objective, 16 shots" % kind)
+print("C2 (%s) %s, 16 shots" % (kind, "lsrtm_objective" if lsrtm else "fwi_objective"))
 print("C2 fwi_objective, 16 shots, nt=%d: %.1f ms per gradient (%.2f ms per shot, %.1f shots/s, %.1f Gpt/s)  f=%.4e |g|=%.4e" % (
     nt, 1e3 * wall, 1e3 * wall / 16, 16 / wall, 16 * 2 * nt * N / wall / 1e9, float(f), float(np.linalg.norm(g))), flush=True)
 ctx.set_option("profile", 1)
