@@ -231,7 +231,8 @@ struct judi_model {
     DevBuf dm_src_buf;
     const float *dm_src() const { return dm_src_buf.p ? dm_src_buf.p : dm.p; }
     DevBuf r3[3];                // 3-D TTI: symmetry axis (sin th cos ph, sin th sin ph, cos th)
-    DevBuf ttiABC[3];            // 3-D TTI, constant density: A0 = b delta~, B0 = b sqrt((eps~-delta~) delta~), C0 = b (eps~-delta~)
+    DevBuf ttiABC[3];            // 3-D TTI: A0 = b delta~, B0 = b sqrt((eps~-delta~) delta~), C0 = b (eps~-delta~)
+    DevBuf tti_mi;               // 3-D TTI with a density field: m * b (tile ring of the single-pass kernel)
     DevBuf damp[3];              // 1-D damping profiles per dimension (value of `damp`)
     std::vector<float> damp_h[3];
     Region phys, full;
@@ -339,7 +340,7 @@ struct Wavefield {
     CUtensorMap tmap_dm;          // tile box over the model's dm (Born)
     CUtensorMap tmap_coef;        // variable density: haloed box over irho ...
     CUtensorMap tmap_irho;        // ... and its tile box
-    CUtensorMap tmap_par[6];      // 3-D TTI single pass: parameter planes A0, B0, C0, r
+    CUtensorMap tmap_par[7];      // 3-D TTI single pass: parameter planes A0, B0, C0, r [, b]
     bool has_tmap = false;
     bool two_pass_only = false;   // flux-form physics: never take the single-pass kernels
     bool generic_only = false;    // flux-form physics: one-point-per-thread kernels only (isic / fwi Born)

@@ -520,7 +520,7 @@ void Wavefield::init(const judi_model *M, bool born_scratch)
     } else if (tti3d_supported(M)) {
         for (int f = 0; f < nf; f++)
             for (int s = 0; s < 2; s++) tti3d_encode(M, b[f][s].p, &tmap_halo[f][s], &tmap_tile[f][s]);
-        tti3d_encode(M, M->m.p, nullptr, &tmap_m);
+        tti3d_encode(M, M->irho_field ? M->tti_mi.p : M->m.p, nullptr, &tmap_m);
         tti3d_encode_coef(M, tmap_par);
         has_tmap = true;
     }

@@ -305,12 +305,16 @@ __global__ void tti_axis_kernel(const float *__restrict__ theta, const float *__
 
 // point-wise TTI coefficients of the closed-form rotation (flux3d.cu), constant density b:
 // the same fp32 expressions the two-pass kernel evaluates per node and step
-__global__ void tti_abc_kernel(const float *__restrict__ eps, const float *__restrict__ delta, float b,
+// (bf: b as a field, or nullptr for the constant; mi: optional output m * b)
+__global__ void tti_abc_kernel(const float *__restrict__ eps, const float *__restrict__ delta, float bc,
+                               const float *__restrict__ bf, const float *__restrict__ m,
                                long long n, float *__restrict__ A0, float *__restrict__ B0,
-                               float *__restrict__ C0)
+                               float *__restrict__ C0, float *__restrict__ mi)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float b = bf ? bf[i] : bc;
+    if (mi) { mi[i] = __fmul_rn(m[i], b); return; }
     const float e = eps[i], d = delta[i];
     const float emd = __fsub_rn(e, d);
     A0[i] = __fmul_rn(b, d);
@@ -435,11 +439,20 @@ void model_build(judi_model *M, judi_ctx *ctx, const judi_model_desc *desc)
             launch_count(ctx, "tti_axis");
         }
         if (M->ndim == 3) {
-            if (!M->irho_field && (M->so == 8 || M->so == 4)) {
+            if (M->so == 8 || M->so == 4) {
                 for (int d = 0; d < 3; d++) M->ttiABC[d] = DevBuf(ctx, (size_t)M->g.nalloc, false);
-                tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c, M->g.nalloc,
-                                                            M->ttiABC[0].p, M->ttiABC[1].p, M->ttiABC[2].p);
+                tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c,
+                                                            M->irho_field ? M->irho.p : nullptr, M->m.p, M->g.nalloc,
+                                                            M->ttiABC[0].p, M->ttiABC[1].p, M->ttiABC[2].p,
+                                                            nullptr);
                 launch_count(ctx, "tti_abc");
+                if (M->irho_field) {
+                    // the single-pass kernel's tile ring carries m * b for a density field
+                    M->tti_mi = DevBuf(ctx, (size_t)M->g.nalloc, false);
+                    tti_abc_kernel<<<nb, 256, 0, ctx->stream>>>(M->eps.p, M->delta.p, M->irho_c, M->irho.p, M->m.p,
+                                                                M->g.nalloc, nullptr, nullptr, nullptr, M->tti_mi.p);
+                    launch_count(ctx, "tti_abc");
+                }
             }
         }
         if (M->tti && !M->irho_field) {

@@ -49,7 +49,10 @@
 
 // Geometry of one CTA for stencil radius R = space_order / 2 (2 or 4).  The x layout works in groups
 // of 4 points and keeps one halo group per side whatever R <= 4 is; the y / z extents follow R.
-template <int R_>
+// RHO: the model has a density field -- a seventh parameter plane carries b = 1/rho to the flux
+// nodes, the tile ring carries m * b instead of m, and the D role reads b of its own points from
+// global memory where a flavour needs it (imaging condition, Born source).
+template <int R_, bool RHO_ = false>
 struct TtiC {
     static constexpr int R = R_;
     static constexpr int TXG = 8, TX = 4 * TXG, TY = 16;      // tile: 8 groups of 4 x-points, 16 rows
@@ -57,7 +60,7 @@ struct TtiC {
     static constexpr int USLOT = ((UPX * UPY + 31) / 32) * 32;
     static constexpr int CPX = TX + 8, CPY = TY + 2 * R - 1;  // parameter plane, origin (x0-4, y0-R)
     static constexpr int CSLOT = ((CPX * CPY + 31) / 32) * 32;  // 128-byte aligned slots
-    static constexpr int NPAR = 6;                            // A0, B0, C0, rx, ry, rz
+    static constexpr int NPAR = RHO_ ? 7 : 6;                 // A0, B0, C0, rx, ry, rz [, b]
     static constexpr int PSLOT = TX * TY;
     static constexpr int NS = 8, NC = 3, NP = 3;              // ring depths: u planes, parameter planes, tiles
     static constexpr int NQ = 2 * R;                          // z-queue: planes zf-(R-1) .. zf+R
@@ -77,7 +80,7 @@ struct TtiC {
     static_assert(R == 2 || R == 4, "x halo of one 4-point group: R <= 4");
     static_assert(R + 1 + LEADU <= NS, "u ring too short");
 };
-constexpr int TTI_NPAR = 6;
+constexpr int TTI_NPAR = 7;
 
 struct TtiMaps {
     CUtensorMap U1, U2;        // haloed planes of u1(t), u2(t)
@@ -96,6 +99,7 @@ struct TtiArgs {
     float *dd_out[2];        // Born background pass: write delta = u+ - 2u + u- of both fields
     const float *dd_in[2];   // Born linearised pass: delta of the background fields ...
     const float *dm;         // ... and the model perturbation: q_f = -dm irho delta_f
+    const float *irho;       // RHO: b = 1/rho (Grid layout), read by the D role of the IC / Born flavours
 };
 
 // what rides on the step (compile-time mask): snapshot save, imaging condition, illumination,
@@ -130,11 +134,11 @@ __device__ __forceinline__ void tti_dx(const float *wx, const float4 &l, const f
 // (2R-1 float4 moves per field), 2 = main loop unrolled by two with one spare slot, shifted by two
 // every second plane (half the moves, twice the code), NQ = rotated at compile time (no moves,
 // NQ times the code).
-template <int R, int FUSE, int UF, int UD>
+template <int R, int FUSE, int UF, int UD, bool RHO = false>
 __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
     tti3d_tma(const __grid_constant__ TtiMaps tm, const TtiArgs a)
 {
-    typedef TtiC<R> C;
+    typedef TtiC<R, RHO> C;
     constexpr int TXG = C::TXG, TX = C::TX, TY = C::TY, UPX = C::UPX, USLOT = C::USLOT, CPX = C::CPX;
     constexpr int CPY = C::CPY, CSLOT = C::CSLOT, NPAR = C::NPAR, PSLOT = C::PSLOT, NS = C::NS, NC = C::NC;
     constexpr int NP = C::NP, NQ = C::NQ, NI = C::NI, NF = C::NF, ND = C::ND, FXW = C::FXW, FX = C::FX;
@@ -309,6 +313,8 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                     const float4 C4 = *(const float4 *)(pc + 2 * CSLOT);
                     const float4 rx4 = *(const float4 *)(pc + 3 * CSLOT), ry4 = *(const float4 *)(pc + 4 * CSLOT);
                     const float4 rz4 = *(const float4 *)(pc + 5 * CSLOT);
+                    [[maybe_unused]] float4 b4;
+                    if (RHO) b4 = *(const float4 *)(pc + 6 * CSLOT);
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const f2 A0 = h ? hi2(A4) : lo2(A4), B0 = h ? hi2(B4) : lo2(B4);
@@ -318,7 +324,8 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                         const f2 d1 = fma2(rz, G[0][2][h], fma2(ry, G[0][1][h], mul2(rx, G[0][0][h])));
                         const f2 d2 = fma2(rz, G[1][2][h], fma2(ry, G[1][1][h], mul2(rx, G[1][0][h])));
                         const f2 nB0 = mul2s(-1.f, B0);
-                        const f2 sP = fma2(nB0, d2, mul2(sub2(bb, A0), d1));
+                        const f2 bh = RHO ? (h ? hi2(b4) : lo2(b4)) : bb;
+                        const f2 sP = fma2(nB0, d2, mul2(sub2(bh, A0), d1));
                         const f2 sM = fma2(nB0, d1, mul2(mul2s(-1.f, C0), d2));
                         P[0][h] = fma2(sP, rx, fma2(B0, G[1][0][h], mul2(A0, G[0][0][h])));
                         P[1][h] = fma2(sP, ry, fma2(B0, G[1][1][h], mul2(A0, G[0][1][h])));
@@ -410,8 +417,11 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
             [[maybe_unused]] bool fin = false, fvec = false;
             [[maybe_unused]] float4 us1, us2, G4, I4;
             [[maybe_unused]] float4 dq1 = make_float4(0.f, 0.f, 0.f, 0.f), dq2 = dq1, dm4 = dq1;
+            [[maybe_unused]] float4 ir4 = make_float4(a.irho_c, a.irho_c, a.irho_c, a.irho_c);
             if (out) {
                 dz_s = __ldg(a.dz + z);
+                // (a partial group at the x edge reads into the replicated halo of the allocation)
+                if (RHO && (f_q || f_grad) && act) ir4 = __ldg((const float4 *)(a.irho + gout));
                 if (f_q && act) {
                     // (a partial group at the x edge reads into the zero halo of the allocation)
                     dq1 = *(const float4 *)(a.dd_in[0] + gout);
@@ -497,7 +507,9 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                 // delta = (dt^2 H - sd (u - u-)) / (m irho + sd),  u+ = (u + (u - u-)) + delta
                 const f2 dzv = pk1(dz_s);
                 const f2 sd0 = mul2s(cf.dt, add2(dxy0, dzv)), sd1 = mul2s(cf.dt, add2(dxy1, dzv));
-                const f2 den0 = fma2s(a.irho_c, lo2(m4), sd0), den1 = fma2s(a.irho_c, hi2(m4), sd1);
+                // RHO: the tile ring carries m * b
+                const f2 den0 = RHO ? add2(lo2(m4), sd0) : fma2s(a.irho_c, lo2(m4), sd0);
+                const f2 den1 = RHO ? add2(hi2(m4), sd1) : fma2s(a.irho_c, hi2(m4), sd1);
                 const f2 r0 = pk(__frcp_rn(den0.x), __frcp_rn(den0.y));
                 const f2 r1 = pk(__frcp_rn(den1.x), __frcp_rn(den1.y));
                 const f2 nsd0 = mul2s(-1.f, sd0), nsd1 = mul2s(-1.f, sd1);
@@ -511,7 +523,8 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                         // dt^2 * lin_src = -dm irho (u+ - 2u + u-) of the background field
                         // (sensitivity.py:174-188; the post-injection part is added by sparse.cu)
                         const float4 dq = f ? dq2 : dq1;
-                        const f2 w0 = mul2s(-a.irho_c, lo2(dm4)), w1 = mul2s(-a.irho_c, hi2(dm4));
+                        const f2 w0 = RHO ? mul2(mul2s(-1.f, lo2(ir4)), lo2(dm4)) : mul2s(-a.irho_c, lo2(dm4));
+                        const f2 w1 = RHO ? mul2(mul2s(-1.f, hi2(ir4)), hi2(dm4)) : mul2s(-a.irho_c, hi2(dm4));
                         h0 = fma2(w0, lo2(dq), h0);
                         h1 = fma2(w1, hi2(dq), h1);
                     }
@@ -548,7 +561,11 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                             // gradient -= gcoef irho (us1 delta1 + us2 delta2)   (sensitivity.py:55-69)
                             const f2 ic0 = fma2(lo2(us2), dl[1][0], mul2(lo2(us1), dl[0][0]));
                             const f2 ic1 = fma2(hi2(us2), dl[1][1], mul2(hi2(us1), dl[0][1]));
-                            *(float4 *)(fz.grad + ri) = cat4(fma2s(-gc, ic0, lo2(G4)), fma2s(-gc, ic1, hi2(G4)));
+                            if (RHO)
+                                *(float4 *)(fz.grad + ri) = cat4(fma2(mul2s(-fz.gcoef, lo2(ir4)), ic0, lo2(G4)),
+                                                                 fma2(mul2s(-fz.gcoef, hi2(ir4)), ic1, hi2(G4)));
+                            else
+                                *(float4 *)(fz.grad + ri) = cat4(fma2s(-gc, ic0, lo2(G4)), fma2s(-gc, ic1, hi2(G4)));
                         }
                         if (f_il) {
                             // illumination += dt (u1^2 + u2^2)   (fields_exprs.py:240-255)
@@ -567,7 +584,9 @@ __global__ void __launch_bounds__(TtiC<R>::NTHREADS, 1)
                             if (f_grad) {
                                 const float ic = __fmaf_rn(fz.usnap[1][ri + e], d2v[e],
                                                            __fmul_rn(fz.usnap[0][ri + e], d1v[e]));
-                                fz.grad[ri + e] = __fmaf_rn(-gc, ic, fz.grad[ri + e]);
+                                const float irv[4] = {ir4.x, ir4.y, ir4.z, ir4.w};
+                                const float gce = RHO ? __fmul_rn(fz.gcoef, irv[e]) : gc;
+                                fz.grad[ri + e] = __fmaf_rn(-gce, ic, fz.grad[ri + e]);
                             }
                             if (f_il) {
                                 const float e2 = __fmaf_rn(u2v[e], u2v[e], __fmul_rn(u1v[e], u1v[e]));
@@ -979,8 +998,8 @@ __global__ void __launch_bounds__(ttih::NTHREADS, 1)
 // ---- host side ---------------------------------------------------------------------------------
 bool tti3d_supported(const judi_model *M)
 {
-    return M->ndim == 3 && M->tti && !M->visco && !M->irho_field && (M->r == 4 || M->r == 2) && M->ctx->encode_tiled != nullptr &&
-           M->ctx->opt_tti_fused && M->ttiABC[0].p != nullptr;
+    return M->ndim == 3 && M->tti && !M->visco && (M->r == 4 || M->r == 2) && M->ctx->encode_tiled != nullptr &&
+           M->ctx->opt_tti_fused && M->ttiABC[0].p != nullptr && (!M->irho_field || M->tti_mi.p != nullptr);
 }
 
 void tti3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map, CUtensorMap *tile_map)
@@ -994,6 +1013,8 @@ void tti3d_encode_coef(const judi_model *M, CUtensorMap *maps)
     const int cpy = M->r == 2 ? TtiC<2>::CPY : TtiC<4>::CPY;
     for (int p = 0; p < 3; p++) tma_encode_box(M, M->ttiABC[p].p, TtiC<4>::CPX, cpy, &maps[p]);
     for (int p = 0; p < 3; p++) tma_encode_box(M, M->r3[p].p, TtiC<4>::CPX, cpy, &maps[3 + p]);
+    if (M->irho_field) tma_encode_box(M, M->irho.p, TtiC<4>::CPX, cpy, &maps[6]);
+    else maps[6] = maps[0];
 }
 
 // z-chunks per tile column: whole waves of one CTA per SM, counting the 14 warm-up planes
@@ -1013,10 +1034,10 @@ static int tti3d_chunks(const judi_ctx *ctx, int ntiles, int nz, int warm)
 }
 
 // lin: launch on the linearised wavefield (Born source in); otherwise on the background field
-template <int R, int FUSE>
+template <int R, int FUSE, bool RHO = false>
 static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
 {
-    typedef TtiC<R> C;
+    typedef TtiC<R, RHO> C;
     judi_ctx *ctx = M->ctx;
     // register queues: 2 shifted every plane (default), 1 rotated at compile time, 3 / 4 only the
     // F / D role rotated
@@ -1026,16 +1047,21 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
     int var = ctx->opt_tti_fused;
     if (var == 1 && ROTQ == 1) var = 2;
     if (var != 1 && var != 5 && var != 6 && var != 7) var = 2;
-    void (*kern)(const TtiMaps, const TtiArgs) =
-        var == 1 ? tti3d_tma<R, FUSE, ROTQ, ROTQ> : var == 5 ? tti3d_tma<R, FUSE, 2, 2>
-        : var == 6 ? tti3d_tma<R, FUSE, 2, 1> : var == 7 ? tti3d_tma<R, FUSE, 1, 2> : tti3d_tma<R, FUSE, 1, 1>;
+    void (*kern)(const TtiMaps, const TtiArgs);
+    if constexpr (RHO) {
+        var = 2;                  // the density-field kernel exists with shifted queues only
+        kern = tti3d_tma<R, FUSE, 1, 1, true>;
+    } else {
+        kern = var == 1 ? tti3d_tma<R, FUSE, ROTQ, ROTQ> : var == 5 ? tti3d_tma<R, FUSE, 2, 2>
+               : var == 6 ? tti3d_tma<R, FUSE, 2, 1> : var == 7 ? tti3d_tma<R, FUSE, 1, 2> : tti3d_tma<R, FUSE, 1, 1>;
+    }
     static bool configured[8] = {false, false, false, false, false, false, false, false};
     if (!configured[var]) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured[var] = true;
     }
     // option tti_fused = 8: the half-width-thread kernel (R = 4; plain / save / imaging condition)
-    constexpr bool HOK = R == 4 && (FUSE == 0 || FUSE == TF_SNAP || FUSE == TF_GRAD);
+    constexpr bool HOK = !RHO && R == 4 && (FUSE == 0 || FUSE == TF_SNAP || FUSE == TF_GRAD);
     bool half = false;
     if constexpr (HOK) {
         if (ctx->opt_tti_fused == 8) {
@@ -1065,6 +1091,7 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
     }
     a.dx = M->damp[0].p; a.dy = M->damp[1].p; a.dz = M->damp[2].p;
     a.irho_c = M->irho_c;
+    a.irho = M->irho.p;
     if (!lin) a.f = s.f;
     const int ntx = (M->N[0] + C::TX - 1) / C::TX, nty = (M->N[1] + C::TY - 1) / C::TY;
     int nzc = tti3d_chunks(ctx, ntx * nty, M->N[2], C::WARM);
@@ -1078,7 +1105,10 @@ static void tti3d_launch_r(const judi_model *M, const StepArgs &s, bool lin)
 template <int FUSE>
 static void tti3d_launch(const judi_model *M, const StepArgs &s, bool lin = false)
 {
-    if (M->r == 2) tti3d_launch_r<2, FUSE>(M, s, lin);
+    if (M->irho_field) {
+        if (M->r == 2) tti3d_launch_r<2, FUSE, true>(M, s, lin);
+        else tti3d_launch_r<4, FUSE, true>(M, s, lin);
+    } else if (M->r == 2) tti3d_launch_r<2, FUSE>(M, s, lin);
     else tti3d_launch_r<4, FUSE>(M, s, lin);
 }
 

@@ -52,14 +52,14 @@ def model_args(kind="iso", ndim=2, so=8, with_dm=True, n=None, nbl=None, fs=Fals
         v += 0.1 * (1 + np.sin(np.arange(n[0]) / 5.0)).astype(np.float32).reshape((-1, 1, 1))
     m = (1 / v ** 2).astype(np.float32)
     kw = {}
-    if kind in ("rho", "visco"):
+    if kind in ("rho", "visco", "ttirho"):
         kw["rho"] = ((v + .5) / 2).astype(np.float32)
     if kind in ("visco", "viscoc"):
         # test/seismic_utils.jl:50-53: qp0 = 3.516 (1000 v)^2.2 1e-6, Model(n, d, o, m, rho0, qp0);
         # "viscoc" is the same with a constant density (the b * p.laplace branch of FD_utils.py:18)
         kw["qp"] = (3.516 * ((v * 1000.) ** 2.2) * 1e-6).astype(np.float32)
         kw["f0"] = 0.02
-    if kind == "tti":
+    if kind in ("tti", "ttirho"):
         kw.update(epsilon=((v - 1.5) / 12).astype(np.float32),
                   delta=((v - 1.5) / 14).astype(np.float32),
                   theta=((v - 1.5) / 4).astype(np.float32))

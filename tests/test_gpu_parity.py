@@ -49,7 +49,9 @@ def both(kind, ndim, so, nt=NT, **kw):
 
 # every propagator of the north star at every space order it names (kernels.py:46-77,144-182 and
 # FD_utils.py:11-105 are generic in space_order), + the visco-acoustic family
+# ("ttirho": TTI with a density field, the reference's own TTI test model, seismic_utils.jl:23-63)
 CASES = [(k, nd, so) for nd in (2, 3) for k in ("iso", "rho", "tti") for so in (8, 4, 16)] + \
+        [("ttirho", 3, 8), ("ttirho", 3, 4), ("ttirho", 3, 16), ("ttirho", 2, 8)] + \
         [("visco", 2, 8), ("viscoc", 2, 8), ("visco", 2, 4), ("visco", 3, 8), ("viscoc", 3, 8)]
 
 
@@ -126,7 +128,7 @@ def test_born_and_gradient_parity_and_dot(kind, ndim, so):
 
 
 @pytest.mark.parametrize("kind,ndim", [("iso", 2), ("tti", 2), ("iso", 3), ("rho", 3), ("tti", 3),
-                                       ("visco", 2), ("viscoc", 3)])
+                                       ("ttirho", 3), ("visco", 2), ("viscoc", 3)])
 def test_fwi_objective_and_options(kind, ndim):
     """fwi objective value + gradient, t_sub, checkpointing, physical-domain snapshots,
     lsrtm (born_fwd, nlind), illumination (test_gradients.jl, test_all_options.jl)."""

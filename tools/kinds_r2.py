@@ -42,19 +42,21 @@ if "so" in which:
     v = velocity(n)
     src, rec = geom(n)
     for so in (4, 8, 16):
-        for kind in ("tti", "rho"):
+        for kind in ("tti", "rho", "ttirho"):
+            if kind == "ttirho" and so == 16:
+                continue
             kw = dict(m=(1 / v ** 2).astype(np.float32))
-            if kind == "tti":
+            if kind in ("tti", "ttirho"):
                 kw.update(epsilon=(0.2 * (v - 1.5) / 4).astype(np.float32), delta=(0.1 * (v - 1.5) / 4).astype(np.float32),
                           theta=(np.pi / 6 * (v - 1.5) / 4).astype(np.float32), phi=np.float32(np.pi / 8))
-            else:
+            if kind in ("rho", "ttirho"):
                 kw["rho"] = ((v + .5) / 2).astype(np.float32)
             gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=so, nbl=40, **kw)
             dt = float(gm.critical_dt)
             q = ricker(nt, dt, 0.008)
             dobs = np.zeros((nt, rec.shape[0]), dtype=np.float32)
             for opt, label in ((1, "single-pass"), (0, "two-pass")):
-                ctx.set_option("tti_fused" if kind == "tti" else "varc_fused", 2 if (opt and kind == "tti") else opt)
+                ctx.set_option("varc_fused" if kind == "rho" else "tti_fused", opt if kind == "rho" else (2 if opt else 0))
                 run("%s so%d %s" % (kind, so, label),
                     lambda: J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=2, snapshot_region="physical"))
             ctx.set_option("tti_fused", 2); ctx.set_option("varc_fused", 1)
