@@ -1,6 +1,6 @@
 """Single-pass 3-D TTI kernel against the two-pass form on the C5 grid: time per step of the
 plain / save / IC flavours and relative difference of shot record and gradient.
-usage: python tools/tti_tune.py [nt] [variants e.g. 0,1,2] [zchunks e.g. 0,1,2]"""
+usage: python tools/tti_tune.py [nt] [variants e.g. 0,1,2] [zchunks e.g. 0,1,2] [space order] [rho]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,13 +9,17 @@ from bench import velocity, ricker
 nt = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 variants = [int(s) for s in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2]
 zcs = [int(s) for s in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+so = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+rho = len(sys.argv) > 5
 n = (301, 301, 201)
 v = velocity(n)
 eps = (0.2 * (v - 1.5) / 4).astype(np.float32); dlt = (0.1 * (v - 1.5) / 4).astype(np.float32)
 th = (np.pi / 6 * (v - 1.5) / 4).astype(np.float32)
 ctx = J.get_context(0)
 dm = (0.05 * (1 / v ** 2) * np.sin(np.arange(n[2]) / 7.)[None, None, :]).astype(np.float32)
-gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=8, nbl=40, m=(1 / v ** 2).astype(np.float32),
+kw = {"rho": ((v + .5) / 2).astype(np.float32)} if rho else {}
+print("space order %d%s" % (so, ", density field" if rho else ""))
+gm = J.Model((0., 0., 0.), (25.,) * 3, n, space_order=so, nbl=40, m=(1 / v ** 2).astype(np.float32), **kw,
              epsilon=eps, delta=dlt, theta=th, phi=np.float32(np.pi / 8), dm=dm)
 dt = float(gm.critical_dt)
 q = ricker(nt, dt, 0.03)
