@@ -1,5 +1,6 @@
 // tti3d.cu -- single-pass 3-D TTI time step for sm_100a (space orders 4 and 8: a template on the
-// stencil radius R; constant density; the figures below are for R = 4).
+// stencil radius R; constant density or, RHO, a density field; the figures below are for R = 4,
+// constant density).
 // Replaces the Devito loop nest of tti_kernel (src/pysource/kernels.py:144-182 with the rotated
 // self-adjoint operator of FD_utils.py:24-105) -- and the two-pass form of flux3d.cu, whose six
 // flux fields cost 48 of its 119 B per grid point in HBM round trips and whose synchronous
@@ -44,7 +45,11 @@
 // registers, 8 warps) ran 0.85 ms: the tile warps' serial F + D chain at 0.2 IPC was the critical
 // path; (3) splitting the roles over 11 compute warps gave 0.72 ms.  The compile-time rotated
 // queues (ROT, option tti_fused=1) avoid 64 register moves per thread and plane but run slower
-// (0.80 ms) than the shifted queues (tti_fused=2, the default): 8x the code.
+// (0.80 ms) than the shifted queues (tti_fused=2, the default): 8x the code.  Round 2 bracketed the
+// design from both sides (profiles/r02_tti_tune.log): thinner threads (tti3d_h below: twice the warps,
+// +15 % shared-memory wavefronts) are 3-7 % slower, fatter ones (two rows per D thread: -7 %
+// wavefronts, half the D warps) 1.4-2.3x slower -- F and D are a two-stage pipeline one plane
+// apart, each stage a serial per-warp chain, under a shared-memory pipe that is 72 % busy.
 #include "tma_util.cuh"
 
 // Geometry of one CTA for stencil radius R = space_order / 2 (2 or 4).  The x layout works in groups
