@@ -667,11 +667,16 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
 {
     JUDI_REQUIRE(s.tmap && s.tmap_prev && s.tmap_m, "tensor maps missing");
     int v = variant_of(M);
-    if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2>(M, s); return; }
+    // so = 4: two producer warps (the u(t-1) / m tiles then run NP planes ahead instead of one) are
+    // 3 % faster than one (0.175 vs 0.180 ms on the C3 grid, profiles/r02_so16_sweep.log)
+    if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2, 2, false>(M, s); return; }
     if (M->r == 8) {
-        // so = 16: 80 x 32 haloed planes, 16-slot ring, one CTA per SM (0.33 ms/step on the C3
-        // grid; a 64 x 32 tile with a 10-slot ring and 512 consumers was slower: 0.41 ms)
-        launch_variant<8, 16, 16, 16, 4, 1>(M, s);
+        // so = 16: 80 x 32 haloed planes, 16-slot ring, one CTA per SM, two producer warps, shifted
+        // queue: 0.30 ms/step on the C3 grid.  The shared-memory pipe is ~90 % busy (23 LDS.128 per
+        // thread and plane: 880 wavefronts per ~990-cycle tile plane), which is why every other
+        // shape measures the same 0.33 ms as the one-producer form (profiles/r02_so16_sweep.log):
+        // 32 x 16 or 64 x 8 tiles at two CTAs per SM, a 12-slot ring, rotated vs shifted queue.
+        launch_variant<8, 16, 16, 16, 4, 1, 2, false>(M, s);
         return;
     }
     switch (v) {

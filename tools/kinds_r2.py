@@ -42,7 +42,7 @@ if "so" in which:
     v = velocity(n)
     src, rec = geom(n)
     for so in (4, 8, 16):
-        for kind in ("tti", "rho", "ttirho"):
+        for kind in ("iso", "tti", "rho", "ttirho"):
             if kind == "ttirho" and so == 16:
                 continue
             kw = dict(m=(1 / v ** 2).astype(np.float32))
@@ -56,6 +56,8 @@ if "so" in which:
             q = ricker(nt, dt, 0.008)
             dobs = np.zeros((nt, rec.shape[0]), dtype=np.float32)
             for opt, label in ((1, "single-pass"), (0, "two-pass")):
+                if kind == "iso" and not opt:
+                    continue
                 ctx.set_option("varc_fused" if kind == "rho" else "tti_fused", opt if kind == "rho" else (2 if opt else 0))
                 run("%s so%d %s" % (kind, so, label),
                     lambda: J.J_adjoint(gm, src, q, rec, dobs, return_obj=True, t_sub=2, snapshot_region="physical"))
