@@ -26,6 +26,25 @@ the stencil to better than ~15 %.  They are kept here as (1) an end-to-end regre
 JUDI-level driver (time_resample -> propagate -> time_resample, judiVector norm, remove_padding)
 on a published experiment, GPU against oracle at the north-star tolerances, and (2) a recorded,
 bounded deviation from the reference's printed values (asserted within 20 %).
+
+WHAT THE NOTEBOOK DOES PIN (added in the second session of round 2).
+(a) The amplitude factor cancels in max(J'r . wb_mask) / phi = 1 / (4 gscale phi): the notebook
+    gives 0.039343, the restatement 0.039222 (-0.31 %), i.e. the normalisation of J' relative to
+    the objective (dt weights, residual resampling, imaging-condition weight) agrees with what
+    Devito produced; asserted < 1 %.  With a layer of 320 cells phi and max(G) move by +1.4 % /
+    0.0 % while norm(dobs)^2 moves by -10 %: the first two are interior quantities, the third is
+    dominated by grazing paths along the layer.
+(b) Cell 37 plots dobs / d0 of the LAST receiver (x = 3735 m, z = 3750 m) for shots 1, 4, 8.  The
+    extrema of those six curves were read off the figure's pixels (tests/tools/nb03_read_figure.py,
+    run in the build container where /root/reference exists; +-3 ms, +-0.03 in amplitude): the
+    restatement puts every peak and trough of the five non-grazing traces within 4 ms of the
+    figure (one 2 ms sample is the reading accuracy) -- velocity, time axis, wavelet delay,
+    injection / interpolation timing and both resamplings agree with the Devito run -- and within
+    7 ... 16 % in amplitude (the notebook is LOWER).  The sixth trace (shot 8: source and receiver
+    both on the bottom edge, 3720 m along the layer) has +4.41 / -2.15 in the figure, +2.62 / -1.36
+    in the restatement and +4.74 / -3.41 in free space: the absorbing layer of the code that made
+    the notebook took far less out of a grazing wave than v4.1.7's damp_op profile does, which is
+    the part of the 11 % that belongs to the layer.
 """
 import numpy as np
 import pytest
@@ -35,6 +54,11 @@ from oracle import oracle as O
 NB_SCALE = 0.018069575143305386
 NB_PHI = 8.04513e+05
 NB_GSCALE = 3.15937e-5
+# (shot, model) -> (t_max [ms], max, t_min [ms], min) of the last receiver's trace, read from the
+# figure of cell 37 by tests/tools/nb03_read_figure.py
+NB_FIG37 = {(1, "true"): (3668, 1.75, 3585, -1.38), (1, "init"): (3734, 3.62, 3651, -2.51),
+            (4, "true"): (3070, 5.74, 2993, -3.45), (4, "init"): (3076, 4.13, 2993, -2.78),
+            (8, "init"): (2683, 4.41, 2605, -2.15)}
 
 N = (251, 251)
 D = (15., 15.)
@@ -105,6 +129,38 @@ def test_notebook_03_known_answers_oracle_f64():
     assert abs(gscale / 2.7179e-5 - 1) < 2e-4
     # recorded deviation from the values a 2021 JUDI printed (see the module docstring)
     assert max(abs(x) for x in dev) < 0.20
+    # the amplitude-free combination max(G wb_mask) / phi agrees with the notebook (docstring (a))
+    ratio = (1 / (4 * gscale * phi)) / (1 / (4 * NB_GSCALE * NB_PHI))
+    print("max(G)/phi vs notebook: %+.2f%%" % (100 * (ratio - 1)))
+    assert abs(ratio - 1) < 0.01
+
+
+def test_notebook_03_figure_traces_oracle():
+    """Kinematics and amplitudes of the traces the notebook plots in cell 37 (docstring (b))."""
+    m, m0 = _models()
+    zsrc, rec = _geometry()
+    q = O.ricker_wavelet(TN, DT, F0)
+    nt = q.shape[0]
+    for name, mm in (("true", m), ("init", m0)):
+        M = O.Model(ORG, D, N, space_order=8, nbl=40, m=mm, precision="f64")
+        dtc = np.float32(M.critical_dt)
+        ntc = int(np.floor(np.float32(TN) / dtc)) + 1
+        qc = O.time_resample(q, (0, DT, nt), (0, dtc, ntc))
+        for shot in (1, 4, 8):
+            src = np.array([[D[0], zsrc[shot - 1]]], np.float32)
+            r, _ = O.forward_rec(M, src, qc, rec)
+            tr = O.time_resample(r, (0, dtc, r.shape[0]), (0, DT, nt))[:, -1]
+            if (shot, name) not in NB_FIG37:
+                continue
+            tmax, vmax, tmin, vmin = NB_FIG37[(shot, name)]
+            got = (float(DT) * tr.argmax(), tr.max(), float(DT) * tr.argmin(), tr.min())
+            print("shot %d %s: figure %s, restatement (%.0f, %.2f, %.0f, %.2f)"
+                  % ((shot, name, NB_FIG37[(shot, name)]) + got))
+            if shot == 8:
+                # grazing path along the absorbing layer: recorded, not asserted (docstring)
+                continue
+            assert abs(got[0] - tmax) <= 4 and abs(got[2] - tmin) <= 4
+            assert 0.80 < vmax / got[1] < 1.0 and 0.80 < vmin / got[3] < 1.0
 
 
 @pytest.mark.gpu
