@@ -51,7 +51,12 @@ struct TmaArgs {
 // (u-, m, ul-, dm) in one tile slot, and the Born source -dm (u+ - 2u + u-) goes from group 0 to
 // group 1 through a shared-memory tile ring guarded by per-warp mbarriers.  32 B per grid point
 // of HBM traffic instead of the 44 B of two launches that exchange delta through HBM.
-template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1, bool DUAL = false>
+// YR > 0: Y role.  NYT = tile points / (4 YR) extra threads each own YR consecutive rows of one
+// 4-point group and evaluate the y part of the Laplacian of the centre plane for all of them from
+// ONE window of YR + 2R row vectors (so = 16: 20 LDS.128 per 4 rows instead of 16 per row); the
+// result reaches the consumer threads through a small shared-memory ring (one LDS.128).  Same
+// operations in the same order as the consumer's own y loop: bit-identical wavefields.
+template <int R, int TXT, int TYT, int NS, int NP, int NPW = 1, bool DUAL = false, int YR = 0>
 struct TmaCfg {
     static constexpr int HR = ((R + 3) / 4) * 4;  // x halo in shared memory (float4 aligned)
     static constexpr int TX = 4 * TXT, TY = TYT;
@@ -64,10 +69,15 @@ struct TmaCfg {
     static constexpr int ND = 2;                  // delta-exchange slots (DUAL)
     static constexpr int USTRIDE = NG * SLOT;     // floats per ring slot (u [, ul] plane)
     static constexpr int PSTRIDE = 2 * NG * PSLOT;  // floats per tile slot (u-, m [, ul-, dm])
-    static constexpr int NTHREADS = NG * NCONS + 32 * NPW;   // + producer warp(s)
-    static constexpr int NBAR = 2 * NS + 2 * NP + (DUAL ? 2 * ND * (NCONS / 32) : 0);
+    static constexpr int NYT = YR ? NCONS / YR : 0;   // Y-role threads
+    static constexpr int NYW = NYT / 32;
+    static constexpr int NY = 3;                      // y-sum ring slots
+    static constexpr int NTHREADS = NG * NCONS + 32 * NPW + NYT;   // + producer warp(s) [+ Y warps]
+    static constexpr int NBAR = 2 * NS + 2 * NP + (DUAL ? 2 * ND * (NCONS / 32) : 0) + (YR ? 2 * NY : 0);
     static constexpr size_t SMEM = (size_t)NS * USTRIDE * 4 + (size_t)NP * PSTRIDE * 4 +
-                                   (DUAL ? (size_t)ND * PSLOT * 4 : 0) + NBAR * 8 + 128;
+                                   (DUAL ? (size_t)ND * PSLOT * 4 : 0) + (YR ? (size_t)NY * PSLOT * 4 : 0) +
+                                   NBAR * 8 + 128;
+    static_assert(YR == 0 || (!DUAL && TYT % YR == 0 && NYT % 32 == 0), "Y role: whole warps, no DUAL");
 };
 
 // FUSE is a compile-time mask of what rides on the step, so that each flavour of launch carries
@@ -83,11 +93,11 @@ struct TmaMaps {   // tensor maps of one launch (kernel parameter, __grid_consta
     CUtensorMap U2, P2, D;    // DUAL: haloed ul(t), tile ul(t-1), tile dm
 };
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT, bool DUAL>
-__global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT, bool DUAL, int YR = 0>
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW + (YR ? TXT * TYT / YR : 0), MINB)
     acoustic3d_tma(const __grid_constant__ TmaMaps tm, const TmaArgs a)
 {
-    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL> C;
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL, YR> C;
     constexpr int HR = C::HR, TX = C::TX, TY = C::TY, PX = C::PX, PY = C::PY, SLOT = C::SLOT;
     constexpr int PSLOT = C::PSLOT, NQ = C::NQ, NCW = C::NCONS / 32;
     constexpr int NG = C::NG, ND = C::ND, USTRIDE = C::USTRIDE, PSTRIDE = C::PSTRIDE;
@@ -100,12 +110,16 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
     float *ringU = (float *)(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float *ringP = ringU + NS * USTRIDE;              // [NP][2 NG][PSLOT]: u(t-1), m [, ul(t-1), dm]
     float *ringD = ringP + NP * PSTRIDE;              // DUAL: [ND][PSLOT] delta of the background
-    uint64_t *fullU = (uint64_t *)(ringD + (DUAL ? ND * PSLOT : 0));
+    [[maybe_unused]] float *ringY = ringD + (DUAL ? ND * PSLOT : 0);   // YR: [NY][PSLOT] y sums
+    uint64_t *fullU = (uint64_t *)(ringY + (YR ? C::NY * PSLOT : 0));
     uint64_t *emptyU = fullU + NS;
     uint64_t *fullP = emptyU + NS;
     uint64_t *emptyP = fullP + NP;
     [[maybe_unused]] uint64_t *fullD = emptyP + NP;   // DUAL: [ND][NCW], one per consumer warp
     [[maybe_unused]] uint64_t *emptyD = fullD + ND * NCW;
+    [[maybe_unused]] uint64_t *fullY = emptyD + (DUAL ? ND * NCW : 0);   // YR: [NY]
+    [[maybe_unused]] uint64_t *emptyY = fullY + C::NY;
+    constexpr int NYW = C::NYW, NY = C::NY;
 
     const Grid &g = a.g;
     const Coefs &cf = a.cf;
@@ -116,7 +130,9 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
     const int total = nzc + 2 * R;  // u planes this CTA consumes: z0-R .. z1-1+R
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NG * NCW); }
+        for (int s = 0; s < NS; s++) { mbar_init(&fullU[s], 1); mbar_init(&emptyU[s], NG * NCW + NYW); }
+        if (YR)
+            for (int s = 0; s < NY; s++) { mbar_init(&fullY[s], NYW); mbar_init(&emptyY[s], NCW); }
         for (int s = 0; s < NP; s++) { mbar_init(&fullP[s], 1); mbar_init(&emptyP[s], NG * NCW); }
         if (DUAL)
             for (int s = 0; s < ND * NCW; s++) { mbar_init(&fullD[s], 1); mbar_init(&emptyD[s], 1); }
@@ -124,6 +140,54 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
     }
     __syncthreads();
 
+    if (YR > 0 && threadIdx.x >= NG * C::NCONS + 32 * NPW) {
+        // ===== Y warps: y part of the Laplacian of every centre plane, YR rows per thread ========
+        constexpr int YRR = YR > 0 ? YR : 1;
+        const int yid = (int)threadIdx.x - (NG * C::NCONS + 32 * NPW);
+        const int ytx = yid % TXT, yr0 = (yid / TXT) * YRR;
+        const int ylane = threadIdx.x & 31;
+        const int win = yr0 * PX + HR + 4 * ytx;        // first row of the window in a u slot
+        const int yout = yr0 * TX + 4 * ytx;
+        // planes 0 .. R-1 of the chunk are never centres (the consumers release them unread too)
+        if (ylane == 0)
+            for (int j = 0; j < R && j < total; j++) mbar_arrive(&emptyU[j % NS]);
+        for (int i = 0; i < nzc; i++) {
+            const int j = i + R, s = j % NS;
+            mbar_wait(&fullU[s], (uint32_t)((j / NS) & 1));
+            const float *col = ringU + s * USTRIDE + win;
+            float4 w[YRR + 2 * R];
+#pragma unroll
+            for (int k = 0; k < YRR + 2 * R; k++) w[k] = *(const float4 *)(col + k * PX);
+            float4 o[YRR];
+#pragma unroll
+            for (int e = 0; e < YRR; e++) {
+                f2 ly0, ly1;
+                {
+                    const float4 p = w[e + R + 1], m_ = w[e + R - 1];
+                    ly0 = mul2s(cf.cy[1], add2(lo2(p), lo2(m_)));
+                    ly1 = mul2s(cf.cy[1], add2(hi2(p), hi2(m_)));
+                }
+#pragma unroll
+                for (int k = 2; k <= R; k++) {
+                    const float4 p = w[e + R + k], m_ = w[e + R - k];
+                    ly0 = fma2s(cf.cy[k], add2(lo2(p), lo2(m_)), ly0);
+                    ly1 = fma2s(cf.cy[k], add2(hi2(p), hi2(m_)), ly1);
+                }
+                o[e] = cat4(ly0, ly1);
+            }
+            // the plane is dead for this warp (its values are in registers)
+            __syncwarp();
+            if (ylane == 0) mbar_arrive(&emptyU[s]);
+            const int sy = i % NY;
+            if (i >= NY) mbar_wait(&emptyY[sy], (uint32_t)(((i / NY) - 1) & 1));
+            float *yo = ringY + sy * PSLOT + yout;
+#pragma unroll
+            for (int e = 0; e < YRR; e++) *(float4 *)(yo + e * TX) = o[e];
+            __syncwarp();
+            if (ylane == 0) mbar_arrive(&fullY[sy]);
+        }
+        return;
+    }
     if (threadIdx.x >= NG * C::NCONS) {
         // ===== producer warp(s): one lane issues the TMA loads of this CTA =====================
         // NPW == 1: a single lane issues both streams; NPW == 2: warp 0 streams the haloed u(t)
@@ -322,7 +386,15 @@ __global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW, MINB)
                     }
                 }
                 f2 ly0, ly1;
-                {
+                if (YR > 0) {
+                    // the Y warps have the y sums of this plane (or will in a moment)
+                    const int sy = i % NY;
+                    mbar_wait(&fullY[sy], (uint32_t)((i / NY) & 1));
+                    const float4 t = *(const float4 *)(ringY + sy * PSLOT + sm_tile);
+                    ly0 = lo2(t); ly1 = hi2(t);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&emptyY[sy]);
+                } else {
                     const float *ccol = cen + sm_own;
                     {
                         const float4 p = *(const float4 *)(ccol + PX), m_ = *(const float4 *)(ccol - PX);
@@ -546,12 +618,12 @@ void tma3d_encode(const judi_model *M, const float *base, CUtensorMap *halo_map,
 }
 
 template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW, bool ROT, int FUSE,
-          bool DUAL = false>
+          bool DUAL = false, int YR = 0>
 static void launch_fused(const judi_model *M, const StepArgs &s)
 {
-    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL> C;
+    typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL, YR> C;
     judi_ctx *ctx = M->ctx;
-    auto kern = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, FUSE, NPW, ROT, DUAL>;
+    auto kern = acoustic3d_tma<R, TXT, TYT, NS, NP, MINB, FUSE, NPW, ROT, DUAL, YR>;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -613,10 +685,10 @@ static int fuse_mask(const StepArgs &s)
            (s.f.wrec ? F_WREC : 0) | ((s.qsrc && s.sfield) ? F_QISIC : 0);
 }
 
-template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true>
+template <int R, int TXT, int TYT, int NS, int NP, int MINB, int NPW = 1, bool ROT = true, int YR = 0>
 static void launch_variant(const judi_model *M, const StepArgs &s)
 {
-#define FUSE_CASE(F) case F: launch_fused<R, TXT, TYT, NS, NP, MINB, NPW, ROT, F>(M, s); return;
+#define FUSE_CASE(F) case F: launch_fused<R, TXT, TYT, NS, NP, MINB, NPW, ROT, F, false, YR>(M, s); return;
     switch (fuse_mask(s)) {
         FUSE_CASE(0)
         FUSE_CASE(F_SNAP)
@@ -676,7 +748,13 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
         // thread and plane: 880 wavefronts per ~990-cycle tile plane), which is why every other
         // shape measures the same 0.33 ms as the one-producer form (profiles/r02_so16_sweep.log):
         // 32 x 16 or 64 x 8 tiles at two CTAs per SM, a 12-slot ring, rotated vs shifted queue.
-        launch_variant<8, 16, 16, 16, 4, 1, 2, false>(M, s);
+        // Y role (ctx option "tile" 32 / 34: 2 / 4 rows per Y thread): the 16 y loads of every
+        // consumer thread become one, the Y warps read 18 / 20 row vectors per 2 / 4 rows
+        switch (M->ctx->opt_tile) {
+        case 32: launch_variant<8, 16, 16, 16, 4, 1, 2, false, 2>(M, s); break;
+        case 34: launch_variant<8, 16, 16, 16, 4, 1, 2, false, 4>(M, s); break;
+        default: launch_variant<8, 16, 16, 16, 4, 1, 2, false>(M, s); break;
+        }
         return;
     }
     switch (v) {
