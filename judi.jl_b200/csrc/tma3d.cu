@@ -69,7 +69,7 @@ struct TmaCfg {
     static constexpr int ND = 2;                  // delta-exchange slots (DUAL)
     static constexpr int USTRIDE = NG * SLOT;     // floats per ring slot (u [, ul] plane)
     static constexpr int PSTRIDE = 2 * NG * PSLOT;  // floats per tile slot (u-, m [, ul-, dm])
-    static constexpr int NYT = YR ? NCONS / YR : 0;   // Y-role threads
+    static constexpr int NYT = (YR > 0) * (NCONS / (YR > 0 ? YR : 1));   // Y-role threads
     static constexpr int NYW = NYT / 32;
     static constexpr int NY = 3;                      // y-sum ring slots
     static constexpr int NTHREADS = NG * NCONS + 32 * NPW + NYT;   // + producer warp(s) [+ Y warps]
@@ -94,7 +94,7 @@ struct TmaMaps {   // tensor maps of one launch (kernel parameter, __grid_consta
 };
 
 template <int R, int TXT, int TYT, int NS, int NP, int MINB, int FUSE, int NPW, bool ROT, bool DUAL, int YR = 0>
-__global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW + (YR ? TXT * TYT / YR : 0), MINB)
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * TXT * TYT + 32 * NPW + (YR > 0) * (TXT * TYT / (YR > 0 ? YR : 1)), MINB)
     acoustic3d_tma(const __grid_constant__ TmaMaps tm, const TmaArgs a)
 {
     typedef TmaCfg<R, TXT, TYT, NS, NP, NPW, DUAL, YR> C;
@@ -744,17 +744,18 @@ void tma3d_step(const judi_model *M, const StepArgs &s)
     if (M->r == 2) { launch_variant<2, 16, 16, 8, 4, 2, 2, false>(M, s); return; }
     if (M->r == 8) {
         // so = 16: 80 x 32 haloed planes, 16-slot ring, one CTA per SM, two producer warps, shifted
-        // queue: 0.30 ms/step on the C3 grid.  The shared-memory pipe is ~90 % busy (23 LDS.128 per
-        // thread and plane: 880 wavefronts per ~990-cycle tile plane), which is why every other
-        // shape measures the same 0.33 ms as the one-producer form (profiles/r02_so16_sweep.log):
-        // 32 x 16 or 64 x 8 tiles at two CTAs per SM, a 12-slot ring, rotated vs shifted queue.
-        // Y role (ctx option "tile" 32 / 34: 2 / 4 rows per Y thread): the 16 y loads of every
-        // consumer thread become one, the Y warps read 18 / 20 row vectors per 2 / 4 rows
-        switch (M->ctx->opt_tile) {
-        case 32: launch_variant<8, 16, 16, 16, 4, 1, 2, false, 2>(M, s); break;
-        case 34: launch_variant<8, 16, 16, 16, 4, 1, 2, false, 4>(M, s); break;
-        default: launch_variant<8, 16, 16, 16, 4, 1, 2, false>(M, s); break;
-        }
+        // queue: 0.30 ms/step on the C3 grid; every other shape measures the same 0.33 ms as the
+        // one-producer form (profiles/r02_so16_sweep.log): 32 x 16 or 64 x 8 tiles at two CTAs per
+        // SM, a 12-slot ring, rotated vs shifted queue.
+        // Y role (ctx option "tile" 34: Y warps, 4 rows per thread) -- measured, not the default: the
+        // consumers' 16 y loads become one and the shared-memory wavefronts of a plane drop by 36 %
+        // (ncu: data pipe 65 % -> 41 % busy), results bit-identical, and the step is 5 % SLOWER
+        // (0.318 vs 0.302 ms): this kernel is bound by instruction issue and latency at 2.5 warps per
+        // scheduler (161 registers, one CTA per SM, 56 % issue-active, 19 % of the instructions are
+        // register-queue moves), not by the shared-memory pipe; a tile ring of 6 - 8 slots instead
+        // of 4 is 6 - 10 % slower too (profiles/r02_so16_yrole.md).
+        if (M->ctx->opt_tile == 34) launch_variant<8, 16, 16, 16, 4, 1, 2, false, 4>(M, s);
+        else launch_variant<8, 16, 16, 16, 4, 1, 2, false>(M, s);
         return;
     }
     switch (v) {
