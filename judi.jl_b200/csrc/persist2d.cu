@@ -13,6 +13,7 @@
 // Born source and the imaging condition are post-injection by construction.
 #include "common.cuh"
 #include "propagate.h"
+#include "tma_util.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -168,6 +169,10 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
         if (a.dir > 0) { if (++ph == a.t_sub) { ph = 0; sidx += a.slot; } }
         else if (ph == 0) { ph = a.t_sub - 1; sidx -= a.slot; }
         else ph--;
+        // the snapshot the NEXT imaging step reads (sidx already points at it): its lines are pulled
+        // into L2 while this step runs -- the adjoint sweep reads the whole pool from DRAM, one
+        // dependent load per tile visit (profiles/r02_p2d_resident_experiment.md)
+        const float *usnap_n = (usnap_t && t != a.t1 && sidx >= 0) ? a.usnap + sidx : nullptr;
         // ---- stencil + injection + fused extras, tile by tile --------------------------------
         if constexpr (VEC) {
             constexpr int NV = (R + 3) / 4, HRV = 4 * NV, NW = 4 + 2 * HRV;
@@ -284,6 +289,7 @@ __device__ __forceinline__ void acoustic2d_body(const P2Args &a, const int lb, c
                             *(float4 *)(a.illum + ri) = I4;
                         }
                         if (usnap_t) {
+                            if (usnap_n) prefetch_l2(usnap_n + ri);
                             const float4 us4 = *(const float4 *)(usnap_t + ri);
                             float4 G4 = *(float4 *)(a.grad + ri);
                             G4.x -= a.gcoef * a.irho_c * us4.x * dl[0]; G4.y -= a.gcoef * a.irho_c * us4.y * dl[1];
