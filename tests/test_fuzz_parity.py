@@ -16,7 +16,7 @@ import pytest
 from conftest import rel_l2
 from oracle import oracle as O
 
-NCASES_3D, NCASES_2D = 16, 12
+NCASES_3D, NCASES_2D = 12, 12
 
 
 def make_case(seed, ndim):
