@@ -135,7 +135,9 @@ int judi_ctx_stencil_stats(judi_ctx *ctx, double *ms, long long *launches, doubl
 #define JUDI_NUM_KINDS 4
 int judi_ctx_stencil_stats_kind(judi_ctx *ctx, int kind, double *ms, long long *launches);
 int judi_ctx_reset_stats(judi_ctx *ctx);
-/* tuning knobs: "acoustic3d_kernel" (0 generic, 1 TMA z-marching), "zchunks", ... */
+/* tuning knobs: "acoustic3d_kernel" (0 generic, 1 TMA z-marching), "zchunks", "tile", ...; the
+ * same "key=value,key=value" list is read from the environment variable JUDI_B200_OPTIONS when a
+ * context is created (judi_ctx_create fails on an unknown key) */
 int judi_ctx_set_option(judi_ctx *ctx, const char *key, int value);
 /* Page-lock a caller-owned host array (a Julia Array that outlives many shots: the model's m, the
  * observed data, the gradient the per-shot results are summed into) so that the copies of every

@@ -58,6 +58,25 @@ judi_ctx *judi_ctx_create(int device)
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) ctx->encode_tiled = fn;
     else cudaGetLastError();
+    // tuning switches from the environment, e.g. JUDI_B200_OPTIONS="tile=6,zchunks=8" (the keys of
+    // judi_ctx_set_option): lets a caller that does not own the context (bench.py, a Julia session)
+    // select a kernel variant without a code change
+    if (const char *env = getenv("JUDI_B200_OPTIONS")) {
+        std::string str(env);
+        size_t pos = 0;
+        while (pos < str.size()) {
+            size_t end = str.find(',', pos);
+            if (end == std::string::npos) end = str.size();
+            const std::string kv = str.substr(pos, end - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && judi_ctx_set_option(ctx, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)) != 0) {
+                std::string msg = std::string("JUDI_B200_OPTIONS: ") + judi_last_error();
+                judi_ctx_destroy(ctx);
+                throw JudiError(msg);
+            }
+            pos = end + 1;
+        }
+    }
     return ctx;
     API_END(nullptr)
 }
