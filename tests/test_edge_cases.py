@@ -93,3 +93,30 @@ def test_ragged_multishot_list_matches_the_sum_of_single_shots():
     f, g = J.objectives.fwi_objective(gm, shots)
     assert abs(float(f) - fs) <= 1e-4 * abs(fs)
     assert rel_l2(g, O.remove_padding(gs, om.padsizes)) < 1e-3
+
+
+def test_so16_y_role_variant_is_bit_identical():
+    """acoustic3d_tma at so = 16 with the y part of the Laplacian computed by the Y warps (ctx option
+    tile = 34, profiles/r02_so16_yrole.md): same operations in the same order, so shot record and
+    gradient must equal the default instantiation bit for bit (odd grid shape: partial tiles)."""
+    import judi_jl_b200 as J
+    args = model_args("iso", 3, 16, n=(75, 41, 38), nbl=12)
+    src, rec = geometry(args)
+    ctx = J.get_context(0)
+    out = []
+    try:
+        for tile in (8, 34):
+            ctx.set_option("tile", tile)
+            gm = J.Model(**args)
+            dt = float(gm.critical_dt)
+            q = O.ricker_wavelet(89 * dt, dt, 0.03)[:90]
+            d, _ = J.forward_rec(gm, src, q, rec)
+            f, g, _, _ = J.J_adjoint(gm, src, q, rec, (0.5 * d).astype(np.float32), return_obj=True, t_sub=2)
+            out.append((d, np.array(g), float(f)))
+    finally:
+        ctx.set_option("tile", 8)
+    assert np.linalg.norm(out[0][0]) > 0
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+    om = O.Model(precision="f32", **args)
+    do, _ = O.forward_rec(om, src, q, rec)
+    assert rel_l2(out[1][0], do) < 1e-4
