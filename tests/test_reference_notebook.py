@@ -45,6 +45,14 @@ WHAT THE NOTEBOOK DOES PIN (added in the second session of round 2).
     in the restatement and +4.74 / -3.41 in free space: the absorbing layer of the code that made
     the notebook took far less out of a grazing wave than v4.1.7's damp_op profile does, which is
     the part of the 11 % that belongs to the layer.
+(c) Third session: `tests/tools/nb03_abc_variants.py` is a second, independent restatement of the
+    forward experiment in plain numpy (no oracle C code).  With v4.1.7's boundary term it gives
+    scale = 0.0160153, the oracle's value to seven digits (asserted below); with the older
+    mask-type layer `u+ = damp (2u - damp u- + dt^2/m L)` (layer of nbl cells, dt = 0.42 h/vmax)
+    it gives -10.0 %, with the profile not divided by h -22 %: the boundary formulation of the
+    older code generations does not explain the deviation either.  Summary of the three
+    quantities: phi and max(G) share one factor (notebook / restatement = 0.858 / 0.860, also
+    with a 320-cell layer, i.e. in free space), norm(dobs)^2 has 0.786.
 """
 import numpy as np
 import pytest
@@ -161,6 +169,21 @@ def test_notebook_03_figure_traces_oracle():
                 continue
             assert abs(got[0] - tmax) <= 4 and abs(got[2] - tmin) <= 4
             assert 0.80 < vmax / got[1] < 1.0 and 0.80 < vmin / got[3] < 1.0
+
+
+def test_notebook_03_independent_numpy_restatement():
+    """A second restatement of the forward experiment (plain numpy, its own Laplacian, layer,
+    injection and interpolation; tests/tools/nb03_abc_variants.py) gives the oracle's `scale`."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "nb03_abc_variants", os.path.join(os.path.dirname(__file__), "tools", "nb03_abc_variants.py"))
+    V = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(V)
+    m, _ = _models()
+    scale = V.scale_of(V.run(m, abc="damp417"))
+    print("numpy restatement: scale %.7f" % scale)
+    assert abs(scale - 0.0160153) < 2e-6
 
 
 @pytest.mark.gpu
