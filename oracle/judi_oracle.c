@@ -108,7 +108,7 @@ static void fornberg(double z, const double *x, int n, int m, double *c /* (m+1)
 static void make_weights(ogrid *g)
 {
     int r = g->r;
-    double x[2 * MAXR + 1], c[3 * (2 * MAXR + 1)];
+    double x[2 * MAXR + 1] = {0}, c[3 * (2 * MAXR + 1)];
     int n = 2 * r + 1;
     for (int i = 0; i < n; i++) x[i] = i - r;
     fornberg(0.0, x, n, 2, c);

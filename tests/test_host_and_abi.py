@@ -149,3 +149,126 @@ def test_out_of_scope_entry_points_fail_loudly():
                  "forward_wf_src_norec", "adjoint_w", "born_rec", "born_rec_w", "J_adjoint",
                  "wri_func"):
         assert callable(getattr(J.interface, name))
+
+
+# ---- the Julia `ccall` twin (julia/B200Backend.jl) against the header ---------------------------
+def _header_prototypes():
+    """name -> (return class, [argument classes]) from include/judi_b200.h; a class is one of
+    'int', 'float', 'size_t', 'longlong', 'ptr', 'void'."""
+    txt = open(os.path.join(ROOT, "include", "judi_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+
+    def cls(decl):
+        decl = decl.strip()
+        if "*" in decl or "[" in decl or "judi_misfit_fn" in decl:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned|struct)\b", "", decl).split()
+        t = base[0] if base else "void"
+        return {"int": "int", "float": "float", "size_t": "size_t", "long": "longlong",
+                "void": "void", "double": "double"}[t]
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(judi_[a-z0-9_A-Z]+)\s*\(([^;{}]*?)\)\s*;", txt, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        if name == "judi_misfit_fn" or "typedef" in ret:
+            continue
+        args = [a for a in (x.strip() for x in args.replace("\n", " ").split(",")) if a and a != "void"]
+        protos[name] = (cls(ret + (" *" if ret.strip().endswith("*") else "")), [cls(a) for a in args])
+    return protos
+
+
+_JL_CLASS = {"Cint": "int", "Cfloat": "float", "Csize_t": "size_t", "Clonglong": "longlong",
+             "Cvoid": "void", "Cstring": "ptr", "Cdouble": "double"}
+
+
+def _julia_ccalls():
+    """[(name, return class, [argument classes], number of values passed)] of every ccall in
+    julia/B200Backend.jl."""
+    src = open(os.path.join(ROOT, "julia", "B200Backend.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    out = []
+    for m in re.finditer(r"ccall\(\(:(judi_[a-z0-9_A-Z]+), LIB\)\s*,", src):
+        # balanced scan of the rest of the call
+        i, depth, parts, cur = m.end(), 1, [], ""
+        while depth > 0:
+            c = src[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            if c == "," and depth == 1:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                cur += c
+            i += 1
+        parts.append(cur.strip())
+        ret, argt, vals = parts[0], parts[1], parts[2:]
+        assert argt.startswith("(") and argt.endswith(")"), (m.group(1), argt)
+        inner = argt[1:-1].strip()
+        types, d, cur = [], 0, ""
+        for c in inner:
+            if c == "{":
+                d += 1
+            elif c == "}":
+                d -= 1
+            if c == "," and d == 0:
+                types.append(cur.strip())
+                cur = ""
+            else:
+                cur += c
+        if cur.strip():
+            types.append(cur.strip())
+
+        def jcls(t):
+            return "ptr" if t.startswith(("Ptr{", "Ref{")) else _JL_CLASS[t]
+        out.append((m.group(1), jcls(ret), [jcls(t) for t in types], len([v for v in vals if v])))
+    return out
+
+
+def test_julia_ccall_twin_matches_the_header():
+    """Every ccall of julia/B200Backend.jl (the binding INTEGRATION.md hands to a JUDI maintainer;
+    no Julia in this image, so it cannot be executed here) names an exported symbol and passes the
+    number and kind (int / float / size_t / pointer) of arguments the header declares."""
+    protos = _header_prototypes()
+    assert set(protos) == set(_header_symbols())
+    calls = _julia_ccalls()
+    assert len(calls) >= 20
+    for name, ret, types, nvals in calls:
+        assert name in protos, "%s is not declared in include/judi_b200.h" % name
+        pret, pargs = protos[name]
+        assert ret == pret, "%s: Julia return type class %s, header %s" % (name, ret, pret)
+        assert types == pargs, "%s: Julia argument types %s, header %s" % (name, types, pargs)
+        assert nvals == len(types), "%s: %d values for %d declared arguments" % (name, nvals, len(types))
+    # the entry points of the hot path all have a twin
+    named = {c[0] for c in calls}
+    for must in ("judi_model_create", "judi_forward_rec", "judi_born_rec", "judi_J_adjoint",
+                 "judi_fg_multishot", "judi_fg_multishot_reduced", "judi_comm_init",
+                 "judi_forward_rec_w", "judi_adjoint_w", "judi_born_rec_w", "judi_forward_wf_src",
+                 "judi_forward_wf_src_norec", "judi_remove_padding", "judi_time_resample"):
+        assert must in named, must
+
+
+def test_ctypes_binding_matches_the_header_prototypes():
+    """Argument count and int / float / pointer class of every ctypes signature against the header."""
+    from judi_jl_b200 import _lib
+    protos = _header_prototypes()
+
+    def ccls(t):
+        if t is None:
+            return "void"
+        if t in (ctypes.c_int,):
+            return "int"
+        if t is ctypes.c_float:
+            return "float"
+        if t is ctypes.c_size_t:
+            return "size_t"
+        if t is ctypes.c_longlong:
+            return "longlong"
+        return "ptr"
+    for name, (res, args) in _lib.SIGNATURES.items():
+        pret, pargs = protos[name]
+        assert ccls(res) == pret, (name, res, pret)
+        assert [ccls(a) for a in args] == pargs, (name, [ccls(a) for a in args], pargs)
