@@ -38,6 +38,8 @@ judi_ctx *judi_ctx_create(int device)
         throw JudiError(std::string("libjudi_b200 is built for sm_100a (B200) only; found ") +
                         prop.name);
     judi_ctx *ctx = new judi_ctx();
+    // a failure below must not leak the half-built context
+    struct Guard { judi_ctx *c; ~Guard() { if (c) judi_ctx_destroy(c); } } guard{ctx};
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -70,13 +72,12 @@ judi_ctx *judi_ctx_create(int device)
             const std::string kv = str.substr(pos, end - pos);
             const size_t eq = kv.find('=');
             if (eq != std::string::npos && judi_ctx_set_option(ctx, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)) != 0) {
-                std::string msg = std::string("JUDI_B200_OPTIONS: ") + judi_last_error();
-                judi_ctx_destroy(ctx);
-                throw JudiError(msg);
+                throw JudiError(std::string("JUDI_B200_OPTIONS: ") + judi_last_error());
             }
             pos = end + 1;
         }
     }
+    guard.c = nullptr;
     return ctx;
     API_END(nullptr)
 }
@@ -84,13 +85,13 @@ judi_ctx *judi_ctx_create(int device)
 void judi_ctx_destroy(judi_ctx *ctx)
 {
     if (!ctx) return;
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     comm_destroy(ctx);
     if (ctx->red_p) cudaFreeAsync(ctx->red_p, ctx->stream);
     if (ctx->arena_p) cudaFree(ctx->arena_p);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->own_pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
