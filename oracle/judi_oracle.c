@@ -12,6 +12,12 @@
  * import stub; tests/golden/make_reference_golden.py, tests/test_reference_golden.py): the
  * point-wise algebra of this file -- tti_flux_point (FD_utils.sa_tti), ic_point / linsrc_point
  * (sensitivity.py ic_dict / ls_dict) -- plus, in oracle.py, critical dt, padsizes, Loss, nsave.
+ * CHAINED to two constants Devito's own test-suite asserts for its acoustic example (norm(rec) =
+ * 459.1678, 369.955 with a free surface; recalled from Devito's public repository, not under
+ * /root/reference): tests/test_devito_known_answer.py -- a numpy restatement with this file's
+ * conventions reproduces them to 4e-4 / 7e-4 and equals this file's forward shot record to 3.5e-8
+ * on the same problem.  That covers the acoustic Laplacian, time loop, injection and
+ * interpolation; the staggered (TTI / density-field) stencils and the gradients stay unpinned.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (judi.jl_b200/csrc) never links or calls it.
