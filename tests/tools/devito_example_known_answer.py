@@ -15,6 +15,11 @@ in the reference's Python: the centred `.laplace` weights, the one-sided `u.dt` 
 `src dt^2 / m` into the new level with (bi/tri)linear weights, interpolation of the current level,
 and the damping profile Devito's own example Model builds (layer of nbl cells).
 
+Result: 459.339 (+0.037 %) and, with the free surface, 370.217 (+0.071 %).  The residual is inside
+the spread of the fp32 accumulation of Devito's `norm` builtin (it sums rec^2 in the record's own
+dtype): a sequential fp32 sum of the SAME numpy record gives 459.063 / 369.738, two partial sums
+459.268 / 370.107 -- Devito's constants lie between the two in both cases.
+
     python tests/tools/devito_example_known_answer.py
 """
 import itertools
