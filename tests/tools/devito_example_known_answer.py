@@ -5,7 +5,7 @@ Devito (the third-party dependency the reference's arithmetic lives in; absent f
 pins its own acoustic example in its test-suite: `examples/seismic/acoustic/acoustic_example.py`
 `run()` with the defaults shape = (50, 50, 50), spacing = 20 m, tn = 1000 ms, space_order = 4,
 nbl = 40, preset 'layers-isotropic' (3 layers, 1.5 ... 3.5 km/s), kernel OT2, and
-`tests/test_..::test_isoacoustic` asserts `norm(rec) == 459.1678` (rtol 1e-3) -- recalled from
+its `test_isoacoustic` (same file) asserts `norm(rec) == 459.1678` (rtol 1e-3) -- recalled from
 Devito's public repository, NOT present under /root/reference, so this script is evidence about
 the `[dv]` assumptions, not a parity test of the reference's own files.
 
