@@ -1,0 +1,211 @@
+"""A second Devito-produced known answer, this one through the STAGGERED operator
+`div(b * grad(p, shift=.5), shift=-.5)` -- the very expression the reference uses for models with
+a density field (`FD_utils.laplacian`, FD_utils.py:11-21) and, with the rotation in between, for
+TTI (`FD_utils.py:84-105`).
+
+Devito pins its visco-acoustic example in `examples/seismic/viscoacoustic/viscoacoustic_example.py`:
+`run()` with the defaults (2-D 50 x 50 cells of 20 m, nbl = 40, space_order = 4, tn = 1000 ms,
+preset 'layers-viscoacoustic': three layers 1.5 ... 3.5 km/s, qp = 3.516 (1000 vp)^2.2 1e-6,
+b = 1 / (0.31 (1000 vp)^0.25), Ricker 10 Hz one cell deep, 50 receivers two cells deep), kernel
+'sls', time_order 2, must give `norm(rec) = 684.385` (atol 1e-2) -- recalled from Devito's public
+repository; Devito is not in this image and the number is not under /root/reference.
+
+Devito's scheme (Bai et al. 2014, `sls_2nd_order`, mask-type layer `damp = 1 - profile`):
+    L   = div(b grad(p, shift=.5), shift=-.5)          4-point staggered stencils, b at the NODE
+    r+  = damp (r + dt ((tt / t_s) rho L - r / t_s))                      forward Euler
+    p+  = damp (2 p - damp p- + dt^2 bm ((1 + tt) L - b r+)),  bm = rho vp^2
+    p+ += src dt^2 / m  (bilinear);   rec[t] = interp(p[t]);   loop 1 .. nt-2
+
+Result of this restatement: **684.3899** (Devito 684.385: +7e-6, inside Devito's atol).  What the
+constant discriminates (Devito's acceptance window is 684.375 ... 684.395):
+    b averaged to the half node instead of node-valued        684.4526   rejected
+    centred time difference for the memory variable           685.5075   rejected
+    single mask (no `damp p-`)                                687.5957   rejected
+    receivers read the new level / loop runs to nt-1          684.3902   NOT resolved
+So the staggered first-derivative weights and the node-valued coefficient inside `div(b grad)` --
+the `[dv]` items of SURVEY Appendix A that the acoustic constants of
+devito_example_known_answer.py cannot see -- are held to 1.5e-5 by a number Devito produced.
+
+`judi_record()` runs the REFERENCE's equations (kernels.py:46-77 with a density field, and
+SLS_2nd_order kernels.py:80-141) on the same model with the same operator code, for the chain to
+the oracle in tests/test_devito_known_answer.py.
+
+    python tests/tools/devito_visco_known_answer.py
+"""
+import numpy as np
+
+DEVITO_NORM_REC_SLS = 684.385
+DEVITO_ATOL = 1e-2
+SHAPE, H, NBL, SO, F0 = (50, 50), 20.0, 40, 4, 0.010
+
+
+def model_fields():
+    """vp, qp, b of Devito's 'layers-viscoacoustic' preset on the physical grid."""
+    nl = 3
+    v = np.full(SHAPE, 1.5)
+    vi = np.linspace(1.5, 3.5, nl)
+    for i in range(1, nl):
+        v[..., i * int(SHAPE[-1] / nl):] = vi[i]
+    qp = 3.516 * ((v * 1000.) ** 2.2) * 1e-6
+    b = 1 / (0.31 * (v * 1000.) ** 0.25)
+    return v, qp, b
+
+
+def geometry():
+    """source / receiver coordinates in metres, as Devito's setup_geometry places them"""
+    dom = H * (SHAPE[0] - 1)
+    src = np.array([[0.5 * dom, H]], np.float32)
+    rec = np.stack([np.linspace(0.0, dom, SHAPE[0]), np.full(SHAPE[0], 2 * H)], axis=1).astype(np.float32)
+    return src, rec
+
+
+def _profile(width):
+    i = np.arange(width, dtype=np.float64)
+    pos = np.abs((width - i + 1) / float(width))
+    return 1.5 * np.log(1000.) / width * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / H
+
+
+def layer(width):
+    """sum of the 1-D absorbing profiles (0 in the interior), `width` cells on every side"""
+    n = SHAPE[0] + 2 * NBL
+    d = np.zeros((n, n))
+    prof = _profile(width)
+    for ax in range(2):
+        shp = [1, 1]
+        shp[ax] = width
+        sl = [slice(None)] * 2
+        sl[ax] = slice(0, width)
+        d[tuple(sl)] += prof.reshape(shp)
+        sl[ax] = slice(n - width, n)
+        d[tuple(sl)] += prof[::-1].reshape(shp)
+    return d
+
+
+class Staggered(object):
+    """4-point staggered first derivatives on the padded grid (zero outside)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.w = np.array([1 / 24, -9 / 8, 9 / 8, -1 / 24]) / H
+
+    def shift(self, a, ax, off):
+        p = np.pad(a, 2)
+        sl = [slice(2, 2 + self.n)] * 2
+        sl[ax] = slice(2 + off, 2 + off + self.n)
+        return p[tuple(sl)]
+
+    def dplus(self, a, ax):      # at x + h/2 from x-h, x, x+h, x+2h
+        return sum(self.w[k] * self.shift(a, ax, off) for k, off in enumerate((-1, 0, 1, 2)))
+
+    def dminus(self, a, ax):     # at x - h/2 from x-2h, x-h, x, x+h
+        return sum(self.w[k] * self.shift(a, ax, off) for k, off in enumerate((-2, -1, 0, 1)))
+
+    def div_b_grad(self, b, p, b_at_node=True):
+        out = 0
+        for ax in range(2):
+            bb = b if b_at_node else 0.5 * (b + self.shift(b, ax, 1))
+            out = out + self.dminus(bb * self.dplus(p, ax), ax)
+        return out
+
+
+def _wavelet(dt, tn):
+    nt = int(np.ceil((tn + dt) / dt))
+    t = np.linspace(0, dt * (nt - 1), nt)
+    rr = np.pi * F0 * (t - 1 / F0)
+    return (1 - 2 * rr ** 2) * np.exp(-rr ** 2), nt
+
+
+def _sls(qp):
+    t_s = (np.sqrt(1 + 1 / qp ** 2) - 1 / qp) / F0
+    t_ep = 1 / (F0 ** 2 * t_s)
+    return t_s, t_ep / t_s - 1
+
+
+def _sparse():
+    sx = (0.5 * H * (SHAPE[0] - 1)) / H + NBL
+    ix = int(np.floor(sx))
+    ax_ = sx - ix
+    return ((ix, 1 - ax_), (ix + 1, ax_)), 1 + NBL, 2 + NBL
+
+
+def devito_sls(b_at_node=True, r_dt="forward", double_mask=True, rec_level="current", tn=1000.0):
+    """Devito's visco-acoustic example -> (norm(rec), dt, nt)."""
+    from sympy import finite_diff_weights as fd_w
+    pad = lambda a: np.pad(a, NBL, mode="edge")
+    vp, qp, b = (pad(a) for a in model_fields())
+    c = fd_w(2, range(-SO, SO + 1), 0)[-1][-1]
+    cfl = float(np.sqrt(4.0 / (2 * sum(abs(float(x)) for x in c))))
+    dt = float(np.float32("%.3e" % (cfl * H / vp.max())))
+    q, nt = _wavelet(dt, tn)
+    n = SHAPE[0] + 2 * NBL
+    damp = 1.0 - layer(NBL)
+    t_s, tt = _sls(qp)
+    rho = 1 / b
+    bm = rho * vp ** 2
+    m = 1 / vp ** 2
+    S = Staggered(n)
+    cells, sz, rz = _sparse()
+    p, pp, r, rp = (np.zeros((n, n)) for _ in range(4))
+    rec = np.zeros((nt, SHAPE[0]))
+    for it in range(1, nt - 1):
+        L = S.div_b_grad(b, p, b_at_node)
+        if r_dt == "forward":
+            rn = damp * (r + dt * ((tt / t_s) * rho * L - r / t_s))
+        else:
+            rn = damp * (rp + 2 * dt * ((tt / t_s) * rho * L - r / t_s))
+        pn = damp * (2 * p - (damp if double_mask else 1) * pp + dt ** 2 * bm * ((1 + tt) * L - b * rn))
+        for ix, wgt in cells:
+            pn[ix, sz] += wgt * q[it] * dt ** 2 / m[ix, sz]
+        rec[it] = (p if rec_level == "current" else pn)[NBL:NBL + SHAPE[0], rz]
+        pp, p = p, pn
+        rp, r = r, rn
+    return float(np.sqrt((rec ** 2).sum())), dt, nt
+
+
+def judi_record(dt, tn=400.0, visco=False):
+    """The REFERENCE's equations on the same model / geometry, with the reference's layer
+    (nbl - 3 cells, models.py:74-94) -> (record (nt, nrec), wavelet (nt,)).
+
+    density field:   solve(m b u.dt2 + damp u.dt - div(b grad u), u.forward)          kernels.py:46-77
+    visco-acoustic:  r+ = mask solve(b r.dt - (tt/t_s) L + (b/t_s) r, r.forward)       kernels.py:120-123
+                     solve(m b p.dt2 - (1 + tt) L + b r+ + (1 - mask) p.dt, p.forward)  kernels.py:126-128
+    with u.dt = (u+ - u) / dt, mask = 1 - profile; source src dt^2 / (m b) into the new level."""
+    pad = lambda a: np.pad(a, NBL, mode="edge")
+    # parameters enter the reference as float32 arrays
+    v, qp, b = model_fields()
+    m = pad((1.0 / v ** 2).astype(np.float32).astype(np.float64))
+    b = pad(b.astype(np.float32).astype(np.float64))
+    qp = pad(qp.astype(np.float32).astype(np.float64))
+    q, nt = _wavelet(dt, tn)
+    q = q.astype(np.float32).astype(np.float64)
+    n = SHAPE[0] + 2 * NBL
+    dl = layer(NBL - 3)
+    S = Staggered(n)
+    cells, sz, rz = _sparse()
+    t_s, tt = _sls(qp)
+    u, up, r = (np.zeros((n, n)) for _ in range(3))
+    rec = np.zeros((nt, SHAPE[0]))
+    a_, b_ = m * b / dt ** 2, dl / dt
+    for it in range(1, nt - 1):
+        L = S.div_b_grad(b, u)
+        if visco:
+            r = (1 - dl) * (r + dt * ((tt / t_s) * L / b - r / t_s))
+            rhs = (1 + tt) * L - b * r
+        else:
+            rhs = L
+        un = (a_ * (2 * u - up) + b_ * u + rhs) / (a_ + b_)
+        for ix, wgt in cells:
+            un[ix, sz] += wgt * q[it] * dt ** 2 / (m[ix, sz] * b[ix, sz])
+        rec[it] = u[NBL:NBL + SHAPE[0], rz]
+        up, u = u, un
+    return rec, q
+
+
+if __name__ == "__main__":
+    for kw in (dict(), dict(b_at_node=False), dict(r_dt="centred"), dict(double_mask=False),
+               dict(rec_level="new")):
+        nr, dt, nt = devito_sls(**kw)
+        ok = abs(nr - DEVITO_NORM_REC_SLS) <= DEVITO_ATOL
+        print("%-28s dt = %.3f nt = %d: norm(rec) = %.4f  (Devito %.3f, %+.1e)  %s"
+              % (", ".join("%s=%s" % kv for kv in kw.items()) or "oracle conventions", dt, nt, nr,
+                 DEVITO_NORM_REC_SLS, nr / DEVITO_NORM_REC_SLS - 1, "accepted" if ok else "REJECTED"), flush=True)
