@@ -272,3 +272,82 @@ def test_ctypes_binding_matches_the_header_prototypes():
         pret, pargs = protos[name]
         assert ccls(res) == pret, (name, res, pret)
         assert [ccls(a) for a in args] == pargs, (name, [ccls(a) for a in args], pargs)
+
+
+def _header_structs():
+    """name -> [(field, class)] for every `typedef struct { ... } judi_xxx;` of the header; class is
+    'int', 'float', 'ptr', an embedded struct name, or ('int' | 'float', n) for a fixed array."""
+    txt = open(os.path.join(ROOT, "include", "judi_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef struct\s*\{(.*?)\}\s*(judi_[a-z_]+)\s*;", txt, flags=re.S):
+        fields = []
+        for decl in m.group(1).split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            base, names = decl.rsplit(" ", 1)[0], None
+            # "judi_param epsilon, delta, theta, phi" / "const float *data" / "int shape[3]"
+            mm = re.match(r"(const\s+)?([a-z_]+)\s+(.*)", decl)
+            typ, names = mm.group(2), [n.strip() for n in mm.group(3).split(",")]
+            for n in names:
+                if n.startswith("*"):
+                    fields.append((n.lstrip("*"), "ptr"))
+                elif "[" in n:
+                    fields.append((n.split("[")[0], (typ, int(n.split("[")[1].rstrip("]")))))
+                else:
+                    fields.append((n, typ))
+        out[m.group(2)] = fields
+    return out
+
+
+def test_struct_layouts_agree_between_header_ctypes_and_julia():
+    """A field out of order in a binding is silent memory corruption: compare field names, order and
+    type class of judi_param / judi_model_desc / judi_jopts / judi_shot across the header, the ctypes
+    Structures the GPU tests use and the Julia structs of julia/B200Backend.jl."""
+    from judi_jl_b200 import _lib
+    H = _header_structs()
+    assert set(H) >= {"judi_param", "judi_model_desc", "judi_jopts", "judi_shot"}
+    cmap = {"judi_param": _lib.JudiParam, "judi_model_desc": _lib.JudiModelDesc,
+            "judi_jopts": _lib.JudiJopts, "judi_shot": _lib.JudiShot}
+
+    def ccls(t):
+        if t is ctypes.c_int:
+            return "int"
+        if t is ctypes.c_float:
+            return "float"
+        if t is ctypes.c_void_p or hasattr(t, "contents"):
+            return "ptr"
+        if issubclass(t, ctypes.Array):
+            return (ccls(t._type_), t._length_)
+        if issubclass(t, ctypes.Structure):
+            return {v: k for k, v in cmap.items()}[t]
+        raise AssertionError(t)
+    for name, S in cmap.items():
+        assert [(f, ccls(t)) for f, t in S._fields_] == H[name], name
+
+    # Julia: `struct JudiX  # judi_x` ... `end`, fields `name::Type` separated by ';' or newlines
+    src = open(os.path.join(ROOT, "julia", "B200Backend.jl")).read()
+    jl = {}
+    for m in re.finditer(r"struct\s+(Judi[A-Za-z]+)\s*#\s*(judi_[a-z_]+)\s*\n(.*?)\nend", src, flags=re.S):
+        body = re.sub(r"#[^\n]*", "", m.group(3))
+        fields = []
+        for f in re.split(r"[;\n]", body):
+            f = f.strip()
+            if not f:
+                continue
+            n, t = f.split("::")
+            if t.startswith("Ptr{"):
+                c = "ptr"
+            elif t.startswith("NTuple{"):
+                k, et = re.match(r"NTuple\{(\d+),\s*(\w+)\}", t).groups()
+                c = ({"Cint": "int", "Cfloat": "float"}[et], int(k))
+            elif t in ("Cint", "Cfloat"):
+                c = {"Cint": "int", "Cfloat": "float"}[t]
+            else:
+                c = {"JudiParam": "judi_param"}[t]
+            fields.append((n.strip(), c))
+        jl[m.group(2)] = fields
+    assert set(jl) >= {"judi_param", "judi_model_desc", "judi_jopts"}, sorted(jl)
+    for name, fields in jl.items():
+        assert fields == H[name], (name, fields, H[name])
