@@ -665,3 +665,35 @@ def test_full_size_adjoint_and_linearity(kind):
     assert dot_ok(c, e, dt * np.linalg.norm(dl), np.linalg.norm(y))
     gc, _, _ = J.J_adjoint(gm, src, q, rec, y, is_residual=True, checkpointing=True)
     assert np.array_equal(gc, g)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("so", [4, 8])
+def test_tti_kernels_without_anisotropy_equal_the_density_field_kernels(ndim, so):
+    """epsilon = delta = 0: R^T (b I) R = b I for any tilt / azimuth, so the TTI kernels must
+    reproduce the density-field (staggered div(b grad)) kernels -- the operator that
+    tests/test_devito_known_answer.py holds against a Devito-produced constant (oracle twin of this
+    test: test_oracle_properties.py::test_tti_without_anisotropy_is_the_staggered_acoustic_operator)."""
+    import judi_jl_b200 as J
+    a = model_args("tti", ndim, so=so, with_dm=False)
+    v = 1 / np.sqrt(a["m"])
+    zero = np.zeros(a["shape"], np.float32)
+    tti = dict(a, epsilon=zero, delta=zero, dt=np.float32(0.5))
+    tti["theta"] = (0.7 * np.sin(v * 3.0)).astype(np.float32)
+    if ndim == 3:
+        tti["phi"] = (1.1 * np.cos(v * 2.0)).astype(np.float32)
+    iso = {k: val for k, val in a.items() if k not in ("epsilon", "delta", "theta", "phi")}
+    iso.update(b=np.ones(a["shape"], np.float32), dt=np.float32(0.5))
+    Mt, Mi = J.Model(**tti), J.Model(**iso)
+    assert float(Mt.critical_dt) == float(Mi.critical_dt) == 0.5
+    src, rec = geometry(a)
+    nt = 160 if ndim == 2 else 80
+    q = O.ricker_wavelet((nt - 1) * 0.5, 0.5, 0.03)[:nt]
+    dt_, _ = J.forward_rec(Mt, src, q, rec)
+    di_, _ = J.forward_rec(Mi, src, q, rec)
+    do_, _ = O.forward_rec(O.Model(precision="f64", **iso), src, q, rec)
+    e_ti, e_to = rel_l2(dt_, di_), rel_l2(dt_, do_)
+    print("TTI(0) vs density-field kernels %dD so=%d: %.2e; vs the fp64 oracle's density-field path %.2e"
+          % (ndim, so, e_ti, e_to))
+    assert np.linalg.norm(di_) > 0
+    assert e_ti < 2e-5 and e_to < 1e-4

@@ -216,3 +216,34 @@ def test_adjoint_scheme_is_the_forward_scheme_in_reversed_time(kind):
     av, _ = O.forward_rec(vm, rec, y, src, fw=False)
     bv, _ = O.forward_rec(vm, rec, y[::-1].copy(), src, fw=True)
     assert not np.array_equal(av, bv[::-1])
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+@pytest.mark.parametrize("so", [4, 8])
+def test_tti_without_anisotropy_is_the_staggered_acoustic_operator(ndim, so):
+    """With epsilon = delta = 0 the tensor of sa_tti (FD_utils.py:84-105) is A = b I, B = C = 0, so
+    R^T A R = b I for ANY tilt / azimuth field and the first TTI field obeys
+    m u.dt2 + damp u.dt = div(b grad(u, shift=.5), shift=-.5): the density-field operator, which
+    tests/test_devito_known_answer.py holds against a Devito-produced constant.  End-to-end check of
+    the rotation as implemented (orthogonality at every node, heterogeneous angles), of the wiring
+    (source into and receivers from the first field only) and of the staggered stencils inside the
+    TTI path."""
+    a = model_args("tti", ndim, so=so, with_dm=False)
+    v = 1 / np.sqrt(a["m"])
+    zero = np.zeros(a["shape"], np.float32)
+    tti = dict(a, epsilon=zero, delta=zero, dt=np.float32(0.5))
+    tti["theta"] = (0.7 * np.sin(v * 3.0)).astype(np.float32)
+    if ndim == 3:
+        tti["phi"] = (1.1 * np.cos(v * 2.0)).astype(np.float32)
+    iso = {k: val for k, val in a.items() if k not in ("epsilon", "delta", "theta", "phi")}
+    iso.update(b=np.ones(a["shape"], np.float32), dt=np.float32(0.5))
+    Mt, Mi = O.Model(precision="f64", **tti), O.Model(precision="f64", **iso)
+    assert Mt.is_tti and Mi.irho_field is not None
+    assert float(Mt.critical_dt) == float(Mi.critical_dt) == 0.5
+    src, rec = geometry(a)
+    nt = 120 if ndim == 2 else 60
+    q = O.ricker_wavelet((nt - 1) * 0.5, 0.5, 0.03)[:nt]
+    dt_, _ = O.forward_rec(Mt, src, q, rec)
+    di_, _ = O.forward_rec(Mi, src, q, rec)
+    assert np.linalg.norm(di_) > 0
+    assert rel_l2(dt_, di_) < 1e-10
