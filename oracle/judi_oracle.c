@@ -1,13 +1,15 @@
 /*
  * judi_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
  *
- * PARITY UNPINNED: the reference (slimgroup/JUDI.jl v4.1.7) gets this arithmetic from
- * Devito-JIT-generated C, and Devito is neither vendored under /root/reference nor installable
- * in the build container.  The reference ships no golden wavefield / shot-record / gradient
- * vectors for this path.  This file therefore restates the *published*
- * algorithm -- the symbolic equations in src/pysource plus Devito's documented lowering of them --
- * and its time loops are pinned only by the reference's own property tests (adjoint dot tests,
- * Taylor rates, linearity, lsrtm(dm=0,nlind)==fwi) which tests/ re-runs against it.
+ * PARITY PINNED IN PART, UNPINNED FOR THE REST (DESIGN.md section 2 has the full account).  The
+ * reference (slimgroup/JUDI.jl v4.1.7) gets this arithmetic from Devito-JIT-generated C, and
+ * Devito is neither vendored under /root/reference nor installable in the build container.  The
+ * reference ships no golden wavefield / shot-record / gradient vectors for this path (SURVEY.md
+ * section 8c).  This file therefore restates the *published* algorithm -- the symbolic equations
+ * in src/pysource plus Devito's documented lowering of them.  UNPINNED: every gradient / imaging
+ * condition number, the anisotropic part of the TTI tensor end to end, the sidedness of u.dt in
+ * the damping term, the last time-loop index; those rest on the reference's own property tests
+ * (adjoint dot tests, Taylor rates, linearity, lsrtm(dm=0,nlind)==fwi) which tests/ re-runs.
  * PINNED to the reference's own Python executed in the build container (src/pysource with a devito
  * import stub; tests/golden/make_reference_golden.py, tests/test_reference_golden.py): the
  * point-wise algebra of this file -- tti_flux_point (FD_utils.sa_tti), ic_point / linsrc_point
