@@ -18,7 +18,7 @@
  * 459.1678, 369.955 with a free surface; recalled from Devito's public repository, not under
  * /root/reference): tests/test_devito_known_answer.py -- a numpy restatement with this file's
  * conventions reproduces them to 4e-4 / 7e-4 and equals this file's forward shot record to 3.5e-8
- * on the same problem; a third constant (684.385, Devito's visco-acoustic example) does the same
+ * on the same problem; two more constants (684.385 and 677.673, the SLS and Kelvin-Voigt kernels of Devito's visco-acoustic example) do the same
  * for div(b grad(p, shift=.5), shift=-.5) with b at the node (7e-6 to Devito, 1.7e-9 to this file).
  * That covers the acoustic Laplacian, the staggered stencils, time loop, injection and
  * interpolation; the TTI rotation end to end and the gradients stay unpinned.
