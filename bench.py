@@ -436,7 +436,7 @@ def run_b200(args):
                                                      snapshot_region=args.snapshot_region)
                 return J.objectives.fwi_objective(mh, shots, t_sub=args.t_sub,
                                                   snapshot_region=args.snapshot_region)
-            for _ in range(min(args.warmup, 2)):
+            for _ in range(args.warmup):      # the same W untimed steps as the device-resident region
                 step_host()
             barrier()
             clocks_e2e = ClockSampler(local)
