@@ -24,6 +24,8 @@ constant discriminates (Devito's acceptance window is 684.375 ... 684.395):
     centred time difference for the memory variable           685.5075   rejected
     single mask (no `damp p-`)                                687.5957   rejected
     receivers read the new level / loop runs to nt-1          684.3902   NOT resolved
+    loop starts at 0 instead of 1 (fp32 sum: 684.3907 / KV 677.6796 against 684.3854 / 677.6732
+    for the loop from 1 and Devito's 684.385 / 677.673)                  third decimal of both misses
 So the staggered first-derivative weights and the node-valued coefficient inside `div(b grad)` --
 the `[dv]` items of SURVEY Appendix A that the acoustic constants of
 devito_example_known_answer.py cannot see -- are held to 1.5e-5 by a number Devito produced.
