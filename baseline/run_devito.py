@@ -7,6 +7,7 @@ box that has `pip install devito`:
     export DEVITO_LANGUAGE=openmp OMP_NUM_THREADS=$(nproc)
     python baseline/run_devito.py --pysource /path/to/JUDI.jl/src/pysource parity  --out devito_golden.npz
     python baseline/run_devito.py --pysource ... bench --tn 200          # Gpt/s of the reference CPU path
+    python baseline/run_devito.py --pysource ... devito-examples         # Devito's own example constants
 
 `parity` writes, for every physics x dimension of the test matrix, the shot record, the Born data
 and the gradient of src/pysource/interface.py on the SAME arrays the GPU tests use; if the oracle is
@@ -100,6 +101,27 @@ def bench(ns):
              2 * (nt - 2) * npts / wall / 1e9, os.environ.get("OMP_NUM_THREADS", "?")))
 
 
+def devito_examples(ns):
+    """Re-produce, with Devito itself, the four constants tests/test_devito_known_answer.py chains the
+    oracle and the CUDA library to.  They are quoted from Devito's own assertions
+    (examples/seismic/acoustic/acoustic_example.py::test_isoacoustic,
+    examples/seismic/viscoacoustic/viscoacoustic_example.py::test_viscoacoustic) from memory -- this
+    command is how a box that has Devito (with its `examples` package importable) confirms them."""
+    from devito import norm
+    from examples.seismic.acoustic.acoustic_example import run as run_acoustic
+    from examples.seismic.viscoacoustic.viscoacoustic_example import run as run_visco
+    want = {"acoustic": 459.1678, "acoustic, free surface": 369.955,
+            "visco-acoustic sls": 684.385, "visco-acoustic kv": 677.673}
+    got = {}
+    got["acoustic"] = float(norm(run_acoustic(fs=False, dtype=np.float32)[3][0]))
+    got["acoustic, free surface"] = float(norm(run_acoustic(fs=True, dtype=np.float32)[3][0]))
+    got["visco-acoustic sls"] = float(norm(run_visco(kernel="sls", time_order=2, dtype=np.float32)[3][0]))
+    got["visco-acoustic kv"] = float(norm(run_visco(kernel="kv", time_order=2, dtype=np.float32)[3][0]))
+    for k in want:
+        print("%-24s Devito now %.4f, quoted in this repository %.4f (%+.1e)"
+              % (k, got[k], want[k], got[k] / want[k] - 1))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--pysource", required=True, help="path of the reference's src/pysource")
@@ -109,10 +131,11 @@ if __name__ == "__main__":
     p2 = sub.add_parser("bench")
     p2.add_argument("--shape", type=int, nargs=3, default=[401, 401, 201])
     p2.add_argument("--tn", type=float, default=200.)
+    sub.add_parser("devito-examples")
     ns = ap.parse_args()
     sys.path.insert(0, ns.pysource)
     try:
         import devito  # noqa: F401
     except ImportError:
         sys.exit("devito is not importable here: run this script on a box with `pip install devito`")
-    {"parity": parity, "bench": bench}[ns.cmd](ns)
+    {"parity": parity, "bench": bench, "devito-examples": devito_examples}[ns.cmd](ns)
